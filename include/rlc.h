@@ -1,0 +1,204 @@
+/* rlc.h -- C-ABI of librlc.so: the B200 (sm_100a) sampled-action critic path of RLControl.
+ *
+ * Drop-in boundary.  Every entry point takes plain pointers and sizes, returns an
+ * int status (0 = ok, negative = error, see rlc_status_string), never throws, never owns caller
+ * memory and is stream-ordered on the cudaStream_t passed as `void* stream` (NULL = default
+ * stream).  All data pointers are DEVICE pointers unless the name ends in `_host`.
+ * The only state is the opaque rlc_handle (workspace + pre-packed tensor-core operands).
+ * A handle is not thread-safe (same as one reference network object: single Python thread,
+ * agents/base_agent.py:40-70).
+ *
+ * Each function cites the reference interface (file:line under the RLControl checkout) that a
+ * maintainer would re-bind to it; INTEGRATION.md shows the ctypes stub.
+ *
+ * Canonical parameter vector `theta` (fp32, contiguous, caller-owned):
+ *     [ W1 (in1 x H1) | b1 (H1) | W2 (in2 x H2) | b2 (H2) | w3 (H2) | b3 (1) ]   all [in,out]-major
+ *   T-in  (SoftQNetwork, forwardkl_network.py:250-268):  in1 = S+A, in2 = H1
+ *   T-mid (critic_network.py:77-99 family):              in1 = S,   in2 = H1+A (rows H1.. = action)
+ * Gradients and Adam moments use the same layout, so the data-parallel all-reduce is one
+ * contiguous buffer.
+ */
+#ifndef RLC_H_
+#define RLC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLC_VERSION 100
+
+/* status codes */
+#define RLC_OK 0
+#define RLC_ERR_INVALID (-1)  /* bad shape / null pointer / unsupported combination */
+#define RLC_ERR_ARCH (-2)     /* device is not sm_100 (tensor-core path) */
+#define RLC_ERR_ALLOC (-3)    /* workspace allocation failed */
+#define RLC_ERR_CUDA (-4)     /* CUDA runtime error (rlc_last_cuda_error has the text) */
+#define RLC_ERR_UNSUPPORTED (-5)
+
+/* critic topology */
+#define RLC_TIN 0  /* concat [s;a] at the input: SoftQNetwork, sql qf_network */
+#define RLC_TMID 1 /* concat [h1;a] at layer 2: critic_network.py family      */
+
+/* source layout of the six tensors handed to rlc_pack_theta */
+#define RLC_LAYOUT_OUT_IN 0 /* torch nn.Linear weight [out,in] (forwardkl_network.py:254-256) */
+#define RLC_LAYOUT_IN_OUT 1 /* tf.contrib.layers.fully_connected kernel [in,out]              */
+
+/* action tensor layout for B x N evaluation */
+#define RLC_ACT_SHARED 0    /* a[N,A] broadcast over states (quadrature grid, forwardkl_network.py:104-105) */
+#define RLC_ACT_PER_STATE 1 /* a[B,N,A] (ActorExpert.py:166, qt_opt_network.py:160)                         */
+
+/* arithmetic of the critic evaluation */
+#define RLC_PREC_FP32 0 /* CUDA-core fp32 FMA, fp32 accumulate (bit-comparable to the CPU path ~1e-6) */
+#define RLC_PREC_FP16 1 /* tcgen05.mma kind::f16, fp16 operands, fp32 accumulate in TMEM (default for large B*N) */
+#define RLC_PREC_BF16 2 /* tcgen05.mma kind::f16, bf16 operands, fp32 accumulate in TMEM */
+#define RLC_PREC_AUTO 3 /* FP16 tensor path when B*N >= 16384 rows and the shape is supported, else FP32 */
+
+/* Adam flavour of rlc_adam_step */
+#define RLC_ADAM_TORCH 0 /* torch.optim.Adam: p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps) */
+#define RLC_ADAM_TF 1    /* tf.train.AdamOptimizer: p -= lr*sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v)+eps) */
+
+typedef struct rlc_handle rlc_handle;
+
+/* One critic network = dims + a pointer to its canonical parameter vector.
+ * smin/smax: device pointers to S floats each, or NULL.  Only honoured for RLC_TMID and the TF
+ * T-in critic (tf.clip_by_value(inputs, state_min, state_max), critic_network.py:71,
+ * sql_network.py:278-279); the torch SoftQNetwork never clips. */
+typedef struct rlc_critic {
+  int32_t topology;
+  int32_t S, A, H1, H2;
+  const float* theta;
+  const float* smin;
+  const float* smax;
+} rlc_critic;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+int rlc_version(void);
+const char* rlc_status_string(int status);
+const char* rlc_last_cuda_error(void);
+int rlc_create(rlc_handle** out, int device);
+int rlc_destroy(rlc_handle* h);
+/* number of kernels this handle has launched (bench.py's gpu_launches) */
+int64_t rlc_launch_count(const rlc_handle* h);
+
+/* ---- parameters ------------------------------------------------------------------------ */
+int64_t rlc_theta_numel(int topology, int S, int A, int H1, int H2);
+/* off[0..5] = element offsets of W1,b1,W2,b2,w3,b3 inside theta */
+int rlc_theta_offsets(int topology, int S, int A, int H1, int H2, int64_t off[6]);
+/* Replaces `linearN.weight/bias` (forwardkl_network.py:254-259) or the TF variables
+ * `fully_connected_N/weights|biases` (critic_network.py:79-97): device tensors in `layout` ->
+ * canonical theta. */
+int rlc_pack_theta(int topology, int S, int A, int H1, int H2, int layout, const float* W1,
+                   const float* b1, const float* W2, const float* b2, const float* W3,
+                   const float* b3, float* theta_out, void* stream);
+int rlc_unpack_theta(int topology, int S, int A, int H1, int H2, int layout, const float* theta,
+                     float* W1, float* b1, float* W2, float* b2, float* W3, float* b3,
+                     void* stream);
+/* Tell the handle that c->theta changed (drops the cached fp16/bf16 operand pack). The step
+ * functions below call it themselves. */
+int rlc_invalidate_pack(rlc_handle* h, const float* theta);
+
+/* ---- critic evaluation (rows a1, a2, a6, a7) --------------------------------------------
+ * Replaces q_net(stacked_s, stacked_a) (forwardkl_network.py:160-164, reversekl_network.py:176-181)
+ * and predict_q / predict_q_target(inputs, action, phase) (ae_network.py:377-399,
+ * qt_opt_network.py:107-129, critic_network.py:101-123) on the state-major stack
+ * row = b*N + n.  s[B,S]; a per act_mode; q_out[B,N] fp32.  The broadcast/concat is fused:
+ * the stacked tensors are never materialised. */
+int rlc_critic_eval(rlc_handle* h, const rlc_critic* c, const float* s, int B, const float* a,
+                    int N, int act_mode, int precision, float* q_out, void* stream);
+
+/* B x N evaluation *and* dQ/da of a T-mid critic without materialising the stack: the AE+
+ * ascent (ae_plus_network.py:310-343, ActorExpert_Plus.py:130) evaluates action_grads on B*N rows
+ * whose states repeat N times.  dqda_out[B,N,A]; q_out[B,N] or NULL. */
+int rlc_tmid_eval_grad(rlc_handle* h, const rlc_critic* c, const float* s, int B, const float* a,
+                       int N, int act_mode, float* q_out, float* dqda_out, void* stream);
+/* Diagnostic: synchronises `stream` and returns the code raised by a bounded mbarrier wait inside
+ * the tcgen05 kernel (0 = none, <0 = CUDA error). The flag is cleared on read. */
+int rlc_umma_last_error(rlc_handle* h, void* stream);
+
+/* ---- per-state reductions (rows a3, a4, a8, a9, a10) ------------------------------------ */
+/* row.argsort()[::-1][:k] (ActorExpert.py:177, qt_opt_network.py:166): descending, ties -> larger
+ * index first.  idx_out[B,k] int64; q_sel_out[B,k] or NULL;
+ * optional elite gather (ActorExpert.py:178): actions[B,N,A] (or [N,A] if act_mode shared) ->
+ * elites_out[B,k,A], pass NULL to skip. 1 <= k <= 64, k <= N. */
+int rlc_reduce_topk(rlc_handle* h, const float* q, int B, int N, int k, int64_t* idx_out,
+                    float* q_sel_out, const float* actions, int A, int act_mode,
+                    float* elites_out, void* stream);
+/* np.argmax / np.max / np.mean over axis 1 (optimal_q_network.py:156-159, ActorCritic.py:139,158).
+ * any output may be NULL. argmax = first maximal index. */
+int rlc_reduce_stats(rlc_handle* h, const float* q, int B, int N, int64_t* argmax_out,
+                     float* max_out, float* mean_out, void* stream);
+/* SQL soft value (sql_network.py:76-84): logsumexp_n q - log N + A log 2. */
+int rlc_reduce_lse(rlc_handle* h, const float* q, int B, int N, int action_dim, float* v_out,
+                   void* stream);
+/* ForwardKL grid reduction (forwardkl_network.py:165-194). w[N], logp[B,N].
+ * loss_b_out[B] = -sum_n w_n p_n logp; boltz_out[B,N] (p, may be NULL);
+ * dlogp_out[B,N] = d(mean_b loss_b)/dlogp = -w_n p_n / B_total (may be NULL).
+ * B_total: the global batch the mean is taken over (== B on one GPU, B*world when states are
+ * sharded). */
+int rlc_reduce_fkl(rlc_handle* h, const float* q, const float* w, const float* logp, int B,
+                   int N, float entropy_scale, int B_total, float* loss_b_out, float* boltz_out,
+                   float* dlogp_out, void* stream);
+/* ReverseKL grid reduction (reversekl_network.py:181-190; hard: 197-203). v[B]. */
+int rlc_reduce_rkl(rlc_handle* h, const float* q, const float* v, const float* w,
+                   const float* logp, int B, int N, float entropy_scale, int hard, int B_total,
+                   float* loss_b_out, float* dlogp_out, void* stream);
+
+/* ---- CEM (rows a11, a12) ----------------------------------------------------------------
+ * iterate_cem_multidim (qt_opt_network.py:132-175) + BoundedVarGaussianMixture refit
+ * (utils/boundedvar_gaussian_mixture.py:10-75), all iterations in one launch, random draws
+ * supplied: u0[B,N,A] in [0,1) (iter 0: a = amin + u0*(amax-amin)); noise[(iters-1),B,N,A] ~N(0,1);
+ * comp_u[(iters-1),B,N] in [0,1) picks the mixture component.  T-mid critics only
+ * (QT-Opt's critic).  amin/amax: A floats (device).  Outputs: weights[B,M], means[B,M,A],
+ * vars[B,M,A], best_action[B,A] (= means[argmax weights], qt_opt_network.py:180),
+ * elite_idx[iters,B,top_m] int64 (may be NULL). 1 <= num_modal <= 2, top_m <= 32, A <= 8. */
+int rlc_cem(rlc_handle* h, const rlc_critic* c, const float* s, int B, int N, int iters,
+            int top_m, int num_modal, const float* u0, const float* noise, const float* comp_u,
+            const float* amin, const float* amax, float* weights_out, float* means_out,
+            float* vars_out, float* best_action_out, int64_t* elite_idx_out, void* stream);
+/* The refit alone: X[B,k,A] elites -> mixture; resp0[B,k,M] initial responsibilities or NULL
+ * (NULL = deterministic farthest-point split). */
+int rlc_gmm_refit(rlc_handle* h, const float* X, int B, int k, int A, int num_modal,
+                  const float* resp0, float tol, int max_iter, float* weights_out,
+                  float* means_out, float* vars_out, int32_t* n_iter_out, void* stream);
+
+/* ---- backward (rows a14, a15, a16) -------------------------------------------------------- */
+/* tf.gradients(q, action) on R stacked rows (ae_network.py:117,352-358; critic_network.py:58,
+ * 169-183; sql_network.py:101-107).  s[R,S], a[R,A] -> dqda_out[R,A]; q_out[R] or NULL. */
+int rlc_critic_grad_action(rlc_handle* h, const rlc_critic* c, const float* s, const float* a,
+                           int R, float* dqda_out, float* q_out, void* stream);
+/* Gradient of mean((y - Q(s,a))^2) over B rows wrt theta (critic_network.py:54-55,
+ * forwardkl_network.py:133-140,199-201).  grad_out[numel theta]; loss_out[1]; q_out[B] or NULL.
+ * B_total as in rlc_reduce_fkl (mean over the global batch; sum-allreduce the result). */
+int rlc_critic_grads(rlc_handle* h, const rlc_critic* c, const float* s, const float* a,
+                     const float* y, int B, int B_total, float* grad_out, float* loss_out,
+                     float* q_out, void* stream);
+/* One Adam step on a flat vector; step is the 1-based count.  When target != NULL also applies
+ * the soft update target += tau (theta_new - target) (critic_network.py:29,197-198). */
+int rlc_adam_step(rlc_handle* h, float* theta, const float* grad, float* m, float* v,
+                  int64_t n, int step, float lr, float beta1, float beta2, float eps,
+                  int variant, float* target, float tau, void* stream);
+int rlc_soft_update(rlc_handle* h, float* target, const float* online, int64_t n, float tau,
+                    void* stream);
+
+/* ---- replay minibatch gather (row a17) ---------------------------------------------------
+ * map(np.array, zip(*batch)) of ReplayBuffer.sample_batch (utils/replaybuffer.py:32-37) over a
+ * device-resident struct-of-arrays ring: state[cap,S], action[cap,A], reward[cap],
+ * next_state[cap,S], gamma[cap].  idx[B] = physical slots (int64).  Outputs are dense [B,...]. */
+int rlc_replay_gather(rlc_handle* h, const float* state, const float* action,
+                      const float* reward, const float* next_state, const float* gamma,
+                      int64_t cap, int S, int A, const int64_t* idx, int B, float* s_out,
+                      float* a_out, float* r_out, float* s2_out, float* g_out, void* stream);
+/* Scatter n new transitions (host staging already copied to device, rows [n,...]) into ring
+ * slots slot[n] (ReplayBuffer.add, utils/replaybuffer.py:25-27). */
+int rlc_replay_scatter(rlc_handle* h, float* state, float* action, float* reward,
+                       float* next_state, float* gamma, int64_t cap, int S, int A,
+                       const int64_t* slot, int n, const float* s_in, const float* a_in,
+                       const float* r_in, const float* s2_in, const float* g_in, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLC_H_ */

@@ -1,0 +1,616 @@
+"""CPU oracle for the sampled-action critic path of RLControl (numpy restatement).
+
+TEST INFRASTRUCTURE ONLY.  Nothing in ``rlcontrol_b200/`` may import this module; it is
+used by ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference``
+legs of ``bench.py`` as the *checker* (or the timed CPU arm), never as the product path.
+
+Every function cites the reference file:line (relative to the RLControl checkout) whose
+arithmetic it restates.  Parity status:
+
+* T-in critic (``SoftQNetwork``), FKL / RKL reductions, critic regression step (torch Adam):
+  PINNED against the reference's own torch classes run in the build container
+  (``oracle/make_golden.py`` -> ``tests/golden/*.npz``).
+* T-mid critic topology, concat order and weight layout: PINNED against the five trained
+  ``Bimodal1DEnv_trueQ_ckpt`` checkpoints + the env ``reward_func`` closed forms.
+* Bounded diagonal GMM refit: EM pinned against scikit-learn's ``GaussianMixture`` run through a
+  ``BoundedVarGaussianMixture``-equivalent subclass given the same initial responsibilities
+  (k-means init consumes RNG and is version dependent: "parity unpinned" for the init only).
+* TF Adam / TF graphs: TensorFlow 1.15 cannot be installed -> restated from the TF documentation
+  of ``tf.train.AdamOptimizer``; "parity unpinned" for the TF optimizer step.
+"""
+from __future__ import annotations
+
+import math
+import numpy as np
+
+F32 = np.float32
+
+# --------------------------------------------------------------------------------------
+# Critic forward passes
+# --------------------------------------------------------------------------------------
+
+
+def stack_state_major(s: np.ndarray, n: int) -> np.ndarray:
+    """``state.unsqueeze(1).repeat(1,N,1).reshape(-1,S)`` (forwardkl_network.py:161-162) ==
+    ``np.repeat(state_batch, N, axis=0)`` (ActorExpert.py:168): row = b*N + n."""
+    return np.repeat(np.asarray(s), n, axis=0)
+
+
+def stack_actions(a: np.ndarray, b: int) -> np.ndarray:
+    """Shared grid ``[N,A]`` -> ``intgrl_actions.repeat(B,1,1).reshape(-1,A)``
+    (forwardkl_network.py:104-105, reversekl_network.py:178-179); per-state ``[B,N,A]`` ->
+    ``reshape(B*N, A)`` (ActorExpert.py:166)."""
+    a = np.asarray(a)
+    if a.ndim == 2:
+        return np.tile(a, (b, 1))
+    return a.reshape(-1, a.shape[-1])
+
+
+def tin_forward(s, a, W1, b1, W2, b2, W3, b3, dtype=F32):
+    """T-in critic, ``SoftQNetwork.forward`` (forwardkl_network.py:263-268,
+    reversekl_network.py:272-282): ``x=cat([s,a],1)``; Linear+ReLU; Linear+ReLU; Linear.
+    Weights are torch ``nn.Linear`` layout ``[out, in]`` (y = x W^T + b).
+    ``s``: [R,S], ``a``: [R,A] (already stacked).  Returns q [R] in ``dtype``."""
+    x = np.concatenate([np.asarray(s, dtype), np.asarray(a, dtype)], axis=1)
+    h1 = np.maximum(x @ np.asarray(W1, dtype).T + np.asarray(b1, dtype), 0)
+    h2 = np.maximum(h1 @ np.asarray(W2, dtype).T + np.asarray(b2, dtype), 0)
+    q = h2 @ np.asarray(W3, dtype).reshape(-1) + np.asarray(b3, dtype).reshape(())
+    return q.astype(dtype)
+
+
+def tin_eval(s, a, params, dtype=F32):
+    """B x N sampled-action evaluation exactly as the reference executes it: materialise the
+    state-major stack (forwardkl_network.py:160-164) and run the critic on B*N rows.
+    ``s`` [B,S]; ``a`` [N,A] (shared grid) or [B,N,A].  Returns q [B,N]."""
+    s = np.asarray(s)
+    a = np.asarray(a)
+    B = s.shape[0]
+    N = a.shape[0] if a.ndim == 2 else a.shape[1]
+    q = tin_forward(stack_state_major(s, N), stack_actions(a, B), *params, dtype=dtype)
+    return q.reshape(B, N)
+
+
+def clip_state(s, smin, smax, dtype=F32):
+    """Input "normalisation" of the TF graphs: ``RunningMeanStd`` mean/var are baked in as the
+    constants 0/1 (utils/running_mean_std.py:4-7,31-32; base_network_manager.py:37) so the only
+    live op is ``tf.clip_by_value(x, state_min, state_max)`` (critic_network.py:71,
+    qt_opt_network.py:79)."""
+    if smin is None:
+        return np.asarray(s, dtype)
+    return np.clip(np.asarray(s, dtype), np.asarray(smin, dtype), np.asarray(smax, dtype))
+
+
+def tmid_forward(s, a, W1, b1, W2, b2, W3, b3, smin=None, smax=None, dtype=F32):
+    """T-mid critic ``network()`` (critic_network.py:77-99, qt_opt_network.py:83-105,
+    ae_network.py:213-227): ``h1=ReLU(clip(s) W1 + b1)``; ``h2=ReLU(concat([h1,a]) W2 + b2)``;
+    ``q=h2 W3 + b3``.  TF ``fully_connected`` kernels are ``[in, out]`` (y = x W + b);
+    rows 0..H1-1 of W2 multiply h1, rows H1.. multiply the action (verified on the trueQ
+    checkpoint).  ``s`` [R,S], ``a`` [R,A] stacked.  Returns q [R]."""
+    x = clip_state(s, smin, smax, dtype)
+    h1 = np.maximum(x @ np.asarray(W1, dtype) + np.asarray(b1, dtype), 0)
+    z = np.concatenate([h1, np.asarray(a, dtype)], axis=1)
+    h2 = np.maximum(z @ np.asarray(W2, dtype) + np.asarray(b2, dtype), 0)
+    q = h2 @ np.asarray(W3, dtype).reshape(-1) + np.asarray(b3, dtype).reshape(())
+    return q.astype(dtype)
+
+
+def tmid_eval(s, a, params, smin=None, smax=None, dtype=F32):
+    """``predict_q(stacked_states, stacked_actions, phase)`` on the un-hoisted stack, as TF runs
+    it (ae_network.py:377-387, qt_opt_network.py:107-117).  Returns q [B,N]."""
+    s = np.asarray(s)
+    a = np.asarray(a)
+    B = s.shape[0]
+    N = a.shape[0] if a.ndim == 2 else a.shape[1]
+    q = tmid_forward(stack_state_major(s, N), stack_actions(a, B), *params,
+                     smin=smin, smax=smax, dtype=dtype)
+    return q.reshape(B, N)
+
+
+def tmid_eval_hoisted(s, a, params, smin=None, smax=None, dtype=F32):
+    """Algebraically identical T-mid evaluation with the state-only terms hoisted
+    (SURVEY 0.4): p_b = h1_b W2[:H1] + b2; q = ReLU(p_b + a W2[H1:]) . w3 + b3."""
+    W1, b1, W2, b2, W3, b3 = [np.asarray(p, dtype) for p in params]
+    H1 = W1.shape[1]
+    x = clip_state(s, smin, smax, dtype)
+    h1 = np.maximum(x @ W1 + b1, 0)
+    p = h1 @ W2[:H1] + b2                                   # [B,H2]
+    a = np.asarray(a, dtype)
+    if a.ndim == 2:
+        pa = (a @ W2[H1:])[None, :, :]                      # [1,N,H2]
+    else:
+        pa = a @ W2[H1:]                                    # [B,N,H2]
+    h2 = np.maximum(p[:, None, :] + pa, 0)
+    return (h2 @ W3.reshape(-1) + b3.reshape(())).astype(dtype)
+
+
+# --------------------------------------------------------------------------------------
+# Per-state reductions
+# --------------------------------------------------------------------------------------
+
+
+def topk_desc(q, k):
+    """Per-state elites: ``row.argsort()[::-1][:k]`` (ActorExpert.py:177, qt_opt_network.py:166).
+    numpy's default introsort does not define the order of ties, so the oracle fixes it as the
+    reverse of a *stable* ascending sort (ties: larger index first), which is what numpy
+    produces for the insertion-sort sized rows and what the CUDA kernel implements."""
+    q = np.asarray(q)
+    idx = np.argsort(q, axis=1, kind="stable")[:, ::-1][:, :k]
+    return np.ascontiguousarray(idx.astype(np.int64))
+
+
+def gather_elites(actions, idx):
+    """``[actions[idxs] for actions, idxs in zip(action_batch, selected_idxs)]``
+    (ActorExpert.py:178, qt_opt_network.py:168-170).  actions [B,N,A], idx [B,k]."""
+    return np.take_along_axis(np.asarray(actions), np.asarray(idx)[:, :, None], axis=1)
+
+
+def argmax_max_mean(q):
+    """``np.argmax / np.max / np.mean(axis=1)`` (optimal_q_network.py:156-159,
+    ActorCritic.py:139,158,210,223).  np.argmax returns the first maximal index."""
+    q = np.asarray(q)
+    return np.argmax(q, axis=1).astype(np.int64), np.max(q, axis=1), np.mean(q, axis=1, dtype=q.dtype)
+
+
+def sql_soft_value(q_targ, action_dim):
+    """SQL soft value (sql_network.py:76-84): ``logsumexp_n Q - log N + A log 2``."""
+    q = np.asarray(q_targ, F32)
+    m = np.max(q, axis=1, keepdims=True)
+    lse = (m[:, 0] + np.log(np.sum(np.exp(q - m), axis=1, dtype=F32))).astype(F32)
+    return (lse - F32(np.log(F32(q.shape[1]))) + F32(action_dim * np.log(2))).astype(F32)
+
+
+def fkl_reduce(q, w, logp, entropy_scale, dtype=F32):
+    """ForwardKL policy loss over the quadrature grid (forwardkl_network.py:165-194):
+    ``t=q/alpha``; ``m_b=max_n t``; ``e=exp(t-m)``; ``z_b=sum_n w_n e``; ``p=e/z`` (detached);
+    ``loss = -mean_b sum_n w_n p logpi``.
+    Returns (loss scalar, per-state loss [B], boltzmann p [B,N], dloss/dlogp [B,N])."""
+    q = np.asarray(q, dtype)
+    w = np.asarray(w, dtype)
+    logp = np.asarray(logp, dtype)
+    t = q / dtype(entropy_scale)
+    m = np.max(t, axis=1, keepdims=True)
+    e = np.exp(t - m)
+    z = np.sum(e * w[None, :], axis=1, keepdims=True)
+    p = e / z
+    per_state = -np.sum(p * logp * w[None, :], axis=1)
+    loss = np.mean(per_state)
+    dlogp = -(p * w[None, :]) / dtype(q.shape[0])
+    return dtype(loss), per_state.astype(dtype), p.astype(dtype), dlogp.astype(dtype)
+
+
+def rkl_reduce(q, v, w, logp, entropy_scale, hard=False, dtype=F32):
+    """ReverseKL policy loss (reversekl_network.py:181-190; hard variant :197-203):
+    integrand ``-exp(logpi) * ((q - v).detach() - alpha*logpi)`` (hard: no entropy term),
+    times ``w_n``, summed over n, mean over b.
+    Returns (loss, per-state loss [B], dloss/dlogp [B,N])."""
+    q = np.asarray(q, dtype)
+    v = np.asarray(v, dtype).reshape(-1, 1)
+    w = np.asarray(w, dtype)
+    logp = np.asarray(logp, dtype)
+    al = dtype(0.0 if hard else entropy_scale)
+    pe = np.exp(logp)
+    adv = q - v
+    integrand = -pe * (adv - al * logp)
+    per_state = np.sum(integrand * w[None, :], axis=1)
+    loss = np.mean(per_state)
+    # d/dlogp [-e^l (adv - al*l)] = -e^l (adv - al*l) + al*e^l = -e^l (adv - al*l - al)
+    dlogp = (-pe * (adv - al * logp - al)) * w[None, :] / dtype(q.shape[0])
+    return dtype(loss), per_state.astype(dtype), dlogp.astype(dtype)
+
+
+# --------------------------------------------------------------------------------------
+# Quadrature grid (third-party: quadpy, unpinned in requirements.txt:4)
+# --------------------------------------------------------------------------------------
+
+
+def clenshaw_curtis(n):
+    """``quadpy.c1.clenshaw_curtis(n)`` (call sites forwardkl_network.py:64,
+    reversekl_network.py:69): n nodes x_j = -cos(j*pi/(n-1)) on [-1,1] and the classical
+    Clenshaw-Curtis weights (published algorithm; quadpy is not vendored in the reference).
+    The reference then drops both endpoints (``points[1:-1]``)."""
+    if n < 2:
+        raise ValueError("clenshaw_curtis needs n >= 2")
+    N = n - 1
+    j = np.arange(n)
+    theta = np.pi * j / N
+    x = -np.cos(theta)
+    w = np.zeros(n)
+    for i in range(n):
+        s = 0.0
+        for k in range(1, N // 2 + 1):
+            bk = 1.0 if 2 * k == N else 2.0
+            s += bk / (4.0 * k * k - 1.0) * math.cos(2.0 * k * theta[i])
+        c = 1.0 if i in (0, N) else 2.0
+        w[i] = c / N * (1.0 - s)
+    return x, w
+
+
+def clenshaw_curtis_fast(n):
+    """Vectorised version of :func:`clenshaw_curtis` (same arithmetic, numpy)."""
+    N = n - 1
+    theta = np.pi * np.arange(n) / N
+    x = -np.cos(theta)
+    k = np.arange(1, N // 2 + 1)
+    bk = np.where(2 * k == N, 1.0, 2.0)
+    s = (bk / (4.0 * k * k - 1.0))[None, :] * np.cos(2.0 * k[None, :] * theta[:, None])
+    c = np.full(n, 2.0)
+    c[0] = c[-1] = 1.0
+    w = c / N * (1.0 - s.sum(axis=1))
+    return x, w
+
+
+def intg_grid_1d(n_param, action_max):
+    """A=1 integration grid of FKL/RKL (forwardkl_network.py:60-71): interior CC nodes scaled
+    by action_max, interior weights unscaled, both fp32."""
+    x, w = clenshaw_curtis_fast(int(n_param))
+    acts = (x[1:-1].astype(F32)[:, None] * F32(action_max)).astype(F32)
+    return acts, w[1:-1].astype(F32)
+
+
+# --------------------------------------------------------------------------------------
+# tanh-Gaussian log-prob on the grid (actor side; an *input* to the hot path)
+# --------------------------------------------------------------------------------------
+
+
+def tanh_gauss_logprob_1d(mean, log_std, actions, action_scale, eps=1e-6):
+    """``PolicyNetwork.get_logprob`` for action_dim==1 (forwardkl_network.py:324-344):
+    Normal(mean,std).log_prob(atanh(a/scale)) - log(1-(a/scale)^2+eps).
+    mean/log_std [B,1], actions [N,1] -> [B,N]."""
+    mean = np.asarray(mean, F32).reshape(-1, 1)
+    log_std = np.asarray(log_std, F32).reshape(-1, 1)
+    na = (np.asarray(actions, F32).reshape(1, -1) / F32(action_scale)).astype(F32)
+    at = ((np.log(1 + na) - np.log(1 - na)) / 2).astype(F32)
+    std = np.exp(log_std)
+    lp = -((at - mean) ** 2) / (2 * std * std) - log_std - F32(math.log(math.sqrt(2 * math.pi)))
+    lp = lp - np.log(1 - na * na + F32(eps))
+    return lp.astype(F32)
+
+
+# --------------------------------------------------------------------------------------
+# CEM: bounded diagonal GMM refit + loop
+# --------------------------------------------------------------------------------------
+
+ACTION_BOUND = 2.0                  # utils/boundedvar_gaussian_mixture.py:7
+SIGMA_BOUND = 1.0                   # utils/boundedvar_gaussian_mixture.py:8
+VAR_LO = math.exp(-2 * SIGMA_BOUND)
+VAR_HI = math.exp(2 * SIGMA_BOUND)
+REG_COVAR = 1e-6                    # sklearn GaussianMixture default
+
+
+def _estimate_diag(X, resp, reg_covar=REG_COVAR):
+    """sklearn ``_estimate_gaussian_parameters(..., 'diag')``: nk = sum resp + 10 eps;
+    means = resp^T X / nk; cov = resp^T X^2/nk - 2 means*(resp^T X)/nk + means^2 + reg."""
+    nk = resp.sum(axis=0) + 10 * np.finfo(resp.dtype).eps
+    means = resp.T @ X / nk[:, None]
+    avg_X2 = resp.T @ (X * X) / nk[:, None]
+    avg_means2 = means ** 2
+    avg_X_means = means * (resp.T @ X) / nk[:, None]
+    cov = avg_X2 - 2 * avg_X_means + avg_means2 + reg_covar
+    return nk, means, cov
+
+
+def _bound(means, cov):
+    """The two ``np.clip`` lines of boundedvar_gaussian_mixture.py:27-28 and :68-69."""
+    return (np.clip(means, -ACTION_BOUND, ACTION_BOUND), np.clip(cov, VAR_LO, VAR_HI))
+
+
+def _e_step_diag(X, weights, means, cov):
+    """sklearn ``_estimate_log_gaussian_prob`` (diag) + ``_estimate_log_weights`` +
+    logsumexp normalisation.  Returns (mean log-likelihood, log_resp)."""
+    n, d = X.shape
+    prec_chol = 1.0 / np.sqrt(cov)                         # _compute_precision_cholesky('diag')
+    log_det = np.sum(np.log(prec_chol), axis=1)
+    prec = prec_chol ** 2
+    log_prob = (np.sum(means ** 2 * prec, axis=1)
+                - 2.0 * (X @ (means * prec).T)
+                + (X ** 2) @ prec.T)
+    log_gauss = -0.5 * (d * np.log(2 * np.pi) + log_prob) + log_det
+    weighted = log_gauss + np.log(weights)
+    m = np.max(weighted, axis=1, keepdims=True)
+    norm = m[:, 0] + np.log(np.sum(np.exp(weighted - m), axis=1))
+    log_resp = weighted - norm[:, None]
+    return float(np.mean(norm)), log_resp
+
+
+def gmm_fit_bounded(X, resp0, tol=1e-2, max_iter=100, reg_covar=REG_COVAR):
+    """``BoundedVarGaussianMixture(n_components=M, covariance_type='diag', tol=1e-2).fit(X)``
+    (qt_opt_network.py:173; utils/boundedvar_gaussian_mixture.py:10-75) given the initial
+    responsibilities ``resp0`` [k,M] that sklearn derives from its k-means init (one-hot).
+    sklearn ``BaseMixture.fit_predict`` loop: initialise -> repeat {E, M, lower-bound change <
+    tol -> stop}.  Returns (weights [M], means [M,A], covariances [M,A], n_iter)."""
+    X = np.asarray(X, np.float64)
+    resp0 = np.asarray(resp0, np.float64)
+    n = X.shape[0]
+    nk, means, cov = _estimate_diag(X, resp0, reg_covar)       # _initialize :22-23
+    means, cov = _bound(means, cov)                            # :27-28
+    weights = nk / n                                           # :30
+    lower = -np.inf
+    n_iter = 0
+    for n_iter in range(1, max_iter + 1):
+        prev = lower
+        ll, log_resp = _e_step_diag(X, weights, means, cov)
+        nk, means, cov = _estimate_diag(X, np.exp(log_resp), reg_covar)   # _m_step :62-64
+        means, cov = _bound(means, cov)                                   # :68-69
+        weights = nk / n                                                  # :72
+        lower = ll
+        if abs(lower - prev) < tol:
+            break
+    return weights, means, cov, n_iter
+
+
+def gmm_fit_1comp(X, reg_covar=REG_COVAR):
+    """Closed form for ``n_components=1``: resp==1 so one M-step is the fixed
+    point: mu=clip(mean), var=clip(E[x^2]-mu0^2+1e-6) with mu0 the *unclipped* mean."""
+    X = np.asarray(X, np.float64)
+    resp = np.ones((X.shape[0], 1))
+    nk, means, cov = _estimate_diag(X, resp, reg_covar)
+    means, cov = _bound(means, cov)
+    return np.ones(1), means, cov
+
+
+def farthest_point_labels(X):
+    """Deterministic 2-way initial partition used by the device CEM in place of sklearn's
+    RNG-consuming k-means init ("parity unpinned" for the init): seed c0 = the
+    first elite (best Q), c1 = the elite farthest from c0 (lowest index on ties); label each
+    elite by the nearer seed (c0 on ties)."""
+    X = np.asarray(X, np.float64)
+    d0 = np.sum((X - X[0]) ** 2, axis=1)
+    j = int(np.argmax(d0))
+    d1 = np.sum((X - X[j]) ** 2, axis=1)
+    return (d1 < d0).astype(np.int64)
+
+
+def labels_to_resp(labels, M):
+    r = np.zeros((len(labels), M))
+    r[np.arange(len(labels)), labels] = 1.0
+    return r
+
+
+def gmm_sample_with_noise(weights, means, cov, comp_u, normal_noise):
+    """Restatement of ``GaussianMixture.sample`` with the RNG draws supplied as tensors:
+    component pick by inverse CDF of ``comp_u`` [N] over ``weights``; x = mu_c + sqrt(var_c)*z.
+    (sklearn draws a multinomial count and stacks per-component blocks; the *distribution* is the
+    same, the ordering is not -- the CEM only consumes the samples as a set per state.)"""
+    cdf = np.cumsum(weights)
+    cdf[-1] = 1.0 + 1e-12
+    c = np.searchsorted(cdf, comp_u, side="right")
+    c = np.minimum(c, len(weights) - 1)
+    return means[c] + np.sqrt(cov[c]) * normal_noise
+
+
+def cem_iterate(q_fn, s, u0, noise, comp_u, top_m, num_modal, a_min, a_max, tol=1e-2):
+    """``iterate_cem_multidim`` (qt_opt_network.py:132-175) with the random draws supplied:
+    iter 0 actions = a_min + u0*(a_max-a_min), u0 [B,N,A] in [0,1); later iters sample the
+    refit mixture (samples are *not* clipped to the action box, QT_OPT.py:41 clips only the
+    final action).  ``q_fn(s, actions[B,N,A]) -> q [B,N]``.
+    Returns (weights [B,M], means [B,M,A], covs [B,M,A], elites_idx per iter [iters,B,top_m])."""
+    s = np.asarray(s)
+    B, N, A = u0.shape
+    iters = 1 + (0 if noise is None else noise.shape[0])
+    a_min = np.asarray(a_min, np.float64)
+    a_max = np.asarray(a_max, np.float64)
+    actions = a_min + u0.astype(np.float64) * (a_max - a_min)
+    Wt = np.zeros((B, num_modal))
+    Mu = np.zeros((B, num_modal, A))
+    Cv = np.zeros((B, num_modal, A))
+    all_idx = np.zeros((iters, B, top_m), np.int64)
+    for it in range(iters):
+        if it > 0:
+            actions = np.stack([
+                gmm_sample_with_noise(Wt[b], Mu[b], Cv[b], comp_u[it - 1, b], noise[it - 1, b])
+                for b in range(B)])
+        q = q_fn(s, actions.astype(F32))
+        idx = topk_desc(q, top_m)
+        all_idx[it] = idx
+        el = gather_elites(actions.astype(F32), idx).astype(np.float64)
+        for b in range(B):
+            if num_modal == 1:
+                w, mu, cv = gmm_fit_1comp(el[b])
+            else:
+                resp0 = labels_to_resp(farthest_point_labels(el[b]), num_modal)
+                w, mu, cv, _ = gmm_fit_bounded(el[b], resp0, tol=tol)
+            Wt[b], Mu[b], Cv[b] = w, mu, cv
+    return Wt, Mu, Cv, all_idx
+
+
+def cem_final_action(weights, means):
+    """``gmm.means_[np.argmax(gmm.weights_)]`` (qt_opt_network.py:180)."""
+    k = np.argmax(weights, axis=1)
+    return means[np.arange(means.shape[0]), k]
+
+
+# --------------------------------------------------------------------------------------
+# Backward: dQ/da and the critic regression step
+# --------------------------------------------------------------------------------------
+
+
+def tin_dq_da(s, a, params, dtype=np.float64):
+    """``tf.gradients(q, action)`` for the T-in critic (sql_network.py:101-107):
+    dq/da = W1[:, S:]^T ( relu'(z1) * (W2^T (relu'(z2) * w3)) ).  s [R,S], a [R,A]."""
+    W1, b1, W2, b2, W3, b3 = [np.asarray(p, dtype) for p in params]
+    S = np.asarray(s).shape[1]
+    x = np.concatenate([np.asarray(s, dtype), np.asarray(a, dtype)], axis=1)
+    z1 = x @ W1.T + b1
+    h1 = np.maximum(z1, 0)
+    z2 = h1 @ W2.T + b2
+    g2 = (z2 > 0) * W3.reshape(1, -1)
+    g1 = (g2 @ W2) * (z1 > 0)
+    return g1 @ W1[:, S:]
+
+
+def tmid_dq_da(s, a, params, smin=None, smax=None, dtype=np.float64):
+    """``self.action_grads = tf.gradients(self.q_prediction, self.action_input)``
+    (ae_network.py:117, critic_network.py:58): dq/da = (relu'(z2) * w3) W2[H1:]^T."""
+    W1, b1, W2, b2, W3, b3 = [np.asarray(p, dtype) for p in params]
+    H1 = W1.shape[1]
+    x = clip_state(s, smin, smax, dtype)
+    h1 = np.maximum(x @ W1 + b1, 0)
+    z2 = np.concatenate([h1, np.asarray(a, dtype)], axis=1) @ W2 + b2
+    g2 = (z2 > 0) * W3.reshape(1, -1)
+    return g2 @ W2[H1:].T
+
+
+def q_gradient_ascent(dq_da_fn, s, a0, lr, a_min, a_max, max_steps=10, stop_tol=1e-3):
+    """AE+ action refinement (ae_plus_network.py:310-343): up to ``max_steps`` steps
+    ``a += flag*lr*grad``, clipped to the box; a row stops (flag=0) once
+    mean(|delta a|)/a_max <= stop_tol."""
+    a = np.array(a0, np.float64)
+    flag = np.ones((a.shape[0], 1))
+    amax0 = float(np.asarray(a_max).reshape(-1)[0])
+    for _ in range(max_steps):
+        g = dq_da_fn(s, a)
+        new = np.clip(a + flag * lr * g, a_min, a_max)
+        delta = np.mean(np.abs(new - a), axis=1, keepdims=True) / amax0
+        a = new
+        flag = flag * (delta > stop_tol)
+        if not flag.any():
+            break
+    return a
+
+
+def tin_mse_grads(s, a, y, params, dtype=np.float64):
+    """Gradients of ``nn.MSELoss()(q_net(s,a), y)`` (forwardkl_network.py:133-140) wrt the six
+    T-in parameter tensors (torch layout).  Returns (loss, [gW1,gb1,gW2,gb2,gW3,gb3])."""
+    W1, b1, W2, b2, W3, b3 = [np.asarray(p, dtype) for p in params]
+    x = np.concatenate([np.asarray(s, dtype), np.asarray(a, dtype)], axis=1)
+    B = x.shape[0]
+    z1 = x @ W1.T + b1
+    h1 = np.maximum(z1, 0)
+    z2 = h1 @ W2.T + b2
+    h2 = np.maximum(z2, 0)
+    q = h2 @ W3.reshape(-1) + b3.reshape(())
+    d = q - np.asarray(y, dtype).reshape(-1)
+    loss = np.mean(d * d)
+    dq = (2.0 / B) * d                                      # [B]
+    gW3 = (dq[:, None] * h2).sum(0).reshape(W3.shape)
+    gb3 = np.array([dq.sum()]).reshape(b3.shape)
+    g2 = dq[:, None] * W3.reshape(1, -1) * (z2 > 0)
+    gW2 = g2.T @ h1
+    gb2 = g2.sum(0)
+    g1 = (g2 @ W2) * (z1 > 0)
+    gW1 = g1.T @ x
+    gb1 = g1.sum(0)
+    return loss, [gW1, gb1, gW2, gb2, gW3, gb3]
+
+
+def tmid_mse_grads(s, a, y, params, smin=None, smax=None, dtype=np.float64):
+    """Gradients of ``tf.reduce_mean(tf.squared_difference(y, q))`` (critic_network.py:54-55,
+    qt_opt_network.py:65-66) wrt the T-mid parameters (TF ``[in,out]`` layout)."""
+    W1, b1, W2, b2, W3, b3 = [np.asarray(p, dtype) for p in params]
+    x = clip_state(s, smin, smax, dtype)
+    B = x.shape[0]
+    z1 = x @ W1 + b1
+    h1 = np.maximum(z1, 0)
+    zc = np.concatenate([h1, np.asarray(a, dtype)], axis=1)
+    z2 = zc @ W2 + b2
+    h2 = np.maximum(z2, 0)
+    q = h2 @ W3.reshape(-1) + b3.reshape(())
+    d = q - np.asarray(y, dtype).reshape(-1)
+    loss = np.mean(d * d)
+    dq = (2.0 / B) * d
+    gW3 = (h2 * dq[:, None]).sum(0).reshape(W3.shape)
+    gb3 = np.array([dq.sum()]).reshape(b3.shape)
+    g2 = dq[:, None] * W3.reshape(1, -1) * (z2 > 0)
+    gW2 = zc.T @ g2
+    gb2 = g2.sum(0)
+    H1 = W1.shape[1]
+    g1 = (g2 @ W2[:H1].T) * (z1 > 0)
+    gW1 = x.T @ g1
+    gb1 = g1.sum(0)
+    return loss, [gW1, gb1, gW2, gb2, gW3, gb3]
+
+
+def adam_step_torch(p, g, m, v, t, lr, b1=0.9, b2=0.999, eps=1e-8):
+    """``torch.optim.Adam`` (torch 1.7.1 default, no amsgrad / weight decay; optimizer built at
+    forwardkl_network.py:54-56): denom = sqrt(v)/sqrt(1-b2^t) + eps; p -= lr/(1-b1^t) * m/denom.
+    ``t`` is the 1-based step count.  Returns (p, m, v)."""
+    m = b1 * m + (1 - b1) * g
+    v = b2 * v + (1 - b2) * g * g
+    bc1 = 1 - b1 ** t
+    bc2 = 1 - b2 ** t
+    denom = np.sqrt(v) / math.sqrt(bc2) + eps
+    return p - (lr / bc1) * m / denom, m, v
+
+
+def adam_step_tf(p, g, m, v, t, lr, b1=0.9, b2=0.999, eps=1e-8):
+    """``tf.train.AdamOptimizer`` (critic_network.py:55): lr_t = lr*sqrt(1-b2^t)/(1-b1^t);
+    p -= lr_t * m / (sqrt(v) + eps)  (epsilon outside the bias correction)."""
+    m = b1 * m + (1 - b1) * g
+    v = b2 * v + (1 - b2) * g * g
+    lr_t = lr * math.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+    return p - lr_t * m / (np.sqrt(v) + eps), m, v
+
+
+def soft_update(target, online, tau):
+    """theta' += tau (theta - theta') (critic_network.py:29; torch form
+    forwardkl_network.py:211-215 ``t*(1-tau) + p*tau``)."""
+    return target + tau * (online - target)
+
+
+# --------------------------------------------------------------------------------------
+# Replay buffer sampling / gather
+# --------------------------------------------------------------------------------------
+
+
+def sample_n_k(rng: np.random.RandomState, n: int, k: int):
+    """``RandomAccessQueue.sample_n_k`` (utils/custom_collections.py:107-131): k distinct
+    uniform indices from range(n); ``choice(replace=False)`` when 3k >= n, else a rejection
+    scheme over 2k draws."""
+    if not 0 <= k <= n:
+        raise ValueError("Sample larger than population or is negative")
+    if k == 0:
+        return np.empty((0,), dtype=np.int64)
+    if 3 * k >= n:
+        return rng.choice(n, k, replace=False)
+    result = rng.choice(n, 2 * k)
+    selected = set()
+    j = k
+    for i in range(k):
+        x = result[i]
+        while x in selected:
+            x = result[i] = result[j]
+            j += 1
+            if j == 2 * k:
+                result[k:] = rng.choice(n, k)
+                j = k
+        selected.add(x)
+    return result[:k]
+
+
+def replay_gather(store, idx):
+    """``map(np.array, zip(*batch))`` (utils/replaybuffer.py:32-37) over a struct-of-arrays
+    store ``{'state','action','reward','next_state','gamma'}`` in logical FIFO order."""
+    idx = np.asarray(idx)
+    return tuple(store[k][idx] for k in ("state", "action", "reward", "next_state", "gamma"))
+
+
+# --------------------------------------------------------------------------------------
+# TF checkpoint decoder for the trueQ fixture
+# --------------------------------------------------------------------------------------
+
+TRUEQ_OFFSETS = {                      # byte offsets inside every *.data-00000-of-00001
+    "b1": (8, (200,)),
+    "W1": (2408, (1, 200)),
+    "b2": (4808, (200,)),
+    "W2": (7208, (201, 200)),
+    "b3": (489608, (1,)),
+    "W3": (489620, (200, 1)),
+}
+
+
+def decode_trueq_checkpoint(path):
+    """Read ``main/qf`` tensors of a ``Bimodal1DEnv_*_trueQ_learned.data-00000-of-00001`` bundle
+    as raw little-endian fp32 at the offsets decoded from the ``.index`` table."""
+    raw = open(path, "rb").read()
+    out = {}
+    for name, (off, shape) in TRUEQ_OFFSETS.items():
+        n = int(np.prod(shape))
+        out[name] = np.frombuffer(raw, dtype="<f4", count=n, offset=off).reshape(shape).copy()
+    return out
+
+
+def bimodal_reward(action, maxima=(-0.6, 0.6), stddev=(0.2, 0.2), height=(1.0, 1.0)):
+    """Closed-form ``reward_func`` of the Bimodal1D bandits (environments/environments.py:573-587
+    for eq_var1; the variants differ in maxima/stddev/height)."""
+    a = np.asarray(action, np.float64)
+    return sum(h * np.exp(-0.5 * ((a - mx) / sd) ** 2) for mx, sd, h in zip(maxima, stddev, height))

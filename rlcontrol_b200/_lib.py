@@ -1,0 +1,90 @@
+"""ctypes binding of librlc.so (include/rlc.h).  There is no CPU fallback: if the library is
+missing or a call fails, this module raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librlc.so")
+
+TIN, TMID = 0, 1
+LAYOUT_OUT_IN, LAYOUT_IN_OUT = 0, 1
+ACT_SHARED, ACT_PER_STATE = 0, 1
+PREC_FP32, PREC_FP16, PREC_BF16, PREC_AUTO = 0, 1, 2, 3
+ADAM_TORCH, ADAM_TF = 0, 1
+
+PREC_BY_NAME = {"fp32": PREC_FP32, "fp16": PREC_FP16, "bf16": PREC_BF16, "auto": PREC_AUTO}
+
+
+class RlcCritic(C.Structure):
+    _fields_ = [("topology", C.c_int32), ("S", C.c_int32), ("A", C.c_int32), ("H1", C.c_int32),
+                ("H2", C.c_int32), ("theta", C.c_void_p), ("smin", C.c_void_p),
+                ("smax", C.c_void_p)]
+
+
+class RlcError(RuntimeError):
+    """Non-zero status from the C-ABI (map C status -> RuntimeError)."""
+
+
+_p, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+_cr = C.POINTER(RlcCritic)
+
+# name -> (restype, argtypes); must list every symbol include/rlc.h declares
+SIGNATURES = {
+    "rlc_version": (_i, []),
+    "rlc_status_string": (C.c_char_p, [_i]),
+    "rlc_last_cuda_error": (C.c_char_p, []),
+    "rlc_create": (_i, [C.POINTER(_p), _i]),
+    "rlc_destroy": (_i, [_p]),
+    "rlc_launch_count": (_i64, [_p]),
+    "rlc_theta_numel": (_i64, [_i, _i, _i, _i, _i]),
+    "rlc_theta_offsets": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i64)]),
+    "rlc_pack_theta": (_i, [_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "rlc_unpack_theta": (_i, [_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "rlc_invalidate_pack": (_i, [_p, _p]),
+    "rlc_critic_eval": (_i, [_p, _cr, _p, _i, _p, _i, _i, _i, _p, _p]),
+    "rlc_tmid_eval_grad": (_i, [_p, _cr, _p, _i, _p, _i, _i, _p, _p, _p]),
+    "rlc_umma_last_error": (_i, [_p, _p]),
+    "rlc_reduce_topk": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p]),
+    "rlc_reduce_stats": (_i, [_p, _p, _i, _i, _p, _p, _p, _p]),
+    "rlc_reduce_lse": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "rlc_reduce_fkl": (_i, [_p, _p, _p, _p, _i, _i, _f, _i, _p, _p, _p, _p]),
+    "rlc_reduce_rkl": (_i, [_p, _p, _p, _p, _p, _i, _i, _f, _i, _i, _p, _p, _p]),
+    "rlc_cem": (_i, [_p, _cr, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "rlc_gmm_refit": (_i, [_p, _p, _i, _i, _i, _i, _p, _f, _i, _p, _p, _p, _p, _p]),
+    "rlc_critic_grad_action": (_i, [_p, _cr, _p, _p, _i, _p, _p, _p]),
+    "rlc_critic_grads": (_i, [_p, _cr, _p, _p, _p, _i, _i, _p, _p, _p, _p]),
+    "rlc_adam_step": (_i, [_p, _p, _p, _p, _p, _i64, _i, _f, _f, _f, _f, _i, _p, _f, _p]),
+    "rlc_soft_update": (_i, [_p, _p, _p, _i64, _f, _p]),
+    "rlc_replay_gather": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p]),
+    "rlc_replay_scatter": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen librlc.so (built in-tree by ``__graft_entry__.build()`` / ``make -C csrc``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RlcError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                       f"g.build()'` (nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here == header/library drift
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int):
+    if status != 0:
+        lib = load()
+        msg = lib.rlc_status_string(status).decode()
+        if status == -4:
+            msg += ": " + lib.rlc_last_cuda_error().decode()
+        raise RlcError(f"librlc status {status}: {msg}")

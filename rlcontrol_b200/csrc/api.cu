@@ -1,0 +1,119 @@
+// Handle lifecycle, workspace and the evaluation dispatcher of librlc.so.
+#include <new>
+
+#include "common.cuh"
+
+thread_local char g_rlc_cuda_err[512] = {0};
+
+extern "C" int rlc_version(void) { return RLC_VERSION; }
+
+extern "C" const char* rlc_status_string(int status) {
+  switch (status) {
+    case RLC_OK: return "ok";
+    case RLC_ERR_INVALID: return "invalid argument (shape, null pointer or unsupported combination)";
+    case RLC_ERR_ARCH: return "device is not sm_100: the tensor-core path needs a B200";
+    case RLC_ERR_ALLOC: return "workspace allocation failed";
+    case RLC_ERR_CUDA: return "CUDA runtime error";
+    case RLC_ERR_UNSUPPORTED: return "shape not supported by this kernel";
+    default: return "unknown status";
+  }
+}
+
+extern "C" const char* rlc_last_cuda_error(void) { return g_rlc_cuda_err; }
+
+extern "C" int rlc_create(rlc_handle** out, int device) {
+  RLC_REQUIRE(out);
+  *out = nullptr;
+  int count = 0;
+  RLC_CUDA(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return RLC_ERR_INVALID;
+  cudaDeviceProp prop;
+  RLC_CUDA(cudaGetDeviceProperties(&prop, device));
+  rlc_handle* h = new (std::nothrow) rlc_handle();
+  if (!h) return RLC_ERR_ALLOC;
+  memset(h, 0, sizeof(*h));
+  h->device = device;
+  h->sm_major = prop.major;
+  h->sm_minor = prop.minor;
+  h->num_sms = prop.multiProcessorCount;
+  h->smem_optin = prop.sharedMemPerBlockOptin;
+  RLC_CUDA(cudaSetDevice(device));
+  if (cudaMalloc((void**)&h->err_flag, 256) != cudaSuccess) {
+    (void)cudaGetLastError();
+    delete h;
+    return RLC_ERR_ALLOC;
+  }
+  RLC_CUDA(cudaMemset(h->err_flag, 0, 256));
+  *out = h;
+  return RLC_OK;
+}
+
+extern "C" int rlc_destroy(rlc_handle* h) {
+  if (!h) return RLC_OK;
+  if (h->ws) cudaFree(h->ws);
+  if (h->err_flag) cudaFree(h->err_flag);
+  for (int i = 0; i < RLC_MAX_PACKS; ++i)
+    if (h->packs[i].dev) cudaFree(h->packs[i].dev);
+  delete h;
+  return RLC_OK;
+}
+
+extern "C" int64_t rlc_launch_count(const rlc_handle* h) { return h ? h->launches : 0; }
+
+int rlc_workspace(rlc_handle* h, size_t bytes, void** out) {
+  if (bytes > h->ws_bytes) {
+    RLC_CUDA(cudaDeviceSynchronize());
+    if (h->ws) cudaFree(h->ws);
+    h->ws = nullptr;
+    h->ws_bytes = 0;
+    size_t want = bytes + (bytes >> 2) + 4096;
+    cudaError_t e = cudaMalloc(&h->ws, want);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      return RLC_ERR_ALLOC;
+    }
+    h->ws_bytes = want;
+  }
+  *out = h->ws;
+  return RLC_OK;
+}
+
+extern "C" int64_t rlc_theta_numel(int topology, int S, int A, int H1, int H2) {
+  if ((topology != RLC_TIN && topology != RLC_TMID) || S < 1 || A < 1 || H1 < 1 || H2 < 1) return -1;
+  return theta_view(topology, S, A, H1, H2).numel;
+}
+
+extern "C" int rlc_theta_offsets(int topology, int S, int A, int H1, int H2, int64_t off[6]) {
+  RLC_REQUIRE(off && (topology == RLC_TIN || topology == RLC_TMID) && S >= 1 && A >= 1 && H1 >= 1 && H2 >= 1);
+  const ThetaView t = theta_view(topology, S, A, H1, H2);
+  off[0] = t.oW1; off[1] = t.ob1; off[2] = t.oW2; off[3] = t.ob2; off[4] = t.ow3; off[5] = t.ob3;
+  return RLC_OK;
+}
+
+extern "C" int rlc_invalidate_pack(rlc_handle* h, const float* theta) {
+  RLC_REQUIRE(h);
+  for (int i = 0; i < RLC_MAX_PACKS; ++i)
+    if (h->packs[i].theta == theta) h->packs[i].valid = false;
+  return RLC_OK;
+}
+
+extern "C" int rlc_critic_eval(rlc_handle* h, const rlc_critic* c, const float* s, int B,
+                               const float* a, int N, int act_mode, int precision, float* q_out,
+                               void* stream) {
+  RLC_REQUIRE(h && critic_ok(c) && s && a && q_out && B >= 0 && N >= 0);
+  RLC_REQUIRE(act_mode == RLC_ACT_SHARED || act_mode == RLC_ACT_PER_STATE);
+  RLC_REQUIRE(precision >= RLC_PREC_FP32 && precision <= RLC_PREC_AUTO);
+  if ((long long)B * N == 0) return RLC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == RLC_PREC_AUTO) {
+    precision = (c->topology == RLC_TIN && (long long)B * N >= 16384 && rlc_umma_supported(h, c, B, N))
+                    ? RLC_PREC_FP16
+                    : RLC_PREC_FP32;
+  }
+  if (precision == RLC_PREC_FP32) return rlc_eval_fp32(h, c, s, B, a, N, act_mode, q_out, st);
+  // tensor-core path: T-in only (T-mid is not a dense contraction once hoisted)
+  if (c->topology != RLC_TIN) return RLC_ERR_UNSUPPORTED;
+  if (h->sm_major != 10) return RLC_ERR_ARCH;
+  if (!rlc_umma_supported(h, c, B, N)) return RLC_ERR_UNSUPPORTED;
+  return rlc_eval_umma(h, c, s, B, a, N, act_mode, precision, q_out, st);
+}

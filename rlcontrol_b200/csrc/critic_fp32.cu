@@ -1,0 +1,730 @@
+// CUDA-core fp32 critic kernels: fused B x N evaluation for both topologies, the hoisted T-mid
+// row kernel (with dQ/da), and the B-row training path (forward, backward, weight grads) built on
+// one tiled SGEMM.  These are the exact-parity path and the path for small, launch-bound
+// configs; the large T-in evaluation runs on tcgen05 (critic_umma.cu).
+#include "common.cuh"
+
+// =============================================================================================
+// Fused two-layer kernel: 64 rows per CTA, h1 tile kept in shared memory, layer 2 register-tiled
+// (4 rows x NJ strided columns per thread), epilogue = w3 dot (T-in q) or store p (T-mid term).
+// =============================================================================================
+enum { MODE_TIN_Q = 0, MODE_TMID_P = 1 };
+
+template <int NJ, int MODE>
+__global__ void __launch_bounds__(256)
+k_mlp2_rows(const float* __restrict__ s, const float* __restrict__ a, int act_per_state,
+            long long R, int N, int S, int A, int H1, int H2, const float* __restrict__ W1,
+            const float* __restrict__ b1, const float* __restrict__ W2,
+            const float* __restrict__ b2, const float* __restrict__ w3,
+            const float* __restrict__ b3, const float* __restrict__ smin,
+            const float* __restrict__ smax, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  const int K1 = (MODE == MODE_TIN_Q) ? S + A : S;
+  const int H1P = H1 + 1;
+  float* xs = sm;             // [64][K1]
+  float* h1s = sm + 64 * K1;  // [64][H1P]
+  const long long r0 = (long long)blockIdx.x * 64;
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < 64 * K1; i += 256) {
+    const int r = i / K1, k = i - r * K1;
+    const long long row = r0 + r;
+    float v = 0.f;
+    if (row < R) {
+      if (MODE == MODE_TIN_Q) {
+        const long long b = row / N;
+        if (k < S) {
+          v = s[b * S + k];
+          if (smin) v = fminf(fmaxf(v, smin[k]), smax[k]);
+        } else {
+          const long long arow = act_per_state ? row : (row - b * N);
+          v = a[arow * A + (k - S)];
+        }
+      } else {
+        v = s[row * S + k];
+        if (smin) v = fminf(fmaxf(v, smin[k]), smax[k]);
+      }
+    }
+    xs[i] = v;
+  }
+  __syncthreads();
+
+  for (int i = tid; i < 64 * H1; i += 256) {
+    const int r = i / H1, j = i - r * H1;
+    float acc = b1[j];
+    const float* xr = xs + r * K1;
+    for (int k = 0; k < K1; ++k) acc = fmaf(xr[k], __ldg(W1 + (long long)k * H1 + j), acc);
+    h1s[r * H1P + j] = fmaxf(acc, 0.f);
+  }
+  __syncthreads();
+
+  const int rg = tid >> 4, cg = tid & 15;
+  float acc[4][NJ];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
+  const float* h = h1s + (rg * 4) * H1P;
+  for (int k = 0; k < H1; ++k) {
+    const float h0 = h[k], h1v = h[H1P + k], h2v = h[2 * H1P + k], h3v = h[3 * H1P + k];
+    const float* wrow = W2 + (long long)k * H2 + cg;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const float w = (cg + 16 * j < H2) ? __ldg(wrow + 16 * j) : 0.f;
+      acc[0][j] = fmaf(h0, w, acc[0][j]);
+      acc[1][j] = fmaf(h1v, w, acc[1][j]);
+      acc[2][j] = fmaf(h2v, w, acc[2][j]);
+      acc[3][j] = fmaf(h3v, w, acc[3][j]);
+    }
+  }
+
+  if (MODE == MODE_TIN_Q) {
+    float qs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int c = cg + 16 * j;
+      if (c < H2) {
+        const float bb = __ldg(b2 + c), ww = __ldg(w3 + c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) qs[i] = fmaf(ww, fmaxf(acc[i][j] + bb, 0.f), qs[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) qs[i] += __shfl_xor_sync(0xffffffffu, qs[i], o);
+    }
+    if (cg == 0) {
+      const float bb3 = __ldg(b3);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long row = r0 + rg * 4 + i;
+        if (row < R) out[row] = qs[i] + bb3;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int c = cg + 16 * j;
+      if (c < H2) {
+        const float bb = __ldg(b2 + c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const long long row = r0 + rg * 4 + i;
+          if (row < R) out[row * H2 + c] = acc[i][j] + bb;
+        }
+      }
+    }
+  }
+}
+
+template <int MODE>
+static int launch_mlp2(rlc_handle* h, const float* s, const float* a, int act_per_state,
+                       long long R, int N, int S, int A, int H1, int H2, const float* W1,
+                       const float* b1, const float* W2, const float* b2, const float* w3,
+                       const float* b3, const float* smin, const float* smax, float* out,
+                       cudaStream_t st) {
+  if (R == 0) return RLC_OK;
+  const int K1 = (MODE == MODE_TIN_Q) ? S + A : S;
+  const size_t smem = (size_t)(64 * K1 + 64 * (H1 + 1)) * sizeof(float);
+  if (smem > h->smem_optin) return RLC_ERR_UNSUPPORTED;
+  const long long blocks = (R + 63) / 64;
+  if (blocks > 0x7fffffffLL) return RLC_ERR_INVALID;
+#define RLC_MLP2_CASE(NJ)                                                                        \
+  {                                                                                              \
+    auto kern = k_mlp2_rows<NJ, MODE>;                                                           \
+    RLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<(unsigned)blocks, 256, smem, st>>>(s, a, act_per_state, R, N, S, A, H1, H2, W1, b1,   \
+                                              W2, b2, w3, b3, smin, smax, out);                  \
+  }
+  if (H2 <= 64) RLC_MLP2_CASE(4)
+  else if (H2 <= 208) RLC_MLP2_CASE(13)
+  else if (H2 <= 304) RLC_MLP2_CASE(19)
+  else if (H2 <= 512) RLC_MLP2_CASE(32)
+  else return RLC_ERR_UNSUPPORTED;
+#undef RLC_MLP2_CASE
+  RLC_LAUNCH_CHECK(h);
+  return RLC_OK;
+}
+
+int rlc_tmid_state_term(rlc_handle* h, const rlc_critic* c, const float* s, int B, float* p_out,
+                        cudaStream_t st) {
+  const ThetaView t = theta_view(RLC_TMID, c->S, c->A, c->H1, c->H2);
+  const float* th = c->theta;
+  return launch_mlp2<MODE_TMID_P>(h, s, nullptr, 0, B, 1, c->S, c->A, c->H1, c->H2, th + t.oW1,
+                                  th + t.ob1, th + t.oW2, th + t.ob2, th + t.ow3, th + t.ob3,
+                                  c->smin, c->smax, p_out, st);
+}
+
+// =============================================================================================
+// T-mid row kernel (hoisted): q = sum_j w3_j relu(p[b][j] + sum_i a_i W2a[i][j]) + b3, and
+// optionally dq/da_i = sum_j [z_j>0] w3_j W2a[i][j].  One thread per (b,n) row; W2a / w3 in smem.
+// =============================================================================================
+template <int AT, bool GRAD>
+__global__ void __launch_bounds__(256)
+k_tmid_rows(const float* __restrict__ p, const float* __restrict__ a, int act_per_state,
+            long long R, int N, int A, int H2, const float* __restrict__ W2a,
+            const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ q_out,
+            float* __restrict__ dqda_out) {
+  extern __shared__ float sm[];
+  const int H2P = (H2 + 3) & ~3;
+  float* w3s = sm;         // [H2P]
+  float* was = sm + H2P;   // [AT][H2P]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < H2P; i += 256) w3s[i] = (i < H2) ? w3[i] : 0.f;
+  for (int i = tid; i < AT * H2P; i += 256) {
+    const int ai = i / H2P, j = i - ai * H2P;
+    was[i] = (ai < A && j < H2) ? W2a[(long long)ai * H2 + j] : 0.f;
+  }
+  __syncthreads();
+  const long long row = (long long)blockIdx.x * 256 + tid;
+  if (row >= R) return;
+  const long long b = row / N;
+  const long long arow = act_per_state ? row : (row - b * N);
+  float ar[AT];
+#pragma unroll
+  for (int i = 0; i < AT; ++i) ar[i] = (i < A) ? a[arow * A + i] : 0.f;
+  const float* pb = p + b * H2;
+  float q = 0.f;
+  float g[AT];
+#pragma unroll
+  for (int i = 0; i < AT; ++i) g[i] = 0.f;
+  for (int j = 0; j < H2P; j += 4) {
+    float z[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) z[u] = (j + u < H2) ? __ldg(pb + j + u) : 0.f;
+#pragma unroll
+    for (int i = 0; i < AT; ++i) {
+      const float4 w = *reinterpret_cast<const float4*>(was + i * H2P + j);
+      z[0] = fmaf(ar[i], w.x, z[0]);
+      z[1] = fmaf(ar[i], w.y, z[1]);
+      z[2] = fmaf(ar[i], w.z, z[2]);
+      z[3] = fmaf(ar[i], w.w, z[3]);
+    }
+    const float4 w3v = *reinterpret_cast<const float4*>(w3s + j);
+    const float w3a[4] = {w3v.x, w3v.y, w3v.z, w3v.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      q = fmaf(w3a[u], fmaxf(z[u], 0.f), q);
+      if (GRAD) {
+        const float gw = (z[u] > 0.f) ? w3a[u] : 0.f;
+#pragma unroll
+        for (int i = 0; i < AT; ++i) g[i] = fmaf(gw, was[i * H2P + j + u], g[i]);
+      }
+    }
+  }
+  if (q_out) q_out[row] = q + __ldg(b3);
+  if (GRAD) {
+#pragma unroll
+    for (int i = 0; i < AT; ++i)
+      if (i < A) dqda_out[row * A + i] = g[i];
+  }
+}
+
+template <bool GRAD>
+static int launch_tmid_rows(rlc_handle* h, const rlc_critic* c, const float* p, const float* a,
+                            int act_per_state, long long R, int N, float* q_out, float* dqda_out,
+                            cudaStream_t st) {
+  if (R == 0) return RLC_OK;
+  const ThetaView t = theta_view(RLC_TMID, c->S, c->A, c->H1, c->H2);
+  const float* W2a = c->theta + t.oW2 + (int64_t)c->H1 * c->H2;
+  const float* w3 = c->theta + t.ow3;
+  const float* b3 = c->theta + t.ob3;
+  const int H2P = (c->H2 + 3) & ~3;
+  const long long blocks = (R + 255) / 256;
+  if (blocks > 0x7fffffffLL) return RLC_ERR_INVALID;
+#define RLC_TMID_CASE(AT)                                                                        \
+  {                                                                                              \
+    const size_t smem = (size_t)(H2P * (1 + AT)) * sizeof(float);                                \
+    if (smem > h->smem_optin) return RLC_ERR_UNSUPPORTED;                                        \
+    auto kern = k_tmid_rows<AT, GRAD>;                                                           \
+    RLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<(unsigned)blocks, 256, smem, st>>>(p, a, act_per_state, R, N, c->A, c->H2, W2a, w3,   \
+                                              b3, q_out, dqda_out);                              \
+  }
+  if (c->A <= 1) RLC_TMID_CASE(1)
+  else if (c->A <= 2) RLC_TMID_CASE(2)
+  else if (c->A <= 4) RLC_TMID_CASE(4)
+  else if (c->A <= 8) RLC_TMID_CASE(8)
+  else if (c->A <= 16) RLC_TMID_CASE(16)
+  else if (c->A <= 32) RLC_TMID_CASE(32)
+  else return RLC_ERR_UNSUPPORTED;
+#undef RLC_TMID_CASE
+  RLC_LAUNCH_CHECK(h);
+  return RLC_OK;
+}
+
+int rlc_eval_fp32(rlc_handle* h, const rlc_critic* c, const float* s, int B, const float* a, int N,
+                  int act_mode, float* q_out, cudaStream_t st) {
+  const long long R = (long long)B * N;
+  const ThetaView t = theta_view(c->topology, c->S, c->A, c->H1, c->H2);
+  const float* th = c->theta;
+  if (c->topology == RLC_TIN) {
+    return launch_mlp2<MODE_TIN_Q>(h, s, a, act_mode == RLC_ACT_PER_STATE, R, N, c->S, c->A, c->H1,
+                                   c->H2, th + t.oW1, th + t.ob1, th + t.oW2, th + t.ob2,
+                                   th + t.ow3, th + t.ob3, c->smin, c->smax, q_out, st);
+  }
+  void* ws = nullptr;
+  int rc = rlc_workspace(h, (size_t)B * c->H2 * sizeof(float), &ws);
+  if (rc) return rc;
+  float* p = (float*)ws;
+  rc = rlc_tmid_state_term(h, c, s, B, p, st);
+  if (rc) return rc;
+  return launch_tmid_rows<false>(h, c, p, a, act_mode == RLC_ACT_PER_STATE, R, N, q_out, nullptr,
+                                 st);
+}
+
+// =============================================================================================
+// Tiled SGEMM used by the B-row training path and the T-in dQ/da:
+//   C[M,N] = opA(A)[M,K] * opB(B)[K,N]  (+ bias[N]) ; optional relu on A at load (A := relu(A)),
+//   optional mask multiply C *= (Z > 0).  Row-major with leading dimensions.
+// =============================================================================================
+struct GemmEpi {
+  const float* bias;   // per output column or nullptr
+  const float* maskZ;  // same shape/ld as C or nullptr: C *= (Z>0)
+  int ldz;
+  int reluA;
+  float alpha;
+};
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+k_gemm(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ Bm,
+       int ldb, float* __restrict__ C, int ldc, GemmEpi epi) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int tr = tid >> 4, tc = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const int e = tid + l * 256;  // 0..1023
+      {
+        int m, k;
+        if (TA) { m = e & 63; k = e >> 6; } else { k = e & 15; m = e >> 4; }
+        const int gm = m0 + m, gk = k0 + k;
+        float v = 0.f;
+        if (gm < M && gk < K) v = TA ? A[(long long)gk * lda + gm] : A[(long long)gm * lda + gk];
+        if (epi.reluA) v = fmaxf(v, 0.f);
+        As[k][m] = v;
+      }
+      {
+        int n, k;
+        if (TB) { k = e & 15; n = e >> 4; } else { n = e & 63; k = e >> 6; }
+        const int gn = n0 + n, gk = k0 + k;
+        float v = 0.f;
+        if (gn < N && gk < K) v = TB ? Bm[(long long)gn * ldb + gk] : Bm[(long long)gk * ldb + gn];
+        Bs[k][n] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = As[k][tr * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = Bs[k][tc * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + tr * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tc * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j] * epi.alpha;
+      if (epi.bias) v += epi.bias[gn];
+      if (epi.maskZ && !(epi.maskZ[(long long)gm * epi.ldz + gn] > 0.f)) v = 0.f;
+      C[(long long)gm * ldc + gn] = v;
+    }
+  }
+}
+
+static int gemm(rlc_handle* h, bool ta, bool tb, int M, int N, int K, const float* A, int lda,
+                const float* Bm, int ldb, float* C, int ldc, GemmEpi epi, cudaStream_t st) {
+  if (M == 0 || N == 0) return RLC_OK;
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  if (!ta && !tb) k_gemm<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, Bm, ldb, C, ldc, epi);
+  else if (ta && !tb) k_gemm<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, Bm, ldb, C, ldc, epi);
+  else if (!ta && tb) k_gemm<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, Bm, ldb, C, ldc, epi);
+  else k_gemm<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, Bm, ldb, C, ldc, epi);
+  RLC_LAUNCH_CHECK(h);
+  return RLC_OK;
+}
+
+// X[R, in1] = T-in: [clip(s), a] ; T-mid: clip(s)
+__global__ void k_build_x(const float* __restrict__ s, const float* __restrict__ a, long long R,
+                          int S, int A, int tin, const float* __restrict__ smin,
+                          const float* __restrict__ smax, float* __restrict__ X) {
+  const int K1 = tin ? S + A : S;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * K1) return;
+  const long long r = i / K1;
+  const int k = (int)(i - r * K1);
+  float v;
+  if (k < S) {
+    v = s[r * S + k];
+    if (smin) v = fminf(fmaxf(v, smin[k]), smax[k]);
+  } else {
+    v = a[r * A + (k - S)];
+  }
+  X[i] = v;
+}
+
+// T-mid: ZC[R, H1+A] = [relu(Z1), a]
+__global__ void k_build_zc(const float* __restrict__ Z1, const float* __restrict__ a, long long R,
+                           int H1, int A, float* __restrict__ ZC) {
+  const int W = H1 + A;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * W) return;
+  const long long r = i / W;
+  const int k = (int)(i - r * W);
+  ZC[i] = (k < H1) ? fmaxf(Z1[r * H1 + k], 0.f) : a[r * A + (k - H1)];
+}
+
+// Per row: q = relu(Z2) . w3 + b3 ; dq = scale*(q - y) (if y) else 1 ; G2 = dq * w3 * [Z2>0].
+// One warp per row. loss_acc += sum (q-y)^2 / B_total.
+__global__ void k_head(const float* __restrict__ Z2, long long R, int H2,
+                       const float* __restrict__ w3, const float* __restrict__ b3,
+                       const float* __restrict__ y, float inv_btotal, float* __restrict__ q_out,
+                       float* __restrict__ dq_out, float* __restrict__ G2,
+                       float* __restrict__ loss_acc) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const float* z = Z2 + row * H2;
+  float q = 0.f;
+  for (int j = lane; j < H2; j += 32) q = fmaf(w3[j], fmaxf(z[j], 0.f), q);
+  q = warp_sum(q) + b3[0];
+  float dq = 1.f;
+  if (y) {
+    const float d = q - y[row];
+    dq = 2.f * inv_btotal * d;
+    if (lane == 0 && loss_acc) atomicAdd(loss_acc, d * d * inv_btotal);
+  }
+  if (lane == 0) {
+    if (q_out) q_out[row] = q;
+    if (dq_out) dq_out[row] = dq;
+  }
+  if (G2)
+    for (int j = lane; j < H2; j += 32) G2[row * H2 + j] = (z[j] > 0.f) ? dq * w3[j] : 0.f;
+}
+
+// out[n] = sum_r M[r, n]   (column sums; one thread per column, coalesced across columns)
+__global__ void k_colsum(const float* __restrict__ Mx, long long R, int N, int ld,
+                         float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float acc = 0.f;
+  for (long long r = 0; r < R; ++r) acc += Mx[r * ld + n];
+  out[n] = acc;
+}
+
+// gw3[j] = sum_r relu(Z2[r,j]) * dq[r] ; gb3 = sum_r dq[r]  (thread per column j; j==H2 -> gb3)
+__global__ void k_head_grads(const float* __restrict__ Z2, const float* __restrict__ dq,
+                             long long R, int H2, float* __restrict__ gw3,
+                             float* __restrict__ gb3) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > H2) return;
+  float acc = 0.f;
+  if (j == H2) {
+    for (long long r = 0; r < R; ++r) acc += dq[r];
+    gb3[0] = acc;
+  } else {
+    for (long long r = 0; r < R; ++r) acc = fmaf(fmaxf(Z2[r * H2 + j], 0.f), dq[r], acc);
+    gw3[j] = acc;
+  }
+}
+
+struct TrainWs {
+  float *X, *Z1, *ZC, *Z2, *G2, *G1, *dq;
+};
+
+static size_t train_ws_bytes(const rlc_critic* c, long long R) {
+  const ThetaView t = theta_view(c->topology, c->S, c->A, c->H1, c->H2);
+  size_t n = (size_t)R * (t.in1 + 2 * (size_t)c->H1 + 2 * (size_t)c->H2 + 1);
+  if (c->topology == RLC_TMID) n += (size_t)R * (c->H1 + c->A);
+  return n * sizeof(float) + 64 * 16;
+}
+
+static TrainWs carve(const rlc_critic* c, long long R, float* base) {
+  const ThetaView t = theta_view(c->topology, c->S, c->A, c->H1, c->H2);
+  auto take = [&](size_t n) {
+    float* p = base;
+    base += (n + 3) & ~(size_t)3;
+    return p;
+  };
+  TrainWs w;
+  w.X = take((size_t)R * t.in1);
+  w.Z1 = take((size_t)R * c->H1);
+  w.ZC = (c->topology == RLC_TMID) ? take((size_t)R * (c->H1 + c->A)) : nullptr;
+  w.Z2 = take((size_t)R * c->H2);
+  w.G2 = take((size_t)R * c->H2);
+  w.G1 = take((size_t)R * c->H1);
+  w.dq = take((size_t)R);
+  return w;
+}
+
+// Forward over R stacked rows storing pre-activations; then head.  y==nullptr -> dq=1 (dQ/da).
+static int forward_rows(rlc_handle* h, const rlc_critic* c, const float* s, const float* a,
+                        long long R, const float* y, float inv_btotal, TrainWs& w, float* q_out,
+                        float* loss_acc, cudaStream_t st) {
+  const ThetaView t = theta_view(c->topology, c->S, c->A, c->H1, c->H2);
+  const float* th = c->theta;
+  const int tin = c->topology == RLC_TIN;
+  {
+    const long long n = R * t.in1;
+    k_build_x<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s, a, R, c->S, c->A, tin, c->smin,
+                                                           c->smax, w.X);
+    RLC_LAUNCH_CHECK(h);
+  }
+  GemmEpi e1{th + t.ob1, nullptr, 0, 0, 1.f};
+  int rc = gemm(h, false, false, (int)R, c->H1, t.in1, w.X, t.in1, th + t.oW1, c->H1, w.Z1, c->H1,
+                e1, st);
+  if (rc) return rc;
+  GemmEpi e2{th + t.ob2, nullptr, 0, 0, 1.f};
+  if (tin) {
+    e2.reluA = 1;
+    rc = gemm(h, false, false, (int)R, c->H2, c->H1, w.Z1, c->H1, th + t.oW2, c->H2, w.Z2, c->H2,
+              e2, st);
+  } else {
+    const long long n = R * (c->H1 + c->A);
+    k_build_zc<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.Z1, a, R, c->H1, c->A, w.ZC);
+    RLC_LAUNCH_CHECK(h);
+    rc = gemm(h, false, false, (int)R, c->H2, c->H1 + c->A, w.ZC, c->H1 + c->A, th + t.oW2, c->H2,
+              w.Z2, c->H2, e2, st);
+  }
+  if (rc) return rc;
+  k_head<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(w.Z2, R, c->H2, th + t.ow3, th + t.ob3,
+                                                           y, inv_btotal, q_out, w.dq, w.G2,
+                                                           loss_acc);
+  RLC_LAUNCH_CHECK(h);
+  return RLC_OK;
+}
+
+extern "C" int rlc_critic_grad_action(rlc_handle* h, const rlc_critic* c, const float* s,
+                                      const float* a, int R, float* dqda_out, float* q_out,
+                                      void* stream) {
+  RLC_REQUIRE(h && critic_ok(c) && s && a && dqda_out && R >= 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (R == 0) return RLC_OK;
+  const ThetaView t = theta_view(c->topology, c->S, c->A, c->H1, c->H2);
+  const float* th = c->theta;
+  const int CH = 16384;  // row chunk bounds the workspace
+  void* ws = nullptr;
+  int rc = rlc_workspace(h, train_ws_bytes(c, R < CH ? R : CH), &ws);
+  if (rc) return rc;
+  for (long long r0 = 0; r0 < R; r0 += CH) {
+    const long long n = (R - r0 < CH) ? (R - r0) : CH;
+    TrainWs w = carve(c, n, (float*)ws);
+    rc = forward_rows(h, c, s + r0 * c->S, a + r0 * c->A, n, nullptr, 0.f, w,
+                      q_out ? q_out + r0 : nullptr, nullptr, st);
+    if (rc) return rc;
+    GemmEpi e{nullptr, nullptr, 0, 0, 1.f};
+    if (c->topology == RLC_TMID) {
+      // dA = G2 * W2a^T, W2a = rows H1.. of W2 ([A,H2])
+      rc = gemm(h, false, true, (int)n, c->A, c->H2, w.G2, c->H2,
+                th + t.oW2 + (int64_t)c->H1 * c->H2, c->H2, dqda_out + r0 * c->A, c->A, e, st);
+    } else {
+      GemmEpi em{nullptr, w.Z1, c->H1, 0, 1.f};
+      rc = gemm(h, false, true, (int)n, c->H1, c->H2, w.G2, c->H2, th + t.oW2, c->H2, w.G1, c->H1,
+                em, st);
+      if (rc) return rc;
+      // dA = G1 * W1a^T, W1a = rows S.. of W1 ([A,H1])
+      rc = gemm(h, false, true, (int)n, c->A, c->H1, w.G1, c->H1,
+                th + t.oW1 + (int64_t)c->S * c->H1, c->H1, dqda_out + r0 * c->A, c->A, e, st);
+    }
+    if (rc) return rc;
+  }
+  return RLC_OK;
+}
+
+extern "C" int rlc_critic_grads(rlc_handle* h, const rlc_critic* c, const float* s, const float* a,
+                                const float* y, int B, int B_total, float* grad_out,
+                                float* loss_out, float* q_out, void* stream) {
+  RLC_REQUIRE(h && critic_ok(c) && s && a && y && grad_out && B >= 1 && B_total >= B);
+  cudaStream_t st = (cudaStream_t)stream;
+  const ThetaView t = theta_view(c->topology, c->S, c->A, c->H1, c->H2);
+  const float* th = c->theta;
+  void* ws = nullptr;
+  int rc = rlc_workspace(h, train_ws_bytes(c, B), &ws);
+  if (rc) return rc;
+  TrainWs w = carve(c, B, (float*)ws);
+  if (loss_out) RLC_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+  rc = forward_rows(h, c, s, a, B, y, 1.f / (float)B_total, w, q_out, loss_out, st);
+  if (rc) return rc;
+  // head grads
+  k_head_grads<<<(c->H2 + 1 + 127) / 128, 128, 0, st>>>(w.Z2, w.dq, B, c->H2, grad_out + t.ow3,
+                                                        grad_out + t.ob3);
+  RLC_LAUNCH_CHECK(h);
+  // gb2 = colsum(G2)
+  k_colsum<<<(c->H2 + 127) / 128, 128, 0, st>>>(w.G2, B, c->H2, c->H2, grad_out + t.ob2);
+  RLC_LAUNCH_CHECK(h);
+  GemmEpi e{nullptr, nullptr, 0, 0, 1.f};
+  if (c->topology == RLC_TIN) {
+    GemmEpi er = e;
+    er.reluA = 1;  // gW2 = relu(Z1)^T G2
+    rc = gemm(h, true, false, c->H1, c->H2, B, w.Z1, c->H1, w.G2, c->H2, grad_out + t.oW2, c->H2,
+              er, st);
+  } else {
+    rc = gemm(h, true, false, c->H1 + c->A, c->H2, B, w.ZC, c->H1 + c->A, w.G2, c->H2,
+              grad_out + t.oW2, c->H2, e, st);
+  }
+  if (rc) return rc;
+  // G1 = (G2 W2[:H1]^T) * [Z1>0]
+  GemmEpi em{nullptr, w.Z1, c->H1, 0, 1.f};
+  rc = gemm(h, false, true, B, c->H1, c->H2, w.G2, c->H2, th + t.oW2, c->H2, w.G1, c->H1, em, st);
+  if (rc) return rc;
+  k_colsum<<<(c->H1 + 127) / 128, 128, 0, st>>>(w.G1, B, c->H1, c->H1, grad_out + t.ob1);
+  RLC_LAUNCH_CHECK(h);
+  // gW1 = X^T G1
+  rc = gemm(h, true, false, t.in1, c->H1, B, w.X, t.in1, w.G1, c->H1, grad_out + t.oW1, c->H1, e,
+            st);
+  return rc;
+}
+
+// T-mid dQ/da over a B x N block without materialising the stack (AE+ ascent, ae_plus_network.py:
+// 310-343, evaluates B*N rows whose states repeat): exposed through rlc_critic_eval's sibling.
+extern "C" int rlc_tmid_eval_grad(rlc_handle* h, const rlc_critic* c, const float* s, int B,
+                                  const float* a, int N, int act_mode, float* q_out,
+                                  float* dqda_out, void* stream) {
+  RLC_REQUIRE(h && critic_ok(c) && c->topology == RLC_TMID && s && a && dqda_out && B >= 0 && N >= 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((long long)B * N == 0) return RLC_OK;
+  void* ws = nullptr;
+  int rc = rlc_workspace(h, (size_t)B * c->H2 * sizeof(float), &ws);
+  if (rc) return rc;
+  rc = rlc_tmid_state_term(h, c, s, B, (float*)ws, st);
+  if (rc) return rc;
+  return launch_tmid_rows<true>(h, c, (const float*)ws, a, act_mode == RLC_ACT_PER_STATE,
+                                (long long)B * N, N, q_out, dqda_out, st);
+}
+
+// =============================================================================================
+// theta pack / unpack, Adam, soft update
+// =============================================================================================
+// dst[in,out] <- src (layout OUT_IN: src[out,in] ; IN_OUT: copy). unpack = reverse.
+__global__ void k_repack(const float* __restrict__ src, float* __restrict__ dst, int in, int out,
+                         int src_is_out_in, int reverse) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)in * out) return;
+  const int r = (int)(i / out), c = (int)(i - (long long)r * out);  // canonical [in=r][out=c]
+  const long long ext = src_is_out_in ? ((long long)c * in + r) : i;
+  if (!reverse) dst[i] = src[ext];
+  else dst[ext] = src[i];
+}
+
+static int repack(const float* src, float* dst, int in, int out, int layout, int reverse,
+                  cudaStream_t st) {
+  const long long n = (long long)in * out;
+  k_repack<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, in, out,
+                                                        layout == RLC_LAYOUT_OUT_IN, reverse);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return rlc_cuda_fail(e, __FILE__, __LINE__);
+  return RLC_OK;
+}
+
+extern "C" int rlc_pack_theta(int topology, int S, int A, int H1, int H2, int layout,
+                              const float* W1, const float* b1, const float* W2, const float* b2,
+                              const float* W3, const float* b3, float* theta, void* stream) {
+  RLC_REQUIRE(W1 && b1 && W2 && b2 && W3 && b3 && theta);
+  RLC_REQUIRE(topology == RLC_TIN || topology == RLC_TMID);
+  RLC_REQUIRE(layout == RLC_LAYOUT_OUT_IN || layout == RLC_LAYOUT_IN_OUT);
+  cudaStream_t st = (cudaStream_t)stream;
+  const ThetaView t = theta_view(topology, S, A, H1, H2);
+  int rc = repack(W1, theta + t.oW1, t.in1, H1, layout, 0, st);
+  if (rc) return rc;
+  rc = repack(W2, theta + t.oW2, t.in2, H2, layout, 0, st);
+  if (rc) return rc;
+  RLC_CUDA(cudaMemcpyAsync(theta + t.ob1, b1, H1 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  RLC_CUDA(cudaMemcpyAsync(theta + t.ob2, b2, H2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  RLC_CUDA(cudaMemcpyAsync(theta + t.ow3, W3, H2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  RLC_CUDA(cudaMemcpyAsync(theta + t.ob3, b3, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return RLC_OK;
+}
+
+extern "C" int rlc_unpack_theta(int topology, int S, int A, int H1, int H2, int layout,
+                                const float* theta, float* W1, float* b1, float* W2, float* b2,
+                                float* W3, float* b3, void* stream) {
+  RLC_REQUIRE(W1 && b1 && W2 && b2 && W3 && b3 && theta);
+  RLC_REQUIRE(topology == RLC_TIN || topology == RLC_TMID);
+  RLC_REQUIRE(layout == RLC_LAYOUT_OUT_IN || layout == RLC_LAYOUT_IN_OUT);
+  cudaStream_t st = (cudaStream_t)stream;
+  const ThetaView t = theta_view(topology, S, A, H1, H2);
+  int rc = repack(theta + t.oW1, W1, t.in1, H1, layout, 1, st);
+  if (rc) return rc;
+  rc = repack(theta + t.oW2, W2, t.in2, H2, layout, 1, st);
+  if (rc) return rc;
+  RLC_CUDA(cudaMemcpyAsync(b1, theta + t.ob1, H1 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  RLC_CUDA(cudaMemcpyAsync(b2, theta + t.ob2, H2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  RLC_CUDA(cudaMemcpyAsync(W3, theta + t.ow3, H2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  RLC_CUDA(cudaMemcpyAsync(b3, theta + t.ob3, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return RLC_OK;
+}
+
+__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                       float* __restrict__ v, long long n, float lr_eff, float b1, float b2,
+                       float eps, float inv_sqrt_bc2, float* __restrict__ target, float tau) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float pn = p[i] - lr_eff * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+  p[i] = pn;
+  if (target) target[i] += tau * (pn - target[i]);
+}
+
+extern "C" int rlc_adam_step(rlc_handle* h, float* theta, const float* grad, float* m, float* v,
+                             int64_t n, int step, float lr, float beta1, float beta2, float eps,
+                             int variant, float* target, float tau, void* stream) {
+  RLC_REQUIRE(h && theta && grad && m && v && n >= 0 && step >= 1);
+  RLC_REQUIRE(variant == RLC_ADAM_TORCH || variant == RLC_ADAM_TF);
+  if (n == 0) return RLC_OK;
+  const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+  float lr_eff, isb2;
+  if (variant == RLC_ADAM_TORCH) {  // denom = sqrt(v)/sqrt(bc2) + eps ; step = lr/bc1
+    lr_eff = (float)(lr / bc1);
+    isb2 = (float)(1.0 / sqrt(bc2));
+  } else {  // lr_t = lr*sqrt(bc2)/bc1 ; denom = sqrt(v) + eps
+    lr_eff = (float)(lr * sqrt(bc2) / bc1);
+    isb2 = 1.f;
+  }
+  k_adam<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      theta, grad, m, v, n, lr_eff, beta1, beta2, eps, isb2, target, tau);
+  RLC_LAUNCH_CHECK(h);
+  rlc_invalidate_pack(h, theta);
+  if (target) rlc_invalidate_pack(h, target);
+  return RLC_OK;
+}
+
+__global__ void k_soft(float* __restrict__ t, const float* __restrict__ o, long long n, float tau) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) t[i] += tau * (o[i] - t[i]);
+}
+
+extern "C" int rlc_soft_update(rlc_handle* h, float* target, const float* online, int64_t n,
+                               float tau, void* stream) {
+  RLC_REQUIRE(h && target && online && n >= 0);
+  if (n == 0) return RLC_OK;
+  k_soft<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(target, online, n, tau);
+  RLC_LAUNCH_CHECK(h);
+  rlc_invalidate_pack(h, target);
+  return RLC_OK;
+}

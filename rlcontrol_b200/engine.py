@@ -1,0 +1,327 @@
+"""Host-side wrapper of the C-ABI: torch tensors in, torch tensors out, device memory and streams
+from PyTorch, all arithmetic in librlc.so.  One :class:`Engine` per process/GPU; one
+:class:`Critic` per critic network (online / target)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (ACT_PER_STATE, ACT_SHARED, ADAM_TF, ADAM_TORCH, LAYOUT_IN_OUT, LAYOUT_OUT_IN,
+                   PREC_AUTO, PREC_BY_NAME, PREC_FP32, TIN, TMID, RlcCritic, check)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(x, device) -> torch.Tensor:
+    """numpy / torch, float64 or float32 -> contiguous fp32 on device (the reference casts at the
+    feed: torch.FloatTensor(x) forwardkl_network.py:125-129; TF placeholders are float32)."""
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.float32).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32).to(device)
+
+
+class Engine:
+    """Owns the rlc_handle (workspace + packed tensor-core operands) of one CUDA device."""
+
+    def __init__(self, device: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise _lib.RlcError("rlcontrol_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+        self.lib = _lib.load()
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device_index):
+            check(self.lib.rlc_create(C.byref(h), self.device_index))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rlc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.rlc_launch_count(self.h))
+
+    def umma_error(self) -> int:
+        return int(self.lib.rlc_umma_last_error(self.h, _stream()))
+
+    # ------------------------------------------------------------------ reductions (K3)
+    def topk(self, q: torch.Tensor, k: int, actions: Optional[torch.Tensor] = None):
+        """``row.argsort()[::-1][:k]`` per state (ActorExpert.py:177). Returns (idx[B,k] int64,
+        q_sel[B,k], elites[B,k,A] or None)."""
+        B, N = q.shape
+        idx = torch.empty((B, k), dtype=torch.int64, device=q.device)
+        qs = torch.empty((B, k), dtype=torch.float32, device=q.device)
+        elites, A, mode = None, 0, ACT_SHARED
+        if actions is not None:
+            A = actions.shape[-1]
+            mode = ACT_PER_STATE if actions.dim() == 3 else ACT_SHARED
+            elites = torch.empty((B, k, A), dtype=torch.float32, device=q.device)
+        check(self.lib.rlc_reduce_topk(self.h, _ptr(q), B, N, k, _ptr(idx), _ptr(qs), _ptr(actions),
+                                       A, mode, _ptr(elites), _stream()))
+        return idx, qs, elites
+
+    def stats(self, q: torch.Tensor):
+        """(argmax int64 [B], max [B], mean [B]) over the sample axis."""
+        B, N = q.shape
+        am = torch.empty((B,), dtype=torch.int64, device=q.device)
+        mx = torch.empty((B,), dtype=torch.float32, device=q.device)
+        mean = torch.empty((B,), dtype=torch.float32, device=q.device)
+        check(self.lib.rlc_reduce_stats(self.h, _ptr(q), B, N, _ptr(am), _ptr(mx), _ptr(mean), _stream()))
+        return am, mx, mean
+
+    def soft_value(self, q: torch.Tensor, action_dim: int):
+        """SQL ``logsumexp - log N + A log 2`` (sql_network.py:76-84)."""
+        B, N = q.shape
+        v = torch.empty((B,), dtype=torch.float32, device=q.device)
+        check(self.lib.rlc_reduce_lse(self.h, _ptr(q), B, N, int(action_dim), _ptr(v), _stream()))
+        return v
+
+    def fkl(self, q, w, logp, entropy_scale: float, b_total: Optional[int] = None,
+            want_boltz: bool = True, want_grad: bool = True):
+        """ForwardKL grid reduction (forwardkl_network.py:165-194).
+        Returns (loss_b [B], boltz [B,N] | None, dlogp [B,N] | None)."""
+        B, N = q.shape
+        loss_b = torch.empty((B,), dtype=torch.float32, device=q.device)
+        boltz = torch.empty_like(q) if want_boltz else None
+        dlogp = torch.empty_like(q) if want_grad else None
+        check(self.lib.rlc_reduce_fkl(self.h, _ptr(q), _ptr(w), _ptr(logp), B, N, float(entropy_scale),
+                                      int(b_total or B), _ptr(loss_b), _ptr(boltz), _ptr(dlogp),
+                                      _stream()))
+        return loss_b, boltz, dlogp
+
+    def rkl(self, q, v, w, logp, entropy_scale: float, hard: bool = False,
+            b_total: Optional[int] = None, want_grad: bool = True):
+        """ReverseKL grid reduction (reversekl_network.py:181-190 / 197-203)."""
+        B, N = q.shape
+        loss_b = torch.empty((B,), dtype=torch.float32, device=q.device)
+        dlogp = torch.empty_like(q) if want_grad else None
+        check(self.lib.rlc_reduce_rkl(self.h, _ptr(q), _ptr(v), _ptr(w), _ptr(logp), B, N,
+                                      float(entropy_scale), int(bool(hard)), int(b_total or B),
+                                      _ptr(loss_b), _ptr(dlogp), _stream()))
+        return loss_b, dlogp
+
+    def gmm_refit(self, X: torch.Tensor, num_modal: int, resp0: Optional[torch.Tensor] = None,
+                  tol: float = 1e-2, max_iter: int = 100):
+        """Bounded diagonal GMM refit (utils/boundedvar_gaussian_mixture.py). X [B,k,A]."""
+        B, k, A = X.shape
+        w = torch.empty((B, num_modal), dtype=torch.float32, device=X.device)
+        mu = torch.empty((B, num_modal, A), dtype=torch.float32, device=X.device)
+        var = torch.empty((B, num_modal, A), dtype=torch.float32, device=X.device)
+        nit = torch.empty((B,), dtype=torch.int32, device=X.device)
+        check(self.lib.rlc_gmm_refit(self.h, _ptr(X), B, k, A, num_modal, _ptr(resp0), float(tol),
+                                     int(max_iter), _ptr(w), _ptr(mu), _ptr(var), _ptr(nit), _stream()))
+        return w, mu, var, nit
+
+    # ------------------------------------------------------------------ optimiser pieces
+    def adam_step(self, theta, grad, m, v, step: int, lr: float, variant: int = ADAM_TORCH,
+                  beta1=0.9, beta2=0.999, eps=1e-8, target=None, tau: float = 0.0):
+        check(self.lib.rlc_adam_step(self.h, _ptr(theta), _ptr(grad), _ptr(m), _ptr(v), theta.numel(),
+                                     int(step), float(lr), float(beta1), float(beta2), float(eps),
+                                     int(variant), _ptr(target), float(tau), _stream()))
+
+    def soft_update(self, target, online, tau: float):
+        check(self.lib.rlc_soft_update(self.h, _ptr(target), _ptr(online), target.numel(), float(tau),
+                                       _stream()))
+
+
+class Critic:
+    """One critic network on the device: dims + canonical ``theta`` (see include/rlc.h)."""
+
+    def __init__(self, engine: Engine, topology: int, S: int, A: int, H1: int, H2: int,
+                 state_min: Optional[Sequence[float]] = None,
+                 state_max: Optional[Sequence[float]] = None):
+        self.eng = engine
+        self.topology, self.S, self.A, self.H1, self.H2 = int(topology), int(S), int(A), int(H1), int(H2)
+        n = engine.lib.rlc_theta_numel(self.topology, S, A, H1, H2)
+        if n <= 0:
+            raise ValueError("invalid critic dimensions")
+        self.theta = torch.zeros((n,), dtype=torch.float32, device=engine.device)
+        off = (C.c_int64 * 6)()
+        check(engine.lib.rlc_theta_offsets(self.topology, S, A, H1, H2, off))
+        self.offsets = list(off)
+        self.smin = None if state_min is None else _f32(np.asarray(state_min, np.float64).reshape(-1), engine.device)
+        self.smax = None if state_max is None else _f32(np.asarray(state_max, np.float64).reshape(-1), engine.device)
+        if (self.smin is None) != (self.smax is None):
+            raise ValueError("state_min and state_max must be given together")
+        if self.smin is not None and (self.smin.numel() != S or self.smax.numel() != S):
+            raise ValueError("state bounds must have S entries")
+        self._desc = RlcCritic()
+        self._refresh()
+
+    def _refresh(self):
+        d = self._desc
+        d.topology, d.S, d.A, d.H1, d.H2 = self.topology, self.S, self.A, self.H1, self.H2
+        d.theta = self.theta.data_ptr()
+        d.smin = None if self.smin is None else self.smin.data_ptr()
+        d.smax = None if self.smax is None else self.smax.data_ptr()
+
+    @property
+    def in1(self):
+        return self.S + self.A if self.topology == TIN else self.S
+
+    @property
+    def in2(self):
+        return self.H1 if self.topology == TIN else self.H1 + self.A
+
+    # ------------------------------------------------------------------ parameters
+    def load(self, W1, b1, W2, b2, W3, b3, layout: int):
+        """Load the six tensors in the reference's own layout (torch ``[out,in]`` or TF
+        ``[in,out]``)."""
+        dev = self.eng.device
+        ts = [_f32(x, dev) for x in (W1, b1, W2, b2, W3, b3)]
+        exp1 = (self.H1, self.in1) if layout == LAYOUT_OUT_IN else (self.in1, self.H1)
+        exp2 = (self.H2, self.in2) if layout == LAYOUT_OUT_IN else (self.in2, self.H2)
+        if tuple(ts[0].shape) != exp1 or tuple(ts[2].shape) != exp2 or ts[1].numel() != self.H1 \
+                or ts[3].numel() != self.H2 or ts[4].numel() != self.H2 or ts[5].numel() != 1:
+            raise ValueError(f"weight shapes do not match critic dims: {[tuple(t.shape) for t in ts]}")
+        check(self.eng.lib.rlc_pack_theta(self.topology, self.S, self.A, self.H1, self.H2, layout,
+                                          *[_ptr(t) for t in ts], _ptr(self.theta), _stream()))
+        self.invalidate()
+        return self
+
+    def export(self, layout: int):
+        dev = self.eng.device
+        s1 = (self.H1, self.in1) if layout == LAYOUT_OUT_IN else (self.in1, self.H1)
+        s2 = (self.H2, self.in2) if layout == LAYOUT_OUT_IN else (self.in2, self.H2)
+        s3 = (1, self.H2) if layout == LAYOUT_OUT_IN else (self.H2, 1)
+        outs = [torch.empty(s, dtype=torch.float32, device=dev) for s in
+                (s1, (self.H1,), s2, (self.H2,), s3, (1,))]
+        check(self.eng.lib.rlc_unpack_theta(self.topology, self.S, self.A, self.H1, self.H2, layout,
+                                            _ptr(self.theta), *[_ptr(t) for t in outs], _stream()))
+        return outs
+
+    def invalidate(self):
+        check(self.eng.lib.rlc_invalidate_pack(self.eng.h, _ptr(self.theta)))
+
+    def copy_from(self, other: "Critic"):
+        self.theta.copy_(other.theta)
+        self.invalidate()
+
+    # ------------------------------------------------------------------ evaluation (K1/K2)
+    def eval(self, s, a, precision="auto") -> torch.Tensor:
+        """Q for every (state, action) pair: s [B,S]; a [N,A] (shared grid) or [B,N,A].
+        Returns q [B,N] fp32 on the device."""
+        dev = self.eng.device
+        s = _f32(s, dev)
+        a = _f32(a, dev)
+        if s.dim() != 2 or s.shape[1] != self.S:
+            raise ValueError(f"states must be [B,{self.S}], got {tuple(s.shape)}")
+        B = s.shape[0]
+        if a.dim() == 2:
+            mode, N = ACT_SHARED, a.shape[0]
+        elif a.dim() == 3 and a.shape[0] == B:
+            mode, N = ACT_PER_STATE, a.shape[1]
+        else:
+            raise ValueError(f"actions must be [N,A] or [B,N,A], got {tuple(a.shape)}")
+        if a.shape[-1] != self.A:
+            raise ValueError(f"action dim {a.shape[-1]} != {self.A}")
+        prec = PREC_BY_NAME[precision] if isinstance(precision, str) else int(precision)
+        q = torch.empty((B, N), dtype=torch.float32, device=dev)
+        check(self.eng.lib.rlc_critic_eval(self.eng.h, C.byref(self._desc), _ptr(s), B, _ptr(a), N,
+                                           mode, prec, _ptr(q), _stream()))
+        return q
+
+    def eval_grad(self, s, a):
+        """T-mid only: (q [B,N], dq/da [B,N,A]) without materialising the stack."""
+        dev = self.eng.device
+        s, a = _f32(s, dev), _f32(a, dev)
+        B = s.shape[0]
+        mode, N = (ACT_SHARED, a.shape[0]) if a.dim() == 2 else (ACT_PER_STATE, a.shape[1])
+        q = torch.empty((B, N), dtype=torch.float32, device=dev)
+        g = torch.empty((B, N, self.A), dtype=torch.float32, device=dev)
+        check(self.eng.lib.rlc_tmid_eval_grad(self.eng.h, C.byref(self._desc), _ptr(s), B, _ptr(a), N,
+                                              mode, _ptr(q), _ptr(g), _stream()))
+        return q, g
+
+    def grad_action(self, s_rows, a_rows):
+        """``tf.gradients(q, action)`` on R stacked rows. Returns (dq/da [R,A], q [R])."""
+        dev = self.eng.device
+        s, a = _f32(s_rows, dev), _f32(a_rows, dev)
+        R = s.shape[0]
+        g = torch.empty((R, self.A), dtype=torch.float32, device=dev)
+        q = torch.empty((R,), dtype=torch.float32, device=dev)
+        check(self.eng.lib.rlc_critic_grad_action(self.eng.h, C.byref(self._desc), _ptr(s), _ptr(a), R,
+                                                  _ptr(g), _ptr(q), _stream()))
+        return g, q
+
+    def grads(self, s, a, y, b_total: Optional[int] = None):
+        """Gradient of mean((y-Q)^2) wrt theta. Returns (grad [numel], loss [1], q [B])."""
+        dev = self.eng.device
+        s, a, y = _f32(s, dev), _f32(a, dev), _f32(y, dev).reshape(-1)
+        B = s.shape[0]
+        grad = torch.empty_like(self.theta)
+        loss = torch.empty((1,), dtype=torch.float32, device=dev)
+        q = torch.empty((B,), dtype=torch.float32, device=dev)
+        check(self.eng.lib.rlc_critic_grads(self.eng.h, C.byref(self._desc), _ptr(s), _ptr(a), _ptr(y), B,
+                                            int(b_total or B), _ptr(grad), _ptr(loss), _ptr(q), _stream()))
+        return grad, loss, q
+
+    # ------------------------------------------------------------------ CEM (K4)
+    def cem(self, s, u0, noise, comp_u, top_m: int, num_modal: int, a_min, a_max,
+            want_idx: bool = False):
+        """QT-Opt CEM (qt_opt_network.py:132-175) with supplied draws. u0 [B,N,A];
+        noise [iters-1,B,N,A] or None; comp_u [iters-1,B,N] or None."""
+        dev = self.eng.device
+        s, u0 = _f32(s, dev), _f32(u0, dev)
+        B, N, A = u0.shape
+        iters = 1 + (0 if noise is None else noise.shape[0])
+        noise = None if noise is None else _f32(noise, dev)
+        comp_u = None if comp_u is None else _f32(comp_u, dev)
+        amin = _f32(np.broadcast_to(np.asarray(a_min, np.float64), (A,)), dev)
+        amax = _f32(np.broadcast_to(np.asarray(a_max, np.float64), (A,)), dev)
+        w = torch.empty((B, num_modal), dtype=torch.float32, device=dev)
+        mu = torch.empty((B, num_modal, A), dtype=torch.float32, device=dev)
+        var = torch.empty((B, num_modal, A), dtype=torch.float32, device=dev)
+        best = torch.empty((B, A), dtype=torch.float32, device=dev)
+        idx = torch.empty((iters, B, top_m), dtype=torch.int64, device=dev) if want_idx else None
+        check(self.eng.lib.rlc_cem(self.eng.h, C.byref(self._desc), _ptr(s), B, N, iters, int(top_m),
+                                   int(num_modal), _ptr(u0), _ptr(noise), _ptr(comp_u), _ptr(amin),
+                                   _ptr(amax), _ptr(w), _ptr(mu), _ptr(var), _ptr(best), _ptr(idx),
+                                   _stream()))
+        return w, mu, var, best, idx
+
+
+class CriticOptimizer:
+    """Adam state for one critic + the optional data-parallel gradient all-reduce
+    (critic regression step, rows a15/a16)."""
+
+    def __init__(self, critic: Critic, lr: float, variant: int = ADAM_TORCH, target: Optional[Critic] = None,
+                 tau: float = 0.0, process_group=None):
+        self.critic, self.lr, self.variant = critic, float(lr), int(variant)
+        self.m = torch.zeros_like(critic.theta)
+        self.v = torch.zeros_like(critic.theta)
+        self.t = 0
+        self.target, self.tau = target, float(tau)
+        self.pg = process_group
+
+    def step(self, s, a, y, world_size: int = 1):
+        """One regression step on this rank's shard of the batch. With world_size>1 the per-rank
+        gradients are already scaled by 1/B_total, so a SUM all-reduce reproduces the reference's
+        batch mean."""
+        B = s.shape[0]
+        grad, loss, q = self.critic.grads(s, a, y, b_total=B * world_size)
+        if world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.pg)
+        self.t += 1
+        self.critic.eng.adam_step(self.critic.theta, grad, self.m, self.v, self.t, self.lr, self.variant,
+                                  target=None if self.target is None else self.target.theta, tau=self.tau)
+        return loss, q

@@ -1,0 +1,66 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/rlc.h declares (no
+compute calls without a GPU), and the pure-host helpers behave."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "rlc.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(rlc_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    from rlcontrol_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in rlc.h but not exported by librlc.so"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == set(names)
+    assert lib.rlc_version() == 100
+
+
+def test_host_only_entry_points():
+    from rlcontrol_b200 import _lib
+    lib = _lib.load()
+    assert lib.rlc_status_string(0) == b"ok"
+    assert b"invalid" in lib.rlc_status_string(-1)
+    # theta layout arithmetic (no device needed)
+    n_tin = lib.rlc_theta_numel(_lib.TIN, 17, 6, 400, 300)
+    assert n_tin == 23 * 400 + 400 + 400 * 300 + 300 + 300 + 1 == 130201
+    n_tmid = lib.rlc_theta_numel(_lib.TMID, 1, 1, 200, 200)
+    assert n_tmid == 200 + 200 + 201 * 200 + 200 + 200 + 1
+    off = (ctypes.c_int64 * 6)()
+    assert lib.rlc_theta_offsets(_lib.TMID, 1, 1, 200, 200, off) == 0
+    assert list(off) == [0, 200, 400, 400 + 201 * 200, 400 + 201 * 200 + 200, 400 + 201 * 200 + 400]
+    assert lib.rlc_theta_numel(7, 1, 1, 1, 1) == -1
+    assert lib.rlc_theta_offsets(_lib.TIN, 0, 1, 1, 1, off) == -1
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import rlcontrol_b200 as rb
+    with pytest.raises(rb.RlcError):
+        rb.Engine(0)
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under rlcontrol_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "rlcontrol_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn

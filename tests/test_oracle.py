@@ -1,0 +1,232 @@
+"""CPU tests: the oracle restatement against the committed golden vectors (generated from the
+reference's own classes by oracle/make_golden.py) and internal consistency."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import oracle_np as onp
+
+
+def _params(g, prefix=""):
+    return [g[prefix + k] for k in ("W1", "b1", "W2", "b2", "W3", "b3")]
+
+
+@pytest.mark.parametrize("name", ["tin_cfg1.npz", "tin_400_300.npz", "tin_cfg4_exact.npz"])
+def test_tin_forward_matches_reference_softqnetwork(name):
+    g = golden(name)
+    q = onp.tin_eval(g["s"], g["a"], _params(g))
+    assert q.shape == g["q"].shape
+    np.testing.assert_allclose(q, g["q"], rtol=2e-5, atol=2e-6)
+
+
+def test_trueq_checkpoints_reproduce_reward():
+    g = golden("trueq.npz")
+    grid = g["grid"]
+    bounds = {"eq_var1": 0.05, "eq_var2": 0.08, "eq_var3": 0.11, "uneq_var1": 0.05, "uneq_var2": 0.11}
+    for v, bound in bounds.items():
+        p = [g[f"{v}_{k}"] for k in ("W1", "b1", "W2", "b2", "W3", "b3")]
+        assert p[2].shape == (201, 200)            # rows 0..199 <-> h1, row 200 <-> action
+        q = onp.tmid_forward(np.zeros((grid.size, 1), np.float32), grid[:, None], *p)
+        assert np.max(np.abs(q - g[f"{v}_reward"])) < bound
+        # concat order matters: swapping the action row to the front must break the fit
+        W2s = np.concatenate([p[2][200:], p[2][:200]], axis=0)
+        qs = onp.tmid_forward(np.zeros((grid.size, 1), np.float32), grid[:, None], p[0], p[1], W2s, *p[3:])
+        assert np.max(np.abs(qs - g[f"{v}_reward"])) > 2 * bound
+
+
+def test_tmid_hoisted_equals_naive():
+    rng = np.random.RandomState(0)
+    S, A, H1, H2, B, N = 5, 3, 40, 30, 7, 33
+    p = [rng.randn(S, H1) * .3, rng.randn(H1) * .1, rng.randn(H1 + A, H2) * .3, rng.randn(H2) * .1,
+         rng.randn(H2, 1), rng.randn(1)]
+    s = rng.randn(B, S) * 3
+    smin, smax = -np.ones(S), np.ones(S) * 2
+    for a in (rng.randn(N, A), rng.randn(B, N, A)):
+        q0 = onp.tmid_eval(s, a, p, smin, smax, dtype=np.float64)
+        q1 = onp.tmid_eval_hoisted(s, a, p, smin, smax, dtype=np.float64)
+        np.testing.assert_allclose(q0, q1, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("name,kind", [("fkl_update.npz", "fkl"), ("rkl_update.npz", "rkl")])
+def test_policy_loss_matches_reference_update(name, kind):
+    g = golden(name)
+    p = _params(g, "pre_")
+    q = onp.tin_eval(g["s"].astype(np.float32), g["grid_a"], p)
+    np.testing.assert_allclose(q, g["grid_q"], rtol=2e-5, atol=2e-5)
+    if kind == "fkl":
+        loss, per_state, boltz, dlogp = onp.fkl_reduce(g["grid_q"], g["grid_w"], g["logp"], float(g["alpha"]))
+        assert abs(boltz @ g["grid_w"] - 1).max() < 1e-5
+    else:
+        loss, per_state, dlogp = onp.rkl_reduce(g["grid_q"], g["v"], g["grid_w"], g["logp"], float(g["alpha"]))
+    assert abs(loss - float(g["pi_loss"])) <= 2e-5 * max(1.0, abs(float(g["pi_loss"])))
+    # gradient wrt logp by central differences (fp64)
+    lp = g["logp"].astype(np.float64)
+    eps = 1e-6
+    for (b, n) in [(0, 0), (3, 17), (31, 61)]:
+        d = np.zeros_like(lp)
+        d[b, n] = eps
+        if kind == "fkl":
+            f = lambda l: onp.fkl_reduce(g["grid_q"], g["grid_w"], l, float(g["alpha"]), dtype=np.float64)[0]
+        else:
+            f = lambda l: onp.rkl_reduce(g["grid_q"], g["v"], g["grid_w"], l, float(g["alpha"]), dtype=np.float64)[0]
+        fd = (f(lp + d) - f(lp - d)) / (2 * eps)
+        assert abs(fd - dlogp[b, n]) <= 1e-4 * max(1e-3, abs(fd))
+
+
+def test_critic_step_matches_reference_adam():
+    """a15: one MSE/Adam step reproduces the q_net parameters after the reference update."""
+    g = golden("fkl_update.npz")
+    pre = [g["pre_" + k].astype(np.float64) for k in ("W1", "b1", "W2", "b2", "W3", "b3")]
+    post = [g["post_" + k] for k in ("W1", "b1", "W2", "b2", "W3", "b3")]
+    loss, grads = onp.tin_mse_grads(g["s"].astype(np.float32), g["a"].astype(np.float32), g["y"], pre)
+    assert abs(loss - float(g["q_loss"])) < 1e-4 * float(g["q_loss"])
+    for p0, gr, p1 in zip(pre, grads, post):
+        new, _, _ = onp.adam_step_torch(p0, gr, np.zeros_like(p0), np.zeros_like(p0), 1, float(g["lr"]))
+        np.testing.assert_allclose(new, p1, rtol=0, atol=2e-6)
+
+
+def test_mse_grads_finite_difference():
+    rng = np.random.RandomState(1)
+    S, A, H1, H2, B = 4, 2, 9, 7, 6
+    s, a, y = rng.randn(B, S), rng.randn(B, A), rng.randn(B)
+    tin = [rng.randn(H1, S + A), rng.randn(H1), rng.randn(H2, H1), rng.randn(H2), rng.randn(1, H2), rng.randn(1)]
+    tmid = [rng.randn(S, H1), rng.randn(H1), rng.randn(H1 + A, H2), rng.randn(H2), rng.randn(H2, 1), rng.randn(1)]
+    for fn, p in ((onp.tin_mse_grads, tin), (onp.tmid_mse_grads, tmid)):
+        loss, grads = fn(s, a, y, p)
+        for i in range(6):
+            idx = tuple(rng.randint(0, d) for d in p[i].shape)
+            pp = [x.copy() for x in p]; pm = [x.copy() for x in p]
+            pp[i][idx] += 1e-6; pm[i][idx] -= 1e-6
+            fd = (fn(s, a, y, pp)[0] - fn(s, a, y, pm)[0]) / 2e-6
+            assert abs(fd - grads[i][idx]) < 1e-5 * max(1.0, abs(fd))
+
+
+def test_dq_da_finite_difference():
+    rng = np.random.RandomState(2)
+    S, A, H1, H2, R = 4, 3, 11, 8, 5
+    s, a = rng.randn(R, S), rng.randn(R, A)
+    tin = [rng.randn(H1, S + A), rng.randn(H1), rng.randn(H2, H1), rng.randn(H2), rng.randn(1, H2), rng.randn(1)]
+    tmid = [rng.randn(S, H1), rng.randn(H1), rng.randn(H1 + A, H2), rng.randn(H2), rng.randn(H2, 1), rng.randn(1)]
+    g = onp.tin_dq_da(s, a, tin)
+    g2 = onp.tmid_dq_da(s, a, tmid)
+    for i in range(A):
+        d = np.zeros_like(a); d[:, i] = 1e-6
+        fd = (onp.tin_forward(s, a + d, *tin, dtype=np.float64) - onp.tin_forward(s, a - d, *tin, dtype=np.float64)) / 2e-6
+        np.testing.assert_allclose(g[:, i], fd, rtol=1e-5, atol=1e-6)
+        fd2 = (onp.tmid_forward(s, a + d, *tmid, dtype=np.float64) - onp.tmid_forward(s, a - d, *tmid, dtype=np.float64)) / 2e-6
+        np.testing.assert_allclose(g2[:, i], fd2, rtol=1e-5, atol=1e-6)
+
+
+def test_clenshaw_curtis():
+    g = golden("cc.npz")
+    x, w = onp.clenshaw_curtis(64)
+    np.testing.assert_allclose(x, g["x64"], atol=0)
+    np.testing.assert_allclose(w, g["w64"], atol=0)
+    xf, wf = onp.clenshaw_curtis_fast(64)
+    np.testing.assert_allclose(xf, x, atol=1e-15)
+    np.testing.assert_allclose(wf, w, atol=1e-14)
+    assert abs(w.sum() - 2.0) < 1e-12
+    # n-point CC integrates polynomials of degree <= n-1 exactly
+    for deg in (0, 2, 10, 40, 62):
+        exact = 2.0 / (deg + 1)
+        assert abs(np.sum(w * x ** deg) - exact) < 1e-12
+    # the reference drops both endpoints: the remaining weights sum to just under 2
+    assert abs(w[1:-1].sum() - 1.9995) < 1e-3
+    x2, w2 = onp.clenshaw_curtis_fast(1026)
+    assert abs(w2[1:-1].sum() - 1.999998) < 1e-5
+    acts, ww = onp.intg_grid_1d(64, 2.0)
+    assert acts.shape == (62, 1) and ww.shape == (62,) and acts.dtype == np.float32
+    assert np.all(np.abs(acts) < 2.0)
+
+
+def test_gmm_refit_matches_sklearn_bounded():
+    g = golden("gmm.npz")
+    for c in range(g["X"].shape[0]):
+        k, A = int(g["k"][c]), int(g["A"][c])
+        X = g["X"][c][:k, :A]
+        w, mu, cv, nit = onp.gmm_fit_bounded(X, g["resp0"][c][:k])
+        assert nit == int(g["n_iter"][c])
+        np.testing.assert_allclose(w, g["weights"][c], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(mu, g["means"][c][:, :A], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(cv, g["covs"][c][:, :A], rtol=1e-9, atol=1e-12)
+        assert np.all(np.abs(mu) <= 2) and np.all(cv >= np.exp(-2) - 1e-15) and np.all(cv <= np.exp(2) + 1e-15)
+
+
+def test_gmm_one_component_closed_form():
+    rng = np.random.RandomState(3)
+    X = rng.randn(6, 4) * 3
+    w, mu, cv = onp.gmm_fit_1comp(X)
+    w2, mu2, cv2, nit = onp.gmm_fit_bounded(X, np.ones((6, 1)))
+    assert nit == 2
+    np.testing.assert_allclose(mu, mu2, atol=1e-12)
+    np.testing.assert_allclose(cv, cv2, atol=1e-12)
+    m0 = X.mean(0)
+    np.testing.assert_allclose(mu[0], np.clip(m0, -2, 2), atol=1e-12)
+    np.testing.assert_allclose(cv[0], np.clip((X * X).mean(0) - m0 ** 2 + 1e-6, np.exp(-2), np.exp(2)), atol=1e-9)
+
+
+def test_topk_and_stats_semantics():
+    q = np.array([[1., 3., 3., 2., -1.], [0., 0., 0., 0., 0.]], np.float32)
+    idx = onp.topk_desc(q, 3)
+    assert idx.tolist() == [[2, 1, 3], [4, 3, 2]]       # ties: larger index first
+    am, mx, mean = onp.argmax_max_mean(q)
+    assert am.tolist() == [1, 0] and mx.tolist() == [3., 0.]
+    rng = np.random.RandomState(4)
+    q = rng.randn(16, 120).astype(np.float32)
+    idx = onp.topk_desc(q, 6)
+    for b in range(16):
+        assert idx[b].tolist() == list(q[b].argsort()[::-1][:6])     # no ties -> same as reference
+    el = onp.gather_elites(rng.randn(16, 120, 2), idx)
+    assert el.shape == (16, 6, 2)
+
+
+def test_sql_soft_value():
+    rng = np.random.RandomState(5)
+    q = rng.randn(8, 30).astype(np.float32) * 5
+    v = onp.sql_soft_value(q, 2)
+    ref = np.log(np.exp(q.astype(np.float64)).sum(1)) - np.log(30) + 2 * np.log(2)
+    np.testing.assert_allclose(v, ref, rtol=1e-5)
+
+
+def test_sample_n_k_matches_reference_scheme():
+    for n, k in ((10, 5), (1000, 32), (100000, 32), (50, 0)):
+        r1 = np.random.RandomState(7)
+        idx = onp.sample_n_k(r1, n, k)
+        assert len(idx) == k and len(set(idx.tolist())) == k and all(0 <= i < n for i in idx)
+        # same stream of draws as the reference algorithm (custom_collections.py:107-131)
+        r2 = np.random.RandomState(7)
+        if k and 3 * k >= n:
+            assert idx.tolist() == r2.choice(n, k, replace=False).tolist()
+    with pytest.raises(ValueError):
+        onp.sample_n_k(np.random.RandomState(0), 3, 5)
+
+
+def test_adam_variants_and_soft_update():
+    p, g = np.array([1.0, -2.0]), np.array([0.5, -0.25])
+    m = v = np.zeros(2)
+    pt, _, _ = onp.adam_step_torch(p, g, m, v, 1, 1e-3)
+    ptf, _, _ = onp.adam_step_tf(p, g, m, v, 1, 1e-3)
+    np.testing.assert_allclose(pt, p - 1e-3 * np.sign(g), atol=1e-9)
+    np.testing.assert_allclose(ptf, pt, atol=1e-9)          # differ only through eps placement
+    assert not np.array_equal(pt, ptf)
+    t = onp.soft_update(np.zeros(2), np.ones(2), 0.01)
+    np.testing.assert_allclose(t, 0.01)
+
+
+def test_cem_runs_and_respects_bounds():
+    rng = np.random.RandomState(6)
+    S, A, H1, H2, B, N = 3, 2, 16, 12, 4, 64
+    p = [rng.randn(S, H1) * .5, rng.randn(H1) * .1, rng.randn(H1 + A, H2) * .5, rng.randn(H2) * .1,
+         rng.randn(H2, 1), rng.randn(1)]
+    s = rng.randn(B, S)
+    u0 = rng.uniform(size=(B, N, A))
+    noise = rng.randn(2, B, N, A)
+    cu = rng.uniform(size=(2, B, N))
+    qf = lambda st, ac: onp.tmid_eval(st, ac, p)
+    for M in (1, 2):
+        W, Mu, Cv, idx = onp.cem_iterate(qf, s, u0, noise, cu, 6, M, -np.ones(A), np.ones(A))
+        assert W.shape == (B, M) and np.allclose(W.sum(1), 1, atol=1e-9)
+        assert np.all(np.abs(Mu) <= 2) and np.all(Cv >= np.exp(-2) - 1e-12) and np.all(Cv <= np.exp(2) + 1e-12)
+        assert idx.shape == (3, B, 6)
+        act = onp.cem_final_action(W, Mu)
+        assert act.shape == (B, A)
