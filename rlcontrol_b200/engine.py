@@ -235,6 +235,8 @@ class Critic:
             raise ValueError(f"action dim {a.shape[-1]} != {self.A}")
         prec = PREC_BY_NAME[precision] if isinstance(precision, str) else int(precision)
         q = torch.empty((B, N), dtype=torch.float32, device=dev)
+        if B * N == 0:
+            return q
         check(self.eng.lib.rlc_critic_eval(self.eng.h, C.byref(self._desc), _ptr(s), B, _ptr(a), N,
                                            mode, prec, _ptr(q), _stream()))
         return q
