@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py -- sampled-action critic evaluation throughput on B200 (BASELINE.json's metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # the reference-equivalent CPU path
+
+Workload (config.workload = "cfg4"): ForwardKL large batch, per GPU B=4096 states x N=1024 grid
+actions, S=17, A=6, 400-300 T-in critic (BASELINE.json configs[3], the shape the target is quoted
+on).  One *step* = one pass of the hot path over one replay minibatch:
+    K1  rlc_critic_eval   q[B,N] = Q(s_b, a_n)   (tcgen05 kernel, fp16 operands / fp32 accumulate)
+    K3  rlc_reduce_fkl    per-state Boltzmann weights + policy loss over the grid
+metric = (s,a) Q-evaluations per second, whole job (all ranks).  States shard over ranks with no
+data-path collective (weak scaling: every rank gets its own B=4096 minibatch).
+
+value : inputs already resident in HBM, CUDA events on the launching stream around exactly K steps.
+e2e   : the same step through the public API with HOST (pinned) inputs: H2D copy of the states and
+        the policy log-probabilities, D2H read of the per-state loss, inside the timed region.
+roofline : dominant kernel = K1; achieved = algorithmic flops / its mean launch time
+        measured with CUDA events in this process; peak from MEASURED_PEAKS.json.
+cpu_baseline / --impl reference : oracle/oracle_torch.py (the reference's torch-CPU arithmetic,
+        materialised stacks) on all host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOAD = dict(workload="cfg4", B_per_gpu=4096, N=1024, S=17, A=6, H1=400, H2=300, topology="T-in",
+                reduction="forward_kl", action_layout="shared_grid[N,A]", entropy_scale=0.1)
+RING = 10                     # rotating input/output sets: 10 x (q 16.8 MB + logp 16.8 MB) > 126 MB L2
+METRIC = "sampled_q_evals_per_sec"
+UNIT = "Q-evals/s"
+
+
+def algorithmic_flops(B, N, S, A, H1, H2):
+    """F = B*2*S*H1 + B*N*2*(A*H1 + H1*H2 + H2)."""
+    return B * 2 * S * H1 + B * N * 2 * (A * H1 + H1 * H2 + H2)
+
+
+def make_params(rng, S, A, H1, H2):
+    """torch nn.Linear default init + U(+-3e-3) last layer scaled x100 ("trained-like")."""
+    k1, k2 = 1 / np.sqrt(S + A), 1 / np.sqrt(H1)
+    u = lambda k, *sh: rng.uniform(-k, k, sh).astype(np.float32)
+    return [u(k1, H1, S + A), u(k1, H1), u(k2, H2, H1), u(k2, H2), u(0.3, 1, H2), u(0.3, 1)]
+
+
+def make_inputs(rng, B, N, S, A):
+    from oracle import oracle_np as onp            # grid weights only (Clenshaw-Curtis interior)
+    s = np.clip(rng.randn(B, S), -10, 10).astype(np.float32)
+    a = rng.uniform(-1, 1, (N, A)).astype(np.float32)
+    _, w = onp.intg_grid_1d(N + 2, 1.0)
+    logp = (rng.randn(B, N) * 0.5 - 1).astype(np.float32)
+    return s, a, np.asarray(w, np.float32), logp
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self._stop = index, [], set(), threading.Event()
+        self.max_mhz, self.thread = None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                    nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                mask = int(get(self.h))
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": int(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference's torch-CPU path)
+# ---------------------------------------------------------------------------------------------
+def cpu_arm(params, s, a, w, logp, entropy_scale, budget_s=12.0, b_sample=256, max_reps=40, warmup=1):
+    """Times oracle_torch.fkl_sampled_step on the first b_sample states (a bounded sample of the
+    workload; the full B=4096 stack would need 12 GB of fp32 activations on the host)."""
+    from oracle import oracle_torch as ot
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    net = ot.SoftQNetworkPort(*params)
+    ts, ta, tw, tl = (torch.as_tensor(x) for x in (s[:b_sample], a, w, logp[:b_sample]))
+    for _ in range(warmup):
+        ot.fkl_sampled_step(net, ts, ta, tw, tl, entropy_scale)
+    times, t_end = [], time.perf_counter() + budget_s
+    while len(times) < max_reps and (time.perf_counter() < t_end or len(times) < 3):
+        t0 = time.perf_counter()
+        ot.fkl_sampled_step(net, ts, ta, tw, tl, entropy_scale)
+        times.append(time.perf_counter() - t0)
+    med = float(np.median(times))
+    evals = b_sample * a.shape[0]
+    return {"value": evals / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"first {b_sample} of {s.shape[0]} states x N={a.shape[0]} ({evals} rows), "
+                      f"median of {len(times)} reps, oracle/oracle_torch.py (reference torch-CPU arithmetic)",
+            "ms_per_sample": med * 1e3}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference-equivalent CPU path on this box's host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    W = WORKLOAD
+    rng = np.random.RandomState(0)
+    params = make_params(rng, W["S"], W["A"], W["H1"], W["H2"])
+    s, a, w, logp = make_inputs(rng, W["B_per_gpu"], W["N"], W["S"], W["A"])
+    from oracle import oracle_torch as ot
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    net = ot.SoftQNetworkPort(*params)
+    b_sample = 256
+    ts, ta, tw, tl = (torch.as_tensor(x) for x in (s[:b_sample], a, w, logp[:b_sample]))
+    for _ in range(max(args.warmup, 1)):
+        ot.fkl_sampled_step(net, ts, ta, tw, tl, W["entropy_scale"])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ot.fkl_sampled_step(net, ts, ta, tw, tl, W["entropy_scale"])
+    dt = time.perf_counter() - t0
+    evals = b_sample * W["N"]
+    value = evals * args.steps / dt
+    sample = (f"each step = first {b_sample} of {W['B_per_gpu']} states x N={W['N']} ({evals} rows) of the cfg4 "
+              f"minibatch through oracle/oracle_torch.py (the reference's torch-CPU arithmetic, materialised stacks)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": dict(W, sample_states_per_step=b_sample),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_b200(args, rank, local_rank, world):
+    import torch.distributed as dist
+    import rlcontrol_b200 as rb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = WORKLOAD
+    B, N, S, A, H1, H2 = W["B_per_gpu"], W["N"], W["S"], W["A"], W["H1"], W["H2"]
+    alpha = W["entropy_scale"]
+    rng = np.random.RandomState(0)
+    params = make_params(rng, S, A, H1, H2)                       # identical weights on every rank
+    rng_in = np.random.RandomState(1000 + rank)                   # each rank: its own minibatch shard
+    s_np, a_np, w_np, logp_np = make_inputs(rng_in, B, N, S, A)
+    a_np, w_np = make_inputs(np.random.RandomState(1), 1, N, S, A)[1:3]   # the grid is shared by all ranks
+
+    eng = rb.Engine(local_rank)
+    critic = rb.Critic(eng, rb.TIN, S, A, H1, H2).load(*params, rb.LAYOUT_OUT_IN)
+    prec = args.precision
+    t = lambda x: torch.as_tensor(x, device=dev)
+    a_d, w_d = t(a_np), t(w_np)
+    # rotating sets so that consecutive steps never find their inputs/outputs in L2
+    s_ring = [t(np.roll(s_np, i, axis=0).copy()) for i in range(RING)]
+    logp_ring = [t(np.roll(logp_np, i, axis=0).copy()) for i in range(RING)]
+    q_ring = [torch.empty((B, N), dtype=torch.float32, device=dev) for _ in range(RING)]
+
+    def step(i):
+        j = i % RING
+        q = critic.eval_into(s_ring[j], a_d, q_ring[j], prec)
+        loss_b, _, _ = eng.fkl(q, w_d, logp_ring[j], alpha, want_boltz=False, want_grad=False)
+        return loss_b
+
+    # ---- parity gate on this rank's first states (rows checked against the CPU oracle) ----
+    from oracle import oracle_np as onp
+    loss0 = step(0)
+    torch.cuda.synchronize()
+    if eng.umma_error() != 0:
+        raise SystemExit("bench.py: tcgen05 kernel raised its error flag")
+    rows = np.arange(0, B, B // 8)[:8]
+    q_ref = onp.tin_eval(s_np[rows], a_np, params, dtype=np.float64)
+    q_gpu = q_ring[0][torch.as_tensor(rows, device=dev)].cpu().numpy()
+    den = np.maximum(np.abs(q_ref), np.sqrt((q_ref ** 2).mean(1, keepdims=True)))
+    err = np.abs(q_gpu - q_ref) / den
+    parity = {"rows_checked": int(q_ref.size), "rel_err_rms": float(np.sqrt((err ** 2).mean())),
+              "rel_err_max": float(err.max())}
+    if prec in ("fp16", "bf16"):
+        q_rnd = onp.tin_eval_rounded(s_np[rows], a_np, params, prec)
+        parity["vs_stated_arithmetic_max"] = float((np.abs(q_gpu - q_rnd) / den).max())
+        ok = parity["vs_stated_arithmetic_max"] < 5e-5
+    else:
+        ok = parity["rel_err_max"] < 2e-5
+    _, per_state, _, _ = onp.fkl_reduce(q_gpu, w_np, logp_np[rows], alpha, dtype=np.float64)
+    ok = ok and np.allclose(loss0.cpu().numpy()[rows], per_state, rtol=1e-3, atol=1e-5)
+    if not ok:
+        raise SystemExit(f"bench.py: parity gate failed: {parity}")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: exactly K steps between two events ----
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    launches0 = eng.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        ev0.record()
+        for i in range(args.steps):
+            step(args.warmup + i)
+        ev1.record()
+        barrier()
+    launches = eng.launches - launches0
+    ms_total = ev0.elapsed_time(ev1)
+
+    # ---- dominant kernel alone (roofline): K1 launches only, CUDA events on the same stream ----
+    k1_reps = max(args.steps, 10)
+    for i in range(3):
+        critic.eval_into(s_ring[i % RING], a_d, q_ring[i % RING], prec)
+    torch.cuda.synchronize()
+    ev0.record()
+    for i in range(k1_reps):
+        critic.eval_into(s_ring[i % RING], a_d, q_ring[i % RING], prec)
+    ev1.record()
+    torch.cuda.synchronize()
+    k1_ms = ev0.elapsed_time(ev1) / k1_reps
+
+    # ---- end to end through the public API: pinned host inputs in, host result out ----
+    s_host = [torch.as_tensor(np.roll(s_np, i, axis=0).copy()).pin_memory() for i in range(2)]
+    logp_host = [torch.as_tensor(np.roll(logp_np, i, axis=0).copy()).pin_memory() for i in range(2)]
+    loss_host = torch.empty((B,), dtype=torch.float32).pin_memory()
+    s_dev, logp_dev = torch.empty_like(s_ring[0]), torch.empty_like(logp_ring[0])
+
+    def e2e_step(i):
+        s_dev.copy_(s_host[i & 1], non_blocking=True)
+        logp_dev.copy_(logp_host[i & 1], non_blocking=True)
+        q = critic.eval_into(s_dev, a_d, q_ring[i % RING], prec)
+        loss_b, _, _ = eng.fkl(q, w_d, logp_dev, alpha, want_boltz=False, want_grad=False)
+        loss_host.copy_(loss_b, non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the caller reads the loss every step
+        return float(loss_host[0])
+
+    for i in range(args.warmup):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    ev1.record()
+    barrier()
+    e2e_ms = max(ev0.elapsed_time(ev1), 0.0)
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    h2d = s_dev.numel() * 4 + logp_dev.numel() * 4
+    d2h = loss_host.numel() * 4
+
+    # ---- secondary: critic regression update (a15/a16) incl. the NCCL grad all-reduce when N>1 ----
+    a_reg = t(rng_in.uniform(-1, 1, (B, A)).astype(np.float32))
+    y_reg = t(rng_in.randn(B).astype(np.float32))
+    opt = rb.CriticOptimizer(rb.Critic(eng, rb.TIN, S, A, H1, H2).load(*params, rb.LAYOUT_OUT_IN), lr=1e-3)
+    for _ in range(3):
+        opt.step(s_ring[0], a_reg, y_reg, world_size=world)
+    barrier()
+    upd_reps = 20
+    ev0.record()
+    for _ in range(upd_reps):
+        opt.step(s_ring[0], a_reg, y_reg, world_size=world)
+    ev1.record()
+    barrier()
+    upd_ms = ev0.elapsed_time(ev1) / upd_reps
+
+    # ---- max over ranks ----
+    tm = torch.tensor([ms_total, e2e_ms, k1_ms, upd_ms, e2e_wall_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms, k1_ms, upd_ms, e2e_wall_ms = [float(x) for x in tm.cpu()]
+
+    if rank == 0:
+        peaks, peak_src = {}, "fallback"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+            peak_src = "measured"
+        except Exception:
+            pass
+        peak_tf = float(peaks.get("bf16_tflops", 1590.0))
+        flops = algorithmic_flops(B, N, S, A, H1, H2)
+        achieved = flops / (k1_ms * 1e-3) / 1e12
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        evals_total = world * B * N * args.steps
+        line = {
+            "metric": METRIC, "value": evals_total / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp16": "f16 operands, f32 accumulate (tcgen05 kind::f16)",
+                      "bf16": "bf16 operands, f32 accumulate (tcgen05 kind::f16)",
+                      "fp32": "f32"}[prec],
+            "data": "synthetic",
+            "config": dict(W, global_states=B * world, precision=prec,
+                           l2="rotating %d input/output sets (%.0f MB > 126 MB L2), no flush kernels in the timed region"
+                              % (RING, RING * 2 * B * N * 4 / 1e6),
+                           parallelism=f"states sharded over {world} rank(s), no data-path collective"),
+            "clocks": clocks.summary(),
+            "e2e": {"value": evals_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                    "wall_ms_per_step": e2e_wall_ms / args.steps,
+                    "api": "Critic.eval_into + Engine.fkl on pinned host states/logp, loss read back every step"},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "k_critic_umma (K1 fused T-in critic eval)", "bound": "tensor",
+                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                         "peak_source": f"{peak_src} bf16_tflops (burst; sustained "
+                                        f"{peaks.get('bf16_tflops_sustained', 1400.0)})",
+                         "flops_per_launch": flops, "ms_per_launch": k1_ms, "traffic": traffic},
+            "parity": parity,
+            "extra": {"critic_update_ms": upd_ms, "critic_updates_per_sec": 1e3 / upd_ms,
+                      "critic_update_rows_per_rank": B,
+                      "critic_update_allreduce": "nccl sum of theta_Q grads" if world > 1 else "none (1 rank)"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_arm(params, s_np, a_np, w_np, logp_np, alpha)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -70,6 +70,39 @@ def tin_eval(s, a, params, dtype=F32):
     return q.reshape(B, N)
 
 
+def round_operand(x, kind):
+    """Round-to-nearest-even of an fp64/fp32 array to the tensor-core operand type ``kind``
+    ('fp16' saturating at +-65504, or 'bf16'), returned as float64.  Used to restate the
+    *stated arithmetic* of the tcgen05 path (fp16/bf16 operands, fp32 accumulate)."""
+    x = np.asarray(x, np.float32)
+    if kind == "fp16":
+        return np.clip(x, -65504.0, 65504.0).astype(np.float16).astype(np.float64)
+    if kind == "bf16":
+        u = x.view(np.uint32).astype(np.uint64)
+        u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+        return u.astype(np.uint32).view(np.float32).astype(np.float64)
+    raise ValueError(kind)
+
+
+def tin_eval_rounded(s, a, params, kind="fp16"):
+    """T-in evaluation with the operand rounding of the tensor-core path made explicit (fp64
+    accumulate): x=[s;a], W1, b1 (folded as a ones column), the ReLU'd layer-1 activations and W2
+    are rounded to ``kind``; b2, W3, b3 and all accumulation stay wide.  The CUDA kernel must
+    match THIS to ~1e-5 (it does exactly this arithmetic with fp32 accumulators); the distance
+    of this function from ``tin_eval(..., float64)`` is the precision cost of the operand type."""
+    W1, b1, W2, b2, W3, b3 = [np.asarray(p, np.float64) for p in params]
+    s = np.asarray(s)
+    a = np.asarray(a)
+    B = s.shape[0]
+    N = a.shape[0] if a.ndim == 2 else a.shape[1]
+    x = np.concatenate([stack_state_major(s, N), stack_actions(a, B)], axis=1)
+    r = lambda z: round_operand(z, kind)
+    h1 = np.maximum(r(x) @ r(W1).T + r(b1), 0)
+    h2 = np.maximum(r(h1) @ r(W2).T + b2, 0)
+    q = h2 @ W3.reshape(-1) + b3.reshape(())
+    return q.reshape(B, N)
+
+
 def clip_state(s, smin, smax, dtype=F32):
     """Input "normalisation" of the TF graphs: ``RunningMeanStd`` mean/var are baked in as the
     constants 0/1 (utils/running_mean_std.py:4-7,31-32; base_network_manager.py:37) so the only

@@ -241,6 +241,23 @@ class Critic:
                                            mode, prec, _ptr(q), _stream()))
         return q
 
+    def eval_into(self, s: torch.Tensor, a: torch.Tensor, q_out: torch.Tensor, precision="auto") -> torch.Tensor:
+        """Allocation-free variant of :meth:`eval` for steady-state loops: ``s``, ``a`` and
+        ``q_out`` [B,N] are contiguous fp32 tensors already on this engine's device."""
+        for x in (s, a, q_out):
+            if x.device != self.eng.device or x.dtype != torch.float32 or not x.is_contiguous():
+                raise ValueError("eval_into needs contiguous fp32 tensors on the engine's device")
+        B = s.shape[0]
+        mode, N = (ACT_SHARED, a.shape[0]) if a.dim() == 2 else (ACT_PER_STATE, a.shape[1])
+        if s.shape[1] != self.S or a.shape[-1] != self.A or tuple(q_out.shape) != (B, N) or \
+                (a.dim() == 3 and a.shape[0] != B):
+            raise ValueError("eval_into: shape mismatch")
+        prec = PREC_BY_NAME[precision] if isinstance(precision, str) else int(precision)
+        if B * N:
+            check(self.eng.lib.rlc_critic_eval(self.eng.h, C.byref(self._desc), _ptr(s), B, _ptr(a), N,
+                                               mode, prec, _ptr(q_out), _stream()))
+        return q_out
+
     def eval_grad(self, s, a):
         """T-mid only: (q [B,N], dq/da [B,N,A]) without materialising the stack."""
         dev = self.eng.device

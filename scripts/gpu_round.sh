@@ -1,0 +1,22 @@
+#!/bin/bash
+# One gpurun call: GPU parity tests, smoke, bench (both arms), ncu launch list + one full capture of K1.
+# Usage (from the repo root, on the GPU box): bash scripts/gpu_round.sh [tag]
+TAG=${1:-r01}
+OUT=gpurun_out
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > $OUT/smi_$TAG.csv 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_$TAG.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/smoke_$TAG.log
+timeout 600 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc=$?"
+tail -c 3000 $OUT/bench_$TAG.json
+timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/bench_ref_$TAG.json 2>&1
+if [ "${NCU:-1}" = "1" ]; then
+  CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+  timeout 300 $CMD > $OUT/plain_$TAG.log 2>&1 &&
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_launches_$TAG.log 2>&1
+  echo "ncu launches rc=$?"
+  timeout 300 $CMD > $OUT/plain2_$TAG.log 2>&1 &&
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_critic_umma -s 4 -c 2 -o $OUT/k1_$TAG -f $CMD > $OUT/ncu_full_$TAG.log 2>&1
+  echo "ncu full rc=$?"
+fi
+ls -la $OUT | tail -20

@@ -230,3 +230,49 @@ def test_cem_runs_and_respects_bounds():
         assert idx.shape == (3, B, 6)
         act = onp.cem_final_action(W, Mu)
         assert act.shape == (B, A)
+
+
+# ----------------------------------------------------------------------------- ports timed by bench.py
+@pytest.mark.parametrize("name", ["tin_cfg1.npz", "tin_400_300.npz"])
+def test_torch_port_matches_reference_golden(name):
+    """oracle_torch.SoftQNetworkPort (the CPU arm bench.py times) == the reference's SoftQNetwork."""
+    import torch
+    from oracle import oracle_torch as ot
+    g = golden(name)
+    net = ot.SoftQNetworkPort(*_params(g))
+    s, a = torch.as_tensor(g["s"]), torch.as_tensor(g["a"])
+    B, N = s.shape[0], a.shape[0]
+    q = net(s.unsqueeze(1).repeat(1, N, 1).reshape(-1, s.shape[1]), a.repeat(B, 1, 1).reshape(-1, a.shape[1]))
+    np.testing.assert_allclose(q.reshape(B, N).numpy(), g["q"], rtol=2e-5, atol=2e-6)
+
+
+def test_torch_port_fkl_step_matches_reference_update():
+    import torch
+    from oracle import oracle_torch as ot
+    g = golden("fkl_update.npz")
+    net = ot.SoftQNetworkPort(*_params(g, "pre_"))
+    t = lambda x: torch.as_tensor(np.asarray(x, np.float32))
+    loss_b, q = ot.fkl_sampled_step(net, t(g["s"]), t(g["grid_a"]), t(g["grid_w"]), t(g["logp"]), float(g["alpha"]))
+    np.testing.assert_allclose(q.numpy(), g["grid_q"], rtol=2e-5, atol=2e-5)
+    assert abs(float(loss_b.mean()) - float(g["pi_loss"])) <= 2e-5 * max(1.0, abs(float(g["pi_loss"])))
+
+
+def test_rounded_operand_oracle():
+    """tin_eval_rounded: exact when the operands are representable; otherwise within the stated
+    precision budget of the operand type (same figures test_gpu_parity gates the kernel on)."""
+    from conftest import rel_err
+    g = golden("tin_400_300.npz")
+    p = _params(g)
+    exact = onp.tin_eval(g["s"], g["a"], p, dtype=np.float64)
+    for kind, (rms_b, max_b) in {"fp16": (2e-3, 2e-2), "bf16": (1e-2, 1e-1)}.items():
+        e = rel_err(onp.tin_eval_rounded(g["s"], g["a"], p, kind), exact)
+        assert 1e-6 < np.sqrt((e ** 2).mean()) < rms_b and e.max() < max_b
+    # representable operands -> no rounding anywhere -> equals the exact path
+    rng = np.random.RandomState(0)
+    S, A, H1, H2 = 3, 2, 8, 8
+    ints = lambda *sh: rng.randint(-2, 3, sh).astype(np.float32)
+    p = [ints(H1, S + A), ints(H1), ints(H2, H1), ints(H2), ints(1, H2), ints(1)]
+    s, a = ints(4, S), ints(5, A)
+    np.testing.assert_array_equal(onp.tin_eval_rounded(s, a, p, "bf16"), onp.tin_eval(s, a, p, dtype=np.float64))
+    x = np.array([1.0, 1.0 + 2 ** -11, 1.0 + 3 * 2 ** -11, 70000.0, -1e-8], np.float32)
+    np.testing.assert_array_equal(onp.round_operand(x, "fp16"), [1.0, 1.0, 1.0 + 2 ** -9, 65504.0, -0.0])
