@@ -51,7 +51,6 @@ struct UmmaParams {
   // smem carve (bytes from the 1024-aligned base)
   int sm_w2, sm_w1, sm_x, sm_h1, sm_par, sm_bar, x_stage_bytes, h1_stage_bytes;
   int num_pair_tiles;
-  int variant;  // bit0: swap LBO/SBO roles ; bit1: rank->B-half mapping swapped (debug only)
   int* err;     // device error flag (0 = ok)
 };
 
@@ -91,7 +90,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
@@ -116,7 +115,7 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
                : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() {
@@ -177,19 +176,6 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
-// no-swizzle K-major shared-memory matrix descriptor.
-// kdir_bytes: stride between 8-element K chunks; mn_bytes: stride between 8-row groups.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t kdir_bytes,
-                                              uint32_t mn_bytes, int swap) {
-  const uint32_t lbo = swap ? mn_bytes : kdir_bytes;
-  const uint32_t sbo = swap ? kdir_bytes : mn_bytes;
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version for sm_100
-  return d;                // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
-}
 __device__ __forceinline__ uint32_t make_idesc(int fmt, int M, int N) {
   // c_format F32 (1) @4 ; a_format @7 ; b_format @10 ; a/b K-major (0) ; N>>3 @17 ; M>>4 @24
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) |
@@ -210,15 +196,12 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 }
 template <int PREC>
 __device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
-  if (PREC == RLC_PREC_BF16) {
-    __nv_bfloat162 t = __floats2bfloat162_rn(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
-    return *reinterpret_cast<uint32_t*>(&t);
-  } else {
-    __half2 t = __floats2half2_rn(lo, hi);
-    t = __hmax2(t, __half2half2(__ushort_as_half((unsigned short)0)));
-    t = __hmin2(t, __half2half2(__ushort_as_half((unsigned short)0x7BFF)));
-    return *reinterpret_cast<uint32_t*>(&t);
-  }
+  uint32_t r;  // one F2FP: relu, saturate to the largest finite value, round-to-nearest-even, pack
+  if (PREC == RLC_PREC_BF16)
+    asm("cvt.rn.relu.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else
+    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 
 }  // namespace um
@@ -228,7 +211,7 @@ __device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
 // ------------------------------------------------------------------------------------------
 // barrier slots (8 bytes each) inside sm_bar
 enum {
-  BAR_X_FULL = 0,       // [2]   count 6  (leader)   producers -> MMA
+  BAR_X_FULL = 0,       // [2]   count 6  (leader)   3 producer warps x 2 CTAs -> MMA
   BAR_X_EMPTY = 2,      // [2]   count 1  (both)     MMA commit -> producers
   BAR_L1_FULL = 4,      // [2]   count 1  (both)     MMA commit -> ep1
   BAR_L1_EMPTY = 6,     // [2]   count 8  (leader)   ep1 -> MMA
@@ -238,6 +221,18 @@ enum {
   BAR_L2_EMPTY = 15,    // [2]   count 8  (leader)   ep2 -> MMA (half A, half B)
   BAR_COUNT = 17
 };
+
+namespace um {
+// The shared-memory descriptor of every operand here has the same upper word: SBO = 128 B between
+// 8-row groups, descriptor version 1 (sm_100), no swizzle.  Only the lower word moves.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint64_t desc64(uint32_t lo) {
+  constexpr uint32_t hi = (128u >> 4) | (1u << 14);
+  return ((uint64_t)hi << 32) | (uint64_t)lo;
+}
+}  // namespace um
 
 template <int PREC>
 __global__ void __launch_bounds__(UM_THREADS, 1) k_critic_umma(const UmmaParams P) {
@@ -251,7 +246,6 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_critic_umma(const UmmaParams 
   const uint32_t rank = um::cta_rank();
   const uint32_t pair = um::cluster_id_x();
   const uint32_t npairs = um::num_clusters_x();
-  const int swap = P.variant & 1;
 
   const uint32_t sW2 = base + P.sm_w2, sW1 = base + P.sm_w1, sX = base + P.sm_x,
                  sH1 = base + P.sm_h1, sBar = base + P.sm_bar;
@@ -262,8 +256,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_critic_umma(const UmmaParams 
 
   // ---- prologue: resident weights -> smem, barriers, TMEM ----
   {
-    const int brank = (P.variant & 2) ? (int)(rank ^ 1u) : (int)rank;
-    const uint4* src = reinterpret_cast<const uint4*>(P.blob[brank]);
+    const uint4* src = reinterpret_cast<const uint4*>(P.blob[rank]);
     uint4* dW2 = reinterpret_cast<uint4*>(base_ptr + P.sm_w2);
     const int n2 = (P.off_w1 - P.off_w2) >> 4;
     for (int i = tid; i < n2; i += UM_THREADS) dW2[i] = __ldg(src + (P.off_w2 >> 4) + i);
@@ -296,87 +289,118 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_critic_umma(const UmmaParams 
   um::cluster_sync();
   um::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const float c0 = __ldg(reinterpret_cast<const float*>(P.blob[0] + P.off_c0));
 
   const int ntiles = (P.num_pair_tiles > (int)pair)
                          ? (P.num_pair_tiles - (int)pair + (int)npairs - 1) / (int)npairs
                          : 0;
+  const int nch = P.nch;
   const uint32_t L1COL = (uint32_t)P.H2P;  // TMEM column of L1 accumulator buffer 0
 
   if (warp == 0) {
     // =================================== MMA issuer (leader CTA) ===================================
+    // One warp waits, one elected lane issues.  Everything the issue loop needs is hoisted into
+    // registers (descriptor words, per-K-step increments, instruction descriptors): between two
+    // tcgen05.mma there is one 32-bit add per operand.
     if (rank == 0) {
-      const int fmt = (PREC == RLC_PREC_BF16) ? 1 : 0;
-      const uint32_t lbo_x = 128u * 16u;                 // X / H1 tiles: 128 rows per K chunk
+      const bool issuer = um::elect_one();
+      const uint32_t fmt = (PREC == RLC_PREC_BF16) ? 1u : 0u;
+      const uint32_t lbo_x = 128u * 16u;                        // X / H1 tiles: 128 rows per K chunk
       const uint32_t lbo_w1 = (uint32_t)(P.H1P / 2) * 16u;
       const uint32_t lbo_w2 = (uint32_t)(P.H2P / 2) * 16u;
+      const uint32_t x_lo0 = um::desc_lo(sX, lbo_x), x_lo1 = um::desc_lo(sX + P.x_stage_bytes, lbo_x);
+      const uint32_t h1_lo0 = um::desc_lo(sH1, lbo_x);
+      const uint32_t h1_stage16 = (uint32_t)P.h1_stage_bytes >> 4;
+      const uint32_t w1_lo = um::desc_lo(sW1, lbo_w1), w2_lo = um::desc_lo(sW2, lbo_w2);
+      const uint32_t a_kstep = (2u * lbo_x) >> 4;               // one K=16 step of an A tile
+      const uint32_t w1_kstep = (2u * lbo_w1) >> 4, w2_kstep = (2u * lbo_w2) >> 4;
+      const uint32_t w2_half_off = (uint32_t)(P.NA / 2);        // rows of half B start here (>>4 of bytes)
+      const uint32_t idA = um::make_idesc(fmt, 256, P.NA);
+      const uint32_t idB = um::make_idesc(fmt, 256, P.NB > 0 ? P.NB : 16);
+      const uint32_t id1_full = um::make_idesc(fmt, 256, P.CH);
+      const uint32_t id1_last = um::make_idesc(fmt, 256, P.chw[nch - 1]);
+      const int k1steps = P.K1P / 16;
+      const int CH = P.CH, last_w = P.chw[nch - 1];
+      const bool two_halves = P.NB > 0;
+      const uint32_t dL2A = tmem_base, dL2B = tmem_base + (uint32_t)P.NA;
+
       bool ok = true;
-      const long long U = (long long)ntiles * P.nch;
-      for (long long u = 0; u <= U && ok; ++u) {
-        if (u < U) {
-          // ---- layer 1, chunk c of tile tl ----
-          const int tl = (int)(u / P.nch), c = (int)(u % P.nch);
-          const int xs = tl & 1;
-          if (c == 0) ok = ok && um::mbar_wait(bar(BAR_X_FULL + xs), (tl >> 1) & 1, P.err, 11);
-          const int lb = (int)(u & 1);
-          ok = ok && um::mbar_wait(bar(BAR_L1_EMPTY + lb), (uint32_t)(((u >> 1) & 1) ^ 1), P.err, 12);
-          um::tc_fence_after();
-          if (ok && um::elect_one()) {
-            const uint32_t idesc = um::make_idesc(fmt, 256, P.chw[c]);
-            const uint32_t d = tmem_base + L1COL + (uint32_t)(lb * P.CH);
-            for (int k = 0; k < P.K1P / 16; ++k) {
-              const uint64_t ad = um::make_desc(sX + xs * P.x_stage_bytes + (uint32_t)(2 * k) * lbo_x,
-                                                lbo_x, 128, swap);
-              const uint64_t bd = um::make_desc(
-                  sW1 + (uint32_t)(2 * k) * lbo_w1 + (uint32_t)(P.ch0[c] / 2) * 16u, lbo_w1, 128, swap);
-              um::mma2(d, ad, bd, idesc, k > 0);
-            }
-            um::commit2(bar(BAR_L1_FULL + lb));
-            if (c == P.nch - 1) um::commit2(bar(BAR_X_EMPTY + xs));
-          }
-          __syncwarp();
+      // layer-2 work for the unit issued one step earlier (software pipeline of depth 1)
+      uint32_t stg = 0, h1_par = 0;                             // H1 ring stage / parity of unit v
+      auto issue_l2 = [&](int tlv, int cv) {
+        ok = ok && um::mbar_wait(bar(BAR_H1_FULL + (int)stg), h1_par, P.err, 13);
+        const int ksteps = (cv == nch - 1 ? last_w : CH) >> 4;
+        const uint32_t a0 = h1_lo0 + stg * h1_stage16;
+        const uint32_t b0 = w2_lo + (uint32_t)(cv * (CH >> 3)) * (lbo_w2 >> 4);
+        const uint32_t acc0 = cv > 0 ? 1u : 0u;
+        if (cv == 0) ok = ok && um::mbar_wait(bar(BAR_L2_EMPTY + 0), (uint32_t)((tlv & 1) ^ 1), P.err, 14);
+        um::tc_fence_after();
+        if (ok && issuer) {
+#pragma unroll 1
+          for (int k = 0; k < ksteps; ++k)
+            um::mma2(dL2A, um::desc64(a0 + (uint32_t)k * a_kstep), um::desc64(b0 + (uint32_t)k * w2_kstep),
+                     idA, acc0 | (uint32_t)(k > 0));
         }
-        if (u >= 1) {
-          // ---- layer 2 over the K-slice produced from chunk (u-1) ----
-          const long long v = u - 1;
-          const int tl = (int)(v / P.nch), c = (int)(v % P.nch);
-          const int stg = (int)(v % UM_NST);
-          ok = ok && um::mbar_wait(bar(BAR_H1_FULL + stg), (uint32_t)((v / UM_NST) & 1), P.err, 13);
-          if (c == 0) {
-            ok = ok && um::mbar_wait(bar(BAR_L2_EMPTY + 0), (uint32_t)((tl & 1) ^ 1), P.err, 14);
-            ok = ok && um::mbar_wait(bar(BAR_L2_EMPTY + 1), (uint32_t)((tl & 1) ^ 1), P.err, 15);
+        if (two_halves) {
+          if (cv == 0) {
+            ok = ok && um::mbar_wait(bar(BAR_L2_EMPTY + 1), (uint32_t)((tlv & 1) ^ 1), P.err, 15);
+            um::tc_fence_after();
           }
+          if (ok && issuer) {
+#pragma unroll 1
+            for (int k = 0; k < ksteps; ++k)
+              um::mma2(dL2B, um::desc64(a0 + (uint32_t)k * a_kstep),
+                       um::desc64(b0 + w2_half_off + (uint32_t)k * w2_kstep), idB, acc0 | (uint32_t)(k > 0));
+          }
+        }
+        if (ok && issuer) {
+          um::commit2(bar(BAR_H1_EMPTY + (int)stg));
+          if (cv == nch - 1) um::commit2(bar(BAR_L2_FULL));
+        }
+        __syncwarp();
+        if (++stg == UM_NST) { stg = 0; h1_par ^= 1u; }
+      };
+
+      uint32_t u = 0;
+      int ptl = 0, pc = 0;
+      for (int tl = 0; tl < ntiles && ok; ++tl) {
+        const int xs = tl & 1;
+        for (int c = 0; c < nch && ok; ++c, ++u) {
+          // ---- layer 1, chunk c of tile tl ----
+          if (c == 0) ok = ok && um::mbar_wait(bar(BAR_X_FULL + xs), (uint32_t)((tl >> 1) & 1), P.err, 11);
+          const uint32_t lb = u & 1u;
+          ok = ok && um::mbar_wait(bar(BAR_L1_EMPTY + (int)lb), ((u >> 1) & 1u) ^ 1u, P.err, 12);
           um::tc_fence_after();
-          if (ok && um::elect_one()) {
-            const uint32_t idA = um::make_idesc(fmt, 256, P.NA);
-            const uint32_t idB = um::make_idesc(fmt, 256, P.NB > 0 ? P.NB : 16);
-            const int ksteps = P.chw[c] / 16;
-            for (int half = 0; half < 2; ++half) {
-              if (half == 1 && P.NB == 0) break;
-              for (int k = 0; k < ksteps; ++k) {
-                const uint64_t ad = um::make_desc(
-                    sH1 + stg * P.h1_stage_bytes + (uint32_t)(2 * k) * lbo_x, lbo_x, 128, swap);
-                const uint32_t kc = (uint32_t)(P.ch0[c] / 8 + 2 * k);  // global 8-wide K chunk
-                const uint32_t rowoff = half ? (uint32_t)(P.NA / 2) * 16u : 0u;
-                const uint64_t bd = um::make_desc(sW2 + kc * lbo_w2 + rowoff, lbo_w2, 128, swap);
-                um::mma2(tmem_base + (half ? (uint32_t)P.NA : 0u), ad, bd, half ? idB : idA,
-                         (c > 0 || k > 0) ? 1u : 0u);
-              }
-            }
-            um::commit2(bar(BAR_H1_EMPTY + stg));
-            if (c == P.nch - 1) um::commit2(bar(BAR_L2_FULL));
+          if (ok && issuer) {
+            const uint32_t d = tmem_base + L1COL + lb * (uint32_t)CH;
+            const uint32_t a0 = xs ? x_lo1 : x_lo0;
+            const uint32_t b0 = w1_lo + (uint32_t)(c * (CH >> 1));
+            const uint32_t idesc = (c == nch - 1) ? id1_last : id1_full;
+#pragma unroll 1
+            for (int k = 0; k < k1steps; ++k)
+              um::mma2(d, um::desc64(a0 + (uint32_t)k * a_kstep), um::desc64(b0 + (uint32_t)k * w1_kstep), idesc,
+                       (uint32_t)(k > 0));
+            um::commit2(bar(BAR_L1_FULL + (int)lb));
+            if (c == nch - 1) um::commit2(bar(BAR_X_EMPTY + xs));
           }
           __syncwarp();
+          // ---- layer 2 over the K-slice produced from the previous unit ----
+          if (u > 0) issue_l2(ptl, pc);
+          ptl = tl; pc = c;
         }
       }
+      if (u > 0 && ok) issue_l2(ptl, pc);
     }
   } else if (warp < 4) {
     // =================================== X producers (3 warps) ===================================
+    // thread <-> row: the [s_b ; a_n ; 1] row is assembled in registers and written as K1P/8
+    // 16-byte core-matrix rows.  Rows past R are zero.
     const int pt = tid - 32;  // 0..95
     const uint32_t xfull_leader0 = um::mapa(bar(BAR_X_FULL + 0), 0);
     const uint32_t xfull_leader1 = um::mapa(bar(BAR_X_FULL + 1), 0);
     bool ok = true;
-    const int K1 = P.S + P.A;
+    const int S = P.S, K1 = P.S + P.A, KC1 = P.KC1;
+    const uint32_t N = (uint32_t)P.N;
+    const bool clip = P.smin != nullptr;
     for (int tl = 0; tl < ntiles && ok; ++tl) {
       const int xs = tl & 1;
       ok = um::mbar_wait(bar(BAR_X_EMPTY + xs), (uint32_t)(((tl >> 1) & 1) ^ 1), P.err, 21);
@@ -384,35 +408,41 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_critic_umma(const UmmaParams 
       const long long tile = (long long)pair + (long long)tl * npairs;
       const long long row0 = tile * 256 + (long long)rank * 128;
       unsigned char* xbase = base_ptr + P.sm_x + xs * P.x_stage_bytes;
-      for (int item = pt; item < 128 * P.KC1; item += 96) {
-        const int r = item & 127, kc = item >> 7;
+      for (int r = pt; r < 128; r += 96) {
         const long long row = row0 + r;
-        float v[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = 0.f;
-        if (row < P.R) {
-          const long long b = row / P.N;
-          const long long arow = P.act_per_state ? row : (row - b * P.N);
+        const bool live = row < P.R;
+        const float* sp = P.s;
+        const float* ap = P.a;
+        if (live) {
+          const uint32_t b = (uint32_t)row / N;   // R = B*N < 2^31 rows is enforced on the host
+          sp += (size_t)b * S;
+          ap += (size_t)(P.act_per_state ? (uint32_t)row : ((uint32_t)row - b * N)) * P.A;
+        }
+        for (int kc = 0; kc < KC1; ++kc) {
+          float v[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int k = kc * 8 + e;
-            if (k < P.S) {
-              float t = __ldg(P.s + b * P.S + k);
-              if (P.smin) t = fminf(fmaxf(t, __ldg(P.smin + k)), __ldg(P.smax + k));
-              v[e] = t;
-            } else if (k < K1) {
-              v[e] = __ldg(P.a + arow * P.A + (k - P.S));
-            } else if (k == K1) {
-              v[e] = 1.f;
+            float t = 0.f;
+            if (live) {
+              if (k < S) {
+                t = __ldg(sp + k);
+                if (clip) t = fminf(fmaxf(t, __ldg(P.smin + k)), __ldg(P.smax + k));
+              } else if (k < K1) {
+                t = __ldg(ap + (k - S));
+              } else if (k == K1) {
+                t = 1.f;
+              }
             }
+            v[e] = t;
           }
+          uint4 pk;
+          pk.x = um::pack2<PREC>(v[0], v[1]);
+          pk.y = um::pack2<PREC>(v[2], v[3]);
+          pk.z = um::pack2<PREC>(v[4], v[5]);
+          pk.w = um::pack2<PREC>(v[6], v[7]);
+          *reinterpret_cast<uint4*>(xbase + kc * 2048 + r * 16) = pk;
         }
-        uint4 pk;
-        pk.x = um::pack2<PREC>(v[0], v[1]);
-        pk.y = um::pack2<PREC>(v[2], v[3]);
-        pk.z = um::pack2<PREC>(v[4], v[5]);
-        pk.w = um::pack2<PREC>(v[6], v[7]);
-        *reinterpret_cast<uint4*>(xbase + kc * 2048 + r * 16) = pk;
       }
       um::fence_proxy_async();
       __syncwarp();
@@ -423,39 +453,45 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_critic_umma(const UmmaParams 
     const int q4 = warp & 3;
     const int row = q4 * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    const uint32_t l1e0 = um::mapa(bar(BAR_L1_EMPTY + 0), 0), l1e1 = um::mapa(bar(BAR_L1_EMPTY + 1), 0);
+    const uint32_t h1f0 = um::mapa(bar(BAR_H1_FULL), 0);   // the cluster window is linear: +8 per stage
     bool ok = true;
-    const long long U = (long long)ntiles * P.nch;
-    for (long long u = 0; u < U && ok; ++u) {
-      const int c = (int)(u % P.nch);
-      const int lb = (int)(u & 1), stg = (int)(u % UM_NST);
-      ok = um::mbar_wait(bar(BAR_L1_FULL + lb), (uint32_t)((u >> 1) & 1), P.err, 31);
-      ok = ok && um::mbar_wait(bar(BAR_H1_EMPTY + stg), (uint32_t)(((u / UM_NST) & 1) ^ 1), P.err, 32);
-      if (!ok) break;
-      um::tc_fence_after();
-      unsigned char* hbase = base_ptr + P.sm_h1 + stg * P.h1_stage_bytes + row * 16;
-      const uint32_t tcol = lane_addr + L1COL + (uint32_t)(lb * P.CH);
-      for (int j0 = 0; j0 < P.chw[c]; j0 += 16) {
-        uint32_t v[16];
-        um::tmem_ld16(tcol + (uint32_t)j0, v);
-        um::tmem_ld_wait();
-        uint4 p0, p1;
-        p0.x = um::pack2_relu<PREC>(__uint_as_float(v[0]), __uint_as_float(v[1]));
-        p0.y = um::pack2_relu<PREC>(__uint_as_float(v[2]), __uint_as_float(v[3]));
-        p0.z = um::pack2_relu<PREC>(__uint_as_float(v[4]), __uint_as_float(v[5]));
-        p0.w = um::pack2_relu<PREC>(__uint_as_float(v[6]), __uint_as_float(v[7]));
-        p1.x = um::pack2_relu<PREC>(__uint_as_float(v[8]), __uint_as_float(v[9]));
-        p1.y = um::pack2_relu<PREC>(__uint_as_float(v[10]), __uint_as_float(v[11]));
-        p1.z = um::pack2_relu<PREC>(__uint_as_float(v[12]), __uint_as_float(v[13]));
-        p1.w = um::pack2_relu<PREC>(__uint_as_float(v[14]), __uint_as_float(v[15]));
-        *reinterpret_cast<uint4*>(hbase + (j0 / 8) * 2048) = p0;
-        *reinterpret_cast<uint4*>(hbase + (j0 / 8 + 1) * 2048) = p1;
-      }
-      um::tc_fence_before();
-      um::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) {
-        um::mbar_arrive_cluster(um::mapa(bar(BAR_L1_EMPTY + lb), 0));
-        um::mbar_arrive_cluster(um::mapa(bar(BAR_H1_FULL + stg), 0));
+    uint32_t u = 0, stg = 0, h1_par = 0;
+    const int CH = P.CH, last_w = P.chw[nch - 1];
+    for (int tl = 0; tl < ntiles && ok; ++tl) {
+      for (int c = 0; c < nch; ++c, ++u) {
+        const uint32_t lb = u & 1u;
+        ok = um::mbar_wait(bar(BAR_L1_FULL + (int)lb), (u >> 1) & 1u, P.err, 31);
+        ok = ok && um::mbar_wait(bar(BAR_H1_EMPTY + (int)stg), h1_par ^ 1u, P.err, 32);
+        if (!ok) break;
+        um::tc_fence_after();
+        unsigned char* hbase = base_ptr + P.sm_h1 + stg * P.h1_stage_bytes + row * 16;
+        const uint32_t tcol = lane_addr + L1COL + lb * (uint32_t)CH;
+        const int w = (c == nch - 1) ? last_w : CH;
+        for (int j0 = 0; j0 < w; j0 += 16) {
+          uint32_t v[16];
+          um::tmem_ld16(tcol + (uint32_t)j0, v);
+          um::tmem_ld_wait();
+          uint4 p0, p1;
+          p0.x = um::pack2_relu<PREC>(__uint_as_float(v[0]), __uint_as_float(v[1]));
+          p0.y = um::pack2_relu<PREC>(__uint_as_float(v[2]), __uint_as_float(v[3]));
+          p0.z = um::pack2_relu<PREC>(__uint_as_float(v[4]), __uint_as_float(v[5]));
+          p0.w = um::pack2_relu<PREC>(__uint_as_float(v[6]), __uint_as_float(v[7]));
+          p1.x = um::pack2_relu<PREC>(__uint_as_float(v[8]), __uint_as_float(v[9]));
+          p1.y = um::pack2_relu<PREC>(__uint_as_float(v[10]), __uint_as_float(v[11]));
+          p1.z = um::pack2_relu<PREC>(__uint_as_float(v[12]), __uint_as_float(v[13]));
+          p1.w = um::pack2_relu<PREC>(__uint_as_float(v[14]), __uint_as_float(v[15]));
+          *reinterpret_cast<uint4*>(hbase + (j0 / 8) * 2048) = p0;
+          *reinterpret_cast<uint4*>(hbase + (j0 / 8 + 1) * 2048) = p1;
+        }
+        um::tc_fence_before();
+        um::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          um::mbar_arrive_cluster(lb ? l1e1 : l1e0);
+          um::mbar_arrive_cluster(h1f0 + 8u * stg);
+        }
+        if (++stg == UM_NST) { stg = 0; h1_par ^= 1u; }
       }
     }
   } else {
@@ -464,6 +500,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_critic_umma(const UmmaParams 
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
     const uint32_t l2e0 = um::mapa(bar(BAR_L2_EMPTY + 0), 0);
     const uint32_t l2e1 = um::mapa(bar(BAR_L2_EMPTY + 1), 0);
+    const float c0 = __ldg(reinterpret_cast<const float*>(P.blob[0] + P.off_c0));
     bool ok = true;
     for (int tl = 0; tl < ntiles && ok; ++tl) {
       ok = um::mbar_wait(bar(BAR_L2_FULL), (uint32_t)(tl & 1), P.err, 41);
@@ -688,21 +725,16 @@ static int get_pack(rlc_handle* h, const rlc_critic* c, int prec, const PackGeom
   return RLC_OK;
 }
 
-static int g_umma_variant = -1;
-
 int rlc_eval_umma(rlc_handle* h, const rlc_critic* c, const float* s, int B, const float* a, int N,
                   int act_mode, int prec, float* q_out, cudaStream_t st) {
   PackGeom G;
   if (!make_geom(c, G)) return RLC_ERR_UNSUPPORTED;
+  if ((long long)B * N >= (1ll << 31)) return RLC_ERR_UNSUPPORTED;  // 32-bit row arithmetic in the producers
   const SmemPlan sp = plan_smem(G);
   if ((size_t)sp.total > h->smem_optin) return RLC_ERR_UNSUPPORTED;
   rlc_pack* pk = nullptr;
   int rc = get_pack(h, c, prec, G, st, &pk);
   if (rc) return rc;
-  if (g_umma_variant < 0) {
-    const char* e = getenv("RLC_UMMA_VARIANT");
-    g_umma_variant = e ? atoi(e) : 0;
-  }
   int* err = h->err_flag;
 
   UmmaParams P;
@@ -721,7 +753,6 @@ int rlc_eval_umma(rlc_handle* h, const rlc_critic* c, const float* s, int B, con
   P.sm_par = sp.sm_par; P.sm_bar = sp.sm_bar; P.x_stage_bytes = sp.x_stage;
   P.h1_stage_bytes = sp.h1_stage;
   P.num_pair_tiles = (int)((P.R + 255) / 256);
-  P.variant = g_umma_variant;
   P.err = err;
 
   int pairs = h->num_sms / 2;

@@ -264,7 +264,7 @@ def test_rounded_operand_oracle():
     g = golden("tin_400_300.npz")
     p = _params(g)
     exact = onp.tin_eval(g["s"], g["a"], p, dtype=np.float64)
-    for kind, (rms_b, max_b) in {"fp16": (2e-3, 2e-2), "bf16": (1e-2, 1e-1)}.items():
+    for kind, (rms_b, max_b) in {"fp16": (2.5e-3, 2e-2), "bf16": (2e-2, 1.5e-1)}.items():
         e = rel_err(onp.tin_eval_rounded(g["s"], g["a"], p, kind), exact)
         assert 1e-6 < np.sqrt((e ** 2).mean()) < rms_b and e.max() < max_b
     # representable operands -> no rounding anywhere -> equals the exact path
