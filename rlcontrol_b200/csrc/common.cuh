@@ -13,6 +13,7 @@
 struct rlc_pack {
   const float* theta;  // key
   int topology, S, A, H1, H2, prec;
+  int ch;              // layer-1 chunk width the pack was built for (W1 rows are split per chunk)
   void* dev;           // packed blob
   size_t bytes;
   bool valid;

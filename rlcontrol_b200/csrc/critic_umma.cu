@@ -24,7 +24,6 @@
 
 #define UM_THREADS 384
 #define UM_NST 3           // H1 ring stages
-#define UM_MAXCH 8         // max layer-1 chunks
 #define UM_WAIT_LIMIT (1u << 26)
 
 struct UmmaParams {
@@ -41,10 +40,9 @@ struct UmmaParams {
   int H1P, KC2;        // layer-2 K (=H1 padded to 16), number of 8-wide K chunks
   int H2P;             // layer-2 N padded to 16
   int NA, NB;          // layer-2 N split (NA + NB = H2P), both % 16 == 0, NB may be 0
-  int nch;             // number of layer-1 chunks
-  int ch0[UM_MAXCH];   // first feature of chunk
-  int chw[UM_MAXCH];   // width of chunk (multiple of 16, <= CH)
-  int CH;              // max chunk width == TMEM columns per L1 buffer
+  int nch;             // number of layer-1 chunks: chunk c covers features [c*CH, min((c+1)*CH, H1P))
+  int CH;              // chunk width (multiple of 16) == TMEM columns per L1 buffer
+  int nb1;             // TS variant: number of L1 chunk buffers in TMEM (2 or 3)
   // packed blob for each cta rank (device), and byte offsets inside it
   const unsigned char* blob[2];
   int off_w2, off_w1, off_w3, off_nb2, off_c0, blob_bytes;
@@ -52,6 +50,9 @@ struct UmmaParams {
   int sm_w2, sm_w1, sm_x, sm_h1, sm_par, sm_bar, x_stage_bytes, h1_stage_bytes;
   int num_pair_tiles;
   int* err;     // device error flag (0 = ok)
+  long long* prof;  // optional cycle accounting (RLC_UMMA_PROF=1), 32 x int64 per pair
+  const uint4* sp;  // TS variant: packed state part of X, [B][KC1] 16-byte chunks
+  const uint4* ap;  // TS variant: packed action part of X, [KC1][N] (shared grid only)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -317,9 +318,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_critic_umma(const UmmaParams 
       const uint32_t idA = um::make_idesc(fmt, 256, P.NA);
       const uint32_t idB = um::make_idesc(fmt, 256, P.NB > 0 ? P.NB : 16);
       const uint32_t id1_full = um::make_idesc(fmt, 256, P.CH);
-      const uint32_t id1_last = um::make_idesc(fmt, 256, P.chw[nch - 1]);
+      const uint32_t id1_last = um::make_idesc(fmt, 256, (P.H1P - (nch - 1) * P.CH));
       const int k1steps = P.K1P / 16;
-      const int CH = P.CH, last_w = P.chw[nch - 1];
+      const int CH = P.CH, last_w = (P.H1P - (nch - 1) * P.CH);
       const bool two_halves = P.NB > 0;
       const uint32_t dL2A = tmem_base, dL2B = tmem_base + (uint32_t)P.NA;
 
@@ -457,7 +458,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_critic_umma(const UmmaParams 
     const uint32_t h1f0 = um::mapa(bar(BAR_H1_FULL), 0);   // the cluster window is linear: +8 per stage
     bool ok = true;
     uint32_t u = 0, stg = 0, h1_par = 0;
-    const int CH = P.CH, last_w = P.chw[nch - 1];
+    const int CH = P.CH, last_w = (P.H1P - (nch - 1) * P.CH);
     for (int tl = 0; tl < ntiles && ok; ++tl) {
       for (int c = 0; c < nch; ++c, ++u) {
         const uint32_t lb = u & 1u;
@@ -541,11 +542,495 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_critic_umma(const UmmaParams 
 }
 
 // ------------------------------------------------------------------------------------------
+// K1 (TS variant, default): layer-2's A operand is read from TENSOR MEMORY.
+//
+// Epilogue 1 converts a layer-1 accumulator chunk (fp32, CH columns) to fp16 *in place* (CH/2
+// columns, two values per 32-bit cell) with tcgen05.ld -> F2FP.RELU -> tcgen05.st, and layer 2 is
+// issued as tcgen05.mma [d_tmem], [a_tmem], b_desc: the ReLU'd activations never touch shared
+// memory, which removes ~100 KB of st.shared + 200 KB of tensor-core operand reads per 128-row
+// tile from the 128 B/clk shared-memory port, the proxy fence, and one barrier (the chunk buffer
+// is recycled by MMA issue order: L1(u+NB1) is issued after L2(u), and tcgen05.mma executes in
+// order).  TMEM: [0,H2P) layer-2 accumulator, then NB1 chunk buffers of CH columns.
+//
+// 16 warps per CTA: 0 = MMA issuer (leader CTA), 1-3 = X producers (OR of two pre-packed 16-byte
+// tables: state part SP[b][kc] and action part AP[kc][n]), 4-7 = epilogue 1, 8-15 = epilogue 2
+// (two warps per TMEM lane quarter, each draining half of the columns of each accumulator half, so
+// the accumulator is handed back to the MMA issuer after one tcgen05.ld round trip).
+// ------------------------------------------------------------------------------------------
+#define TS_THREADS 512
+enum {
+  TB_X_FULL = 0,     // [2]   count 6  (leader)   3 producer warps x 2 CTAs -> MMA
+  TB_X_EMPTY = 2,    // [2]   count 1  (both)     MMA commit -> producers
+  TB_L1_FULL = 4,    // [3]   count 1  (both)     MMA commit -> ep1
+  TB_H1_FULL = 7,    // [3]   count 8  (leader)   ep1 (4 warps x 2 CTAs) -> MMA
+  TB_L2_FULL = 10,   // [1]   count 1  (both)     MMA commit -> ep2
+  TB_L2_EMPTY = 11,  // [2]   count 16 (leader)   ep2 (8 warps x 2 CTAs) -> MMA (half A, half B)
+  TB_COUNT = 13
+};
+
+namespace um {
+__device__ __forceinline__ void mma2_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
+               "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16p(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8p(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+                 "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+}  // namespace um
+
+// Pre-pass: 16-byte X chunks.  SP[b][kc] = fp16/bf16 of the (clipped) state entries that fall in
+// K chunk kc, plus the ones column at k = S+A; AP[kc][n] = the action entries (shared grid only).
+// A row of X is SP[b][kc] | AP[kc][n] (the two parts occupy disjoint halfwords; +0.0 = 0x0000).
+template <int PREC>
+__global__ void k_xparts(const float* __restrict__ s, const float* __restrict__ a,
+                         const float* __restrict__ smin, const float* __restrict__ smax, int B, int N,
+                         int S, int A, int KC1, int shared_actions, uint4* __restrict__ SP,
+                         uint4* __restrict__ AP) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nsp = (long long)B * KC1, nap = shared_actions ? (long long)N * KC1 : 0;
+  if (gid >= nsp + nap) return;
+  float v[8];
+  const int K1 = S + A;
+  if (gid < nsp) {
+    const int b = (int)(gid / KC1), kc = (int)(gid % KC1);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kc * 8 + e;
+      float t = 0.f;
+      if (k < S) {
+        t = __ldg(s + (size_t)b * S + k);
+        if (smin) t = fminf(fmaxf(t, __ldg(smin + k)), __ldg(smax + k));
+      } else if (k == K1) {
+        t = 1.f;
+      }
+      v[e] = t;
+    }
+  } else {
+    const long long g = gid - nsp;
+    const int kc = (int)(g / N), n = (int)(g % N);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kc * 8 + e;
+      v[e] = (k >= S && k < K1) ? __ldg(a + (size_t)n * A + (k - S)) : 0.f;
+    }
+  }
+  uint4 pk;
+  pk.x = um::pack2<PREC>(v[0], v[1]);
+  pk.y = um::pack2<PREC>(v[2], v[3]);
+  pk.z = um::pack2<PREC>(v[4], v[5]);
+  pk.w = um::pack2<PREC>(v[6], v[7]);
+  if (gid < nsp) SP[gid] = pk;
+  else AP[gid - nsp] = pk;
+}
+
+template <int PREC>
+__global__ void __launch_bounds__(TS_THREADS, 1) k_critic_umma_ts(const UmmaParams P) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw_addr = um::smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  unsigned char* base_ptr = smem_raw + (base - raw_addr);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = um::cta_rank();
+  const uint32_t pair = um::cluster_id_x();
+  const uint32_t npairs = um::num_clusters_x();
+
+  const uint32_t sW2 = base + P.sm_w2, sW1 = base + P.sm_w1, sX = base + P.sm_x, sBar = base + P.sm_bar;
+  const float* w3s = reinterpret_cast<const float*>(base_ptr + P.sm_par);
+  const float* nb2s = w3s + P.H2P;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + P.sm_bar + TB_COUNT * 8);
+  float* qpart = reinterpret_cast<float*>(base_ptr + P.sm_h1);   // [2][128] partial dot products
+  auto bar = [&](int i) -> uint32_t { return sBar + 8u * (uint32_t)i; };
+
+  // ---- prologue: resident weights -> smem, barriers, TMEM ----
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(P.blob[rank]);
+    uint4* dW2 = reinterpret_cast<uint4*>(base_ptr + P.sm_w2);
+    const int n2 = (P.off_w1 - P.off_w2) >> 4;
+    for (int i = tid; i < n2; i += TS_THREADS) dW2[i] = __ldg(src + (P.off_w2 >> 4) + i);
+    uint4* dW1 = reinterpret_cast<uint4*>(base_ptr + P.sm_w1);
+    const int n1 = (P.off_w3 - P.off_w1) >> 4;
+    for (int i = tid; i < n1; i += TS_THREADS) dW1[i] = __ldg(src + (P.off_w1 >> 4) + i);
+    uint4* dP = reinterpret_cast<uint4*>(base_ptr + P.sm_par);
+    const int np = (P.off_c0 - P.off_w3) >> 4;
+    for (int i = tid; i < np; i += TS_THREADS) dP[i] = __ldg(src + (P.off_w3 >> 4) + i);
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      um::mbar_init(bar(TB_X_FULL + i), 6);
+      um::mbar_init(bar(TB_X_EMPTY + i), 1);
+      um::mbar_init(bar(TB_L2_EMPTY + i), 16);
+    }
+    for (int i = 0; i < 3; ++i) {
+      um::mbar_init(bar(TB_L1_FULL + i), 1);
+      um::mbar_init(bar(TB_H1_FULL + i), 8);
+    }
+    um::mbar_init(bar(TB_L2_FULL), 1);
+    um::fence_mbar_init();
+  }
+  um::fence_proxy_async();
+  if (warp == 0) um::tmem_alloc2(um::smem_u32(tmem_slot), 512);
+  um::tc_fence_before();
+  __syncthreads();
+  um::cluster_sync();
+  um::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // optional cycle accounting (RLC_UMMA_PROF=1): 8 x int64 per role, 32 per pair
+  long long pw0 = 0, pw1 = 0, pw2 = 0, pi0 = 0, pi1 = 0;
+  const bool prof = P.prof != nullptr;
+  const long long t_begin = prof ? clock64() : 0;
+#define PROF_T() (prof ? clock64() : 0)
+
+  const int ntiles = (P.num_pair_tiles > (int)pair)
+                         ? (P.num_pair_tiles - (int)pair + (int)npairs - 1) / (int)npairs
+                         : 0;
+  const int nch = P.nch, CH = P.CH, last_w = P.H1P - (P.nch - 1) * P.CH;
+  const uint32_t NB1 = (uint32_t)P.nb1;
+  const uint32_t L1COL = (uint32_t)P.H2P;
+
+  if (warp == 0) {
+    // =================================== MMA issuer (leader CTA) ===================================
+    if (rank == 0) {
+      const bool issuer = um::elect_one();
+      const uint32_t fmt = (PREC == RLC_PREC_BF16) ? 1u : 0u;
+      const uint32_t lbo_x = 128u * 16u;
+      const uint32_t lbo_w1 = (uint32_t)(P.H1P / 2) * 16u;
+      const uint32_t lbo_w2 = (uint32_t)(P.H2P / 2) * 16u;
+      const uint32_t x_lo0 = um::desc_lo(sX, lbo_x), x_lo1 = um::desc_lo(sX + P.x_stage_bytes, lbo_x);
+      const uint32_t w1_lo = um::desc_lo(sW1, lbo_w1), w2_lo = um::desc_lo(sW2, lbo_w2);
+      const uint32_t a_kstep = (2u * lbo_x) >> 4;
+      const uint32_t w1_kstep = (2u * lbo_w1) >> 4, w2_kstep = (2u * lbo_w2) >> 4;
+      const uint32_t w2_half_off = (uint32_t)(P.NA / 2);
+      const uint32_t idA = um::make_idesc(fmt, 256, P.NA);
+      const uint32_t idB = um::make_idesc(fmt, 256, P.NB > 0 ? P.NB : 16);
+      const uint32_t id1_full = um::make_idesc(fmt, 256, CH);
+      const uint32_t id1_last = um::make_idesc(fmt, 256, last_w);
+      const int k1steps = P.K1P / 16;
+      const bool two_halves = P.NB > 0;
+      const uint32_t dL2A = tmem_base, dL2B = tmem_base + (uint32_t)P.NA;
+      const int total = ntiles * nch;
+
+      bool ok = true;
+      // cursor of the layer-1 issue (runs NB1-1 units ahead of the layer-2 cursor)
+      int tl1 = 0, c1 = 0;
+      uint32_t lb1 = 0;
+      auto issue_l1 = [&]() {
+        const int xs = tl1 & 1;
+        long long t0 = PROF_T();
+        if (c1 == 0) ok = ok && um::mbar_wait(bar(TB_X_FULL + xs), (uint32_t)((tl1 >> 1) & 1), P.err, 11);
+        um::tc_fence_after();
+        long long t1 = PROF_T();
+        pw0 += t1 - t0;
+        if (ok && issuer) {
+          const uint32_t d = tmem_base + L1COL + lb1 * (uint32_t)CH;
+          const uint32_t a0 = xs ? x_lo1 : x_lo0;
+          const uint32_t b0 = w1_lo + (uint32_t)(c1 * (CH >> 1));
+          const uint32_t idesc = (c1 == nch - 1) ? id1_last : id1_full;
+#pragma unroll 1
+          for (int k = 0; k < k1steps; ++k)
+            um::mma2(d, um::desc64(a0 + (uint32_t)k * a_kstep), um::desc64(b0 + (uint32_t)k * w1_kstep), idesc,
+                     (uint32_t)(k > 0));
+          um::commit2(bar(TB_L1_FULL + (int)lb1));
+          if (c1 == nch - 1) um::commit2(bar(TB_X_EMPTY + xs));
+        }
+        __syncwarp();
+        pi0 += PROF_T() - t1;
+        if (++lb1 == NB1) lb1 = 0;
+        if (++c1 == nch) { c1 = 0; ++tl1; }
+      };
+      int issued1 = 0;
+      const int ahead = (int)NB1 - 1;
+      for (; issued1 < ahead && issued1 < total && ok; ++issued1) issue_l1();
+
+      uint32_t lb2 = 0, par2 = 0;   // chunk buffer / parity of the layer-2 cursor
+      for (int tl = 0; tl < ntiles && ok; ++tl) {
+        for (int c = 0; c < nch && ok; ++c) {
+          if (issued1 < total) { issue_l1(); ++issued1; }
+          // ---- layer 2 over K-slice c: A = fp16 activations in TMEM, B = W2 slice in smem ----
+          long long t0 = PROF_T();
+          ok = ok && um::mbar_wait(bar(TB_H1_FULL + (int)lb2), par2, P.err, 13);
+          long long t1 = PROF_T();
+          pw1 += t1 - t0;
+          const int ksteps = (c == nch - 1 ? last_w : CH) >> 4;
+          const uint32_t a0 = tmem_base + L1COL + lb2 * (uint32_t)CH;       // 8 columns per K=16 step
+          const uint32_t b0 = w2_lo + (uint32_t)(c * (CH >> 3)) * (lbo_w2 >> 4);
+          const uint32_t acc0 = c > 0 ? 1u : 0u;
+          if (c == 0) ok = ok && um::mbar_wait(bar(TB_L2_EMPTY + 0), (uint32_t)((tl & 1) ^ 1), P.err, 14);
+          um::tc_fence_after();
+          long long t2 = PROF_T();
+          pw2 += t2 - t1;
+          if (ok && issuer) {
+#pragma unroll 1
+            for (int k = 0; k < ksteps; ++k)
+              um::mma2_ts(dL2A, a0 + 8u * (uint32_t)k, um::desc64(b0 + (uint32_t)k * w2_kstep), idA,
+                          acc0 | (uint32_t)(k > 0));
+          }
+          if (two_halves) {
+            if (c == 0) {
+              long long t3 = PROF_T();
+              ok = ok && um::mbar_wait(bar(TB_L2_EMPTY + 1), (uint32_t)((tl & 1) ^ 1), P.err, 15);
+              um::tc_fence_after();
+              long long t4 = PROF_T();
+              pw2 += t4 - t3;
+              t2 += t4 - t3;
+            }
+            if (ok && issuer) {
+#pragma unroll 1
+              for (int k = 0; k < ksteps; ++k)
+                um::mma2_ts(dL2B, a0 + 8u * (uint32_t)k, um::desc64(b0 + w2_half_off + (uint32_t)k * w2_kstep),
+                            idB, acc0 | (uint32_t)(k > 0));
+            }
+          }
+          if (ok && issuer && c == nch - 1) um::commit2(bar(TB_L2_FULL));
+          __syncwarp();
+          pi1 += PROF_T() - t2;
+          if (++lb2 == NB1) { lb2 = 0; par2 ^= 1u; }
+        }
+      }
+      if (prof && issuer) {
+        long long* o = P.prof + (size_t)pair * 32;
+        o[0] = clock64() - t_begin; o[1] = pw0; o[2] = pw1; o[3] = pw2; o[4] = pi0; o[5] = pi1; o[6] = ntiles;
+      }
+    }
+  } else if (warp < 4) {
+    // =================================== X producers (3 warps) ===================================
+    // X[r][kc] = SP[b][kc] | AP[kc][n]  (two 16-byte loads and an OR per chunk); per-state actions
+    // are packed inline from a[B,N,A].
+    const int pt = tid - 32;  // 0..95
+    const uint32_t xfull_leader0 = um::mapa(bar(TB_X_FULL + 0), 0);
+    const uint32_t xfull_leader1 = um::mapa(bar(TB_X_FULL + 1), 0);
+    bool ok = true;
+    const int S = P.S, K1 = P.S + P.A, KC1 = P.KC1, A = P.A;
+    const uint32_t N = (uint32_t)P.N;
+    const uint4* __restrict__ SP = P.sp;
+    const uint4* __restrict__ AP = P.ap;
+    const int kc_a0 = S >> 3, kc_a1 = (K1 - 1) >> 3;   // K chunks that contain action entries
+    for (int tl = 0; tl < ntiles && ok; ++tl) {
+      const int xs = tl & 1;
+      long long t0 = PROF_T();
+      ok = um::mbar_wait(bar(TB_X_EMPTY + xs), (uint32_t)(((tl >> 1) & 1) ^ 1), P.err, 21);
+      if (!ok) break;
+      long long t1 = PROF_T();
+      pw0 += t1 - t0;
+      const long long tile = (long long)pair + (long long)tl * npairs;
+      const long long row0 = tile * 256 + (long long)rank * 128;
+      unsigned char* xbase = base_ptr + P.sm_x + xs * P.x_stage_bytes;
+      for (int r = pt; r < 128; r += 96) {
+        const long long row = row0 + r;
+        uint4* dst = reinterpret_cast<uint4*>(xbase + r * 16);
+        if (row < P.R) {
+          const uint32_t b = (uint32_t)row / N, n = (uint32_t)row - b * N;
+          const uint4* sp = SP + (size_t)b * KC1;
+          if (!P.act_per_state) {
+            for (int kc = 0; kc < KC1; ++kc) {
+              uint4 x = __ldg(sp + kc);
+              const uint4 y = __ldg(AP + (size_t)kc * N + n);
+              x.x |= y.x; x.y |= y.y; x.z |= y.z; x.w |= y.w;
+              dst[kc * 128] = x;
+            }
+          } else {
+            const float* ap = P.a + (size_t)(uint32_t)row * A;
+            for (int kc = 0; kc < KC1; ++kc) {
+              uint4 x = __ldg(sp + kc);
+              if (kc >= kc_a0 && kc <= kc_a1) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const int k = kc * 8 + e;
+                  v[e] = (k >= S && k < K1) ? __ldg(ap + (k - S)) : 0.f;
+                }
+                x.x |= um::pack2<PREC>(v[0], v[1]);
+                x.y |= um::pack2<PREC>(v[2], v[3]);
+                x.z |= um::pack2<PREC>(v[4], v[5]);
+                x.w |= um::pack2<PREC>(v[6], v[7]);
+              }
+              dst[kc * 128] = x;
+            }
+          }
+        } else {
+          for (int kc = 0; kc < KC1; ++kc) dst[kc * 128] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+      um::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) um::mbar_arrive_cluster(xs ? xfull_leader1 : xfull_leader0);
+      pi0 += PROF_T() - t1;
+    }
+    if (prof && rank == 0 && tid == 32) { long long* o = P.prof + (size_t)pair * 32 + 8; o[0] = pw0; o[1] = pi0; }
+  } else if (warp < 8) {
+    // ============ epilogue 1: L1 accumulator chunk -> relu -> fp16, in place in TMEM ============
+    // All tcgen05.ld of the chunk are issued back to back (<= 96 columns), one wait, convert,
+    // then tcgen05.st into the first half of the same columns.
+    const int q4 = warp & 3;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    const uint32_t h1f0 = um::mapa(bar(TB_H1_FULL), 0);
+    bool ok = true;
+    uint32_t lb = 0, par = 0;
+    for (int tl = 0; tl < ntiles && ok; ++tl) {
+      for (int c = 0; c < nch; ++c) {
+        long long t0 = PROF_T();
+        ok = um::mbar_wait(bar(TB_L1_FULL + (int)lb), par, P.err, 31);
+        if (!ok) break;
+        um::tc_fence_after();
+        long long t1 = PROF_T();
+        pw0 += t1 - t0;
+        const uint32_t tcol = lane_addr + L1COL + lb * (uint32_t)CH;
+        const int w = (c == nch - 1) ? last_w : CH;
+        uint32_t v[96];
+#pragma unroll
+        for (int p = 0; p < 6; ++p)
+          if (p * 16 < w) um::tmem_ld16p(tcol + (uint32_t)(p * 16), v + p * 16);
+        um::tmem_ld_wait();
+        { long long tt = PROF_T(); pw1 += tt - t1; }
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+          if (p * 16 < w) {
+            uint32_t o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              o[e] = um::pack2_relu<PREC>(__uint_as_float(v[p * 16 + 2 * e]), __uint_as_float(v[p * 16 + 2 * e + 1]));
+            um::tmem_st8(tcol + (uint32_t)(p * 8), o);
+          }
+        }
+        um::tmem_st_wait();
+        um::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) um::mbar_arrive_cluster(h1f0 + 8u * lb);
+        pi0 += PROF_T() - t1;
+        if (++lb == NB1) { lb = 0; par ^= 1u; }
+      }
+    }
+    if (prof && rank == 0 && tid == 128) { long long* o = P.prof + (size_t)pair * 32 + 16; o[0] = pw0; o[1] = pi0; o[2] = pw1; }
+  } else {
+    // ================ epilogue 2 (8 warps): L2 acc -> bias/relu/w3 dot -> q ======================
+    // warp w: TMEM lane quarter w&3, column half ch = (w-8)>>2 of each accumulator half.  The
+    // columns of a half are pulled into registers with back-to-back tcgen05.ld, the accumulator
+    // half is released to the MMA issuer right after the wait, the arithmetic runs from registers.
+    const int q4 = warp & 3, chalf = (warp - 8) >> 2;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    const uint32_t l2e0 = um::mapa(bar(TB_L2_EMPTY + 0), 0);
+    const uint32_t l2e1 = um::mapa(bar(TB_L2_EMPTY + 1), 0);
+    const float c0 = __ldg(reinterpret_cast<const float*>(P.blob[0] + P.off_c0));
+    const int rloc = q4 * 32 + lane;
+    bool ok = true;
+    for (int tl = 0; tl < ntiles && ok; ++tl) {
+      long long t0 = PROF_T();
+      ok = um::mbar_wait(bar(TB_L2_FULL), (uint32_t)(tl & 1), P.err, 41);
+      if (!ok) break;
+      um::tc_fence_after();
+      long long t1 = PROF_T();
+      pw0 += t1 - t0;
+      float acc = 0.f;
+      for (int half = 0; half < 2; ++half) {
+        const int hb = half ? P.NA : 0, hn = half ? P.NB : P.NA;      // this accumulator half
+        if (hn > 0) {
+          // my columns: [j_begin, j_end) -- split of the half in units of 8 columns
+          const int units = hn >> 3, u0 = chalf ? (units + 1) / 2 : 0, u1 = chalf ? units : (units + 1) / 2;
+          const int j_begin = hb + u0 * 8, j_end = hb + u1 * 8;
+          for (int jb = j_begin; jb < j_end; jb += 96) {
+            const int w = (j_end - jb < 96) ? (j_end - jb) : 96;
+            uint32_t v[96];
+#pragma unroll
+            for (int p = 0; p < 6; ++p) {
+              if (p * 16 + 16 <= w) um::tmem_ld16p(lane_addr + (uint32_t)(jb + p * 16), v + p * 16);
+              else if (p * 16 < w) um::tmem_ld8p(lane_addr + (uint32_t)(jb + p * 16), v + p * 16);
+            }
+            um::tmem_ld_wait();
+            if (half == 0) { long long tt = PROF_T(); pw1 += tt - t1; }
+            if (jb + 96 >= j_end) {               // last round of this half: hand it back
+              um::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) um::mbar_arrive_cluster(half ? l2e1 : l2e0);
+            }
+#pragma unroll
+            for (int p = 0; p < 12; ++p) {
+              if (p * 8 < w) {
+                const int j = jb + p * 8;
+                const float4 wa = *reinterpret_cast<const float4*>(w3s + j);
+                const float4 wb = *reinterpret_cast<const float4*>(w3s + j + 4);
+                const float4 na = *reinterpret_cast<const float4*>(nb2s + j);
+                const float4 nb = *reinterpret_cast<const float4*>(nb2s + j + 4);
+                acc = fmaf(wa.x, fmaxf(__uint_as_float(v[p * 8 + 0]), na.x), acc);
+                acc = fmaf(wa.y, fmaxf(__uint_as_float(v[p * 8 + 1]), na.y), acc);
+                acc = fmaf(wa.z, fmaxf(__uint_as_float(v[p * 8 + 2]), na.z), acc);
+                acc = fmaf(wa.w, fmaxf(__uint_as_float(v[p * 8 + 3]), na.w), acc);
+                acc = fmaf(wb.x, fmaxf(__uint_as_float(v[p * 8 + 4]), nb.x), acc);
+                acc = fmaf(wb.y, fmaxf(__uint_as_float(v[p * 8 + 5]), nb.y), acc);
+                acc = fmaf(wb.z, fmaxf(__uint_as_float(v[p * 8 + 6]), nb.z), acc);
+                acc = fmaf(wb.w, fmaxf(__uint_as_float(v[p * 8 + 7]), nb.w), acc);
+              }
+            }
+          }
+          if (j_begin >= j_end) {                 // nothing to drain for this warp: still hand back
+            um::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) um::mbar_arrive_cluster(half ? l2e1 : l2e0);
+          }
+        } else {
+          __syncwarp();
+          if (lane == 0) um::mbar_arrive_cluster(half ? l2e1 : l2e0);
+        }
+      }
+      // combine the two column halves of each row through shared memory
+      float* qp = qpart + (tl & 1) * 128;
+      if (chalf) qp[rloc] = acc;
+      long long t5 = PROF_T();
+      um::named_bar_sync(1, 256);
+      pw2 += PROF_T() - t5;
+      if (!chalf) {
+        const long long tile = (long long)pair + (long long)tl * npairs;
+        const long long row = tile * 256 + (long long)rank * 128 + rloc;
+        if (row < P.R) P.q[row] = acc + qp[rloc] + c0;
+      }
+      pi0 += PROF_T() - t1;
+    }
+    if (prof && rank == 0 && tid == 256) { long long* o = P.prof + (size_t)pair * 32 + 24; o[0] = pw0; o[1] = pi0; o[2] = pw1; o[3] = pw2; }
+  }
+#undef PROF_T
+
+  um::tc_fence_before();
+  __syncthreads();
+  um::cluster_sync();
+  if (warp == 0) um::tmem_dealloc2(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------
 // Weight pre-pack: theta (fp32 canonical) -> per-rank blobs in the UMMA core-matrix layout
 // ------------------------------------------------------------------------------------------
 struct PackGeom {
-  int S, A, H1, H2, K1P, H1P, H2P, NA, NB, nch, CH;
-  int ch0[UM_MAXCH], chw[UM_MAXCH];
+  int S, A, H1, H2, K1P, H1P, H2P, NA, NB, nch, CH, nb1, ts;
   int off_w2, off_w1, off_w3, off_nb2, off_c0, blob_bytes;
 };
 
@@ -595,11 +1080,11 @@ __global__ void k_pack_umma(const float* __restrict__ theta, PackGeom G, unsigne
   } else if (gid < nW2 + nW1) {
     const long long g = gid - nW2;
     const int k = (int)(g / G.H1P), j = (int)(g % G.H1P);
-    int c = 0;
-    while (c + 1 < G.nch && j >= G.ch0[c + 1]) ++c;
-    const int within = j - G.ch0[c], hw = G.chw[c] / 2;
+    const int c = j / G.CH, c0f = c * G.CH;
+    const int cw = (G.H1P - c0f < G.CH) ? (G.H1P - c0f) : G.CH;
+    const int within = j - c0f, hw = cw / 2;
     const int rank = within / hw;
-    const int l = G.ch0[c] / 2 + within % hw;
+    const int l = c0f / 2 + within % hw;
     float v = 0.f;
     if (j < G.H1) {
       if (k < K1) v = W1[(long long)k * G.H1 + j];
@@ -626,9 +1111,9 @@ __global__ void k_pack_umma(const float* __restrict__ theta, PackGeom G, unsigne
   }
 }
 
-static bool make_geom(const rlc_critic* c, PackGeom& G) {
+static bool make_geom(const rlc_critic* c, PackGeom& G, int ts) {
   memset(&G, 0, sizeof(G));
-  G.S = c->S; G.A = c->A; G.H1 = c->H1; G.H2 = c->H2;
+  G.S = c->S; G.A = c->A; G.H1 = c->H1; G.H2 = c->H2; G.ts = ts;
   G.K1P = (c->S + c->A + 1 + 15) & ~15;
   G.H1P = (c->H1 + 15) & ~15;
   G.H2P = (c->H2 + 15) & ~15;
@@ -637,16 +1122,30 @@ static bool make_geom(const rlc_critic* c, PackGeom& G) {
   if (G.H2P <= 256) { G.NA = G.H2P; G.NB = 0; }
   else { G.NA = ((G.H2P / 2) + 15) & ~15; G.NB = G.H2P - G.NA; }
   if (G.NA > 256 || G.NB > 256) return false;
-  int ch = ((512 - G.H2P) / 2) & ~15;
-  if (ch > 80) ch = 80;
+  const int free_cols = 512 - G.H2P;
+  int ch;
+  if (ts) {
+    // three chunk buffers when they can be >= 32 columns wide, else two
+    // widest chunks first (fewer barrier round trips, longer MMAs); a third buffer only if free
+    G.nb1 = 2;
+    ch = (free_cols / 2) & ~15;
+    if (ch > 96) ch = 96;                       // epilogue 1 holds one chunk in registers
+    if (ch == 96 && free_cols >= 3 * 96) G.nb1 = 3;
+    const char* e = getenv("RLC_UMMA_TS_CH");   // tuning knob: "<nb1>x<ch>"
+    if (e) {
+      int nb = 0, cw = 0;
+      if (sscanf(e, "%dx%d", &nb, &cw) == 2 && (nb == 2 || nb == 3) && cw >= 16 && (cw & 15) == 0 &&
+          cw <= 96 && nb * cw <= free_cols) { G.nb1 = nb; ch = cw; }
+    }
+  } else {
+    G.nb1 = 2;
+    ch = (free_cols / 2) & ~15;
+    if (ch > 80) ch = 80;
+  }
   if (ch < 16) return false;
+  if (ch > G.H1P) ch = G.H1P;
   G.CH = ch;
   G.nch = (G.H1P + ch - 1) / ch;
-  if (G.nch > UM_MAXCH) return false;
-  for (int i = 0; i < G.nch; ++i) {
-    G.ch0[i] = i * ch;
-    G.chw[i] = (G.H1P - i * ch < ch) ? (G.H1P - i * ch) : ch;
-  }
   G.off_w2 = 0;
   G.off_w1 = G.off_w2 + (G.H1P / 8) * (G.H2P / 2) * 16;
   G.off_w3 = G.off_w1 + (G.K1P / 8) * (G.H1P / 2) * 16;
@@ -668,16 +1167,26 @@ static SmemPlan plan_smem(const PackGeom& G) {
   p.sm_x = (p.sm_par + (G.off_c0 - G.off_w3) + 127) & ~127;
   p.x_stage = (G.K1P / 8) * 2048;
   p.sm_h1 = p.sm_x + 2 * p.x_stage;
-  p.h1_stage = (G.CH / 8) * 2048;
-  p.sm_bar = p.sm_h1 + UM_NST * p.h1_stage;
+  p.h1_stage = G.ts ? 0 : (G.CH / 8) * 2048;     // TS variant keeps the activations in TMEM
+  p.sm_bar = p.sm_h1 + (G.ts ? 1024 : UM_NST * p.h1_stage);   // TS: [2][128] fp32 partial dots
   p.total = p.sm_bar + BAR_COUNT * 8 + 16 + 1024;  // + alignment slack
   return p;
+}
+
+// 1 = TS variant (layer-2 A operand from tensor memory), 0 = SS variant (shared-memory ring)
+static int umma_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("RLC_UMMA_MODE");
+    mode = (e && (e[0] == 't' || e[0] == 'T')) ? 1 : 0;   // SS stays the default until TS is faster
+  }
+  return mode;
 }
 
 bool rlc_umma_supported(const rlc_handle* h, const rlc_critic* c, int B, int N) {
   if (h->sm_major != 10 || c->topology != RLC_TIN) return false;
   PackGeom G;
-  if (!make_geom(c, G)) return false;
+  if (!make_geom(c, G, umma_mode())) return false;
   const SmemPlan p = plan_smem(G);
   if ((size_t)p.total > h->smem_optin) return false;
   (void)B; (void)N;
@@ -690,7 +1199,7 @@ static int get_pack(rlc_handle* h, const rlc_critic* c, int prec, const PackGeom
   for (int i = 0; i < RLC_MAX_PACKS; ++i) {
     rlc_pack& p = h->packs[i];
     if (p.theta == c->theta && p.prec == prec && p.S == c->S && p.A == c->A && p.H1 == c->H1 &&
-        p.H2 == c->H2 && p.dev) { slot = &p; break; }
+        p.H2 == c->H2 && p.ch == G.CH && p.dev) { slot = &p; break; }
   }
   if (!slot) {
     slot = &h->packs[h->pack_rr];
@@ -708,7 +1217,7 @@ static int get_pack(rlc_handle* h, const rlc_critic* c, int prec, const PackGeom
       slot->bytes = (size_t)2 * G.blob_bytes;
     }
     slot->theta = c->theta; slot->prec = prec; slot->topology = c->topology;
-    slot->S = c->S; slot->A = c->A; slot->H1 = c->H1; slot->H2 = c->H2;
+    slot->S = c->S; slot->A = c->A; slot->H1 = c->H1; slot->H2 = c->H2; slot->ch = G.CH;
     slot->valid = false;
   }
   if (!slot->valid) {
@@ -728,7 +1237,8 @@ static int get_pack(rlc_handle* h, const rlc_critic* c, int prec, const PackGeom
 int rlc_eval_umma(rlc_handle* h, const rlc_critic* c, const float* s, int B, const float* a, int N,
                   int act_mode, int prec, float* q_out, cudaStream_t st) {
   PackGeom G;
-  if (!make_geom(c, G)) return RLC_ERR_UNSUPPORTED;
+  const int ts = umma_mode();
+  if (!make_geom(c, G, ts)) return RLC_ERR_UNSUPPORTED;
   if ((long long)B * N >= (1ll << 31)) return RLC_ERR_UNSUPPORTED;  // 32-bit row arithmetic in the producers
   const SmemPlan sp = plan_smem(G);
   if ((size_t)sp.total > h->smem_optin) return RLC_ERR_UNSUPPORTED;
@@ -743,8 +1253,7 @@ int rlc_eval_umma(rlc_handle* h, const rlc_critic* c, const float* s, int B, con
   P.R = (long long)B * N; P.N = N; P.S = c->S; P.A = c->A;
   P.act_per_state = act_mode == RLC_ACT_PER_STATE;
   P.K1P = G.K1P; P.KC1 = G.K1P / 8; P.H1P = G.H1P; P.KC2 = G.H1P / 8; P.H2P = G.H2P;
-  P.NA = G.NA; P.NB = G.NB; P.nch = G.nch; P.CH = G.CH;
-  for (int i = 0; i < UM_MAXCH; ++i) { P.ch0[i] = G.ch0[i]; P.chw[i] = G.chw[i]; }
+  P.NA = G.NA; P.NB = G.NB; P.nch = G.nch; P.CH = G.CH; P.nb1 = G.nb1;
   P.blob[0] = (const unsigned char*)pk->dev;
   P.blob[1] = P.blob[0] + G.blob_bytes;
   P.off_w2 = G.off_w2; P.off_w1 = G.off_w1; P.off_w3 = G.off_w3; P.off_nb2 = G.off_nb2;
@@ -761,7 +1270,7 @@ int rlc_eval_umma(rlc_handle* h, const rlc_critic* c, const float* s, int B, con
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(pairs * 2));
-  cfg.blockDim = dim3(UM_THREADS);
+  cfg.blockDim = dim3(ts ? TS_THREADS : UM_THREADS);
   cfg.dynamicSmemBytes = (size_t)sp.total;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -771,14 +1280,48 @@ int rlc_eval_umma(rlc_handle* h, const rlc_critic* c, const float* s, int B, con
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (prec == RLC_PREC_BF16) {
-    RLC_CUDA(cudaFuncSetAttribute(k_critic_umma<RLC_PREC_BF16>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
-    RLC_CUDA(cudaLaunchKernelEx(&cfg, k_critic_umma<RLC_PREC_BF16>, P));
-  } else {
-    RLC_CUDA(cudaFuncSetAttribute(k_critic_umma<RLC_PREC_FP16>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
-    RLC_CUDA(cudaLaunchKernelEx(&cfg, k_critic_umma<RLC_PREC_FP16>, P));
+  if (ts) {
+    const int KC1 = G.K1P / 8;
+    const int shared = act_mode == RLC_ACT_SHARED;
+    const size_t nsp = (size_t)B * KC1, nap = shared ? (size_t)N * KC1 : 0;
+    void* ws = nullptr;
+    rc = rlc_workspace(h, (nsp + nap) * sizeof(uint4), &ws);
+    if (rc) return rc;
+    uint4* SP = (uint4*)ws;
+    uint4* AP = SP + nsp;
+    const unsigned blocks = (unsigned)((nsp + nap + 255) / 256);
+    if (prec == RLC_PREC_BF16)
+      k_xparts<RLC_PREC_BF16><<<blocks, 256, 0, st>>>(s, a, c->smin, c->smax, B, N, c->S, c->A, KC1, shared, SP, AP);
+    else
+      k_xparts<RLC_PREC_FP16><<<blocks, 256, 0, st>>>(s, a, c->smin, c->smax, B, N, c->S, c->A, KC1, shared, SP, AP);
+    RLC_LAUNCH_CHECK(h);
+    P.sp = SP; P.ap = AP;
+  }
+  static int prof_on = -1;
+  static long long* prof_dev = nullptr;
+  if (prof_on < 0) { const char* e = getenv("RLC_UMMA_PROF"); prof_on = (e && e[0] == '1') ? 1 : 0; }
+  if (prof_on && ts) {
+    if (!prof_dev) RLC_CUDA(cudaMalloc(&prof_dev, 128 * 32 * sizeof(long long)));
+    RLC_CUDA(cudaMemsetAsync(prof_dev, 0, 128 * 32 * sizeof(long long), st));
+    P.prof = prof_dev;
+  }
+  void (*kern)(const UmmaParams) =
+      ts ? (prec == RLC_PREC_BF16 ? k_critic_umma_ts<RLC_PREC_BF16> : k_critic_umma_ts<RLC_PREC_FP16>)
+         : (prec == RLC_PREC_BF16 ? k_critic_umma<RLC_PREC_BF16> : k_critic_umma<RLC_PREC_FP16>);
+  RLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
+  RLC_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
+  if (prof_on && ts) {   // debug only: synchronises
+    static long long hostp[128 * 32];
+    RLC_CUDA(cudaStreamSynchronize(st));
+    RLC_CUDA(cudaMemcpy(hostp, prof_dev, sizeof(hostp), cudaMemcpyDeviceToHost));
+    const long long* o = hostp;  // pair 0
+    const double T = (double)o[0], nt = (double)(o[6] > 0 ? o[6] : 1);
+    fprintf(stderr, "[umma prof pair0] tiles %lld total %.0f cyc (%.0f/tile) | MMA: waitX %.1f%% waitH1 %.1f%% waitL2E %.1f%% "
+            "issueL1 %.1f%% issueL2 %.1f%% | producer wait %.1f%% work %.1f%% | ep1 wait %.1f%% work %.1f%% | "
+            "ep2 wait %.1f%% work %.1f%% || ep1 ld+wait %.1f%% | ep2 first ld+wait %.1f%% pairbar %.1f%%\n", o[6], T, T / nt,
+            100 * o[1] / T, 100 * o[2] / T, 100 * o[3] / T,
+            100 * o[4] / T, 100 * o[5] / T, 100 * o[8] / T, 100 * o[9] / T, 100 * o[16] / T, 100 * o[17] / T,
+            100 * o[24] / T, 100 * o[25] / T, 100 * o[18] / T, 100 * o[26] / T, 100 * o[27] / T);
   }
   RLC_LAUNCH_CHECK(h);
   return RLC_OK;

@@ -19,8 +19,11 @@ def main():
     a = torch.rand(N, A, device="cuda") * 2 - 1
     a_ps = torch.rand(B, N, A, device="cuda") * 2 - 1
     flops = B * 2 * S * H1 + B * N * 2 * (A * H1 + H1 * H2 + H2)
-    for name, act, prec in (("fp16 shared", a, "fp16"), ("fp16 per-state", a_ps, "fp16"), ("bf16 shared", a, "bf16"),
-                            ("fp32 shared (B/8)", a, "fp32")):
+    cases = (("fp16 shared", a, "fp16"), ("fp16 per-state", a_ps, "fp16"), ("bf16 shared", a, "bf16"),
+             ("fp32 shared (B/8)", a, "fp32"))
+    if os.environ.get("ONLY"):
+        cases = [c for c in cases if c[0].startswith(os.environ["ONLY"] + " shared")]
+    for name, act, prec in cases:
         ss = s if prec != "fp32" else s[: B // 8]
         for _ in range(3):
             q = cr.eval(ss, act if act.dim() == 2 else act[: ss.shape[0]], prec)
