@@ -231,7 +231,8 @@ def run_b200(args, rank, local_rank, world):
     parity = {"rows_checked": int(q_ref.size), "rel_err_rms": float(np.sqrt((err ** 2).mean())),
               "rel_err_max": float(err.max())}
     if prec in ("fp16", "bf16"):
-        q_rnd = onp.tin_eval_rounded(s_np[rows], a_np, params, prec)
+        q_rnd = onp.tin_eval_rounded(s_np[rows], a_np, params, prec,
+                                       head="folded" if eng.lib.rlc_umma_mode() == 1 else "ss")
         d = np.abs(q_gpu - q_rnd) / den
         parity["vs_stated_arithmetic_rms"] = float(np.sqrt((d ** 2).mean()))
         parity["vs_stated_arithmetic_max"] = float(d.max())

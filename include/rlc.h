@@ -117,6 +117,11 @@ int rlc_tmid_eval_grad(rlc_handle* h, const rlc_critic* c, const float* s, int B
 /* Diagnostic: synchronises `stream` and returns the code raised by a bounded mbarrier wait inside
  * the tcgen05 kernel (0 = none, <0 = CUDA error). The flag is cleared on read. */
 int rlc_umma_last_error(rlc_handle* h, void* stream);
+/* Diagnostic: which stated arithmetic the tensor path uses (tests pick the matching oracle).
+ * 0 = "SS": q = b3 + sum_j w3_j relu(h1.fp16(W2[:,j]) + b2_j)                      (fp32 head)
+ * 1 = "TS": q = b3 + 2^-k sum_j sign(w3_j) relu(h1.fp16(2^k|w3_j|W2[:,j]) + fp16(2^k|w3_j|b2_j))
+ *           (output head folded into layer 2's operands).  Env RLC_UMMA_MODE. */
+int rlc_umma_mode(void);
 
 /* ---- per-state reductions (rows a3, a4, a8, a9, a10) ------------------------------------ */
 /* row.argsort()[::-1][:k] (ActorExpert.py:177, qt_opt_network.py:166): descending, ties -> larger

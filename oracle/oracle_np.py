@@ -84,12 +84,20 @@ def round_operand(x, kind):
     raise ValueError(kind)
 
 
-def tin_eval_rounded(s, a, params, kind="fp16"):
+def tin_eval_rounded(s, a, params, kind="fp16", head="ss"):
     """T-in evaluation with the operand rounding of the tensor-core path made explicit (fp64
-    accumulate): x=[s;a], W1, b1 (folded as a ones column), the ReLU'd layer-1 activations and W2
-    are rounded to ``kind``; b2, W3, b3 and all accumulation stay wide.  The CUDA kernel must
-    match THIS to ~1e-5 (it does exactly this arithmetic with fp32 accumulators); the distance
-    of this function from ``tin_eval(..., float64)`` is the precision cost of the operand type."""
+    accumulate): x=[s;a], W1, b1 (folded as a ones column) and the ReLU'd layer-1 activations are
+    rounded to ``kind``.  Two stated arithmetics for layer 2 + head (rlc_umma_mode()):
+
+    ``head="ss"``     W2 rounded; b2, W3, b3 and all accumulation wide:
+                      q = b3 + sum_j w3_j relu(h1 . r(W2[j,:]) + b2_j)
+    ``head="folded"`` the output head is folded into layer 2's operands (TS kernel):
+                      q = b3 + 2^-k sum_j sign(w3_j) relu(h1 . r(2^k |w3_j| W2[j,:]) + r(2^k |w3_j| b2_j))
+                      with 2^k max|w3| in [1,2); the products 2^k|w3_j|*x are formed in fp32 (one
+                      rounding, as the pack kernel does) before the rounding to ``kind``.
+
+    The CUDA kernel must match THIS to ~1e-5 rms (it does exactly this arithmetic with fp32
+    accumulators); the distance from ``tin_eval(..., float64)`` is the cost of the operand type."""
     W1, b1, W2, b2, W3, b3 = [np.asarray(p, np.float64) for p in params]
     s = np.asarray(s)
     a = np.asarray(a)
@@ -97,9 +105,24 @@ def tin_eval_rounded(s, a, params, kind="fp16"):
     N = a.shape[0] if a.ndim == 2 else a.shape[1]
     x = np.concatenate([stack_state_major(s, N), stack_actions(a, B)], axis=1)
     r = lambda z: round_operand(z, kind)
-    h1 = np.maximum(r(x) @ r(W1).T + r(b1), 0)
-    h2 = np.maximum(r(h1) @ r(W2).T + b2, 0)
-    q = h2 @ W3.reshape(-1) + b3.reshape(())
+    h1 = r(np.maximum(r(x) @ r(W1).T + r(b1), 0))
+    w3 = W3.reshape(-1)
+    if head == "ss":
+        h2 = np.maximum(h1 @ r(W2).T + b2, 0)
+        q = h2 @ w3 + b3.reshape(())
+    elif head == "folded":
+        mx = np.float32(np.abs(w3).max())
+        scale = np.float32(1.0)
+        if mx > 0 and np.isfinite(mx):
+            scale = np.float32(np.ldexp(1.0, 1 - int(np.frexp(mx)[1])))
+        sw = scale * np.abs(w3).astype(np.float32)                                   # exact (power of two)
+        W2s = r(sw[:, None] * np.asarray(params[2], np.float32))                     # fp32 product, then kind
+        bs = r(sw * np.asarray(params[3], np.float32).reshape(-1))
+        z = np.maximum(h1 @ W2s.T + bs, 0)
+        sign = np.where(w3 < 0, -1.0, 1.0)
+        q = (z @ sign) / np.float64(scale) + b3.reshape(())
+    else:
+        raise ValueError(head)
     return q.reshape(B, N)
 
 

@@ -604,6 +604,17 @@ __device__ __forceinline__ void tmem_ld8p(uint32_t taddr, uint32_t* v) {
                : "r"(taddr)
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld32p(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st16p(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+               : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -654,7 +665,7 @@ __global__ void k_xparts(const float* __restrict__ s, const float* __restrict__ 
   else AP[gid - nsp] = pk;
 }
 
-template <int PREC>
+template <int PREC, bool PROF>
 __global__ void __launch_bounds__(TS_THREADS, 1) k_critic_umma_ts(const UmmaParams P) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_addr = um::smem_u32(smem_raw);
@@ -667,8 +678,6 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_critic_umma_ts(const UmmaPara
   const uint32_t npairs = um::num_clusters_x();
 
   const uint32_t sW2 = base + P.sm_w2, sW1 = base + P.sm_w1, sX = base + P.sm_x, sBar = base + P.sm_bar;
-  const float* w3s = reinterpret_cast<const float*>(base_ptr + P.sm_par);
-  const float* nb2s = w3s + P.H2P;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + P.sm_bar + TB_COUNT * 8);
   float* qpart = reinterpret_cast<float*>(base_ptr + P.sm_h1);   // [2][128] partial dot products
   auto bar = [&](int i) -> uint32_t { return sBar + 8u * (uint32_t)i; };
@@ -682,9 +691,6 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_critic_umma_ts(const UmmaPara
     uint4* dW1 = reinterpret_cast<uint4*>(base_ptr + P.sm_w1);
     const int n1 = (P.off_w3 - P.off_w1) >> 4;
     for (int i = tid; i < n1; i += TS_THREADS) dW1[i] = __ldg(src + (P.off_w1 >> 4) + i);
-    uint4* dP = reinterpret_cast<uint4*>(base_ptr + P.sm_par);
-    const int np = (P.off_c0 - P.off_w3) >> 4;
-    for (int i = tid; i < np; i += TS_THREADS) dP[i] = __ldg(src + (P.off_w3 >> 4) + i);
   }
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -709,9 +715,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_critic_umma_ts(const UmmaPara
 
   // optional cycle accounting (RLC_UMMA_PROF=1): 8 x int64 per role, 32 per pair
   long long pw0 = 0, pw1 = 0, pw2 = 0, pi0 = 0, pi1 = 0;
-  const bool prof = P.prof != nullptr;
+  const bool prof = PROF && P.prof != nullptr;
   const long long t_begin = prof ? clock64() : 0;
-#define PROF_T() (prof ? clock64() : 0)
+#define PROF_T() ((PROF && prof) ? clock64() : 0)
 
   const int ntiles = (P.num_pair_tiles > (int)pair)
                          ? (P.num_pair_tiles - (int)pair + (int)npairs - 1) / (int)npairs
@@ -910,21 +916,28 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_critic_umma_ts(const UmmaPara
         const int w = (c == nch - 1) ? last_w : CH;
         uint32_t v[96];
 #pragma unroll
-        for (int p = 0; p < 6; ++p)
-          if (p * 16 < w) um::tmem_ld16p(tcol + (uint32_t)(p * 16), v + p * 16);
+        for (int p = 0; p < 3; ++p) {
+          if (p * 32 + 32 <= w) um::tmem_ld32p(tcol + (uint32_t)(p * 32), v + p * 32);
+          else if (p * 32 < w) um::tmem_ld16p(tcol + (uint32_t)(p * 32), v + p * 32);
+        }
         um::tmem_ld_wait();
         { long long tt = PROF_T(); pw1 += tt - t1; }
 #pragma unroll
-        for (int p = 0; p < 6; ++p) {
-          if (p * 16 < w) {
-            uint32_t o[8];
+        for (int p = 0; p < 3; ++p) {
+          if (p * 32 < w) {
+            uint32_t o[16];
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-              o[e] = um::pack2_relu<PREC>(__uint_as_float(v[p * 16 + 2 * e]), __uint_as_float(v[p * 16 + 2 * e + 1]));
-            um::tmem_st8(tcol + (uint32_t)(p * 8), o);
+            for (int e = 0; e < 16; ++e)
+              o[e] = um::pack2_relu<PREC>(__uint_as_float(v[p * 32 + 2 * e]), __uint_as_float(v[p * 32 + 2 * e + 1]));
+            if (p * 32 + 32 <= w) um::tmem_st16p(tcol + (uint32_t)(p * 16), o);
+            else um::tmem_st8(tcol + (uint32_t)(p * 16), o);
           }
         }
+        long long t6 = PROF_T();
         um::tmem_st_wait();
+        long long t7 = PROF_T();
+        pw2 += t6 - t1;      // ld+wait + cvt + st issue
+        pi1 += t7 - t6;      // wait::st
         um::tc_fence_before();
         __syncwarp();
         if (lane == 0) um::mbar_arrive_cluster(h1f0 + 8u * lb);
@@ -932,17 +945,21 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_critic_umma_ts(const UmmaPara
         if (++lb == NB1) { lb = 0; par ^= 1u; }
       }
     }
-    if (prof && rank == 0 && tid == 128) { long long* o = P.prof + (size_t)pair * 32 + 16; o[0] = pw0; o[1] = pi0; o[2] = pw1; }
+    if (prof && rank == 0 && tid == 128) { long long* o = P.prof + (size_t)pair * 32 + 16; o[0] = pw0; o[1] = pi0; o[2] = pw1; o[3] = pw2; o[4] = pi1; }
   } else {
-    // ================ epilogue 2 (8 warps): L2 acc -> bias/relu/w3 dot -> q ======================
-    // warp w: TMEM lane quarter w&3, column half ch = (w-8)>>2 of each accumulator half.  The
-    // columns of a half are pulled into registers with back-to-back tcgen05.ld, the accumulator
-    // half is released to the MMA issuer right after the wait, the arithmetic runs from registers.
+    // ================ epilogue 2 (8 warps): L2 acc -> relu -> signed sum -> q ====================
+    // warp w: TMEM lane quarter w&3, column half (w-8)>>2 of each accumulator half.  The columns
+    // are pulled into registers with back-to-back tcgen05.ld, the accumulator half is released to
+    // the MMA issuer right after the wait, the arithmetic runs from registers.  The output head
+    // is folded into W2 (see k_pack_head): q = b3 + 2^-k (sum_{j<npos} relu - sum_{j>=npos} relu),
+    // so there are no per-column constants to fetch.
     const int q4 = warp & 3, chalf = (warp - 8) >> 2;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
     const uint32_t l2e0 = um::mapa(bar(TB_L2_EMPTY + 0), 0);
     const uint32_t l2e1 = um::mapa(bar(TB_L2_EMPTY + 1), 0);
-    const float c0 = __ldg(reinterpret_cast<const float*>(P.blob[0] + P.off_c0));
+    const int npos = __ldg(reinterpret_cast<const int*>(P.blob[0] + P.off_c0));
+    const float inv_scale = __ldg(reinterpret_cast<const float*>(P.blob[0] + P.off_c0) + 2);
+    const float b3v = __ldg(reinterpret_cast<const float*>(P.blob[0] + P.off_c0) + 3);
     const int rloc = q4 * 32 + lane;
     bool ok = true;
     for (int tl = 0; tl < ntiles && ok; ++tl) {
@@ -952,58 +969,61 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_critic_umma_ts(const UmmaPara
       um::tc_fence_after();
       long long t1 = PROF_T();
       pw0 += t1 - t0;
-      float acc = 0.f;
+      float accp = 0.f, accn = 0.f;
       for (int half = 0; half < 2; ++half) {
         const int hb = half ? P.NA : 0, hn = half ? P.NB : P.NA;      // this accumulator half
-        if (hn > 0) {
-          // my columns: [j_begin, j_end) -- split of the half in units of 8 columns
-          const int units = hn >> 3, u0 = chalf ? (units + 1) / 2 : 0, u1 = chalf ? units : (units + 1) / 2;
-          const int j_begin = hb + u0 * 8, j_end = hb + u1 * 8;
-          for (int jb = j_begin; jb < j_end; jb += 96) {
-            const int w = (j_end - jb < 96) ? (j_end - jb) : 96;
-            uint32_t v[96];
+        // my columns: [j_begin, j_end) -- split of the half in units of 8 columns
+        const int units = hn >> 3, u0 = chalf ? (units + 1) / 2 : 0, u1 = chalf ? units : (units + 1) / 2;
+        const int j_begin = hb + u0 * 8, j_end = hb + u1 * 8;
+        for (int jb = j_begin; jb < j_end; jb += 96) {
+          const int w = (j_end - jb < 96) ? (j_end - jb) : 96;
+          uint32_t v[96];
 #pragma unroll
-            for (int p = 0; p < 6; ++p) {
-              if (p * 16 + 16 <= w) um::tmem_ld16p(lane_addr + (uint32_t)(jb + p * 16), v + p * 16);
-              else if (p * 16 < w) um::tmem_ld8p(lane_addr + (uint32_t)(jb + p * 16), v + p * 16);
-            }
-            um::tmem_ld_wait();
-            if (half == 0) { long long tt = PROF_T(); pw1 += tt - t1; }
-            if (jb + 96 >= j_end) {               // last round of this half: hand it back
-              um::tc_fence_before();
-              __syncwarp();
-              if (lane == 0) um::mbar_arrive_cluster(half ? l2e1 : l2e0);
-            }
-#pragma unroll
-            for (int p = 0; p < 12; ++p) {
-              if (p * 8 < w) {
-                const int j = jb + p * 8;
-                const float4 wa = *reinterpret_cast<const float4*>(w3s + j);
-                const float4 wb = *reinterpret_cast<const float4*>(w3s + j + 4);
-                const float4 na = *reinterpret_cast<const float4*>(nb2s + j);
-                const float4 nb = *reinterpret_cast<const float4*>(nb2s + j + 4);
-                acc = fmaf(wa.x, fmaxf(__uint_as_float(v[p * 8 + 0]), na.x), acc);
-                acc = fmaf(wa.y, fmaxf(__uint_as_float(v[p * 8 + 1]), na.y), acc);
-                acc = fmaf(wa.z, fmaxf(__uint_as_float(v[p * 8 + 2]), na.z), acc);
-                acc = fmaf(wa.w, fmaxf(__uint_as_float(v[p * 8 + 3]), na.w), acc);
-                acc = fmaf(wb.x, fmaxf(__uint_as_float(v[p * 8 + 4]), nb.x), acc);
-                acc = fmaf(wb.y, fmaxf(__uint_as_float(v[p * 8 + 5]), nb.y), acc);
-                acc = fmaf(wb.z, fmaxf(__uint_as_float(v[p * 8 + 6]), nb.z), acc);
-                acc = fmaf(wb.w, fmaxf(__uint_as_float(v[p * 8 + 7]), nb.w), acc);
-              }
+          for (int p = 0; p < 3; ++p) {
+            if (p * 32 + 32 <= w) um::tmem_ld32p(lane_addr + (uint32_t)(jb + p * 32), v + p * 32);
+            else if (p * 32 < w) {
+              const int rem = w - p * 32;             // 8, 16 or 24
+              if (rem >= 16) um::tmem_ld16p(lane_addr + (uint32_t)(jb + p * 32), v + p * 32);
+              if (rem == 8) um::tmem_ld8p(lane_addr + (uint32_t)(jb + p * 32), v + p * 32);
+              if (rem == 24) um::tmem_ld8p(lane_addr + (uint32_t)(jb + p * 32 + 16), v + p * 32 + 16);
             }
           }
-          if (j_begin >= j_end) {                 // nothing to drain for this warp: still hand back
+          um::tmem_ld_wait();
+          if (half == 0) { long long tt = PROF_T(); pw1 += tt - t1; }
+          if (jb + 96 >= j_end) {               // last round of this half: hand it back
             um::tc_fence_before();
             __syncwarp();
             if (lane == 0) um::mbar_arrive_cluster(half ? l2e1 : l2e0);
           }
-        } else {
+#pragma unroll
+          for (int p = 0; p < 12; ++p) {
+            if (p * 8 < w) {
+              const int j = jb + p * 8;
+              float r[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) r[e] = fmaxf(__uint_as_float(v[p * 8 + e]), 0.f);
+              if (j + 8 <= npos) {
+                accp += ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+              } else if (j >= npos) {
+                accn += ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+              } else {                          // the one unit that straddles the sign boundary
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  if (j + e < npos) accp += r[e];
+                  else accn += r[e];
+                }
+              }
+            }
+          }
+        }
+        if (j_begin >= j_end) {                 // nothing to drain for this warp: still hand back
+          um::tc_fence_before();
           __syncwarp();
           if (lane == 0) um::mbar_arrive_cluster(half ? l2e1 : l2e0);
         }
       }
       // combine the two column halves of each row through shared memory
+      const float acc = accp - accn;
       float* qp = qpart + (tl & 1) * 128;
       if (chalf) qp[rloc] = acc;
       long long t5 = PROF_T();
@@ -1012,7 +1032,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_critic_umma_ts(const UmmaPara
       if (!chalf) {
         const long long tile = (long long)pair + (long long)tl * npairs;
         const long long row = tile * 256 + (long long)rank * 128 + rloc;
-        if (row < P.R) P.q[row] = acc + qp[rloc] + c0;
+        if (row < P.R) P.q[row] = fmaf(inv_scale, acc + qp[rloc], b3v);
       }
       pi0 += PROF_T() - t1;
     }
@@ -1045,6 +1065,52 @@ __device__ __forceinline__ unsigned short to_h(float x) {
   return *reinterpret_cast<unsigned short*>(&t);
 }
 
+// TS variant, output head folded into layer 2 (so that epilogue 2 needs no per-column constants):
+//   q = b3 + sum_j w3_j relu(z_j + b2_j)
+//     = b3 + 2^-k ( sum_{w3_j >= 0} relu(z'_j) - sum_{w3_j < 0} relu(z'_j) ),
+//   z'_j = h1 . (2^k |w3_j| W2[:,j]) + 2^k |w3_j| b2_j
+// The columns of W2 are scaled by 2^k |w3_j| (k: max_j 2^k |w3_j| in [1,2), exact) and stably
+// partitioned by the sign of w3_j (non-negative first); the bias rides on an always-one layer-1
+// feature (index H1: zero W1 column, bias 1).  This kernel computes the partition and k.
+// blob area off_w3: int inv[H2P] (destination column -> source column, -1 = zero column);
+// blob slot off_c0: {int npos; float scale; float inv_scale; float b3}.
+__global__ void k_pack_head(const float* __restrict__ theta, PackGeom G, unsigned char* blob0,
+                            unsigned char* blob1) {
+  const ThetaView t = theta_view(RLC_TIN, G.S, G.A, G.H1, G.H2);
+  const float* w3 = theta + t.ow3;
+  const float* b3 = theta + t.ob3;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int* inv0 = reinterpret_cast<int*>(blob0 + G.off_w3);
+  int* inv1 = reinterpret_cast<int*>(blob1 + G.off_w3);
+  int npos = 0;
+  float mx = 0.f;
+  for (int j = 0; j < G.H2; ++j) {
+    const float w = w3[j];
+    if (!(w < 0.f)) ++npos;
+    mx = fmaxf(mx, fabsf(w));
+  }
+  int p = 0, n = npos;
+  for (int j = 0; j < G.H2; ++j) {
+    const int d = (!(w3[j] < 0.f)) ? p++ : n++;
+    inv0[d] = j;
+    inv1[d] = j;
+  }
+  for (int d = G.H2; d < G.H2P; ++d) { inv0[d] = -1; inv1[d] = -1; }
+  int e = 0;
+  float scale = 1.f;
+  if (mx > 0.f && isfinite(mx)) {
+    (void)frexpf(mx, &e);              // mx = m * 2^e, m in [0.5,1)  ->  2^(1-e) * mx in [1,2)
+    scale = ldexpf(1.f, 1 - e);
+  }
+  for (int r = 0; r < 2; ++r) {
+    unsigned char* blob = r ? blob1 : blob0;
+    reinterpret_cast<int*>(blob + G.off_c0)[0] = npos;
+    reinterpret_cast<float*>(blob + G.off_c0)[1] = scale;
+    reinterpret_cast<float*>(blob + G.off_c0)[2] = 1.f / scale;
+    reinterpret_cast<float*>(blob + G.off_c0)[3] = b3[0];
+  }
+}
+
 template <int PREC>
 __global__ void k_pack_umma(const float* __restrict__ theta, PackGeom G, unsigned char* blob0,
                             unsigned char* blob1) {
@@ -1072,7 +1138,16 @@ __global__ void k_pack_umma(const float* __restrict__ theta, PackGeom G, unsigne
       rank = m / hN;
       l = G.NA / 2 + m % hN;
     }
-    const float v = (k < G.H1 && n < G.H2) ? W2[(long long)k * G.H2 + n] : 0.f;
+    float v = 0.f;
+    if (G.ts) {
+      const int j = reinterpret_cast<const int*>(blob0 + G.off_w3)[n];   // written by k_pack_head
+      if (j >= 0 && k <= G.H1) {
+        const float sw = reinterpret_cast<const float*>(blob0 + G.off_c0)[1] * fabsf(w3[j]);
+        v = sw * (k < G.H1 ? W2[(long long)k * G.H2 + j] : b2[j]);       // one fp32 rounding, then fp16
+      }
+    } else {
+      v = (k < G.H1 && n < G.H2) ? W2[(long long)k * G.H2 + n] : 0.f;
+    }
     unsigned char* blob = rank ? blob1 : blob0;
     const long long off = (long long)G.off_w2 + (long long)(k / 8) * ((G.H2P / 2) * 16) +
                           (long long)(l / 8) * 128 + (l % 8) * 16 + (k % 8) * 2;
@@ -1089,12 +1164,14 @@ __global__ void k_pack_umma(const float* __restrict__ theta, PackGeom G, unsigne
     if (j < G.H1) {
       if (k < K1) v = W1[(long long)k * G.H1 + j];
       else if (k == K1) v = b1[j];
+    } else if (G.ts && j == G.H1 && k == K1) {
+      v = 1.f;                                    // the always-one feature that carries layer 2's bias
     }
     unsigned char* blob = rank ? blob1 : blob0;
     const long long off = (long long)G.off_w1 + (long long)(k / 8) * ((G.H1P / 2) * 16) +
                           (long long)(l / 8) * 128 + (l % 8) * 16 + (k % 8) * 2;
     *reinterpret_cast<unsigned short*>(blob + off) = to_h<PREC>(v);
-  } else if (gid < nW2 + nW1 + G.H2P) {
+  } else if (!G.ts && gid < nW2 + nW1 + G.H2P) {
     const int j = (int)(gid - nW2 - nW1);
     const float w = (j < G.H2) ? w3[j] : 0.f;
     const float nb = (j < G.H2) ? -b2[j] : 0.f;
@@ -1103,7 +1180,7 @@ __global__ void k_pack_umma(const float* __restrict__ theta, PackGeom G, unsigne
       reinterpret_cast<float*>(blob + G.off_w3)[j] = w;
       reinterpret_cast<float*>(blob + G.off_nb2)[j] = nb;
     }
-  } else if (gid == nW2 + nW1 + G.H2P) {
+  } else if (!G.ts && gid == nW2 + nW1 + G.H2P) {
     float c0 = b3[0];
     for (int j = 0; j < G.H2; ++j) c0 = fmaf(w3[j], b2[j], c0);
     *reinterpret_cast<float*>(blob0 + G.off_c0) = c0;
@@ -1115,7 +1192,7 @@ static bool make_geom(const rlc_critic* c, PackGeom& G, int ts) {
   memset(&G, 0, sizeof(G));
   G.S = c->S; G.A = c->A; G.H1 = c->H1; G.H2 = c->H2; G.ts = ts;
   G.K1P = (c->S + c->A + 1 + 15) & ~15;
-  G.H1P = (c->H1 + 15) & ~15;
+  G.H1P = (c->H1 + (ts ? 1 : 0) + 15) & ~15;   // TS: + the always-one feature (bias of layer 2)
   G.H2P = (c->H2 + 15) & ~15;
   if (G.K1P > 64 || G.H2P > 480 || G.H2P < 32) return false;
   // layer-2 N split: one instruction if <= 256 else two halves rounded to 16
@@ -1173,12 +1250,12 @@ static SmemPlan plan_smem(const PackGeom& G) {
   return p;
 }
 
-// 1 = TS variant (layer-2 A operand from tensor memory), 0 = SS variant (shared-memory ring)
+// 1 = TS variant (layer-2 A operand from tensor memory, default), 0 = SS variant (shared-memory ring)
 static int umma_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("RLC_UMMA_MODE");
-    mode = (e && (e[0] == 't' || e[0] == 'T')) ? 1 : 0;   // SS stays the default until TS is faster
+    mode = (e && (e[0] == 's' || e[0] == 'S')) ? 0 : 1;
   }
   return mode;
 }
@@ -1225,6 +1302,10 @@ static int get_pack(rlc_handle* h, const rlc_critic* c, int prec, const PackGeom
     unsigned char* b1 = b0 + G.blob_bytes;
     const long long n = (long long)G.H1P * G.H2P + (long long)G.K1P * G.H1P + G.H2P + 1;
     const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (G.ts) {
+      k_pack_head<<<1, 32, 0, st>>>(c->theta, G, b0, b1);
+      RLC_LAUNCH_CHECK(h);
+    }
     if (prec == RLC_PREC_BF16) k_pack_umma<RLC_PREC_BF16><<<blocks, 256, 0, st>>>(c->theta, G, b0, b1);
     else k_pack_umma<RLC_PREC_FP16><<<blocks, 256, 0, st>>>(c->theta, G, b0, b1);
     RLC_LAUNCH_CHECK(h);
@@ -1306,7 +1387,8 @@ int rlc_eval_umma(rlc_handle* h, const rlc_critic* c, const float* s, int B, con
     P.prof = prof_dev;
   }
   void (*kern)(const UmmaParams) =
-      ts ? (prec == RLC_PREC_BF16 ? k_critic_umma_ts<RLC_PREC_BF16> : k_critic_umma_ts<RLC_PREC_FP16>)
+      ts ? (P.prof ? (prec == RLC_PREC_BF16 ? k_critic_umma_ts<RLC_PREC_BF16, true> : k_critic_umma_ts<RLC_PREC_FP16, true>)
+                   : (prec == RLC_PREC_BF16 ? k_critic_umma_ts<RLC_PREC_BF16, false> : k_critic_umma_ts<RLC_PREC_FP16, false>))
          : (prec == RLC_PREC_BF16 ? k_critic_umma<RLC_PREC_BF16> : k_critic_umma<RLC_PREC_FP16>);
   RLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
   RLC_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
@@ -1318,14 +1400,16 @@ int rlc_eval_umma(rlc_handle* h, const rlc_critic* c, const float* s, int B, con
     const double T = (double)o[0], nt = (double)(o[6] > 0 ? o[6] : 1);
     fprintf(stderr, "[umma prof pair0] tiles %lld total %.0f cyc (%.0f/tile) | MMA: waitX %.1f%% waitH1 %.1f%% waitL2E %.1f%% "
             "issueL1 %.1f%% issueL2 %.1f%% | producer wait %.1f%% work %.1f%% | ep1 wait %.1f%% work %.1f%% | "
-            "ep2 wait %.1f%% work %.1f%% || ep1 ld+wait %.1f%% | ep2 first ld+wait %.1f%% pairbar %.1f%%\n", o[6], T, T / nt,
+            "ep2 wait %.1f%% work %.1f%% || ep1 ld+wait %.1f%% thru-st-issue %.1f%% wait::st %.1f%% | ep2 first ld+wait %.1f%% pairbar %.1f%%\n", o[6], T, T / nt,
             100 * o[1] / T, 100 * o[2] / T, 100 * o[3] / T,
             100 * o[4] / T, 100 * o[5] / T, 100 * o[8] / T, 100 * o[9] / T, 100 * o[16] / T, 100 * o[17] / T,
-            100 * o[24] / T, 100 * o[25] / T, 100 * o[18] / T, 100 * o[26] / T, 100 * o[27] / T);
+            100 * o[24] / T, 100 * o[25] / T, 100 * o[18] / T, 100 * o[19] / T, 100 * o[20] / T, 100 * o[26] / T, 100 * o[27] / T);
   }
   RLC_LAUNCH_CHECK(h);
   return RLC_OK;
 }
+
+extern "C" int rlc_umma_mode(void) { return umma_mode(); }
 
 // Debug/diagnostic: last error flag raised by a bounded wait inside the kernel (0 = none).
 extern "C" int rlc_umma_last_error(rlc_handle* h, void* stream) {
