@@ -338,8 +338,8 @@ class CriticOptimizer:
         B = s.shape[0]
         grad, loss, q = self.critic.grads(s, a, y, b_total=B * world_size)
         if world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.pg)
+            from .parallel import allreduce_grad_
+            allreduce_grad_(grad, self.pg)
         self.t += 1
         self.critic.eng.adam_step(self.critic.theta, grad, self.m, self.v, self.t, self.lr, self.variant,
                                   target=None if self.target is None else self.target.theta, tau=self.tau)
