@@ -232,7 +232,7 @@ def run_b200(args, rank, local_rank, world):
               "rel_err_max": float(err.max())}
     if prec in ("fp16", "bf16"):
         q_rnd = onp.tin_eval_rounded(s_np[rows], a_np, params, prec,
-                                       head="folded" if eng.lib.rlc_umma_mode() == 1 else "ss")
+                                       head=critic.tensor_arithmetic(True))
         d = np.abs(q_gpu - q_rnd) / den
         parity["vs_stated_arithmetic_rms"] = float(np.sqrt((d ** 2).mean()))
         parity["vs_stated_arithmetic_max"] = float(d.max())
@@ -362,7 +362,7 @@ def run_b200(args, rank, local_rank, world):
                     "wall_ms_per_step": e2e_wall_ms / args.steps,
                     "api": "Critic.eval_into + Engine.fkl on pinned host states/logp, loss read back every step"},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "k_critic_umma (K1 fused T-in critic eval)", "bound": "tensor",
+            "roofline": {"kernel": "K1 fused T-in critic eval: k_critic_umma_grid (+ k_grid_parts pre-pass) [%s arithmetic]" % critic.tensor_arithmetic(True), "bound": "tensor",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "peak_source": f"{peak_src} bf16_tflops (burst; sustained "
                                         f"{peaks.get('bf16_tflops_sustained', 1400.0)})",

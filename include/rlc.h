@@ -117,11 +117,17 @@ int rlc_tmid_eval_grad(rlc_handle* h, const rlc_critic* c, const float* s, int B
 /* Diagnostic: synchronises `stream` and returns the code raised by a bounded mbarrier wait inside
  * the tcgen05 kernel (0 = none, <0 = CUDA error). The flag is cleared on read. */
 int rlc_umma_last_error(rlc_handle* h, void* stream);
-/* Diagnostic: which stated arithmetic the tensor path uses (tests pick the matching oracle).
- * 0 = "SS": q = b3 + sum_j w3_j relu(h1.fp16(W2[:,j]) + b2_j)                      (fp32 head)
- * 1 = "TS": q = b3 + 2^-k sum_j sign(w3_j) relu(h1.fp16(2^k|w3_j|W2[:,j]) + fp16(2^k|w3_j|b2_j))
- *           (output head folded into layer 2's operands).  Env RLC_UMMA_MODE. */
-int rlc_umma_mode(void);
+/* Diagnostic: which stated arithmetic the tensor path uses for this critic shape and action layout
+ * (tests pick the matching oracle restatement, oracle_np.tin_eval_rounded(head=...)):
+ *  -1  shape not supported by the tensor path
+ *   0  "ss"     q = b3 + sum_j w3_j relu(h1.r(W2[:,j]) + b2_j), h1 = r(relu(r([s;a;1]).r(W1')))
+ *   1  "folded" same h1; output head folded into layer 2's operands:
+ *               q = b3 + 2^-k sum_j sign(w3_j) relu(h1.r(2^k|w3_j|W2[:,j]) + r(2^k|w3_j|b2_j))
+ *   3  "grid"   shared action grids: hoisted layer 1, h1 = relu(r(r(b1+W1s s_b) + r(W1a a_n))),
+ *               then the folded head (K1-grid kernel)
+ * r() = rounding to the operand type (fp16/bf16); accumulation is fp32.  Env knobs (debug):
+ * RLC_UMMA_MODE=ss selects 0; RLC_UMMA_GRID=0 disables 3. */
+int rlc_umma_mode(const rlc_critic* c, int act_mode);
 
 /* ---- per-state reductions (rows a3, a4, a8, a9, a10) ------------------------------------ */
 /* row.argsort()[::-1][:k] (ActorExpert.py:177, qt_opt_network.py:166): descending, ties -> larger

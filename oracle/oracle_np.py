@@ -96,6 +96,11 @@ def tin_eval_rounded(s, a, params, kind="fp16", head="ss"):
                       with 2^k max|w3| in [1,2); the products 2^k|w3_j|*x are formed in fp32 (one
                       rounding, as the pack kernel does) before the rounding to ``kind``.
 
+    ``head="grid"``   shared action grids only (K1-grid kernel): layer 1 is hoisted,
+                      h1 = relu(r(r(b1 + W1s s_b) + r(W1a a_n)))  -- the two partial pre-activations
+                      are formed in fp32 and rounded to ``kind``, their sum is rounded once more
+                      (one packed fma) -- followed by the folded head.
+
     The CUDA kernel must match THIS to ~1e-5 rms (it does exactly this arithmetic with fp32
     accumulators); the distance from ``tin_eval(..., float64)`` is the cost of the operand type."""
     W1, b1, W2, b2, W3, b3 = [np.asarray(p, np.float64) for p in params]
@@ -105,7 +110,27 @@ def tin_eval_rounded(s, a, params, kind="fp16", head="ss"):
     N = a.shape[0] if a.ndim == 2 else a.shape[1]
     x = np.concatenate([stack_state_major(s, N), stack_actions(a, B)], axis=1)
     r = lambda z: round_operand(z, kind)
-    h1 = r(np.maximum(r(x) @ r(W1).T + r(b1), 0))
+    if head == "grid":
+        if a.ndim != 2:
+            raise ValueError("head='grid' is the shared-grid arithmetic")
+        S = s.shape[1]
+        f32 = np.float32
+
+        def fma_chain(xs, Wt, init):
+            """acc = init; for k: acc = fl32(acc + x_k * W_k)  -- the pre-pass kernel's fp32 FMA
+            order (the product of two fp32 values is exact in fp64)."""
+            acc = np.broadcast_to(np.asarray(init, f32), (xs.shape[0], Wt.shape[1])).astype(f32)
+            for k in range(xs.shape[1]):
+                acc = (acc.astype(np.float64) + xs[:, k:k + 1].astype(np.float64) * Wt[k].astype(np.float64)).astype(f32)
+            return acc
+
+        W1f = np.asarray(params[0], f32)                       # [H1, S+A]
+        ps = r(fma_chain(np.asarray(s, f32), W1f[:, :S].T.copy(), np.asarray(params[1], f32)))
+        pa = r(fma_chain(np.asarray(a, f32), W1f[:, S:].T.copy(), f32(0)))
+        h1 = r(np.maximum(ps[:, None, :] + pa[None, :, :], 0)).reshape(B * N, -1)
+        head = "folded"
+    else:
+        h1 = r(np.maximum(r(x) @ r(W1).T + r(b1), 0))
     w3 = W3.reshape(-1)
     if head == "ss":
         h2 = np.maximum(h1 @ r(W2).T + b2, 0)

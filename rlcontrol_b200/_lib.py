@@ -46,7 +46,7 @@ SIGNATURES = {
     "rlc_critic_eval": (_i, [_p, _cr, _p, _i, _p, _i, _i, _i, _p, _p]),
     "rlc_tmid_eval_grad": (_i, [_p, _cr, _p, _i, _p, _i, _i, _p, _p, _p]),
     "rlc_umma_last_error": (_i, [_p, _p]),
-    "rlc_umma_mode": (_i, []),
+    "rlc_umma_mode": (_i, [_cr, _i]),
     "rlc_reduce_topk": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p]),
     "rlc_reduce_stats": (_i, [_p, _p, _i, _i, _p, _p, _p, _p]),
     "rlc_reduce_lse": (_i, [_p, _p, _i, _i, _i, _p, _p]),

@@ -1198,6 +1198,13 @@ static bool make_geom(const rlc_critic* c, PackGeom& G, int ts) {
   // layer-2 N split: one instruction if <= 256 else two halves rounded to 16
   if (G.H2P <= 256) { G.NA = G.H2P; G.NB = 0; }
   else { G.NA = ((G.H2P / 2) + 15) & ~15; G.NB = G.H2P - G.NA; }
+  {
+    const char* e = getenv("RLC_UMMA_NA");      // tuning knob: columns of the first layer-2 MMA
+    if (e) {
+      const int na = atoi(e);
+      if (na >= 16 && (na & 15) == 0 && na <= 256 && na <= G.H2P && G.H2P - na <= 256) { G.NA = na; G.NB = G.H2P - na; }
+    }
+  }
   if (G.NA > 256 || G.NB > 256) return false;
   const int free_cols = 512 - G.H2P;
   int ch;
@@ -1315,6 +1322,8 @@ static int get_pack(rlc_handle* h, const rlc_critic* c, int prec, const PackGeom
   return RLC_OK;
 }
 
+#include "critic_umma_grid.cuh"
+
 int rlc_eval_umma(rlc_handle* h, const rlc_critic* c, const float* s, int B, const float* a, int N,
                   int act_mode, int prec, float* q_out, cudaStream_t st) {
   PackGeom G;
@@ -1326,6 +1335,10 @@ int rlc_eval_umma(rlc_handle* h, const rlc_critic* c, const float* s, int B, con
   rlc_pack* pk = nullptr;
   int rc = get_pack(h, c, prec, G, st, &pk);
   if (rc) return rc;
+  if (ts && act_mode == RLC_ACT_SHARED && grid_mode()) {
+    rc = rlc_eval_umma_grid(h, c, G, pk, s, B, a, N, prec, q_out, st);
+    if (rc != RLC_ERR_UNSUPPORTED) return rc;       // geometry the grid kernel cannot take: generic TS kernel
+  }
   int* err = h->err_flag;
 
   UmmaParams P;
@@ -1409,7 +1422,16 @@ int rlc_eval_umma(rlc_handle* h, const rlc_critic* c, const float* s, int B, con
   return RLC_OK;
 }
 
-extern "C" int rlc_umma_mode(void) { return umma_mode(); }
+extern "C" int rlc_umma_mode(const rlc_critic* c, int act_mode) {
+  if (!critic_ok(c) || c->topology != RLC_TIN) return -1;
+  PackGeom G;
+  const int ts = umma_mode();
+  if (!make_geom(c, G, ts)) return -1;
+  if (!ts) return 0;
+  GridPlan gp;
+  if (act_mode == RLC_ACT_SHARED && grid_mode() && plan_grid(G, gp)) return 3;
+  return 1;
+}
 
 // Debug/diagnostic: last error flag raised by a bounded wait inside the kernel (0 = none).
 extern "C" int rlc_umma_last_error(rlc_handle* h, void* stream) {

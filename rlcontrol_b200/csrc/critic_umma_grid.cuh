@@ -1,0 +1,580 @@
+// K1-grid: fused T-in critic evaluation for a SHARED action grid a[N,A] (ForwardKL / ReverseKL
+// quadrature, forwardkl_network.py:104-105,160-164).  Included by critic_umma.cu.
+//
+// With a shared grid, layer 1 separates:  W1 [s_b ; a_n] + b1 = PS[b] + PA[n]  with
+//   PS[b] = b1 + W1s s_b   (one row per state)      PA[n] = W1a a_n   (one row per grid action)
+// so the B*N x (S+A) x H1 contraction collapses to B + N rows, computed once per launch by a small
+// fp32 pre-pass (k_grid_parts) and stored as fp16.  The main kernel then needs no layer-1 MMA, no
+// X tile and -- the point -- no tcgen05.ld of a layer-1 accumulator: epilogue 1 forms
+//   h1 = relu(PS[b] + PA[n])          (one HFMA2.RELU per two activations, fp16)
+// from shared memory and writes it straight into tensor memory as layer 2's A operand, running
+// AHEAD of the tensor pipe (it depends on nothing the MMA produces).  Per 128-row tile the warps'
+// TMEM traffic drops from 463 KB (205 KB ld + 102 KB st + 156 KB ld) to 258 KB and the tensor pipe
+// only runs layer 2.
+//
+// CTA tile = 4 states x 32 grid actions (TMEM lane r <-> state b0 + r/32, action n0 + r%32), so a
+// warp (one TMEM lane quarter) owns one state and PA tiles are reused by four states.  A CTA pair
+// (cta_group::2, M=256) covers two consecutive CTA tiles.  Layer 2 and the output head are the
+// TS variant's (folded head, sign-partitioned columns; k_pack_head).
+//
+// Layer 2 runs in TWO PASSES per tile: all K chunks into accumulator half A (columns [0,NA)), then
+// all K chunks into half B.  The whole tile's activations (H1P fp16 = H1P/2 TMEM columns) stay
+// resident next to the accumulator (H2P + H1P/2 <= 512 columns: 304 + 208 at 400-300), so
+// epilogue 2 drains half A while the tensor pipe is busy with pass B, and half B while it runs
+// pass A of the next tile: the accumulator hand-over costs the tensor pipe nothing.
+//
+// Warps: 0 MMA issuer (leader) | 1 loader (cp.async.bulk of PA chunk tiles and PS rows into
+// shared-memory rings, mbarrier complete_tx) | 4-7 epilogue 1 | 8-15 epilogue 2.
+#pragma once
+
+#define GR_THREADS 512
+#define GR_PA_STAGES 4
+#define GR_MAX_NCH 8
+#define GR_PITCH_PAD 8  // halfs of padding per PA row: pitch (CH+8)*2 B keeps 16-byte LDS conflict-free
+
+struct GridParams {
+  float* q;
+  int B, N;
+  int H1P, H2P, NA, NB;
+  int CH, nch, nbuf;          // layer-1 feature chunking: chunk c = features [c*CH, min(H1P,(c+1)*CH))
+  int NT;                     // 32-action blocks per state = ceil(N/32)
+  long long num_cta_tiles;    // ceil(B/4) * NT
+  int num_pair_tiles;
+  const __half* ps;           // [B][H1P]                fp16/bf16 bits
+  const __half* pa;           // [nch][NT*32][CH+8]      fp16/bf16 bits, zero rows past N
+  const unsigned char* blob[2];
+  int off_w2, off_w1, off_c0;
+  int sm_w2, sm_pa, sm_ps, sm_qp, sm_bar, pa_stage_bytes, ps_stage_bytes;
+  int* err;
+  long long* prof;            // RLC_UMMA_PROF=1: 32 x int64 per pair
+};
+
+enum {
+  GB_PA_FULL = 0,     // [4]  count 1 + tx   (local)    loader -> ep1
+  GB_PA_EMPTY = 4,    // [4]  count 4        (local)    ep1 warps -> loader
+  GB_PS_FULL = 8,     // [2]  count 1 + tx   (local)    loader -> ep1
+  GB_PS_EMPTY = 10,   // [2]  count 4        (local)    ep1 warps -> loader
+  GB_H1_FULL = 12,    // [8]  count 8        (leader)   ep1 (4 warps x 2 CTAs) -> MMA, one per K chunk
+  GB_H1_EMPTY = 20,   // [8]  count 1        (both)     MMA commit (last pass over the chunk) -> ep1
+  GB_L2_FULL = 28,    // [2]  count 1        (both)     MMA commit -> ep2 (half A, half B)
+  GB_L2_EMPTY = 30,   // [2]  count 16       (leader)   ep2 (8 warps x 2 CTAs) -> MMA
+  GB_COUNT = 32
+};
+
+namespace um {
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+template <int PREC>
+__device__ __forceinline__ uint32_t add_relu2(uint32_t a, uint32_t b) {
+  uint32_t r;   // relu(a + b) on two packed halves, one rounding (fma with 1.0)
+  if (PREC == RLC_PREC_BF16)
+    asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(0x3F803F80u), "r"(b));
+  else
+    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(0x3C003C00u), "r"(b));
+  return r;
+}
+}  // namespace um
+
+// Pre-pass (fp32 FMA, then one rounding to the operand type):
+//   PS[b][j] = b1[j] + sum_k clip(s[b][k]) W1[k][j]   (j < H1);  PS[b][H1] = 1 (the bias carrier of
+//   layer 2, see k_pack_head);  PA[c][n][jj] = sum_k a[n][k] W1[S+k][c*CH+jj].
+template <int PREC>
+__global__ void k_grid_parts(const float* __restrict__ theta, const float* __restrict__ s,
+                             const float* __restrict__ a, const float* __restrict__ smin,
+                             const float* __restrict__ smax, int B, int N, int S, int A, int H1, int H2,
+                             int H1P, int CH, int nch, int NT, unsigned short* __restrict__ PS,
+                             unsigned short* __restrict__ PA) {
+  const ThetaView t = theta_view(RLC_TIN, S, A, H1, H2);
+  const float* W1 = theta + t.oW1;   // [S+A][H1]
+  const float* b1 = theta + t.ob1;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nps = (long long)B * H1P;
+  const int pitch = CH + GR_PITCH_PAD;
+  const long long npa = (long long)nch * NT * 32 * pitch;
+  if (gid < nps) {
+    const int b = (int)(gid / H1P), j = (int)(gid % H1P);
+    float acc = 0.f;
+    if (j < H1) {
+      acc = b1[j];
+      for (int k = 0; k < S; ++k) {
+        float x = __ldg(s + (size_t)b * S + k);
+        if (smin) x = fminf(fmaxf(x, __ldg(smin + k)), __ldg(smax + k));
+        acc = fmaf(x, W1[(size_t)k * H1 + j], acc);
+      }
+    } else if (j == H1) {
+      acc = 1.f;
+    }
+    PS[gid] = to_h<PREC>(acc);
+  } else if (gid < nps + npa) {
+    const long long g = gid - nps;
+    const int jj = (int)(g % pitch);
+    const long long rn = g / pitch;
+    const int n = (int)(rn % ((long long)NT * 32)), c = (int)(rn / ((long long)NT * 32));
+    const int j = c * CH + jj;
+    float acc = 0.f;
+    if (jj < CH && j < H1 && n < N) {
+      for (int k = 0; k < A; ++k) acc = fmaf(__ldg(a + (size_t)n * A + k), W1[(size_t)(S + k) * H1 + j], acc);
+    }
+    PA[g] = to_h<PREC>(acc);
+  }
+}
+
+template <int PREC, bool PROF>
+__global__ void __launch_bounds__(GR_THREADS, 1) k_critic_umma_grid(const GridParams P) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw_addr = um::smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  unsigned char* base_ptr = smem_raw + (base - raw_addr);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = um::cta_rank();
+  const uint32_t pair = um::cluster_id_x();
+  const uint32_t npairs = um::num_clusters_x();
+
+  const uint32_t sW2 = base + P.sm_w2, sPA = base + P.sm_pa, sPS = base + P.sm_ps, sBar = base + P.sm_bar;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + P.sm_bar + GB_COUNT * 8);
+  float* qpart = reinterpret_cast<float*>(base_ptr + P.sm_qp);   // [2][128] partial sums
+  auto bar = [&](int i) -> uint32_t { return sBar + 8u * (uint32_t)i; };
+
+  // ---- prologue: resident W2' -> smem, barriers, TMEM ----
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(P.blob[rank]);
+    uint4* dW2 = reinterpret_cast<uint4*>(base_ptr + P.sm_w2);
+    const int n2 = (P.off_w1 - P.off_w2) >> 4;
+    for (int i = tid; i < n2; i += GR_THREADS) dW2[i] = __ldg(src + (P.off_w2 >> 4) + i);
+  }
+  if (tid == 0) {
+    for (int i = 0; i < GR_PA_STAGES; ++i) {
+      um::mbar_init(bar(GB_PA_FULL + i), 1);
+      um::mbar_init(bar(GB_PA_EMPTY + i), 4);
+    }
+    for (int i = 0; i < 2; ++i) {
+      um::mbar_init(bar(GB_PS_FULL + i), 1);
+      um::mbar_init(bar(GB_PS_EMPTY + i), 4);
+      um::mbar_init(bar(GB_L2_FULL + i), 1);
+      um::mbar_init(bar(GB_L2_EMPTY + i), 16);
+    }
+    for (int i = 0; i < GR_MAX_NCH; ++i) {
+      um::mbar_init(bar(GB_H1_FULL + i), 8);
+      um::mbar_init(bar(GB_H1_EMPTY + i), 1);
+    }
+    um::fence_mbar_init();
+  }
+  um::fence_proxy_async();
+  if (warp == 0) um::tmem_alloc2(um::smem_u32(tmem_slot), 512);
+  um::tc_fence_before();
+  __syncthreads();
+  um::cluster_sync();
+  um::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  long long pa_ = 0, pb_ = 0, pc_ = 0, pd_ = 0, pe_ = 0;   // PROF accumulators (meaning per role)
+  const bool prof = PROF && P.prof != nullptr;
+  const long long t_begin = prof ? clock64() : 0;
+#define GPROF_T() ((PROF && prof) ? clock64() : 0)
+
+  const int ntiles = (P.num_pair_tiles > (int)pair)
+                         ? (P.num_pair_tiles - (int)pair + (int)npairs - 1) / (int)npairs
+                         : 0;
+  const int nch = P.nch, CH = P.CH, last_w = P.H1P - (P.nch - 1) * P.CH;
+  const uint32_t H1COL = (uint32_t)P.H2P;            // TMEM column of activation buffer 0
+  const uint32_t bufcols = (uint32_t)(CH >> 1);      // two halves per 32-bit cell
+  // CTA tile of pair-tile t: ct = 2*t + rank -> state group ct / NT, action block ct % NT
+  auto tile_coords = [&](int tl, int& b0, int& n0) {
+    long long ct = 2ll * ((long long)pair + (long long)tl * npairs) + rank;
+    if (ct >= P.num_cta_tiles) ct = P.num_cta_tiles - 1;   // odd tail: recompute the last tile, never stored twice
+    b0 = (int)(ct / P.NT) * 4;
+    n0 = (int)(ct % P.NT) * 32;
+  };
+
+  if (warp == 0) {
+    // =================================== MMA issuer (leader CTA) ===================================
+    if (rank == 0) {
+      const bool issuer = um::elect_one();
+      const uint32_t fmt = (PREC == RLC_PREC_BF16) ? 1u : 0u;
+      const uint32_t lbo_w2 = (uint32_t)(P.H2P / 2) * 16u;
+      const uint32_t w2_lo = um::desc_lo(sW2, lbo_w2);
+      const uint32_t w2_kstep = (2u * lbo_w2) >> 4;
+      const uint32_t w2_half_off = (uint32_t)(P.NA / 2);
+      const uint32_t idA = um::make_idesc(fmt, 256, P.NA);
+      const uint32_t idB = um::make_idesc(fmt, 256, P.NB > 0 ? P.NB : 16);
+      const bool two_halves = P.NB > 0;
+      const uint32_t dL2A = tmem_base, dL2B = tmem_base + (uint32_t)P.NA;
+      bool ok = true;
+      for (int tl = 0; tl < ntiles && ok; ++tl) {
+        const uint32_t tpar = (uint32_t)(tl & 1);
+        for (int pass = 0; pass < (two_halves ? 2 : 1) && ok; ++pass) {
+          long long t0 = GPROF_T();
+          ok = ok && um::mbar_wait(bar(GB_L2_EMPTY + pass), tpar ^ 1u, P.err, 14 + pass);
+          long long t1 = GPROF_T();
+          pb_ += t1 - t0;
+          const bool last_pass = pass == (two_halves ? 1 : 0);
+          for (int c = 0; c < nch && ok; ++c) {
+            long long t2 = GPROF_T();
+            if (pass == 0) ok = ok && um::mbar_wait(bar(GB_H1_FULL + c), tpar, P.err, 13);
+            um::tc_fence_after();
+            long long t3 = GPROF_T();
+            pa_ += t3 - t2;
+            const int ksteps = (c == nch - 1 ? last_w : CH) >> 4;
+            const uint32_t a0 = tmem_base + H1COL + (uint32_t)c * bufcols;       // 8 columns per K=16 step
+            const uint32_t b0 = w2_lo + (uint32_t)(c * (CH >> 3)) * (lbo_w2 >> 4) + (pass ? w2_half_off : 0u);
+            const uint32_t acc0 = c > 0 ? 1u : 0u;
+            if (ok && issuer) {
+              const uint32_t d = pass ? dL2B : dL2A, idesc = pass ? idB : idA;
+#pragma unroll 1
+              for (int k = 0; k < ksteps; ++k)
+                um::mma2_ts(d, a0 + 8u * (uint32_t)k, um::desc64(b0 + (uint32_t)k * w2_kstep), idesc,
+                            acc0 | (uint32_t)(k > 0));
+              if (last_pass) um::commit2(bar(GB_H1_EMPTY + c));      // chunk buffer free for the next tile
+              if (c == nch - 1) um::commit2(bar(GB_L2_FULL + pass));
+            }
+            __syncwarp();
+            pc_ += GPROF_T() - t3;
+          }
+        }
+      }
+      if (prof && issuer) {
+        long long* o = P.prof + (size_t)pair * 32;
+        o[0] = clock64() - t_begin; o[1] = pa_; o[2] = pb_; o[3] = pc_; o[6] = ntiles;
+      }
+    }
+  } else if (warp == 1) {
+    // =================================== loader (one lane) ===================================
+    if (lane == 0) {
+      bool ok = true;
+      const int pitch_b = (CH + GR_PITCH_PAD) * 2;
+      const uint32_t pa_tile_bytes = 32u * (uint32_t)pitch_b;
+      const uint32_t ps_row_bytes = (uint32_t)P.H1P * 2u;
+      const size_t pa_chunk_stride = (size_t)P.NT * 32 * pitch_b;   // bytes between chunks in PA
+      uint32_t st = 0, spar = 0;
+      for (int tl = 0; tl < ntiles && ok; ++tl) {
+        int b0, n0;
+        tile_coords(tl, b0, n0);
+        const int pb = tl & 1;
+        ok = um::mbar_wait(bar(GB_PS_EMPTY + pb), (uint32_t)(((tl >> 1) & 1) ^ 1), P.err, 51);
+        if (!ok) break;
+        um::mbar_expect_tx(bar(GB_PS_FULL + pb), 4u * ps_row_bytes);
+        for (int i = 0; i < 4; ++i) {
+          const int b = (b0 + i < P.B) ? b0 + i : P.B - 1;
+          um::bulk_g2s(sPS + (uint32_t)(pb * P.ps_stage_bytes) + (uint32_t)i * ps_row_bytes,
+                       reinterpret_cast<const unsigned char*>(P.ps) + (size_t)b * ps_row_bytes, ps_row_bytes,
+                       bar(GB_PS_FULL + pb));
+        }
+        for (int c = 0; c < nch && ok; ++c) {
+          ok = um::mbar_wait(bar(GB_PA_EMPTY + (int)st), spar ^ 1u, P.err, 52);
+          if (!ok) break;
+          um::mbar_expect_tx(bar(GB_PA_FULL + (int)st), pa_tile_bytes);
+          um::bulk_g2s(sPA + st * (uint32_t)P.pa_stage_bytes,
+                       reinterpret_cast<const unsigned char*>(P.pa) + (size_t)c * pa_chunk_stride +
+                           (size_t)n0 * pitch_b,
+                       pa_tile_bytes, bar(GB_PA_FULL + (int)st));
+          if (++st == GR_PA_STAGES) { st = 0; spar ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===== epilogue 1: h1 = relu(PS[b] + PA[n]) (packed fp16) -> TMEM (layer 2's A operand) =====
+    const int q4 = warp & 3;                       // TMEM lane quarter == state b0 + q4 of the tile
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    const uint32_t h1f0 = um::mapa(bar(GB_H1_FULL), 0);
+    const int pitch_b = (CH + GR_PITCH_PAD) * 2;
+    bool ok = true;
+    uint32_t st = 0, spar = 0;
+    for (int tl = 0; tl < ntiles && ok; ++tl) {
+      const int pb = tl & 1;
+      const uint32_t tpar = (uint32_t)(tl & 1);
+      ok = um::mbar_wait(bar(GB_PS_FULL + pb), (uint32_t)((tl >> 1) & 1), P.err, 33);
+      if (!ok) break;
+      const unsigned char* ps_row = base_ptr + P.sm_ps + pb * P.ps_stage_bytes + q4 * (P.H1P * 2);
+      for (int c = 0; c < nch; ++c) {
+        long long t0 = GPROF_T();
+        ok = um::mbar_wait(bar(GB_PA_FULL + (int)st), spar, P.err, 31);
+        long long t1 = GPROF_T();
+        ok = ok && um::mbar_wait(bar(GB_H1_EMPTY + c), tpar ^ 1u, P.err, 32);
+        if (!ok) break;
+        um::tc_fence_after();
+        long long t2 = GPROF_T();
+        pa_ += t1 - t0;
+        pb_ += t2 - t1;
+        const int w = (c == nch - 1) ? last_w : CH;
+        const uint4* pa4 = reinterpret_cast<const uint4*>(base_ptr + P.sm_pa + st * P.pa_stage_bytes + lane * pitch_b);
+        const uint4* ps4 = reinterpret_cast<const uint4*>(ps_row + c * CH * 2);
+        const uint32_t tcol = lane_addr + H1COL + (uint32_t)c * bufcols;
+        if (w == 96) {
+          // full chunk: straight-line code, 12 x (2 LDS.128 + 4 HFMA2.RELU) + 3 STTM.x16
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {
+            uint32_t o[16];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 x = pa4[p * 4 + g];
+              const uint4 y = ps4[p * 4 + g];
+              o[g * 4 + 0] = um::add_relu2<PREC>(x.x, y.x);
+              o[g * 4 + 1] = um::add_relu2<PREC>(x.y, y.y);
+              o[g * 4 + 2] = um::add_relu2<PREC>(x.z, y.z);
+              o[g * 4 + 3] = um::add_relu2<PREC>(x.w, y.w);
+            }
+            um::tmem_st16p(tcol + (uint32_t)(p * 16), o);
+          }
+        } else {
+#pragma unroll 1
+          for (int p = 0; p * 16 < w; ++p) {      // 16 activations (8 packed cells) per step
+            uint32_t o[8];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const uint4 x = pa4[p * 2 + g];
+              const uint4 y = ps4[p * 2 + g];
+              o[g * 4 + 0] = um::add_relu2<PREC>(x.x, y.x);
+              o[g * 4 + 1] = um::add_relu2<PREC>(x.y, y.y);
+              o[g * 4 + 2] = um::add_relu2<PREC>(x.z, y.z);
+              o[g * 4 + 3] = um::add_relu2<PREC>(x.w, y.w);
+            }
+            um::tmem_st8(tcol + (uint32_t)(p * 8), o);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) um::mbar_arrive_local(bar(GB_PA_EMPTY + (int)st));   // PA stage consumed
+        long long t3 = GPROF_T();
+        um::tmem_st_wait();
+        um::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) um::mbar_arrive_cluster(h1f0 + 8u * (uint32_t)c);
+        long long t4 = GPROF_T();
+        pc_ += t3 - t2;
+        pd_ += t4 - t3;
+        if (++st == GR_PA_STAGES) { st = 0; spar ^= 1u; }
+      }
+      __syncwarp();
+      if (lane == 0) um::mbar_arrive_local(bar(GB_PS_EMPTY + pb));
+    }
+    if (prof && rank == 0 && tid == 128) {
+      long long* o = P.prof + (size_t)pair * 32 + 8; o[0] = pa_; o[1] = pb_; o[2] = pc_; o[3] = pd_;
+    }
+  } else if (warp >= 8) {
+    // ================ epilogue 2 (8 warps): L2 acc -> relu -> signed sum -> q ====================
+    const int q4 = warp & 3, chalf = (warp - 8) >> 2;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    const uint32_t l2e0 = um::mapa(bar(GB_L2_EMPTY + 0), 0);
+    const uint32_t l2e1 = um::mapa(bar(GB_L2_EMPTY + 1), 0);
+    const int npos = __ldg(reinterpret_cast<const int*>(P.blob[0] + P.off_c0));
+    const float inv_scale = __ldg(reinterpret_cast<const float*>(P.blob[0] + P.off_c0) + 2);
+    const float b3v = __ldg(reinterpret_cast<const float*>(P.blob[0] + P.off_c0) + 3);
+    const int rloc = q4 * 32 + lane;
+    bool ok = true;
+    for (int tl = 0; tl < ntiles && ok; ++tl) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int half = 0; half < 2; ++half) {
+        const int hb = half ? P.NA : 0, hn = half ? P.NB : P.NA;
+        long long t0 = GPROF_T();
+        if (hn > 0 || half == 0) {
+          ok = um::mbar_wait(bar(GB_L2_FULL + (hn > 0 ? half : 0)), (uint32_t)(tl & 1), P.err, 41);
+          if (!ok) break;
+          um::tc_fence_after();
+        }
+        long long t1 = GPROF_T();
+        pa_ += t1 - t0;
+        const int units = hn >> 3, u0 = chalf ? (units + 1) / 2 : 0, u1 = chalf ? units : (units + 1) / 2;
+        const int j_begin = hb + u0 * 8, j_end = hb + u1 * 8;
+        for (int jb = j_begin; jb < j_end; jb += 96) {
+          const int w = (j_end - jb < 96) ? (j_end - jb) : 96;
+          uint32_t v[96];
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {
+            if (p * 32 + 32 <= w) um::tmem_ld32p(lane_addr + (uint32_t)(jb + p * 32), v + p * 32);
+            else if (p * 32 < w) {
+              const int rem = w - p * 32;             // 8, 16 or 24
+              if (rem >= 16) um::tmem_ld16p(lane_addr + (uint32_t)(jb + p * 32), v + p * 32);
+              if (rem == 8) um::tmem_ld8p(lane_addr + (uint32_t)(jb + p * 32), v + p * 32);
+              if (rem == 24) um::tmem_ld8p(lane_addr + (uint32_t)(jb + p * 32 + 16), v + p * 32 + 16);
+            }
+          }
+          um::tmem_ld_wait();
+          { long long tt = GPROF_T(); pb_ += tt - t1; t1 = tt; }
+          if (jb + 96 >= j_end) {               // last round of this half: hand it back
+            um::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) um::mbar_arrive_cluster(half ? l2e1 : l2e0);
+          }
+          // acc += sign_j * relu(z_j): units of 8 columns carry one sign except the unit that
+          // straddles npos (at most one per row), which takes the per-column branch.
+#pragma unroll
+          for (int p = 0; p < 12; ++p) {
+            if (p * 8 < w) {
+              const int j = jb + p * 8;
+              if (j + 8 <= npos || j >= npos) {
+                const float sg = (j >= npos) ? -1.f : 1.f;
+                a0 = fmaf(fmaxf(__uint_as_float(v[p * 8 + 0]), 0.f), sg, a0);
+                a1 = fmaf(fmaxf(__uint_as_float(v[p * 8 + 1]), 0.f), sg, a1);
+                a2 = fmaf(fmaxf(__uint_as_float(v[p * 8 + 2]), 0.f), sg, a2);
+                a3 = fmaf(fmaxf(__uint_as_float(v[p * 8 + 3]), 0.f), sg, a3);
+                a0 = fmaf(fmaxf(__uint_as_float(v[p * 8 + 4]), 0.f), sg, a0);
+                a1 = fmaf(fmaxf(__uint_as_float(v[p * 8 + 5]), 0.f), sg, a1);
+                a2 = fmaf(fmaxf(__uint_as_float(v[p * 8 + 6]), 0.f), sg, a2);
+                a3 = fmaf(fmaxf(__uint_as_float(v[p * 8 + 7]), 0.f), sg, a3);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  a0 = fmaf(fmaxf(__uint_as_float(v[p * 8 + e]), 0.f), (j + e >= npos) ? -1.f : 1.f, a0);
+              }
+            }
+          }
+        }
+        if (j_begin >= j_end) {                 // nothing to drain for this warp: still hand back
+          um::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) um::mbar_arrive_cluster(half ? l2e1 : l2e0);
+        }
+        pc_ += GPROF_T() - t1;
+      }
+      if (!ok) break;
+      long long t5 = GPROF_T();
+      const float acc = (a0 + a1) + (a2 + a3);
+      float* qp = qpart + (tl & 1) * 128;
+      if (chalf) qp[rloc] = acc;
+      um::named_bar_sync(1, 256);
+      if (!chalf) {
+        const long long ct = 2ll * ((long long)pair + (long long)tl * npairs) + rank;
+        if (ct < P.num_cta_tiles) {
+          const int b = (int)(ct / P.NT) * 4 + q4, n = (int)(ct % P.NT) * 32 + lane;
+          if (b < P.B && n < P.N) P.q[(size_t)b * P.N + n] = fmaf(inv_scale, acc + qp[rloc], b3v);
+        }
+      }
+      pd_ += GPROF_T() - t5;
+    }
+    if (prof && rank == 0 && tid == 256) {
+      long long* o = P.prof + (size_t)pair * 32 + 16; o[0] = pa_; o[1] = pb_; o[2] = pc_; o[3] = pd_;
+    }
+  }
+#undef GPROF_T
+
+  um::tc_fence_before();
+  __syncthreads();
+  um::cluster_sync();
+  if (warp == 0) um::tmem_dealloc2(tmem_base, 512);
+}
+
+// host launcher --------------------------------------------------------------------------------
+static int grid_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("RLC_UMMA_GRID");
+    mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  return mode;
+}
+
+struct GridPlan {
+  int CH, nch, nbuf, sm_w2, sm_pa, sm_ps, sm_qp, sm_bar, pa_stage, ps_stage, total;
+};
+
+static bool plan_grid(const PackGeom& G, GridPlan& p) {
+  const int free_cols = 512 - G.H2P;
+  if (G.H1P / 2 > free_cols) return false;    // the tile's activations must fit next to the accumulator
+  int ch = 96;
+  const char* e = getenv("RLC_UMMA_GRID_CH");
+  if (e) { const int v = atoi(e); if (v >= 16 && v <= 96 && (v & 15) == 0) ch = v; }
+  if (ch > G.H1P) ch = G.H1P;
+  p.CH = ch;
+  p.nch = (G.H1P + ch - 1) / ch;
+  if (p.nch > GR_MAX_NCH) return false;
+  p.nbuf = p.nch;
+  p.sm_w2 = 0;
+  p.pa_stage = 32 * (ch + GR_PITCH_PAD) * 2;
+  p.sm_pa = ((G.off_w1 - G.off_w2) + 127) & ~127;
+  p.ps_stage = 4 * G.H1P * 2;
+  p.sm_ps = p.sm_pa + GR_PA_STAGES * p.pa_stage;
+  p.sm_qp = (p.sm_ps + 2 * p.ps_stage + 127) & ~127;
+  p.sm_bar = p.sm_qp + 1024;
+  p.total = p.sm_bar + GB_COUNT * 8 + 16 + 1024;
+  return true;
+}
+
+static int rlc_eval_umma_grid(rlc_handle* h, const rlc_critic* c, const PackGeom& G, rlc_pack* pk, const float* s,
+                              int B, const float* a, int N, int prec, float* q_out, cudaStream_t st) {
+  GridPlan gp;
+  if (!plan_grid(G, gp) || (size_t)gp.total > h->smem_optin) return RLC_ERR_UNSUPPORTED;
+  const int NT = (N + 31) / 32;
+  const int pitch = gp.CH + GR_PITCH_PAD;
+  const size_t nps = (size_t)B * G.H1P, npa = (size_t)gp.nch * NT * 32 * pitch;
+  void* ws = nullptr;
+  int rc = rlc_workspace(h, (nps + npa) * sizeof(unsigned short) + 256, &ws);
+  if (rc) return rc;
+  unsigned short* PS = (unsigned short*)ws;
+  unsigned short* PA = PS + ((nps + 63) & ~(size_t)63);       // keep PA 128-byte aligned
+  {
+    const unsigned blocks = (unsigned)((nps + npa + 255) / 256);
+    if (prec == RLC_PREC_BF16)
+      k_grid_parts<RLC_PREC_BF16><<<blocks, 256, 0, st>>>(c->theta, s, a, c->smin, c->smax, B, N, c->S, c->A,
+                                                          c->H1, c->H2, G.H1P, gp.CH, gp.nch, NT, PS, PA);
+    else
+      k_grid_parts<RLC_PREC_FP16><<<blocks, 256, 0, st>>>(c->theta, s, a, c->smin, c->smax, B, N, c->S, c->A,
+                                                          c->H1, c->H2, G.H1P, gp.CH, gp.nch, NT, PS, PA);
+    RLC_LAUNCH_CHECK(h);
+  }
+  GridParams P;
+  memset(&P, 0, sizeof(P));
+  P.q = q_out; P.B = B; P.N = N;
+  P.H1P = G.H1P; P.H2P = G.H2P; P.NA = G.NA; P.NB = G.NB;
+  P.CH = gp.CH; P.nch = gp.nch; P.nbuf = gp.nbuf; P.NT = NT;
+  P.num_cta_tiles = (long long)((B + 3) / 4) * NT;
+  P.num_pair_tiles = (int)((P.num_cta_tiles + 1) / 2);
+  P.ps = (const __half*)PS; P.pa = (const __half*)PA;
+  P.blob[0] = (const unsigned char*)pk->dev;
+  P.blob[1] = P.blob[0] + G.blob_bytes;
+  P.off_w2 = G.off_w2; P.off_w1 = G.off_w1; P.off_c0 = G.off_c0;
+  P.sm_w2 = gp.sm_w2; P.sm_pa = gp.sm_pa; P.sm_ps = gp.sm_ps; P.sm_qp = gp.sm_qp; P.sm_bar = gp.sm_bar;
+  P.pa_stage_bytes = gp.pa_stage; P.ps_stage_bytes = gp.ps_stage;
+  P.err = h->err_flag;
+
+  int pairs = h->num_sms / 2;
+  if (pairs > P.num_pair_tiles) pairs = P.num_pair_tiles;
+  if (pairs < 1) pairs = 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(pairs * 2));
+  cfg.blockDim = dim3(GR_THREADS);
+  cfg.dynamicSmemBytes = (size_t)gp.total;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static int prof_on = -1;
+  static long long* prof_dev = nullptr;
+  if (prof_on < 0) { const char* e = getenv("RLC_UMMA_PROF"); prof_on = (e && e[0] == '1') ? 1 : 0; }
+  if (prof_on) {
+    if (!prof_dev) RLC_CUDA(cudaMalloc(&prof_dev, 128 * 32 * sizeof(long long)));
+    RLC_CUDA(cudaMemsetAsync(prof_dev, 0, 128 * 32 * sizeof(long long), st));
+    P.prof = prof_dev;
+  }
+  void (*kern)(const GridParams) =
+      P.prof ? (prec == RLC_PREC_BF16 ? k_critic_umma_grid<RLC_PREC_BF16, true> : k_critic_umma_grid<RLC_PREC_FP16, true>)
+             : (prec == RLC_PREC_BF16 ? k_critic_umma_grid<RLC_PREC_BF16, false> : k_critic_umma_grid<RLC_PREC_FP16, false>);
+  RLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gp.total));
+  RLC_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
+  RLC_LAUNCH_CHECK(h);
+  if (prof_on) {   // debug only: synchronises
+    static long long hp[128 * 32];
+    RLC_CUDA(cudaStreamSynchronize(st));
+    RLC_CUDA(cudaMemcpy(hp, prof_dev, sizeof(hp), cudaMemcpyDeviceToHost));
+    const long long* o = hp;
+    const double T = (double)o[0], nt = (double)(o[6] > 0 ? o[6] : 1);
+    fprintf(stderr, "[grid prof pair0] CH %d nbuf %d tiles %lld total %.0f cyc (%.0f/tile) | MMA: waitH1 %.1f%% waitL2E %.1f%% issue %.1f%% | "
+            "ep1: waitPA %.1f%% waitH1E %.1f%% build+st %.1f%% wait::st+arrive %.1f%% | ep2: waitL2F %.1f%% ld+wait %.1f%% math %.1f%% tail %.1f%%\n",
+            gp.CH, gp.nbuf, o[6], T, T / nt, 100 * o[1] / T, 100 * o[2] / T, 100 * o[3] / T, 100 * o[8] / T, 100 * o[9] / T,
+            100 * o[10] / T, 100 * o[11] / T, 100 * o[16] / T, 100 * o[17] / T, 100 * o[18] / T, 100 * o[19] / T);
+  }
+  return RLC_OK;
+}

@@ -16,7 +16,7 @@ if [ "${NCU:-1}" = "1" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_launches_$TAG.log 2>&1
   echo "ncu launches rc=$?"
   timeout 300 $CMD > $OUT/plain2_$TAG.log 2>&1 &&
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_critic_umma -s 4 -c 2 -o $OUT/k1_$TAG -f $CMD > $OUT/ncu_full_$TAG.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_critic_umma_grid -s 4 -c 2 -o $OUT/k1_$TAG -f $CMD > $OUT/ncu_full_$TAG.log 2>&1
   echo "ncu full rc=$?"
 fi
 ls -la $OUT | tail -20
