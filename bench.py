@@ -8,13 +8,14 @@ Workload (config.workload = "cfg4"): ForwardKL large batch, per GPU B=4096 state
 actions, S=17, A=6, 400-300 T-in critic (BASELINE.json configs[3], the shape the target is quoted
 on).  One *step* = one pass of the hot path over one replay minibatch:
     K1  rlc_critic_eval   q[B,N] = Q(s_b, a_n)   (tcgen05 kernel, fp16 operands / fp32 accumulate)
-    K3  rlc_reduce_fkl    per-state Boltzmann weights + policy loss over the grid
+    K3  rlc_reduce_fkl_policy  per-state Boltzmann weights + policy loss over the grid, with the
+                          tanh-Gaussian log-density evaluated in place from mean/log_std [B,A]
 metric = (s,a) Q-evaluations per second, whole job (all ranks).  States shard over ranks with no
 data-path collective (weak scaling: every rank gets its own B=4096 minibatch).
 
 value : inputs already resident in HBM, CUDA events on the launching stream around exactly K steps.
 e2e   : the same step through the public API with HOST (pinned) inputs: H2D copy of the states and
-        the policy log-probabilities, D2H read of the per-state loss, inside the timed region.
+        the policy head outputs (mean, log_std), D2H read of the per-state loss, in the timed region.
 roofline : dominant kernel = K1; achieved = algorithmic flops / its mean launch time
         measured with CUDA events in this process; peak from MEASURED_PEAKS.json.
 cpu_baseline / --impl reference : oracle/oracle_torch.py (the reference's torch-CPU arithmetic,
@@ -37,8 +38,8 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 WORKLOAD = dict(workload="cfg4", B_per_gpu=4096, N=1024, S=17, A=6, H1=400, H2=300, topology="T-in",
-                reduction="forward_kl", action_layout="shared_grid[N,A]", entropy_scale=0.1)
-RING = 10                     # rotating input/output sets: 10 x (q 16.8 MB + logp 16.8 MB) > 126 MB L2
+                reduction="forward_kl (Boltzmann weights + tanh-Gaussian log-density + policy loss and its gradient wrt the policy head)", action_layout="shared_grid[N,A]", entropy_scale=0.1)
+RING = 10                     # rotating input/output sets: 10 x q[B,N] (16.8 MB each) = 168 MB > 126 MB L2
 METRIC = "sampled_q_evals_per_sec"
 UNIT = "Q-evals/s"
 
@@ -60,8 +61,9 @@ def make_inputs(rng, B, N, S, A):
     s = np.clip(rng.randn(B, S), -10, 10).astype(np.float32)
     a = rng.uniform(-1, 1, (N, A)).astype(np.float32)
     _, w = onp.intg_grid_1d(N + 2, 1.0)
-    logp = (rng.randn(B, N) * 0.5 - 1).astype(np.float32)
-    return s, a, np.asarray(w, np.float32), logp
+    mean = (rng.randn(B, A) * 0.5).astype(np.float32)          # policy head outputs (actor side, fed in)
+    log_std = (rng.randn(B, A) * 0.3 - 0.5).astype(np.float32)
+    return s, a, np.asarray(w, np.float32), (mean, log_std)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -120,14 +122,15 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU arm (oracle port of the reference's torch-CPU path)
 # ---------------------------------------------------------------------------------------------
-def cpu_arm(params, s, a, w, logp, entropy_scale, budget_s=12.0, b_sample=256, max_reps=40, warmup=1):
+def cpu_arm(params, s, a, w, pol, entropy_scale, budget_s=12.0, b_sample=256, max_reps=40, warmup=1):
     """Times oracle_torch.fkl_sampled_step on the first b_sample states (a bounded sample of the
     workload; the full B=4096 stack would need 12 GB of fp32 activations on the host)."""
     from oracle import oracle_torch as ot
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     net = ot.SoftQNetworkPort(*params)
-    ts, ta, tw, tl = (torch.as_tensor(x) for x in (s[:b_sample], a, w, logp[:b_sample]))
+    ts, ta, tw = (torch.as_tensor(x) for x in (s[:b_sample], a, w))
+    tl = (torch.as_tensor(pol[0][:b_sample]), torch.as_tensor(pol[1][:b_sample]))
     for _ in range(warmup):
         ot.fkl_sampled_step(net, ts, ta, tw, tl, entropy_scale)
     times, t_end = [], time.perf_counter() + budget_s
@@ -150,13 +153,14 @@ def run_reference(args, rank, world):
     W = WORKLOAD
     rng = np.random.RandomState(0)
     params = make_params(rng, W["S"], W["A"], W["H1"], W["H2"])
-    s, a, w, logp = make_inputs(rng, W["B_per_gpu"], W["N"], W["S"], W["A"])
+    s, a, w, pol = make_inputs(rng, W["B_per_gpu"], W["N"], W["S"], W["A"])
     from oracle import oracle_torch as ot
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     net = ot.SoftQNetworkPort(*params)
     b_sample = 256
-    ts, ta, tw, tl = (torch.as_tensor(x) for x in (s[:b_sample], a, w, logp[:b_sample]))
+    ts, ta, tw = (torch.as_tensor(x) for x in (s[:b_sample], a, w))
+    tl = (torch.as_tensor(pol[0][:b_sample]), torch.as_tensor(pol[1][:b_sample]))
     for _ in range(max(args.warmup, 1)):
         ot.fkl_sampled_step(net, ts, ta, tw, tl, W["entropy_scale"])
     t0 = time.perf_counter()
@@ -198,7 +202,7 @@ def run_b200(args, rank, local_rank, world):
     rng = np.random.RandomState(0)
     params = make_params(rng, S, A, H1, H2)                       # identical weights on every rank
     rng_in = np.random.RandomState(1000 + rank)                   # each rank: its own minibatch shard
-    s_np, a_np, w_np, logp_np = make_inputs(rng_in, B, N, S, A)
+    s_np, a_np, w_np, (mean_np, lstd_np) = make_inputs(rng_in, B, N, S, A)
     a_np, w_np = make_inputs(np.random.RandomState(1), 1, N, S, A)[1:3]   # the grid is shared by all ranks
 
     eng = rb.Engine(local_rank)
@@ -208,13 +212,15 @@ def run_b200(args, rank, local_rank, world):
     a_d, w_d = t(a_np), t(w_np)
     # rotating sets so that consecutive steps never find their inputs/outputs in L2
     s_ring = [t(np.roll(s_np, i, axis=0).copy()) for i in range(RING)]
-    logp_ring = [t(np.roll(logp_np, i, axis=0).copy()) for i in range(RING)]
+    mean_ring = [t(np.roll(mean_np, i, axis=0).copy()) for i in range(RING)]
+    lstd_ring = [t(np.roll(lstd_np, i, axis=0).copy()) for i in range(RING)]
+    ACTION_SCALE = 1.0
     q_ring = [torch.empty((B, N), dtype=torch.float32, device=dev) for _ in range(RING)]
 
     def step(i):
         j = i % RING
         q = critic.eval_into(s_ring[j], a_d, q_ring[j], prec)
-        loss_b, _, _ = eng.fkl(q, w_d, logp_ring[j], alpha, want_boltz=False, want_grad=False)
+        loss_b, dmean, dlstd, _ = eng.fkl_policy(q, w_d, a_d, ACTION_SCALE, mean_ring[j], lstd_ring[j], alpha)
         return loss_b
 
     # ---- parity gate on this rank's first states (rows checked against the CPU oracle) ----
@@ -239,7 +245,7 @@ def run_b200(args, rank, local_rank, world):
         ok = parity["vs_stated_arithmetic_rms"] < 3e-5 and parity["vs_stated_arithmetic_max"] < 2e-3
     else:
         ok = parity["rel_err_max"] < 2e-5
-    _, per_state, _, _ = onp.fkl_reduce(q_gpu, w_np, logp_np[rows], alpha, dtype=np.float64)
+    per_state = onp.fkl_policy_reduce(q_gpu, w_np, a_np, mean_np[rows], lstd_np[rows], ACTION_SCALE, alpha)[0]
     ok = ok and np.allclose(loss0.cpu().numpy()[rows], per_state, rtol=1e-3, atol=1e-5)
     if not ok:
         raise SystemExit(f"bench.py: parity gate failed: {parity}")
@@ -276,34 +282,35 @@ def run_b200(args, rank, local_rank, world):
     torch.cuda.synchronize()
     k1_ms = ev0.elapsed_time(ev1) / k1_reps
 
-    # ---- end to end through the public API: pinned host inputs in, host result out ----
-    s_host = [torch.as_tensor(np.roll(s_np, i, axis=0).copy()).pin_memory() for i in range(2)]
-    logp_host = [torch.as_tensor(np.roll(logp_np, i, axis=0).copy()).pin_memory() for i in range(2)]
-    loss_host = torch.empty((B,), dtype=torch.float32).pin_memory()
-    s_dev, logp_dev = torch.empty_like(s_ring[0]), torch.empty_like(logp_ring[0])
+    # ---- end to end through the public API: host inputs in, host result out, every step ----
+    # rlcontrol_b200.steps.ForwardKLGridStep: one CUDA-graph launch = H2D of the minibatch (states,
+    # policy head outputs) from pinned memory, K1, K3, D2H of loss and policy-head gradients.
+    from rlcontrol_b200.steps import ForwardKLGridStep
+    fstep = ForwardKLGridStep(critic, a_d, w_d, ACTION_SCALE, alpha, B, precision=prec)
+    host_in = [(torch.as_tensor(np.roll(s_np, i, axis=0).copy()), torch.as_tensor(np.roll(mean_np, i, axis=0).copy()),
+                torch.as_tensor(np.roll(lstd_np, i, axis=0).copy())) for i in range(4)]
 
     def e2e_step(i):
-        s_dev.copy_(s_host[i & 1], non_blocking=True)
-        logp_dev.copy_(logp_host[i & 1], non_blocking=True)
-        q = critic.eval_into(s_dev, a_d, q_ring[i % RING], prec)
-        loss_b, _, _ = eng.fkl(q, w_d, logp_dev, alpha, want_boltz=False, want_grad=False)
-        loss_host.copy_(loss_b, non_blocking=True)
-        torch.cuda.current_stream().synchronize()          # the caller reads the loss every step
-        return float(loss_host[0])
+        hs, hm, hl = host_in[i & 3]
+        loss_host, dmean_host, _ = fstep(hs, hm, hl)       # copies into pinned staging, launches, synchronises
+        return float(loss_host[0]) + float(dmean_host[0, 0])
 
+    chk = e2e_step(0)
+    loss_ref0 = onp.fkl_policy_reduce(q_ring[0][:1].cpu().numpy(), w_np, a_np, mean_np[:1], lstd_np[:1], ACTION_SCALE, alpha)
+    if not np.isfinite(chk) or abs(float(fstep.loss_host[0]) - float(loss_ref0[0][0])) > 1e-3 * max(1.0, abs(float(loss_ref0[0][0]))):
+        raise SystemExit("bench.py: e2e step disagrees with the oracle")
     for i in range(args.warmup):
         e2e_step(i)
     barrier()
     t0 = time.perf_counter()
-    ev0.record()
     for i in range(args.steps):
         e2e_step(i)
-    ev1.record()
-    barrier()
-    e2e_ms = max(ev0.elapsed_time(ev1), 0.0)
+    torch.cuda.synchronize()
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3
-    h2d = s_dev.numel() * 4 + logp_dev.numel() * 4
-    d2h = loss_host.numel() * 4
+    e2e_ms = e2e_wall_ms          # host-synchronous every step: wall clock IS the end-to-end time
+    barrier()
+    h2d = (fstep.s_host.numel() + fstep.mean_host.numel() + fstep.log_std_host.numel()) * 4
+    d2h = (fstep.loss_host.numel() + fstep.dmean_host.numel() + fstep.dlog_std_host.numel()) * 4
 
     # ---- secondary: critic regression update (a15/a16) incl. the NCCL grad all-reduce when N>1 ----
     a_reg = t(rng_in.uniform(-1, 1, (B, A)).astype(np.float32))
@@ -360,7 +367,7 @@ def run_b200(args, rank, local_rank, world):
             "e2e": {"value": evals_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
                     "wall_ms_per_step": e2e_wall_ms / args.steps,
-                    "api": "Critic.eval_into + Engine.fkl on pinned host states/logp, loss read back every step"},
+                    "api": "rlcontrol_b200.steps.ForwardKLGridStep(states, mean, log_std) -> (loss_b, dmean, dlog_std): host arrays in, host arrays out, one CUDA-graph launch + sync per step; timed with the host clock"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "K1 fused T-in critic eval: k_critic_umma_grid (+ k_grid_parts pre-pass) [%s arithmetic]" % critic.tensor_arithmetic(True), "bound": "tensor",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
@@ -373,7 +380,7 @@ def run_b200(args, rank, local_rank, world):
                       "critic_update_allreduce": "nccl sum of theta_Q grads" if world > 1 else "none (1 rank)"},
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_arm(params, s_np, a_np, w_np, logp_np, alpha)
+            line["cpu_baseline"] = cpu_arm(params, s_np, a_np, w_np, (mean_np, lstd_np), alpha)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

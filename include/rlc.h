@@ -157,6 +157,22 @@ int rlc_reduce_rkl(rlc_handle* h, const float* q, const float* v, const float* w
                    const float* logp, int B, int N, float entropy_scale, int hard, int B_total,
                    float* loss_b_out, float* dlogp_out, void* stream);
 
+/* The same two reductions with PolicyNetwork.get_logprob (forwardkl_network.py:324-351; row a5)
+ * evaluated in place from the policy head outputs mean[B,A], log_std[B,A] on the shared grid
+ * grid[N,A] (tanh-Gaussian; for A > 1 std is the MVN covariance exactly as the reference passes it,
+ * :350).  No [B,N] log-density tensor is read; the gradient of mean_b loss_b comes back as
+ * dmean_out[B,A], dlog_std_out[B,A] (may be NULL); logp_out[B,N] is optional (NULL to skip).
+ * 1 <= A <= 8. */
+int rlc_reduce_fkl_policy(rlc_handle* h, const float* q, const float* w, const float* grid, int A,
+                          float action_scale, const float* mean, const float* log_std, int B, int N,
+                          float entropy_scale, int B_total, float* loss_b_out, float* dmean_out,
+                          float* dlog_std_out, float* logp_out, void* stream);
+int rlc_reduce_rkl_policy(rlc_handle* h, const float* q, const float* v, const float* w,
+                          const float* grid, int A, float action_scale, const float* mean,
+                          const float* log_std, int B, int N, float entropy_scale, int hard,
+                          int B_total, float* loss_b_out, float* dmean_out, float* dlog_std_out,
+                          float* logp_out, void* stream);
+
 /* ---- CEM (rows a11, a12) ----------------------------------------------------------------
  * iterate_cem_multidim (qt_opt_network.py:132-175) + BoundedVarGaussianMixture refit
  * (utils/boundedvar_gaussian_mixture.py:10-75), all iterations in one launch, random draws

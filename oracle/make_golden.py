@@ -305,6 +305,46 @@ def gen_gmm():
     print("gmm cases", len(Xs), "n_iter", Its)
 
 
+def gen_policy_logp(torch, fkl_mod, rkl_mod):
+    """The reference's own PolicyNetwork.forward + get_logprob (forwardkl_network.py:288-344,
+    reversekl_network.py twin) for action_dim 1, 2 and 3 -- pins the tanh-Gaussian log-density
+    including the A>1 quirk (MultivariateNormal(mean, diag_embed(std)): std used as the covariance),
+    and, through autograd, d(sum c*logp)/d(mean, log_std)."""
+    save = {}
+    for A, mod in ((1, fkl_mod), (2, fkl_mod), (3, rkl_mod)):
+        torch.manual_seed(10 + A)
+        rng = np.random.RandomState(20 + A)
+        S, B, N, scale = 4, 6, 40, 2.0
+        pi = mod.PolicyNetwork(S, A, 16, 16, scale)
+        with torch.no_grad():                       # make the heads non-trivial
+            pi.mean_linear.weight.mul_(100.0)
+            pi.log_std_linear.weight.mul_(150.0)
+        states = torch.tensor(rng.randn(B, S), dtype=torch.float32)
+        acts = torch.tensor(rng.uniform(-0.98, 0.98, (N, A)) * scale, dtype=torch.float32)
+        tiled = acts.unsqueeze(0).repeat(B, 1, 1)                     # [B,N,A] as the reference tiles it
+        mean, log_std = pi.forward(states)
+        mean.retain_grad()
+        log_std.retain_grad()
+        std = log_std.exp()
+        normal = pi.get_distribution(mean, std)
+        na = tiled.permute(1, 0, 2) / pi.action_scale
+        lp = normal.log_prob(pi.atanh(na))
+        if len(lp.shape) == 2:
+            lp = lp.unsqueeze(-1)
+        lp = lp - torch.log(1 - na.pow(2) + 1e-6).sum(dim=-1, keepdim=True)
+        lp = lp.permute(1, 0, 2).reshape(B, N)
+        ref = pi.get_logprob(states, tiled).reshape(B, N)
+        assert torch.allclose(lp, ref)
+        c = torch.tensor(rng.randn(B, N), dtype=torch.float32)
+        (c * lp).sum().backward()
+        save.update({f"A{A}_mean": mean.detach().numpy(), f"A{A}_log_std": log_std.detach().numpy(),
+                     f"A{A}_actions": acts.numpy(), f"A{A}_scale": np.float32(scale),
+                     f"A{A}_logp": ref.detach().numpy(), f"A{A}_c": c.numpy(),
+                     f"A{A}_dmean": mean.grad.numpy(), f"A{A}_dlog_std": log_std.grad.numpy()})
+    np.savez_compressed(os.path.join(OUT, "policy_logp.npz"), **save)
+    print("policy_logp", {k: v.shape for k, v in save.items() if k.endswith("logp")})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     install_stubs()
@@ -321,6 +361,7 @@ def main():
             action_max=2.0, scale_last=1.0, seed=2)
     gen_update(torch, forwardkl_network, "ForwardKLNetwork", "fkl_update.npz", alpha=0.1)
     gen_update(torch, reversekl_network, "ReverseKLNetwork", "rkl_update.npz", alpha=0.1)
+    gen_policy_logp(torch, forwardkl_network, reversekl_network)
     gen_trueq()
     gen_gmm()
     x, w = onp.clenshaw_curtis(64)

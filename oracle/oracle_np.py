@@ -347,6 +347,55 @@ def tanh_gauss_logprob_1d(mean, log_std, actions, action_scale, eps=1e-6):
     return lp.astype(F32)
 
 
+def tanh_gauss_logprob(mean, log_std, actions, action_scale, eps=1e-6, dtype=np.float64):
+    """``PolicyNetwork.get_logprob`` for any action_dim (forwardkl_network.py:324-351,
+    reversekl_network.py:346-374).  u = atanh(a/scale) = (log(1+x) - log(1-x))/2 (:353-354).
+      A == 1: Normal(mean, std).log_prob(u)                = -(u-m)^2/(2 std^2) - log std - log sqrt(2 pi)
+      A  > 1: MultivariateNormal(mean, diag_embed(std))    -- std is passed as the COVARIANCE (:350), so
+              log_prob = -1/2 sum_k (u_k-m_k)^2/std_k - 1/2 sum_k log std_k - A/2 log(2 pi)
+    minus sum_k log(1 - x_k^2 + eps).  mean/log_std [B,A], actions [N,A] -> (logp [B,N],
+    dlogp/dmean [B,N,A], dlogp/dlog_std [B,N,A])."""
+    mean = np.asarray(mean, dtype)
+    log_std = np.asarray(log_std, dtype)
+    B, A = mean.shape
+    x = np.asarray(actions, dtype) / dtype(action_scale)                 # [N,A]
+    u = (np.log(1 + x) - np.log(1 - x)) / 2
+    jac = np.log(1 - x * x + dtype(eps)).sum(axis=1)                     # [N]
+    d = u[None, :, :] - mean[:, None, :]                                 # [B,N,A]
+    std = np.exp(log_std)[:, None, :]
+    if A == 1:
+        lp = (-(d * d) / (2 * std * std) - log_std[:, None, :] - dtype(0.5 * math.log(2 * math.pi))).sum(-1)
+        dmean = d / (std * std)
+        dlstd = d * d / (std * std) - 1
+    else:
+        lp = (-(d * d) / (2 * std)).sum(-1) - 0.5 * log_std.sum(-1)[:, None] - dtype(0.5 * A * math.log(2 * math.pi))
+        dmean = d / std
+        dlstd = 0.5 * d * d / std - 0.5
+    return (lp - jac[None, :]).astype(dtype), dmean.astype(dtype), dlstd.astype(dtype)
+
+
+def fkl_policy_reduce(q, w, actions, mean, log_std, action_scale, entropy_scale, b_total=None, dtype=np.float64):
+    """ForwardKL grid reduction with the policy log-density evaluated in place (a3 + a5):
+    returns (per-state loss [B], dL/dmean [B,A], dL/dlog_std [B,A], logp [B,N]) for
+    L = mean_b loss_b; Boltzmann weights are constants for the gradient (``.detach()``,
+    forwardkl_network.py:176-184)."""
+    lp, dm, ds = tanh_gauss_logprob(mean, log_std, actions, action_scale, dtype=dtype)
+    _, per_state, _, dlogp = fkl_reduce(q, w, lp, entropy_scale, dtype=dtype)
+    if b_total is not None:
+        dlogp = dlogp * dtype(np.asarray(q).shape[0]) / dtype(b_total)
+    return per_state, (dlogp[:, :, None] * dm).sum(1), (dlogp[:, :, None] * ds).sum(1), lp
+
+
+def rkl_policy_reduce(q, v, w, actions, mean, log_std, action_scale, entropy_scale, hard=False, b_total=None,
+                      dtype=np.float64):
+    """ReverseKL counterpart of :func:`fkl_policy_reduce` (reversekl_network.py:181-203)."""
+    lp, dm, ds = tanh_gauss_logprob(mean, log_std, actions, action_scale, dtype=dtype)
+    _, per_state, dlogp = rkl_reduce(q, v, w, lp, entropy_scale, hard=hard, dtype=dtype)
+    if b_total is not None:
+        dlogp = dlogp * dtype(np.asarray(q).shape[0]) / dtype(b_total)
+    return per_state, (dlogp[:, :, None] * dm).sum(1), (dlogp[:, :, None] * ds).sum(1), lp
+
+
 # --------------------------------------------------------------------------------------
 # CEM: bounded diagonal GMM refit + loop
 # --------------------------------------------------------------------------------------

@@ -29,13 +29,38 @@ class SoftQNetworkPort(torch.nn.Module):
         return torch.nn.functional.linear(x, self.W3.reshape(1, -1), self.b3.reshape(1))  # :267
 
 
-def fkl_sampled_step(qnet: SoftQNetworkPort, state, grid_actions, grid_weights, logp, entropy_scale):
-    """The hot loop of ``ForwardKLNetwork.update_network`` (forwardkl_network.py:160-194), with
-    the policy log-probabilities ``logp`` [B,N] fed in (actor side is outside the path):
-    stack states, tile the grid, evaluate Q on B*N rows, Boltzmann-normalise per state and form
-    the per-state loss.  Returns (loss_b [B], q [B,N])."""
+def get_logprob_port(mean, log_std, grid_actions, action_scale, epsilon=1e-6):
+    """``PolicyNetwork.get_logprob`` (forwardkl_network.py:324-351) given the head outputs
+    mean/log_std [B,A] (the two-layer actor trunk is per-state work outside the path): tile the
+    grid to [B,N,A], atanh, Normal / MultivariateNormal(mean, diag_embed(std)) log_prob, tanh
+    Jacobian.  Returns [B,N]."""
+    B, N = mean.shape[0], grid_actions.shape[0]
+    tiled = grid_actions.unsqueeze(0).repeat(B, 1, 1)                                    # :104-106
+    na = tiled.permute(1, 0, 2) / action_scale                                           # :329
+    at = (torch.log(1 + na) - torch.log(1 - na)) / 2                                     # :330,353-354
+    std = log_std.exp()                                                                  # :333
+    if mean.shape[1] == 1:
+        normal = torch.distributions.Normal(mean, std)                                   # :347-348
+    else:
+        normal = torch.distributions.MultivariateNormal(mean, torch.diag_embed(std))     # :350
+    lp = normal.log_prob(at)                                                             # :337
+    if lp.dim() == 2:
+        lp = lp.unsqueeze(-1)
+    lp = lp - torch.log(1 - na.pow(2) + epsilon).sum(dim=-1, keepdim=True)               # :342
+    return lp.permute(1, 0, 2).reshape(B, N)                                             # :343
+
+
+def fkl_sampled_step(qnet: SoftQNetworkPort, state, grid_actions, grid_weights, logp, entropy_scale,
+                     action_scale=1.0):
+    """The hot loop of ``ForwardKLNetwork.update_network`` (forwardkl_network.py:160-194):
+    stack states, tile the grid, evaluate Q on B*N rows, Boltzmann-normalise per state, evaluate
+    the policy log-density on the grid and form the per-state loss.  ``logp`` is either the
+    [B,N] log-probabilities or the policy head outputs ``(mean, log_std)`` [B,A] each (then
+    ``get_logprob_port`` runs inside, as in the reference).  Returns (loss_b [B], q [B,N])."""
     B, N = state.shape[0], grid_actions.shape[0]
     with torch.no_grad():
+        if isinstance(logp, (tuple, list)):
+            logp = get_logprob_port(logp[0], logp[1], grid_actions, action_scale)
         stacked_s = state.unsqueeze(1).repeat(1, N, 1).reshape(-1, state.shape[1])       # :161-162
         stacked_a = grid_actions.repeat(B, 1, 1).reshape(-1, grid_actions.shape[1])      # :104-105
         q = qnet(stacked_s, stacked_a).reshape(B, N)                                     # :164

@@ -52,6 +52,8 @@ SIGNATURES = {
     "rlc_reduce_lse": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "rlc_reduce_fkl": (_i, [_p, _p, _p, _p, _i, _i, _f, _i, _p, _p, _p, _p]),
     "rlc_reduce_rkl": (_i, [_p, _p, _p, _p, _p, _i, _i, _f, _i, _i, _p, _p, _p]),
+    "rlc_reduce_fkl_policy": (_i, [_p, _p, _p, _p, _i, _f, _p, _p, _i, _i, _f, _i, _p, _p, _p, _p, _p]),
+    "rlc_reduce_rkl_policy": (_i, [_p, _p, _p, _p, _p, _i, _f, _p, _p, _i, _i, _f, _i, _i, _p, _p, _p, _p, _p]),
     "rlc_cem": (_i, [_p, _cr, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "rlc_gmm_refit": (_i, [_p, _p, _i, _i, _i, _i, _p, _f, _i, _p, _p, _p, _p, _p]),
     "rlc_critic_grad_action": (_i, [_p, _cr, _p, _p, _i, _p, _p, _p]),

@@ -146,6 +146,148 @@ k_rkl(const float* __restrict__ q, const float* __restrict__ v, const float* __r
   if (lane == 0) loss_b[b] = acc;
 }
 
+// ---- policy-fused grid reductions (rows a3/a4 + a5) -------------------------------------------
+// PolicyNetwork.get_logprob (forwardkl_network.py:324-351) is evaluated in place from the policy
+// head outputs mean[B,A], log_std[B,A]: no [B,N] log-density tensor is read, and the gradient comes
+// back as dL/dmean, dL/dlog_std [B,A].  Terms that depend on the grid only are tabulated once:
+//   U[n][k] = atanh(a_nk/scale) = (log(1+x) - log(1-x))/2     J[n] = sum_k log(1 - x^2 + eps)
+__global__ void k_grid_logterms(const float* __restrict__ grid, int N, int A, float inv_scale, float eps,
+                                float* __restrict__ U, float* __restrict__ J) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float j = 0.f;
+  for (int k = 0; k < A; ++k) {
+    const float x = grid[(size_t)n * A + k] * inv_scale;
+    U[(size_t)n * A + k] = (logf(1.f + x) - logf(1.f - x)) * 0.5f;
+    j += logf(1.f - x * x + eps);
+  }
+  J[n] = j;
+}
+
+#define POL_MAX_A 8
+#define POL_NPL 32   // q values cached per lane (N <= 1024 stays in registers)
+
+// MODE 0: ForwardKL (Boltzmann weights over the grid, detached); MODE 1: ReverseKL.
+template <int MODE, int A>
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
+k_policy_reduce(const float* __restrict__ q, const float* __restrict__ v, const float* __restrict__ w,
+                const float* __restrict__ U, const float* __restrict__ J, const float* __restrict__ mean,
+                const float* __restrict__ log_std, int B, int N, float alpha, float inv_btotal,
+                float* __restrict__ loss_b, float* __restrict__ dmean, float* __restrict__ dlstd,
+                float* __restrict__ logp_out) {
+  const int b = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float* row = q + (long long)b * N;
+  // per-state constants of the log-density (A == 1: Normal(mean, std); A > 1: the reference hands
+  // std to MultivariateNormal as the covariance, forwardkl_network.py:350)
+  float mu[A], h[A], gs[A];   // h: coefficient of d^2 ; gs: d^2 factor in dlogp/dlog_std
+  float c0 = 0.f;
+#pragma unroll
+  for (int k = 0; k < A; ++k) {
+    const float ls = log_std[(size_t)b * A + k];
+    const float sd = expf(ls);
+    mu[k] = mean[(size_t)b * A + k];
+    if (A == 1) {
+      h[k] = 0.5f / (sd * sd);
+      gs[k] = 1.f / (sd * sd);
+      c0 = -ls - 0.9189385332046727f;                       // log sqrt(2 pi)
+    } else {
+      h[k] = 0.5f / sd;
+      gs[k] = 0.5f / sd;
+      c0 -= 0.5f * ls;
+    }
+  }
+  if (A > 1) c0 -= 0.9189385332046727f * (float)A;
+  const bool cached = N <= 32 * POL_NPL;
+  float qc[POL_NPL];
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < POL_NPL; ++i) {
+      const int n = lane + 32 * i;
+      qc[i] = n < N ? row[n] : 0.f;
+    }
+  }
+  float m = 0.f, z = 1.f;
+  if (MODE == 0) {
+    m = -CUDART_INF_F;
+    if (cached) {
+#pragma unroll
+      for (int i = 0; i < POL_NPL; ++i)
+        if (lane + 32 * i < N) m = fmaxf(m, __fdiv_rn(qc[i], alpha));
+    } else {
+      for (int n = lane; n < N; n += 32) m = fmaxf(m, __fdiv_rn(row[n], alpha));
+    }
+    m = warp_max(m);
+    z = 0.f;
+    if (cached) {
+#pragma unroll
+      for (int i = 0; i < POL_NPL; ++i) {
+        const int n = lane + 32 * i;
+        if (n < N) {
+          qc[i] = expf(__fdiv_rn(qc[i], alpha) - m);        // reuse the register for e_n
+          z = fmaf(qc[i], w[n], z);
+        }
+      }
+    } else {
+      for (int n = lane; n < N; n += 32) z = fmaf(expf(__fdiv_rn(row[n], alpha) - m), w[n], z);
+    }
+    z = warp_sum(z);
+  }
+  const float vb = (MODE == 1) ? v[b] : 0.f;
+  float acc = 0.f, gm[A], gl[A];
+#pragma unroll
+#pragma unroll
+  for (int k = 0; k < A; ++k) { gm[k] = 0.f; gl[k] = 0.f; }
+  auto body = [&](int n, float qe) {
+    // log pi(a_n | s_b)
+    float lp = c0 - J[n];
+    float d[A];
+  #pragma unroll
+  for (int k = 0; k < A; ++k) {
+      d[k] = U[(size_t)n * A + k] - mu[k];
+      lp = fmaf(-h[k] * d[k], d[k], lp);
+    }
+    float g;   // dL/dlogp_bn
+    if (MODE == 0) {
+      const float pw = __fdiv_rn(qe, z) * w[n];            // Boltzmann weight x quadrature weight
+      acc = fmaf(pw, lp, acc);
+      g = -pw * inv_btotal;
+    } else {
+      const float pe = expf(lp);
+      const float inner = (qe - vb) - alpha * lp;
+      acc = fmaf(-pe * inner, w[n], acc);
+      g = (-pe * (inner - alpha)) * w[n] * inv_btotal;
+    }
+  #pragma unroll
+  for (int k = 0; k < A; ++k) {
+      gm[k] = fmaf(g, 2.f * h[k] * d[k], gm[k]);
+      gl[k] = fmaf(g, (A == 1) ? (gs[k] * d[k] * d[k] - 1.f) : (gs[k] * d[k] * d[k] - 0.5f), gl[k]);
+    }
+    if (logp_out) logp_out[(long long)b * N + n] = lp;
+  };
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < POL_NPL; ++i) {
+      const int n = lane + 32 * i;
+      if (n < N) body(n, qc[i]);
+    }
+  } else {
+    for (int n = lane; n < N; n += 32)
+      body(n, MODE == 0 ? expf(__fdiv_rn(row[n], alpha) - m) : row[n]);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) loss_b[b] = (MODE == 0) ? -acc : acc;
+#pragma unroll
+  for (int k = 0; k < A; ++k) {
+    const float a1 = warp_sum(gm[k]), a2 = warp_sum(gl[k]);
+    if (lane == 0) {
+      if (dmean) dmean[(size_t)b * A + k] = a1;
+      if (dlstd) dlstd[(size_t)b * A + k] = a2;
+    }
+  }
+}
+
 static inline unsigned nblocks(int B) { return (unsigned)((B + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK); }
 
 extern "C" int rlc_reduce_topk(rlc_handle* h, const float* q, int B, int N, int k,
@@ -203,4 +345,59 @@ extern "C" int rlc_reduce_rkl(rlc_handle* h, const float* q, const float* v, con
       dlogp_out);
   RLC_LAUNCH_CHECK(h);
   return RLC_OK;
+}
+
+static int policy_reduce(rlc_handle* h, int mode, const float* q, const float* v, const float* w,
+                         const float* grid, int A, float action_scale, const float* mean,
+                         const float* log_std, int B, int N, float alpha, int B_total, float* loss_b_out,
+                         float* dmean_out, float* dlog_std_out, float* logp_out, cudaStream_t st) {
+  RLC_REQUIRE(h && q && w && grid && mean && log_std && loss_b_out && B >= 0 && N >= 1 && A >= 1 &&
+              A <= POL_MAX_A && B_total >= B && B_total >= 1 && action_scale > 0.f);
+  if (B == 0) return RLC_OK;
+  void* ws = nullptr;
+  int rc = rlc_workspace(h, ((size_t)N * A + N) * sizeof(float), &ws);
+  if (rc) return rc;
+  float* U = (float*)ws;
+  float* J = U + (size_t)N * A;
+  k_grid_logterms<<<(N + 127) / 128, 128, 0, st>>>(grid, N, A, 1.f / action_scale, 1e-6f, U, J);
+  RLC_LAUNCH_CHECK(h);
+#define POL_LAUNCH(MODE_, A_)                                                                               \
+  k_policy_reduce<MODE_, A_><<<nblocks(B), 32 * WARPS_PER_BLOCK, 0, st>>>(                                  \
+      q, v, w, U, J, mean, log_std, B, N, alpha, 1.f / (float)B_total, loss_b_out, dmean_out, dlog_std_out, \
+      logp_out)
+#define POL_SWITCH(MODE_)                    \
+  switch (A) {                               \
+    case 1: POL_LAUNCH(MODE_, 1); break;     \
+    case 2: POL_LAUNCH(MODE_, 2); break;     \
+    case 3: POL_LAUNCH(MODE_, 3); break;     \
+    case 4: POL_LAUNCH(MODE_, 4); break;     \
+    case 5: POL_LAUNCH(MODE_, 5); break;     \
+    case 6: POL_LAUNCH(MODE_, 6); break;     \
+    case 7: POL_LAUNCH(MODE_, 7); break;     \
+    default: POL_LAUNCH(MODE_, 8); break;    \
+  }
+  if (mode == 0) { POL_SWITCH(0) } else { POL_SWITCH(1) }
+#undef POL_SWITCH
+#undef POL_LAUNCH
+  RLC_LAUNCH_CHECK(h);
+  return RLC_OK;
+}
+
+extern "C" int rlc_reduce_fkl_policy(rlc_handle* h, const float* q, const float* w, const float* grid, int A,
+                                     float action_scale, const float* mean, const float* log_std, int B, int N,
+                                     float entropy_scale, int B_total, float* loss_b_out, float* dmean_out,
+                                     float* dlog_std_out, float* logp_out, void* stream) {
+  RLC_REQUIRE(entropy_scale > 0.f);
+  return policy_reduce(h, 0, q, nullptr, w, grid, A, action_scale, mean, log_std, B, N, entropy_scale, B_total,
+                       loss_b_out, dmean_out, dlog_std_out, logp_out, (cudaStream_t)stream);
+}
+
+extern "C" int rlc_reduce_rkl_policy(rlc_handle* h, const float* q, const float* v, const float* w,
+                                     const float* grid, int A, float action_scale, const float* mean,
+                                     const float* log_std, int B, int N, float entropy_scale, int hard,
+                                     int B_total, float* loss_b_out, float* dmean_out, float* dlog_std_out,
+                                     float* logp_out, void* stream) {
+  RLC_REQUIRE(v);
+  return policy_reduce(h, 1, q, v, w, grid, A, action_scale, mean, log_std, B, N, hard ? 0.f : entropy_scale,
+                       B_total, loss_b_out, dmean_out, dlog_std_out, logp_out, (cudaStream_t)stream);
 }

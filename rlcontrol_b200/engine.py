@@ -118,6 +118,39 @@ class Engine:
                                       _ptr(loss_b), _ptr(dlogp), _stream()))
         return loss_b, dlogp
 
+    def fkl_policy(self, q, w, grid, action_scale: float, mean, log_std, entropy_scale: float,
+                   b_total: Optional[int] = None, want_grad: bool = True, want_logp: bool = False):
+        """ForwardKL grid reduction with ``PolicyNetwork.get_logprob`` evaluated in place
+        (forwardkl_network.py:165-194 + :324-351).  Returns (loss_b [B], dmean [B,A] | None,
+        dlog_std [B,A] | None, logp [B,N] | None)."""
+        B, N = q.shape
+        A = grid.shape[-1]
+        loss_b = torch.empty((B,), dtype=torch.float32, device=q.device)
+        dm = torch.empty((B, A), dtype=torch.float32, device=q.device) if want_grad else None
+        ds = torch.empty((B, A), dtype=torch.float32, device=q.device) if want_grad else None
+        lp = torch.empty_like(q) if want_logp else None
+        check(self.lib.rlc_reduce_fkl_policy(self.h, _ptr(q), _ptr(w), _ptr(grid), A, float(action_scale),
+                                             _ptr(mean), _ptr(log_std), B, N, float(entropy_scale),
+                                             int(b_total or B), _ptr(loss_b), _ptr(dm), _ptr(ds), _ptr(lp),
+                                             _stream()))
+        return loss_b, dm, ds, lp
+
+    def rkl_policy(self, q, v, w, grid, action_scale: float, mean, log_std, entropy_scale: float,
+                   hard: bool = False, b_total: Optional[int] = None, want_grad: bool = True,
+                   want_logp: bool = False):
+        """ReverseKL counterpart (reversekl_network.py:181-203 + :346-374)."""
+        B, N = q.shape
+        A = grid.shape[-1]
+        loss_b = torch.empty((B,), dtype=torch.float32, device=q.device)
+        dm = torch.empty((B, A), dtype=torch.float32, device=q.device) if want_grad else None
+        ds = torch.empty((B, A), dtype=torch.float32, device=q.device) if want_grad else None
+        lp = torch.empty_like(q) if want_logp else None
+        check(self.lib.rlc_reduce_rkl_policy(self.h, _ptr(q), _ptr(v), _ptr(w), _ptr(grid), A,
+                                             float(action_scale), _ptr(mean), _ptr(log_std), B, N,
+                                             float(entropy_scale), int(bool(hard)), int(b_total or B),
+                                             _ptr(loss_b), _ptr(dm), _ptr(ds), _ptr(lp), _stream()))
+        return loss_b, dm, ds, lp
+
     def gmm_refit(self, X: torch.Tensor, num_modal: int, resp0: Optional[torch.Tensor] = None,
                   tol: float = 1e-2, max_iter: int = 100):
         """Bounded diagonal GMM refit (utils/boundedvar_gaussian_mixture.py). X [B,k,A]."""

@@ -1,0 +1,101 @@
+"""Whole hot-path steps as single CUDA-graph launches (host buffers in, host result out).
+
+The reference's hot loop crosses Python -> ATen / TF once per op; here one *step* of the
+sampled-action path (H2D of the minibatch, critic evaluation on the grid, per-state reduction, D2H
+of the result) is captured once and replayed with one ``cudaGraphLaunch``: small configs are
+launch-latency-bound, large ones still save ~10 launches and copies of host overhead.
+Everything inside the graph is librlc kernels and cudaMemcpyAsync on pinned buffers."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .engine import Critic, _f32
+
+
+class ForwardKLGridStep:
+    """ForwardKL sampled-action step on a shared quadrature grid (forwardkl_network.py:160-194 with
+    ``get_logprob`` :324-351 fused): ``loss_b, dmean, dlog_std = step(states, mean, log_std)``.
+
+    Inputs are written into the pinned staging tensors ``s_host`` [B,S], ``mean_host`` [B,A],
+    ``log_std_host`` [B,A] (or passed to ``__call__`` which copies them there); outputs land in
+    the pinned ``loss_host`` [B], ``dmean_host`` [B,A], ``dlog_std_host`` [B,A].  ``q`` [B,N] stays
+    on the device (``self.q``)."""
+
+    def __init__(self, critic: Critic, grid, weights, action_scale: float, entropy_scale: float, B: int,
+                 precision="auto", b_total: Optional[int] = None, use_graph: bool = True,
+                 repack_each_step: bool = False):
+        eng = critic.eng
+        dev = eng.device
+        self.critic, self.eng = critic, eng
+        self.grid, self.w = _f32(grid, dev), _f32(weights, dev).reshape(-1)
+        self.N, self.A = self.grid.shape
+        if self.A != critic.A or self.w.numel() != self.N:
+            raise ValueError("grid / weights do not match the critic")
+        self.B, self.scale, self.alpha, self.prec = int(B), float(action_scale), float(entropy_scale), precision
+        self.b_total = int(b_total or B)
+        # training loops change theta between steps: rebuild the tensor-core operand pack inside the step
+        self.repack = bool(repack_each_step)
+        pin = lambda *sh: torch.empty(sh, dtype=torch.float32).pin_memory()
+        devt = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)
+        self.s_host, self.mean_host, self.log_std_host = pin(B, critic.S), pin(B, self.A), pin(B, self.A)
+        self.loss_host, self.dmean_host, self.dlog_std_host = pin(B), pin(B, self.A), pin(B, self.A)
+        self.s, self.mean, self.log_std = devt(B, critic.S), devt(B, self.A), devt(B, self.A)
+        self.q = devt(B, self.N)
+        self._graph = None
+        self._stream = torch.cuda.Stream(device=dev)
+        if use_graph:
+            self._capture()
+
+    def _enqueue(self):
+        self.s.copy_(self.s_host, non_blocking=True)
+        self.mean.copy_(self.mean_host, non_blocking=True)
+        self.log_std.copy_(self.log_std_host, non_blocking=True)
+        if self.repack:
+            self.critic.invalidate()
+        self.critic.eval_into(self.s, self.grid, self.q, self.prec)
+        loss_b, dm, ds, _ = self.eng.fkl_policy(self.q, self.w, self.grid, self.scale, self.mean, self.log_std,
+                                                self.alpha, b_total=self.b_total)
+        self.loss_host.copy_(loss_b, non_blocking=True)
+        self.dmean_host.copy_(dm, non_blocking=True)
+        self.dlog_std_host.copy_(ds, non_blocking=True)
+
+    def _capture(self):
+        # warm up outside the capture: workspace growth, operand pack and func attributes allocate/sync
+        with torch.cuda.stream(self._stream):
+            for _ in range(2):
+                self._enqueue()
+        self._stream.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=self._stream):
+            self._enqueue()
+        self._graph = g
+
+    def invalidate(self):
+        """Call after the critic's theta changed when ``repack_each_step`` is off: the captured graph
+        does not contain the pack kernels, so run one eager step (which rebuilds the pack in place;
+        the graph reads the same device buffers afterwards)."""
+        self.critic.invalidate()
+        with torch.cuda.stream(self._stream):
+            self._enqueue()
+        self._stream.synchronize()
+
+    def launch(self):
+        """Enqueue one step on the step's stream (no host synchronisation)."""
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            with torch.cuda.stream(self._stream):
+                self._enqueue()
+
+    def __call__(self, states=None, mean=None, log_std=None):
+        if states is not None:
+            self.s_host.copy_(torch.as_tensor(states, dtype=torch.float32).reshape(self.s_host.shape))
+        if mean is not None:
+            self.mean_host.copy_(torch.as_tensor(mean, dtype=torch.float32).reshape(self.mean_host.shape))
+        if log_std is not None:
+            self.log_std_host.copy_(torch.as_tensor(log_std, dtype=torch.float32).reshape(self.log_std_host.shape))
+        self.launch()
+        self._stream.synchronize()
+        return self.loss_host, self.dmean_host, self.dlog_std_host

@@ -276,3 +276,47 @@ def test_rounded_operand_oracle():
     np.testing.assert_array_equal(onp.tin_eval_rounded(s, a, p, "bf16"), onp.tin_eval(s, a, p, dtype=np.float64))
     x = np.array([1.0, 1.0 + 2 ** -11, 1.0 + 3 * 2 ** -11, 70000.0, -1e-8], np.float32)
     np.testing.assert_array_equal(onp.round_operand(x, "fp16"), [1.0, 1.0, 1.0 + 2 ** -9, 65504.0, -0.0])
+
+
+@pytest.mark.parametrize("A", [1, 2, 3])
+def test_policy_logprob_matches_reference(A):
+    """oracle.tanh_gauss_logprob == the reference's own PolicyNetwork.get_logprob and its autograd
+    (golden policy_logp.npz; A>1 pins the diag_embed(std)-as-covariance quirk)."""
+    g = golden("policy_logp.npz")
+    k = lambda n: g[f"A{A}_{n}"]
+    lp, dm, ds = onp.tanh_gauss_logprob(k("mean"), k("log_std"), k("actions"), float(k("scale")))
+    np.testing.assert_allclose(lp, k("logp"), rtol=2e-5, atol=2e-5)
+    c = k("c").astype(np.float64)
+    np.testing.assert_allclose((c[:, :, None] * dm).sum(1), k("dmean"), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose((c[:, :, None] * ds).sum(1), k("dlog_std"), rtol=1e-4, atol=1e-4)
+    if A == 1:
+        lp1 = onp.tanh_gauss_logprob_1d(k("mean"), k("log_std"), k("actions"), float(k("scale")))
+        np.testing.assert_allclose(lp1, k("logp"), rtol=2e-5, atol=2e-5)
+
+
+def test_fkl_policy_reduce_consistent_with_golden_update():
+    """With logp taken from the reference's update (fkl_update.npz) the fused reduction equals
+    fkl_reduce; with logp recomputed from (mean, log_std) it equals the composition."""
+    g = golden("policy_logp.npz")
+    rng = np.random.RandomState(3)
+    B, N = g["A2_logp"].shape
+    q, w = rng.randn(B, N), rng.uniform(0.01, 0.1, N)
+    per, dmean, dls, lp = onp.fkl_policy_reduce(q, w, g["A2_actions"], g["A2_mean"], g["A2_log_std"], 2.0, 0.3)
+    _, per2, _, dlogp = onp.fkl_reduce(q, w, g["A2_logp"].astype(np.float64), 0.3, dtype=np.float64)
+    np.testing.assert_allclose(per, per2, rtol=1e-4, atol=1e-5)
+    # finite-difference check of dL/dmean
+    eps = 1e-6
+    m = g["A2_mean"].astype(np.float64)
+    m2 = m.copy(); m2[1, 0] += eps
+    f = lambda mm: onp.fkl_policy_reduce(q, w, g["A2_actions"], mm, g["A2_log_std"], 2.0, 0.3)[0].mean()
+    assert abs((f(m2) - f(m)) / eps - dmean[1, 0]) < 1e-4 * max(1.0, abs(dmean[1, 0]))
+
+
+@pytest.mark.parametrize("A", [1, 2, 3])
+def test_torch_port_get_logprob_matches_reference(A):
+    import torch
+    from oracle import oracle_torch as ot
+    g = golden("policy_logp.npz")
+    k = lambda n: torch.as_tensor(g[f"A{A}_{n}"])
+    lp = ot.get_logprob_port(k("mean"), k("log_std"), k("actions"), float(g[f"A{A}_scale"]))
+    np.testing.assert_allclose(lp.numpy(), g[f"A{A}_logp"], rtol=1e-6, atol=1e-6)
