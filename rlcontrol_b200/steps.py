@@ -83,10 +83,10 @@ class ForwardKLGridStep:
 
     def launch(self):
         """Enqueue one step on the step's stream (no host synchronisation)."""
-        if self._graph is not None:
-            self._graph.replay()
-        else:
-            with torch.cuda.stream(self._stream):
+        with torch.cuda.stream(self._stream):          # CUDAGraph.replay() launches on the CURRENT stream
+            if self._graph is not None:
+                self._graph.replay()
+            else:
                 self._enqueue()
 
     def __call__(self, states=None, mean=None, log_std=None):
