@@ -290,9 +290,13 @@ struct GemmEpi {
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256)
 k_gemm(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ Bm,
-       int ldb, float* __restrict__ C, int ldc, GemmEpi epi) {
+       int ldb, float* __restrict__ C, int ldc, GemmEpi epi, int klen, long long cz_stride) {
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
+  // split-K: slice blockIdx.z covers K range [z*klen, min(K,(z+1)*klen)) and writes its own C slab
+  const int kbeg = blockIdx.z * klen;
+  K = (kbeg + klen < K) ? kbeg + klen : K;
+  C += (long long)blockIdx.z * cz_stride;
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   const int tr = tid >> 4, tc = tid & 15;
@@ -301,7 +305,7 @@ k_gemm(int M, int N, int K, const float* __restrict__ A, int lda, const float* _
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  for (int k0 = kbeg; k0 < K; k0 += 16) {
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
       const int e = tid + l * 256;  // 0..1023
@@ -354,14 +358,48 @@ k_gemm(int M, int N, int K, const float* __restrict__ A, int lda, const float* _
   }
 }
 
+static int gemm_z(rlc_handle* h, bool ta, bool tb, int M, int N, int K, const float* A, int lda,
+                  const float* Bm, int ldb, float* C, int ldc, GemmEpi epi, int nz, int klen,
+                  long long cz_stride, cudaStream_t st) {
+  if (M == 0 || N == 0) return RLC_OK;
+  dim3 grid((N + 63) / 64, (M + 63) / 64, nz);
+  if (!ta && !tb) k_gemm<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, Bm, ldb, C, ldc, epi, klen, cz_stride);
+  else if (ta && !tb) k_gemm<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, Bm, ldb, C, ldc, epi, klen, cz_stride);
+  else if (!ta && tb) k_gemm<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, Bm, ldb, C, ldc, epi, klen, cz_stride);
+  else k_gemm<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, Bm, ldb, C, ldc, epi, klen, cz_stride);
+  RLC_LAUNCH_CHECK(h);
+  return RLC_OK;
+}
+
 static int gemm(rlc_handle* h, bool ta, bool tb, int M, int N, int K, const float* A, int lda,
                 const float* Bm, int ldb, float* C, int ldc, GemmEpi epi, cudaStream_t st) {
-  if (M == 0 || N == 0) return RLC_OK;
-  dim3 grid((N + 63) / 64, (M + 63) / 64);
-  if (!ta && !tb) k_gemm<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, Bm, ldb, C, ldc, epi);
-  else if (ta && !tb) k_gemm<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, Bm, ldb, C, ldc, epi);
-  else if (!ta && tb) k_gemm<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, Bm, ldb, C, ldc, epi);
-  else k_gemm<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, Bm, ldb, C, ldc, epi);
+  return gemm_z(h, ta, tb, M, N, K, A, lda, Bm, ldb, C, ldc, epi, 1, K > 0 ? K : 1, 0, st);
+}
+
+// out[i] = sum_z part[z][i]  (fixed order: deterministic)
+__global__ void k_sum_slabs(const float* __restrict__ part, long long n, int nz, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = 0.f;
+  for (int z = 0; z < nz; ++z) acc += part[(long long)z * n + i];
+  out[i] = acc;
+}
+
+// Weight-gradient GEMM C[M,N] = op(A)^T B with a long reduction dimension K = batch rows and a small
+// M x N: split K over gridDim.z so the grid fills the GPU, then sum the slabs in a fixed order.
+#define SPLITK_MAX 32
+static int gemm_splitk(rlc_handle* h, int M, int N, int K, const float* A, int lda, const float* Bm, int ldb,
+                       float* C, GemmEpi epi, float* slabs, cudaStream_t st) {
+  int nz = (K + 127) / 128;
+  if (nz > SPLITK_MAX) nz = SPLITK_MAX;
+  if (nz <= 1 || !slabs) return gemm(h, true, false, M, N, K, A, lda, Bm, ldb, C, N, epi, st);
+  int klen = (K + nz - 1) / nz;
+  klen = (klen + 15) & ~15;
+  nz = (K + klen - 1) / klen;
+  int rc = gemm_z(h, true, false, M, N, K, A, lda, Bm, ldb, slabs, N, epi, nz, klen, (long long)M * N, st);
+  if (rc) return rc;
+  const long long n = (long long)M * N;
+  k_sum_slabs<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(slabs, n, nz, C);
   RLC_LAUNCH_CHECK(h);
   return RLC_OK;
 }
@@ -424,40 +462,59 @@ __global__ void k_head(const float* __restrict__ Z2, long long R, int H2,
     for (int j = lane; j < H2; j += 32) G2[row * H2 + j] = (z[j] > 0.f) ? dq * w3[j] : 0.f;
 }
 
-// out[n] = sum_r M[r, n]   (column sums; one thread per column, coalesced across columns)
-__global__ void k_colsum(const float* __restrict__ Mx, long long R, int N, int ld,
-                         float* __restrict__ out) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// Column reductions over the batch rows, two deterministic stages: stage 1 = one block per
+// (128 columns x one row chunk) writing part[chunk][n]; stage 2 = k_sum_slabs over the chunks.
+//   MODE 0: out[n] = sum_r M[r,n]
+//   MODE 1: out[j] = sum_r relu(Z2[r,j]) dq[r] (j < N) ; out[N] = sum_r dq[r]     (head grads)
+template <int MODE>
+__global__ void __launch_bounds__(128)
+k_colred_part(const float* __restrict__ Mx, const float* __restrict__ dq, long long R, int N, int ld,
+              int rows_per_chunk, float* __restrict__ part) {
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  const int ncols = N + (MODE == 1 ? 1 : 0);
+  if (n >= ncols) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+  const long long r1 = (r0 + rows_per_chunk < R) ? r0 + rows_per_chunk : R;
   float acc = 0.f;
-  for (long long r = 0; r < R; ++r) acc += Mx[r * ld + n];
-  out[n] = acc;
+  if (MODE == 1 && n == N) {
+    for (long long r = r0; r < r1; ++r) acc += dq[r];
+  } else if (MODE == 1) {
+    for (long long r = r0; r < r1; ++r) acc = fmaf(fmaxf(Mx[r * ld + n], 0.f), dq[r], acc);
+  } else {
+    for (long long r = r0; r < r1; ++r) acc += Mx[r * ld + n];
+  }
+  part[(long long)blockIdx.y * ncols + n] = acc;
 }
 
-// gw3[j] = sum_r relu(Z2[r,j]) * dq[r] ; gb3 = sum_r dq[r]  (thread per column j; j==H2 -> gb3)
-__global__ void k_head_grads(const float* __restrict__ Z2, const float* __restrict__ dq,
-                             long long R, int H2, float* __restrict__ gw3,
-                             float* __restrict__ gb3) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j > H2) return;
-  float acc = 0.f;
-  if (j == H2) {
-    for (long long r = 0; r < R; ++r) acc += dq[r];
-    gb3[0] = acc;
-  } else {
-    for (long long r = 0; r < R; ++r) acc = fmaf(fmaxf(Z2[r * H2 + j], 0.f), dq[r], acc);
-    gw3[j] = acc;
-  }
+#define COLRED_MAX_CHUNKS 256
+template <int MODE>
+static int colred(rlc_handle* h, const float* Mx, const float* dq, long long R, int N, int ld, float* part,
+                  float* out, cudaStream_t st) {
+  const int ncols = N + (MODE == 1 ? 1 : 0);
+  int nchunks = (int)((R + 15) / 16);
+  if (nchunks > COLRED_MAX_CHUNKS) nchunks = COLRED_MAX_CHUNKS;
+  if (nchunks < 1) nchunks = 1;
+  const int rpc = (int)((R + nchunks - 1) / nchunks);
+  nchunks = (int)((R + rpc - 1) / rpc);
+  dim3 grid((ncols + 127) / 128, nchunks);
+  k_colred_part<MODE><<<grid, 128, 0, st>>>(Mx, dq, R, N, ld, rpc, part);
+  RLC_LAUNCH_CHECK(h);
+  k_sum_slabs<<<(ncols + 255) / 256, 256, 0, st>>>(part, ncols, nchunks, out);
+  RLC_LAUNCH_CHECK(h);
+  return RLC_OK;
 }
 
 struct TrainWs {
-  float *X, *Z1, *ZC, *Z2, *G2, *G1, *dq;
+  float *X, *Z1, *ZC, *Z2, *G2, *G1, *dq, *slabs, *part;
 };
 
 static size_t train_ws_bytes(const rlc_critic* c, long long R) {
   const ThetaView t = theta_view(c->topology, c->S, c->A, c->H1, c->H2);
   size_t n = (size_t)R * (t.in1 + 2 * (size_t)c->H1 + 2 * (size_t)c->H2 + 1);
   if (c->topology == RLC_TMID) n += (size_t)R * (c->H1 + c->A);
+  const size_t maxw = (size_t)(c->H1 > c->H2 ? c->H1 : c->H2) + 1;
+  n += (size_t)SPLITK_MAX * (size_t)(t.in2 > t.in1 ? t.in2 : t.in1) * maxw;   // split-K slabs of the largest weight
+  n += (size_t)COLRED_MAX_CHUNKS * maxw;                                        // column-reduction partials
   return n * sizeof(float) + 64 * 16;
 }
 
@@ -476,6 +533,9 @@ static TrainWs carve(const rlc_critic* c, long long R, float* base) {
   w.G2 = take((size_t)R * c->H2);
   w.G1 = take((size_t)R * c->H1);
   w.dq = take((size_t)R);
+  const size_t maxw = (size_t)(c->H1 > c->H2 ? c->H1 : c->H2) + 1;
+  w.slabs = take((size_t)SPLITK_MAX * (size_t)(t.in2 > t.in1 ? t.in2 : t.in1) * maxw);
+  w.part = take((size_t)COLRED_MAX_CHUNKS * maxw);
   return w;
 }
 
@@ -568,33 +628,30 @@ extern "C" int rlc_critic_grads(rlc_handle* h, const rlc_critic* c, const float*
   rc = forward_rows(h, c, s, a, B, y, 1.f / (float)B_total, w, q_out, loss_out, st);
   if (rc) return rc;
   // head grads
-  k_head_grads<<<(c->H2 + 1 + 127) / 128, 128, 0, st>>>(w.Z2, w.dq, B, c->H2, grad_out + t.ow3,
-                                                        grad_out + t.ob3);
-  RLC_LAUNCH_CHECK(h);
+  // gw3[j] = sum_r relu(Z2[r,j]) dq[r], gb3 = sum_r dq[r]: theta stores [w3 (H2) | b3 (1)] contiguously
+  rc = colred<1>(h, w.Z2, w.dq, B, c->H2, c->H2, w.part, grad_out + t.ow3, st);
+  if (rc) return rc;
   // gb2 = colsum(G2)
-  k_colsum<<<(c->H2 + 127) / 128, 128, 0, st>>>(w.G2, B, c->H2, c->H2, grad_out + t.ob2);
-  RLC_LAUNCH_CHECK(h);
+  rc = colred<0>(h, w.G2, nullptr, B, c->H2, c->H2, w.part, grad_out + t.ob2, st);
+  if (rc) return rc;
   GemmEpi e{nullptr, nullptr, 0, 0, 1.f};
   if (c->topology == RLC_TIN) {
     GemmEpi er = e;
     er.reluA = 1;  // gW2 = relu(Z1)^T G2
-    rc = gemm(h, true, false, c->H1, c->H2, B, w.Z1, c->H1, w.G2, c->H2, grad_out + t.oW2, c->H2,
-              er, st);
+    rc = gemm_splitk(h, c->H1, c->H2, B, w.Z1, c->H1, w.G2, c->H2, grad_out + t.oW2, er, w.slabs, st);
   } else {
-    rc = gemm(h, true, false, c->H1 + c->A, c->H2, B, w.ZC, c->H1 + c->A, w.G2, c->H2,
-              grad_out + t.oW2, c->H2, e, st);
+    rc = gemm_splitk(h, c->H1 + c->A, c->H2, B, w.ZC, c->H1 + c->A, w.G2, c->H2, grad_out + t.oW2, e,
+                     w.slabs, st);
   }
   if (rc) return rc;
   // G1 = (G2 W2[:H1]^T) * [Z1>0]
   GemmEpi em{nullptr, w.Z1, c->H1, 0, 1.f};
   rc = gemm(h, false, true, B, c->H1, c->H2, w.G2, c->H2, th + t.oW2, c->H2, w.G1, c->H1, em, st);
   if (rc) return rc;
-  k_colsum<<<(c->H1 + 127) / 128, 128, 0, st>>>(w.G1, B, c->H1, c->H1, grad_out + t.ob1);
-  RLC_LAUNCH_CHECK(h);
+  rc = colred<0>(h, w.G1, nullptr, B, c->H1, c->H1, w.part, grad_out + t.ob1, st);
+  if (rc) return rc;
   // gW1 = X^T G1
-  rc = gemm(h, true, false, t.in1, c->H1, B, w.X, t.in1, w.G1, c->H1, grad_out + t.oW1, c->H1, e,
-            st);
-  return rc;
+  return gemm_splitk(h, t.in1, c->H1, B, w.X, t.in1, w.G1, c->H1, grad_out + t.oW1, e, w.slabs, st);
 }
 
 // T-mid dQ/da over a B x N block without materialising the stack (AE+ ascent, ae_plus_network.py:
