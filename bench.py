@@ -327,6 +327,36 @@ def run_b200(args, rank, local_rank, world):
     barrier()
     upd_ms = ev0.elapsed_time(ev1) / upd_reps
 
+    # ---- secondary: cfg1 (Pendulum ReverseKL/ForwardKL shape: B=32, N=62, S=3, A=1, 200-200), the README
+    # command's per-environment-step update, hot-path part: critic regression step (grads, Adam,
+    # operand repack) + grid evaluation + policy reduction, host-synchronous like the reference's loop
+    c1 = dict(S=3, A=1, H1=200, H2=200, B=32, N=62)
+    rng1 = np.random.RandomState(5)
+    p1 = make_params(rng1, c1["S"], c1["A"], c1["H1"], c1["H2"])
+    cr1 = rb.Critic(eng, rb.TIN, c1["S"], c1["A"], c1["H1"], c1["H2"]).load(*p1, rb.LAYOUT_OUT_IN)
+    grid1, w1 = onp.intg_grid_1d(c1["N"] + 2, 2.0)
+    st1 = ForwardKLGridStep(cr1, grid1, w1, 2.0, alpha, c1["B"], precision="auto", repack_each_step=True)
+    opt1 = rb.CriticOptimizer(cr1, lr=1e-3)
+    s1 = rng1.randn(c1["B"], c1["S"]).astype(np.float32)
+    a1 = rng1.uniform(-2, 2, (c1["B"], c1["A"])).astype(np.float32)
+    y1 = rng1.randn(c1["B"]).astype(np.float32)
+    m1, l1 = (rng1.randn(c1["B"], 1) * .5).astype(np.float32), (rng1.randn(c1["B"], 1) * .3 - .5).astype(np.float32)
+    s1d, a1d, y1d = t(s1), t(a1), t(y1)
+
+    def update_cfg1():
+        opt1.step(s1d, a1d, y1d)                   # a15/a16: critic regression (theta changes)
+        return float(st1(s1, m1, l1)[0][0])        # a1-a5: grid eval + reduction with the NEW theta, loss on the host
+
+    for _ in range(20):
+        update_cfg1()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n_upd = 200
+    for _ in range(n_upd):
+        update_cfg1()
+    torch.cuda.synchronize()
+    cfg1_ms = (time.perf_counter() - t0) * 1e3 / n_upd
+
     # ---- max over ranks ----
     tm = torch.tensor([ms_total, e2e_ms, k1_ms, upd_ms, e2e_wall_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -376,6 +406,13 @@ def run_b200(args, rank, local_rank, world):
                          "flops_per_launch": flops, "ms_per_launch": k1_ms, "traffic": traffic},
             "parity": parity,
             "extra": {"critic_update_ms": upd_ms, "critic_updates_per_sec": 1e3 / upd_ms,
+                      "agent_update_hot_path_ms": ms_total / args.steps + upd_ms,
+                      "agent_updates_per_sec": world * 1e3 / (ms_total / args.steps + upd_ms),
+                      "agent_update_definition": "cfg4 per rank: critic regression step (grads + all-reduce + Adam) "
+                                                 "+ sampled-action evaluation + ForwardKL policy reduction",
+                      "cfg1_update_ms": cfg1_ms, "cfg1_updates_per_sec": 1e3 / cfg1_ms,
+                      "cfg1_definition": "B=32 N=62 S=3 A=1 200-200 (README command shape), host-synchronous update: "
+                                         "critic step + repack + grid eval + FKL reduction, loss read on the host",
                       "critic_update_rows_per_rank": B,
                       "critic_update_allreduce": "nccl sum of theta_Q grads" if world > 1 else "none (1 rank)"},
         }
