@@ -301,12 +301,20 @@ def run_b200(args, rank, local_rank, world):
         raise SystemExit("bench.py: e2e step disagrees with the oracle")
     for i in range(args.warmup):
         e2e_step(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        e2e_step(i)
-    torch.cuda.synchronize()
-    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    # host-timed: exactly K steps per trial; 5 trials, the median is reported (host jitter on a shared box
+    # occasionally doubles a single 20-step window), min/max kept in the line
+    import gc
+    gc.disable()
+    trials = []
+    for _ in range(5):
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        trials.append((time.perf_counter() - t0) * 1e3)
+    gc.enable()
+    e2e_wall_ms = float(np.median(trials))
     e2e_ms = e2e_wall_ms          # host-synchronous every step: wall clock IS the end-to-end time
     barrier()
     h2d = (fstep.s_host.numel() + fstep.mean_host.numel() + fstep.log_std_host.numel()) * 4
@@ -396,7 +404,8 @@ def run_b200(args, rank, local_rank, world):
             "clocks": clocks.summary(),
             "e2e": {"value": evals_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
-                    "wall_ms_per_step": e2e_wall_ms / args.steps,
+                    "wall_ms_per_step": e2e_wall_ms / args.steps, "trials": 5,
+                    "trial_ms_per_step_min_max": [min(trials) / args.steps, max(trials) / args.steps],
                     "api": "rlcontrol_b200.steps.ForwardKLGridStep(states, mean, log_std) -> (loss_b, dmean, dlog_std): host arrays in, host arrays out, one CUDA-graph launch + sync per step; timed with the host clock"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "K1 fused T-in critic eval: k_critic_umma_grid (+ k_grid_parts pre-pass) [%s arithmetic]" % critic.tensor_arithmetic(True), "bound": "tensor",
