@@ -99,7 +99,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.001)
 
     def __enter__(self):
         if self.nv is not None:

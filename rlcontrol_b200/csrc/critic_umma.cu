@@ -1079,23 +1079,36 @@ __global__ void k_pack_head(const float* __restrict__ theta, PackGeom G, unsigne
   const ThetaView t = theta_view(RLC_TIN, G.S, G.A, G.H1, G.H2);
   const float* w3 = theta + t.ow3;
   const float* b3 = theta + t.ob3;
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;   // one warp: ballot-based stable partition
+  const int lane = threadIdx.x;
   int* inv0 = reinterpret_cast<int*>(blob0 + G.off_w3);
   int* inv1 = reinterpret_cast<int*>(blob1 + G.off_w3);
   int npos = 0;
   float mx = 0.f;
-  for (int j = 0; j < G.H2; ++j) {
-    const float w = w3[j];
-    if (!(w < 0.f)) ++npos;
+  for (int j0 = 0; j0 < G.H2; j0 += 32) {
+    const int j = j0 + lane;
+    const float w = (j < G.H2) ? w3[j] : 0.f;
+    npos += __popc(__ballot_sync(0xffffffffu, j < G.H2 && !(w < 0.f)));
     mx = fmaxf(mx, fabsf(w));
   }
+  mx = warp_max(mx);
   int p = 0, n = npos;
-  for (int j = 0; j < G.H2; ++j) {
-    const int d = (!(w3[j] < 0.f)) ? p++ : n++;
-    inv0[d] = j;
-    inv1[d] = j;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int j0 = 0; j0 < G.H2; j0 += 32) {
+    const int j = j0 + lane;
+    const bool live = j < G.H2;
+    const bool pos = live && !(w3[j] < 0.f);
+    const unsigned mp = __ballot_sync(0xffffffffu, pos), mn = __ballot_sync(0xffffffffu, live && !pos);
+    if (live) {
+      const int d = pos ? p + __popc(mp & lt) : n + __popc(mn & lt);
+      inv0[d] = j;
+      inv1[d] = j;
+    }
+    p += __popc(mp);
+    n += __popc(mn);
   }
-  for (int d = G.H2; d < G.H2P; ++d) { inv0[d] = -1; inv1[d] = -1; }
+  for (int d = G.H2 + lane; d < G.H2P; d += 32) { inv0[d] = -1; inv1[d] = -1; }
+  if (lane != 0) return;
   int e = 0;
   float scale = 1.f;
   if (mx > 0.f && isfinite(mx)) {

@@ -25,7 +25,8 @@ k_topk(const float* __restrict__ q, int B, int N, int k, long long* __restrict__
   for (int t = 0; t < k; ++t) {
     float bv = -CUDART_INF_F;
     int bi = -1;
-    for (int n = lane; n < N; n += 32) {
+  #pragma unroll 8
+  for (int n = lane; n < N; n += 32) {
       float v = row[n];
       if (v != v) v = CUDART_INF_F;  // NaN ordered like +inf (numpy sorts NaN last ascending)
       const bool below = (v < lastv) || (v == lastv && n < lasti);
@@ -60,6 +61,7 @@ k_stats(const float* __restrict__ q, int B, int N, long long* __restrict__ argma
   const float* row = q + (long long)b * N;
   float bv = -CUDART_INF_F, sum = 0.f;
   int bi = 0x7fffffff;
+#pragma unroll 8
   for (int n = lane; n < N; n += 32) {
     const float v = row[n];
     sum += v;
@@ -86,9 +88,11 @@ k_lse(const float* __restrict__ q, int B, int N, float offset, float* __restrict
   if (b >= B) return;
   const float* row = q + (long long)b * N;
   float m = -CUDART_INF_F;
+#pragma unroll 8
   for (int n = lane; n < N; n += 32) m = fmaxf(m, row[n]);
   m = warp_max(m);
   float s = 0.f;
+#pragma unroll 8
   for (int n = lane; n < N; n += 32) s += expf(row[n] - m);
   s = warp_sum(s);
   if (lane == 0) v_out[b] = m + logf(s) + offset;
@@ -105,12 +109,15 @@ k_fkl(const float* __restrict__ q, const float* __restrict__ w, const float* __r
   const float* row = q + (long long)b * N;
   const float* lp = logp + (long long)b * N;
   float m = -CUDART_INF_F;
+#pragma unroll 8
   for (int n = lane; n < N; n += 32) m = fmaxf(m, __fdiv_rn(row[n], alpha));
   m = warp_max(m);
   float z = 0.f;
+#pragma unroll 8
   for (int n = lane; n < N; n += 32) z = fmaf(expf(__fdiv_rn(row[n], alpha) - m), w[n], z);
   z = warp_sum(z);
   float acc = 0.f;
+#pragma unroll 8
   for (int n = lane; n < N; n += 32) {
     const float p = __fdiv_rn(expf(__fdiv_rn(row[n], alpha) - m), z);
     const float pw = p * w[n];
@@ -134,6 +141,7 @@ k_rkl(const float* __restrict__ q, const float* __restrict__ v, const float* __r
   const float* lp = logp + (long long)b * N;
   const float vb = v[b];
   float acc = 0.f;
+#pragma unroll 8
   for (int n = lane; n < N; n += 32) {
     const float l = lp[n];
     const float pe = expf(l);
@@ -165,19 +173,44 @@ __global__ void k_grid_logterms(const float* __restrict__ grid, int N, int A, fl
 }
 
 #define POL_MAX_A 8
-#define POL_NPL 32   // q values cached per lane (N <= 1024 stays in registers)
+#define POL_THREADS 256
+#define POL_NPT 4    // q values cached per thread (N <= 1024 stays in registers)
 
+// block-wide reductions over POL_THREADS threads (8 warps); `red` is 8 floats of shared memory
+__device__ __forceinline__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  __syncthreads();                                   // protect `red` from the previous use
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int i = 1; i < POL_THREADS / 32; ++i) r = fmaxf(r, red[i]);
+  return r;
+}
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int i = 0; i < POL_THREADS / 32; ++i) r += red[i];     // fixed order: deterministic
+  return r;
+}
+
+// One CTA per state (256 threads x up to 4 grid actions each in registers): the N-way reductions are
+// block-wide, so B x N = 4 M pairs expose 1 M threads of parallelism instead of 4096 serial warps.
 // MODE 0: ForwardKL (Boltzmann weights over the grid, detached); MODE 1: ReverseKL.
 template <int MODE, int A>
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
+__global__ void __launch_bounds__(POL_THREADS)
 k_policy_reduce(const float* __restrict__ q, const float* __restrict__ v, const float* __restrict__ w,
                 const float* __restrict__ U, const float* __restrict__ J, const float* __restrict__ mean,
                 const float* __restrict__ log_std, int B, int N, float alpha, float inv_btotal,
                 float* __restrict__ loss_b, float* __restrict__ dmean, float* __restrict__ dlstd,
                 float* __restrict__ logp_out) {
-  const int b = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (b >= B) return;
+  __shared__ float red[POL_THREADS / 32];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
   const float* row = q + (long long)b * N;
   // per-state constants of the log-density (A == 1: Normal(mean, std); A > 1: the reference hands
   // std to MultivariateNormal as the covariance, forwardkl_network.py:350)
@@ -199,12 +232,12 @@ k_policy_reduce(const float* __restrict__ q, const float* __restrict__ v, const 
     }
   }
   if (A > 1) c0 -= 0.9189385332046727f * (float)A;
-  const bool cached = N <= 32 * POL_NPL;
-  float qc[POL_NPL];
+  const bool cached = N <= POL_THREADS * POL_NPT;
+  float qc[POL_NPT];
   if (cached) {
 #pragma unroll
-    for (int i = 0; i < POL_NPL; ++i) {
-      const int n = lane + 32 * i;
+    for (int i = 0; i < POL_NPT; ++i) {
+      const int n = tid + POL_THREADS * i;
       qc[i] = n < N ? row[n] : 0.f;
     }
   }
@@ -213,38 +246,37 @@ k_policy_reduce(const float* __restrict__ q, const float* __restrict__ v, const 
     m = -CUDART_INF_F;
     if (cached) {
 #pragma unroll
-      for (int i = 0; i < POL_NPL; ++i)
-        if (lane + 32 * i < N) m = fmaxf(m, __fdiv_rn(qc[i], alpha));
+      for (int i = 0; i < POL_NPT; ++i)
+        if (tid + POL_THREADS * i < N) m = fmaxf(m, __fdiv_rn(qc[i], alpha));
     } else {
-      for (int n = lane; n < N; n += 32) m = fmaxf(m, __fdiv_rn(row[n], alpha));
+      for (int n = tid; n < N; n += POL_THREADS) m = fmaxf(m, __fdiv_rn(row[n], alpha));
     }
-    m = warp_max(m);
+    m = block_max(m, red);
     z = 0.f;
     if (cached) {
 #pragma unroll
-      for (int i = 0; i < POL_NPL; ++i) {
-        const int n = lane + 32 * i;
+      for (int i = 0; i < POL_NPT; ++i) {
+        const int n = tid + POL_THREADS * i;
         if (n < N) {
           qc[i] = expf(__fdiv_rn(qc[i], alpha) - m);        // reuse the register for e_n
           z = fmaf(qc[i], w[n], z);
         }
       }
     } else {
-      for (int n = lane; n < N; n += 32) z = fmaf(expf(__fdiv_rn(row[n], alpha) - m), w[n], z);
+      for (int n = tid; n < N; n += POL_THREADS) z = fmaf(expf(__fdiv_rn(row[n], alpha) - m), w[n], z);
     }
-    z = warp_sum(z);
+    z = block_sum(z, red);
   }
   const float vb = (MODE == 1) ? v[b] : 0.f;
   float acc = 0.f, gm[A], gl[A];
-#pragma unroll
 #pragma unroll
   for (int k = 0; k < A; ++k) { gm[k] = 0.f; gl[k] = 0.f; }
   auto body = [&](int n, float qe) {
     // log pi(a_n | s_b)
     float lp = c0 - J[n];
     float d[A];
-  #pragma unroll
-  for (int k = 0; k < A; ++k) {
+#pragma unroll
+    for (int k = 0; k < A; ++k) {
       d[k] = U[(size_t)n * A + k] - mu[k];
       lp = fmaf(-h[k] * d[k], d[k], lp);
     }
@@ -259,8 +291,8 @@ k_policy_reduce(const float* __restrict__ q, const float* __restrict__ v, const 
       acc = fmaf(-pe * inner, w[n], acc);
       g = (-pe * (inner - alpha)) * w[n] * inv_btotal;
     }
-  #pragma unroll
-  for (int k = 0; k < A; ++k) {
+#pragma unroll
+    for (int k = 0; k < A; ++k) {
       gm[k] = fmaf(g, 2.f * h[k] * d[k], gm[k]);
       gl[k] = fmaf(g, (A == 1) ? (gs[k] * d[k] * d[k] - 1.f) : (gs[k] * d[k] * d[k] - 0.5f), gl[k]);
     }
@@ -268,23 +300,32 @@ k_policy_reduce(const float* __restrict__ q, const float* __restrict__ v, const 
   };
   if (cached) {
 #pragma unroll
-    for (int i = 0; i < POL_NPL; ++i) {
-      const int n = lane + 32 * i;
+    for (int i = 0; i < POL_NPT; ++i) {
+      const int n = tid + POL_THREADS * i;
       if (n < N) body(n, qc[i]);
     }
   } else {
-    for (int n = lane; n < N; n += 32)
+    for (int n = tid; n < N; n += POL_THREADS)
       body(n, MODE == 0 ? expf(__fdiv_rn(row[n], alpha) - m) : row[n]);
   }
+  // the 2A+1 output sums in one pass: warp shuffles, one shared-memory exchange, fixed-order final sum
+  __shared__ float fin[POL_THREADS / 32][2 * POL_MAX_A + 1];
   acc = warp_sum(acc);
-  if (lane == 0) loss_b[b] = (MODE == 0) ? -acc : acc;
 #pragma unroll
-  for (int k = 0; k < A; ++k) {
-    const float a1 = warp_sum(gm[k]), a2 = warp_sum(gl[k]);
-    if (lane == 0) {
-      if (dmean) dmean[(size_t)b * A + k] = a1;
-      if (dlstd) dlstd[(size_t)b * A + k] = a2;
-    }
+  for (int k = 0; k < A; ++k) { gm[k] = warp_sum(gm[k]); gl[k] = warp_sum(gl[k]); }
+  if ((tid & 31) == 0) {
+    fin[tid >> 5][0] = acc;
+#pragma unroll
+    for (int k = 0; k < A; ++k) { fin[tid >> 5][1 + k] = gm[k]; fin[tid >> 5][1 + A + k] = gl[k]; }
+  }
+  __syncthreads();
+  if (tid < 2 * A + 1) {
+    float r = 0.f;
+#pragma unroll
+    for (int i = 0; i < POL_THREADS / 32; ++i) r += fin[i][tid];
+    if (tid == 0) loss_b[b] = (MODE == 0) ? -r : r;
+    else if (tid <= A) { if (dmean) dmean[(size_t)b * A + (tid - 1)] = r; }
+    else { if (dlstd) dlstd[(size_t)b * A + (tid - 1 - A)] = r; }
   }
 }
 
@@ -362,7 +403,7 @@ static int policy_reduce(rlc_handle* h, int mode, const float* q, const float* v
   k_grid_logterms<<<(N + 127) / 128, 128, 0, st>>>(grid, N, A, 1.f / action_scale, 1e-6f, U, J);
   RLC_LAUNCH_CHECK(h);
 #define POL_LAUNCH(MODE_, A_)                                                                               \
-  k_policy_reduce<MODE_, A_><<<nblocks(B), 32 * WARPS_PER_BLOCK, 0, st>>>(                                  \
+  k_policy_reduce<MODE_, A_><<<(unsigned)B, POL_THREADS, 0, st>>>(                                          \
       q, v, w, U, J, mean, log_std, B, N, alpha, 1.f / (float)B_total, loss_b_out, dmean_out, dlog_std_out, \
       logp_out)
 #define POL_SWITCH(MODE_)                    \
