@@ -207,6 +207,12 @@ int rlc_critic_grads(rlc_handle* h, const rlc_critic* c, const float* s, const f
 int rlc_adam_step(rlc_handle* h, float* theta, const float* grad, float* m, float* v,
                   int64_t n, int step, float lr, float beta1, float beta2, float eps,
                   int variant, float* target, float tau, void* stream);
+/* CUDA-graph-safe variant: the 1-based step count lives on the device in state_dev[0] (a 16-byte
+ * device buffer, zero-initialised by the caller; words 1..2 are scratch for the derived factors) and
+ * is incremented by the call, so a captured update advances on every replay. */
+int rlc_adam_step_dev(rlc_handle* h, float* theta, const float* grad, float* m, float* v,
+                      int64_t n, int32_t* state_dev, float lr, float beta1, float beta2, float eps,
+                      int variant, float* target, float tau, void* stream);
 int rlc_soft_update(rlc_handle* h, float* target, const float* online, int64_t n, float tau,
                     void* stream);
 

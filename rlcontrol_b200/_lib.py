@@ -59,6 +59,7 @@ SIGNATURES = {
     "rlc_critic_grad_action": (_i, [_p, _cr, _p, _p, _i, _p, _p, _p]),
     "rlc_critic_grads": (_i, [_p, _cr, _p, _p, _p, _i, _i, _p, _p, _p, _p]),
     "rlc_adam_step": (_i, [_p, _p, _p, _p, _p, _i64, _i, _f, _f, _f, _f, _i, _p, _f, _p]),
+    "rlc_adam_step_dev": (_i, [_p, _p, _p, _p, _p, _i64, _p, _f, _f, _f, _f, _i, _p, _f, _p]),
     "rlc_soft_update": (_i, [_p, _p, _p, _i64, _f, _p]),
     "rlc_replay_gather": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p]),
     "rlc_replay_scatter": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p]),

@@ -771,6 +771,57 @@ extern "C" int rlc_adam_step(rlc_handle* h, float* theta, const float* grad, flo
   return RLC_OK;
 }
 
+// CUDA-graph-safe Adam: the step count lives on the device (state_dev[0]) so a captured update
+// advances it on every replay; a one-thread kernel bumps it and derives the two scalar factors.
+__global__ void k_adam_prep(int* state_dev, float lr, float b1, float b2, int variant) {
+  const int t = ++state_dev[0];
+  const double bc1 = 1.0 - pow((double)b1, (double)t), bc2 = 1.0 - pow((double)b2, (double)t);
+  float lr_eff, isb2;
+  if (variant == RLC_ADAM_TORCH) {
+    lr_eff = (float)((double)lr / bc1);
+    isb2 = (float)(1.0 / sqrt(bc2));
+  } else {
+    lr_eff = (float)((double)lr * sqrt(bc2) / bc1);
+    isb2 = 1.f;
+  }
+  reinterpret_cast<float*>(state_dev)[1] = lr_eff;
+  reinterpret_cast<float*>(state_dev)[2] = isb2;
+}
+
+__global__ void k_adam_dev(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                           float* __restrict__ v, long long n, const int* __restrict__ state_dev, float b1,
+                           float b2, float eps, float* __restrict__ target, float tau) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float lr_eff = reinterpret_cast<const float*>(state_dev)[1];
+  const float inv_sqrt_bc2 = reinterpret_cast<const float*>(state_dev)[2];
+  const float gi = g[i];
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float pn = p[i] - lr_eff * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+  p[i] = pn;
+  if (target) target[i] += tau * (pn - target[i]);
+}
+
+extern "C" int rlc_adam_step_dev(rlc_handle* h, float* theta, const float* grad, float* m, float* v,
+                                 int64_t n, int32_t* state_dev, float lr, float beta1, float beta2,
+                                 float eps, int variant, float* target, float tau, void* stream) {
+  RLC_REQUIRE(h && theta && grad && m && v && state_dev && n >= 0);
+  RLC_REQUIRE(variant == RLC_ADAM_TORCH || variant == RLC_ADAM_TF);
+  if (n == 0) return RLC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_adam_prep<<<1, 1, 0, st>>>(state_dev, lr, beta1, beta2, variant);
+  RLC_LAUNCH_CHECK(h);
+  k_adam_dev<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(theta, grad, m, v, n, state_dev, beta1, beta2, eps,
+                                                         target, tau);
+  RLC_LAUNCH_CHECK(h);
+  rlc_invalidate_pack(h, theta);
+  if (target) rlc_invalidate_pack(h, target);
+  return RLC_OK;
+}
+
 __global__ void k_soft(float* __restrict__ t, const float* __restrict__ o, long long n, float tau) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) t[i] += tau * (o[i] - t[i]);

@@ -170,6 +170,13 @@ class Engine:
                                      int(step), float(lr), float(beta1), float(beta2), float(eps),
                                      int(variant), _ptr(target), float(tau), _stream()))
 
+    def adam_step_dev(self, theta, grad, m, v, state_dev, lr: float, variant: int = ADAM_TORCH,
+                      beta1=0.9, beta2=0.999, eps=1e-8, target=None, tau: float = 0.0):
+        """Graph-safe Adam step: the step count lives in ``state_dev`` (int32[4] on the device)."""
+        check(self.lib.rlc_adam_step_dev(self.h, _ptr(theta), _ptr(grad), _ptr(m), _ptr(v), theta.numel(),
+                                         _ptr(state_dev), float(lr), float(beta1), float(beta2), float(eps),
+                                         int(variant), _ptr(target), float(tau), _stream()))
+
     def soft_update(self, target, online, tau: float):
         check(self.lib.rlc_soft_update(self.h, _ptr(target), _ptr(online), target.numel(), float(tau),
                                        _stream()))
@@ -367,8 +374,22 @@ class CriticOptimizer:
         self.m = torch.zeros_like(critic.theta)
         self.v = torch.zeros_like(critic.theta)
         self.t = 0
+        self.state_dev = torch.zeros((4,), dtype=torch.int32, device=critic.theta.device)   # graph-safe step count
         self.target, self.tau = target, float(tau)
         self.pg = process_group
+
+    def step_graph_safe(self, s, a, y, world_size: int = 1):
+        """Same as :meth:`step` but with the Adam step count on the device (``rlc_adam_step_dev``), so the
+        call can sit inside a captured CUDA graph and still advance on every replay.  Do not mix with
+        :meth:`step` on the same optimiser (two counters)."""
+        B = s.shape[0]
+        grad, loss, q = self.critic.grads(s, a, y, b_total=B * world_size)
+        if world_size > 1:
+            from .parallel import allreduce_grad_
+            allreduce_grad_(grad, self.pg)
+        self.critic.eng.adam_step_dev(self.critic.theta, grad, self.m, self.v, self.state_dev, self.lr, self.variant,
+                                      target=None if self.target is None else self.target.theta, tau=self.tau)
+        return loss, q
 
     def step(self, s, a, y, world_size: int = 1):
         """One regression step on this rank's shard of the batch. With world_size>1 the per-rank

@@ -99,3 +99,91 @@ class ForwardKLGridStep:
         self.launch()
         self._stream.synchronize()
         return self.loss_host, self.dmean_host, self.dlog_std_host
+
+
+class GridAgentUpdateStep:
+    """The hot-path part of one ForwardKL / ReverseKL ``update_network`` (forwardkl_network.py:123-209,
+    reversekl_network.py:130-217) as ONE CUDA graph:
+
+        H2D (s, a, y, mean, log_std[, v])  ->  critic regression step on the B rows (grads, Adam with a
+        device-side step count, operand repack)  ->  grid evaluation with the NEW theta  ->  policy
+        reduction with the log-density fused  ->  D2H (q_loss, loss_b, dmean, dlog_std)
+
+    ``y`` is the regression target the reference forms from the target V net (``r + gamma V'(s')``, :137-138)
+    and ``mean, log_std`` the policy head outputs: V and pi are per-state networks outside the path.  Small
+    configs (cfg1: B=32, N=62) are launch-latency-bound: one graph launch replaces ~25 launches + copies.
+    Several agents (independent sweep INDEX runs, cfg5) each own a step on its own stream and Engine and
+    overlap on one GPU: ``launch()`` them all, then ``wait()``."""
+
+    def __init__(self, critic: Critic, optimizer, grid, weights, action_scale: float, entropy_scale: float,
+                 B: int, kind: str = "fkl", hard: bool = False, precision="auto", use_graph: bool = True):
+        if kind not in ("fkl", "rkl"):
+            raise ValueError("kind must be 'fkl' or 'rkl'")
+        eng, dev = critic.eng, critic.eng.device
+        self.critic, self.eng, self.opt, self.kind, self.hard = critic, eng, optimizer, kind, bool(hard)
+        self.grid, self.w = _f32(grid, dev), _f32(weights, dev).reshape(-1)
+        self.N, self.A = self.grid.shape
+        self.B, self.scale, self.alpha, self.prec = int(B), float(action_scale), float(entropy_scale), precision
+        pin = lambda *sh: torch.empty(sh, dtype=torch.float32).pin_memory()
+        devt = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)
+        S, A = critic.S, self.A
+        self.host_in = dict(s=pin(B, S), a=pin(B, A), y=pin(B), mean=pin(B, A), log_std=pin(B, A), v=pin(B))
+        self.dev_in = dict(s=devt(B, S), a=devt(B, A), y=devt(B), mean=devt(B, A), log_std=devt(B, A), v=devt(B))
+        self.host_out = dict(q_loss=pin(1), loss_b=pin(B), dmean=pin(B, A), dlog_std=pin(B, A))
+        self.q = devt(B, self.N)
+        self._graph = None
+        self._stream = torch.cuda.Stream(device=dev)
+        if use_graph:
+            with torch.cuda.stream(self._stream):
+                for _ in range(2):
+                    self._enqueue()
+            self._stream.synchronize()
+            # the warm-up advanced the optimiser twice; that is part of this object's contract (see reset_optimizer)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self._stream):
+                self._enqueue()
+            self._graph = g
+
+    def reset_optimizer(self):
+        """Zero the Adam moments and step count (e.g. after the capture warm-up updates)."""
+        self.opt.m.zero_()
+        self.opt.v.zero_()
+        self.opt.state_dev.zero_()
+
+    def _enqueue(self):
+        d, h = self.dev_in, self.host_in
+        for k in ("s", "a", "y", "mean", "log_std") + (("v",) if self.kind == "rkl" else ()):
+            d[k].copy_(h[k], non_blocking=True)
+        q_loss, _ = self.opt.step_graph_safe(d["s"], d["a"], d["y"])          # theta changes; pack invalidated
+        self.critic.eval_into(d["s"], self.grid, self.q, self.prec)
+        if self.kind == "fkl":
+            loss_b, dm, ds, _ = self.eng.fkl_policy(self.q, self.w, self.grid, self.scale, d["mean"], d["log_std"],
+                                                    self.alpha)
+        else:
+            loss_b, dm, ds, _ = self.eng.rkl_policy(self.q, d["v"], self.w, self.grid, self.scale, d["mean"],
+                                                    d["log_std"], self.alpha, hard=self.hard)
+        o = self.host_out
+        o["q_loss"].copy_(q_loss, non_blocking=True)
+        o["loss_b"].copy_(loss_b, non_blocking=True)
+        o["dmean"].copy_(dm, non_blocking=True)
+        o["dlog_std"].copy_(ds, non_blocking=True)
+
+    def set_inputs(self, **arrays):
+        for k, x in arrays.items():
+            self.host_in[k].copy_(torch.as_tensor(x, dtype=torch.float32).reshape(self.host_in[k].shape))
+
+    def launch(self):
+        with torch.cuda.stream(self._stream):
+            if self._graph is not None:
+                self._graph.replay()
+            else:
+                self._enqueue()
+
+    def wait(self):
+        self._stream.synchronize()
+        return self.host_out
+
+    def __call__(self, **arrays):
+        self.set_inputs(**arrays)
+        self.launch()
+        return self.wait()
