@@ -343,27 +343,54 @@ def run_b200(args, rank, local_rank, world):
     p1 = make_params(rng1, c1["S"], c1["A"], c1["H1"], c1["H2"])
     cr1 = rb.Critic(eng, rb.TIN, c1["S"], c1["A"], c1["H1"], c1["H2"]).load(*p1, rb.LAYOUT_OUT_IN)
     grid1, w1 = onp.intg_grid_1d(c1["N"] + 2, 2.0)
-    st1 = ForwardKLGridStep(cr1, grid1, w1, 2.0, alpha, c1["B"], precision="auto", repack_each_step=True)
-    opt1 = rb.CriticOptimizer(cr1, lr=1e-3)
+    from rlcontrol_b200.steps import GridAgentUpdateStep
     s1 = rng1.randn(c1["B"], c1["S"]).astype(np.float32)
     a1 = rng1.uniform(-2, 2, (c1["B"], c1["A"])).astype(np.float32)
     y1 = rng1.randn(c1["B"]).astype(np.float32)
     m1, l1 = (rng1.randn(c1["B"], 1) * .5).astype(np.float32), (rng1.randn(c1["B"], 1) * .3 - .5).astype(np.float32)
-    s1d, a1d, y1d = t(s1), t(a1), t(y1)
+    v1 = rng1.randn(c1["B"]).astype(np.float32)
+
+    def make_agent(engine):
+        cr = rb.Critic(engine, rb.TIN, c1["S"], c1["A"], c1["H1"], c1["H2"]).load(*p1, rb.LAYOUT_OUT_IN)
+        return GridAgentUpdateStep(cr, rb.CriticOptimizer(cr, lr=1e-3), grid1, w1, 2.0, alpha, c1["B"], kind="rkl",
+                                   precision="auto")
+
+    # one agent, host-synchronous: inputs written, ONE graph launch (critic step + repack + grid eval + RKL
+    # reduction), outputs read -- what one environment step of the README command pays on the hot path
+    ag = make_agent(eng)
 
     def update_cfg1():
-        opt1.step(s1d, a1d, y1d)                   # a15/a16: critic regression (theta changes)
-        return float(st1(s1, m1, l1)[0][0])        # a1-a5: grid eval + reduction with the NEW theta, loss on the host
+        return float(ag(s=s1, a=a1, y=y1, mean=m1, log_std=l1, v=v1)["loss_b"][0])
 
     for _ in range(20):
         update_cfg1()
     torch.cuda.synchronize()
+    n_upd = 300
     t0 = time.perf_counter()
-    n_upd = 200
     for _ in range(n_upd):
         update_cfg1()
     torch.cuda.synchronize()
     cfg1_ms = (time.perf_counter() - t0) * 1e3 / n_upd
+
+    # cfg5 share of one GPU: 8 independent agents (sweep INDEX runs), each its own Engine/stream/graph,
+    # overlapping on the device; replicas only, no communication
+    agents = [make_agent(rb.Engine(local_rank)) for _ in range(8)]
+
+    def sweep_step():
+        for g in agents:
+            g.set_inputs(s=s1, a=a1, y=y1, mean=m1, log_std=l1, v=v1)
+            g.launch()
+        return sum(float(g.wait()["loss_b"][0]) for g in agents)
+
+    for _ in range(10):
+        sweep_step()
+    torch.cuda.synchronize()
+    n_sw = 100
+    t0 = time.perf_counter()
+    for _ in range(n_sw):
+        sweep_step()
+    torch.cuda.synchronize()
+    sweep_ms = (time.perf_counter() - t0) * 1e3 / n_sw
 
     # ---- max over ranks ----
     tm = torch.tensor([ms_total, e2e_ms, k1_ms, upd_ms, e2e_wall_ms], dtype=torch.float64, device=dev)
@@ -420,8 +447,12 @@ def run_b200(args, rank, local_rank, world):
                       "agent_update_definition": "cfg4 per rank: critic regression step (grads + all-reduce + Adam) "
                                                  "+ sampled-action evaluation + ForwardKL policy reduction",
                       "cfg1_update_ms": cfg1_ms, "cfg1_updates_per_sec": 1e3 / cfg1_ms,
-                      "cfg1_definition": "B=32 N=62 S=3 A=1 200-200 (README command shape), host-synchronous update: "
-                                         "critic step + repack + grid eval + FKL reduction, loss read on the host",
+                      "cfg1_definition": "B=32 N=62 S=3 A=1 200-200 (README command shape), host-synchronous update through "
+                                         "steps.GridAgentUpdateStep: inputs from host, one CUDA-graph launch (critic regression "
+                                         "step + operand repack + grid eval + ReverseKL reduction), outputs read on the host",
+                      "cfg5_sweep8_updates_per_sec": world * 8 * 1e3 / sweep_ms, "cfg5_sweep8_ms_per_round": sweep_ms,
+                      "cfg5_definition": "8 independent cfg1 agents per GPU (own Engine, stream and graph each), one update "
+                                         "each per round, host-synchronous per round; replicas only",
                       "critic_update_rows_per_rank": B,
                       "critic_update_allreduce": "nccl sum of theta_Q grads" if world > 1 else "none (1 rank)"},
         }
