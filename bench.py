@@ -69,54 +69,67 @@ def make_inputs(rng, B, N, S, A):
 # ---------------------------------------------------------------------------------------------
 # clocks during the timed region
 # ---------------------------------------------------------------------------------------------
-class ClockSampler:
-    def __init__(self, index):
-        self.index, self.samples, self.reasons, self._stop = index, [], set(), threading.Event()
-        self.max_mhz, self.thread = None, None
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-        except Exception:
-            self.nv = None
+_SAMPLER_SRC = r"""
+import sys, time, json
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+mx = int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+out = []
+sys.stdout.write("ready\n"); sys.stdout.flush()
+import select
+while True:
+    out.append((time.time(), int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(get(h))))
+    if select.select([sys.stdin], [], [], 0.0005)[0]:
+        break
+sys.stdout.write(json.dumps({"max": mx, "samples": out}) + "\n"); sys.stdout.flush()
+"""
 
-    def _run(self):
-        nv = self.nv
-        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
-                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
-                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
-                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
-        while not self._stop.is_set():
-            try:
-                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
-                    nv.nvmlDeviceGetCurrentClocksThrottleReasons
-                mask = int(get(self.h))
-                for k, bit in names.items():
-                    if mask & bit:
-                        self.reasons.add(k)
-            except Exception:
-                pass
-            time.sleep(0.001)
+
+class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region, sampled by a helper PROCESS (pynvml, ~1 kHz)
+    so that the polling never takes this process's GIL away from the launch loop.  The helper runs from
+    construction; only samples whose timestamp falls inside [__enter__, __exit__] are reported."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+
+    def __init__(self, index):
+        import subprocess
+        self.t0 = self.t1 = None
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(index)], stdin=subprocess.PIPE,
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            if self.proc.stdout.readline().strip() != "ready":
+                raise RuntimeError("sampler did not start")
+        except Exception:
+            self.proc = None
 
     def __enter__(self):
-        if self.nv is not None:
-            self.thread = threading.Thread(target=self._run, daemon=True)
-            self.thread.start()
+        self.t0 = time.time()
         return self
 
     def __exit__(self, *exc):
-        self._stop.set()
-        if self.thread is not None:
-            self.thread.join()
+        self.t1 = time.time()
+        self.data = None
+        if self.proc is not None:                 # stop the helper right away: nothing polls NVML after the window
+            try:
+                out, _ = self.proc.communicate("stop\n", timeout=10)
+                self.data = json.loads(out.strip().splitlines()[-1])
+            except Exception:
+                self.proc.kill()
 
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
-        return {"sm_mhz": int(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        data = getattr(self, "data", None)
+        if data is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        inside = [(mhz, mask) for (ts, mhz, mask) in data["samples"] if self.t0 <= ts <= self.t1]
+        if not inside:      # region shorter than one sampling period: take the nearest samples around it
+            inside = sorted(data["samples"], key=lambda x: abs(x[0] - 0.5 * (self.t0 + self.t1)))[:3]
+            inside = [(mhz, mask) for (_, mhz, mask) in inside]
+        reasons = sorted({k for k, bit in self.REASONS.items() for (_, mask) in inside if mask & bit})
+        return {"sm_mhz": int(np.median([m for m, _ in inside])), "sm_max_mhz": data["max"], "reasons": reasons,
+                "samples": len(inside), "sampler": "helper process, pynvml, ~1 kHz"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -256,12 +269,13 @@ def run_b200(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     # ---- device-resident timing: exactly K steps between two events ----
+    clocks = ClockSampler(local_rank)          # helper process starts sampling now; the window is marked below
     for i in range(args.warmup):
         step(i)
     barrier()
     launches0 = eng.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
+    with clocks:
         ev0.record()
         for i in range(args.steps):
             step(args.warmup + i)
