@@ -88,43 +88,40 @@ __device__ __forceinline__ uint32_t add_relu2(uint32_t a, uint32_t b) {
 //   PS[b][j] = b1[j] + sum_k clip(s[b][k]) W1[k][j]   (j < H1);  PS[b][H1] = 1 (the bias carrier of
 //   layer 2, see k_pack_head);  PA[c][n][jj] = sum_k a[n][k] W1[S+k][c*CH+jj].
 template <int PREC>
-__global__ void k_grid_parts(const float* __restrict__ theta, const float* __restrict__ s,
-                             const float* __restrict__ a, const float* __restrict__ smin,
-                             const float* __restrict__ smax, int B, int N, int S, int A, int H1, int H2,
-                             int H1P, int CH, int nch, int NT, unsigned short* __restrict__ PS,
-                             unsigned short* __restrict__ PA) {
+__global__ void __launch_bounds__(128)
+k_grid_parts(const float* __restrict__ theta, const float* __restrict__ s, const float* __restrict__ a,
+             const float* __restrict__ smin, const float* __restrict__ smax, int B, int N, int S, int A,
+             int H1, int H2, int H1P, int CH, int nch, int NT, unsigned short* __restrict__ PS,
+             unsigned short* __restrict__ PA) {
+  // grid: x = row (states first, then padded grid actions), y = feature block of 128; no 64-bit divisions
   const ThetaView t = theta_view(RLC_TIN, S, A, H1, H2);
   const float* W1 = theta + t.oW1;   // [S+A][H1]
   const float* b1 = theta + t.ob1;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long nps = (long long)B * H1P;
-  const int pitch = CH + GR_PITCH_PAD;
-  const long long npa = (long long)nch * NT * 32 * pitch;
-  if (gid < nps) {
-    const int b = (int)(gid / H1P), j = (int)(gid % H1P);
+  const int j = blockIdx.y * 128 + threadIdx.x;
+  const int row = blockIdx.x;
+  if (j >= H1P) return;
+  if (row < B) {
     float acc = 0.f;
     if (j < H1) {
       acc = b1[j];
       for (int k = 0; k < S; ++k) {
-        float x = __ldg(s + (size_t)b * S + k);
+        float x = __ldg(s + (size_t)row * S + k);
         if (smin) x = fminf(fmaxf(x, __ldg(smin + k)), __ldg(smax + k));
         acc = fmaf(x, W1[(size_t)k * H1 + j], acc);
       }
     } else if (j == H1) {
       acc = 1.f;
     }
-    PS[gid] = to_h<PREC>(acc);
-  } else if (gid < nps + npa) {
-    const long long g = gid - nps;
-    const int jj = (int)(g % pitch);
-    const long long rn = g / pitch;
-    const int n = (int)(rn % ((long long)NT * 32)), c = (int)(rn / ((long long)NT * 32));
-    const int j = c * CH + jj;
+    PS[(size_t)row * H1P + j] = to_h<PREC>(acc);
+  } else {
+    const int n = row - B;                                   // 0 .. NT*32-1 (rows past N are zero)
+    const int pitch = CH + GR_PITCH_PAD;
+    const int c = j / CH, jj = j - c * CH;
     float acc = 0.f;
-    if (jj < CH && j < H1 && n < N) {
+    if (j < H1 && n < N) {
       for (int k = 0; k < A; ++k) acc = fmaf(__ldg(a + (size_t)n * A + k), W1[(size_t)(S + k) * H1 + j], acc);
     }
-    PA[g] = to_h<PREC>(acc);
+    PA[((size_t)c * NT * 32 + n) * pitch + jj] = to_h<PREC>(acc);   // the 8 padding halfs per row are never read
   }
 }
 
@@ -511,12 +508,12 @@ static int rlc_eval_umma_grid(rlc_handle* h, const rlc_critic* c, const PackGeom
   unsigned short* PS = (unsigned short*)ws;
   unsigned short* PA = PS + ((nps + 63) & ~(size_t)63);       // keep PA 128-byte aligned
   {
-    const unsigned blocks = (unsigned)((nps + npa + 255) / 256);
+    const dim3 blocks((unsigned)(B + NT * 32), (unsigned)((G.H1P + 127) / 128));
     if (prec == RLC_PREC_BF16)
-      k_grid_parts<RLC_PREC_BF16><<<blocks, 256, 0, st>>>(c->theta, s, a, c->smin, c->smax, B, N, c->S, c->A,
+      k_grid_parts<RLC_PREC_BF16><<<blocks, 128, 0, st>>>(c->theta, s, a, c->smin, c->smax, B, N, c->S, c->A,
                                                           c->H1, c->H2, G.H1P, gp.CH, gp.nch, NT, PS, PA);
     else
-      k_grid_parts<RLC_PREC_FP16><<<blocks, 256, 0, st>>>(c->theta, s, a, c->smin, c->smax, B, N, c->S, c->A,
+      k_grid_parts<RLC_PREC_FP16><<<blocks, 128, 0, st>>>(c->theta, s, a, c->smin, c->smax, B, N, c->S, c->A,
                                                           c->H1, c->H2, G.H1P, gp.CH, gp.nch, NT, PS, PA);
     RLC_LAUNCH_CHECK(h);
   }
