@@ -620,6 +620,59 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 }  // namespace um
 
+// acc += sign_p * relu(z) over NU units of 8 accumulator columns held in registers; units p < kpos belong
+// to the non-negative-w3 group (+), the rest to the negative group (-).  Straight-line: per unit one
+// compare/select for the sign, 8 FMNMX, 8 FFMA on four independent accumulators.
+template <int NU>
+__device__ __forceinline__ void relu_signed_sum(const uint32_t* v, int kpos, float& a0, float& a1, float& a2,
+                                                float& a3) {
+#pragma unroll
+  for (int p = 0; p < NU; ++p) {
+    const float sg = (p < kpos) ? 1.f : -1.f;
+    a0 = fmaf(fmaxf(__uint_as_float(v[p * 8 + 0]), 0.f), sg, a0);
+    a1 = fmaf(fmaxf(__uint_as_float(v[p * 8 + 1]), 0.f), sg, a1);
+    a2 = fmaf(fmaxf(__uint_as_float(v[p * 8 + 2]), 0.f), sg, a2);
+    a3 = fmaf(fmaxf(__uint_as_float(v[p * 8 + 3]), 0.f), sg, a3);
+    a0 = fmaf(fmaxf(__uint_as_float(v[p * 8 + 4]), 0.f), sg, a0);
+    a1 = fmaf(fmaxf(__uint_as_float(v[p * 8 + 5]), 0.f), sg, a1);
+    a2 = fmaf(fmaxf(__uint_as_float(v[p * 8 + 6]), 0.f), sg, a2);
+    a3 = fmaf(fmaxf(__uint_as_float(v[p * 8 + 7]), 0.f), sg, a3);
+  }
+}
+
+// One round of up to 96 columns (w, multiple of 8) whose first `rel` columns belong to the + group.
+// Fast path: no unit straddles the group boundary (sign per unit, straight-line code specialised on the
+// unit count); the one round per row that does straddle takes the per-column path.
+__device__ __forceinline__ void relu_signed_round(const uint32_t* v, int w, int rel, float& a0, float& a1,
+                                                  float& a2, float& a3) {
+  if (rel <= 0 || rel >= w || (rel & 7) == 0) {
+    const int kpos = rel <= 0 ? 0 : (rel >= w ? 12 : (rel >> 3));
+    switch (w >> 3) {
+      case 12: relu_signed_sum<12>(v, kpos, a0, a1, a2, a3); break;
+      case 11: relu_signed_sum<11>(v, kpos, a0, a1, a2, a3); break;
+      case 10: relu_signed_sum<10>(v, kpos, a0, a1, a2, a3); break;
+      case 9: relu_signed_sum<9>(v, kpos, a0, a1, a2, a3); break;
+      case 8: relu_signed_sum<8>(v, kpos, a0, a1, a2, a3); break;
+      case 7: relu_signed_sum<7>(v, kpos, a0, a1, a2, a3); break;
+      case 6: relu_signed_sum<6>(v, kpos, a0, a1, a2, a3); break;
+      case 5: relu_signed_sum<5>(v, kpos, a0, a1, a2, a3); break;
+      case 4: relu_signed_sum<4>(v, kpos, a0, a1, a2, a3); break;
+      case 3: relu_signed_sum<3>(v, kpos, a0, a1, a2, a3); break;
+      case 2: relu_signed_sum<2>(v, kpos, a0, a1, a2, a3); break;
+      default: relu_signed_sum<1>(v, kpos, a0, a1, a2, a3); break;
+    }
+  } else {
+#pragma unroll
+    for (int p = 0; p < 12; ++p) {
+      if (p * 8 < w) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          a0 = fmaf(fmaxf(__uint_as_float(v[p * 8 + e]), 0.f), (p * 8 + e >= rel) ? -1.f : 1.f, a0);
+      }
+    }
+  }
+}
+
 // Pre-pass: 16-byte X chunks.  SP[b][kc] = fp16/bf16 of the (clipped) state entries that fall in
 // K chunk kc, plus the ones column at k = S+A; AP[kc][n] = the action entries (shared grid only).
 // A row of X is SP[b][kc] | AP[kc][n] (the two parts occupy disjoint halfwords; +0.0 = 0x0000).
@@ -969,7 +1022,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_critic_umma_ts(const UmmaPara
       um::tc_fence_after();
       long long t1 = PROF_T();
       pw0 += t1 - t0;
-      float accp = 0.f, accn = 0.f;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       for (int half = 0; half < 2; ++half) {
         const int hb = half ? P.NA : 0, hn = half ? P.NB : P.NA;      // this accumulator half
         // my columns: [j_begin, j_end) -- split of the half in units of 8 columns
@@ -995,26 +1048,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_critic_umma_ts(const UmmaPara
             __syncwarp();
             if (lane == 0) um::mbar_arrive_cluster(half ? l2e1 : l2e0);
           }
-#pragma unroll
-          for (int p = 0; p < 12; ++p) {
-            if (p * 8 < w) {
-              const int j = jb + p * 8;
-              float r[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) r[e] = fmaxf(__uint_as_float(v[p * 8 + e]), 0.f);
-              if (j + 8 <= npos) {
-                accp += ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-              } else if (j >= npos) {
-                accn += ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-              } else {                          // the one unit that straddles the sign boundary
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  if (j + e < npos) accp += r[e];
-                  else accn += r[e];
-                }
-              }
-            }
-          }
+          relu_signed_round(v, w, npos - jb, a0, a1, a2, a3);
         }
         if (j_begin >= j_end) {                 // nothing to drain for this warp: still hand back
           um::tc_fence_before();
@@ -1023,7 +1057,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_critic_umma_ts(const UmmaPara
         }
       }
       // combine the two column halves of each row through shared memory
-      const float acc = accp - accn;
+      const float acc = (a0 + a1) + (a2 + a3);
       float* qp = qpart + (tl & 1) * 128;
       if (chalf) qp[rloc] = acc;
       long long t5 = PROF_T();

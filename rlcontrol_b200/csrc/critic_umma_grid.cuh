@@ -401,29 +401,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_critic_umma_grid(const GridPa
             __syncwarp();
             if (lane == 0) um::mbar_arrive_cluster(half ? l2e1 : l2e0);
           }
-          // acc += sign_j * relu(z_j): units of 8 columns carry one sign except the unit that
-          // straddles npos (at most one per row), which takes the per-column branch.
-#pragma unroll
-          for (int p = 0; p < 12; ++p) {
-            if (p * 8 < w) {
-              const int j = jb + p * 8;
-              if (j + 8 <= npos || j >= npos) {
-                const float sg = (j >= npos) ? -1.f : 1.f;
-                a0 = fmaf(fmaxf(__uint_as_float(v[p * 8 + 0]), 0.f), sg, a0);
-                a1 = fmaf(fmaxf(__uint_as_float(v[p * 8 + 1]), 0.f), sg, a1);
-                a2 = fmaf(fmaxf(__uint_as_float(v[p * 8 + 2]), 0.f), sg, a2);
-                a3 = fmaf(fmaxf(__uint_as_float(v[p * 8 + 3]), 0.f), sg, a3);
-                a0 = fmaf(fmaxf(__uint_as_float(v[p * 8 + 4]), 0.f), sg, a0);
-                a1 = fmaf(fmaxf(__uint_as_float(v[p * 8 + 5]), 0.f), sg, a1);
-                a2 = fmaf(fmaxf(__uint_as_float(v[p * 8 + 6]), 0.f), sg, a2);
-                a3 = fmaf(fmaxf(__uint_as_float(v[p * 8 + 7]), 0.f), sg, a3);
-              } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-                  a0 = fmaf(fmaxf(__uint_as_float(v[p * 8 + e]), 0.f), (j + e >= npos) ? -1.f : 1.f, a0);
-              }
-            }
-          }
+          relu_signed_round(v, w, npos - jb, a0, a1, a2, a3);
         }
         if (j_begin >= j_end) {                 // nothing to drain for this warp: still hand back
           um::tc_fence_before();
