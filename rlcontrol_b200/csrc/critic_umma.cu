@@ -578,6 +578,15 @@ __device__ __forceinline__ void mma2_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] += A[tmem] * B[smem]^T (accumulate always: the predicate is a constant, nothing to compute)
+__device__ __forceinline__ void mma2_ts_acc(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.eq.b32 p, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
@@ -851,10 +860,17 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_critic_umma_ts(const UmmaPara
           long long t2 = PROF_T();
           pw2 += t2 - t1;
           if (ok && issuer) {
+            if (ksteps == 6) {      // full chunk: back-to-back issue, operands precomputed
+              um::mma2_ts(dL2A, a0, um::desc64(b0), idA, acc0);
+#pragma unroll
+              for (int k = 1; k < 6; ++k)
+                um::mma2_ts_acc(dL2A, a0 + 8u * (uint32_t)k, um::desc64(b0 + (uint32_t)k * w2_kstep), idA);
+            } else {
 #pragma unroll 1
-            for (int k = 0; k < ksteps; ++k)
-              um::mma2_ts(dL2A, a0 + 8u * (uint32_t)k, um::desc64(b0 + (uint32_t)k * w2_kstep), idA,
-                          acc0 | (uint32_t)(k > 0));
+              for (int k = 0; k < ksteps; ++k)
+                um::mma2_ts(dL2A, a0 + 8u * (uint32_t)k, um::desc64(b0 + (uint32_t)k * w2_kstep), idA,
+                            acc0 | (uint32_t)(k > 0));
+            }
           }
           if (two_halves) {
             if (c == 0) {
@@ -866,10 +882,17 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_critic_umma_ts(const UmmaPara
               t2 += t4 - t3;
             }
             if (ok && issuer) {
+              if (ksteps == 6) {
+                um::mma2_ts(dL2B, a0, um::desc64(b0 + w2_half_off), idB, acc0);
+#pragma unroll
+                for (int k = 1; k < 6; ++k)
+                  um::mma2_ts_acc(dL2B, a0 + 8u * (uint32_t)k, um::desc64(b0 + w2_half_off + (uint32_t)k * w2_kstep), idB);
+              } else {
 #pragma unroll 1
-              for (int k = 0; k < ksteps; ++k)
-                um::mma2_ts(dL2B, a0 + 8u * (uint32_t)k, um::desc64(b0 + w2_half_off + (uint32_t)k * w2_kstep),
-                            idB, acc0 | (uint32_t)(k > 0));
+                for (int k = 0; k < ksteps; ++k)
+                  um::mma2_ts(dL2B, a0 + 8u * (uint32_t)k, um::desc64(b0 + w2_half_off + (uint32_t)k * w2_kstep),
+                              idB, acc0 | (uint32_t)(k > 0));
+              }
             }
           }
           if (ok && issuer && c == nch - 1) um::commit2(bar(TB_L2_FULL));

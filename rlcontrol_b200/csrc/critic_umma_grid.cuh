@@ -47,6 +47,7 @@ struct GridParams {
   int sm_w2, sm_pa, sm_ps, sm_qp, sm_bar, pa_stage_bytes, ps_stage_bytes;
   int* err;
   long long* prof;            // RLC_UMMA_PROF=1: 32 x int64 per pair
+  int micro;                  // debug: 1 = tensor-pipe microbenchmark (MMA issuer free-runs, epilogues idle, output garbage)
 };
 
 enum {
@@ -178,6 +179,18 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_critic_umma_grid(const GridPa
   const bool prof = PROF && P.prof != nullptr;
   const long long t_begin = prof ? clock64() : 0;
 #define GPROF_T() ((PROF && prof) ? clock64() : 0)
+  // event trace (pair 0, leader CTA, first 12 tiles): role r appends (code, clock - t_begin) pairs at prof[4096 + r*2048 ..]
+  int tr_n = 0;
+  const bool tracing = PROF && prof && pair == 0 && rank == 0;
+#define GTRACE(role, code)                                                        \
+  do {                                                                            \
+    if (PROF && tracing && tr_n < 1000) {                                         \
+      long long* tb = P.prof + 4096 + (role) * 2048;                              \
+      tb[2 * tr_n] = (code);                                                      \
+      tb[2 * tr_n + 1] = clock64() - t_begin;                                     \
+      ++tr_n;                                                                     \
+    }                                                                             \
+  } while (0)
 
   const int ntiles = (P.num_pair_tiles > (int)pair)
                          ? (P.num_pair_tiles - (int)pair + (int)npairs - 1) / (int)npairs
@@ -211,14 +224,17 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_critic_umma_grid(const GridPa
         const uint32_t tpar = (uint32_t)(tl & 1);
         for (int pass = 0; pass < (two_halves ? 2 : 1) && ok; ++pass) {
           long long t0 = GPROF_T();
-          ok = ok && um::mbar_wait(bar(GB_L2_EMPTY + pass), tpar ^ 1u, P.err, 14 + pass);
+          GTRACE(0, tl * 100 + pass * 10 + 8);        // waiting for accumulator half
+          if (!P.micro) ok = ok && um::mbar_wait(bar(GB_L2_EMPTY + pass), tpar ^ 1u, P.err, 14 + pass);
+          GTRACE(0, tl * 100 + pass * 10 + 9);        // got accumulator half
           long long t1 = GPROF_T();
           pb_ += t1 - t0;
           const bool last_pass = pass == (two_halves ? 1 : 0);
           for (int c = 0; c < nch && ok; ++c) {
             long long t2 = GPROF_T();
-            if (pass == 0) ok = ok && um::mbar_wait(bar(GB_H1_FULL + c), tpar, P.err, 13);
+            if (pass == 0 && !P.micro) ok = ok && um::mbar_wait(bar(GB_H1_FULL + c), tpar, P.err, 13);
             um::tc_fence_after();
+            if (issuer) GTRACE(0, tl * 100 + pass * 10 + c);   // chunk ready, issuing
             long long t3 = GPROF_T();
             pa_ += t3 - t2;
             const int ksteps = (c == nch - 1 ? last_w : CH) >> 4;
@@ -227,14 +243,24 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_critic_umma_grid(const GridPa
             const uint32_t acc0 = c > 0 ? 1u : 0u;
             if (ok && issuer) {
               const uint32_t d = pass ? dL2B : dL2A, idesc = pass ? idB : idA;
+              if (ksteps == 6) {
+                // full 96-wide chunk: six back-to-back tcgen05.mma, all operands precomputed (the issuing
+                // thread must stay well under the ~72-80 cycles one of these MMAs takes)
+                um::mma2_ts(d, a0, um::desc64(b0), idesc, acc0);
+#pragma unroll
+                for (int k = 1; k < 6; ++k)
+                  um::mma2_ts_acc(d, a0 + 8u * (uint32_t)k, um::desc64(b0 + (uint32_t)k * w2_kstep), idesc);
+              } else {
 #pragma unroll 1
-              for (int k = 0; k < ksteps; ++k)
-                um::mma2_ts(d, a0 + 8u * (uint32_t)k, um::desc64(b0 + (uint32_t)k * w2_kstep), idesc,
-                            acc0 | (uint32_t)(k > 0));
+                for (int k = 0; k < ksteps; ++k)
+                  um::mma2_ts(d, a0 + 8u * (uint32_t)k, um::desc64(b0 + (uint32_t)k * w2_kstep), idesc,
+                              acc0 | (uint32_t)(k > 0));
+              }
               if (last_pass) um::commit2(bar(GB_H1_EMPTY + c));      // chunk buffer free for the next tile
               if (c == nch - 1) um::commit2(bar(GB_L2_FULL + pass));
             }
             __syncwarp();
+            if (issuer) GTRACE(0, tl * 100 + pass * 10 + c + 50);   // chunk issued
             pc_ += GPROF_T() - t3;
           }
         }
@@ -244,6 +270,8 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_critic_umma_grid(const GridPa
         o[0] = clock64() - t_begin; o[1] = pa_; o[2] = pb_; o[3] = pc_; o[6] = ntiles;
       }
     }
+  } else if (P.micro) {
+    // microbenchmark: nobody but the MMA issuer works
   } else if (warp == 1) {
     // =================================== loader (one lane) ===================================
     if (lane == 0) {
@@ -299,6 +327,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_critic_umma_grid(const GridPa
         ok = ok && um::mbar_wait(bar(GB_H1_EMPTY + c), tpar ^ 1u, P.err, 32);
         if (!ok) break;
         um::tc_fence_after();
+        if (tid == 128) GTRACE(1, tl * 100 + c);            // chunk buffer free + PA here: start building
         long long t2 = GPROF_T();
         pa_ += t1 - t0;
         pb_ += t2 - t1;
@@ -345,6 +374,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_critic_umma_grid(const GridPa
         um::tc_fence_before();
         __syncwarp();
         if (lane == 0) um::mbar_arrive_cluster(h1f0 + 8u * (uint32_t)c);
+        if (tid == 128) GTRACE(1, tl * 100 + c + 50);       // chunk published
         long long t4 = GPROF_T();
         pc_ += t3 - t2;
         pd_ += t4 - t3;
@@ -379,6 +409,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_critic_umma_grid(const GridPa
         }
         long long t1 = GPROF_T();
         pa_ += t1 - t0;
+        if (tid == 256) GTRACE(2, tl * 100 + half * 10 + 0);      // accumulator half full
         const int units = hn >> 3, u0 = chalf ? (units + 1) / 2 : 0, u1 = chalf ? units : (units + 1) / 2;
         const int j_begin = hb + u0 * 8, j_end = hb + u1 * 8;
         for (int jb = j_begin; jb < j_end; jb += 96) {
@@ -396,6 +427,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_critic_umma_grid(const GridPa
           }
           um::tmem_ld_wait();
           { long long tt = GPROF_T(); pb_ += tt - t1; t1 = tt; }
+          if (tid == 256) GTRACE(2, tl * 100 + half * 10 + 1);    // loaded (released right after)
           if (jb + 96 >= j_end) {               // last round of this half: hand it back
             um::tc_fence_before();
             __syncwarp();
@@ -409,6 +441,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_critic_umma_grid(const GridPa
           if (lane == 0) um::mbar_arrive_cluster(half ? l2e1 : l2e0);
         }
         pc_ += GPROF_T() - t1;
+        if (tid == 256) GTRACE(2, tl * 100 + half * 10 + 2);      // math done
       }
       if (!ok) break;
       long long t5 = GPROF_T();
@@ -430,6 +463,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_critic_umma_grid(const GridPa
     }
   }
 #undef GPROF_T
+#undef GTRACE
 
   um::tc_fence_before();
   __syncthreads();
@@ -530,9 +564,14 @@ static int rlc_eval_umma_grid(rlc_handle* h, const rlc_critic* c, const PackGeom
   static long long* prof_dev = nullptr;
   if (prof_on < 0) { const char* e = getenv("RLC_UMMA_PROF"); prof_on = (e && e[0] == '1') ? 1 : 0; }
   if (prof_on) {
-    if (!prof_dev) RLC_CUDA(cudaMalloc(&prof_dev, 128 * 32 * sizeof(long long)));
-    RLC_CUDA(cudaMemsetAsync(prof_dev, 0, 128 * 32 * sizeof(long long), st));
+    if (!prof_dev) RLC_CUDA(cudaMalloc(&prof_dev, (4096 + 3 * 2048) * sizeof(long long)));
+    RLC_CUDA(cudaMemsetAsync(prof_dev, 0, (4096 + 3 * 2048) * sizeof(long long), st));
     P.prof = prof_dev;
+  }
+  {
+    static int micro = -1;     // debug: tensor-pipe microbenchmark (results are garbage), RLC_UMMA_MICRO=1
+    if (micro < 0) { const char* mi = getenv("RLC_UMMA_MICRO"); micro = mi ? atoi(mi) : 0; }
+    P.micro = micro;
   }
   void (*kern)(const GridParams) =
       P.prof ? (prec == RLC_PREC_BF16 ? k_critic_umma_grid<RLC_PREC_BF16, true> : k_critic_umma_grid<RLC_PREC_FP16, true>)
@@ -541,9 +580,18 @@ static int rlc_eval_umma_grid(rlc_handle* h, const rlc_critic* c, const PackGeom
   RLC_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
   RLC_LAUNCH_CHECK(h);
   if (prof_on) {   // debug only: synchronises
-    static long long hp[128 * 32];
+    static long long hp[4096 + 3 * 2048];
     RLC_CUDA(cudaStreamSynchronize(st));
     RLC_CUDA(cudaMemcpy(hp, prof_dev, sizeof(hp), cudaMemcpyDeviceToHost));
+    if (getenv("RLC_UMMA_TRACE")) {
+      const char* names[3] = {"MMA", "EP1", "EP2"};
+      for (int r = 0; r < 3; ++r)
+        for (int i = 0; i < 1000; ++i) {
+          const long long code = hp[4096 + r * 2048 + 2 * i], tc = hp[4096 + r * 2048 + 2 * i + 1];
+          if (tc == 0 && code == 0 && i > 0) break;
+          if (code / 100 >= 6 && code / 100 <= 8) fprintf(stderr, "TRACE %s %lld %lld\n", names[r], code, tc);
+        }
+    }
     const long long* o = hp;
     const double T = (double)o[0], nt = (double)(o[6] > 0 ? o[6] : 1);
     fprintf(stderr, "[grid prof pair0] CH %d nbuf %d tiles %lld total %.0f cyc (%.0f/tile) | MMA: waitH1 %.1f%% waitL2E %.1f%% issue %.1f%% | "
