@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librlc.so")
+LIB_PATH = os.environ.get("RLC_LIB_PATH") or os.path.join(_HERE, "librlc.so")   # env override: A/B builds
 
 TIN, TMID = 0, 1
 LAYOUT_OUT_IN, LAYOUT_IN_OUT = 0, 1

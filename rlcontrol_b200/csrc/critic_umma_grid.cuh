@@ -24,10 +24,15 @@
 // pass A of the next tile: the accumulator hand-over costs the tensor pipe nothing.
 //
 // Warps: 0 MMA issuer (leader) | 1 loader (cp.async.bulk of PA chunk tiles and PS rows into
-// shared-memory rings, mbarrier complete_tx) | 4-7 epilogue 1 | 8-15 epilogue 2.
+// shared-memory rings, mbarrier complete_tx) | 4 x GR_E1G epilogue 1 | 4 x GR_E2G epilogue 2 (each
+// group of 4 warps covers the four TMEM lane quarters and takes a share of the columns).
 #pragma once
 
-#define GR_THREADS 512
+#define GR_E1G 1
+#define GR_E2G 2
+#define GR_VR (GR_E2G >= 3 ? 56 : 96)   // accumulator columns an epilogue-2 thread holds in registers per round
+#define GR_W2_0 (4 + 4 * GR_E1G)                    // first epilogue-2 warp
+#define GR_THREADS (32 * (4 + 4 * GR_E1G + 4 * GR_E2G))
 #define GR_PA_STAGES 4
 #define GR_MAX_NCH 8
 #define GR_PITCH_PAD 8  // halfs of padding per PA row: pitch (CH+8)*2 B keeps 16-byte LDS conflict-free
@@ -153,16 +158,16 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_critic_umma_grid(const GridPa
   if (tid == 0) {
     for (int i = 0; i < GR_PA_STAGES; ++i) {
       um::mbar_init(bar(GB_PA_FULL + i), 1);
-      um::mbar_init(bar(GB_PA_EMPTY + i), 4);
+      um::mbar_init(bar(GB_PA_EMPTY + i), 4 * GR_E1G);
     }
     for (int i = 0; i < 2; ++i) {
       um::mbar_init(bar(GB_PS_FULL + i), 1);
-      um::mbar_init(bar(GB_PS_EMPTY + i), 4);
+      um::mbar_init(bar(GB_PS_EMPTY + i), 4 * GR_E1G);
       um::mbar_init(bar(GB_L2_FULL + i), 1);
-      um::mbar_init(bar(GB_L2_EMPTY + i), 16);
+      um::mbar_init(bar(GB_L2_EMPTY + i), 8 * GR_E2G);
     }
     for (int i = 0; i < GR_MAX_NCH; ++i) {
-      um::mbar_init(bar(GB_H1_FULL + i), 8);
+      um::mbar_init(bar(GB_H1_FULL + i), 8 * GR_E1G);
       um::mbar_init(bar(GB_H1_EMPTY + i), 1);
     }
     um::fence_mbar_init();
@@ -306,9 +311,10 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_critic_umma_grid(const GridPa
         }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < GR_W2_0) {
     // ===== epilogue 1: h1 = relu(PS[b] + PA[n]) (packed fp16) -> TMEM (layer 2's A operand) =====
     const int q4 = warp & 3;                       // TMEM lane quarter == state b0 + q4 of the tile
+    const int cg = (warp - 4) >> 2;                // which share of each chunk's columns this warp builds
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
     const uint32_t h1f0 = um::mapa(bar(GB_H1_FULL), 0);
     const int pitch_b = (CH + GR_PITCH_PAD) * 2;
@@ -335,6 +341,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_critic_umma_grid(const GridPa
         const uint4* pa4 = reinterpret_cast<const uint4*>(base_ptr + P.sm_pa + st * P.pa_stage_bytes + lane * pitch_b);
         const uint4* ps4 = reinterpret_cast<const uint4*>(ps_row + c * CH * 2);
         const uint32_t tcol = lane_addr + H1COL + (uint32_t)c * bufcols;
+#if GR_E1G == 1
         if (w == 96) {
           // full chunk: straight-line code, 12 x (2 LDS.128 + 4 HFMA2.RELU) + 3 STTM.x16
 #pragma unroll
@@ -367,6 +374,41 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_critic_umma_grid(const GridPa
             um::tmem_st8(tcol + (uint32_t)(p * 8), o);
           }
         }
+#else
+        // my units of 16 activations (8 packed TMEM cells); stored two units at a time (tcgen05.st.x16,
+        // fewer and wider TMEM stores are measurably faster) with a single-unit tail
+        const int nunit = w >> 4, ub = nunit * cg / GR_E1G, ue = nunit * (cg + 1) / GR_E1G;
+        constexpr int MAXU = (6 + GR_E1G - 1) / GR_E1G;
+#pragma unroll
+        for (int i = 0; i < MAXU; i += 2) {
+          const int u = ub + i;
+          if (u + 1 < ue) {
+            uint32_t o[16];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 x = pa4[u * 2 + g];
+              const uint4 y = ps4[u * 2 + g];
+              o[g * 4 + 0] = um::add_relu2<PREC>(x.x, y.x);
+              o[g * 4 + 1] = um::add_relu2<PREC>(x.y, y.y);
+              o[g * 4 + 2] = um::add_relu2<PREC>(x.z, y.z);
+              o[g * 4 + 3] = um::add_relu2<PREC>(x.w, y.w);
+            }
+            um::tmem_st16p(tcol + (uint32_t)(u * 8), o);
+          } else if (u < ue) {
+            uint32_t o[8];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const uint4 x = pa4[u * 2 + g];
+              const uint4 y = ps4[u * 2 + g];
+              o[g * 4 + 0] = um::add_relu2<PREC>(x.x, y.x);
+              o[g * 4 + 1] = um::add_relu2<PREC>(x.y, y.y);
+              o[g * 4 + 2] = um::add_relu2<PREC>(x.z, y.z);
+              o[g * 4 + 3] = um::add_relu2<PREC>(x.w, y.w);
+            }
+            um::tmem_st8(tcol + (uint32_t)(u * 8), o);
+          }
+        }
+#endif
         __syncwarp();
         if (lane == 0) um::mbar_arrive_local(bar(GB_PA_EMPTY + (int)st));   // PA stage consumed
         long long t3 = GPROF_T();
@@ -386,9 +428,9 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_critic_umma_grid(const GridPa
     if (prof && rank == 0 && tid == 128) {
       long long* o = P.prof + (size_t)pair * 32 + 8; o[0] = pa_; o[1] = pb_; o[2] = pc_; o[3] = pd_;
     }
-  } else if (warp >= 8) {
-    // ================ epilogue 2 (8 warps): L2 acc -> relu -> signed sum -> q ====================
-    const int q4 = warp & 3, chalf = (warp - 8) >> 2;
+  } else if (warp >= GR_W2_0) {
+    // ================ epilogue 2 (4 x GR_E2G warps): L2 acc -> relu -> signed sum -> q ====================
+    const int q4 = warp & 3, cg = (warp - GR_W2_0) >> 2;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
     const uint32_t l2e0 = um::mapa(bar(GB_L2_EMPTY + 0), 0);
     const uint32_t l2e1 = um::mapa(bar(GB_L2_EMPTY + 1), 0);
@@ -409,14 +451,14 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_critic_umma_grid(const GridPa
         }
         long long t1 = GPROF_T();
         pa_ += t1 - t0;
-        if (tid == 256) GTRACE(2, tl * 100 + half * 10 + 0);      // accumulator half full
-        const int units = hn >> 3, u0 = chalf ? (units + 1) / 2 : 0, u1 = chalf ? units : (units + 1) / 2;
+        if (tid == 32 * GR_W2_0) GTRACE(2, tl * 100 + half * 10 + 0);      // accumulator half full
+        const int units = hn >> 3, u0 = units * cg / GR_E2G, u1 = units * (cg + 1) / GR_E2G;
         const int j_begin = hb + u0 * 8, j_end = hb + u1 * 8;
-        for (int jb = j_begin; jb < j_end; jb += 96) {
-          const int w = (j_end - jb < 96) ? (j_end - jb) : 96;
-          uint32_t v[96];
+        for (int jb = j_begin; jb < j_end; jb += GR_VR) {
+          const int w = (j_end - jb < GR_VR) ? (j_end - jb) : GR_VR;
+          uint32_t v[GR_VR];
 #pragma unroll
-          for (int p = 0; p < 3; ++p) {
+          for (int p = 0; p < (GR_VR + 31) / 32; ++p) {
             if (p * 32 + 32 <= w) um::tmem_ld32p(lane_addr + (uint32_t)(jb + p * 32), v + p * 32);
             else if (p * 32 < w) {
               const int rem = w - p * 32;             // 8, 16 or 24
@@ -427,8 +469,8 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_critic_umma_grid(const GridPa
           }
           um::tmem_ld_wait();
           { long long tt = GPROF_T(); pb_ += tt - t1; t1 = tt; }
-          if (tid == 256) GTRACE(2, tl * 100 + half * 10 + 1);    // loaded (released right after)
-          if (jb + 96 >= j_end) {               // last round of this half: hand it back
+          if (tid == 32 * GR_W2_0) GTRACE(2, tl * 100 + half * 10 + 1);    // loaded (released right after)
+          if (jb + GR_VR >= j_end) {               // last round of this half: hand it back
             um::tc_fence_before();
             __syncwarp();
             if (lane == 0) um::mbar_arrive_cluster(half ? l2e1 : l2e0);
@@ -441,24 +483,27 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_critic_umma_grid(const GridPa
           if (lane == 0) um::mbar_arrive_cluster(half ? l2e1 : l2e0);
         }
         pc_ += GPROF_T() - t1;
-        if (tid == 256) GTRACE(2, tl * 100 + half * 10 + 2);      // math done
+        if (tid == 32 * GR_W2_0) GTRACE(2, tl * 100 + half * 10 + 2);      // math done
       }
       if (!ok) break;
       long long t5 = GPROF_T();
       const float acc = (a0 + a1) + (a2 + a3);
-      float* qp = qpart + (tl & 1) * 128;
-      if (chalf) qp[rloc] = acc;
-      um::named_bar_sync(1, 256);
-      if (!chalf) {
+      float* qp = qpart + (tl & 1) * (128 * (GR_E2G - 1));
+      if (cg) qp[(cg - 1) * 128 + rloc] = acc;
+      um::named_bar_sync(1, 128 * GR_E2G);
+      if (!cg) {
         const long long ct = 2ll * ((long long)pair + (long long)tl * npairs) + rank;
         if (ct < P.num_cta_tiles) {
           const int b = (int)(ct / P.NT) * 4 + q4, n = (int)(ct % P.NT) * 32 + lane;
-          if (b < P.B && n < P.N) P.q[(size_t)b * P.N + n] = fmaf(inv_scale, acc + qp[rloc], b3v);
+          float tot = acc;
+#pragma unroll
+          for (int g = 0; g < GR_E2G - 1; ++g) tot += qp[g * 128 + rloc];
+          if (b < P.B && n < P.N) P.q[(size_t)b * P.N + n] = fmaf(inv_scale, tot, b3v);
         }
       }
       pd_ += GPROF_T() - t5;
     }
-    if (prof && rank == 0 && tid == 256) {
+    if (prof && rank == 0 && tid == 32 * GR_W2_0) {
       long long* o = P.prof + (size_t)pair * 32 + 16; o[0] = pa_; o[1] = pb_; o[2] = pc_; o[3] = pd_;
     }
   }
@@ -502,7 +547,7 @@ static bool plan_grid(const PackGeom& G, GridPlan& p) {
   p.ps_stage = 4 * G.H1P * 2;
   p.sm_ps = p.sm_pa + GR_PA_STAGES * p.pa_stage;
   p.sm_qp = (p.sm_ps + 2 * p.ps_stage + 127) & ~127;
-  p.sm_bar = p.sm_qp + 1024;
+  p.sm_bar = p.sm_qp + 2 * 128 * 4 * (GR_E2G > 1 ? GR_E2G - 1 : 1);
   p.total = p.sm_bar + GB_COUNT * 8 + 16 + 1024;
   return true;
 }
