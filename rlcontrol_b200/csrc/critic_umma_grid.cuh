@@ -30,9 +30,10 @@
 
 #define GR_E1G 1
 #define GR_E2G 2
+#define GR_E1C 1
 #define GR_VR (GR_E2G >= 3 ? 56 : 96)   // accumulator columns an epilogue-2 thread holds in registers per round
-#define GR_W2_0 (4 + 4 * GR_E1G)                    // first epilogue-2 warp
-#define GR_THREADS (32 * (4 + 4 * GR_E1G + 4 * GR_E2G))
+#define GR_W2_0 (4 + 4 * GR_E1G * GR_E1C)                    // first epilogue-2 warp
+#define GR_THREADS (32 * (4 + 4 * GR_E1G * GR_E1C + 4 * GR_E2G))
 #define GR_PA_STAGES 4
 #define GR_MAX_NCH 8
 #define GR_PITCH_PAD 8  // halfs of padding per PA row: pitch (CH+8)*2 B keeps 16-byte LDS conflict-free
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_critic_umma_grid(const GridPa
     }
     for (int i = 0; i < 2; ++i) {
       um::mbar_init(bar(GB_PS_FULL + i), 1);
-      um::mbar_init(bar(GB_PS_EMPTY + i), 4 * GR_E1G);
+      um::mbar_init(bar(GB_PS_EMPTY + i), 4 * GR_E1G * GR_E1C);
       um::mbar_init(bar(GB_L2_FULL + i), 1);
       um::mbar_init(bar(GB_L2_EMPTY + i), 8 * GR_E2G);
     }
@@ -314,7 +315,8 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_critic_umma_grid(const GridPa
   } else if (warp >= 4 && warp < GR_W2_0) {
     // ===== epilogue 1: h1 = relu(PS[b] + PA[n]) (packed fp16) -> TMEM (layer 2's A operand) =====
     const int q4 = warp & 3;                       // TMEM lane quarter == state b0 + q4 of the tile
-    const int cg = (warp - 4) >> 2;                // which share of each chunk's columns this warp builds
+    const int cg = ((warp - 4) >> 2) % GR_E1G;     // which share of each chunk's columns this warp builds
+    const int cgrp = ((warp - 4) >> 2) / GR_E1G;   // which chunks (global chunk index % GR_E1C == cgrp)
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
     const uint32_t h1f0 = um::mapa(bar(GB_H1_FULL), 0);
     const int pitch_b = (CH + GR_PITCH_PAD) * 2;
@@ -327,6 +329,10 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_critic_umma_grid(const GridPa
       if (!ok) break;
       const unsigned char* ps_row = base_ptr + P.sm_ps + pb * P.ps_stage_bytes + q4 * (P.H1P * 2);
       for (int c = 0; c < nch; ++c) {
+        if (GR_E1C > 1 && (tl * nch + c) % GR_E1C != cgrp) {      // another group's chunk: just advance the ring cursor
+          if (++st == GR_PA_STAGES) { st = 0; spar ^= 1u; }
+          continue;
+        }
         long long t0 = GPROF_T();
         ok = um::mbar_wait(bar(GB_PA_FULL + (int)st), spar, P.err, 31);
         long long t1 = GPROF_T();

@@ -119,15 +119,18 @@ class Engine:
         return loss_b, dlogp
 
     def fkl_policy(self, q, w, grid, action_scale: float, mean, log_std, entropy_scale: float,
-                   b_total: Optional[int] = None, want_grad: bool = True, want_logp: bool = False):
+                   b_total: Optional[int] = None, want_grad: bool = True, want_logp: bool = False, out=None):
         """ForwardKL grid reduction with ``PolicyNetwork.get_logprob`` evaluated in place
         (forwardkl_network.py:165-194 + :324-351).  Returns (loss_b [B], dmean [B,A] | None,
         dlog_std [B,A] | None, logp [B,N] | None)."""
         B, N = q.shape
         A = grid.shape[-1]
-        loss_b = torch.empty((B,), dtype=torch.float32, device=q.device)
-        dm = torch.empty((B, A), dtype=torch.float32, device=q.device) if want_grad else None
-        ds = torch.empty((B, A), dtype=torch.float32, device=q.device) if want_grad else None
+        if out is not None:                 # preallocated (loss_b [B], dmean [B,A], dlog_std [B,A]) device tensors
+            loss_b, dm, ds = out
+        else:
+            loss_b = torch.empty((B,), dtype=torch.float32, device=q.device)
+            dm = torch.empty((B, A), dtype=torch.float32, device=q.device) if want_grad else None
+            ds = torch.empty((B, A), dtype=torch.float32, device=q.device) if want_grad else None
         lp = torch.empty_like(q) if want_logp else None
         check(self.lib.rlc_reduce_fkl_policy(self.h, _ptr(q), _ptr(w), _ptr(grid), A, float(action_scale),
                                              _ptr(mean), _ptr(log_std), B, N, float(entropy_scale),

@@ -37,29 +37,40 @@ class ForwardKLGridStep:
         self.b_total = int(b_total or B)
         # training loops change theta between steps: rebuild the tensor-core operand pack inside the step
         self.repack = bool(repack_each_step)
-        pin = lambda *sh: torch.empty(sh, dtype=torch.float32).pin_memory()
-        devt = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)
-        self.s_host, self.mean_host, self.log_std_host = pin(B, critic.S), pin(B, self.A), pin(B, self.A)
-        self.loss_host, self.dmean_host, self.dlog_std_host = pin(B), pin(B, self.A), pin(B, self.A)
-        self.s, self.mean, self.log_std = devt(B, critic.S), devt(B, self.A), devt(B, self.A)
-        self.q = devt(B, self.N)
+        # one flat pinned input buffer [s | mean | log_std] and one flat output buffer [loss | dmean | dlog_std],
+        # mirrored on the device: ONE H2D and ONE D2H copy per step (each small copy costs a few us of latency)
+        S, A = critic.S, self.A
+        n_in, n_out = B * (S + 2 * A), B * (1 + 2 * A)
+        self._in_host = torch.empty((n_in,), dtype=torch.float32).pin_memory()
+        self._out_host = torch.empty((n_out,), dtype=torch.float32).pin_memory()
+        self._in_dev = torch.empty((n_in,), dtype=torch.float32, device=dev)
+        self._out_dev = torch.empty((n_out,), dtype=torch.float32, device=dev)
+
+        def views(flat, shapes):
+            out, off = [], 0
+            for sh in shapes:
+                n = int(torch.Size(sh).numel())
+                out.append(flat[off:off + n].view(sh))
+                off += n
+            return out
+        self.s_host, self.mean_host, self.log_std_host = views(self._in_host, [(B, S), (B, A), (B, A)])
+        self.s, self.mean, self.log_std = views(self._in_dev, [(B, S), (B, A), (B, A)])
+        self.loss_host, self.dmean_host, self.dlog_std_host = views(self._out_host, [(B,), (B, A), (B, A)])
+        self._out_views = tuple(views(self._out_dev, [(B,), (B, A), (B, A)]))
+        self.q = torch.empty((B, self.N), dtype=torch.float32, device=dev)
         self._graph = None
         self._stream = torch.cuda.Stream(device=dev)
         if use_graph:
             self._capture()
 
     def _enqueue(self):
-        self.s.copy_(self.s_host, non_blocking=True)
-        self.mean.copy_(self.mean_host, non_blocking=True)
-        self.log_std.copy_(self.log_std_host, non_blocking=True)
+        self._in_dev.copy_(self._in_host, non_blocking=True)
         if self.repack:
             self.critic.invalidate()
         self.critic.eval_into(self.s, self.grid, self.q, self.prec)
-        loss_b, dm, ds, _ = self.eng.fkl_policy(self.q, self.w, self.grid, self.scale, self.mean, self.log_std,
-                                                self.alpha, b_total=self.b_total)
-        self.loss_host.copy_(loss_b, non_blocking=True)
-        self.dmean_host.copy_(dm, non_blocking=True)
-        self.dlog_std_host.copy_(ds, non_blocking=True)
+        self.eng.fkl_policy(self.q, self.w, self.grid, self.scale, self.mean, self.log_std, self.alpha,
+                            b_total=self.b_total, out=self._out_views)
+        self._out_host.copy_(self._out_dev, non_blocking=True)
 
     def _capture(self):
         # warm up outside the capture: workspace growth, operand pack and func attributes allocate/sync
