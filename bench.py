@@ -434,9 +434,10 @@ def run_b200(args, rank, local_rank, world):
             "metric": METRIC, "value": evals_total / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp16": "f16 operands, f32 accumulate (tcgen05 kind::f16)",
-                      "bf16": "bf16 operands, f32 accumulate (tcgen05 kind::f16)",
-                      "fp32": "f32"}[prec],
+            "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[prec],
+            "dtype_detail": {"fp16": "f16 operands, f32 accumulate in TMEM (tcgen05 kind::f16)",
+                             "bf16": "bf16 operands, f32 accumulate in TMEM (tcgen05 kind::f16)",
+                             "fp32": "f32 CUDA cores"}[prec],
             "data": "synthetic",
             "config": dict(W, global_states=B * world, precision=prec,
                            l2="rotating %d input/output sets (%.0f MB > 126 MB L2), no flush kernels in the timed region"

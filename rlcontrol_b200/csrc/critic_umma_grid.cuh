@@ -100,6 +100,9 @@ k_grid_parts(const float* __restrict__ theta, const float* __restrict__ s, const
              const float* __restrict__ smin, const float* __restrict__ smax, int B, int N, int S, int A,
              int H1, int H2, int H1P, int CH, int nch, int NT, unsigned short* __restrict__ PS,
              unsigned short* __restrict__ PA) {
+  // Programmatic dependent launch: let the main kernel start its prologue (weights -> smem, barriers,
+  // TMEM) while this pre-pass runs; its loader waits (griddepcontrol.wait) before touching PS/PA.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // grid: x = row (states first, then padded grid actions), y = feature block of 128; no 64-bit divisions
   const ThetaView t = theta_view(RLC_TIN, S, A, H1, H2);
   const float* W1 = theta + t.oW1;   // [S+A][H1]
@@ -281,6 +284,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_critic_umma_grid(const GridPa
   } else if (warp == 1) {
     // =================================== loader (one lane) ===================================
     if (lane == 0) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");      // PS/PA tables of the pre-pass are complete and visible
       bool ok = true;
       const int pitch_b = (CH + GR_PITCH_PAD) * 2;
       const uint32_t pa_tile_bytes = 32u * (uint32_t)pitch_b;
@@ -604,13 +608,17 @@ static int rlc_eval_umma_grid(rlc_handle* h, const rlc_critic* c, const PackGeom
   cfg.blockDim = dim3(GR_THREADS);
   cfg.dynamicSmemBytes = (size_t)gp.total;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // overlap our prologue with k_grid_parts
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  static int pdl = -1;
+  if (pdl < 0) { const char* e = getenv("RLC_UMMA_PDL"); pdl = (e && e[0] == '1') ? 1 : 0; }   // measured gain 0.2 %: opt-in
+  cfg.numAttrs = pdl ? 2 : 1;
   static int prof_on = -1;
   static long long* prof_dev = nullptr;
   if (prof_on < 0) { const char* e = getenv("RLC_UMMA_PROF"); prof_on = (e && e[0] == '1') ? 1 : 0; }

@@ -241,15 +241,16 @@ k_policy_reduce(const float* __restrict__ q, const float* __restrict__ v, const 
       qc[i] = n < N ? row[n] : 0.f;
     }
   }
+  const float inv_alpha = 1.f / alpha;   // q/alpha as a multiply: 1 ulp from the reference's division, far inside the tolerance
   float m = 0.f, z = 1.f;
   if (MODE == 0) {
     m = -CUDART_INF_F;
     if (cached) {
 #pragma unroll
       for (int i = 0; i < POL_NPT; ++i)
-        if (tid + POL_THREADS * i < N) m = fmaxf(m, __fdiv_rn(qc[i], alpha));
+        if (tid + POL_THREADS * i < N) m = fmaxf(m, qc[i] * inv_alpha);
     } else {
-      for (int n = tid; n < N; n += POL_THREADS) m = fmaxf(m, __fdiv_rn(row[n], alpha));
+      for (int n = tid; n < N; n += POL_THREADS) m = fmaxf(m, row[n] * inv_alpha);
     }
     m = block_max(m, red);
     z = 0.f;
@@ -258,15 +259,16 @@ k_policy_reduce(const float* __restrict__ q, const float* __restrict__ v, const 
       for (int i = 0; i < POL_NPT; ++i) {
         const int n = tid + POL_THREADS * i;
         if (n < N) {
-          qc[i] = expf(__fdiv_rn(qc[i], alpha) - m);        // reuse the register for e_n
+          qc[i] = expf(qc[i] * inv_alpha - m);        // reuse the register for e_n
           z = fmaf(qc[i], w[n], z);
         }
       }
     } else {
-      for (int n = tid; n < N; n += POL_THREADS) z = fmaf(expf(__fdiv_rn(row[n], alpha) - m), w[n], z);
+      for (int n = tid; n < N; n += POL_THREADS) z = fmaf(expf(row[n] * inv_alpha - m), w[n], z);
     }
     z = block_sum(z, red);
   }
+  const float inv_z = 1.f / z;
   const float vb = (MODE == 1) ? v[b] : 0.f;
   float acc = 0.f, gm[A], gl[A];
 #pragma unroll
@@ -282,7 +284,7 @@ k_policy_reduce(const float* __restrict__ q, const float* __restrict__ v, const 
     }
     float g;   // dL/dlogp_bn
     if (MODE == 0) {
-      const float pw = __fdiv_rn(qe, z) * w[n];            // Boltzmann weight x quadrature weight
+      const float pw = qe * inv_z * w[n];                   // Boltzmann weight x quadrature weight
       acc = fmaf(pw, lp, acc);
       g = -pw * inv_btotal;
     } else {
@@ -306,7 +308,7 @@ k_policy_reduce(const float* __restrict__ q, const float* __restrict__ v, const 
     }
   } else {
     for (int n = tid; n < N; n += POL_THREADS)
-      body(n, MODE == 0 ? expf(__fdiv_rn(row[n], alpha) - m) : row[n]);
+      body(n, MODE == 0 ? expf(row[n] * inv_alpha - m) : row[n]);
   }
   // the 2A+1 output sums in one pass: warp shuffles, one shared-memory exchange, fixed-order final sum
   __shared__ float fin[POL_THREADS / 32][2 * POL_MAX_A + 1];
