@@ -64,3 +64,24 @@ def test_product_does_not_import_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def test_invalid_arguments_return_status_not_crash():
+    """C-ABI error behaviour: bad shapes / null pointers come back as RLC_ERR_INVALID through
+    the int status, nothing throws across the ABI; the Python layer maps it to RlcError(RuntimeError)."""
+    import ctypes as C
+    from rlcontrol_b200 import _lib
+    lib = _lib.load()
+    # no handle, no device needed: argument validation happens first
+    cr = _lib.RlcCritic(0, 3, 1, 16, 16, None, None, None)
+    assert lib.rlc_critic_eval(None, C.byref(cr), None, 1, None, 1, 0, 0, None, None) == -1
+    assert lib.rlc_reduce_topk(None, None, 1, 4, 2, None, None, None, 0, 0, None, None) == -1
+    assert lib.rlc_reduce_fkl(None, None, None, None, 1, 1, 0.1, 1, None, None, None, None) == -1
+    assert lib.rlc_cem(None, C.byref(cr), None, 1, 1, 1, 1, 1, None, None, None, None, None, None, None, None, None, None, None) == -1
+    assert lib.rlc_adam_step(None, None, None, None, None, 4, 1, 1e-3, .9, .999, 1e-8, 0, None, 0.0, None) == -1
+    assert lib.rlc_umma_mode(C.byref(cr), 0) == -1          # theta == NULL -> not a valid critic
+    assert lib.rlc_destroy(None) == 0 and lib.rlc_launch_count(None) == 0
+    with pytest.raises(_lib.RlcError):
+        _lib.check(-1)
+    with pytest.raises(RuntimeError):
+        _lib.check(-5)
