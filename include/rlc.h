@@ -216,6 +216,58 @@ int rlc_adam_step_dev(rlc_handle* h, float* theta, const float* grad, float* m, 
 int rlc_soft_update(rlc_handle* h, float* target, const float* online, int64_t n, float tau,
                     void* stream);
 
+/* ---- B-row networks around the hot path (FKL / RKL update_network) -------------------------
+ * Generic MLP  x[B,in] -> relu(FC(in,H1)) -> relu(FC(H1,H2)) -> FC(H2,O)  on B rows:
+ * ValueNetwork (forwardkl_network.py:270-290, reversekl_network.py:290-312; O = 1) and
+ * PolicyNetwork.forward (forwardkl_network.py:293-322; O = 2A, columns [mean_linear | log_std_linear],
+ * the clamp of log_std is applied by the consumers below).
+ * theta: [ W1 (in x H1) | b1 | W2 (H1 x H2) | b2 | W3 (H2 x O) | b3 (O) ]  all [in,out]-major. */
+typedef struct rlc_mlp {
+  int32_t in, H1, H2, O;
+  const float* theta;
+} rlc_mlp;
+int64_t rlc_mlp_numel(int in, int H1, int H2, int O);
+int rlc_mlp_offsets(int in, int H1, int H2, int O, int64_t off[6]);
+/* floats of the caller-owned activation buffer `act` ([B,H1] | [B,H2] pre-activations) */
+int64_t rlc_mlp_act_numel(int H1, int H2, int B);
+/* out[B,O].  act: optional activation buffer to keep for rlc_mlp_grads (NULL = scratch). */
+int rlc_mlp_forward(rlc_handle* h, const rlc_mlp* m, const float* x, int B, float* out, float* act,
+                    void* stream);
+/* Gradient wrt theta given dout[B,O] = dLoss/dout (loss.backward() of the value / policy losses,
+ * forwardkl_network.py:199-209).  act from rlc_mlp_forward on the same x/theta, or NULL to
+ * recompute.  grad_out[numel]; dx_out[B,in] or NULL. */
+int rlc_mlp_grads(rlc_handle* h, const rlc_mlp* m, const float* x, const float* act,
+                  const float* dout, int B, float* grad_out, float* dx_out, void* stream);
+
+/* PolicyNetwork.evaluate (forwardkl_network.py:303-322, reversekl_network.py:325-344) on the policy
+ * head head[B,2A] = [mean_raw | log_std_raw]; eps[B,A] = the N(0,1) draws behind normal.sample()
+ * (NULL = zeros, i.e. the mean action).  A == 1: Normal(mean, std); A > 1: MultivariateNormal with
+ * covariance diag_embed(std), as the reference passes it (:346-351).
+ * Outputs (any may be NULL): action[B,A] = tanh(z) * action_scale, logp[B], mean_out[B,A] =
+ * tanh(mean) * action_scale, mu_raw_out[B,A] (forward()'s mean, contiguous), log_std_out[B,A]
+ * (clamped), z_out[B,A]. */
+int rlc_policy_evaluate(rlc_handle* h, const float* head, const float* eps, int B, int A,
+                        float action_scale, float log_std_min, float log_std_max, float* action_out,
+                        float* logp_out, float* mean_out, float* mu_raw_out, float* log_std_out,
+                        float* z_out, void* stream);
+/* Regression targets (forwardkl_network.py:137-150): y_q = r + gamma V_targ(s');
+ * target_v = Q(s,a_new) - alpha logp ('sac', sac=1) or (r - alpha logp) + gamma V_targ(s') ('non_sac');
+ * dv[B] = 2 (v - target_v) / B_total; v_loss[1] = mean (v - target_v)^2 (this rank's share).
+ * dv_out/v_loss_out may be NULL (then q_new/logp/v are unused). */
+int rlc_kl_targets(rlc_handle* h, const float* r, const float* gamma, const float* v_next,
+                   const float* q_new, const float* logp, const float* v, int B, int B_total,
+                   float entropy_scale, int sac, float* y_q_out, float* dv_out, float* v_loss_out,
+                   void* stream);
+/* Gradient wrt the raw policy head.  mode 0: chain dmean/dlog_std[B,A] (from
+ * rlc_reduce_{fkl,rkl}_policy) through the log_std clamp.  mode 1 ('ll', reversekl_network.py:161-165)
+ * and mode 2 ('hard_ll', :167-169): likelihood-ratio losses on the detached sample z[B,A] with
+ * logp[B], q_new[B] = Q(s, a_new), v[B]; loss_out[1] receives the policy loss. */
+int rlc_policy_head_grad(rlc_handle* h, const float* head, int B, int A, float log_std_min,
+                         float log_std_max, int mode, const float* dmean, const float* dlog_std,
+                         const float* z, const float* logp, const float* q_new, const float* v,
+                         float entropy_scale, int B_total, float* dhead_out, float* loss_out,
+                         void* stream);
+
 /* ---- replay minibatch gather (row a17) ---------------------------------------------------
  * map(np.array, zip(*batch)) of ReplayBuffer.sample_batch (utils/replaybuffer.py:32-37) over a
  * device-resident struct-of-arrays ring: state[cap,S], action[cap,A], reward[cap],

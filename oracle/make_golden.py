@@ -220,6 +220,108 @@ def gen_update(torch, mod, cls_name, name, alpha, seed=0):
     print(name, "pi_loss", losses["pi_loss"], "q_loss", losses["q_loss"], "N", N)
 
 
+def _net_params(net):
+    """(q, v, target_v, pi) parameter lists in torch layout, copied."""
+    cp = lambda ps: [p.detach().numpy().copy() for p in ps]
+    pi = net.pi_net
+    return dict(
+        q=q_params(net.q_net),
+        v=cp([net.v_net.linear1.weight, net.v_net.linear1.bias, net.v_net.linear2.weight,
+              net.v_net.linear2.bias, net.v_net.linear3.weight, net.v_net.linear3.bias]),
+        tv=cp([net.target_v_net.linear1.weight, net.target_v_net.linear1.bias, net.target_v_net.linear2.weight,
+               net.target_v_net.linear2.bias, net.target_v_net.linear3.weight, net.target_v_net.linear3.bias]),
+        pi=cp([pi.linear1.weight, pi.linear1.bias, pi.linear2.weight, pi.linear2.bias, pi.mean_linear.weight,
+               pi.mean_linear.bias, pi.log_std_linear.weight, pi.log_std_linear.bias]))
+
+
+def gen_full_update(torch, mod, cls_name, name, alpha, optim_type="intg", q_update_type="non_sac", seed=0,
+                    n_updates=2, l1=64, l2=48):
+    """n_updates consecutive reference ``update_network`` + ``update_target_network`` calls
+    (forwardkl_network.py:123-215 / reversekl_network.py:130-224) on Pendulum-shaped batches, ALL three
+    networks recorded before and after every update, and the N(0,1) draws behind ``normal.sample()``
+    recorded as ``eps`` (torch.randn under the same seed; asserted to reproduce the reference's z)."""
+    S, A, B = 3, 1, 32
+    cfg = make_config(S, A, 2.0, B, 64, l1, l2, alpha, state_max=[1.0, 1.0, 8.0])
+    cfg.optim_type, cfg.q_update_type = optim_type, q_update_type
+    cfg.pi_lr, cfg.qf_vf_lr = 1e-3, 2e-3
+    torch.manual_seed(seed)
+    net = getattr(mod, cls_name)(None, None, cfg)
+    with torch.no_grad():                      # O(1) Q, V and policy heads so every term of the update matters
+        net.q_net.linear3.weight.mul_(100.0); net.q_net.linear3.bias.mul_(100.0)
+        net.v_net.linear3.weight.mul_(100.0); net.v_net.linear3.bias.mul_(100.0)
+        net.target_v_net.linear3.weight.mul_(80.0); net.target_v_net.linear3.bias.mul_(80.0)
+        net.pi_net.mean_linear.weight.mul_(60.0); net.pi_net.log_std_linear.weight.mul_(40.0)
+        net.pi_net.log_std_linear.bias.sub_(0.7)
+    rng = np.random.RandomState(seed + 11)
+    save = dict(alpha=np.float64(alpha), pi_lr=np.float64(cfg.pi_lr), qf_vf_lr=np.float64(cfg.qf_vf_lr),
+                tau=np.float64(cfg.tau), optim_type=np.array(optim_type), q_update_type=np.array(q_update_type),
+                action_max=np.float64(2.0), n_param=np.int64(64), l1=np.int64(l1), l2=np.int64(l2),
+                grid_a=net.intgrl_actions.numpy(), grid_w=net.intgrl_weights.numpy())
+    for k, ps in _net_params(net).items():
+        for i, p_ in enumerate(ps):
+            save["pre_%s_%d" % (k, i)] = p_
+    orig_eval = net.pi_net.evaluate
+    zs = []
+
+    def eval_hook(state, epsilon=1e-6):
+        out = orig_eval(state, epsilon)
+        zs.append((out[2].detach().numpy().copy(), out[1].detach().numpy().copy()))
+        return out
+
+    net.pi_net.evaluate = eval_hook
+    orig_backward = torch.Tensor.backward
+    order = []
+
+    def backward_hook(self, *a_, **k_):
+        order.append(float(self.detach()))
+        return orig_backward(self, *a_, **k_)
+
+    batches = {k: [] for k in ("s", "a", "s2", "r", "g", "eps", "z", "logp_sample")}
+    losses = []
+    for u in range(n_updates):
+        s = rng.uniform(-1, 1, size=(B, S)) * np.array([1, 1, 8.0])
+        a = rng.uniform(-2, 2, size=(B, A))
+        s2 = rng.uniform(-1, 1, size=(B, S)) * np.array([1, 1, 8.0])
+        r = -rng.uniform(0, 16, size=(B,))
+        g = np.where(rng.uniform(size=B) < 0.1, 0.0, 0.99)
+        torch.manual_seed(seed + 100 + u)
+        eps = torch.randn(B, A).numpy().copy()
+        with torch.no_grad():
+            mean0, log_std0 = net.pi_net.forward(torch.from_numpy(s.astype(np.float32)))
+        torch.manual_seed(seed + 100 + u)
+        zs.clear(); order.clear()
+        torch.Tensor.backward = backward_hook
+        try:
+            net.update_network(s, a, s2, r, g)
+        finally:
+            torch.Tensor.backward = orig_backward
+        net.update_target_network()
+        z_ref = zs[0][0]
+        z_mine = mean0.numpy() + np.exp(log_std0.numpy()) * eps
+        assert np.allclose(z_ref, z_mine, rtol=0, atol=1e-6), "normal.sample() is not mean + std * randn"
+        losses.append(order[:3])
+        for k, v_ in zip(("s", "a", "s2", "r", "g", "eps", "z", "logp_sample"),
+                         (s, a, s2, r, g, eps, z_ref, zs[0][1].reshape(B))):
+            batches[k].append(v_)
+        for k, ps in _net_params(net).items():
+            for i, p_ in enumerate(ps):
+                save["post%d_%s_%d" % (u, k, i)] = p_
+    net.pi_net.evaluate = orig_eval
+    for k, v_ in batches.items():
+        save[k] = np.asarray(v_)
+    save["losses"] = np.asarray(losses, np.float64)          # [n_updates, (q_loss, v_loss, pi_loss)]
+    # sample_action / predict_action on the final networks (forwardkl_network.py:109-121)
+    st = rng.uniform(-1, 1, size=(5, S)) * np.array([1, 1, 8.0])
+    torch.manual_seed(seed + 500)
+    eps_act = torch.randn(5, A).numpy().copy()
+    torch.manual_seed(seed + 500)
+    save["act_states"], save["act_eps"] = st, eps_act
+    save["act_sample"] = net.sample_action(st)
+    save["act_predict"] = net.predict_action(st)
+    np.savez_compressed(os.path.join(OUT, name), **save)
+    print(name, "losses", np.asarray(losses))
+
+
 def gen_trueq():
     variants = {
         "eq_var1": ((-0.6, 0.6), (0.2, 0.2), (1.0, 1.0)),      # environments.py:573-587
@@ -345,6 +447,31 @@ def gen_policy_logp(torch, fkl_mod, rkl_mod):
     print("policy_logp", {k: v.shape for k, v in save.items() if k.endswith("logp")})
 
 
+def gen_smolyak(forwardkl_network):
+    """The action_dim > 1 integration grid as the reference's constructor builds it
+    (forwardkl_network.py:73-102).  (Its update_network cannot run for A > 1 under torch 2.x: the grid is
+    float64 and torch.cat/Linear refuse the mixed dtypes -- so only the grid is pinned.)"""
+    save = {}
+    for A, l in ((2, 6), (3, 4)):
+        cfg = make_config(3, A, 1.5, 8, 64, 32, 32, 0.1)
+        cfg.l_param = l
+        net = forwardkl_network.ForwardKLNetwork(None, None, cfg)
+        save["a_%d_%d" % (A, l)] = net.intgrl_actions.numpy()
+        save["w_%d_%d" % (A, l)] = net.intgrl_weights.numpy()
+    np.savez_compressed(os.path.join(OUT, "smolyak.npz"), **save)
+
+
+def gen_full_updates(torch, forwardkl_network, reversekl_network):
+    gen_smolyak(forwardkl_network)
+    F, R = (forwardkl_network, "ForwardKLNetwork"), (reversekl_network, "ReverseKLNetwork")
+    gen_full_update(torch, *F, "full_fkl_intg_nonsac.npz", alpha=0.1)
+    gen_full_update(torch, *F, "full_fkl_intg_sac.npz", alpha=0.5, q_update_type="sac", seed=3)
+    gen_full_update(torch, *R, "full_rkl_intg_nonsac.npz", alpha=0.1, seed=4)
+    gen_full_update(torch, *R, "full_rkl_hardintg_sac.npz", alpha=0.2, optim_type="hard_intg", q_update_type="sac", seed=5)
+    gen_full_update(torch, *R, "full_rkl_ll_nonsac.npz", alpha=0.1, optim_type="ll", seed=6)
+    gen_full_update(torch, *R, "full_rkl_hardll_sac.npz", alpha=0.1, optim_type="hard_ll", q_update_type="sac", seed=7)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     install_stubs()
@@ -362,6 +489,7 @@ def main():
     gen_update(torch, forwardkl_network, "ForwardKLNetwork", "fkl_update.npz", alpha=0.1)
     gen_update(torch, reversekl_network, "ReverseKLNetwork", "rkl_update.npz", alpha=0.1)
     gen_policy_logp(torch, forwardkl_network, reversekl_network)
+    gen_full_updates(torch, forwardkl_network, reversekl_network)
     gen_trueq()
     gen_gmm()
     x, w = onp.clenshaw_curtis(64)
@@ -369,4 +497,13 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "full_updates":      # only the full-update fixtures
+        os.makedirs(OUT, exist_ok=True)
+        install_stubs()
+        sys.path.insert(0, REF)
+        import torch
+        torch.set_num_threads(1)
+        from agents.network import forwardkl_network, reversekl_network
+        gen_full_updates(torch, forwardkl_network, reversekl_network)
+    else:
+        main()

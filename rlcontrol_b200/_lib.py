@@ -23,12 +23,18 @@ class RlcCritic(C.Structure):
                 ("smax", C.c_void_p)]
 
 
+class RlcMlp(C.Structure):
+    _fields_ = [("inp", C.c_int32), ("H1", C.c_int32), ("H2", C.c_int32), ("O", C.c_int32),
+                ("theta", C.c_void_p)]
+
+
 class RlcError(RuntimeError):
     """Non-zero status from the C-ABI (map C status -> RuntimeError)."""
 
 
 _p, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
 _cr = C.POINTER(RlcCritic)
+_ml = C.POINTER(RlcMlp)
 
 # name -> (restype, argtypes); must list every symbol include/rlc.h declares
 SIGNATURES = {
@@ -61,6 +67,14 @@ SIGNATURES = {
     "rlc_adam_step": (_i, [_p, _p, _p, _p, _p, _i64, _i, _f, _f, _f, _f, _i, _p, _f, _p]),
     "rlc_adam_step_dev": (_i, [_p, _p, _p, _p, _p, _i64, _p, _f, _f, _f, _f, _i, _p, _f, _p]),
     "rlc_soft_update": (_i, [_p, _p, _p, _i64, _f, _p]),
+    "rlc_mlp_numel": (_i64, [_i, _i, _i, _i]),
+    "rlc_mlp_offsets": (_i, [_i, _i, _i, _i, C.POINTER(_i64)]),
+    "rlc_mlp_act_numel": (_i64, [_i, _i, _i]),
+    "rlc_mlp_forward": (_i, [_p, _ml, _p, _i, _p, _p, _p]),
+    "rlc_mlp_grads": (_i, [_p, _ml, _p, _p, _p, _i, _p, _p, _p]),
+    "rlc_policy_evaluate": (_i, [_p, _p, _p, _i, _i, _f, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
+    "rlc_kl_targets": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _i, _p, _p, _p, _p]),
+    "rlc_policy_head_grad": (_i, [_p, _p, _i, _i, _f, _f, _i, _p, _p, _p, _p, _p, _p, _f, _i, _p, _p, _p]),
     "rlc_replay_gather": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p]),
     "rlc_replay_scatter": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p]),
 }

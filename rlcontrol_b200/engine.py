@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_PER_STATE, ACT_SHARED, ADAM_TF, ADAM_TORCH, LAYOUT_IN_OUT, LAYOUT_OUT_IN,
-                   PREC_AUTO, PREC_BY_NAME, PREC_FP32, TIN, TMID, RlcCritic, check)
+                   PREC_AUTO, PREC_BY_NAME, PREC_FP32, TIN, TMID, RlcCritic, RlcMlp, check)
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -87,6 +87,12 @@ class Engine:
         check(self.lib.rlc_reduce_stats(self.h, _ptr(q), B, N, _ptr(am), _ptr(mx), _ptr(mean), _stream()))
         return am, mx, mean
 
+    def mean_into(self, x: torch.Tensor, out: torch.Tensor):
+        """out[0] = mean(x) over a flat fp32 vector (the ``.mean(-1)`` over states of the policy losses,
+        forwardkl_network.py:194) -- rlc_reduce_stats on a single row."""
+        check(self.lib.rlc_reduce_stats(self.h, _ptr(x), 1, int(x.numel()), None, None, _ptr(out), _stream()))
+        return out
+
     def soft_value(self, q: torch.Tensor, action_dim: int):
         """SQL ``logsumexp - log N + A log 2`` (sql_network.py:76-84)."""
         B, N = q.shape
@@ -140,19 +146,68 @@ class Engine:
 
     def rkl_policy(self, q, v, w, grid, action_scale: float, mean, log_std, entropy_scale: float,
                    hard: bool = False, b_total: Optional[int] = None, want_grad: bool = True,
-                   want_logp: bool = False):
+                   want_logp: bool = False, out=None):
         """ReverseKL counterpart (reversekl_network.py:181-203 + :346-374)."""
         B, N = q.shape
         A = grid.shape[-1]
-        loss_b = torch.empty((B,), dtype=torch.float32, device=q.device)
-        dm = torch.empty((B, A), dtype=torch.float32, device=q.device) if want_grad else None
-        ds = torch.empty((B, A), dtype=torch.float32, device=q.device) if want_grad else None
+        if out is not None:
+            loss_b, dm, ds = out
+        else:
+            loss_b = torch.empty((B,), dtype=torch.float32, device=q.device)
+            dm = torch.empty((B, A), dtype=torch.float32, device=q.device) if want_grad else None
+            ds = torch.empty((B, A), dtype=torch.float32, device=q.device) if want_grad else None
         lp = torch.empty_like(q) if want_logp else None
         check(self.lib.rlc_reduce_rkl_policy(self.h, _ptr(q), _ptr(v), _ptr(w), _ptr(grid), A,
                                              float(action_scale), _ptr(mean), _ptr(log_std), B, N,
                                              float(entropy_scale), int(bool(hard)), int(b_total or B),
                                              _ptr(loss_b), _ptr(dm), _ptr(ds), _ptr(lp), _stream()))
         return loss_b, dm, ds, lp
+
+    # ------------------------------------------------------------------ FKL / RKL B-row pieces
+    def policy_evaluate(self, head, eps, action_scale: float, log_std_min: float = -20.0,
+                        log_std_max: float = 2.0, out=None):
+        """``PolicyNetwork.evaluate`` (forwardkl_network.py:303-322) on the raw head [B,2A] with the
+        normal draws ``eps`` [B,A] (None = mean action).  Returns dict(action, logp, mean, mu_raw,
+        log_std, z); ``out`` may carry preallocated tensors under the same keys."""
+        B, A2 = head.shape
+        A = A2 // 2
+        o = dict(out or {})
+        for k, sh in (("action", (B, A)), ("logp", (B,)), ("mean", (B, A)), ("mu_raw", (B, A)),
+                      ("log_std", (B, A)), ("z", (B, A))):
+            if k not in o:
+                o[k] = torch.empty(sh, dtype=torch.float32, device=head.device)
+        check(self.lib.rlc_policy_evaluate(self.h, _ptr(head), _ptr(eps), B, A, float(action_scale),
+                                           float(log_std_min), float(log_std_max), _ptr(o["action"]),
+                                           _ptr(o["logp"]), _ptr(o["mean"]), _ptr(o["mu_raw"]),
+                                           _ptr(o["log_std"]), _ptr(o["z"]), _stream()))
+        return o
+
+    def kl_targets(self, r, gamma, v_next, q_new, logp, v, entropy_scale: float, sac: bool,
+                   b_total: Optional[int] = None, out=None):
+        """TD / soft-value targets (forwardkl_network.py:137-150). Returns (y_q [B], dv [B], v_loss [1])."""
+        B = r.shape[0]
+        if out is not None:
+            y, dv, vl = out
+        else:
+            y = torch.empty((B,), dtype=torch.float32, device=r.device)
+            dv = torch.empty((B,), dtype=torch.float32, device=r.device)
+            vl = torch.empty((1,), dtype=torch.float32, device=r.device)
+        check(self.lib.rlc_kl_targets(self.h, _ptr(r), _ptr(gamma), _ptr(v_next), _ptr(q_new), _ptr(logp),
+                                      _ptr(v), B, int(b_total or B), float(entropy_scale), int(bool(sac)),
+                                      _ptr(y), _ptr(dv), _ptr(vl), _stream()))
+        return y, dv, vl
+
+    def policy_head_grad(self, head, mode: int, dmean=None, dlog_std=None, z=None, logp=None, q_new=None,
+                         v=None, entropy_scale: float = 0.0, b_total: Optional[int] = None,
+                         log_std_min: float = -20.0, log_std_max: float = 2.0, out=None, loss_out=None):
+        """Gradient wrt the raw policy head [B,2A] (include/rlc.h rlc_policy_head_grad)."""
+        B, A2 = head.shape
+        dhead = out if out is not None else torch.empty_like(head)
+        check(self.lib.rlc_policy_head_grad(self.h, _ptr(head), B, A2 // 2, float(log_std_min),
+                                            float(log_std_max), int(mode), _ptr(dmean), _ptr(dlog_std),
+                                            _ptr(z), _ptr(logp), _ptr(q_new), _ptr(v), float(entropy_scale),
+                                            int(b_total or B), _ptr(dhead), _ptr(loss_out), _stream()))
+        return dhead
 
     def gmm_refit(self, X: torch.Tensor, num_modal: int, resp0: Optional[torch.Tensor] = None,
                   tol: float = 1e-2, max_iter: int = 100):
@@ -342,6 +397,14 @@ class Critic:
                                             int(b_total or B), _ptr(grad), _ptr(loss), _ptr(q), _stream()))
         return grad, loss, q
 
+    def grads_into(self, s, a, y, grad_out, loss_out, q_out=None, b_total: Optional[int] = None):
+        """Allocation-free :meth:`grads` (device fp32 tensors in, preallocated outputs)."""
+        B = s.shape[0]
+        check(self.eng.lib.rlc_critic_grads(self.eng.h, C.byref(self._desc), _ptr(s), _ptr(a), _ptr(y), B,
+                                            int(b_total or B), _ptr(grad_out), _ptr(loss_out), _ptr(q_out),
+                                            _stream()))
+        return grad_out
+
     # ------------------------------------------------------------------ CEM (K4)
     def cem(self, s, u0, noise, comp_u, top_m: int, num_modal: int, a_min, a_max,
             want_idx: bool = False):
@@ -365,6 +428,74 @@ class Critic:
                                    _ptr(amax), _ptr(w), _ptr(mu), _ptr(var), _ptr(best), _ptr(idx),
                                    _stream()))
         return w, mu, var, best, idx
+
+
+class Mlp:
+    """Generic B-row MLP ``x -> relu(FC) -> relu(FC) -> FC(O)`` on the device (include/rlc.h rlc_mlp):
+    the reference's ``ValueNetwork`` (O=1) and ``PolicyNetwork.forward`` (O=2A, [mean | log_std])."""
+
+    def __init__(self, engine: Engine, inp: int, H1: int, H2: int, O: int):
+        self.eng = engine
+        self.inp, self.H1, self.H2, self.O = int(inp), int(H1), int(H2), int(O)
+        n = engine.lib.rlc_mlp_numel(self.inp, self.H1, self.H2, self.O)
+        if n <= 0:
+            raise ValueError("invalid MLP dimensions")
+        self.theta = torch.zeros((n,), dtype=torch.float32, device=engine.device)
+        off = (C.c_int64 * 6)()
+        check(engine.lib.rlc_mlp_offsets(self.inp, self.H1, self.H2, self.O, off))
+        self.offsets = list(off)
+        self._desc = RlcMlp()
+        d = self._desc
+        d.inp, d.H1, d.H2, d.O, d.theta = self.inp, self.H1, self.H2, self.O, self.theta.data_ptr()
+
+    def _views(self):
+        o, t = self.offsets, self.theta
+        return (t[o[0]:o[1]].view(self.inp, self.H1), t[o[1]:o[2]], t[o[2]:o[3]].view(self.H1, self.H2),
+                t[o[3]:o[4]], t[o[4]:o[5]].view(self.H2, self.O), t[o[5]:])
+
+    def load_torch(self, W1, b1, W2, b2, W3, b3):
+        """torch ``nn.Linear`` tensors (weight [out,in]); several output heads are passed as lists and
+        laid side by side in the O columns (``[mean_linear, log_std_linear]``)."""
+        dev = self.eng.device
+        cat = lambda x, dim: torch.cat([_f32(t, dev) for t in x], dim) if isinstance(x, (list, tuple)) else _f32(x, dev)
+        W3, b3 = cat(W3, 0), cat(b3, 0)
+        v = self._views()
+        v[0].copy_(_f32(W1, dev).t()); v[1].copy_(_f32(b1, dev).reshape(-1))
+        v[2].copy_(_f32(W2, dev).t()); v[3].copy_(_f32(b2, dev).reshape(-1))
+        v[4].copy_(W3.reshape(self.O, self.H2).t()); v[5].copy_(b3.reshape(-1))
+        return self
+
+    def export_torch(self):
+        """[W1 [H1,in], b1, W2 [H2,H1], b2, W3 [O,H2], b3 [O]] in torch layout (device tensors)."""
+        v = self._views()
+        return [v[0].t().contiguous(), v[1].clone(), v[2].t().contiguous(), v[3].clone(),
+                v[4].t().contiguous(), v[5].clone()]
+
+    def copy_from(self, other: "Mlp"):
+        self.theta.copy_(other.theta)
+
+    def act_buffer(self, B: int) -> torch.Tensor:
+        n = self.eng.lib.rlc_mlp_act_numel(self.H1, self.H2, int(B))
+        return torch.empty((max(int(n), 1),), dtype=torch.float32, device=self.eng.device)
+
+    def forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None, act: Optional[torch.Tensor] = None):
+        B = x.shape[0]
+        if x.dim() != 2 or x.shape[1] != self.inp:
+            raise ValueError(f"input must be [B,{self.inp}], got {tuple(x.shape)}")
+        if out is None:
+            out = torch.empty((B, self.O), dtype=torch.float32, device=x.device)
+        check(self.eng.lib.rlc_mlp_forward(self.eng.h, C.byref(self._desc), _ptr(x), B, _ptr(out), _ptr(act),
+                                           _stream()))
+        return out
+
+    def grads(self, x: torch.Tensor, dout: torch.Tensor, act: Optional[torch.Tensor] = None,
+              grad_out: Optional[torch.Tensor] = None, want_dx: bool = False):
+        B = x.shape[0]
+        g = grad_out if grad_out is not None else torch.empty_like(self.theta)
+        dx = torch.empty_like(x) if want_dx else None
+        check(self.eng.lib.rlc_mlp_grads(self.eng.h, C.byref(self._desc), _ptr(x), _ptr(act), _ptr(dout), B,
+                                         _ptr(g), _ptr(dx), _stream()))
+        return (g, dx) if want_dx else g
 
 
 class CriticOptimizer:

@@ -1,0 +1,319 @@
+"""Drop-in ``ForwardKLNetwork`` / ``ReverseKLNetwork`` (agents/network/forwardkl_network.py:17-235,
+reversekl_network.py:17-245): same constructor ``(sess, input_norm, config)``, same config keys and the
+same methods the managers call (``agents/ForwardKL.py``, ``agents/ReverseKL.py:31-90``):
+``update_network(s, a, s', r, gamma)``, ``update_target_network()``, ``sample_action(s)``,
+``predict_action(s)``, ``getQFunction(state)``, ``getPolicyFunction(state)``; numpy in, numpy out.
+
+One ``update_network`` is ONE CUDA-graph launch: the minibatch goes up in one pinned copy, then (in the
+reference's order -- every forward pass sees the pre-update parameters, :131-194)
+
+    V(s), V_targ(s'), policy head(s)                      rlc_mlp_forward        (B rows)
+    PolicyNetwork.evaluate with the step's N(0,1) draws   rlc_policy_evaluate
+    Q(s, a_new)                                           rlc_critic_eval        (B rows)
+    y_q, dV                                               rlc_kl_targets
+    Q on the B x N integration grid                       rlc_critic_eval        <- the hot path
+    FKL / RKL reduction with get_logprob fused            rlc_reduce_{fkl,rkl}_policy
+    dLoss/d(policy head)                                  rlc_policy_head_grad
+    three backward passes + three Adam steps              rlc_critic_grads / rlc_mlp_grads / rlc_adam_step_dev
+
+and the three losses come back in one pinned copy.  Nothing runs on the CPU except drawing the normal
+noise from torch's global CPU generator -- the stream ``normal.sample()`` consumes in the reference, so
+``torch.manual_seed`` reproduces the reference's trajectory (pass ``eps=`` to supply the draws).
+Initial weights are drawn exactly as the reference's constructors draw them (same modules, same order)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ._lib import ADAM_TORCH, LAYOUT_OUT_IN, TIN
+from .engine import Critic, Engine, Mlp, _f32
+from .quadrature import integration_grid
+
+LOG_STD_MIN, LOG_STD_MAX = -20.0, 2.0          # PolicyNetwork defaults, forwardkl_network.py:294
+
+
+def _flag(x):
+    return x is True or x == "True"
+
+
+def _linear_init(n_in, n_out, init_w=None):
+    """The tensors ``nn.Linear(n_in, n_out)`` would hold, drawn from torch's global generator in the
+    order the reference's constructors draw them (weight, bias; then the optional ``uniform_`` re-draws,
+    forwardkl_network.py:258-259,302-308)."""
+    lin = torch.nn.Linear(n_in, n_out)
+    if init_w is not None:
+        lin.weight.data.uniform_(-init_w, init_w)
+        lin.bias.data.uniform_(-init_w, init_w)
+    return lin.weight.detach().clone(), lin.bias.detach().clone()
+
+
+class _Adam:
+    """torch.optim.Adam state of one flat parameter vector, step count on the device (graph-safe)."""
+
+    def __init__(self, eng: Engine, theta: torch.Tensor, lr: float):
+        self.eng, self.theta, self.lr = eng, theta, float(lr)
+        self.m, self.v = torch.zeros_like(theta), torch.zeros_like(theta)
+        self.state_dev = torch.zeros((4,), dtype=torch.int32, device=theta.device)
+        self.grad = torch.zeros_like(theta)
+
+    def step(self):
+        self.eng.adam_step_dev(self.theta, self.grad, self.m, self.v, self.state_dev, self.lr, ADAM_TORCH)
+
+
+class _QNet:
+    """``self.q_net`` of the reference object: callable on stacked rows -> [R,1] (numpy or tensors in,
+    device tensor out)."""
+
+    def __init__(self, critic: Critic):
+        self.critic = critic
+
+    def __call__(self, state, action):
+        dev = self.critic.eng.device
+        s, a = _f32(state, dev), _f32(action, dev)
+        return self.critic.eval(s, a[:, None, :], "fp32").reshape(-1, 1)
+
+    forward = __call__
+
+    def eval_grid(self, state_batch, grid_actions, precision="auto"):
+        return self.critic.eval(state_batch, grid_actions, precision)
+
+
+class _KLNetwork(object):
+    KIND = None                                   # "fkl" | "rkl"
+    OPTIM_TYPES = ()
+
+    def __init__(self, sess, input_norm, config):
+        self.sess, self.input_norm, self.config = sess, input_norm, config
+        self.state_dim, self.action_dim = int(config.state_dim), int(config.action_dim)
+        self.state_min, self.state_max = config.state_min, config.state_max
+        self.action_min, self.action_max = config.action_min, config.action_max
+        self.learning_rate = [float(config.pi_lr), float(config.qf_vf_lr)]
+        self.tau, self.norm_type = float(config.tau), getattr(config, "norm_type", "none")
+        self.optim_type = config.optim_type
+        self.q_update_type = config.q_update_type
+        self.use_true_q = _flag(getattr(config, "use_true_q", "False"))
+        self.rng = np.random.RandomState(config.random_seed)
+        self.entropy_scale = float(config.entropy_scale)
+        if self.q_update_type not in ("sac", "non_sac"):
+            raise ValueError("invalid config.q_update_type")
+        if self.optim_type not in self.OPTIM_TYPES:
+            # forwardkl_network.py:152-153 raises for 'll'; reversekl 'reparam' leaves policy_loss undefined (:171-173)
+            raise NotImplementedError("optim_type %r" % (self.optim_type,))
+        S, A = self.state_dim, self.action_dim
+        self.action_scale = float(np.asarray(self.action_max, np.float64).reshape(-1)[0])
+        a1, a2 = int(config.actor_l1_dim), int(config.actor_l2_dim)
+        c1, c2 = int(config.critic_l1_dim), int(config.critic_l2_dim)
+        eng = getattr(config, "engine", None)
+        self.eng = eng if eng is not None else Engine()
+        self.precision = getattr(config, "precision", "auto")
+        dev = self.eng.device
+        # ---- parameters, drawn in the reference's order: pi_net, q_net, v_net, target_v_net (:41-45)
+        pW1, pb1 = _linear_init(S, a1)
+        pW2, pb2 = _linear_init(a1, a2)
+        mW, mb = _linear_init(a2, A, 3e-3)
+        sW, sb = _linear_init(a2, A, 3e-3)
+        qW1, qb1 = _linear_init(S + A, c1)
+        qW2, qb2 = _linear_init(c1, c2)
+        qW3, qb3 = _linear_init(c2, 1, 3e-3)
+        vW1, vb1 = _linear_init(S, c1)
+        vW2, vb2 = _linear_init(c1, c2)
+        vW3, vb3 = _linear_init(c2, 1, 3e-3)
+        for n_in, n_out, iw in ((S, c1, None), (c1, c2, None), (c2, 1, 3e-3)):     # target_v_net's own draws, then
+            _linear_init(n_in, n_out, iw)                                          # overwritten by the copy (:47-49)
+        self.pi = Mlp(self.eng, S, a1, a2, 2 * A).load_torch(pW1, pb1, pW2, pb2, [mW, sW], [mb, sb])
+        self.critic = Critic(self.eng, TIN, S, A, c1, c2).load(qW1, qb1, qW2, qb2, qW3, qb3, LAYOUT_OUT_IN)
+        self.v = Mlp(self.eng, S, c1, c2, 1).load_torch(vW1, vb1, vW2, vb2, vW3, vb3)
+        self.target_v = Mlp(self.eng, S, c1, c2, 1)
+        self.target_v.copy_from(self.v)
+        self.q_net = _QNet(self.critic)
+        self.pi_opt = _Adam(self.eng, self.pi.theta, self.learning_rate[0])
+        self.q_opt = _Adam(self.eng, self.critic.theta, self.learning_rate[1])
+        self.v_opt = _Adam(self.eng, self.v.theta, self.learning_rate[1])
+        # ---- integration grid (:58-102)
+        acts, w = integration_grid(A, self.action_scale, getattr(config, "N_param", 64), getattr(config, "l_param", 6))
+        self.intgrl_actions, self.intgrl_weights = _f32(acts, dev), _f32(w, dev)
+        self.intgrl_actions_len = int(acts.shape[0])
+        self.device = dev
+        self._steps = {}                      # batch size -> captured update
+        self._act = {}                        # batch size -> action-selection buffers
+        self.use_graph = bool(getattr(config, "use_cuda_graph", True))
+
+    # ------------------------------------------------------------------ parameter access (tests, checkpoints)
+    def load_reference_parameters(self, q, v, target_v, pi):
+        """Lists in torch layout: q/v/target_v = [W1,b1,W2,b2,W3,b3]; pi = [W1,b1,W2,b2,Wm,bm,Ws,bs]."""
+        self.critic.load(*q, LAYOUT_OUT_IN)
+        self.v.load_torch(*v)
+        self.target_v.load_torch(*target_v)
+        self.pi.load_torch(pi[0], pi[1], pi[2], pi[3], [pi[4], pi[6]], [pi[5], pi[7]])
+        torch.cuda.synchronize(self.device)
+
+    def export_parameters(self):
+        """dict(q, v, tv, pi) of numpy lists in the same torch layouts."""
+        A = self.action_dim
+        n = lambda ts: [t.detach().cpu().numpy() for t in ts]
+        p = self.pi.export_torch()
+        pi = [p[0], p[1], p[2], p[3], p[4][:A], p[5][:A], p[4][A:], p[5][A:]]
+        return dict(q=n(self.critic.export(LAYOUT_OUT_IN)), v=n(self.v.export_torch()),
+                    tv=n(self.target_v.export_torch()), pi=n(pi))
+
+    # ------------------------------------------------------------------ the update
+    def _build_step(self, B):
+        dev, S, A, N = self.device, self.state_dim, self.action_dim, self.intgrl_actions_len
+        st = type("Step", (), {})()
+        n_in = B * (2 * S + 2 * A + 2)
+        st.in_host = torch.zeros((n_in,), dtype=torch.float32).pin_memory()
+        st.in_dev = torch.zeros((n_in,), dtype=torch.float32, device=dev)
+
+        def views(flat):
+            out, off = {}, 0
+            for k, sh in (("s", (B, S)), ("a", (B, A)), ("s2", (B, S)), ("r", (B,)), ("g", (B,)), ("eps", (B, A))):
+                n = int(np.prod(sh))
+                out[k] = flat[off:off + n].view(sh)
+                off += n
+            return out
+        st.h, st.d = views(st.in_host), views(st.in_dev)
+        st.out_host = torch.zeros((4,), dtype=torch.float32).pin_memory()       # q_loss, v_loss, pi_loss, -
+        st.out_dev = torch.zeros((4,), dtype=torch.float32, device=dev)
+        f = lambda *sh: torch.zeros(sh, dtype=torch.float32, device=dev)
+        st.v_out, st.vnext, st.head = f(B, 1), f(B, 1), f(B, 2 * A)
+        st.act_v, st.act_pi = self.v.act_buffer(B), self.pi.act_buffer(B)
+        st.ev = dict(action=f(B, A), logp=f(B), mean=f(B, A), mu_raw=f(B, A), log_std=f(B, A), z=f(B, A))
+        st.q_new, st.y, st.dv = f(B, 1), f(B), f(B)
+        st.q_grid = f(B, N)
+        st.loss_b, st.dmean, st.dls, st.dhead = f(B), f(B, A), f(B, A), f(B, 2 * A)
+        st.q_reg = f(B)
+        st.stream = torch.cuda.Stream(device=dev)
+        st.graph = None
+        return st
+
+    def _enqueue(self, st, B):
+        eng, d, o = self.eng, st.d, st.out_dev
+        alpha, sac = self.entropy_scale, self.q_update_type == "sac"
+        st.in_dev.copy_(st.in_host, non_blocking=True)
+        # forward passes, all on pre-update parameters (:131-137)
+        self.v.forward(d["s"], out=st.v_out, act=st.act_v)
+        self.target_v.forward(d["s2"], out=st.vnext)
+        self.pi.forward(d["s"], out=st.head, act=st.act_pi)
+        eng.policy_evaluate(st.head, d["eps"], self.action_scale, LOG_STD_MIN, LOG_STD_MAX, out=st.ev)
+        need_q_new = sac or self.optim_type in ("ll", "hard_ll")
+        if need_q_new:
+            self.critic.eval_into(d["s"], st.ev["action"].view(B, 1, -1), st.q_new, "fp32")
+        eng.kl_targets(d["r"], d["g"], st.vnext, st.q_new, st.ev["logp"], st.v_out, alpha, sac,
+                       out=(st.y, st.dv, o[1:2]))
+        # policy loss on the integration grid (:155-194 / reversekl :175-203)
+        if self.optim_type in ("intg", "hard_intg"):
+            self.critic.eval_into(d["s"], self.intgrl_actions, st.q_grid, self.precision)
+            if self.KIND == "fkl":
+                eng.fkl_policy(st.q_grid, self.intgrl_weights, self.intgrl_actions, self.action_scale,
+                               st.ev["mu_raw"], st.ev["log_std"], alpha, out=(st.loss_b, st.dmean, st.dls))
+            else:
+                eng.rkl_policy(st.q_grid, st.v_out.view(-1), self.intgrl_weights, self.intgrl_actions,
+                               self.action_scale, st.ev["mu_raw"], st.ev["log_std"], alpha,
+                               hard=self.optim_type == "hard_intg", out=(st.loss_b, st.dmean, st.dls))
+            eng.policy_head_grad(st.head, 0, dmean=st.dmean, dlog_std=st.dls, out=st.dhead)
+            eng.mean_into(st.loss_b, o[2:3])
+        else:
+            eng.policy_head_grad(st.head, 1 if self.optim_type == "ll" else 2, z=st.ev["z"], logp=st.ev["logp"],
+                                 q_new=st.q_new, v=st.v_out, entropy_scale=alpha, out=st.dhead, loss_out=o[2:3])
+        # backward + Adam, in the reference's order q, v, pi (:199-209)
+        self.critic.grads_into(d["s"], d["a"], st.y, self.q_opt.grad, o[0:1], st.q_reg)
+        self.q_opt.step()
+        self.critic.invalidate()
+        self.v.grads(d["s"], st.dv.view(B, 1), act=st.act_v, grad_out=self.v_opt.grad)
+        self.v_opt.step()
+        self.pi.grads(d["s"], st.dhead, act=st.act_pi, grad_out=self.pi_opt.grad)
+        self.pi_opt.step()
+        st.out_host.copy_(o, non_blocking=True)
+
+    def _snapshot(self):
+        ts = [self.critic.theta, self.v.theta, self.pi.theta]
+        for o in (self.q_opt, self.v_opt, self.pi_opt):
+            ts += [o.m, o.v, o.state_dev]
+        return ts, [t.clone() for t in ts]
+
+    def _step_for(self, B):
+        st = self._steps.get(B)
+        if st is None:
+            st = self._build_step(B)
+            if self.use_graph:
+                # warm-up (workspace growth, function attributes) must not advance the agent: snapshot/restore
+                ts, saved = self._snapshot()
+                with torch.cuda.stream(st.stream):
+                    self._enqueue(st, B)
+                st.stream.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=st.stream):
+                    self._enqueue(st, B)
+                st.graph = g
+                for t, s_ in zip(ts, saved):
+                    t.copy_(s_)
+                self.critic.invalidate()
+                torch.cuda.synchronize(self.device)
+            self._steps[B] = st
+        return st
+
+    def update_network(self, state_batch, action_batch, next_state_batch, reward_batch, gamma_batch, eps=None):
+        s = np.asarray(state_batch, np.float32)
+        B = s.shape[0]
+        st = self._step_for(B)
+        h = st.h
+        if eps is None:
+            # the draws behind normal.sample() in pi_net.evaluate (:305-309): loc + scale * N(0,1), global CPU generator
+            eps = torch.randn(B, self.action_dim)
+        h["s"].copy_(torch.from_numpy(s).view(h["s"].shape))
+        for k, x in (("a", action_batch), ("s2", next_state_batch), ("r", reward_batch), ("g", gamma_batch), ("eps", eps)):
+            h[k].copy_(torch.as_tensor(np.asarray(x, np.float32) if not isinstance(x, torch.Tensor) else x,
+                                       dtype=torch.float32).reshape(h[k].shape))
+        with torch.cuda.stream(st.stream):
+            if st.graph is not None:
+                st.graph.replay()
+            else:
+                self._enqueue(st, B)
+        st.stream.synchronize()
+        self.last_losses = st.out_host[:3].clone().numpy()       # (q_loss, v_loss, pi_loss)
+
+    def update_target_network(self):
+        # target_v <- (1 - tau) target_v + tau v   (:211-215)
+        self.eng.soft_update(self.target_v.theta, self.v.theta, self.tau)
+
+    # ------------------------------------------------------------------ acting
+    def _evaluate(self, state_batch, eps):
+        dev = self.device
+        s = _f32(np.asarray(state_batch, np.float32), dev)
+        head = self.pi.forward(s)
+        e = None if eps is None else _f32(eps, dev)
+        return self.eng.policy_evaluate(head, e, self.action_scale, LOG_STD_MIN, LOG_STD_MAX)
+
+    def sample_action(self, state_batch, eps=None):
+        """pi_net.evaluate(state)[0] (:109-113): one tanh-Gaussian sample per state."""
+        B = np.asarray(state_batch).shape[0]
+        if eps is None:
+            eps = torch.randn(B, self.action_dim)
+        return self._evaluate(state_batch, eps)["action"].cpu().numpy()
+
+    def predict_action(self, state_batch):
+        """tanh(mean) * action_scale (:115-121).  The reference also draws (and discards) a sample here, which
+        advances torch's generator: reproduced so that seeded runs stay aligned."""
+        torch.randn(np.asarray(state_batch).shape[0], self.action_dim)
+        return self._evaluate(state_batch, None)["mean"].cpu().numpy()
+
+    def getQFunction(self, state):
+        s = np.asarray(state, np.float32).reshape(1, -1)
+        return lambda action: self.q_net(s, np.asarray([action], np.float32).reshape(1, -1)).cpu().numpy()
+
+    def getPolicyFunction(self, state):
+        ev = self._evaluate(np.asarray(state, np.float32).reshape(1, -1), None)
+        mean, std = ev["mean"].cpu().numpy(), np.exp(ev["log_std"].cpu().numpy())
+        return lambda action: 1 / (std * np.sqrt(2 * np.pi)) * np.exp(-(action - mean) ** 2 / (2 * std ** 2))
+
+
+class ForwardKLNetwork(_KLNetwork):
+    """agents/network/forwardkl_network.py:17 -- optim_type 'intg' only ('ll' raises there, :152-153)."""
+    KIND = "fkl"
+    OPTIM_TYPES = ("intg",)
+
+
+class ReverseKLNetwork(_KLNetwork):
+    """agents/network/reversekl_network.py:17 -- 'intg', 'hard_intg', 'll', 'hard_ll' ('reparam' has no loss)."""
+    KIND = "rkl"
+    OPTIM_TYPES = ("intg", "hard_intg", "ll", "hard_ll")
