@@ -1,0 +1,240 @@
+"""GPU tests of the ForwardKL / ReverseKL update path: the B-row C-ABI pieces (rlc_mlp_*,
+rlc_policy_evaluate, rlc_kl_targets, rlc_policy_head_grad) against the numpy oracle, and the drop-in
+``ForwardKLNetwork`` / ``ReverseKLNetwork`` (rlcontrol_b200/kl_networks.py) against fixtures recorded
+from the unmodified reference classes (tests/golden/full_*.npz, oracle/make_golden.py)."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+from oracle import oracle_kl as okl
+from test_oracle_kl import FULL, load_full, make_agent
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(eng, x):
+    import torch
+    return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).to(eng.device)
+
+
+def _rand_mlp(rng, inp, H1, H2, O):
+    u = lambda k, *sh: rng.uniform(-k, k, sh).astype(np.float32)
+    return [u(1 / np.sqrt(inp), H1, inp), u(0.3, H1), u(1 / np.sqrt(H1), H2, H1), u(0.3, H2), u(0.5, O, H2), u(0.5, O)]
+
+
+@pytest.mark.parametrize("B,inp,H1,H2,O", [(32, 3, 200, 200, 2), (7, 5, 33, 17, 1), (300, 17, 400, 300, 12), (1, 3, 64, 48, 4)])
+def test_mlp_forward_and_grads_match_oracle(eng, B, inp, H1, H2, O):
+    import rlcontrol_b200 as rb
+    rng = np.random.RandomState(B + O)
+    p = _rand_mlp(rng, inp, H1, H2, O)
+    x = rng.randn(B, inp).astype(np.float32)
+    dout = rng.randn(B, O).astype(np.float32)
+    m = rb.Mlp(eng, inp, H1, H2, O).load_torch(*p)
+    for a, b in zip(m.export_torch(), p):                       # pack/unpack round trip is exact
+        np.testing.assert_array_equal(a.cpu().numpy(), b)
+    ref_out, cache = okl.mlp_forward(x, *p)
+    ref_g = okl.mlp_grads(cache, dout, p[2], p[4])
+    act = m.act_buffer(B)
+    out = m.forward(_t(eng, x), act=act)
+    np.testing.assert_allclose(out.cpu().numpy(), ref_out, rtol=2e-5, atol=2e-5)
+    for use_act in (True, False):                               # kept activations and recomputed forward agree
+        g, dx = m.grads(_t(eng, x), _t(eng, dout), act=act if use_act else None, want_dx=True)
+        g = g.cpu().numpy()
+        o = m.offsets + [g.size]
+        shapes = [(inp, H1), (H1,), (H1, H2), (H2,), (H2, O), (O,)]
+        for i, (r, sh) in enumerate(zip(ref_g, shapes)):
+            mine = g[o[i]:o[i + 1]].reshape(sh)
+            r = r.T if r.ndim == 2 else r                       # oracle is [out,in], theta is [in,out]
+            np.testing.assert_allclose(mine, r, rtol=1e-4, atol=1e-4 * max(1.0, np.abs(r).max()))
+        g1 = (np.asarray(dout, np.float64) @ p[4]) * (cache[3] > 0)
+        g1 = (g1 @ p[2]) * (cache[1] > 0)
+        np.testing.assert_allclose(dx.cpu().numpy(), g1 @ p[0], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("A", [1, 2, 3])
+def test_policy_evaluate_matches_oracle(eng, A):
+    rng = np.random.RandomState(A)
+    B = 37
+    head = rng.randn(B, 2 * A).astype(np.float32)
+    head[:, A:] = head[:, A:] * 2 - 1
+    head[0, A:] = 5.0                                           # clamped above (LOG_STD_MAX = 2)
+    head[1, A:] = -30.0                                         # clamped below
+    eps = rng.randn(B, A).astype(np.float32)
+    ev = eng.policy_evaluate(_t(eng, head), _t(eng, eps), 2.0)
+    mean, ls = head[:, :A], np.clip(head[:, A:], -20, 2)
+    act, lp, z, mt = okl.policy_evaluate(mean, ls, eps, 2.0)
+    np.testing.assert_allclose(ev["action"].cpu().numpy(), act, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(ev["z"].cpu().numpy(), z, rtol=2e-6, atol=2e-6)
+    # log(1 - tanh(z)^2 + 1e-6) is evaluated in fp32 by the reference as well (forwardkl_network.py:313): where
+    # tanh saturates, 1 - a^2 cancels and one ulp of tanh moves the term by O(1) -- those rows get a loose bound
+    sat = (np.abs(np.tanh(z)) > 0.999).any(axis=1)
+    mine = ev["logp"].cpu().numpy()
+    np.testing.assert_allclose(mine[~sat], lp[~sat], rtol=3e-5, atol=3e-4)
+    np.testing.assert_allclose(mine[sat], lp[sat], rtol=0, atol=3.0 * A)
+    assert sat.sum() < len(sat) // 2
+    np.testing.assert_allclose(ev["mean"].cpu().numpy(), mt, rtol=2e-6, atol=2e-6)
+    np.testing.assert_array_equal(ev["mu_raw"].cpu().numpy(), mean)
+    np.testing.assert_array_equal(ev["log_std"].cpu().numpy(), ls)
+    ev0 = eng.policy_evaluate(_t(eng, head), None, 2.0)         # eps = NULL -> the mean action
+    np.testing.assert_allclose(ev0["action"].cpu().numpy(), ev0["mean"].cpu().numpy(), rtol=0, atol=1e-7)
+
+
+@pytest.mark.parametrize("sac", [False, True])
+def test_kl_targets_match_oracle(eng, sac):
+    rng = np.random.RandomState(5)
+    B, alpha = 45, 0.3
+    r, g, vn, qn, lp, v = [rng.randn(B).astype(np.float32) for _ in range(6)]
+    y, dv, vl = eng.kl_targets(*[_t(eng, x) for x in (r, g, vn, qn, lp, v)], alpha, sac, b_total=2 * B)
+    ry = r.astype(np.float64) + g * vn
+    tv = (qn - alpha * lp) if sac else ((r - alpha * lp) + g * vn)
+    np.testing.assert_allclose(y.cpu().numpy(), ry, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(dv.cpu().numpy(), 2 * (v - tv) / (2 * B), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(float(vl.cpu()), np.sum((v - tv) ** 2) / (2 * B), rtol=1e-5)
+
+
+@pytest.mark.parametrize("A,mode", [(1, 0), (1, 1), (1, 2), (3, 0), (3, 1), (3, 2)])
+def test_policy_head_grad_matches_oracle(eng, A, mode):
+    rng = np.random.RandomState(10 * A + mode)
+    B, alpha = 29, 0.2
+    head = rng.randn(B, 2 * A).astype(np.float32)
+    head[0, A:] = 3.0
+    head[1, A:] = -25.0                                         # clamp -> no gradient into log_std
+    dm, ds = rng.randn(B, A).astype(np.float32), rng.randn(B, A).astype(np.float32)
+    z, lp, qn, v = (rng.randn(B, A).astype(np.float32), rng.randn(B).astype(np.float32),
+                    rng.randn(B).astype(np.float32), rng.randn(B).astype(np.float32))
+    import torch
+    loss = torch.zeros(1, device=eng.device)
+    dh = eng.policy_head_grad(_t(eng, head), mode, dmean=_t(eng, dm), dlog_std=_t(eng, ds), z=_t(eng, z), logp=_t(eng, lp),
+                              q_new=_t(eng, qn), v=_t(eng, v), entropy_scale=alpha, loss_out=loss).cpu().numpy()
+    raw = head[:, A:]
+    passm = ((raw >= -20) & (raw <= 2)).astype(np.float64)
+    if mode == 0:
+        rm, rs = dm, ds * passm
+    else:
+        c = (qn - v - alpha * lp) if mode == 1 else (qn - v)
+        coef = (-c.astype(np.float64) / B)[:, None]
+        mu, ls = head[:, :A].astype(np.float64), np.clip(raw, -20, 2).astype(np.float64)
+        t = z - mu
+        if A == 1:
+            rm, rs = coef * t * np.exp(-2 * ls), coef * (t * t * np.exp(-2 * ls) - 1) * passm
+        else:
+            rm, rs = coef * t * np.exp(-ls), coef * (0.5 * t * t * np.exp(-ls) - 0.5) * passm
+        np.testing.assert_allclose(float(loss.cpu()), np.mean(-lp.astype(np.float64) * c), rtol=1e-4, atol=1e-6)
+    scale = max(1.0, np.abs(rm).max(), np.abs(rs).max())
+    np.testing.assert_allclose(dh[:, :A], rm, rtol=1e-4, atol=1e-6 * scale)
+    np.testing.assert_allclose(dh[:, A:], rs, rtol=1e-4, atol=1e-6 * scale)
+
+
+def _config(eng, g, **kw):
+    am = float(g["action_max"])
+    base = dict(state_dim=3, state_min=[-1.0, -1.0, -8.0], state_max=[1.0, 1.0, 8.0], action_dim=1, action_min=[-am],
+                action_max=[am], tau=float(g["tau"]), norm_type="input_norm", random_seed=0,
+                pi_lr=float(g["pi_lr"]), qf_vf_lr=float(g["qf_vf_lr"]), optim_type=str(g["optim_type"]),
+                q_update_type=str(g["q_update_type"]), use_true_q="False", actor_l1_dim=int(g["l1"]),
+                actor_l2_dim=int(g["l2"]), critic_l1_dim=int(g["l1"]), critic_l2_dim=int(g["l2"]),
+                entropy_scale=float(g["alpha"]), N_param=int(g["n_param"]), l_param=6, batch_size=32, engine=eng)
+    base.update(kw)
+    return SimpleNamespace(**base)
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+@pytest.mark.parametrize("name", FULL)
+def test_dropin_update_network_matches_reference(eng, name, use_graph):
+    """The recorded reference run, replayed through the drop-in class: same batches, same normal draws ->
+    every parameter of q_net / v_net / target_v_net / pi_net after update 1 and update 2, the three
+    losses, and sample_action / predict_action on the final networks."""
+    from rlcontrol_b200 import kl_networks
+    g, pre, post = load_full(name)
+    cls = kl_networks.ForwardKLNetwork if "fkl" in name else kl_networks.ReverseKLNetwork
+    net = cls(None, None, _config(eng, g, use_cuda_graph=use_graph))
+    assert net.intgrl_actions_len == g["grid_a"].shape[0]
+    net.load_reference_parameters(pre["q"], pre["v"], pre["tv"], pre["pi"])
+    for u in range(g["s"].shape[0]):
+        net.update_network(g["s"][u], g["a"][u], g["s2"][u], g["r"][u], g["g"][u], eps=g["eps"][u])
+        net.update_target_network()
+        np.testing.assert_allclose(net.last_losses, g["losses"][u], rtol=3e-4, atol=3e-5)
+        mine = net.export_parameters()
+        for k in ("q", "v", "tv", "pi"):
+            for i, (m, ref) in enumerate(zip(mine[k], post[u][k])):
+                move = np.abs(ref - pre[k][i]).max() + 1e-12
+                err = np.abs(m.reshape(ref.shape) - ref).max()
+                assert err <= 5e-3 * move + 5e-7, (name, u, k, i, err, move)
+    st = g["act_states"]
+    np.testing.assert_allclose(net.sample_action(st, eps=g["act_eps"]), g["act_sample"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(net.predict_action(st), g["act_predict"], rtol=1e-4, atol=2e-5)
+
+
+def test_dropin_uses_the_references_random_streams(eng):
+    """Under torch.manual_seed the drop-in draws its initial weights exactly as the reference's constructors do
+    (nn.Linear order pi, q, v, target_v) and its policy noise from the stream normal.sample() consumes."""
+    import torch
+    from rlcontrol_b200 import kl_networks
+    g, _, _ = load_full("full_fkl_intg_nonsac")
+    torch.manual_seed(123)
+    net = kl_networks.ForwardKLNetwork(None, None, _config(eng, g))
+    torch.manual_seed(123)
+    S, A, l1, l2 = 3, 1, int(g["l1"]), int(g["l2"])
+    lin = torch.nn.Linear
+    pi = [lin(S, l1), lin(l1, l2)]
+    heads = []
+    for _ in range(2):
+        h = lin(l2, A)
+        h.weight.data.uniform_(-3e-3, 3e-3)
+        h.bias.data.uniform_(-3e-3, 3e-3)
+        heads.append(h)
+    q1 = lin(S + A, l1)
+    p = net.export_parameters()
+    np.testing.assert_array_equal(p["pi"][0], pi[0].weight.detach().numpy())
+    np.testing.assert_array_equal(p["pi"][6], heads[1].weight.detach().numpy())
+    np.testing.assert_array_equal(p["q"][0], q1.weight.detach().numpy())
+    for a_, b_ in zip(p["v"], p["tv"]):
+        np.testing.assert_array_equal(a_, b_)                   # target_v starts as a copy of v
+    torch.manual_seed(7)
+    a1 = net.sample_action(g["act_states"])
+    torch.manual_seed(7)
+    a2 = net.sample_action(g["act_states"], eps=torch.randn(5, 1))
+    np.testing.assert_array_equal(a1, a2)
+
+
+def test_dropin_rejects_what_the_reference_rejects(eng):
+    from rlcontrol_b200 import kl_networks
+    g, _, _ = load_full("full_fkl_intg_nonsac")
+    with pytest.raises(NotImplementedError):
+        kl_networks.ForwardKLNetwork(None, None, _config(eng, g, optim_type="ll"))     # forwardkl_network.py:152-153
+    with pytest.raises(ValueError):
+        kl_networks.ReverseKLNetwork(None, None, _config(eng, g, q_update_type="td"))  # :157 invalid q_update_type
+
+
+def test_dropin_two_action_dims_matches_oracle(eng):
+    """action_dim = 2 (Smolyak grid, MVN-with-std-as-covariance log-density): the reference itself cannot run this
+    branch under torch 2.x (float64 grid), so the check is against the oracle restatement only."""
+    from rlcontrol_b200 import kl_networks
+    g, _, _ = load_full("full_fkl_intg_nonsac")
+    rng = np.random.RandomState(3)
+    S, A, B, l1, l2 = 4, 2, 16, 40, 24
+    for cls, kind in ((kl_networks.ForwardKLNetwork, "fkl"), (kl_networks.ReverseKLNetwork, "rkl")):
+        cfg = _config(eng, g, state_dim=S, state_min=[-3.0] * S, state_max=[3.0] * S, action_dim=A, action_min=[-1.5] * A,
+                      action_max=[1.5] * A, actor_l1_dim=l1, actor_l2_dim=l2, critic_l1_dim=l1, critic_l2_dim=l2,
+                      l_param=4, optim_type="intg", q_update_type="sac", entropy_scale=0.3)
+        net = cls(None, None, cfg)
+        p = net.export_parameters()
+        p["q"][4] = p["q"][4] * 100
+        p["pi"][4] = p["pi"][4] * 50
+        p["pi"][6] = p["pi"][6] * 30
+        net.load_reference_parameters(p["q"], p["v"], p["tv"], p["pi"])
+        ag = okl.KLAgent(kind, p["q"], p["v"], p["tv"], p["pi"], net.intgrl_actions.cpu().numpy(),
+                         net.intgrl_weights.cpu().numpy(), 1.5, 0.3, cfg.pi_lr, cfg.qf_vf_lr, cfg.tau, "intg", "sac")
+        for u in range(2):
+            s, a, s2 = rng.randn(B, S), rng.uniform(-1.5, 1.5, (B, A)), rng.randn(B, S)
+            r, gm, eps = rng.randn(B), np.full(B, 0.99), rng.randn(B, A).astype(np.float32)
+            net.update_network(s, a, s2, r, gm, eps=eps)
+            net.update_target_network()
+            ref_losses = ag.update(s.astype(np.float32), a.astype(np.float32), s2.astype(np.float32),
+                                   r.astype(np.float32), gm.astype(np.float32), eps)
+            np.testing.assert_allclose(net.last_losses, ref_losses, rtol=5e-4, atol=5e-5)
+        mine = net.export_parameters()
+        for k, ref in (("q", ag.q), ("v", ag.v), ("tv", ag.tv), ("pi", ag.pi)):
+            for i, (m, r_) in enumerate(zip(mine[k], ref)):
+                move = np.abs(r_ - p[k][i]).max() + 1e-12
+                assert np.abs(m.reshape(r_.shape) - r_).max() <= 1e-2 * move + 1e-6, (kind, k, i)
