@@ -163,13 +163,15 @@ static int colred(rlc_handle* h, const float* Mx, const float* dq, long long R, 
                   float* out, cudaStream_t st) {
   const int ncols = N + (MODE == 1 ? 1 : 0);
   int nchunks = (int)((R + 15) / 16);
+  if (R <= 64) nchunks = 1;  // small batches are launch-latency-bound: one stage, straight into `out`
   if (nchunks > COLRED_MAX_CHUNKS) nchunks = COLRED_MAX_CHUNKS;
   if (nchunks < 1) nchunks = 1;
   const int rpc = (int)((R + nchunks - 1) / nchunks);
   nchunks = (int)((R + rpc - 1) / rpc);
   dim3 grid((ncols + 127) / 128, nchunks);
-  k_colred_part<MODE><<<grid, 128, 0, st>>>(Mx, dq, R, N, ld, rpc, part);
+  k_colred_part<MODE><<<grid, 128, 0, st>>>(Mx, dq, R, N, ld, rpc, nchunks == 1 ? out : part);
   RLC_LAUNCH_CHECK(h);
+  if (nchunks == 1) return RLC_OK;
   k_sum_slabs<<<(ncols + 255) / 256, 256, 0, st>>>(part, ncols, nchunks, out);
   RLC_LAUNCH_CHECK(h);
   return RLC_OK;

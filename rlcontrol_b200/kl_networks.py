@@ -107,6 +107,9 @@ class _KLNetwork(object):
         self.eng = eng if eng is not None else Engine()
         self.precision = getattr(config, "precision", "auto")
         dev = self.eng.device
+        # The update's branches (Q regression | grid evaluation + policy | V) overlap on separate streams inside the
+        # captured graph; a handle's scratch is per handle, so each branch gets its own (cheap: scratch only).
+        self.eng_grid, self.eng_v, self.eng_pi = (Engine(self.eng.device_index) for _ in range(3))
         # ---- parameters, drawn in the reference's order: pi_net, q_net, v_net, target_v_net (:41-45)
         pW1, pb1 = _linear_init(S, a1)
         pW2, pb2 = _linear_init(a1, a2)
@@ -120,15 +123,18 @@ class _KLNetwork(object):
         vW3, vb3 = _linear_init(c2, 1, 3e-3)
         for n_in, n_out, iw in ((S, c1, None), (c1, c2, None), (c2, 1, 3e-3)):     # target_v_net's own draws, then
             _linear_init(n_in, n_out, iw)                                          # overwritten by the copy (:47-49)
-        self.pi = Mlp(self.eng, S, a1, a2, 2 * A).load_torch(pW1, pb1, pW2, pb2, [mW, sW], [mb, sb])
+        self.pi = Mlp(self.eng_pi, S, a1, a2, 2 * A).load_torch(pW1, pb1, pW2, pb2, [mW, sW], [mb, sb])
         self.critic = Critic(self.eng, TIN, S, A, c1, c2).load(qW1, qb1, qW2, qb2, qW3, qb3, LAYOUT_OUT_IN)
-        self.v = Mlp(self.eng, S, c1, c2, 1).load_torch(vW1, vb1, vW2, vb2, vW3, vb3)
-        self.target_v = Mlp(self.eng, S, c1, c2, 1)
+        self.critic_grid = Critic(self.eng_grid, TIN, S, A, c1, c2)       # same theta, the grid branch's handle
+        self.critic_grid.theta = self.critic.theta
+        self.critic_grid._refresh()
+        self.v = Mlp(self.eng_v, S, c1, c2, 1).load_torch(vW1, vb1, vW2, vb2, vW3, vb3)
+        self.target_v = Mlp(self.eng_v, S, c1, c2, 1)
         self.target_v.copy_from(self.v)
         self.q_net = _QNet(self.critic)
-        self.pi_opt = _Adam(self.eng, self.pi.theta, self.learning_rate[0])
+        self.pi_opt = _Adam(self.eng_pi, self.pi.theta, self.learning_rate[0])
         self.q_opt = _Adam(self.eng, self.critic.theta, self.learning_rate[1])
-        self.v_opt = _Adam(self.eng, self.v.theta, self.learning_rate[1])
+        self.v_opt = _Adam(self.eng_v, self.v.theta, self.learning_rate[1])
         # ---- integration grid (:58-102)
         acts, w = integration_grid(A, self.action_scale, getattr(config, "N_param", 64), getattr(config, "l_param", 6))
         self.intgrl_actions, self.intgrl_weights = _f32(acts, dev), _f32(w, dev)
@@ -142,6 +148,7 @@ class _KLNetwork(object):
     def load_reference_parameters(self, q, v, target_v, pi):
         """Lists in torch layout: q/v/target_v = [W1,b1,W2,b2,W3,b3]; pi = [W1,b1,W2,b2,Wm,bm,Ws,bs]."""
         self.critic.load(*q, LAYOUT_OUT_IN)
+        self.critic_grid.invalidate()
         self.v.load_torch(*v)
         self.target_v.load_torch(*target_v)
         self.pi.load_torch(pi[0], pi[1], pi[2], pi[3], [pi[4], pi[6]], [pi[5], pi[7]])
@@ -183,46 +190,80 @@ class _KLNetwork(object):
         st.loss_b, st.dmean, st.dls, st.dhead = f(B), f(B, A), f(B, A), f(B, 2 * A)
         st.q_reg = f(B)
         st.stream = torch.cuda.Stream(device=dev)
+        st.s_grid, st.s_v, st.s_pi = (torch.cuda.Stream(device=dev) for _ in range(3))
         st.graph = None
         return st
 
     def _enqueue(self, st, B):
+        """One update on four streams (fork after the upload, join before the download); the dependency edges
+        are exactly the data dependencies of update_network, so the captured graph runs the independent
+        branches side by side: small batches are latency-bound, and this is what shortens the critical path.
+
+            main  : H2D -> [Q(s,a_new)] -> targets -> Q regression grads -> (grid done) Adam(theta_Q) -> D2H
+            s_pi  : policy head(s) -> evaluate
+            s_v   : V(s), V_targ(s')          ... -> V grads -> Adam(theta_V)
+            s_grid: Q on the B x N grid with the PRE-update theta_Q -> reduction -> head grad -> pi grads -> Adam(theta_pi)
+        """
         eng, d, o = self.eng, st.d, st.out_dev
         alpha, sac = self.entropy_scale, self.q_update_type == "sac"
+        intg = self.optim_type in ("intg", "hard_intg")
+        need_q_new = sac or not intg
+        main, s_grid, s_v, s_pi = st.stream, st.s_grid, st.s_v, st.s_pi
         st.in_dev.copy_(st.in_host, non_blocking=True)
+        for br in (s_grid, s_v, s_pi):
+            br.wait_stream(main)
         # forward passes, all on pre-update parameters (:131-137)
-        self.v.forward(d["s"], out=st.v_out, act=st.act_v)
-        self.target_v.forward(d["s2"], out=st.vnext)
-        self.pi.forward(d["s"], out=st.head, act=st.act_pi)
-        eng.policy_evaluate(st.head, d["eps"], self.action_scale, LOG_STD_MIN, LOG_STD_MAX, out=st.ev)
-        need_q_new = sac or self.optim_type in ("ll", "hard_ll")
+        with torch.cuda.stream(s_pi):
+            self.pi.forward(d["s"], out=st.head, act=st.act_pi)
+            self.eng_pi.policy_evaluate(st.head, d["eps"], self.action_scale, LOG_STD_MIN, LOG_STD_MAX, out=st.ev)
+        with torch.cuda.stream(s_v):
+            self.v.forward(d["s"], out=st.v_out, act=st.act_v)
+            self.target_v.forward(d["s2"], out=st.vnext)
+        if intg:
+            with torch.cuda.stream(s_grid):
+                self.critic_grid.eval_into(d["s"], self.intgrl_actions, st.q_grid, self.precision)
+                ev_grid = torch.cuda.Event()
+                ev_grid.record(s_grid)
+        # main: regression targets (:137-150)
+        main.wait_stream(s_pi)
         if need_q_new:
             self.critic.eval_into(d["s"], st.ev["action"].view(B, 1, -1), st.q_new, "fp32")
+        main.wait_stream(s_v)
         eng.kl_targets(d["r"], d["g"], st.vnext, st.q_new, st.ev["logp"], st.v_out, alpha, sac,
                        out=(st.y, st.dv, o[1:2]))
-        # policy loss on the integration grid (:155-194 / reversekl :175-203)
-        if self.optim_type in ("intg", "hard_intg"):
-            self.critic.eval_into(d["s"], self.intgrl_actions, st.q_grid, self.precision)
-            if self.KIND == "fkl":
-                eng.fkl_policy(st.q_grid, self.intgrl_weights, self.intgrl_actions, self.action_scale,
-                               st.ev["mu_raw"], st.ev["log_std"], alpha, out=(st.loss_b, st.dmean, st.dls))
+        # V branch: backward + Adam
+        s_v.wait_stream(main)
+        with torch.cuda.stream(s_v):
+            self.v.grads(d["s"], st.dv.view(B, 1), act=st.act_v, grad_out=self.v_opt.grad)
+            self.v_opt.step()
+        # policy branch (:155-194 / reversekl :175-203), on the grid stream
+        s_grid.wait_stream(main)               # covers s_pi and s_v (evaluate, V(s)) and, for 'll', Q(s,a_new)
+        with torch.cuda.stream(s_grid):
+            if intg:
+                if self.KIND == "fkl":
+                    self.eng_grid.fkl_policy(st.q_grid, self.intgrl_weights, self.intgrl_actions, self.action_scale,
+                                             st.ev["mu_raw"], st.ev["log_std"], alpha, out=(st.loss_b, st.dmean, st.dls))
+                else:
+                    self.eng_grid.rkl_policy(st.q_grid, st.v_out.view(-1), self.intgrl_weights, self.intgrl_actions,
+                                             self.action_scale, st.ev["mu_raw"], st.ev["log_std"], alpha,
+                                             hard=self.optim_type == "hard_intg", out=(st.loss_b, st.dmean, st.dls))
+                self.eng_grid.policy_head_grad(st.head, 0, dmean=st.dmean, dlog_std=st.dls, out=st.dhead)
+                self.eng_grid.mean_into(st.loss_b, o[2:3])
             else:
-                eng.rkl_policy(st.q_grid, st.v_out.view(-1), self.intgrl_weights, self.intgrl_actions,
-                               self.action_scale, st.ev["mu_raw"], st.ev["log_std"], alpha,
-                               hard=self.optim_type == "hard_intg", out=(st.loss_b, st.dmean, st.dls))
-            eng.policy_head_grad(st.head, 0, dmean=st.dmean, dlog_std=st.dls, out=st.dhead)
-            eng.mean_into(st.loss_b, o[2:3])
-        else:
-            eng.policy_head_grad(st.head, 1 if self.optim_type == "ll" else 2, z=st.ev["z"], logp=st.ev["logp"],
-                                 q_new=st.q_new, v=st.v_out, entropy_scale=alpha, out=st.dhead, loss_out=o[2:3])
-        # backward + Adam, in the reference's order q, v, pi (:199-209)
+                self.eng_grid.policy_head_grad(st.head, 1 if self.optim_type == "ll" else 2, z=st.ev["z"],
+                                               logp=st.ev["logp"], q_new=st.q_new, v=st.v_out, entropy_scale=alpha,
+                                               out=st.dhead, loss_out=o[2:3])
+            self.pi.grads(d["s"], st.dhead, act=st.act_pi, grad_out=self.pi_opt.grad)   # eng_pi's scratch: s_pi is idle
+            self.pi_opt.step()
+        # main: Q regression (:133-140,199-201); theta_Q may only change once the grid branch has read it
         self.critic.grads_into(d["s"], d["a"], st.y, self.q_opt.grad, o[0:1], st.q_reg)
+        if intg:
+            main.wait_event(ev_grid)
         self.q_opt.step()
         self.critic.invalidate()
-        self.v.grads(d["s"], st.dv.view(B, 1), act=st.act_v, grad_out=self.v_opt.grad)
-        self.v_opt.step()
-        self.pi.grads(d["s"], st.dhead, act=st.act_pi, grad_out=self.pi_opt.grad)
-        self.pi_opt.step()
+        self.critic_grid.invalidate()
+        for br in (s_grid, s_v, s_pi):
+            main.wait_stream(br)
         st.out_host.copy_(o, non_blocking=True)
 
     def _snapshot(self):
@@ -234,6 +275,9 @@ class _KLNetwork(object):
     def _step_for(self, B):
         st = self._steps.get(B)
         if st is None:
+            # a new batch size may grow a handle's scratch, which would leave older captured graphs with stale
+            # pointers: keep one captured update (the reference's batch size is fixed, config.batch_size)
+            self._steps.clear()
             st = self._build_step(B)
             if self.use_graph:
                 # warm-up (workspace growth, function attributes) must not advance the agent: snapshot/restore
@@ -248,6 +292,7 @@ class _KLNetwork(object):
                 for t, s_ in zip(ts, saved):
                     t.copy_(s_)
                 self.critic.invalidate()
+                self.critic_grid.invalidate()
                 torch.cuda.synchronize(self.device)
             self._steps[B] = st
         return st
@@ -274,7 +319,7 @@ class _KLNetwork(object):
 
     def update_target_network(self):
         # target_v <- (1 - tau) target_v + tau v   (:211-215)
-        self.eng.soft_update(self.target_v.theta, self.v.theta, self.tau)
+        self.eng_v.soft_update(self.target_v.theta, self.v.theta, self.tau)
 
     # ------------------------------------------------------------------ acting
     def _evaluate(self, state_batch, eps):
@@ -282,7 +327,7 @@ class _KLNetwork(object):
         s = _f32(np.asarray(state_batch, np.float32), dev)
         head = self.pi.forward(s)
         e = None if eps is None else _f32(eps, dev)
-        return self.eng.policy_evaluate(head, e, self.action_scale, LOG_STD_MIN, LOG_STD_MAX)
+        return self.eng_pi.policy_evaluate(head, e, self.action_scale, LOG_STD_MIN, LOG_STD_MAX)
 
     def sample_action(self, state_batch, eps=None):
         """pi_net.evaluate(state)[0] (:109-113): one tanh-Gaussian sample per state."""
