@@ -6,10 +6,16 @@
 #include "rows_gemm.cuh"
 
 // =============================================================================================
-// Fused two-layer kernel: 64 rows per CTA, h1 tile kept in shared memory, layer 2 register-tiled
-// (4 rows x NJ strided columns per thread), epilogue = w3 dot (T-in q) or store p (T-mid term).
+// Fused two-layer kernel: 32 rows per CTA (small batches still spread over many SMs), layer-1
+// activations kept in shared memory, W2 streamed through a double-buffered shared-memory ring in
+// 16-row chunks (register-staged: the loads of chunk c+1 are in flight while chunk c is consumed),
+// layer 2 register-tiled: a warp owns 4 rows (activation reads are warp-wide broadcasts, float4
+// along k) and a lane owns the columns lane, lane+32, ... (conflict-free W2 reads).
+// Epilogue = w3 dot (T-in q) or store p (T-mid state term).
 // =============================================================================================
 enum { MODE_TIN_Q = 0, MODE_TMID_P = 1 };
+#define MLP2_TM 32
+#define MLP2_KC 16
 
 template <int NJ, int MODE>
 __global__ void __launch_bounds__(256)
@@ -19,15 +25,28 @@ k_mlp2_rows(const float* __restrict__ s, const float* __restrict__ a, int act_pe
             const float* __restrict__ b2, const float* __restrict__ w3,
             const float* __restrict__ b3, const float* __restrict__ smin,
             const float* __restrict__ smax, float* __restrict__ out) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
+  constexpr int H2S = NJ * 32;
   const int K1 = (MODE == MODE_TIN_Q) ? S + A : S;
-  const int H1P = H1 + 1;
-  float* xs = sm;             // [64][K1]
-  float* h1s = sm + 64 * K1;  // [64][H1P]
-  const long long r0 = (long long)blockIdx.x * 64;
-  const int tid = threadIdx.x;
+  const int K1P = (K1 + 3) & ~3;
+  const int nchunks = (H1 + MLP2_KC - 1) / MLP2_KC;
+  const int H1P = nchunks * MLP2_KC;
+  float* xs = sm;                        // [TM][K1P]
+  float* h1s = xs + MLP2_TM * K1P;       // [TM][H1P]   (columns >= H1 are zero)
+  float* w2s = h1s + MLP2_TM * H1P;      // [2][KC][H2S]
+  const long long r0 = (long long)blockIdx.x * MLP2_TM;
+  const int tid = threadIdx.x, lane = tid & 31, rg = tid >> 5;
 
-  for (int i = tid; i < 64 * K1; i += 256) {
+  // first W2 chunk: issue the loads before the layer-1 work so their latency is hidden behind it
+  constexpr int NST = NJ * MLP2_KC / 8;  // chunk elements per thread
+  float stg[NST];
+#pragma unroll
+  for (int t = 0; t < NST; ++t) {
+    const int e = tid + 256 * t, kr = e / H2S, col = e - kr * H2S;
+    stg[t] = (kr < H1 && col < H2) ? __ldg(W2 + (long long)kr * H2 + col) : 0.f;
+  }
+
+  for (int i = tid; i < MLP2_TM * K1; i += 256) {
     const int r = i / K1, k = i - r * K1;
     const long long row = r0 + r;
     float v = 0.f;
@@ -46,56 +65,83 @@ k_mlp2_rows(const float* __restrict__ s, const float* __restrict__ a, int act_pe
         if (smin) v = fminf(fmaxf(v, smin[k]), smax[k]);
       }
     }
-    xs[i] = v;
+    xs[r * K1P + k] = v;
   }
   __syncthreads();
 
-  for (int i = tid; i < 64 * H1; i += 256) {
-    const int r = i / H1, j = i - r * H1;
-    float acc = b1[j];
-    const float* xr = xs + r * K1;
-    for (int k = 0; k < K1; ++k) acc = fmaf(xr[k], __ldg(W1 + (long long)k * H1 + j), acc);
-    h1s[r * H1P + j] = fmaxf(acc, 0.f);
+  for (int i = tid; i < MLP2_TM * H1P; i += 256) {
+    const int r = i / H1P, j = i - r * H1P;
+    float v = 0.f;
+    if (j < H1) {
+      float acc = b1[j];
+      const float* xr = xs + r * K1P;
+      for (int k = 0; k < K1; ++k) acc = fmaf(xr[k], __ldg(W1 + (long long)k * H1 + j), acc);
+      v = fmaxf(acc, 0.f);
+    }
+    h1s[i] = v;
   }
+#pragma unroll
+  for (int t = 0; t < NST; ++t) w2s[tid + 256 * t] = stg[t];
   __syncthreads();
 
-  const int rg = tid >> 4, cg = tid & 15;
   float acc[4][NJ];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
-  const float* h = h1s + (rg * 4) * H1P;
-  for (int k = 0; k < H1; ++k) {
-    const float h0 = h[k], h1v = h[H1P + k], h2v = h[2 * H1P + k], h3v = h[3 * H1P + k];
-    const float* wrow = W2 + (long long)k * H2 + cg;
+  const float* hrow = h1s + (rg * 4) * H1P;
+  for (int c = 0; c < nchunks; ++c) {
+    const bool more = c + 1 < nchunks;
+    if (more) {
+      const int k0 = (c + 1) * MLP2_KC;
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      const float w = (cg + 16 * j < H2) ? __ldg(wrow + 16 * j) : 0.f;
-      acc[0][j] = fmaf(h0, w, acc[0][j]);
-      acc[1][j] = fmaf(h1v, w, acc[1][j]);
-      acc[2][j] = fmaf(h2v, w, acc[2][j]);
-      acc[3][j] = fmaf(h3v, w, acc[3][j]);
+      for (int t = 0; t < NST; ++t) {
+        const int e = tid + 256 * t, kr = k0 + e / H2S, col = e % H2S;
+        stg[t] = (kr < H1 && col < H2) ? __ldg(W2 + (long long)kr * H2 + col) : 0.f;
+      }
     }
+    const float* wb = w2s + (c & 1) * (MLP2_KC * H2S) + lane;
+#pragma unroll
+    for (int kk = 0; kk < MLP2_KC; kk += 4) {
+      float4 hv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        hv[i] = *reinterpret_cast<const float4*>(hrow + i * H1P + c * MLP2_KC + kk);
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const float w = wb[(kk + k4) * H2S + 32 * j];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float hval = k4 == 0 ? hv[i].x : k4 == 1 ? hv[i].y : k4 == 2 ? hv[i].z : hv[i].w;
+            acc[i][j] = fmaf(hval, w, acc[i][j]);
+          }
+        }
+      }
+    }
+    if (more) {
+      float* wn = w2s + ((c + 1) & 1) * (MLP2_KC * H2S);
+#pragma unroll
+      for (int t = 0; t < NST; ++t) wn[tid + 256 * t] = stg[t];
+    }
+    __syncthreads();
   }
 
   if (MODE == MODE_TIN_Q) {
     float qs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      const int c = cg + 16 * j;
-      if (c < H2) {
-        const float bb = __ldg(b2 + c), ww = __ldg(w3 + c);
+      const int col = lane + 32 * j;
+      if (col < H2) {
+        const float bb = __ldg(b2 + col), ww = __ldg(w3 + col);
 #pragma unroll
         for (int i = 0; i < 4; ++i) qs[i] = fmaf(ww, fmaxf(acc[i][j] + bb, 0.f), qs[i]);
       }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) qs[i] += __shfl_xor_sync(0xffffffffu, qs[i], o);
-    }
-    if (cg == 0) {
+    for (int i = 0; i < 4; ++i) qs[i] = warp_sum(qs[i]);
+    if (lane == 0) {
       const float bb3 = __ldg(b3);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -106,13 +152,13 @@ k_mlp2_rows(const float* __restrict__ s, const float* __restrict__ a, int act_pe
   } else {
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      const int c = cg + 16 * j;
-      if (c < H2) {
-        const float bb = __ldg(b2 + c);
+      const int col = lane + 32 * j;
+      if (col < H2) {
+        const float bb = __ldg(b2 + col);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const long long row = r0 + rg * 4 + i;
-          if (row < R) out[row * H2 + c] = acc[i][j] + bb;
+          if (row < R) out[row * H2 + col] = acc[i][j] + bb;
         }
       }
     }
@@ -127,22 +173,27 @@ static int launch_mlp2(rlc_handle* h, const float* s, const float* a, int act_pe
                        cudaStream_t st) {
   if (R == 0) return RLC_OK;
   const int K1 = (MODE == MODE_TIN_Q) ? S + A : S;
-  const size_t smem = (size_t)(64 * K1 + 64 * (H1 + 1)) * sizeof(float);
+  const int K1P = (K1 + 3) & ~3;
+  const int H1P = (H1 + MLP2_KC - 1) / MLP2_KC * MLP2_KC;
+  const int NJ = H2 <= 64 ? 2 : H2 <= 128 ? 4 : H2 <= 224 ? 7 : H2 <= 320 ? 10 : 16;
+  if (H2 > 512) return RLC_ERR_UNSUPPORTED;
+  const size_t smem =
+      (size_t)(MLP2_TM * K1P + MLP2_TM * H1P + 2 * MLP2_KC * NJ * 32) * sizeof(float);
   if (smem > h->smem_optin) return RLC_ERR_UNSUPPORTED;
-  const long long blocks = (R + 63) / 64;
+  const long long blocks = (R + MLP2_TM - 1) / MLP2_TM;
   if (blocks > 0x7fffffffLL) return RLC_ERR_INVALID;
-#define RLC_MLP2_CASE(NJ)                                                                        \
+#define RLC_MLP2_CASE(NJV)                                                                       \
   {                                                                                              \
-    auto kern = k_mlp2_rows<NJ, MODE>;                                                           \
+    auto kern = k_mlp2_rows<NJV, MODE>;                                                          \
     RLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<(unsigned)blocks, 256, smem, st>>>(s, a, act_per_state, R, N, S, A, H1, H2, W1, b1,   \
                                               W2, b2, w3, b3, smin, smax, out);                  \
   }
-  if (H2 <= 64) RLC_MLP2_CASE(4)
-  else if (H2 <= 208) RLC_MLP2_CASE(13)
-  else if (H2 <= 304) RLC_MLP2_CASE(19)
-  else if (H2 <= 512) RLC_MLP2_CASE(32)
-  else return RLC_ERR_UNSUPPORTED;
+  if (NJ == 2) RLC_MLP2_CASE(2)
+  else if (NJ == 4) RLC_MLP2_CASE(4)
+  else if (NJ == 7) RLC_MLP2_CASE(7)
+  else if (NJ == 10) RLC_MLP2_CASE(10)
+  else RLC_MLP2_CASE(16)
 #undef RLC_MLP2_CASE
   RLC_LAUNCH_CHECK(h);
   return RLC_OK;

@@ -20,8 +20,11 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(256)
 k_gemm(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ Bm,
        int ldb, float* __restrict__ C, int ldc, GemmEpi epi, int klen, long long cz_stride) {
-  __shared__ float As[16][64 + 4];
-  __shared__ float Bs[16][64 + 4];
+  // 64 x 64 output tile, 16-deep k steps, double-buffered shared memory: the global loads of step
+  // k+1 are issued before the FMAs of step k and parked in registers, so their latency overlaps the
+  // math (the B-row training GEMMs are latency-bound: a few CTAs, a dozen dependent k steps).
+  __shared__ float As[2][16][64 + 4];
+  __shared__ float Bs[2][16][64 + 4];
   // split-K: slice blockIdx.z covers K range [z*klen, min(K,(z+1)*klen)) and writes its own C slab
   const int kbeg = blockIdx.z * klen;
   K = (kbeg + klen < K) ? kbeg + klen : K;
@@ -34,7 +37,8 @@ k_gemm(int M, int N, int K, const float* __restrict__ A, int lda, const float* _
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = kbeg; k0 < K; k0 += 16) {
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
       const int e = tid + l * 256;  // 0..1023
@@ -45,7 +49,7 @@ k_gemm(int M, int N, int K, const float* __restrict__ A, int lda, const float* _
         float v = 0.f;
         if (gm < M && gk < K) v = TA ? A[(long long)gk * lda + gm] : A[(long long)gm * lda + gk];
         if (epi.reluA) v = fmaxf(v, 0.f);
-        As[k][m] = v;
+        ra[l] = v;
       }
       {
         int n, k;
@@ -53,23 +57,42 @@ k_gemm(int M, int N, int K, const float* __restrict__ A, int lda, const float* _
         const int gn = n0 + n, gk = k0 + k;
         float v = 0.f;
         if (gn < N && gk < K) v = TB ? Bm[(long long)gn * ldb + gk] : Bm[(long long)gk * ldb + gn];
-        Bs[k][n] = v;
+        rb[l] = v;
       }
     }
-    __syncthreads();
+  };
+  auto park = [&](int buf) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const int e = tid + l * 256;
+      if (TA) As[buf][e >> 6][e & 63] = ra[l]; else As[buf][e & 15][e >> 4] = ra[l];
+      if (TB) Bs[buf][e & 15][e >> 4] = rb[l]; else Bs[buf][e >> 6][e & 63] = rb[l];
+    }
+  };
+  if (kbeg < K) {
+    fetch(kbeg);
+    park(0);
+  }
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = kbeg; k0 < K; k0 += 16) {
+    const bool more = k0 + 16 < K;
+    if (more) fetch(k0 + 16);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       float av[4], bv[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) av[i] = As[k][tr * 4 + i];
+      for (int i = 0; i < 4; ++i) av[i] = As[buf][k][tr * 4 + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bv[j] = Bs[k][tc * 4 + j];
+      for (int j = 0; j < 4; ++j) bv[j] = Bs[buf][k][tc * 4 + j];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
+    if (more) park(buf ^ 1);
     __syncthreads();
+    buf ^= 1;
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
