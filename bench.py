@@ -57,10 +57,10 @@ def make_params(rng, S, A, H1, H2):
 
 
 def make_inputs(rng, B, N, S, A):
-    from oracle import oracle_np as onp            # grid weights only (Clenshaw-Curtis interior)
+    from rlcontrol_b200 import quadrature          # grid weights only (Clenshaw-Curtis interior)
     s = np.clip(rng.randn(B, S), -10, 10).astype(np.float32)
     a = rng.uniform(-1, 1, (N, A)).astype(np.float32)
-    _, w = onp.intg_grid_1d(N + 2, 1.0)
+    _, w = quadrature.grid_1d(N + 2, 1.0)
     mean = (rng.randn(B, A) * 0.5).astype(np.float32)          # policy head outputs (actor side, fed in)
     log_std = (rng.randn(B, A) * 0.3 - 0.5).astype(np.float32)
     return s, a, np.asarray(w, np.float32), (mean, log_std)
@@ -349,62 +349,82 @@ def run_b200(args, rank, local_rank, world):
     barrier()
     upd_ms = ev0.elapsed_time(ev1) / upd_reps
 
-    # ---- secondary: cfg1 (Pendulum ReverseKL/ForwardKL shape: B=32, N=62, S=3, A=1, 200-200), the README
-    # command's per-environment-step update, hot-path part: critic regression step (grads, Adam,
-    # operand repack) + grid evaluation + policy reduction, host-synchronous like the reference's loop
-    c1 = dict(S=3, A=1, H1=200, H2=200, B=32, N=62)
+    # ---- secondary: cfg1 (the README command: Pendulum ReverseKL, B=32, N_param=64 -> N=62, S=3, A=1, 200-200).
+    # One FULL agent update through the drop-in class: ReverseKLNetwork.update_network + update_target_network
+    # (q, v and pi networks, three Adam steps, Polyak), numpy minibatch in, losses out, host-synchronous like
+    # the reference's loop (agents/ReverseKL.py:81-90) -- one CUDA-graph launch per update.
+    from types import SimpleNamespace
+    from rlcontrol_b200 import kl_networks
+
+    def kl_config(engine, S_, A_, amax, B_, n_param, l1_, l2_, **kw):
+        d = dict(state_dim=S_, state_min=[-10.0] * S_, state_max=[10.0] * S_, action_dim=A_, action_min=[-amax] * A_,
+                 action_max=[amax] * A_, tau=0.01, norm_type="input_norm", random_seed=0, pi_lr=1e-3, qf_vf_lr=1e-3,
+                 optim_type="intg", q_update_type="non_sac", use_true_q="False", actor_l1_dim=l1_, actor_l2_dim=l2_,
+                 critic_l1_dim=l1_, critic_l2_dim=l2_, entropy_scale=alpha, N_param=n_param, l_param=6,
+                 batch_size=B_, engine=engine)
+        d.update(kw)
+        return SimpleNamespace(**d)
+
     rng1 = np.random.RandomState(5)
-    p1 = make_params(rng1, c1["S"], c1["A"], c1["H1"], c1["H2"])
-    cr1 = rb.Critic(eng, rb.TIN, c1["S"], c1["A"], c1["H1"], c1["H2"]).load(*p1, rb.LAYOUT_OUT_IN)
-    grid1, w1 = onp.intg_grid_1d(c1["N"] + 2, 2.0)
-    from rlcontrol_b200.steps import GridAgentUpdateStep
-    s1 = rng1.randn(c1["B"], c1["S"]).astype(np.float32)
-    a1 = rng1.uniform(-2, 2, (c1["B"], c1["A"])).astype(np.float32)
-    y1 = rng1.randn(c1["B"]).astype(np.float32)
-    m1, l1 = (rng1.randn(c1["B"], 1) * .5).astype(np.float32), (rng1.randn(c1["B"], 1) * .3 - .5).astype(np.float32)
-    v1 = rng1.randn(c1["B"]).astype(np.float32)
+    B1 = 32
+    batches1 = [(rng1.randn(B1, 3), rng1.uniform(-2, 2, (B1, 1)), rng1.randn(B1, 3), rng1.randn(B1), np.full(B1, 0.99))
+                for _ in range(8)]
+    torch.manual_seed(0)
+    ag = kl_networks.ReverseKLNetwork(None, None, kl_config(rb.Engine(local_rank), 3, 1, 2.0, B1, 64, 200, 200))
 
-    def make_agent(engine):
-        cr = rb.Critic(engine, rb.TIN, c1["S"], c1["A"], c1["H1"], c1["H2"]).load(*p1, rb.LAYOUT_OUT_IN)
-        return GridAgentUpdateStep(cr, rb.CriticOptimizer(cr, lr=1e-3), grid1, w1, 2.0, alpha, c1["B"], kind="rkl",
-                                   precision="auto")
+    def update_cfg1(i):
+        ag.update_network(*batches1[i % 8])
+        ag.update_target_network()
 
-    # one agent, host-synchronous: inputs written, ONE graph launch (critic step + repack + grid eval + RKL
-    # reduction), outputs read -- what one environment step of the README command pays on the hot path
-    ag = make_agent(eng)
-
-    def update_cfg1():
-        return float(ag(s=s1, a=a1, y=y1, mean=m1, log_std=l1, v=v1)["loss_b"][0])
-
-    for _ in range(20):
-        update_cfg1()
+    for i in range(20):
+        update_cfg1(i)
     torch.cuda.synchronize()
     n_upd = 300
     t0 = time.perf_counter()
-    for _ in range(n_upd):
-        update_cfg1()
+    for i in range(n_upd):
+        update_cfg1(i)
     torch.cuda.synchronize()
     cfg1_ms = (time.perf_counter() - t0) * 1e3 / n_upd
 
-    # cfg5 share of one GPU: 8 independent agents (sweep INDEX runs), each its own Engine/stream/graph,
-    # overlapping on the device; replicas only, no communication
-    agents = [make_agent(rb.Engine(local_rank)) for _ in range(8)]
+    # cfg5 share of one GPU: 8 independent agents (sweep INDEX runs, main_concurrent.py:64-81), each with its own
+    # handles / streams / graph, overlapping on the device; replicas only, no communication
+    agents = [kl_networks.ReverseKLNetwork(None, None, kl_config(rb.Engine(local_rank), 3, 1, 2.0, B1, 64, 200, 200))
+              for _ in range(8)]
 
-    def sweep_step():
+    def sweep_step(i):
         for g in agents:
-            g.set_inputs(s=s1, a=a1, y=y1, mean=m1, log_std=l1, v=v1)
-            g.launch()
-        return sum(float(g.wait()["loss_b"][0]) for g in agents)
+            g.update_network_async(*batches1[i % 8])
+            g.update_target_network()
+        return sum(float(g.wait()[0]) for g in agents)
 
-    for _ in range(10):
-        sweep_step()
+    for i in range(10):
+        sweep_step(i)
     torch.cuda.synchronize()
     n_sw = 100
     t0 = time.perf_counter()
-    for _ in range(n_sw):
-        sweep_step()
+    for i in range(n_sw):
+        sweep_step(i)
     torch.cuda.synchronize()
     sweep_ms = (time.perf_counter() - t0) * 1e3 / n_sw
+
+    # cfg4, the full ForwardKL update_network on this rank's B=4096 minibatch with the synthetic [N,A] grid
+    # (q/v/pi networks 400-300, three backward passes and Adam steps; tensor-core grid evaluation inside)
+    torch.manual_seed(1)
+    ag4 = kl_networks.ForwardKLNetwork(None, None, kl_config(rb.Engine(local_rank), S, A, 1.0, B, 64, H1, H2,
+                                                               integration_grid=(a_np, w_np), precision=prec))
+    b4 = (s_np, rng_in.uniform(-1, 1, (B, A)).astype(np.float32), np.roll(s_np, 1, axis=0),
+          rng_in.randn(B).astype(np.float32), np.full(B, 0.99, np.float32))
+    for _ in range(3):
+        ag4.update_network(*b4)
+        ag4.update_target_network()
+    torch.cuda.synchronize()
+    n4 = 20
+    t0 = time.perf_counter()
+    for _ in range(n4):
+        ag4.update_network(*b4)
+        ag4.update_target_network()
+    torch.cuda.synchronize()
+    cfg4_full_ms = (time.perf_counter() - t0) * 1e3 / n4
 
     # ---- max over ranks ----
     tm = torch.tensor([ms_total, e2e_ms, k1_ms, upd_ms, e2e_wall_ms], dtype=torch.float64, device=dev)
@@ -461,13 +481,18 @@ def run_b200(args, rank, local_rank, world):
                       "agent_updates_per_sec": world * 1e3 / (ms_total / args.steps + upd_ms),
                       "agent_update_definition": "cfg4 per rank: critic regression step (grads + all-reduce + Adam) "
                                                  "+ sampled-action evaluation + ForwardKL policy reduction",
+                      "cfg4_full_update_ms": cfg4_full_ms, "cfg4_full_updates_per_sec": 1e3 / cfg4_full_ms,
+                      "cfg4_full_update_definition": "per rank, no gradient all-reduce: kl_networks.ForwardKLNetwork.update_network + "
+                                                     "update_target_network on B=4096 (q, v, pi networks 400-300, grid N=1024, "
+                                                     "three backward passes + Adam steps), numpy minibatch in, losses out, one CUDA graph",
                       "cfg1_update_ms": cfg1_ms, "cfg1_updates_per_sec": 1e3 / cfg1_ms,
-                      "cfg1_definition": "B=32 N=62 S=3 A=1 200-200 (README command shape), host-synchronous update through "
-                                         "steps.GridAgentUpdateStep: inputs from host, one CUDA-graph launch (critic regression "
-                                         "step + operand repack + grid eval + ReverseKL reduction), outputs read on the host",
+                      "cfg1_definition": "README command shape (Pendulum ReverseKL: B=32 N=62 S=3 A=1 200-200): one FULL agent update "
+                                         "through kl_networks.ReverseKLNetwork.update_network + update_target_network (q, v, pi "
+                                         "networks, three Adam steps, Polyak), numpy minibatch in, losses out, host-synchronous, "
+                                         "one CUDA-graph launch per update",
                       "cfg5_sweep8_updates_per_sec": world * 8 * 1e3 / sweep_ms, "cfg5_sweep8_ms_per_round": sweep_ms,
-                      "cfg5_definition": "8 independent cfg1 agents per GPU (own Engine, stream and graph each), one update "
-                                         "each per round, host-synchronous per round; replicas only",
+                      "cfg5_definition": "8 independent cfg1 agents per GPU (own handles, streams and graph each), one full update "
+                                         "each per round, launched back to back then awaited; replicas only",
                       "critic_update_rows_per_rank": B,
                       "critic_update_allreduce": "nccl sum of theta_Q grads" if world > 1 else "none (1 rank)"},
         }

@@ -268,6 +268,37 @@ int rlc_policy_head_grad(rlc_handle* h, const float* head, int B, int A, float l
                          float entropy_scale, int B_total, float* dhead_out, float* loss_out,
                          void* stream);
 
+/* ---- Actor-Expert actor side fused with the sampled-action path ----------------
+ * sample_action (ae_network.py:461-496, ae_actor_network.py:310-341) with the draws supplied:
+ * comp_u[B,N] in [0,1) picks the component as numpy's RandomState.choice(M, N, p=alpha) does
+ * (cdf = cumsum(p)/sum; searchsorted(cdf, u, 'right'); equal_modal != 0: floor(u*M), alpha may be NULL),
+ * normal[B,N,A] ~ N(0,1): action = clip(mean[idx] + sigma[idx] * normal, amin, amax) in float64, cast to
+ * fp32.  The first n_uniform samples of every state are amin + (amax-amin) * uni_u[B,n_uniform,A]
+ * (use_uniform_sampling, :489-493).  alpha[B,M], mean/sigma[B,M,A], M <= 8.  comp_out[B,N] int32 or NULL. */
+int rlc_mixture_sample(rlc_handle* h, const float* alpha, const float* mean, const float* sigma, int B,
+                       int M, int A, int N, int equal_modal, const float* comp_u, const float* normal,
+                       const float* amin, const float* amax, int n_uniform, const float* uni_u,
+                       float* actions_out, int32_t* comp_out, void* stream);
+/* The expert step of ActorExpert.update_network (ActorExpert.py:162-181) in one launch: sample as above,
+ * predict_q on the B*N stack through the (hoisted) T-mid critic, per-state argsort()[::-1][:k], elite
+ * gather.  idx_out[B,k] int64; optional: actions_out[B,N,A], q_out[B,N], q_sel_out[B,k],
+ * elites_out[B,k,A].  T-mid critics, A <= 8, k <= 64. */
+int rlc_ae_expert_step(rlc_handle* h, const rlc_critic* c, const float* s, int B, int N, int k,
+                       const float* alpha, const float* mean, const float* sigma, int M,
+                       int equal_modal, const float* comp_u, const float* normal, const float* amin,
+                       const float* amax, int n_uniform, const float* uni_u, float* actions_out,
+                       float* q_out, int64_t* idx_out, float* q_sel_out, float* elites_out,
+                       void* stream);
+/* get_lossfunc (ae_network.py:262-278) on the elites actions[B,k,A] (state b's mixture against its k
+ * elites; the reference repeats the state k times, ActorExpert.py:179-182):
+ * loss[1] = mean over B_total*k rows of -log(clip(sum_m w_m prod_a N(y_a; mean, sigma), 1e-30, 1e30)),
+ * w = alpha or 1/M; gradients of that loss wrt alpha[B,M], mean[B,M,A], sigma[B,M,A] (any output may be
+ * NULL); nll_out[B,k] per-row values. */
+int rlc_mixture_nll(rlc_handle* h, const float* alpha, const float* mean, const float* sigma,
+                    const float* actions, int B, int M, int A, int k, int equal_modal, int B_total,
+                    float* loss_out, float* nll_out, float* dalpha_out, float* dmean_out,
+                    float* dsigma_out, void* stream);
+
 /* ---- replay minibatch gather (row a17) ---------------------------------------------------
  * map(np.array, zip(*batch)) of ReplayBuffer.sample_batch (utils/replaybuffer.py:32-37) over a
  * device-resident struct-of-arrays ring: state[cap,S], action[cap,A], reward[cap],

@@ -744,3 +744,72 @@ def bimodal_reward(action, maxima=(-0.6, 0.6), stddev=(0.2, 0.2), height=(1.0, 1
     for eq_var1; the variants differ in maxima/stddev/height)."""
     a = np.asarray(action, np.float64)
     return sum(h * np.exp(-0.5 * ((a - mx) / sd) ** 2) for mx, sd, h in zip(maxima, stddev, height))
+
+
+# --------------------------------------------------------------------------------------
+# Actor-Expert actor side (SURVEY 8f N1): mixture sampling and the mixture NLL on the elites
+# --------------------------------------------------------------------------------------
+
+def mixture_pick(alpha, comp_u, equal_modal=False):
+    """Component indices of ``rng.choice(M, N, p=alpha_b)`` (ae_network.py:483-486) given the uniforms numpy
+    draws for it: numpy's legacy ``choice`` computes cdf = cumsum(p); cdf /= cdf[-1] and returns
+    ``cdf.searchsorted(random_sample(N), side='right')`` (float64).  ``equal_modal``: ``rng.choice(M, N)``
+    is ``randint`` in numpy (a different stream); with supplied uniforms it is restated as floor(u*M).
+    alpha [B,M], comp_u [B,N] -> idx [B,N] int64."""
+    alpha = np.asarray(alpha, np.float64)
+    u = np.asarray(comp_u, np.float64)
+    B, M = alpha.shape
+    if equal_modal:
+        return np.minimum((u * M).astype(np.int64), M - 1)
+    idx = np.empty(u.shape, np.int64)
+    for b in range(B):
+        cdf = np.cumsum(alpha[b])
+        cdf /= cdf[-1]
+        idx[b] = np.minimum(cdf.searchsorted(u[b], side="right"), M - 1)
+    return idx
+
+
+def mixture_sample(alpha, mean, sigma, comp_u, normal, a_min, a_max, equal_modal=False, uni_u=None):
+    """``sample_action`` of the Actor-Expert networks (ae_network.py:461-496; ae_actor_network.py:310-341)
+    with the draws supplied: ``np.clip(rng.normal(m[idx], s[idx]), action_min, action_max)`` -- numpy's
+    ``normal(loc, scale)`` is loc + scale * N(0,1) in float64 -- then the first ``uni_u.shape[1]`` samples of
+    every state replaced by ``rng.uniform(action_min, action_max)`` = low + (high-low)*u (:489-493).
+    mean/sigma [B,M,A] (float32, as TF returns them), normal [B,N,A] -> (actions [B,N,A] float64, idx)."""
+    idx = mixture_pick(alpha, comp_u, equal_modal)
+    mean, sigma = np.asarray(mean, np.float64), np.asarray(sigma, np.float64)
+    B = mean.shape[0]
+    rows = np.arange(B)[:, None]
+    act = mean[rows, idx] + sigma[rows, idx] * np.asarray(normal, np.float64)
+    lo, hi = np.asarray(a_min, np.float64), np.asarray(a_max, np.float64)
+    act = np.clip(act, lo, hi)
+    if uni_u is not None and np.asarray(uni_u).shape[1] > 0:
+        u = np.asarray(uni_u, np.float64)
+        act[:, :u.shape[1]] = lo + (hi - lo) * u
+    return act, idx
+
+
+def mixture_nll(alpha, mean, sigma, actions, equal_modal=False, b_total=None):
+    """``get_lossfunc`` (ae_network.py:262-278, tf_normal :230-243) on the elite actions [B,k,A] (the reference
+    repeats each state k times, ActorExpert.py:179-182): density_m = prod_a sqrt(1/(2 pi s^2)) exp(-(y-m)^2/(2 s^2)),
+    mix = sum_m w_m density_m (w = alpha or 1/M), loss = mean over the B*k rows of -log(clip(mix, 1e-30, 1e30)).
+    Returns (loss, nll [B,k], dalpha [B,M], dmean [B,M,A], dsigma [B,M,A]) -- gradients of the loss wrt the
+    mixture parameters the actor network outputs (float64)."""
+    alpha, mean, sigma = (np.asarray(x, np.float64) for x in (alpha, mean, sigma))
+    y = np.asarray(actions, np.float64)
+    B, k, A = y.shape
+    M = alpha.shape[1]
+    R = float((b_total or B) * k)
+    d = y[:, :, None, :] - mean[:, None, :, :]                               # [B,k,M,A]
+    s = sigma[:, None, :, :]
+    dens = np.prod(np.sqrt(1.0 / (2 * np.pi * s * s)) * np.exp(-(d * d) / (2 * s * s)), axis=3)   # [B,k,M]
+    w = np.full((B, 1, M), 1.0 / M) if equal_modal else alpha[:, None, :]
+    mix = (w * dens).sum(2)                                                  # [B,k]
+    inside = (mix >= 1e-30) & (mix <= 1e30)
+    nll = -np.log(np.clip(mix, 1e-30, 1e30))
+    loss = nll.sum() / R
+    g = np.where(inside, -1.0 / np.where(inside, mix, 1.0), 0.0) / R         # dloss/dmix  [B,k]
+    dalpha = np.zeros_like(alpha) if equal_modal else (g[:, :, None] * dens).sum(1)
+    gd = g[:, :, None] * w * dens                                            # dloss/ddens * dens  [B,k,M]
+    dmean = (gd[..., None] * d / (s * s)).sum(1)
+    dsigma = (gd[..., None] * (d * d / (s ** 3) - 1.0 / s)).sum(1)
+    return loss, nll, dalpha, dmean, dsigma

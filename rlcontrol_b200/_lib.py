@@ -75,6 +75,10 @@ SIGNATURES = {
     "rlc_policy_evaluate": (_i, [_p, _p, _p, _i, _i, _f, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
     "rlc_kl_targets": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _i, _p, _p, _p, _p]),
     "rlc_policy_head_grad": (_i, [_p, _p, _i, _i, _f, _f, _i, _p, _p, _p, _p, _p, _p, _f, _i, _p, _p, _p]),
+    "rlc_mixture_sample": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p]),
+    "rlc_ae_expert_step": (_i, [_p, _cr, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p,
+                                _p, _p, _p]),
+    "rlc_mixture_nll": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "rlc_replay_gather": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p]),
     "rlc_replay_scatter": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p]),
 }

@@ -163,6 +163,45 @@ class Engine:
                                              _ptr(loss_b), _ptr(dm), _ptr(ds), _ptr(lp), _stream()))
         return loss_b, dm, ds, lp
 
+    # ------------------------------------------------------------------ Actor-Expert actor side (N1)
+    def mixture_sample(self, alpha, mean, sigma, comp_u, normal, a_min, a_max, equal_modal: bool = False,
+                       uni_u=None, want_comp: bool = False):
+        """``sample_action`` of the AE networks with the draws supplied (ae_network.py:461-496).
+        alpha [B,M] (None with equal_modal), mean/sigma [B,M,A], comp_u [B,N], normal [B,N,A];
+        uni_u [B,n_uniform,A] optional.  Returns actions [B,N,A] (and comp [B,N] int32)."""
+        dev = self.device
+        mean, sigma, comp_u, normal = (_f32(x, dev) for x in (mean, sigma, comp_u, normal))
+        alpha = None if alpha is None else _f32(alpha, dev)
+        B, M, A = mean.shape
+        N = comp_u.shape[1]
+        amin = _f32(np.broadcast_to(np.asarray(a_min, np.float64), (A,)), dev)
+        amax = _f32(np.broadcast_to(np.asarray(a_max, np.float64), (A,)), dev)
+        uni = None if uni_u is None else _f32(uni_u, dev)
+        n_uni = 0 if uni is None else int(uni.shape[1])
+        acts = torch.empty((B, N, A), dtype=torch.float32, device=dev)
+        comp = torch.empty((B, N), dtype=torch.int32, device=dev) if want_comp else None
+        check(self.lib.rlc_mixture_sample(self.h, _ptr(alpha), _ptr(mean), _ptr(sigma), B, M, A, N,
+                                          int(bool(equal_modal)), _ptr(comp_u), _ptr(normal), _ptr(amin),
+                                          _ptr(amax), n_uni, _ptr(uni), _ptr(acts), _ptr(comp), _stream()))
+        return (acts, comp) if want_comp else acts
+
+    def mixture_nll(self, alpha, mean, sigma, actions, equal_modal: bool = False, b_total: Optional[int] = None):
+        """``get_lossfunc`` on the elites (ae_network.py:262-278).  actions [B,k,A].
+        Returns (loss [1], nll [B,k], dalpha [B,M], dmean [B,M,A], dsigma [B,M,A])."""
+        dev = self.device
+        mean, sigma, actions = (_f32(x, dev) for x in (mean, sigma, actions))
+        alpha = None if alpha is None else _f32(alpha, dev)
+        B, M, A = mean.shape
+        k = actions.shape[1]
+        loss = torch.empty((1,), dtype=torch.float32, device=dev)
+        nll = torch.empty((B, k), dtype=torch.float32, device=dev)
+        da = torch.zeros((B, M), dtype=torch.float32, device=dev)
+        dm, ds = torch.empty_like(mean), torch.empty_like(sigma)
+        check(self.lib.rlc_mixture_nll(self.h, _ptr(alpha), _ptr(mean), _ptr(sigma), _ptr(actions), B, M, A, k,
+                                       int(bool(equal_modal)), int(b_total or B), _ptr(loss), _ptr(nll), _ptr(da),
+                                       _ptr(dm), _ptr(ds), _stream()))
+        return loss, nll, da, dm, ds
+
     # ------------------------------------------------------------------ FKL / RKL B-row pieces
     def policy_evaluate(self, head, eps, action_scale: float, log_std_min: float = -20.0,
                         log_std_max: float = 2.0, out=None):
@@ -404,6 +443,35 @@ class Critic:
                                             int(b_total or B), _ptr(grad_out), _ptr(loss_out), _ptr(q_out),
                                             _stream()))
         return grad_out
+
+    def ae_expert_step(self, s, k: int, alpha, mean, sigma, comp_u, normal, a_min, a_max,
+                       equal_modal: bool = False, uni_u=None, want_actions: bool = False, want_q: bool = False):
+        """The expert step of ``ActorExpert.update_network`` (ActorExpert.py:162-181) in one launch: sample N
+        actions per state from the actor's mixture (draws supplied), Q through this (T-mid) critic,
+        per-state top-k, elite gather.  Returns dict(idx [B,k] int64, q_sel [B,k], elites [B,k,A]
+        [, actions [B,N,A]] [, q [B,N]])."""
+        dev = self.eng.device
+        s, mean, sigma, comp_u, normal = (_f32(x, dev) for x in (s, mean, sigma, comp_u, normal))
+        alpha = None if alpha is None else _f32(alpha, dev)
+        B, M, A = mean.shape
+        N = comp_u.shape[1]
+        amin = _f32(np.broadcast_to(np.asarray(a_min, np.float64), (A,)), dev)
+        amax = _f32(np.broadcast_to(np.asarray(a_max, np.float64), (A,)), dev)
+        uni = None if uni_u is None else _f32(uni_u, dev)
+        n_uni = 0 if uni is None else int(uni.shape[1])
+        out = dict(idx=torch.empty((B, k), dtype=torch.int64, device=dev),
+                   q_sel=torch.empty((B, k), dtype=torch.float32, device=dev),
+                   elites=torch.empty((B, k, A), dtype=torch.float32, device=dev))
+        if want_actions:
+            out["actions"] = torch.empty((B, N, A), dtype=torch.float32, device=dev)
+        if want_q:
+            out["q"] = torch.empty((B, N), dtype=torch.float32, device=dev)
+        check(self.eng.lib.rlc_ae_expert_step(self.eng.h, C.byref(self._desc), _ptr(s), B, N, int(k), _ptr(alpha),
+                                              _ptr(mean), _ptr(sigma), M, int(bool(equal_modal)), _ptr(comp_u),
+                                              _ptr(normal), _ptr(amin), _ptr(amax), n_uni, _ptr(uni),
+                                              _ptr(out.get("actions")), _ptr(out.get("q")), _ptr(out["idx"]),
+                                              _ptr(out["q_sel"]), _ptr(out["elites"]), _stream()))
+        return out
 
     # ------------------------------------------------------------------ CEM (K4)
     def cem(self, s, u0, noise, comp_u, top_m: int, num_modal: int, a_min, a_max,

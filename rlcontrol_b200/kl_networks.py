@@ -136,7 +136,10 @@ class _KLNetwork(object):
         self.q_opt = _Adam(self.eng, self.critic.theta, self.learning_rate[1])
         self.v_opt = _Adam(self.eng_v, self.v.theta, self.learning_rate[1])
         # ---- integration grid (:58-102)
-        acts, w = integration_grid(A, self.action_scale, getattr(config, "N_param", 64), getattr(config, "l_param", 6))
+        grid = getattr(config, "integration_grid", None)      # optional (actions [N,A], weights [N]) override
+        acts, w = grid if grid is not None else integration_grid(A, self.action_scale, getattr(config, "N_param", 64),
+                                                                 getattr(config, "l_param", 6))
+        acts, w = np.asarray(acts, np.float32).reshape(-1, A), np.asarray(w, np.float32).reshape(-1)
         self.intgrl_actions, self.intgrl_weights = _f32(acts, dev), _f32(w, dev)
         self.intgrl_actions_len = int(acts.shape[0])
         self.device = dev
@@ -179,6 +182,7 @@ class _KLNetwork(object):
                 off += n
             return out
         st.h, st.d = views(st.in_host), views(st.in_dev)
+        st.h_np = {k: v.numpy() for k, v in st.h.items()}      # numpy views of the pinned staging buffer
         st.out_host = torch.zeros((4,), dtype=torch.float32).pin_memory()       # q_loss, v_loss, pi_loss, -
         st.out_dev = torch.zeros((4,), dtype=torch.float32, device=dev)
         f = lambda *sh: torch.zeros(sh, dtype=torch.float32, device=dev)
@@ -297,29 +301,49 @@ class _KLNetwork(object):
             self._steps[B] = st
         return st
 
-    def update_network(self, state_batch, action_batch, next_state_batch, reward_batch, gamma_batch, eps=None):
+    def update_network_async(self, state_batch, action_batch, next_state_batch, reward_batch, gamma_batch, eps=None):
+        """Stage the minibatch and launch the update without waiting for it (independent agents of a sweep
+        overlap on one GPU this way: launch them all, then :meth:`wait` each)."""
         s = np.asarray(state_batch, np.float32)
         B = s.shape[0]
         st = self._step_for(B)
-        h = st.h
+        h = st.h_np
         if eps is None:
             # the draws behind normal.sample() in pi_net.evaluate (:305-309): loc + scale * N(0,1), global CPU generator
             eps = torch.randn(B, self.action_dim)
-        h["s"].copy_(torch.from_numpy(s).view(h["s"].shape))
-        for k, x in (("a", action_batch), ("s2", next_state_batch), ("r", reward_batch), ("g", gamma_batch), ("eps", eps)):
-            h[k].copy_(torch.as_tensor(np.asarray(x, np.float32) if not isinstance(x, torch.Tensor) else x,
-                                       dtype=torch.float32).reshape(h[k].shape))
+        if isinstance(eps, torch.Tensor):
+            eps = eps.numpy()
+        # float64 -> float32 at the boundary, like torch.FloatTensor(x) in the reference (:125-129)
+        for k, x in (("s", s), ("a", action_batch), ("s2", next_state_batch), ("r", reward_batch), ("g", gamma_batch),
+                     ("eps", eps)):
+            np.copyto(h[k], np.asarray(x).reshape(h[k].shape), casting="same_kind")
         with torch.cuda.stream(st.stream):
             if st.graph is not None:
                 st.graph.replay()
             else:
                 self._enqueue(st, B)
+        self._pending = st
+
+    def wait(self):
+        """Block until the launched update has finished; returns (q_loss, v_loss, pi_loss)."""
+        st = self._pending
         st.stream.synchronize()
-        self.last_losses = st.out_host[:3].clone().numpy()       # (q_loss, v_loss, pi_loss)
+        self.last_losses = st.out_host[:3].clone().numpy()
+        return self.last_losses
+
+    def update_network(self, state_batch, action_batch, next_state_batch, reward_batch, gamma_batch, eps=None):
+        self.update_network_async(state_batch, action_batch, next_state_batch, reward_batch, gamma_batch, eps)
+        self.wait()
 
     def update_target_network(self):
-        # target_v <- (1 - tau) target_v + tau v   (:211-215)
-        self.eng_v.soft_update(self.target_v.theta, self.v.theta, self.tau)
+        # target_v <- (1 - tau) target_v + tau v   (:211-215); on the update's own stream so that it is ordered
+        # after a launched update and before the next one without any device-wide synchronisation
+        st = getattr(self, "_pending", None)
+        if st is None:
+            self.eng_v.soft_update(self.target_v.theta, self.v.theta, self.tau)
+        else:
+            with torch.cuda.stream(st.stream):
+                self.eng_v.soft_update(self.target_v.theta, self.v.theta, self.tau)
 
     # ------------------------------------------------------------------ acting
     def _evaluate(self, state_batch, eps):

@@ -230,6 +230,7 @@ class ActorExpertCritic(_TMidBase):
         l2 = getattr(config, "expert_l2_dim", getattr(config, "l2_dim", None))
         lr = config.learning_rate[1] if hasattr(config, "learning_rate") and np.ndim(config.learning_rate) else config.expert_lr
         self._build(sess, input_norm, config, l1, l2, lr)
+        self.rng = np.random.RandomState(config.random_seed)          # ae_network.py:20
         self.better_q_gd_alpha = getattr(config, "better_q_gd_alpha", 1e-2)
         self.better_q_gd_max_steps = getattr(config, "better_q_gd_max_steps", 10)
         self.better_q_gd_stop = getattr(config, "better_q_gd_stop", 1e-3)
@@ -259,6 +260,29 @@ class ActorExpertCritic(_TMidBase):
         q = self.critic.eval(_np(state_batch), a, self.precision)
         idx, _, elites = self.eng.topk(q, int(k), a)
         return q.cpu().numpy(), idx.cpu().numpy(), elites.cpu().numpy()
+
+    def sample_and_select_elites(self, state_batch, alpha, mean, sigma, k, num_samples, rng=None,
+                                 equal_modal_selection=False, comp_u=None, normal=None):
+        """The whole actor-update preamble of ``ActorExpert.update_network`` (ActorExpert.py:162-181:
+        ``sample_action`` ae_network.py:461-496 -> ``predict_q`` -> per-state ``argsort()[::-1][:k]`` -> elite
+        gather) as ONE launch, from the actor's mixture outputs ``alpha [B,M] | [B,M,1]``, ``mean, sigma [B,M,A]``.
+        The draws come from ``rng`` exactly as the reference consumes them per state (``choice`` uniforms, then
+        ``normal``), or are passed in.  Returns (elites [B,k,A], idx [B,k], sampled actions [B,N,A])."""
+        mean = np.asarray(mean, np.float32)
+        B, M, A = mean.shape
+        N = int(num_samples)
+        if comp_u is None:
+            rng = self.rng if rng is None else rng
+            comp_u, normal = np.empty((B, N)), np.empty((B, N, A))
+            for b in range(B):                                  # same per-state order as the list comprehensions
+                comp_u[b] = rng.random_sample(N)
+            for b in range(B):
+                normal[b] = rng.standard_normal((N, A))
+        alpha = None if alpha is None else np.asarray(alpha, np.float32).reshape(B, M)
+        out = self.critic.ae_expert_step(_np(state_batch), int(k), alpha, mean, _np(sigma), _np(comp_u), _np(normal),
+                                         self.action_min, self.action_max, equal_modal=equal_modal_selection,
+                                         want_actions=True)
+        return out["elites"].cpu().numpy(), out["idx"].cpu().numpy(), out["actions"].cpu().numpy()
 
 
 class SoftQNetwork(object):

@@ -320,3 +320,57 @@ def test_torch_port_get_logprob_matches_reference(A):
     k = lambda n: torch.as_tensor(g[f"A{A}_{n}"])
     lp = ot.get_logprob_port(k("mean"), k("log_std"), k("actions"), float(g[f"A{A}_scale"]))
     np.testing.assert_allclose(lp.numpy(), g[f"A{A}_logp"], rtol=1e-6, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# Actor-Expert actor side (N1): the sampling restatement is pinned on numpy's own RandomState
+# ---------------------------------------------------------------------------------------------
+def test_mixture_sample_reproduces_numpy_choice_and_normal():
+    """ae_network.py:483-488 calls rng.choice(M, N, p=alpha_b) then rng.normal(m[idx], s[idx]) per state; feeding
+    the uniforms / normals numpy itself would draw (same RandomState) reproduces its output bit for bit."""
+    B, M, A, N = 4, 3, 2, 60
+    r = np.random.RandomState(7)
+    alpha = r.dirichlet(np.ones(M), B)
+    mean = r.randn(B, M, A).astype(np.float32)
+    sig = (0.2 + r.rand(B, M, A)).astype(np.float32)
+    rng1, rng2 = np.random.RandomState(5), np.random.RandomState(5)
+    ref, ref_idx, us, zs = [], [], [], []
+    for b in range(B):
+        idx = rng1.choice(M, N, p=alpha[b])
+        ref_idx.append(idx)
+        ref.append(np.clip(rng1.normal(mean[b][idx], sig[b][idx]), -1.0, 1.0))
+        us.append(rng2.random_sample(N))
+        zs.append(rng2.standard_normal((N, A)))
+    act, idx = onp.mixture_sample(alpha, mean, sig, np.array(us), np.array(zs), [-1, -1], [1, 1])
+    np.testing.assert_array_equal(idx, np.array(ref_idx))
+    np.testing.assert_array_equal(act, np.array(ref))
+    # uniform replacement of the first samples (ae_network.py:489-493): low + (high-low)*u
+    uu = r.rand(B, 5, A)
+    act2, _ = onp.mixture_sample(alpha, mean, sig, np.array(us), np.array(zs), [-1, -2], [1, 2], uni_u=uu)
+    np.testing.assert_allclose(act2[:, :5], np.array([-1, -2]) + np.array([2, 4]) * uu)
+    eq = onp.mixture_pick(alpha, np.array(us), equal_modal=True)
+    assert eq.min() >= 0 and eq.max() <= M - 1
+
+
+def test_mixture_nll_gradients_by_finite_differences():
+    r = np.random.RandomState(3)
+    B, M, A, k = 3, 2, 2, 5
+    alpha = r.dirichlet(np.ones(M), B)
+    mean, sig = r.randn(B, M, A) * 0.5, 0.3 + r.rand(B, M, A)
+    y = r.uniform(-1, 1, (B, k, A))
+    loss, nll, da, dm, ds = onp.mixture_nll(alpha, mean, sig, y)
+    assert nll.shape == (B, k) and abs(loss - nll.mean()) < 1e-12
+    eps = 1e-6
+    for arr, grad, which in ((alpha, da, 0), (mean, dm, 1), (sig, ds, 2)):
+        it = np.nditer(arr, flags=["multi_index"])
+        for _ in it:
+            pert = [alpha.copy(), mean.copy(), sig.copy()]
+            pert[which][it.multi_index] += eps
+            num = (onp.mixture_nll(*pert, y)[0] - loss) / eps
+            assert abs(num - grad[it.multi_index]) < 1e-4 * max(1.0, abs(num))
+    # the single-Gaussian closed form: -log N(y; m, s)
+    l1 = onp.mixture_nll(np.ones((1, 1)), [[[0.3]]], [[[0.5]]], [[[0.1]]])[0]
+    assert abs(l1 - (0.5 * np.log(2 * np.pi * 0.25) + 0.04 / 0.5)) < 1e-12
+    # underflow is clipped at 1e-30 and carries no gradient (tf.clip_by_value, ae_network.py:276)
+    lo = onp.mixture_nll(np.ones((1, 1)), [[[0.0]]], [[[0.01]]], [[[5.0]]])
+    assert abs(lo[0] - (-np.log(1e-30))) < 1e-9 and np.all(lo[3] == 0)
