@@ -299,6 +299,19 @@ int rlc_mixture_nll(rlc_handle* h, const float* alpha, const float* mean, const 
                     float* loss_out, float* nll_out, float* dalpha_out, float* dmean_out,
                     float* dsigma_out, void* stream);
 
+/* ---- Soft-Q-learning SVGD actor step -----------------------------------------
+ * action_gradients of sql_network.py:96-117 with adaptive_isotropic_gaussian_kernel
+ * (utils/sql_kernel.py:7-69): fixed[B,Kf,A] / updated[B,Ku,A] = the two halves of the policy's particles
+ * (:176-179); grad_log_p = dQ/da(s, fixed) + d/da sum log(1 - a^2 + eps) (:101-105); bandwidth
+ * h = max(median/log(Kf), h_min), median = (Kf*Ku//2+1)-th largest squared distance;
+ * grad_out[B,Ku,A] = mean_i(kappa grad_log_p + dkappa/dfixed) -- the grad_ys the reference back-propagates
+ * through the policy network (:120).  dqda_scratch[B,Kf,A] is caller-owned scratch (holds dQ/da on return).
+ * Optional: q_fixed_out[B,Kf], kappa_out[B,Kf,Ku], h_out[B].  Kf*Ku <= 4096, A <= 16. */
+int rlc_svgd_action_grads(rlc_handle* h, const rlc_critic* c, const float* s, int B, const float* fixed,
+                          int Kf, const float* updated, int Ku, float h_min, float eps,
+                          float* dqda_scratch, float* grad_out, float* q_fixed_out, float* kappa_out,
+                          float* h_out, void* stream);
+
 /* ---- replay minibatch gather (row a17) ---------------------------------------------------
  * map(np.array, zip(*batch)) of ReplayBuffer.sample_batch (utils/replaybuffer.py:32-37) over a
  * device-resident struct-of-arrays ring: state[cap,S], action[cap,A], reward[cap],

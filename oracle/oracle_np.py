@@ -813,3 +813,33 @@ def mixture_nll(alpha, mean, sigma, actions, equal_modal=False, b_total=None):
     dmean = (gd[..., None] * d / (s * s)).sum(1)
     dsigma = (gd[..., None] * (d * d / (s ** 3) - 1.0 / s)).sum(1)
     return loss, nll, dalpha, dmean, dsigma
+
+
+# --------------------------------------------------------------------------------------
+# Soft-Q-learning SVGD.  TF is not installable: parity UNPINNED, restated
+# from the explicit formulas of utils/sql_kernel.py:7-69 and sql_network.py:96-117.
+# --------------------------------------------------------------------------------------
+
+def adaptive_isotropic_gaussian_kernel(xs, ys, h_min=1e-3, dtype=np.float64):
+    """utils/sql_kernel.py:7-69: xs [B,Kx,D], ys [B,Ky,D] -> (kappa [B,Kx,Ky], dkappa/dxs [B,Kx,Ky,D], h [B]).
+    median = last of top_k(dist_sq, k = Kx*Ky//2 + 1) (the (k)-th largest); h = max(median/log(Kx), h_min)."""
+    xs, ys = np.asarray(xs, dtype), np.asarray(ys, dtype)
+    B, Kx, D = xs.shape
+    Ky = ys.shape[1]
+    diff = xs[:, :, None, :] - ys[:, None, :, :]
+    dist = (diff ** 2).sum(-1)
+    flat = np.sort(dist.reshape(B, Kx * Ky), axis=1)[:, ::-1]
+    med = flat[:, Kx * Ky // 2]
+    h = np.maximum(med / dtype(np.log(Kx)), dtype(h_min))
+    kappa = np.exp(-dist / h[:, None, None])
+    grad = -2 * diff / h[:, None, None, None] * kappa[..., None]
+    return kappa, grad, h
+
+
+def svgd_action_gradients(dqda, fixed, updated, h_min=1e-3, eps=1e-6, dtype=np.float64):
+    """sql_network.py:100-114: log_p = Q + sum log(1 - a^2 + EPS) on the fixed particles,
+    action_gradients = mean_i(kappa * grad_log_p + dkappa) -> [B,Ku,A]."""
+    fixed = np.asarray(fixed, dtype)
+    glp = np.asarray(dqda, dtype) + (-2 * fixed) / (1 - fixed ** 2 + dtype(eps))
+    kappa, kgrad, h = adaptive_isotropic_gaussian_kernel(fixed, updated, h_min, dtype)
+    return (kappa[..., None] * glp[:, :, None, :] + kgrad).mean(axis=1), kappa, h

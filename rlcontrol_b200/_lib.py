@@ -79,6 +79,7 @@ SIGNATURES = {
     "rlc_ae_expert_step": (_i, [_p, _cr, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p,
                                 _p, _p, _p]),
     "rlc_mixture_nll": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "rlc_svgd_action_grads": (_i, [_p, _cr, _p, _i, _p, _i, _p, _i, _f, _f, _p, _p, _p, _p, _p, _p]),
     "rlc_replay_gather": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p]),
     "rlc_replay_scatter": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p]),
 }

@@ -97,6 +97,11 @@ bool rlc_umma_supported(const rlc_handle* h, const rlc_critic* c, int B, int N);
 int rlc_tmid_state_term(rlc_handle* h, const rlc_critic* c, const float* s, int B, float* p_out,
                         cudaStream_t st);
 
+// dQ/da on R stacked rows, state row r/rep (critic_fp32.cu)
+int rlc_critic_grad_action_rep(rlc_handle* h, const rlc_critic* c, const float* s, int rep,
+                               const float* a, long long R, float* dqda_out, float* q_out,
+                               cudaStream_t st);
+
 // warp helpers
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -329,7 +329,7 @@ int rlc_eval_fp32(rlc_handle* h, const rlc_critic* c, const float* s, int B, con
 // X[R, in1] = T-in: [clip(s), a] ; T-mid: clip(s)
 __global__ void k_build_x(const float* __restrict__ s, const float* __restrict__ a, long long R,
                           int S, int A, int tin, const float* __restrict__ smin,
-                          const float* __restrict__ smax, float* __restrict__ X) {
+                          const float* __restrict__ smax, float* __restrict__ X, int rep) {
   const int K1 = tin ? S + A : S;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * K1) return;
@@ -337,7 +337,7 @@ __global__ void k_build_x(const float* __restrict__ s, const float* __restrict__
   const int k = (int)(i - r * K1);
   float v;
   if (k < S) {
-    v = s[r * S + k];
+    v = s[(r / rep) * S + k];  // rep > 1: every state row serves `rep` consecutive stacked rows
     if (smin) v = fminf(fmaxf(v, smin[k]), smax[k]);
   } else {
     v = a[r * A + (k - S)];
@@ -422,14 +422,14 @@ static TrainWs carve(const rlc_critic* c, long long R, float* base) {
 // Forward over R stacked rows storing pre-activations; then head.  y==nullptr -> dq=1 (dQ/da).
 static int forward_rows(rlc_handle* h, const rlc_critic* c, const float* s, const float* a,
                         long long R, const float* y, float inv_btotal, TrainWs& w, float* q_out,
-                        float* loss_acc, cudaStream_t st) {
+                        float* loss_acc, cudaStream_t st, int rep = 1) {
   const ThetaView t = theta_view(c->topology, c->S, c->A, c->H1, c->H2);
   const float* th = c->theta;
   const int tin = c->topology == RLC_TIN;
   {
     const long long n = R * t.in1;
     k_build_x<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s, a, R, c->S, c->A, tin, c->smin,
-                                                           c->smax, w.X);
+                                                           c->smax, w.X, rep);
     RLC_LAUNCH_CHECK(h);
   }
   GemmEpi e1{th + t.ob1, nullptr, 0, 0, 1.f};
@@ -456,23 +456,23 @@ static int forward_rows(rlc_handle* h, const rlc_critic* c, const float* s, cons
   return RLC_OK;
 }
 
-extern "C" int rlc_critic_grad_action(rlc_handle* h, const rlc_critic* c, const float* s,
-                                      const float* a, int R, float* dqda_out, float* q_out,
-                                      void* stream) {
-  RLC_REQUIRE(h && critic_ok(c) && s && a && dqda_out && R >= 0);
-  cudaStream_t st = (cudaStream_t)stream;
+// dQ/da on R stacked rows whose states repeat `rep` times (s has R/rep rows): rep = 1 is the plain
+// stacked form, rep = N the un-materialised B x N form (SQL's SVGD particles, sql_network.py:101-107).
+int rlc_critic_grad_action_rep(rlc_handle* h, const rlc_critic* c, const float* s, int rep,
+                               const float* a, long long R, float* dqda_out, float* q_out,
+                               cudaStream_t st) {
   if (R == 0) return RLC_OK;
   const ThetaView t = theta_view(c->topology, c->S, c->A, c->H1, c->H2);
   const float* th = c->theta;
-  const int CH = 16384;  // row chunk bounds the workspace
+  const long long CH = 16384LL / rep * rep > 0 ? 16384LL / rep * rep : rep;  // row chunk (a multiple of rep) bounds the workspace
   void* ws = nullptr;
   int rc = rlc_workspace(h, train_ws_bytes(c, R < CH ? R : CH), &ws);
   if (rc) return rc;
   for (long long r0 = 0; r0 < R; r0 += CH) {
     const long long n = (R - r0 < CH) ? (R - r0) : CH;
     TrainWs w = carve(c, n, (float*)ws);
-    rc = forward_rows(h, c, s + r0 * c->S, a + r0 * c->A, n, nullptr, 0.f, w,
-                      q_out ? q_out + r0 : nullptr, nullptr, st);
+    rc = forward_rows(h, c, s + (r0 / rep) * c->S, a + r0 * c->A, n, nullptr, 0.f, w,
+                      q_out ? q_out + r0 : nullptr, nullptr, st, rep);
     if (rc) return rc;
     GemmEpi e{nullptr, nullptr, 0, 0, 1.f};
     if (c->topology == RLC_TMID) {
@@ -491,6 +491,13 @@ extern "C" int rlc_critic_grad_action(rlc_handle* h, const rlc_critic* c, const 
     if (rc) return rc;
   }
   return RLC_OK;
+}
+
+extern "C" int rlc_critic_grad_action(rlc_handle* h, const rlc_critic* c, const float* s,
+                                      const float* a, int R, float* dqda_out, float* q_out,
+                                      void* stream) {
+  RLC_REQUIRE(h && critic_ok(c) && s && a && dqda_out && R >= 0);
+  return rlc_critic_grad_action_rep(h, c, s, 1, a, R, dqda_out, q_out, (cudaStream_t)stream);
 }
 
 extern "C" int rlc_critic_grads(rlc_handle* h, const rlc_critic* c, const float* s, const float* a,

@@ -473,6 +473,26 @@ class Critic:
                                               _ptr(out["q_sel"]), _ptr(out["elites"]), _stream()))
         return out
 
+    def svgd_action_grads(self, s, fixed, updated, h_min: float = 1e-3, eps: float = 1e-6, want_aux: bool = False):
+        """Soft-Q-learning SVGD direction (sql_network.py:96-117, utils/sql_kernel.py): fixed [B,Kf,A],
+        updated [B,Ku,A] -> action_gradients [B,Ku,A] (and dict(q_fixed, dqda, kappa, h) with want_aux)."""
+        dev = self.eng.device
+        s, fixed, updated = _f32(s, dev), _f32(fixed, dev), _f32(updated, dev)
+        B, Kf, A = fixed.shape
+        Ku = updated.shape[1]
+        dq = torch.empty((B, Kf, A), dtype=torch.float32, device=dev)
+        g = torch.empty((B, Ku, A), dtype=torch.float32, device=dev)
+        aux = dict(dqda=dq)
+        if want_aux:
+            aux.update(q_fixed=torch.empty((B, Kf), dtype=torch.float32, device=dev),
+                       kappa=torch.empty((B, Kf, Ku), dtype=torch.float32, device=dev),
+                       h=torch.empty((B,), dtype=torch.float32, device=dev))
+        check(self.eng.lib.rlc_svgd_action_grads(self.eng.h, C.byref(self._desc), _ptr(s), B, _ptr(fixed), Kf,
+                                                 _ptr(updated), Ku, float(h_min), float(eps), _ptr(dq), _ptr(g),
+                                                 _ptr(aux.get("q_fixed")), _ptr(aux.get("kappa")), _ptr(aux.get("h")),
+                                                 _stream()))
+        return (g, aux) if want_aux else g
+
     # ------------------------------------------------------------------ CEM (K4)
     def cem(self, s, u0, noise, comp_u, top_m: int, num_modal: int, a_min, a_max,
             want_idx: bool = False):

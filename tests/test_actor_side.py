@@ -119,3 +119,29 @@ def test_actor_expert_critic_sample_and_select(eng):
     q = net.predict_q(np.repeat(s, N, axis=0), acts.reshape(B * N, 1), True).reshape(B, N)
     agree = (onp.topk_desc(q, k) == idx).all(axis=1).mean()
     assert agree >= 0.9
+
+
+@pytest.mark.parametrize("S,A,H1,H2,B,Kf,Ku", [(3, 1, 200, 200, 32, 15, 15), (17, 6, 400, 300, 8, 16, 16), (2, 2, 24, 20, 5, 7, 3),
+                                                (4, 3, 16, 16, 1, 64, 64)])
+def test_svgd_action_gradients_match_oracle(eng, S, A, H1, H2, B, Kf, Ku):
+    """sql.json shape (kernel_n_particles 30, ratio 0.5 -> 15 + 15) and others: dQ/da on the B*Kf rows without
+    materialised states, median bandwidth, Stein direction."""
+    import rlcontrol_b200 as rb
+    rng = np.random.RandomState(Kf * 10 + A)
+    k1, k2 = 1 / np.sqrt(S + A), 1 / np.sqrt(H1)
+    u = lambda k, *sh: rng.uniform(-k, k, sh).astype(np.float32)
+    p = [u(k1, H1, S + A), u(k1, H1), u(k2, H2, H1), u(k2, H2), u(0.5, 1, H2), u(0.5, 1)]
+    cr = rb.Critic(eng, rb.TIN, S, A, H1, H2).load(*p, rb.LAYOUT_OUT_IN)
+    s = rng.randn(B, S).astype(np.float32)
+    parts = np.tanh(rng.randn(B, Kf + Ku, A)).astype(np.float32) * 0.98
+    fixed, updated = np.ascontiguousarray(parts[:, :Kf]), np.ascontiguousarray(parts[:, Kf:])
+    g, aux = cr.svgd_action_grads(s, fixed, updated, want_aux=True)
+    s_rows = np.repeat(s, Kf, axis=0)
+    dq_ref = onp.tin_dq_da(s_rows, fixed.reshape(B * Kf, A), p).reshape(B, Kf, A)
+    np.testing.assert_allclose(aux["dqda"].cpu().numpy(), dq_ref, rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(aux["q_fixed"].cpu().numpy(), onp.tin_forward(s_rows, fixed.reshape(B * Kf, A), *p, dtype=np.float64).reshape(B, Kf),
+                               rtol=2e-5, atol=2e-5)
+    ref, kap, h = onp.svgd_action_gradients(dq_ref, fixed, updated)
+    np.testing.assert_allclose(aux["h"].cpu().numpy(), h, rtol=1e-5)
+    np.testing.assert_allclose(aux["kappa"].cpu().numpy(), kap, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(g.cpu().numpy(), ref, rtol=2e-4, atol=2e-5 * max(1.0, np.abs(ref).max()))

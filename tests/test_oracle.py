@@ -374,3 +374,25 @@ def test_mixture_nll_gradients_by_finite_differences():
     # underflow is clipped at 1e-30 and carries no gradient (tf.clip_by_value, ae_network.py:276)
     lo = onp.mixture_nll(np.ones((1, 1)), [[[0.0]]], [[[0.01]]], [[[5.0]]])
     assert abs(lo[0] - (-np.log(1e-30))) < 1e-9 and np.all(lo[3] == 0)
+
+
+def test_svgd_kernel_restatement_properties():
+    """utils/sql_kernel.py: kappa in (0,1], kappa = 1 on coincident particles, the gradient is the analytic
+    derivative of kappa wrt xs at fixed bandwidth, and the bandwidth is median/log(Kx) floored at h_min."""
+    r = np.random.RandomState(0)
+    xs, ys = r.uniform(-1, 1, (3, 5, 2)), r.uniform(-1, 1, (3, 4, 2))
+    kap, grad, h = onp.adaptive_isotropic_gaussian_kernel(xs, ys)
+    assert kap.shape == (3, 5, 4) and grad.shape == (3, 5, 4, 2) and np.all((kap > 0) & (kap <= 1))
+    d = ((xs[:, :, None] - ys[:, None]) ** 2).sum(-1).reshape(3, -1)
+    np.testing.assert_allclose(h, np.sort(d, 1)[:, ::-1][:, 10] / np.log(5))      # 20 pairs: the 11th largest
+    e = 1e-6
+    x2 = xs.copy()
+    x2[1, 2, 0] += e
+    d2 = ((x2[:, :, None] - ys[:, None]) ** 2).sum(-1)
+    num = (np.exp(-d2[1, 2] / h[1]) - kap[1, 2]) / e
+    np.testing.assert_allclose(num, grad[1, 2, :, 0], rtol=1e-4, atol=1e-6)
+    twin = np.repeat(xs[:, :1], 2, axis=1)
+    same = onp.adaptive_isotropic_gaussian_kernel(twin, twin, h_min=0.5)
+    assert np.all(same[0] == 1.0) and np.all(same[2] == 0.5)                      # zero distances -> h_min floor
+    g, _, _ = onp.svgd_action_gradients(np.zeros((3, 5, 2)), xs * 0.5, ys * 0.5)
+    assert g.shape == (3, 4, 2) and np.all(np.isfinite(g))
