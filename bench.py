@@ -411,7 +411,8 @@ def run_b200(args, rank, local_rank, world):
     # (q/v/pi networks 400-300, three backward passes and Adam steps; tensor-core grid evaluation inside)
     torch.manual_seed(1)
     ag4 = kl_networks.ForwardKLNetwork(None, None, kl_config(rb.Engine(local_rank), S, A, 1.0, B, 64, H1, H2,
-                                                               integration_grid=(a_np, w_np), precision=prec))
+                                                               integration_grid=(a_np, w_np), precision=prec,
+                                                               world_size=world))
     b4 = (s_np, rng_in.uniform(-1, 1, (B, A)).astype(np.float32), np.roll(s_np, 1, axis=0),
           rng_in.randn(B).astype(np.float32), np.full(B, 0.99, np.float32))
     for _ in range(3):
@@ -425,6 +426,10 @@ def run_b200(args, rank, local_rank, world):
         ag4.update_target_network()
     torch.cuda.synchronize()
     cfg4_full_ms = (time.perf_counter() - t0) * 1e3 / n4
+    if world > 1:
+        tt = torch.tensor([cfg4_full_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        cfg4_full_ms = float(tt.cpu())
 
     # ---- max over ranks ----
     tm = torch.tensor([ms_total, e2e_ms, k1_ms, upd_ms, e2e_wall_ms], dtype=torch.float64, device=dev)
@@ -482,9 +487,12 @@ def run_b200(args, rank, local_rank, world):
                       "agent_update_definition": "cfg4 per rank: critic regression step (grads + all-reduce + Adam) "
                                                  "+ sampled-action evaluation + ForwardKL policy reduction",
                       "cfg4_full_update_ms": cfg4_full_ms, "cfg4_full_updates_per_sec": 1e3 / cfg4_full_ms,
-                      "cfg4_full_update_definition": "per rank, no gradient all-reduce: kl_networks.ForwardKLNetwork.update_network + "
-                                                     "update_target_network on B=4096 (q, v, pi networks 400-300, grid N=1024, "
-                                                     "three backward passes + Adam steps), numpy minibatch in, losses out, one CUDA graph",
+                      "cfg4_full_update_definition": "kl_networks.ForwardKLNetwork.update_network + update_target_network, B=4096 "
+                                                     "states per rank (q, v, pi networks 400-300, grid N=1024, three backward "
+                                                     "passes + Adam steps), numpy minibatch in, losses out; " +
+                                                     ("one CUDA graph" if world == 1 else
+                                                      "global batch %d sharded over %d ranks, ONE NCCL sum all-reduce of the "
+                                                      "[g_Q|g_V|g_pi] buffer per update, eager launches" % (B * world, world)),
                       "cfg1_update_ms": cfg1_ms, "cfg1_updates_per_sec": 1e3 / cfg1_ms,
                       "cfg1_definition": "README command shape (Pendulum ReverseKL: B=32 N=62 S=3 A=1 200-200): one FULL agent update "
                                          "through kl_networks.ReverseKLNetwork.update_network + update_target_network (q, v, pi "

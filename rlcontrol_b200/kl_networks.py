@@ -50,11 +50,11 @@ def _linear_init(n_in, n_out, init_w=None):
 class _Adam:
     """torch.optim.Adam state of one flat parameter vector, step count on the device (graph-safe)."""
 
-    def __init__(self, eng: Engine, theta: torch.Tensor, lr: float):
+    def __init__(self, eng: Engine, theta: torch.Tensor, lr: float, grad: torch.Tensor):
         self.eng, self.theta, self.lr = eng, theta, float(lr)
         self.m, self.v = torch.zeros_like(theta), torch.zeros_like(theta)
         self.state_dev = torch.zeros((4,), dtype=torch.int32, device=theta.device)
-        self.grad = torch.zeros_like(theta)
+        self.grad = grad                               # a view into the agent's flat gradient buffer
 
     def step(self):
         self.eng.adam_step_dev(self.theta, self.grad, self.m, self.v, self.state_dev, self.lr, ADAM_TORCH)
@@ -132,9 +132,17 @@ class _KLNetwork(object):
         self.target_v = Mlp(self.eng_v, S, c1, c2, 1)
         self.target_v.copy_from(self.v)
         self.q_net = _QNet(self.critic)
-        self.pi_opt = _Adam(self.eng_pi, self.pi.theta, self.learning_rate[0])
-        self.q_opt = _Adam(self.eng, self.critic.theta, self.learning_rate[1])
-        self.v_opt = _Adam(self.eng_v, self.v.theta, self.learning_rate[1])
+        # one contiguous gradient buffer [theta_Q | theta_V | theta_pi]: the data-parallel exchange is ONE all-reduce
+        nq, nv, npi = self.critic.theta.numel(), self.v.theta.numel(), self.pi.theta.numel()
+        self.grad_flat = torch.zeros((nq + nv + npi,), dtype=torch.float32, device=dev)
+        self.pi_opt = _Adam(self.eng_pi, self.pi.theta, self.learning_rate[0], self.grad_flat[nq + nv:])
+        self.q_opt = _Adam(self.eng, self.critic.theta, self.learning_rate[1], self.grad_flat[:nq])
+        self.v_opt = _Adam(self.eng_v, self.v.theta, self.learning_rate[1], self.grad_flat[nq:nq + nv])
+        # data-parallel: every rank updates on its own shard of the minibatch; all per-rank
+        # gradients are pre-scaled by 1/B_total inside the kernels, so one SUM all-reduce of grad_flat gives the
+        # reference's batch means and every rank then applies identical Adam steps.
+        self.process_group = getattr(config, "process_group", None)
+        self.world_size = int(getattr(config, "world_size", 1))
         # ---- integration grid (:58-102)
         grid = getattr(config, "integration_grid", None)      # optional (actions [N,A], weights [N]) override
         acts, w = grid if grid is not None else integration_grid(A, self.action_scale, getattr(config, "N_param", 64),
@@ -145,7 +153,8 @@ class _KLNetwork(object):
         self.device = dev
         self._steps = {}                      # batch size -> captured update
         self._act = {}                        # batch size -> action-selection buffers
-        self.use_graph = bool(getattr(config, "use_cuda_graph", True))
+        # NCCL inside a multi-stream capture is not worth the risk: the data-parallel update runs eagerly
+        self.use_graph = bool(getattr(config, "use_cuda_graph", True)) and self.world_size == 1
 
     # ------------------------------------------------------------------ parameter access (tests, checkpoints)
     def load_reference_parameters(self, q, v, target_v, pi):
@@ -211,6 +220,8 @@ class _KLNetwork(object):
         eng, d, o = self.eng, st.d, st.out_dev
         alpha, sac = self.entropy_scale, self.q_update_type == "sac"
         intg = self.optim_type in ("intg", "hard_intg")
+        dp = self.world_size > 1
+        bt = B * self.world_size
         need_q_new = sac or not intg
         main, s_grid, s_v, s_pi = st.stream, st.s_grid, st.s_v, st.s_pi
         st.in_dev.copy_(st.in_host, non_blocking=True)
@@ -233,37 +244,54 @@ class _KLNetwork(object):
         if need_q_new:
             self.critic.eval_into(d["s"], st.ev["action"].view(B, 1, -1), st.q_new, "fp32")
         main.wait_stream(s_v)
-        eng.kl_targets(d["r"], d["g"], st.vnext, st.q_new, st.ev["logp"], st.v_out, alpha, sac,
+        eng.kl_targets(d["r"], d["g"], st.vnext, st.q_new, st.ev["logp"], st.v_out, alpha, sac, b_total=bt,
                        out=(st.y, st.dv, o[1:2]))
         # V branch: backward + Adam
         s_v.wait_stream(main)
         with torch.cuda.stream(s_v):
             self.v.grads(d["s"], st.dv.view(B, 1), act=st.act_v, grad_out=self.v_opt.grad)
-            self.v_opt.step()
+            if not dp:
+                self.v_opt.step()
         # policy branch (:155-194 / reversekl :175-203), on the grid stream
         s_grid.wait_stream(main)               # covers s_pi and s_v (evaluate, V(s)) and, for 'll', Q(s,a_new)
         with torch.cuda.stream(s_grid):
             if intg:
                 if self.KIND == "fkl":
                     self.eng_grid.fkl_policy(st.q_grid, self.intgrl_weights, self.intgrl_actions, self.action_scale,
-                                             st.ev["mu_raw"], st.ev["log_std"], alpha, out=(st.loss_b, st.dmean, st.dls))
+                                             st.ev["mu_raw"], st.ev["log_std"], alpha, b_total=bt,
+                                             out=(st.loss_b, st.dmean, st.dls))
                 else:
                     self.eng_grid.rkl_policy(st.q_grid, st.v_out.view(-1), self.intgrl_weights, self.intgrl_actions,
                                              self.action_scale, st.ev["mu_raw"], st.ev["log_std"], alpha,
-                                             hard=self.optim_type == "hard_intg", out=(st.loss_b, st.dmean, st.dls))
+                                             hard=self.optim_type == "hard_intg", b_total=bt,
+                                             out=(st.loss_b, st.dmean, st.dls))
                 self.eng_grid.policy_head_grad(st.head, 0, dmean=st.dmean, dlog_std=st.dls, out=st.dhead)
                 self.eng_grid.mean_into(st.loss_b, o[2:3])
+                if dp:
+                    o[2:3].mul_(1.0 / self.world_size)     # this rank's share of the global mean over states
             else:
                 self.eng_grid.policy_head_grad(st.head, 1 if self.optim_type == "ll" else 2, z=st.ev["z"],
                                                logp=st.ev["logp"], q_new=st.q_new, v=st.v_out, entropy_scale=alpha,
-                                               out=st.dhead, loss_out=o[2:3])
+                                               b_total=bt, out=st.dhead, loss_out=o[2:3])
             self.pi.grads(d["s"], st.dhead, act=st.act_pi, grad_out=self.pi_opt.grad)   # eng_pi's scratch: s_pi is idle
-            self.pi_opt.step()
+            if not dp:
+                self.pi_opt.step()
         # main: Q regression (:133-140,199-201); theta_Q may only change once the grid branch has read it
-        self.critic.grads_into(d["s"], d["a"], st.y, self.q_opt.grad, o[0:1], st.q_reg)
-        if intg:
-            main.wait_event(ev_grid)
-        self.q_opt.step()
+        self.critic.grads_into(d["s"], d["a"], st.y, self.q_opt.grad, o[0:1], st.q_reg, b_total=bt)
+        if dp:
+            # join, ONE all-reduce over [g_Q | g_V | g_pi] (and the three loss shares), identical Adam steps everywhere
+            from .parallel import allreduce_grad_
+            for br in (s_grid, s_v, s_pi):
+                main.wait_stream(br)
+            allreduce_grad_(self.grad_flat, self.process_group)
+            allreduce_grad_(o, self.process_group)     # every loss slot holds this rank's share of the global mean
+            self.q_opt.step()
+            self.v_opt.step()
+            self.pi_opt.step()
+        else:
+            if intg:
+                main.wait_event(ev_grid)
+            self.q_opt.step()
         self.critic.invalidate()
         self.critic_grid.invalidate()
         for br in (s_grid, s_v, s_pi):
