@@ -120,6 +120,93 @@ __device__ int gmm_fit(const double* X, int k, int A, int M, double* resp, doubl
   return it > max_iter ? max_iter : it;
 }
 
+// ---- warp-cooperative versions of the same EM (identical arithmetic and summation order, so the
+// results are bit-identical to the serial functions above): the serial refit on one thread was the
+// critical path of the CEM kernel (fp64 log/exp/div chains while 255 threads idled).
+// Work split: M-step one lane per (component, dim); E-step one lane per (elite, component) pair, then
+// one lane per elite for the normalisation.  X, resp, g and the scratch live in shared memory.
+struct GmmScratch {
+  double wl[CEM_MAX_K * 2];
+  double norm[CEM_MAX_K];
+  double logdet[2], logw[2];
+};
+
+__device__ void gmm_mstep_w(int lane, const double* X, int k, int A, int M, const double* resp, Gmm& g) {
+  const double VAR_LO = 0.1353352832366127, VAR_HI = 7.38905609893065;  // exp(-2), exp(2)
+  for (int p = lane; p < M * A; p += 32) {
+    const int c = p / A, d = p - c * A;
+    double nk = 0.0;
+    for (int i = 0; i < k; ++i) nk += resp[i * 2 + c];
+    nk += 10.0 * 2.220446049250313e-16;
+    double sx = 0.0, sx2 = 0.0;
+    for (int i = 0; i < k; ++i) {
+      const double x = X[i * CEM_MAX_A + d], r = resp[i * 2 + c];
+      sx += r * x;
+      sx2 += r * x * x;
+    }
+    const double mean = sx / nk;
+    const double cov = sx2 / nk - 2.0 * (mean * sx / nk) + mean * mean + 1e-6;
+    g.mu[c][d] = clampd(mean, -2.0, 2.0);
+    g.var[c][d] = clampd(cov, VAR_LO, VAR_HI);
+    if (d == 0) g.w[c] = nk / (double)k;
+  }
+  __syncwarp();
+}
+
+__device__ double gmm_estep_w(int lane, const double* X, int k, int A, int M, const Gmm& g, double* resp,
+                              GmmScratch& sc) {
+  if (lane < M) {
+    double ld = 0.0;
+    for (int d = 0; d < A; ++d) ld += log(1.0 / sqrt(g.var[lane][d]));
+    sc.logdet[lane] = ld;
+    sc.logw[lane] = log(g.w[lane]);
+  }
+  __syncwarp();
+  for (int p = lane; p < k * M; p += 32) {
+    const int i = p / M, c = p - i * M;
+    double lp = 0.0;
+    for (int d = 0; d < A; ++d) {
+      const double pc = 1.0 / sqrt(g.var[c][d]);
+      const double prec = pc * pc;
+      const double x = X[i * CEM_MAX_A + d], mu = g.mu[c][d];
+      lp += mu * mu * prec - 2.0 * x * mu * prec + x * x * prec;
+    }
+    sc.wl[i * 2 + c] = -0.5 * (A * 1.8378770664093453 + lp) + sc.logdet[c] + sc.logw[c];
+  }
+  __syncwarp();
+  for (int i = lane; i < k; i += 32) {
+    double m = -CUDART_INF;
+    for (int c = 0; c < M; ++c) m = fmax(m, sc.wl[i * 2 + c]);
+    double se = 0.0;
+    for (int c = 0; c < M; ++c) se += exp(sc.wl[i * 2 + c] - m);
+    const double norm = m + log(se);
+    sc.norm[i] = norm;
+    for (int c = 0; c < M; ++c) resp[i * 2 + c] = exp(sc.wl[i * 2 + c] - norm);
+    if (M == 1) resp[i * 2 + 1] = 0.0;
+  }
+  __syncwarp();
+  double ll = 0.0;
+  if (lane == 0) {
+    for (int i = 0; i < k; ++i) ll += sc.norm[i];
+    ll /= (double)k;
+  }
+  return __shfl_sync(0xffffffffu, ll, 0);
+}
+
+__device__ int gmm_fit_w(int lane, const double* X, int k, int A, int M, double* resp, double tol, int max_iter,
+                         Gmm& g, GmmScratch& sc) {
+  gmm_mstep_w(lane, X, k, A, M, resp, g);
+  double lower = -CUDART_INF;
+  int it = 0;
+  for (it = 1; it <= max_iter; ++it) {
+    const double prev = lower;
+    lower = gmm_estep_w(lane, X, k, A, M, g, resp, sc);
+    gmm_mstep_w(lane, X, k, A, M, resp, g);
+    if (fabs(lower - prev) < tol) break;   // `lower` is warp-uniform (broadcast from lane 0)
+  }
+  return it > max_iter ? max_iter : it;
+}
+
 // action of sample n in dimension d for the current iteration
 __device__ __forceinline__ float cem_action(int it, long long bn, int d, int A, const float* u0,
                                             const float* noise, const float* comp_u, long long BN,
@@ -153,6 +240,7 @@ k_cem(const float* __restrict__ p, int B, int N, int A, int H2, int iters, int t
   __shared__ Gmm g;
   __shared__ double Xel[CEM_MAX_K * CEM_MAX_A];
   __shared__ double resp[CEM_MAX_K * 2];
+  __shared__ GmmScratch gsc;
   __shared__ float red_v[CEM_THREADS / 32];
   __shared__ int red_i[CEM_THREADS / 32];
   __shared__ int sel[CEM_MAX_K];
@@ -244,15 +332,17 @@ k_cem(const float* __restrict__ p, int B, int N, int A, int H2, int iters, int t
                    : 0.0;
     }
     __syncthreads();
-    // ---- refit ----
-    if (tid == 0) {
+    // ---- refit: warp 0, cooperatively ----
+    if (wid == 0) {
       if (M == 1) {
-        for (int i = 0; i < top_m; ++i) { resp[i * 2] = 1.0; resp[i * 2 + 1] = 0.0; }
-        gmm_mstep(Xel, top_m, A, 1, resp, g);
-        g.w[0] = 1.0;
+        for (int i = lane; i < top_m; i += 32) { resp[i * 2] = 1.0; resp[i * 2 + 1] = 0.0; }
+        __syncwarp();
+        gmm_mstep_w(lane, Xel, top_m, A, 1, resp, g);
+        if (lane == 0) g.w[0] = 1.0;
       } else {
-        gmm_init_labels(Xel, top_m, A, resp);
-        gmm_fit(Xel, top_m, A, 2, resp, 1e-2, 100, g);
+        if (lane == 0) gmm_init_labels(Xel, top_m, A, resp);
+        __syncwarp();
+        gmm_fit_w(lane, Xel, top_m, A, 2, resp, 1e-2, 100, g, gsc);
       }
     }
     __syncthreads();
