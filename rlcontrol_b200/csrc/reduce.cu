@@ -12,6 +12,9 @@ __device__ __forceinline__ bool key_gt(float va, int ia, float vb, int ib) {
 }
 
 // row.argsort()[::-1][:k]: k rounds of "largest key strictly below the previous pick".
+// CACHED: the row lives in registers (N <= 32*NPL), so the k rounds re-read nothing -- the streaming
+// variant re-fetches the row from L2 every round (6 x 16.8 MB at cfg4: 40 us instead of 7).
+template <int NPL>
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
 k_topk(const float* __restrict__ q, int B, int N, int k, long long* __restrict__ idx_out,
        float* __restrict__ q_sel_out, const float* __restrict__ actions, int A, int act_per_state,
@@ -20,17 +23,37 @@ k_topk(const float* __restrict__ q, int B, int N, int k, long long* __restrict__
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
   const float* row = q + (long long)b * N;
+  float rv[NPL > 0 ? NPL : 1];
+  if (NPL > 0) {
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      const int n = lane + 32 * i;
+      float v = n < N ? row[n] : -CUDART_INF_F;
+      if (v != v) v = CUDART_INF_F;  // NaN ordered like +inf (numpy sorts NaN last ascending)
+      rv[i] = v;
+    }
+  }
   float lastv = CUDART_INF_F;
   int lasti = 0x7fffffff;
   for (int t = 0; t < k; ++t) {
     float bv = -CUDART_INF_F;
     int bi = -1;
-  #pragma unroll 8
-  for (int n = lane; n < N; n += 32) {
-      float v = row[n];
-      if (v != v) v = CUDART_INF_F;  // NaN ordered like +inf (numpy sorts NaN last ascending)
-      const bool below = (v < lastv) || (v == lastv && n < lasti);
-      if (below && (bi < 0 || key_gt(v, n, bv, bi))) { bv = v; bi = n; }
+    if (NPL > 0) {
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        const int n = lane + 32 * i;
+        const float v = rv[i];
+        const bool below = (n < N) && ((v < lastv) || (v == lastv && n < lasti));
+        if (below && (bi < 0 || key_gt(v, n, bv, bi))) { bv = v; bi = n; }
+      }
+    } else {
+#pragma unroll 8
+      for (int n = lane; n < N; n += 32) {
+        float v = row[n];
+        if (v != v) v = CUDART_INF_F;
+        const bool below = (v < lastv) || (v == lastv && n < lasti);
+        if (below && (bi < 0 || key_gt(v, n, bv, bi))) { bv = v; bi = n; }
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -98,7 +121,9 @@ k_lse(const float* __restrict__ q, int B, int N, float offset, float* __restrict
   if (lane == 0) v_out[b] = m + logf(s) + offset;
 }
 
-// ForwardKL (forwardkl_network.py:165-194)
+// ForwardKL (forwardkl_network.py:165-194).  NPL > 0: the scaled row q/alpha lives in registers
+// (N <= 32*NPL): one IEEE division and one global read per element instead of three of each.
+template <int NPL>
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
 k_fkl(const float* __restrict__ q, const float* __restrict__ w, const float* __restrict__ logp,
       int B, int N, float alpha, float inv_btotal, float* __restrict__ loss_b,
@@ -109,21 +134,56 @@ k_fkl(const float* __restrict__ q, const float* __restrict__ w, const float* __r
   const float* row = q + (long long)b * N;
   const float* lp = logp + (long long)b * N;
   float m = -CUDART_INF_F;
+  float t[NPL > 0 ? NPL : 1];
+  if (NPL > 0) {
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      const int n = lane + 32 * i;
+      t[i] = n < N ? __fdiv_rn(row[n], alpha) : -CUDART_INF_F;
+      m = fmaxf(m, t[i]);
+    }
+  } else {
 #pragma unroll 8
-  for (int n = lane; n < N; n += 32) m = fmaxf(m, __fdiv_rn(row[n], alpha));
+    for (int n = lane; n < N; n += 32) m = fmaxf(m, __fdiv_rn(row[n], alpha));
+  }
   m = warp_max(m);
   float z = 0.f;
+  if (NPL > 0) {
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      const int n = lane + 32 * i;
+      if (n < N) {
+        t[i] = expf(t[i] - m);
+        z = fmaf(t[i], w[n], z);
+      }
+    }
+  } else {
 #pragma unroll 8
-  for (int n = lane; n < N; n += 32) z = fmaf(expf(__fdiv_rn(row[n], alpha) - m), w[n], z);
+    for (int n = lane; n < N; n += 32) z = fmaf(expf(__fdiv_rn(row[n], alpha) - m), w[n], z);
+  }
   z = warp_sum(z);
   float acc = 0.f;
+  if (NPL > 0) {
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      const int n = lane + 32 * i;
+      if (n < N) {
+        const float p = __fdiv_rn(t[i], z);
+        const float pw = p * w[n];
+        acc = fmaf(pw, lp[n], acc);
+        if (boltz) boltz[(long long)b * N + n] = p;
+        if (dlogp) dlogp[(long long)b * N + n] = -pw * inv_btotal;
+      }
+    }
+  } else {
 #pragma unroll 8
-  for (int n = lane; n < N; n += 32) {
-    const float p = __fdiv_rn(expf(__fdiv_rn(row[n], alpha) - m), z);
-    const float pw = p * w[n];
-    acc = fmaf(pw, lp[n], acc);
-    if (boltz) boltz[(long long)b * N + n] = p;
-    if (dlogp) dlogp[(long long)b * N + n] = -pw * inv_btotal;
+    for (int n = lane; n < N; n += 32) {
+      const float p = __fdiv_rn(expf(__fdiv_rn(row[n], alpha) - m), z);
+      const float pw = p * w[n];
+      acc = fmaf(pw, lp[n], acc);
+      if (boltz) boltz[(long long)b * N + n] = p;
+      if (dlogp) dlogp[(long long)b * N + n] = -pw * inv_btotal;
+    }
   }
   acc = warp_sum(acc);
   if (lane == 0) loss_b[b] = -acc;
@@ -339,7 +399,16 @@ extern "C" int rlc_reduce_topk(rlc_handle* h, const float* q, int B, int N, int 
   RLC_REQUIRE(h && q && idx_out && B >= 0 && N >= 1 && k >= 1 && k <= 64 && k <= N);
   RLC_REQUIRE(!elites_out || (actions && A >= 1));
   if (B == 0) return RLC_OK;
-  k_topk<<<nblocks(B), 32 * WARPS_PER_BLOCK, 0, (cudaStream_t)stream>>>(
+  if (N <= 128) k_topk<4><<<nblocks(B), 32 * WARPS_PER_BLOCK, 0, (cudaStream_t)stream>>>(
+      q, B, N, k, (long long*)idx_out, q_sel_out, actions, A, act_mode == RLC_ACT_PER_STATE,
+      elites_out);
+  else if (N <= 512) k_topk<16><<<nblocks(B), 32 * WARPS_PER_BLOCK, 0, (cudaStream_t)stream>>>(
+      q, B, N, k, (long long*)idx_out, q_sel_out, actions, A, act_mode == RLC_ACT_PER_STATE,
+      elites_out);
+  else if (N <= 1024) k_topk<32><<<nblocks(B), 32 * WARPS_PER_BLOCK, 0, (cudaStream_t)stream>>>(
+      q, B, N, k, (long long*)idx_out, q_sel_out, actions, A, act_mode == RLC_ACT_PER_STATE,
+      elites_out);
+  else k_topk<0><<<nblocks(B), 32 * WARPS_PER_BLOCK, 0, (cudaStream_t)stream>>>(
       q, B, N, k, (long long*)idx_out, q_sel_out, actions, A, act_mode == RLC_ACT_PER_STATE,
       elites_out);
   RLC_LAUNCH_CHECK(h);
@@ -372,8 +441,14 @@ extern "C" int rlc_reduce_fkl(rlc_handle* h, const float* q, const float* w, con
   RLC_REQUIRE(h && q && w && logp && loss_b_out && B >= 0 && N >= 1 && B_total >= B && B_total >= 1);
   RLC_REQUIRE(entropy_scale > 0.f);
   if (B == 0) return RLC_OK;
-  k_fkl<<<nblocks(B), 32 * WARPS_PER_BLOCK, 0, (cudaStream_t)stream>>>(
-      q, w, logp, B, N, entropy_scale, 1.f / (float)B_total, loss_b_out, boltz_out, dlogp_out);
+#define RLC_FKL(NPL_)                                                          \
+  k_fkl<NPL_><<<nblocks(B), 32 * WARPS_PER_BLOCK, 0, (cudaStream_t)stream>>>( \
+      q, w, logp, B, N, entropy_scale, 1.f / (float)B_total, loss_b_out, boltz_out, dlogp_out)
+  // measured on B200 at B=4096, N=1024: the register-cached variant (NPL=32, 93 registers) runs 69 us, the
+  // streaming one 47 us -- occupancy matters more than the re-reads here; small rows still take the cached path
+  if (N <= 128) RLC_FKL(4);
+  else RLC_FKL(0);
+#undef RLC_FKL
   RLC_LAUNCH_CHECK(h);
   return RLC_OK;
 }

@@ -72,6 +72,30 @@ def main():
     print(json.dumps({"config": "cfg2 Actor-Expert B=32 N=120 k=6 200-200 T-mid (predict_q + top-k + elite gather)",
                       "gpu_ms": dt * 1e3, "gpu_q_evals_per_sec": B * N / dt, "cpu_oracle_ms": cpu * 1e3,
                       "note": "launch-latency-bound on the GPU (2 kernels + host overhead per call)"}))
+    # the same step with the sampling on the device too: rlc_ae_expert_step (sample -> Q -> top-k -> gather, one launch
+    # after the state-term launch), preallocated draws; CPU side = numpy choice/normal + the above
+    M = 1
+    alpha = np.ones((B, M), np.float32)
+    mean = np.tanh(rng.randn(B, M, A)).astype(np.float32)
+    sigma = np.exp(rng.uniform(-2, 0, (B, M, A))).astype(np.float32)
+    cu, nz = rng.random_sample((B, N)).astype(np.float32), rng.standard_normal((B, N, A)).astype(np.float32)
+    al, me, si, cud, nzd = t(alpha), t(mean), t(sigma), t(cu), t(nz)
+    lo, hi = -np.ones(A), np.ones(A)
+    dt = gpu_time(lambda: cr.ae_expert_step(sd, k, al, me, si, cud, nzd, lo, hi), reps=200)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(200):
+        cr.ae_expert_step(sd, k, al, me, si, cud, nzd, lo, hi)
+    e1.record()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        a2, _ = onp.mixture_sample(alpha, mean, sigma, cu, nz, lo, hi)
+        q = onp.tmid_eval(s, a2.astype(np.float32), p)
+        onp.gather_elites(a2, onp.topk_desc(q, k))
+    cpu = (time.perf_counter() - t0) / 20
+    print(json.dumps({"config": "cfg2 Actor-Expert fused expert step (mixture sampling + predict_q + top-k + elite gather), B=32 N=120 k=6",
+                      "gpu_ms_host_loop": dt * 1e3, "gpu_ms_device": e0.elapsed_time(e1) / 200, "cpu_oracle_ms": cpu * 1e3}))
 
 
 if __name__ == "__main__":
