@@ -218,7 +218,8 @@ k_rkl(const float* __restrict__ q, const float* __restrict__ v, const float* __r
 // PolicyNetwork.get_logprob (forwardkl_network.py:324-351) is evaluated in place from the policy
 // head outputs mean[B,A], log_std[B,A]: no [B,N] log-density tensor is read, and the gradient comes
 // back as dL/dmean, dL/dlog_std [B,A].  Terms that depend on the grid only are tabulated once:
-//   U[n][k] = atanh(a_nk/scale) = (log(1+x) - log(1-x))/2     J[n] = sum_k log(1 - x^2 + eps)
+//   U[k][n] = atanh(a_nk/scale) = (log(1+x) - log(1-x))/2     J[n] = sum_k log(1 - x^2 + eps)
+// (dimension-major: lane n reads U[k][n], one coalesced wavefront per load instead of A)
 __global__ void k_grid_logterms(const float* __restrict__ grid, int N, int A, float inv_scale, float eps,
                                 float* __restrict__ U, float* __restrict__ J) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -226,15 +227,19 @@ __global__ void k_grid_logterms(const float* __restrict__ grid, int N, int A, fl
   float j = 0.f;
   for (int k = 0; k < A; ++k) {
     const float x = grid[(size_t)n * A + k] * inv_scale;
-    U[(size_t)n * A + k] = (logf(1.f + x) - logf(1.f - x)) * 0.5f;
+    U[(size_t)k * N + n] = (logf(1.f + x) - logf(1.f - x)) * 0.5f;
     j += logf(1.f - x * x + eps);
   }
   J[n] = j;
 }
 
 #define POL_MAX_A 8
-#define POL_THREADS 256
-#define POL_NPT 4    // q values cached per thread (N <= 1024 stays in registers)
+// 64 threads x 16 cached values per state.  (The first version used 256 threads x 4: ncu showed it
+// instruction-bound at 224 instructions per (state, action) pair, half of them the per-thread prologue
+// -- 12 IEEE divisions + 6 expf for the log-density constants -- and the 13 final warp reductions,
+// amortised over only 4 pairs.)
+#define POL_THREADS 64
+#define POL_NPT 16   // q values cached per thread (N <= 1024 stays in registers)
 
 // block-wide reductions over POL_THREADS threads (8 warps); `red` is 8 floats of shared memory
 __device__ __forceinline__ float block_max(float v, float* red) {
@@ -276,22 +281,33 @@ k_policy_reduce(const float* __restrict__ q, const float* __restrict__ v, const 
   // std to MultivariateNormal as the covariance, forwardkl_network.py:350)
   float mu[A], h[A], gs[A];   // h: coefficient of d^2 ; gs: d^2 factor in dlogp/dlog_std
   float c0 = 0.f;
+  // the constants are computed once per state (A lanes) and broadcast through shared memory
+  __shared__ float cst[3 * POL_MAX_A + 1];
+  if (tid < A) {
+    const float ls = log_std[(size_t)b * A + tid];
+    const float sd = expf(ls);
+    cst[tid] = mean[(size_t)b * A + tid];
+    cst[POL_MAX_A + tid] = (A == 1) ? 0.5f / (sd * sd) : 0.5f / sd;
+    cst[2 * POL_MAX_A + tid] = (A == 1) ? 1.f / (sd * sd) : 0.5f / sd;
+  }
+  if (tid == 0) {
+    float c = 0.f;
+    if (A == 1) {
+      c = -log_std[(size_t)b * A] - 0.9189385332046727f;     // log sqrt(2 pi)
+    } else {
+      for (int k = 0; k < A; ++k) c -= 0.5f * log_std[(size_t)b * A + k];
+      c -= 0.9189385332046727f * (float)A;
+    }
+    cst[3 * POL_MAX_A] = c;
+  }
+  __syncthreads();
 #pragma unroll
   for (int k = 0; k < A; ++k) {
-    const float ls = log_std[(size_t)b * A + k];
-    const float sd = expf(ls);
-    mu[k] = mean[(size_t)b * A + k];
-    if (A == 1) {
-      h[k] = 0.5f / (sd * sd);
-      gs[k] = 1.f / (sd * sd);
-      c0 = -ls - 0.9189385332046727f;                       // log sqrt(2 pi)
-    } else {
-      h[k] = 0.5f / sd;
-      gs[k] = 0.5f / sd;
-      c0 -= 0.5f * ls;
-    }
+    mu[k] = cst[k];
+    h[k] = cst[POL_MAX_A + k];
+    gs[k] = cst[2 * POL_MAX_A + k];
   }
-  if (A > 1) c0 -= 0.9189385332046727f * (float)A;
+  c0 = cst[3 * POL_MAX_A];
   const bool cached = N <= POL_THREADS * POL_NPT;
   float qc[POL_NPT];
   if (cached) {
@@ -339,7 +355,7 @@ k_policy_reduce(const float* __restrict__ q, const float* __restrict__ v, const 
     float d[A];
 #pragma unroll
     for (int k = 0; k < A; ++k) {
-      d[k] = U[(size_t)n * A + k] - mu[k];
+      d[k] = U[(size_t)k * N + n] - mu[k];
       lp = fmaf(-h[k] * d[k], d[k], lp);
     }
     float g;   // dL/dlogp_bn
