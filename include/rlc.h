@@ -327,6 +327,16 @@ int rlc_replay_scatter(rlc_handle* h, float* state, float* action, float* reward
                        const int64_t* slot, int n, const float* s_in, const float* a_in,
                        const float* r_in, const float* s2_in, const float* g_in, void* stream);
 
+/* Device-side minibatch index sampling: k distinct uniform indices in [0, n) from a
+ * counter-based Philox stream keyed by (seed, counter) -- a pure function of its arguments, so a run is
+ * reproducible, but NOT the numpy stream of RandomAccessQueue.sample_n_k (custom_collections.py:107-131; the
+ * host sampler in rlcontrol_b200/replaybuffer.py reproduces that one and stays the default).
+ * idx_out[k] = logical FIFO indices, slot_out[k] = ring slots (head + idx) % cap; either may be NULL.
+ * Requires k <= 4096 and 3k < n (the reference's own condition for its rejection scheme), else
+ * RLC_ERR_UNSUPPORTED. */
+int rlc_replay_sample(rlc_handle* h, int64_t n, int k, uint64_t seed, uint64_t counter, int64_t head,
+                      int64_t cap, int64_t* idx_out, int64_t* slot_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

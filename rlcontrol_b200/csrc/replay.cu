@@ -86,3 +86,112 @@ extern "C" int rlc_replay_scatter(rlc_handle* h, float* state, float* action, fl
   RLC_LAUNCH_CHECK(h);
   return RLC_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// N4: device-side minibatch index sampling -- k DISTINCT uniform indices in [0, n), written as ring
+// slots (head + i) % cap, with no host round trip (the host sampler RandomAccessQueue.sample_n_k,
+// custom_collections.py:107-131, stays the default because it reproduces the reference's stream).
+// Counter-based Philox4x32-10 keyed by (seed, call counter): draw (slot i, round r) is a pure function
+// of (seed, counter, i, r).  Duplicates are resolved deterministically: every unresolved slot inserts
+// (value, priority = round<<16 | slot) into an open-addressing hash set in shared memory with
+// atomicMin on the packed word, the lowest priority keeps the value, the others redraw next round.
+// One CTA; k <= 4096, 3k < n (the reference's own condition for its rejection scheme).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+#define SAMPLE_THREADS 256
+#define SAMPLE_MAX_K 4096
+
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+k_sample_distinct(long long n, int k, unsigned long long seed, unsigned long long counter, long long head,
+                  long long cap, long long* __restrict__ idx_out, long long* __restrict__ slot_out,
+                  int table_size) {
+  extern __shared__ unsigned long long tab[];   // entry: (value+1) << 32 | priority ; 0 = empty
+  __shared__ int unresolved;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < table_size; i += SAMPLE_THREADS) tab[i] = 0ull;
+  // per-slot state lives in registers: slots tid, tid+256, ...
+  constexpr int PER = SAMPLE_MAX_K / SAMPLE_THREADS;
+  unsigned int val[PER];
+  bool done[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) { done[j] = (tid + j * SAMPLE_THREADS) >= k; val[j] = 0u; }
+  __syncthreads();
+  const unsigned mask = (unsigned)table_size - 1u;
+  for (int round = 0; round < 64; ++round) {
+    if (tid == 0) unresolved = 0;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      if (done[j]) continue;
+      const int slot = tid + j * SAMPLE_THREADS;
+      uint32_t r[4];
+      philox4x32_10((uint32_t)slot, (uint32_t)round, (uint32_t)counter, (uint32_t)(counter >> 32), (uint32_t)seed,
+                    (uint32_t)(seed >> 32), r);
+      // 64 random bits -> [0, n) by multiply-high (bias < n / 2^64)
+      const unsigned long long r64 = ((unsigned long long)r[0] << 32) | r[1];
+      const unsigned int x = (unsigned int)__umul64hi(r64, (unsigned long long)n);
+      val[j] = x;
+      const unsigned long long word = ((unsigned long long)(x + 1u) << 32) | (unsigned)((round << 16) | slot);
+      unsigned h = (x * 2654435761u) & mask;
+      while (true) {
+        const unsigned long long cur = *(volatile unsigned long long*)&tab[h];
+        if (cur == 0ull) {
+          if (atomicCAS(&tab[h], 0ull, word) == 0ull) break;
+          continue;                                   // lost the race for the empty entry: re-read it
+        }
+        if ((unsigned int)(cur >> 32) == x + 1u) { atomicMin(&tab[h], word); break; }
+        h = (h + 1u) & mask;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      if (done[j]) continue;
+      const int slot = tid + j * SAMPLE_THREADS;
+      const unsigned int x = val[j];
+      unsigned h = (x * 2654435761u) & mask;
+      while ((unsigned int)(*(volatile unsigned long long*)&tab[h] >> 32) != x + 1u) h = (h + 1u) & mask;
+      if ((unsigned int)(tab[h] & 0xffffffffu) == (unsigned)((round << 16) | slot)) {
+        done[j] = true;
+        if (idx_out) idx_out[slot] = (long long)x;
+        if (slot_out) slot_out[slot] = (head + (long long)x) % cap;
+      } else {
+        atomicAdd(&unresolved, 1);
+      }
+    }
+    __syncthreads();
+    if (unresolved == 0) break;
+    __syncthreads();
+  }
+}
+
+extern "C" int rlc_replay_sample(rlc_handle* h, int64_t n, int k, uint64_t seed, uint64_t counter, int64_t head,
+                                 int64_t cap, int64_t* idx_out, int64_t* slot_out, void* stream) {
+  RLC_REQUIRE(h && (idx_out || slot_out) && n >= 1 && k >= 0 && cap >= n && head >= 0 && head < cap);
+  RLC_REQUIRE(n < (1LL << 31));
+  if (k > SAMPLE_MAX_K || 3LL * k >= n) return RLC_ERR_UNSUPPORTED;   // the host sampler covers these
+  if (k == 0) return RLC_OK;
+  int table = 1;
+  while (table < 4 * k) table <<= 1;                                   // load factor <= 1/4... 1/2
+  const size_t smem = (size_t)table * sizeof(unsigned long long);
+  if (smem > h->smem_optin) return RLC_ERR_UNSUPPORTED;
+  RLC_CUDA(cudaFuncSetAttribute(k_sample_distinct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_sample_distinct<<<1, SAMPLE_THREADS, smem, (cudaStream_t)stream>>>(
+      (long long)n, k, (unsigned long long)seed, (unsigned long long)counter, (long long)head, (long long)cap,
+      (long long*)idx_out, (long long*)slot_out, table);
+  RLC_LAUNCH_CHECK(h);
+  return RLC_OK;
+}

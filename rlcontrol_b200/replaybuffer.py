@@ -18,7 +18,12 @@ from .engine import Engine, _ptr, _stream
 
 class ReplayBuffer(object):
     def __init__(self, buffer_size, random_seed, state_dim=None, action_dim=None, engine: Engine = None,
-                 flush_every: int = 256):
+                 flush_every: int = 256, sample_on_device: bool = False):
+        # sample_on_device: draw the minibatch indices with rlc_replay_sample (Philox, no host round trip) instead of
+        # the reference's numpy stream; falls back to the host sampler when 3k >= n or k > 4096
+        self.sample_on_device = bool(sample_on_device)
+        self._seed = int(random_seed) & 0xFFFFFFFFFFFFFFFF
+        self._draws = 0
         self.buffer_size = int(buffer_size)
         self.rng = np.random.RandomState(random_seed)       # custom_collections.py:14-15
         self.eng = engine if engine is not None else Engine()
@@ -124,13 +129,20 @@ class ReplayBuffer(object):
     def sample_batch(self, batch_size, as_numpy=False):
         assert self.get_size() >= batch_size
         self._flush()
+        if self.sample_on_device and 0 < batch_size <= 4096 and 3 * batch_size < self.get_size():
+            slots = torch.empty((int(batch_size),), dtype=torch.int64, device=self.eng.device)
+            check(self.eng.lib.rlc_replay_sample(self.eng.h, self.get_size(), int(batch_size), self._seed, self._draws,
+                                                 self._head, self.buffer_size, None, _ptr(slots), _stream()))
+            self._draws += 1
+            return self.gather_slots(slots, as_numpy=as_numpy)
         idx = np.asarray(self.sample_indices(batch_size), np.int64)
         slots = (self._head + idx) % self.buffer_size
         return self.gather_slots(slots, as_numpy=as_numpy)
 
     def gather_slots(self, slots, as_numpy=False):
         dev, B = self.eng.device, len(slots)
-        slot_t = torch.from_numpy(np.ascontiguousarray(slots, dtype=np.int64)).to(dev)
+        slot_t = slots if isinstance(slots, torch.Tensor) else \
+            torch.from_numpy(np.ascontiguousarray(slots, dtype=np.int64)).to(dev)
         e = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
         s, a, r, s2, g = e(B, self.S), e(B, self.A), e(B), e(B, self.S), e(B)
         check(self.eng.lib.rlc_replay_gather(self.eng.h, _ptr(self.state), _ptr(self.action), _ptr(self.reward),
