@@ -93,6 +93,21 @@ class _TMidBase(object):
     def set_weights(self, W1, b1, W2, b2, W3, b3, target=False):
         (self.target if target else self.critic).load(W1, b1, W2, b2, W3, b3, LAYOUT_IN_OUT)
 
+    def load_tf_checkpoint(self, prefix, scope="main/qf", target=False):
+        """Restore the critic from a TensorFlow V2 bundle (what ``tf.train.Saver.restore`` does for the
+        ``main/qf`` variables, agents/SoftActorCritic.py:37-49), without TensorFlow (``tf_bundle.py``)."""
+        from .tf_bundle import read_critic
+        W1, b1, W2, b2, W3, b3 = read_critic(prefix, scope)
+        self.set_weights(W1, b1, W2, b2, W3, b3, target=target)
+
+    def save_tf_checkpoint(self, prefix, scope="main/qf", target=False):
+        """Write the critic as a V2 bundle with the reference's variable names (byte-compatible container)."""
+        from .tf_bundle import write_bundle
+        names = ["fully_connected", "fully_connected_1", "fully_connected_2"]
+        ws = self.get_weights(target=target)
+        write_bundle(prefix, {"%s/%s/%s" % (scope, names[i // 2], "weights" if i % 2 == 0 else "biases"): np.asarray(w)
+                              for i, w in enumerate(ws)})
+
     def get_weights(self, target=False):
         return [t.cpu().numpy() for t in (self.target if target else self.critic).export(LAYOUT_IN_OUT)]
 

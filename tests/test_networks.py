@@ -129,3 +129,22 @@ def test_soft_q_network_mirror(eng):
     qg = net.eval_grid(s, grid)
     stacked = ref(s.unsqueeze(1).repeat(1, 62, 1).reshape(-1, 3), grid.repeat(30, 1, 1).reshape(-1, 1)).reshape(30, 62)
     np.testing.assert_allclose(qg.cpu().numpy(), stacked.detach().numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_critic_tf_checkpoint_round_trip(eng, tmp_path):
+    """save_tf_checkpoint / load_tf_checkpoint (tf_bundle.py): the restored critic evaluates identically, and the
+    container holds the reference's variable names (agents/SoftActorCritic.py:37-49 restores ``main/qf/*``)."""
+    from rlcontrol_b200.networks import CriticNetwork
+    from rlcontrol_b200 import tf_bundle
+    cfg = _cfg(eng, critic_lr=1e-3, critic_l1_dim=40, critic_l2_dim=24, state_dim=1, state_min=[-1.0], state_max=[1.0], action_dim=1,
+               action_min=[-1.0], action_max=[1.0])
+    a, b = CriticNetwork(None, None, cfg), CriticNetwork(None, None, cfg)
+    rng = np.random.RandomState(1)
+    s, act = rng.uniform(-1, 1, (20, 1)), rng.uniform(-1, 1, (20, 1))
+    assert np.abs(a.predict(s, act, True) - b.predict(s, act, True)).max() > 1e-6
+    pre = str(tmp_path / "ckpt")
+    a.save_tf_checkpoint(pre)
+    names = set(tf_bundle.read_index(pre))
+    assert names == {"main/qf/fully_connected%s/%s" % (sfx, k) for sfx in ("", "_1", "_2") for k in ("weights", "biases")}
+    b.load_tf_checkpoint(pre)
+    np.testing.assert_array_equal(a.predict(s, act, True), b.predict(s, act, True))
