@@ -138,8 +138,11 @@ def test_critic_tf_checkpoint_round_trip(eng, tmp_path):
     from rlcontrol_b200 import tf_bundle
     cfg = _cfg(eng, critic_lr=1e-3, critic_l1_dim=40, critic_l2_dim=24, state_dim=1, state_min=[-1.0], state_max=[1.0], action_dim=1,
                action_min=[-1.0], action_max=[1.0])
-    a, b = CriticNetwork(None, None, cfg), CriticNetwork(None, None, cfg)
+    a = CriticNetwork(None, None, cfg)
+    cfg.random_seed = 99
+    b = CriticNetwork(None, None, cfg)
     rng = np.random.RandomState(1)
+    b.set_weights(*[w + rng.randn(*w.shape).astype(np.float32) * 0.1 for w in b.get_weights()])
     s, act = rng.uniform(-1, 1, (20, 1)), rng.uniform(-1, 1, (20, 1))
     assert np.abs(a.predict(s, act, True) - b.predict(s, act, True)).max() > 1e-6
     pre = str(tmp_path / "ckpt")
