@@ -30,6 +30,22 @@ def _f32(x, device) -> torch.Tensor:
     return torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32).to(device)
 
 
+_BOUNDS = {}
+
+
+def _bounds(x, A: int, dev) -> torch.Tensor:
+    """Action bounds as an fp32 device vector [A]; device tensors pass through, host values are uploaded once and
+    cached (they are constants of the environment, and an H2D copy per call would also break graph capture)."""
+    if isinstance(x, torch.Tensor) and x.device == dev:
+        return x.to(torch.float32).reshape(-1).contiguous()
+    arr = np.broadcast_to(np.asarray(x, np.float64).reshape(-1) if np.ndim(x) else np.asarray(x, np.float64), (A,))
+    key = (str(dev), A, arr.tobytes())
+    t = _BOUNDS.get(key)
+    if t is None:
+        t = _BOUNDS[key] = torch.as_tensor(np.ascontiguousarray(arr), dtype=torch.float32).to(dev)
+    return t
+
+
 class Engine:
     """Owns the rlc_handle (workspace + packed tensor-core operands) of one CUDA device."""
 
@@ -174,8 +190,8 @@ class Engine:
         alpha = None if alpha is None else _f32(alpha, dev)
         B, M, A = mean.shape
         N = comp_u.shape[1]
-        amin = _f32(np.broadcast_to(np.asarray(a_min, np.float64), (A,)), dev)
-        amax = _f32(np.broadcast_to(np.asarray(a_max, np.float64), (A,)), dev)
+        amin = _bounds(a_min, A, dev)
+        amax = _bounds(a_max, A, dev)
         uni = None if uni_u is None else _f32(uni_u, dev)
         n_uni = 0 if uni is None else int(uni.shape[1])
         acts = torch.empty((B, N, A), dtype=torch.float32, device=dev)
@@ -455,8 +471,8 @@ class Critic:
         alpha = None if alpha is None else _f32(alpha, dev)
         B, M, A = mean.shape
         N = comp_u.shape[1]
-        amin = _f32(np.broadcast_to(np.asarray(a_min, np.float64), (A,)), dev)
-        amax = _f32(np.broadcast_to(np.asarray(a_max, np.float64), (A,)), dev)
+        amin = _bounds(a_min, A, dev)
+        amax = _bounds(a_max, A, dev)
         uni = None if uni_u is None else _f32(uni_u, dev)
         n_uni = 0 if uni is None else int(uni.shape[1])
         out = dict(idx=torch.empty((B, k), dtype=torch.int64, device=dev),
@@ -504,8 +520,8 @@ class Critic:
         iters = 1 + (0 if noise is None else noise.shape[0])
         noise = None if noise is None else _f32(noise, dev)
         comp_u = None if comp_u is None else _f32(comp_u, dev)
-        amin = _f32(np.broadcast_to(np.asarray(a_min, np.float64), (A,)), dev)
-        amax = _f32(np.broadcast_to(np.asarray(a_max, np.float64), (A,)), dev)
+        amin = _bounds(a_min, A, dev)
+        amax = _bounds(a_max, A, dev)
         w = torch.empty((B, num_modal), dtype=torch.float32, device=dev)
         mu = torch.empty((B, num_modal, A), dtype=torch.float32, device=dev)
         var = torch.empty((B, num_modal, A), dtype=torch.float32, device=dev)

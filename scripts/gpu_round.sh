@@ -10,6 +10,9 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG
 timeout 600 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc=$?"
 tail -c 3000 $OUT/bench_$TAG.json
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/bench_ref_$TAG.json 2>&1
+timeout 300 python scripts/bench_updates.py 2>/dev/null | grep "^{" > $OUT/updates_$TAG.jsonl
+timeout 300 python scripts/bench_configs.py 2>/dev/null | grep "^{" > $OUT/configs_$TAG.jsonl
+timeout 300 python scripts/bench_hbm_kernels.py 2>/dev/null | grep "^{" > $OUT/hbm_kernels_$TAG.jsonl
 if [ "${NCU:-1}" = "1" ]; then
   CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
   timeout 300 $CMD > $OUT/plain_$TAG.log 2>&1 &&
