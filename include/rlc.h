@@ -337,6 +337,55 @@ int rlc_replay_scatter(rlc_handle* h, float* state, float* action, float* reward
 int rlc_replay_sample(rlc_handle* h, int64_t n, int k, uint64_t seed, uint64_t counter, int64_t head,
                       int64_t cap, int64_t* idx_out, int64_t* slot_out, void* stream);
 
+/* ---- device-resident agent/environment loop ------------------------------------
+ * Replaces the per-step Python of Experiment.run_episode_train / run_episode_eval (experiment.py:101-214),
+ * BaseAgent.update (agents/base_agent.py:52-70) and the environments behind create_environment
+ * (environments/environments.py:16-37) for the two environments the shipped configs name on this path:
+ * gym 0.18.0 `Pendulum-v0` (requirements.txt:9; restated, gym is not vendored -> parity unpinned) and the
+ * Bimodal1DEnv* bandits (environments.py:158-764; pinned on the reference classes).  Environment state, replay
+ * ring and the cursors live in HBM; all randomness is drawn on the host from the reference's own streams and fed
+ * in as tensors, a chunk of steps ahead.  Every call is a few threads of scalar work meant to sit inside a
+ * captured graph between the policy forward pass and the update. */
+#define RLC_ENV_PENDULUM 0
+#define RLC_ENV_BIMODAL1D 1
+#define RLC_ENV_MAX_S 8
+typedef struct rlc_env {
+  int kind, S, A;
+  int episode_limit; /* EPISODE_STEPS_LIMIT (environments.py:52-59; 200 for Pendulum-v0, 1 for the bandits) */
+  double p[8];       /* BIMODAL1D: maxima1, maxima2, stddev1, stddev2, height1, height2 */
+} rlc_env;
+
+/* Reset E environments from rows cursor[0]..cursor[0]+E-1 of reset_feed[feed_rows,2] (host-drawn internal states:
+ * Pendulum (theta, thetadot) ~ U(-[pi,1],[pi,1]) from the env's np_random; bandits start at 0), write their
+ * observations obs[E,S], zero ep_step[E] / ep_ret[E] / ep_done[E] (the last two may be NULL) and advance the
+ * cursor by E (cursor may be NULL: rows 0..E-1). */
+int rlc_env_reset(rlc_handle* h, const rlc_env* env, int E, const double* reset_feed, int64_t feed_rows,
+                  int64_t* cursor, double* env_state, int* ep_step, double* ep_ret, int* ep_done, float* obs,
+                  void* stream);
+/* One evaluation step of E independent episodes (run_episode_eval, experiment.py:196-214): env.step(action[e]),
+ * ep_ret += reward, ep_step += 1, obs <- next observation; an episode freezes once done or at the step limit. */
+int rlc_env_step_eval(rlc_handle* h, const rlc_env* env, int E, double* env_state, int* ep_step, double* ep_ret,
+                      int* ep_done, float* obs, const float* action, void* stream);
+/* Append (ep_ret[E], ep_step[E]) as row cursor[0] of ret_log[log_rows,E] / steps_log[log_rows,E]; cursor[0] += 1. */
+int rlc_eval_store(rlc_handle* h, int E, const double* ep_ret, const int* ep_step, int64_t* cursor,
+                   int64_t log_rows, double* ret_log, int* steps_log, void* stream);
+/* One training step of one environment: env.step(action[A]) from (env_state, obs[S]); the transition
+ * (obs, action, reward, obs', done ? 0 : gamma) is appended to the replay ring (count = cur[1], head = cur[2];
+ * FIFO eviction when full) unless the step was cut by the episode limit (experiment.py:127-134; the bandits are
+ * exempt); reward_log[k] / flag_log[k] (bit0 done, bit1 truncated) with k = cur[0]; obs <- next observation, or on
+ * done the observation of reset_feed row cur[3]++; cur[0]++, cur[4]++ (total steps).  cur = int64[8]. */
+int rlc_env_step_train(rlc_handle* h, const rlc_env* env, int64_t* cur, double* env_state, int* ep_step,
+                       float* obs, const float* action, const double* reset_feed, int64_t reset_rows,
+                       float* rb_state, float* rb_action, float* rb_reward, float* rb_next_state, float* rb_gamma,
+                       int64_t cap, float gamma, int64_t log_rows, double* reward_log, int* flag_log, void* stream);
+/* Stage row k = (cur[0]-1) mod feed_rows (the row rlc_env_step_train just logged) of the host-drawn feeds into the fixed buffers a captured update reads: eps_act[A] <-
+ * eps_act_feed[k] (sample_action's N(0,1) draws), eps_upd[B,A] <- eps_upd_feed[k] (pi.evaluate's draws inside
+ * update_network), slots[B] <- (cur[2] + idx_feed[k,b]) % cap (RandomAccessQueue.sample_n_k's logical indices as
+ * ring slots).  eps_upd_feed / idx_feed may be NULL (steps before learning starts). */
+int rlc_loop_stage(rlc_handle* h, const int64_t* cur, int B, int A, int64_t feed_rows, const float* eps_act_feed,
+                   const float* eps_upd_feed, const int* idx_feed, int64_t cap, float* eps_act, float* eps_upd,
+                   int64_t* slots, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -472,6 +472,32 @@ def gen_full_updates(torch, forwardkl_network, reversekl_network):
     gen_full_update(torch, *R, "full_rkl_hardll_sac.npz", alpha=0.1, optim_type="hard_ll", q_update_type="sac", seed=7)
 
 
+def gen_bimodal_env():
+    """step() of the reference's seven Bimodal1D bandit classes on float32 action arrays (what the agents hand to
+    env.step): rewards and next states, for csrc/envloop.cu and oracle/oracle_env.py."""
+    import warnings
+    warnings.simplefilter("ignore", DeprecationWarning)
+    from environments import environments as envs
+    rng = np.random.RandomState(11)
+    actions = np.concatenate([np.linspace(-2, 2, 81), rng.uniform(-2, 2, 47)]).astype(np.float32)
+    save = {"actions": actions}
+    for name in ("Bimodal1DEnv", "Bimodal1DEnv_uneq_var1", "Bimodal1DEnv_uneq_var2", "Bimodal1DEnv_uneq_var3",
+                 "Bimodal1DEnv_eq_var1", "Bimodal1DEnv_eq_var2", "Bimodal1DEnv_eq_var3"):
+        env = envs.create_environment({"environment": name, "TotalMilSteps": 0.001, "EpisodeSteps": -1,
+                                       "EvalIntervalMilSteps": 0.0001, "EvalEpisodes": 1})
+        rew, nxt = [], []
+        for a in actions:
+            env.reset()
+            s2, r, done, _ = env.step(np.array([a], np.float32))
+            assert done is True and env.EPISODE_STEPS_LIMIT == 1
+            rew.append(float(r))
+            nxt.append(float(s2[0]))
+        save[name + "_reward"], save[name + "_next"] = np.array(rew, np.float64), np.array(nxt, np.float64)
+        save[name + "_bounds"] = np.array([env.state_min[0], env.state_max[0], env.action_min[0], env.action_max[0]])
+    np.savez_compressed(os.path.join(OUT, "bimodal_env.npz"), **save)
+    print("bimodal_env.npz written")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     install_stubs()
@@ -492,6 +518,7 @@ def main():
     gen_full_updates(torch, forwardkl_network, reversekl_network)
     gen_trueq()
     gen_gmm()
+    gen_bimodal_env()
     x, w = onp.clenshaw_curtis(64)
     np.savez_compressed(os.path.join(OUT, "cc.npz"), x64=x, w64=w)
 
@@ -505,5 +532,9 @@ if __name__ == "__main__":
         torch.set_num_threads(1)
         from agents.network import forwardkl_network, reversekl_network
         gen_full_updates(torch, forwardkl_network, reversekl_network)
+    elif len(sys.argv) > 1 and sys.argv[1] == "bimodal_env":     # only the bandit-environment fixture
+        install_stubs()
+        sys.path.insert(0, REF)
+        gen_bimodal_env()
     else:
         main()

@@ -28,6 +28,14 @@ class RlcMlp(C.Structure):
                 ("theta", C.c_void_p)]
 
 
+ENV_PENDULUM, ENV_BIMODAL1D = 0, 1
+
+
+class RlcEnv(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("S", C.c_int32), ("A", C.c_int32), ("episode_limit", C.c_int32),
+                ("p", C.c_double * 8)]
+
+
 class RlcError(RuntimeError):
     """Non-zero status from the C-ABI (map C status -> RuntimeError)."""
 
@@ -35,6 +43,7 @@ class RlcError(RuntimeError):
 _p, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
 _cr = C.POINTER(RlcCritic)
 _ml = C.POINTER(RlcMlp)
+_en = C.POINTER(RlcEnv)
 
 # name -> (restype, argtypes); must list every symbol include/rlc.h declares
 SIGNATURES = {
@@ -83,6 +92,12 @@ SIGNATURES = {
     "rlc_replay_gather": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p]),
     "rlc_replay_sample": (_i, [_p, _i64, _i, C.c_uint64, C.c_uint64, _i64, _i64, _p, _p, _p]),
     "rlc_replay_scatter": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p]),
+    "rlc_env_reset": (_i, [_p, _en, _i, _p, _i64, _p, _p, _p, _p, _p, _p, _p]),
+    "rlc_env_step_eval": (_i, [_p, _en, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "rlc_eval_store": (_i, [_p, _i, _p, _p, _p, _i64, _p, _p, _p]),
+    "rlc_env_step_train": (_i, [_p, _en, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _i64, _f, _i64, _p, _p,
+                                _p]),
+    "rlc_loop_stage": (_i, [_p, _p, _i, _i, _i64, _p, _p, _p, _i64, _p, _p, _p, _p]),
 }
 
 _lib = None

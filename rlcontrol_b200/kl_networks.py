@@ -207,7 +207,7 @@ class _KLNetwork(object):
         st.graph = None
         return st
 
-    def _enqueue(self, st, B):
+    def _enqueue(self, st, B, device_inputs=False):
         """One update on four streams (fork after the upload, join before the download); the dependency edges
         are exactly the data dependencies of update_network, so the captured graph runs the independent
         branches side by side: small batches are latency-bound, and this is what shortens the critical path.
@@ -224,7 +224,8 @@ class _KLNetwork(object):
         bt = B * self.world_size
         need_q_new = sac or not intg
         main, s_grid, s_v, s_pi = st.stream, st.s_grid, st.s_v, st.s_pi
-        st.in_dev.copy_(st.in_host, non_blocking=True)
+        if not device_inputs:                  # device_loop.py fills st.d[...] on the device (replay gather, staged draws)
+            st.in_dev.copy_(st.in_host, non_blocking=True)
         for br in (s_grid, s_v, s_pi):
             br.wait_stream(main)
         # forward passes, all on pre-update parameters (:131-137)
@@ -296,7 +297,8 @@ class _KLNetwork(object):
         self.critic_grid.invalidate()
         for br in (s_grid, s_v, s_pi):
             main.wait_stream(br)
-        st.out_host.copy_(o, non_blocking=True)
+        if not device_inputs:
+            st.out_host.copy_(o, non_blocking=True)
 
     def _snapshot(self):
         ts = [self.critic.theta, self.v.theta, self.pi.theta]
