@@ -386,6 +386,62 @@ int rlc_loop_stage(rlc_handle* h, const int64_t* cur, int B, int A, int64_t feed
                    const float* eps_upd_feed, const int* idx_feed, int64_t cap, float* eps_act, float* eps_upd,
                    int64_t* slots, void* stream);
 
+/* ---- small-minibatch fast path of the ForwardKL / ReverseKL update (cfg1 / cfg5) -------------------
+ * forwardkl_network.py:123-209 / reversekl_network.py:130-217 at B <= 64 rows: every B-row forward pass in ONE
+ * launch (rlc_sb_forward) and every backward pass + Adam (+ Polyak) in ONE launch (rlc_sb_update), around the
+ * B x N grid evaluation (rlc_critic_eval) and its reduction (rlc_reduce_{fkl,rkl}_policy).  theta layouts are those
+ * of rlc_mlp / rlc_critic (T-in): [W1 (in x H1) | b1 | W2 | b2 | W3 (H2 x O) | b3]. */
+#define RLC_SB_MAX_NETS 8
+#define RLC_SB_MAX_B 64
+#define RLC_SB_ROLE_DOUT 0 /* dLoss/dout given */
+#define RLC_SB_ROLE_V 1    /* value regression:  target = (r - alpha logp) + gamma v_next  |  sac: q_new - alpha logp */
+#define RLC_SB_ROLE_Q 2    /* critic regression: y = r + gamma v_next */
+#define RLC_SB_ROLE_PI 3   /* policy head: (dmean, dlog_std) through the log_std clamp; loss = mean_b loss_b */
+typedef struct rlc_sb_net {
+  const float* theta;
+  int inp, H1, H2, O;
+  const float* x0; /* input row b = [x0[b, 0:n0] | x1[b, 0:n1]], n0 + n1 == inp (Q(s,a): x0 = s, x1 = a) */
+  int n0;
+  const float* x1;
+  int n1;
+  float* h1;          /* out, optional: post-ReLU activations [B,H1] / [B,H2] kept for rlc_sb_update */
+  float* h2;
+  float* out;         /* out [B,O] */
+  float* w3_snapshot; /* out, optional [H2*O]: W3 as seen by this forward pass (rlc_sb_update reads it) */
+  int* adam_state;    /* optional int32[4]: ++step and derive the bias-correction factors, as rlc_adam_step_dev */
+  float lr, beta1, beta2;
+  int adam_variant;
+  int policy;         /* 1: O == 2A and PolicyNetwork.evaluate runs as the epilogue (as rlc_policy_evaluate) */
+  const float* eps;   /* [B,A] or NULL (mean action) */
+  float action_scale, log_std_min, log_std_max;
+  float *action, *logp, *mean, *mu_raw, *log_std, *z; /* any may be NULL */
+} rlc_sb_net;
+typedef struct rlc_sb_train {
+  float *theta, *m, *v; /* updated in place (torch/TF Adam as rlc_adam_step_dev) */
+  const int* adam_state; /* factors written by the rlc_sb_forward of the same update */
+  float beta1, beta2, eps;
+  float* target;         /* optional Polyak target: target += tau (theta_new - target) */
+  float tau;
+  int inp, H1, H2, O;
+  const float* x0;
+  int n0;
+  const float* x1;
+  int n1;
+  const float *h1, *h2, *out, *w3_snapshot; /* from rlc_sb_forward on the same x / theta */
+  int role;
+  const float* dout;                        /* ROLE_DOUT: [B,O] */
+  const float *r, *gamma, *v_next, *logp, *q_new; /* ROLE_V / ROLE_Q operands, [B] each */
+  const float *dmean, *dlog_std, *loss_b;   /* ROLE_PI: [B,A], [B,A], [B] (rlc_reduce_*_policy outputs) */
+  float log_std_min, log_std_max, entropy_scale;
+  int sac;
+  float* loss_out;                          /* optional scalar */
+} rlc_sb_train;
+/* All forward passes of nets[0..n_nets) on B <= RLC_SB_MAX_B rows, one launch. */
+int rlc_sb_forward(rlc_handle* h, const rlc_sb_net* nets, int n_nets, int B, void* stream);
+/* All backward passes + optimiser steps, one launch; gradients are means over B_total rows.  Parameters change in
+ * place; no gradient is written out (single-GPU path: the data-parallel update uses rlc_mlp_grads + all-reduce). */
+int rlc_sb_update(rlc_handle* h, const rlc_sb_train* nets, int n_nets, int B, int B_total, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,34 @@ class RlcError(RuntimeError):
     """Non-zero status from the C-ABI (map C status -> RuntimeError)."""
 
 
+SB_MAX_NETS, SB_MAX_B = 8, 64
+SB_ROLE_DOUT, SB_ROLE_V, SB_ROLE_Q, SB_ROLE_PI = 0, 1, 2, 3
+
+
+class RlcSbNet(C.Structure):
+    """rlc_sb_net (include/rlc.h): one forward pass of the small-minibatch fast path."""
+    _fields_ = [("theta", C.c_void_p), ("inp", C.c_int), ("H1", C.c_int), ("H2", C.c_int), ("O", C.c_int),
+                ("x0", C.c_void_p), ("n0", C.c_int), ("x1", C.c_void_p), ("n1", C.c_int),
+                ("h1", C.c_void_p), ("h2", C.c_void_p), ("out", C.c_void_p), ("w3_snapshot", C.c_void_p),
+                ("adam_state", C.c_void_p), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("adam_variant", C.c_int), ("policy", C.c_int), ("eps", C.c_void_p), ("action_scale", C.c_float),
+                ("log_std_min", C.c_float), ("log_std_max", C.c_float), ("action", C.c_void_p), ("logp", C.c_void_p),
+                ("mean", C.c_void_p), ("mu_raw", C.c_void_p), ("log_std", C.c_void_p), ("z", C.c_void_p)]
+
+
+class RlcSbTrain(C.Structure):
+    """rlc_sb_train (include/rlc.h): one backward pass + optimiser step of the small-minibatch fast path."""
+    _fields_ = [("theta", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("adam_state", C.c_void_p),
+                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("target", C.c_void_p),
+                ("tau", C.c_float), ("inp", C.c_int), ("H1", C.c_int), ("H2", C.c_int), ("O", C.c_int),
+                ("x0", C.c_void_p), ("n0", C.c_int), ("x1", C.c_void_p), ("n1", C.c_int),
+                ("h1", C.c_void_p), ("h2", C.c_void_p), ("out", C.c_void_p), ("w3_snapshot", C.c_void_p),
+                ("role", C.c_int), ("dout", C.c_void_p), ("r", C.c_void_p), ("gamma", C.c_void_p),
+                ("v_next", C.c_void_p), ("logp", C.c_void_p), ("q_new", C.c_void_p), ("dmean", C.c_void_p),
+                ("dlog_std", C.c_void_p), ("loss_b", C.c_void_p), ("log_std_min", C.c_float),
+                ("log_std_max", C.c_float), ("entropy_scale", C.c_float), ("sac", C.c_int), ("loss_out", C.c_void_p)]
+
+
 _p, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
 _cr = C.POINTER(RlcCritic)
 _ml = C.POINTER(RlcMlp)
@@ -97,6 +125,8 @@ SIGNATURES = {
     "rlc_eval_store": (_i, [_p, _i, _p, _p, _p, _i64, _p, _p, _p]),
     "rlc_env_step_train": (_i, [_p, _en, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _i64, _f, _i64, _p, _p,
                                 _p]),
+    "rlc_sb_forward": (_i, [_p, C.POINTER(RlcSbNet), _i, _i, _p]),
+    "rlc_sb_update": (_i, [_p, C.POINTER(RlcSbTrain), _i, _i, _i, _p]),
     "rlc_loop_stage": (_i, [_p, _p, _i, _i, _i64, _p, _p, _p, _i64, _p, _p, _p, _p]),
 }
 

@@ -5,6 +5,7 @@
 // and the log-likelihood policy gradients.  fp32 CUDA cores on the shared tiled SGEMM
 // (rows_gemm.cuh); everything is stream-ordered and graph-capturable.
 #include "rows_gemm.cuh"
+#include "policy_math.cuh"
 
 struct MlpView {
   int64_t oW1, ob1, oW2, ob2, oW3, ob3, numel;
@@ -163,32 +164,11 @@ __global__ void k_policy_evaluate(const float* __restrict__ head, const float* _
                                   float* __restrict__ log_std_out, float* __restrict__ z_out) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  const float LOG_SQRT_2PI = 0.9189385332046727f;
-  float lp = 0.f, corr = 0.f;
-  for (int d = 0; d < A; ++d) {
-    const float mu = head[(long long)b * 2 * A + d];
-    const float ls = fminf(fmaxf(head[(long long)b * 2 * A + A + d], lo), hi);
-    const float std = expf(ls);
-    const float e = eps ? eps[(long long)b * A + d] : 0.f;
-    float z;
-    if (A == 1) {
-      z = mu + std * e;
-      const float t = (z - mu);
-      lp += -(t * t) / (2.f * std * std) - ls - LOG_SQRT_2PI;
-    } else {
-      z = mu + sqrtf(std) * e;
-      const float t = (z - mu);
-      lp += -0.5f * (t * t) / std - 0.5f * ls - LOG_SQRT_2PI;
-    }
-    const float a = tanhf(z);
-    corr += logf(1.f - a * a + 1e-6f);
-    if (action) action[(long long)b * A + d] = a * scale;
-    if (mean_out) mean_out[(long long)b * A + d] = tanhf(mu) * scale;
-    if (mu_raw_out) mu_raw_out[(long long)b * A + d] = mu;
-    if (log_std_out) log_std_out[(long long)b * A + d] = ls;
-    if (z_out) z_out[(long long)b * A + d] = z;
-  }
-  if (logp) logp[b] = lp - corr;
+  const long long o = (long long)b * A;
+  policy_evaluate_row(head + 2 * o, eps ? eps + o : nullptr, A, scale, lo, hi, action ? action + o : nullptr,
+                      logp ? logp + b : nullptr, mean_out ? mean_out + o : nullptr,
+                      mu_raw_out ? mu_raw_out + o : nullptr, log_std_out ? log_std_out + o : nullptr,
+                      z_out ? z_out + o : nullptr);
 }
 
 extern "C" int rlc_policy_evaluate(rlc_handle* h, const float* head, const float* eps, int B, int A,

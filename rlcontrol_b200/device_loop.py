@@ -30,7 +30,7 @@ from typing import Sequence
 import numpy as np
 import torch
 
-from ._lib import ENV_BIMODAL1D, ENV_PENDULUM, RlcEnv, check
+from ._lib import ENV_BIMODAL1D, ENV_PENDULUM, SB_MAX_B, RlcEnv, RlcSbNet, check
 from .engine import _ptr, _stream
 from .kl_networks import LOG_STD_MAX, LOG_STD_MIN
 
@@ -193,10 +193,32 @@ class DeviceExperiment:
         self.st = network._build_step(B)
         self.stream = self.st.stream
         self._built = False
+        # small minibatches: the fused launches of csrc/small_batch.cu, with the Polyak step folded into V's Adam and
+        # the acting / evaluation policy passes as one launch each
+        self.small = network._small_ok(B) and E <= SB_MAX_B
+        if self.small:
+            network._build_small(self.st, B)
+            self.st.sb_upd[0].target, self.st.sb_upd[0].tau = network.target_v.theta.data_ptr(), network.tau
+            self.sb_act, self.sb_ev = self._policy_pass(self.obs, self.eps_act, self.head_act, self.act), \
+                self._policy_pass(self.ev_obs, None, self.head_ev, self.ev_act)
+
+    def _policy_pass(self, obs, eps, head, ev):
+        net, n = self.net, (RlcSbNet * 1)()
+        d = n[0]
+        d.theta, d.inp, d.H1, d.H2, d.O = net.pi.theta.data_ptr(), net.pi.inp, net.pi.H1, net.pi.H2, net.pi.O
+        d.x0, d.n0, d.n1, d.out, d.policy = obs.data_ptr(), net.pi.inp, 0, head.data_ptr(), 1
+        d.eps = None if eps is None else eps.data_ptr()
+        d.action_scale, d.log_std_min, d.log_std_max = net.action_scale, LOG_STD_MIN, LOG_STD_MAX
+        d.action, d.logp, d.mean, d.mu_raw, d.log_std, d.z = (ev[k].data_ptr() for k in
+                                                              ("action", "logp", "mean", "mu_raw", "log_std", "z"))
+        return n
 
     # ------------------------------------------------------------------ device pieces (enqueue on the current stream)
     def _act(self):
         net = self.net
+        if self.small:
+            check(self.lib.rlc_sb_forward(self.eng.h, self.sb_act, 1, 1, _stream()))
+            return
         net.pi.forward(self.obs, out=self.head_act)
         net.eng_pi.policy_evaluate(self.head_act, self.eps_act, net.action_scale, LOG_STD_MIN, LOG_STD_MAX, out=self.act)
 
@@ -226,7 +248,8 @@ class DeviceExperiment:
                                              self.B, _ptr(d["s"]), _ptr(d["a"]), _ptr(d["r"]), _ptr(d["s2"]), _ptr(d["g"]),
                                              _stream()))
             self.net._enqueue(self.st, self.B, device_inputs=True)
-            self.net.eng_v.soft_update(self.net.target_v.theta, self.net.v.theta, self.net.tau)
+            if not self.small:
+                self.net.eng_v.soft_update(self.net.target_v.theta, self.net.v.theta, self.net.tau)
         self._act()
 
     def _eval_session(self):
@@ -236,8 +259,11 @@ class DeviceExperiment:
                                      _ptr(self.ev_cursor_reset), _ptr(self.ev_state), _ptr(self.ev_step),
                                      _ptr(self.ev_ret), _ptr(self.ev_done), _ptr(self.ev_obs), _stream()))
         for _ in range(sp.episode_limit):
-            net.pi.forward(self.ev_obs, out=self.head_ev)
-            net.eng_pi.policy_evaluate(self.head_ev, None, net.action_scale, LOG_STD_MIN, LOG_STD_MAX, out=self.ev_act)
+            if self.small:
+                check(self.lib.rlc_sb_forward(self.eng.h, self.sb_ev, 1, E, _stream()))
+            else:
+                net.pi.forward(self.ev_obs, out=self.head_ev)
+                net.eng_pi.policy_evaluate(self.head_ev, None, net.action_scale, LOG_STD_MIN, LOG_STD_MAX, out=self.ev_act)
             check(self.lib.rlc_env_step_eval(self.eng.h, C.byref(sp.desc), E, _ptr(self.ev_state), _ptr(self.ev_step),
                                              _ptr(self.ev_ret), _ptr(self.ev_done), _ptr(self.ev_obs),
                                              _ptr(self.ev_act["mean"]), _stream()))

@@ -25,8 +25,11 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from ._lib import ADAM_TORCH, LAYOUT_OUT_IN, TIN
-from .engine import Critic, Engine, Mlp, _f32
+import ctypes as C
+
+from ._lib import (ADAM_TORCH, LAYOUT_OUT_IN, SB_MAX_B, SB_ROLE_PI, SB_ROLE_Q, SB_ROLE_V, TIN, RlcSbNet, RlcSbTrain,
+                   check)
+from .engine import Critic, Engine, Mlp, _f32, _ptr, _stream
 from .quadrature import integration_grid
 
 LOG_STD_MIN, LOG_STD_MAX = -20.0, 2.0          # PolicyNetwork defaults, forwardkl_network.py:294
@@ -155,6 +158,9 @@ class _KLNetwork(object):
         self._act = {}                        # batch size -> action-selection buffers
         # NCCL inside a multi-stream capture is not worth the risk: the data-parallel update runs eagerly
         self.use_graph = bool(getattr(config, "use_cuda_graph", True)) and self.world_size == 1
+        # small minibatches (cfg1 / cfg5): all B-row forward passes in one launch, all backward passes + Adam in one
+        # launch (csrc/small_batch.cu) instead of ~60 dependent small kernels
+        self.fused_small = bool(getattr(config, "fused_small_batch", True))
 
     # ------------------------------------------------------------------ parameter access (tests, checkpoints)
     def load_reference_parameters(self, q, v, target_v, pi):
@@ -207,6 +213,94 @@ class _KLNetwork(object):
         st.graph = None
         return st
 
+    def _small_ok(self, B):
+        dims = (self.pi.H1, self.pi.H2, self.critic.H1, self.critic.H2)
+        return (self.fused_small and self.world_size == 1 and B <= SB_MAX_B and self.optim_type in ("intg", "hard_intg")
+                and max(dims) <= 512 and self.state_dim + self.action_dim <= 256 and 2 * self.action_dim <= 32)
+
+    def _build_small(self, st, B):
+        """Descriptors of the two fused launches (kept alive on ``st``; the C side copies them at launch)."""
+        dev, S, A, d = self.device, self.state_dim, self.action_dim, st.d
+        f = lambda *sh: torch.zeros(sh, dtype=torch.float32, device=dev)
+        st.sb_buf = dict(h1v=f(B, self.v.H1), h2v=f(B, self.v.H2), h1p=f(B, self.pi.H1), h2p=f(B, self.pi.H2),
+                         h1q=f(B, self.critic.H1), h2q=f(B, self.critic.H2), w3v=f(self.v.H2), w3p=f(self.pi.H2 * 2 * A),
+                         w3q=f(self.critic.H2), h1t=f(B, self.v.H1), h2t=f(B, self.v.H2))
+        bf = st.sb_buf
+        p = lambda t: None if t is None else t.data_ptr()
+        sac = self.q_update_type == "sac"
+        fwd = (RlcSbNet * 4)()
+
+        def net(n, theta, inp, H1, H2, O, x0, n0, x1, n1, h1, h2, out, w3, opt):
+            n.theta, n.inp, n.H1, n.H2, n.O = p(theta), inp, H1, H2, O
+            n.x0, n.n0, n.x1, n.n1 = p(x0), n0, p(x1), n1
+            n.h1, n.h2, n.out, n.w3_snapshot = p(h1), p(h2), p(out), p(w3)
+            if opt is not None:
+                n.adam_state, n.lr, n.beta1, n.beta2, n.adam_variant = p(opt.state_dev), opt.lr, 0.9, 0.999, ADAM_TORCH
+        net(fwd[0], self.v.theta, S, self.v.H1, self.v.H2, 1, d["s"], S, None, 0, bf["h1v"], bf["h2v"], st.v_out, bf["w3v"],
+            self.v_opt)
+        net(fwd[1], self.target_v.theta, S, self.v.H1, self.v.H2, 1, d["s2"], S, None, 0, None, None, st.vnext, None, None)
+        net(fwd[2], self.pi.theta, S, self.pi.H1, self.pi.H2, 2 * A, d["s"], S, None, 0, bf["h1p"], bf["h2p"], st.head,
+            bf["w3p"], self.pi_opt)
+        n = fwd[2]
+        n.policy, n.eps, n.action_scale, n.log_std_min, n.log_std_max = 1, p(d["eps"]), self.action_scale, LOG_STD_MIN, LOG_STD_MAX
+        ev = st.ev
+        n.action, n.logp, n.mean, n.mu_raw, n.log_std, n.z = (p(ev[k]) for k in ("action", "logp", "mean", "mu_raw", "log_std", "z"))
+        net(fwd[3], self.critic.theta, S + A, self.critic.H1, self.critic.H2, 1, d["s"], S, d["a"], A, bf["h1q"], bf["h2q"],
+            st.q_reg, bf["w3q"], self.q_opt)
+        st.sb_fwd = fwd
+        fwd2 = (RlcSbNet * 1)()                       # 'sac': Q(s, a_new) needs the policy's sample first (:143-146)
+        net(fwd2[0], self.critic.theta, S + A, self.critic.H1, self.critic.H2, 1, d["s"], S, ev["action"], A, None, None,
+            st.q_new, None, None)
+        st.sb_fwd2 = fwd2
+        upd = (RlcSbTrain * 3)()
+
+        def tr(n, role, theta, opt, inp, H1, H2, O, x0, n0, x1, n1, h1, h2, out, w3, loss):
+            n.theta, n.m, n.v, n.adam_state = p(theta), p(opt.m), p(opt.v), p(opt.state_dev)
+            n.beta1, n.beta2, n.eps = 0.9, 0.999, 1e-8
+            n.inp, n.H1, n.H2, n.O, n.x0, n.n0, n.x1, n.n1 = inp, H1, H2, O, p(x0), n0, p(x1), n1
+            n.h1, n.h2, n.out, n.w3_snapshot, n.role, n.loss_out = p(h1), p(h2), p(out), p(w3), role, p(loss)
+            n.r, n.gamma, n.v_next, n.logp, n.q_new = p(d["r"]), p(d["g"]), p(st.vnext), p(ev["logp"]), p(st.q_new)
+            n.entropy_scale, n.sac = self.entropy_scale, int(sac)
+            n.log_std_min, n.log_std_max = LOG_STD_MIN, LOG_STD_MAX
+        o = st.out_dev
+        tr(upd[0], SB_ROLE_V, self.v.theta, self.v_opt, S, self.v.H1, self.v.H2, 1, d["s"], S, None, 0, bf["h1v"], bf["h2v"],
+           st.v_out, bf["w3v"], o[1:2])
+        tr(upd[1], SB_ROLE_Q, self.critic.theta, self.q_opt, S + A, self.critic.H1, self.critic.H2, 1, d["s"], S, d["a"], A,
+           bf["h1q"], bf["h2q"], st.q_reg, bf["w3q"], o[0:1])
+        tr(upd[2], SB_ROLE_PI, self.pi.theta, self.pi_opt, S, self.pi.H1, self.pi.H2, 2 * A, d["s"], S, None, 0, bf["h1p"],
+           bf["h2p"], st.head, bf["w3p"], o[2:3])
+        upd[2].dmean, upd[2].dlog_std, upd[2].loss_b = p(st.dmean), p(st.dls), p(st.loss_b)
+        st.sb_upd = upd
+
+    def _enqueue_small(self, st, B, device_inputs=False):
+        """The same update as :meth:`_enqueue` in five launches: grid evaluation (side stream) || all forward passes ->
+        FKL/RKL reduction with get_logprob fused (2) -> all backward passes + Adam."""
+        if getattr(st, "sb_fwd", None) is None:
+            self._build_small(st, B)
+        lib, alpha = self.eng.lib, self.entropy_scale
+        main, s_grid = st.stream, st.s_grid
+        if not device_inputs:
+            st.in_dev.copy_(st.in_host, non_blocking=True)
+        s_grid.wait_stream(main)
+        with torch.cuda.stream(s_grid):
+            self.critic_grid.eval_into(st.d["s"], self.intgrl_actions, st.q_grid, self.precision)   # pre-update theta_Q
+        check(lib.rlc_sb_forward(self.eng.h, st.sb_fwd, 4, B, _stream()))
+        if self.q_update_type == "sac":
+            check(lib.rlc_sb_forward(self.eng.h, st.sb_fwd2, 1, B, _stream()))
+        main.wait_stream(s_grid)
+        if self.KIND == "fkl":
+            self.eng.fkl_policy(st.q_grid, self.intgrl_weights, self.intgrl_actions, self.action_scale, st.ev["mu_raw"],
+                                st.ev["log_std"], alpha, b_total=B, out=(st.loss_b, st.dmean, st.dls))
+        else:
+            self.eng.rkl_policy(st.q_grid, st.v_out.view(-1), self.intgrl_weights, self.intgrl_actions, self.action_scale,
+                                st.ev["mu_raw"], st.ev["log_std"], alpha, hard=self.optim_type == "hard_intg", b_total=B,
+                                out=(st.loss_b, st.dmean, st.dls))
+        check(lib.rlc_sb_update(self.eng.h, st.sb_upd, 3, B, B, _stream()))
+        self.critic.invalidate()
+        self.critic_grid.invalidate()
+        if not device_inputs:
+            st.out_host.copy_(st.out_dev, non_blocking=True)
+
     def _enqueue(self, st, B, device_inputs=False):
         """One update on four streams (fork after the upload, join before the download); the dependency edges
         are exactly the data dependencies of update_network, so the captured graph runs the independent
@@ -217,6 +311,8 @@ class _KLNetwork(object):
             s_v   : V(s), V_targ(s')          ... -> V grads -> Adam(theta_V)
             s_grid: Q on the B x N grid with the PRE-update theta_Q -> reduction -> head grad -> pi grads -> Adam(theta_pi)
         """
+        if self._small_ok(B):
+            return self._enqueue_small(st, B, device_inputs)
         eng, d, o = self.eng, st.d, st.out_dev
         alpha, sac = self.entropy_scale, self.q_update_type == "sac"
         intg = self.optim_type in ("intg", "hard_intg")

@@ -13,6 +13,7 @@ timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/bench_r
 timeout 300 python scripts/bench_updates.py 2>/dev/null | grep "^{" > $OUT/updates_$TAG.jsonl
 timeout 300 python scripts/bench_configs.py 2>/dev/null | grep "^{" > $OUT/configs_$TAG.jsonl
 timeout 300 python scripts/bench_hbm_kernels.py 2>/dev/null | grep "^{" > $OUT/hbm_kernels_$TAG.jsonl
+timeout 300 python scripts/bench_device_loop.py 5000 8 2>/dev/null | grep "^{" > $OUT/device_loop_$TAG.jsonl
 if [ "${NCU:-1}" = "1" ]; then
   CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
   timeout 300 $CMD > $OUT/plain_$TAG.log 2>&1 &&

@@ -239,3 +239,98 @@ def test_dropin_two_action_dims_matches_oracle(eng):
             for i, (m, r_) in enumerate(zip(mine[k], ref)):
                 move = np.abs(r_ - p[k][i]).max() + 1e-12
                 assert np.abs(m.reshape(r_.shape) - r_).max() <= 1e-2 * move + 1e-6, (kind, k, i)
+
+
+# ---------------------------------------------------------------------------------------------
+# small-minibatch fast path (csrc/small_batch.cu): the two fused launches against the oracle, through the C-ABI
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,inp,H1,H2,O", [(32, 3, 200, 200, 2), (7, 5, 33, 17, 3), (64, 23, 400, 300, 1), (1, 3, 64, 48, 4),
+                                           (9, 4, 16, 200, 1)])
+def test_small_batch_forward_and_update_match_oracle(eng, B, inp, H1, H2, O):
+    import ctypes as C
+    import torch
+    from rlcontrol_b200 import _lib
+    from rlcontrol_b200._lib import check
+    rng = np.random.RandomState(B * 7 + O)
+    p = _rand_mlp(rng, inp, H1, H2, O)
+    n0 = inp // 2                                                     # two-part input rows, like Q(s, a)
+    x = rng.randn(B, inp).astype(np.float32)
+    dout = rng.randn(B, O).astype(np.float32)
+    dev = eng.device
+    m = rb_mlp(eng, inp, H1, H2, O, p)
+    theta0 = m.theta.clone()
+    x0, x1 = _t(eng, x[:, :n0].copy()), _t(eng, x[:, n0:].copy())
+    z = lambda *sh: torch.zeros(sh, dtype=torch.float32, device=dev)
+    h1, h2, out, w3 = z(B, H1), z(B, H2), z(B, O), z(H2 * O)
+    state = torch.zeros((4,), dtype=torch.int32, device=dev)
+    state[0] = 4                                                      # the fifth Adam step
+    mom, var, target = _t(eng, rng.randn(m.theta.numel()) * 1e-2), _t(eng, rng.rand(m.theta.numel()) * 1e-3), m.theta.clone() + 0.5
+    mom0, var0, target0 = mom.clone(), var.clone(), target.clone()
+    lr, tau = 1e-2, 0.05
+    net = (_lib.RlcSbNet * 1)()
+    n = net[0]
+    n.theta, n.inp, n.H1, n.H2, n.O = m.theta.data_ptr(), inp, H1, H2, O
+    n.x0, n.n0, n.x1, n.n1 = (x0.data_ptr() if n0 else None), n0, x1.data_ptr(), inp - n0
+    n.h1, n.h2, n.out, n.w3_snapshot = h1.data_ptr(), h2.data_ptr(), out.data_ptr(), w3.data_ptr()
+    n.adam_state, n.lr, n.beta1, n.beta2, n.adam_variant = state.data_ptr(), lr, 0.9, 0.999, 0
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(eng.lib.rlc_sb_forward(eng.h, net, 1, B, st))
+    ref_out, cache = okl.mlp_forward(x, *p)
+    np.testing.assert_allclose(out.cpu().numpy(), ref_out, rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(h1.cpu().numpy(), np.maximum(cache[1], 0), rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(h2.cpu().numpy(), np.maximum(cache[3], 0), rtol=2e-5, atol=2e-5)
+    np.testing.assert_array_equal(w3.cpu().numpy().reshape(H2, O), p[4].T)
+    assert int(state[0]) == 5
+    tr = (_lib.RlcSbTrain * 1)()
+    t = tr[0]
+    d_dev = _t(eng, dout)
+    t.theta, t.m, t.v, t.adam_state = m.theta.data_ptr(), mom.data_ptr(), var.data_ptr(), state.data_ptr()
+    t.beta1, t.beta2, t.eps, t.target, t.tau = 0.9, 0.999, 1e-8, target.data_ptr(), tau
+    t.inp, t.H1, t.H2, t.O, t.x0, t.n0, t.x1, t.n1 = inp, H1, H2, O, n.x0, n0, n.x1, inp - n0
+    t.h1, t.h2, t.out, t.w3_snapshot, t.role, t.dout = n.h1, n.h2, n.out, n.w3_snapshot, _lib.SB_ROLE_DOUT, d_dev.data_ptr()
+    check(eng.lib.rlc_sb_update(eng.h, tr, 1, B, B, st))
+    # reference: oracle gradients, then torch-flavoured Adam (step 5) and the Polyak step, in float64
+    g = okl.mlp_grads(cache, dout, p[2], p[4])
+    flat = np.concatenate([(a.T if a.ndim == 2 else a).reshape(-1) for a in g])           # theta is [in,out]-major
+    m1 = 0.9 * mom0.cpu().numpy().astype(np.float64) + 0.1 * flat
+    v1 = 0.999 * var0.cpu().numpy().astype(np.float64) + 0.001 * flat * flat
+    step = lr / (1 - 0.9 ** 5) * m1 / (np.sqrt(v1) / np.sqrt(1 - 0.999 ** 5) + 1e-8)
+    want = theta0.cpu().numpy().astype(np.float64) - step
+    np.testing.assert_allclose(mom.cpu().numpy(), m1, rtol=1e-4, atol=1e-6 * max(1.0, np.abs(flat).max()))
+    np.testing.assert_allclose(var.cpu().numpy(), v1, rtol=1e-4, atol=1e-9)
+    got = m.theta.cpu().numpy()
+    np.testing.assert_allclose(got - theta0.cpu().numpy(), -step, rtol=2e-3, atol=2e-6)
+    np.testing.assert_allclose(target.cpu().numpy(), target0.cpu().numpy() + tau * (want - target0.cpu().numpy()), rtol=1e-5, atol=1e-6)
+
+
+def rb_mlp(eng, inp, H1, H2, O, p):
+    import rlcontrol_b200 as rb
+    return rb.Mlp(eng, inp, H1, H2, O).load_torch(*p)
+
+
+@pytest.mark.parametrize("name", FULL)
+def test_small_batch_path_equals_generic_path(eng, name):
+    """The fused launches and the generic multi-kernel update are the same arithmetic in a different summation order
+    (the recorded reference run above goes through the fused path wherever it applies)."""
+    from rlcontrol_b200 import kl_networks
+    g, pre, _ = load_full(name)
+    cls = kl_networks.ForwardKLNetwork if "fkl" in name else kl_networks.ReverseKLNetwork
+    outs = []
+    for fused in (True, False):
+        net = cls(None, None, _config(eng, g, fused_small_batch=fused))
+        if fused and not net._small_ok(int(g["s"].shape[1])):
+            pytest.skip("variant not covered by the fused path (likelihood-ratio optim types)")
+        assert fused or not net._small_ok(int(g["s"].shape[1]))
+        net.load_reference_parameters(pre["q"], pre["v"], pre["tv"], pre["pi"])
+        losses = []
+        for u in range(g["s"].shape[0]):
+            net.update_network(g["s"][u], g["a"][u], g["s2"][u], g["r"][u], g["g"][u], eps=g["eps"][u])
+            net.update_target_network()
+            losses.append(net.last_losses.copy())
+        outs.append((net.export_parameters(), np.array(losses)))
+    (pa, la), (pb, lb) = outs
+    np.testing.assert_allclose(la, lb, rtol=2e-4, atol=1e-6)
+    for k in ("q", "v", "tv", "pi"):
+        for i, (a, b) in enumerate(zip(pa[k], pb[k])):
+            move = np.abs(np.asarray(b) - pre[k][i].reshape(np.asarray(b).shape)).max() + 1e-12
+            assert np.abs(a - b).max() <= 2e-3 * move + 2e-7, (k, i)
