@@ -400,11 +400,14 @@ int rlc_loop_stage(rlc_handle* h, const int64_t* cur, int B, int A, int64_t feed
 typedef struct rlc_sb_net {
   const float* theta;
   int inp, H1, H2, O;
-  const float* x0; /* input row b = [x0[b, 0:n0] | x1[b, 0:n1]], n0 + n1 == inp (Q(s,a): x0 = s, x1 = a) */
+  const float* x0; /* input row r = [x0[r / x0_div, 0:n0] | x1[r % x1_mod, 0:n1]], n0 + n1 == inp */
   int n0;
   const float* x1;
   int n1;
-  float* h1;          /* out, optional: post-ReLU activations [B,H1] / [B,H2] kept for rlc_sb_update */
+  int rows;           /* rows of this pass; 0 = the call's B.  With x0_div = x1_mod = N and rows = B*N this is the
+                       * un-materialised B x N stack of row a1/a2 (x0 = s[B,S], x1 = grid[N,A], out = q[B,N]) */
+  int x0_div, x1_mod; /* 0 = identity (row r of x0 / x1) */
+  float* h1;          /* out, optional: post-ReLU activations [rows,H1] / [rows,H2] kept for rlc_sb_update */
   float* h2;
   float* out;         /* out [B,O] */
   float* w3_snapshot; /* out, optional [H2*O]: W3 as seen by this forward pass (rlc_sb_update reads it) */
@@ -436,7 +439,8 @@ typedef struct rlc_sb_train {
   int sac;
   float* loss_out;                          /* optional scalar */
 } rlc_sb_train;
-/* All forward passes of nets[0..n_nets) on B <= RLC_SB_MAX_B rows, one launch. */
+/* All forward passes of nets[0..n_nets) in one launch: B <= RLC_SB_MAX_B rows each unless a net sets `rows`
+ * (<= 65536). */
 int rlc_sb_forward(rlc_handle* h, const rlc_sb_net* nets, int n_nets, int B, void* stream);
 /* All backward passes + optimiser steps, one launch; gradients are means over B_total rows.  Parameters change in
  * place; no gradient is written out (single-GPU path: the data-parallel update uses rlc_mlp_grads + all-reduce). */

@@ -48,6 +48,7 @@ class RlcSbNet(C.Structure):
     """rlc_sb_net (include/rlc.h): one forward pass of the small-minibatch fast path."""
     _fields_ = [("theta", C.c_void_p), ("inp", C.c_int), ("H1", C.c_int), ("H2", C.c_int), ("O", C.c_int),
                 ("x0", C.c_void_p), ("n0", C.c_int), ("x1", C.c_void_p), ("n1", C.c_int),
+                ("rows", C.c_int), ("x0_div", C.c_int), ("x1_mod", C.c_int),
                 ("h1", C.c_void_p), ("h2", C.c_void_p), ("out", C.c_void_p), ("w3_snapshot", C.c_void_p),
                 ("adam_state", C.c_void_p), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
                 ("adam_variant", C.c_int), ("policy", C.c_int), ("eps", C.c_void_p), ("action_scale", C.c_float),

@@ -12,17 +12,30 @@
 //                     crosses CTAs, so there is no grid synchronisation: every CTA reads only pre-update values (its
 //                     own W2 rows staged in shared memory, W3 from a snapshot taken by the forward launch).
 // Latency-bound by construction (a few CTAs, ~1 MB of traffic): no roofline claim; the measure is us per update.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "policy_math.cuh"
 
-#define SB_ROWS 8        // minibatch rows per forward CTA
+#define SB_ROWS 16       // rows per forward CTA
 #define SB_THREADS 256
 #define SB_NI 16         // hidden-1 units per backward CTA
+#define SB_KC 16         // weight rows per ring stage
+#define SB_NST 4         // ring stages (bulk copies in flight: SB_NST * SB_KC * J * 4 bytes, 51 KB at J = 200)
+#define SB_WAIT_LIMIT (1u << 26)
 
 struct SbFwdArgs {
   rlc_sb_net net[RLC_SB_MAX_NETS];
+  int cta_base[RLC_SB_MAX_NETS + 1];
   int n_nets, B;
+  unsigned long long* dbg;   // RLC_SB_DEBUG: %globaltimer trace of CTA 0 / thread 0 (debug builds of the timing scripts)
 };
+__device__ __forceinline__ unsigned long long sb_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define SB_TRACE(slot) do { if (dbg && threadIdx.x == 0 && blockIdx.x == 0) dbg[slot] = sb_now(); } while (0)
 struct SbUpdArgs {
   rlc_sb_train net[RLC_SB_MAX_NETS];
   int cta_base[RLC_SB_MAX_NETS + 1];
@@ -30,43 +43,178 @@ struct SbUpdArgs {
   float inv_btotal;
 };
 
-__device__ __forceinline__ float sb_x(const rlc_sb_net& n, int b, int k) {
-  return k < n.n0 ? n.x0[(long long)b * n.n0 + k] : n.x1[(long long)b * n.n1 + (k - n.n0)];
+__device__ __forceinline__ uint32_t sb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sb_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sb_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sb_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ bool sb_mbar_wait(uint32_t bar, uint32_t parity) {   // bounded: never hangs the GPU
+  uint32_t ok = 0, spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok && ++spins < SB_WAIT_LIMIT);
+  return ok != 0;
+}
+
+__device__ __forceinline__ float sb_x(const rlc_sb_net& n, int r, int k) {
+  if (k < n.n0) return n.x0[(long long)(n.x0_div ? r / n.x0_div : r) * n.n0 + k];
+  return n.x1[(long long)(n.x1_mod ? r % n.x1_mod : r) * n.n1 + (k - n.n0)];
 }
 __device__ __forceinline__ float sb_xt(const rlc_sb_train& n, int b, int k) {
   return k < n.n0 ? n.x0[(long long)b * n.n0 + k] : n.x1[(long long)b * n.n1 + (k - n.n0)];
 }
 
-// one layer for SB_ROWS rows: out[r][j] = bias[j] + sum_k in[k][r] * W[k][j]; `in` is k-major in shared memory so a
-// thread reads its 8 row operands as two broadcast float4.
+// The weights of one layer, W[K][J] row-major in HBM/L2, streamed through a ring of SB_NST shared-memory stages of
+// SB_KC rows each.  When every row segment is 16-byte aligned the stages are filled by cp.async.bulk (one elected
+// thread, mbarrier complete_tx): ~50 KB in flight per CTA without a register of staging -- the first version read W
+// with __ldg inside the k loop and was bound by L2 latency (17.8 us for four 32-row passes).  Odd shapes fall back to
+// cooperative loads of the stage at the point of use.
+struct SbRing {
+  float* buf;        // [SB_NST][SB_KC][jc]
+  uint32_t bar0;     // SB_NST mbarriers
+  uint32_t uses;     // stage fills so far (running over all layers: parity = (uses / SB_NST) & 1)
+};
+
+__device__ __forceinline__ void sb_fma16(float (&acc)[4][4], const float4 a, const float4 w) {
+  acc[0][0] = fmaf(a.x, w.x, acc[0][0]); acc[0][1] = fmaf(a.y, w.x, acc[0][1]);
+  acc[0][2] = fmaf(a.z, w.x, acc[0][2]); acc[0][3] = fmaf(a.w, w.x, acc[0][3]);
+  acc[1][0] = fmaf(a.x, w.y, acc[1][0]); acc[1][1] = fmaf(a.y, w.y, acc[1][1]);
+  acc[1][2] = fmaf(a.z, w.y, acc[1][2]); acc[1][3] = fmaf(a.w, w.y, acc[1][3]);
+  acc[2][0] = fmaf(a.x, w.z, acc[2][0]); acc[2][1] = fmaf(a.y, w.z, acc[2][1]);
+  acc[2][2] = fmaf(a.z, w.z, acc[2][2]); acc[2][3] = fmaf(a.w, w.z, acc[2][3]);
+  acc[3][0] = fmaf(a.x, w.w, acc[3][0]); acc[3][1] = fmaf(a.y, w.w, acc[3][1]);
+  acc[3][2] = fmaf(a.z, w.w, acc[3][2]); acc[3][3] = fmaf(a.w, w.w, acc[3][3]);
+}
+
+// out(r, j) = bias[j] + sum_k in_s[k][r] * W[k][j] for the CTA's 16 rows; `in_s` is k-major ([K][16]).  A thread owns a
+// 4-column x 4-row register tile: per k it reads its 4 weights and its 4 row operands as ONE float4 each (the row
+// operands are a warp-wide broadcast) for 16 FMAs.  The first version gave a thread one column and all 16 rows: four
+// broadcast float4 per k per thread, and the load/store unit's return bandwidth (4 cycles per 128-bit warp load), not
+// the FMA pipe, set the pace (%globaltimer trace: 500 ns per 8-row chunk).  Row groups beyond `nrows` (padding rows
+// of a short pass, e.g. the single row of sample_action) do not compute.  f(j, r, v) consumes one finished value.
+template <class F>
 __device__ __forceinline__ void sb_layer(const float* __restrict__ W, const float* __restrict__ bias, int K, int J,
-                                         const float* __restrict__ in_s, int j, float acc[SB_ROWS]) {
-  const float bj = bias[j];
+                                         const float* __restrict__ in_s, int nrows, SbRing& ring, F f,
+                                         unsigned long long* dbg = nullptr, int dbg0 = 0) {
+  const int tid = threadIdx.x, cq = tid & 63, rg = tid >> 6;
+  const bool row_active = 4 * rg < nrows;
+  for (int jb = 0; jb < J; jb += SB_THREADS) {
+    const int jc = min(SB_THREADS, J - jb), js = (jc + 3) & ~3;       // stage row stride (floats)
+    const bool bulk = ((((uintptr_t)(W + jb)) & 15) == 0) && ((J & 3) == 0) && ((jc & 3) == 0);
+    const int nch = (K + SB_KC - 1) / SB_KC;
+    const uint32_t base_use = ring.uses;
+    auto issue = [&](int c) {   // thread 0 only
+      const int st = (base_use + c) % SB_NST, k0 = c * SB_KC, nk = min(SB_KC, K - k0);
+      const uint32_t bar = ring.bar0 + 8 * st;
+      float* dst = ring.buf + (size_t)st * SB_KC * SB_THREADS;      // stage rows are dense: stride jc
+      sb_mbar_expect_tx(bar, (uint32_t)(nk * jc * 4));
+      if (jc == J) {             // the chunk's rows are contiguous in HBM: ONE copy (a single thread issues these)
+        sb_bulk_g2s(sb_smem_u32(dst), W + (long long)k0 * J, (uint32_t)(nk * J * 4), bar);
+      } else {
+        for (int kk = 0; kk < nk; ++kk)
+          sb_bulk_g2s(sb_smem_u32(dst + kk * jc), W + (long long)(k0 + kk) * J + jb, (uint32_t)(jc * 4), bar);
+      }
+    };
+    // (no proxy fence before refilling a stage: its previous contents were only READ through the generic proxy, and
+    //  the __syncthreads orders those reads before the copy is issued)
+    if (bulk && tid == 0)
+      for (int c = 0; c < min(SB_NST, nch); ++c) issue(c);
+    const bool col_active = 4 * cq < jc;
+    float acc[4][4];   // [column][row]
 #pragma unroll
-  for (int r = 0; r < SB_ROWS; ++r) acc[r] = bj;
-#pragma unroll 4
-  for (int k = 0; k < K; ++k) {
-    const float w = __ldg(W + (long long)k * J + j);
-    const float4 a = *reinterpret_cast<const float4*>(in_s + k * SB_ROWS);
-    const float4 c = *reinterpret_cast<const float4*>(in_s + k * SB_ROWS + 4);
-    acc[0] = fmaf(a.x, w, acc[0]); acc[1] = fmaf(a.y, w, acc[1]);
-    acc[2] = fmaf(a.z, w, acc[2]); acc[3] = fmaf(a.w, w, acc[3]);
-    acc[4] = fmaf(c.x, w, acc[4]); acc[5] = fmaf(c.y, w, acc[5]);
-    acc[6] = fmaf(c.z, w, acc[6]); acc[7] = fmaf(c.w, w, acc[7]);
+    for (int q = 0; q < 4; ++q) {
+      const float bj = (col_active && 4 * cq + q < jc) ? bias[jb + 4 * cq + q] : 0.f;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[q][r] = bj;
+    }
+    for (int c = 0; c < nch; ++c) {
+      const uint32_t use = base_use + c;
+      const int st = use % SB_NST, k0 = c * SB_KC, nk = min(SB_KC, K - k0);
+      const float* wst = ring.buf + (size_t)st * SB_KC * SB_THREADS;
+      if (bulk) {
+        sb_mbar_wait(ring.bar0 + 8 * st, (use / SB_NST) & 1);
+        SB_TRACE(dbg0 + 2 * c);
+      } else {
+        float* wdst = ring.buf + (size_t)st * SB_KC * SB_THREADS;
+        for (int i = tid; i < nk * js; i += SB_THREADS) {
+          const int kk = i / js, jj = i % js;
+          wdst[i] = jj < jc ? __ldg(W + (long long)(k0 + kk) * J + jb + jj) : 0.f;
+        }
+        __syncthreads();
+      }
+      if (col_active && row_active) {
+        const float* wp = wst + 4 * cq;
+        const float* ap = in_s + k0 * SB_ROWS + 4 * rg;
+        if (nk == SB_KC) {       // full chunk: branch-free, operands of 4 k steps loaded ahead of their 64 FMAs
+#pragma unroll
+          for (int kk0 = 0; kk0 < SB_KC; kk0 += 4) {
+            float4 w[4], a[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              w[u] = *reinterpret_cast<const float4*>(wp + (kk0 + u) * js);
+              a[u] = *reinterpret_cast<const float4*>(ap + (kk0 + u) * SB_ROWS);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) sb_fma16(acc, a[u], w[u]);
+          }
+        } else {
+          for (int kk = 0; kk < nk; ++kk)
+            sb_fma16(acc, *reinterpret_cast<const float4*>(ap + kk * SB_ROWS),
+                     *reinterpret_cast<const float4*>(wp + kk * js));
+        }
+      }
+      SB_TRACE(dbg0 + 2 * c + 1);
+      __syncthreads();   // every thread is done with this stage
+      SB_TRACE(dbg0 + 2 * c + 2);
+      if (bulk && tid == 0 && c + SB_NST < nch) issue(c + SB_NST);
+    }
+    ring.uses = bulk ? base_use + nch : base_use;   // the fallback never touches the mbarriers
+    if (col_active) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (4 * cq + q < jc) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) f(jb + 4 * cq + q, 4 * rg + r, row_active ? acc[q][r] : 0.f);
+        }
+    }
   }
 }
 
 __global__ void __launch_bounds__(SB_THREADS) k_sb_forward(const __grid_constant__ SbFwdArgs args) {
-  extern __shared__ __align__(16) float sm[];
-  const int row_ctas = (args.B + SB_ROWS - 1) / SB_ROWS;
-  const int ni = blockIdx.x / row_ctas, rc = blockIdx.x % row_ctas;
+  extern __shared__ __align__(128) float sm[];
+  __shared__ __align__(8) unsigned long long bars[SB_NST];
+  int ni = 0;
+  while (ni + 1 < args.n_nets && (int)blockIdx.x >= args.cta_base[ni + 1]) ++ni;
   const rlc_sb_net& n = args.net[ni];
+  const int rc = blockIdx.x - args.cta_base[ni];
+  const int rows = n.rows ? n.rows : args.B;
   const int tid = threadIdx.x, b0 = rc * SB_ROWS;
   const int inp = n.inp, H1 = n.H1, H2 = n.H2, O = n.O;
-  float* x_s = sm;                          // [inp][8]
-  float* h1_s = x_s + inp * SB_ROWS;        // [H1][8]
-  float* h2_s = h1_s + H1 * SB_ROWS;        // [H2][8]
-  float* o_s = h2_s + H2 * SB_ROWS;         // [8][O]
+  unsigned long long* dbg = args.dbg;
+  SB_TRACE(0);
+  SbRing ring;
+  ring.buf = sm;                                                  // [SB_NST][SB_KC][SB_THREADS]
+  float* x_s = sm + SB_NST * SB_KC * SB_THREADS;                  // [inp][16]
+  float* h1_s = x_s + inp * SB_ROWS;                              // [H1][16]
+  float* h2_s = h1_s + H1 * SB_ROWS;                              // [H2][16]
+  float* o_s = h2_s + H2 * SB_ROWS;                               // [16][O]
+  ring.bar0 = sb_smem_u32(bars);
+  ring.uses = 0;
+  if (tid == 0) {
+    for (int i = 0; i < SB_NST; ++i) sb_mbar_init(ring.bar0 + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   const float* W1 = n.theta;
   const float* b1 = W1 + (long long)inp * H1;
   const float* W2 = b1 + H1;
@@ -93,33 +241,28 @@ __global__ void __launch_bounds__(SB_THREADS) k_sb_forward(const __grid_constant
   }
   for (int i = tid; i < inp * SB_ROWS; i += SB_THREADS) {
     const int k = i / SB_ROWS, r = i % SB_ROWS;
-    x_s[i] = (b0 + r < args.B) ? sb_x(n, b0 + r, k) : 0.f;
+    x_s[i] = (b0 + r < rows) ? sb_x(n, b0 + r, k) : 0.f;
   }
   __syncthreads();
-  float acc[SB_ROWS];
-  for (int j = tid; j < H1; j += SB_THREADS) {
-    sb_layer(W1, b1, inp, H1, x_s, j, acc);
-#pragma unroll
-    for (int r = 0; r < SB_ROWS; ++r) {
-      const float a = fmaxf(acc[r], 0.f);
-      h1_s[j * SB_ROWS + r] = a;
-      if (n.h1 && b0 + r < args.B) n.h1[(long long)(b0 + r) * H1 + j] = a;
-    }
-  }
+  SB_TRACE(1);
+  const int nrows = min(SB_ROWS, rows - b0);
+  sb_layer(W1, b1, inp, H1, x_s, nrows, ring, [&](int j, int r, float v) {
+    const float a = fmaxf(v, 0.f);
+    h1_s[j * SB_ROWS + r] = a;
+    if (n.h1 && r < nrows) n.h1[(long long)(b0 + r) * H1 + j] = a;
+  });
   __syncthreads();
-  for (int j = tid; j < H2; j += SB_THREADS) {
-    sb_layer(W2, b2, H1, H2, h1_s, j, acc);
-#pragma unroll
-    for (int r = 0; r < SB_ROWS; ++r) {
-      const float a = fmaxf(acc[r], 0.f);
-      h2_s[j * SB_ROWS + r] = a;
-      if (n.h2 && b0 + r < args.B) n.h2[(long long)(b0 + r) * H2 + j] = a;
-    }
-  }
+  SB_TRACE(2);
+  sb_layer(W2, b2, H1, H2, h1_s, nrows, ring, [&](int j, int r, float v) {
+    const float a = fmaxf(v, 0.f);
+    h2_s[j * SB_ROWS + r] = a;
+    if (n.h2 && r < nrows) n.h2[(long long)(b0 + r) * H2 + j] = a;
+  }, dbg, 8);
   __syncthreads();
+  SB_TRACE(3);
   // output layer: O is tiny (1 or 2A); one warp per (row, output) dot product
   const int warp = tid >> 5, lane = tid & 31;
-  for (int p = warp; p < SB_ROWS * O; p += SB_THREADS / 32) {
+  for (int p = warp; p < nrows * O; p += SB_THREADS / 32) {
     const int r = p / O, o = p % O;
     float s = 0.f;
     for (int j = lane; j < H2; j += 32) s = fmaf(h2_s[j * SB_ROWS + r], __ldg(W3 + (long long)j * O + o), s);
@@ -127,12 +270,13 @@ __global__ void __launch_bounds__(SB_THREADS) k_sb_forward(const __grid_constant
     if (lane == 0) {
       s += b3[o];
       o_s[r * O + o] = s;
-      if (b0 + r < args.B) n.out[(long long)(b0 + r) * O + o] = s;
+      if (b0 + r < rows) n.out[(long long)(b0 + r) * O + o] = s;
     }
   }
+  SB_TRACE(4);
   if (n.policy) {
     __syncthreads();
-    if (tid < SB_ROWS && b0 + tid < args.B) {
+    if (tid < SB_ROWS && b0 + tid < rows) {
       const int b = b0 + tid, A = O / 2;
       policy_evaluate_row(o_s + tid * O, n.eps ? n.eps + (long long)b * A : nullptr, A, n.action_scale,
                           n.log_std_min, n.log_std_max, n.action ? n.action + (long long)b * A : nullptr,
@@ -143,38 +287,78 @@ __global__ void __launch_bounds__(SB_THREADS) k_sb_forward(const __grid_constant
   }
 }
 
+// Adam (+ Polyak) on one parameter given its gradient; p/m/v(/t) are the pre-update values.
+__device__ __forceinline__ void sb_adam_vals(float p, float m, float v, float t, float g, float lr_eff, float isb2,
+                                             float b1, float b2, float eps, float tau, float& pn, float& mn, float& vn,
+                                             float& tn) {
+  mn = b1 * m + (1.f - b1) * g;
+  vn = b2 * v + (1.f - b2) * g * g;
+  pn = p - lr_eff * mn / (sqrtf(vn) * isb2 + eps);
+  tn = t + tau * (pn - t);
+}
 __device__ __forceinline__ void sb_adam(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v,
                                         float* __restrict__ target, long long i, float g, float lr_eff, float isb2,
                                         float b1, float b2, float eps, float tau) {
-  const float mi = b1 * m[i] + (1.f - b1) * g;
-  const float vi = b2 * v[i] + (1.f - b2) * g * g;
-  m[i] = mi;
-  v[i] = vi;
-  const float pn = theta[i] - lr_eff * mi / (sqrtf(vi) * isb2 + eps);
+  float pn, mn, vn, tn;
+  sb_adam_vals(theta[i], m[i], v[i], target ? target[i] : 0.f, g, lr_eff, isb2, b1, b2, eps, tau, pn, mn, vn, tn);
+  m[i] = mn;
+  v[i] = vn;
   theta[i] = pn;
-  if (target) target[i] += tau * (pn - target[i]);
+  if (target) target[i] = tn;
 }
 
 __global__ void __launch_bounds__(SB_THREADS) k_sb_update(const __grid_constant__ SbUpdArgs args) {
-  extern __shared__ __align__(16) float sm[];
+  extern __shared__ __align__(128) float sm[];
+  __shared__ __align__(8) unsigned long long bar;
   int ni = 0;
   while (ni + 1 < args.n_nets && (int)blockIdx.x >= args.cta_base[ni + 1]) ++ni;
   const rlc_sb_train& n = args.net[ni];
   const int c = blockIdx.x - args.cta_base[ni], C = args.cta_base[ni + 1] - args.cta_base[ni];
-  const int tid = threadIdx.x, B = args.B;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, B = args.B;
   const int inp = n.inp, H1 = n.H1, H2 = n.H2, O = n.O;
-  const int H2p = H2 + 1;                       // padded rows: (b, j) and (i, j) walks hit distinct banks
-  float* h1_s = sm;                             // [B][SB_NI]     (16-byte aligned rows: read as float4)
+  const int H2p = H2 + 1;                       // padded rows: lanes walking b hit distinct banks
+  const int i0 = c * SB_NI, nI = min(SB_NI, H1 - i0);
+  const int Jc = (H2 + C - 1) / C, j0 = c * Jc, nJ = max(0, min(Jc, H2 - j0));
+  // shared-memory carve-up (float offsets; the first four blocks are multiples of 4 floats)
+  float* pw = sm;                               // [4][SB_NI][H2]  theta | m | v | target rows of W2 owned here
+  float* h1_s = pw + 4 * SB_NI * H2;            // [B][SB_NI]
   float* dz1_s = h1_s + B * SB_NI;              // [B][SB_NI]
-  float* red_s = dz1_s + B * SB_NI;             // [SB_THREADS / 32]
-  float* dout_s = red_s + SB_THREADS / 32;      // [B][O]
+  float* red_s = dz1_s + B * SB_NI;             // [8]
+  float* dout_s = red_s + 8;                    // [B][O]
   float* dz2_s = dout_s + B * O;                // [B][H2p]
-  float* w2_s = dz2_s + B * H2p;                // [SB_NI][H2p]   pre-update rows of W2 owned by this CTA
+  float* x_s = dz2_s + B * H2p;                 // [B][inp]
+  float* h2_s = x_s + B * inp;                  // [B][Jc]      this CTA's share of the output layer
   const long long oW1 = 0, ob1 = (long long)inp * H1, oW2 = ob1 + H1, ob2 = oW2 + (long long)H1 * H2, oW3 = ob2 + H2,
                   ob3 = oW3 + (long long)H2 * O;
   const float lr_eff = reinterpret_cast<const float*>(n.adam_state)[1];
   const float isb2 = reinterpret_cast<const float*>(n.adam_state)[2];
-  const int i0 = c * SB_NI, nI = min(SB_NI, H1 - i0);
+  // ---- the CTA's W2 rows (parameters + both moments + the Polyak target) start moving first: one bulk copy each,
+  //      in flight under the whole gradient computation; Adam later reads them from shared memory
+  const long long w2off = oW2 + (long long)i0 * H2;
+  const uint32_t slice_bytes = (uint32_t)(nI * H2 * 4);
+  const bool bulk = ((((uintptr_t)(n.theta + w2off)) | ((uintptr_t)(n.m + w2off)) | ((uintptr_t)(n.v + w2off)) |
+                      (n.target ? (uintptr_t)(n.target + w2off) : 0)) & 15) == 0 && (slice_bytes & 15) == 0 &&
+                    ((SB_NI * H2) & 3) == 0;
+  const uint32_t bar_a = sb_smem_u32(&bar);
+  if (tid == 0) {
+    sb_mbar_init(bar_a, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (bulk) {
+      sb_mbar_expect_tx(bar_a, slice_bytes * (n.target ? 4 : 3));
+      sb_bulk_g2s(sb_smem_u32(pw), n.theta + w2off, slice_bytes, bar_a);
+      sb_bulk_g2s(sb_smem_u32(pw + SB_NI * H2), n.m + w2off, slice_bytes, bar_a);
+      sb_bulk_g2s(sb_smem_u32(pw + 2 * SB_NI * H2), n.v + w2off, slice_bytes, bar_a);
+      if (n.target) sb_bulk_g2s(sb_smem_u32(pw + 3 * SB_NI * H2), n.target + w2off, slice_bytes, bar_a);
+    }
+  }
+  if (!bulk) {
+    for (int p = tid; p < nI * H2; p += SB_THREADS) {
+      pw[p] = n.theta[w2off + p];
+      pw[SB_NI * H2 + p] = n.m[w2off + p];
+      pw[2 * SB_NI * H2 + p] = n.v[w2off + p];
+      if (n.target) pw[3 * SB_NI * H2 + p] = n.target[w2off + p];
+    }
+  }
   // ---- prologue: dLoss/dout for this network's role (B x O values), loss on CTA 0
   float loss_part = 0.f;
   for (int p = tid; p < B * O; p += SB_THREADS) {
@@ -194,7 +378,7 @@ __global__ void __launch_bounds__(SB_THREADS) k_sb_update(const __grid_constant_
       const int A = O / 2;
       if (o < A) {
         d = n.dmean[b * A + o];
-        if (o == 0) loss_part += n.loss_b[b] / (float)B;
+        if (o == 0 && n.loss_b) loss_part += n.loss_b[b] / (float)B;
       } else {
         const float raw = n.out[b * O + o];
         d = (raw >= n.log_std_min && raw <= n.log_std_max) ? n.dlog_std[b * A + (o - A)] : 0.f;
@@ -206,42 +390,45 @@ __global__ void __launch_bounds__(SB_THREADS) k_sb_update(const __grid_constant_
   }
   if (c == 0 && n.loss_out) {                  // deterministic: warp sums, then a serial sum over the 8 warps
     loss_part = warp_sum(loss_part);
-    if ((tid & 31) == 0) red_s[tid >> 5] = loss_part;
+    if (lane == 0) red_s[warp] = loss_part;
   }
-  // stage this CTA's rows of W2 and its hidden-1 activations
-  for (int p = tid; p < nI * H2; p += SB_THREADS) {
-    const int i = p / H2, j = p % H2;
-    w2_s[i * H2p + j] = n.theta[oW2 + (long long)(i0 + i) * H2 + j];
-  }
+  // everything else this CTA reads from HBM, in one batch of independent loads
   for (int p = tid; p < B * SB_NI; p += SB_THREADS) {
     const int b = p / SB_NI, i = p % SB_NI;
     h1_s[p] = i < nI ? n.h1[(long long)b * H1 + i0 + i] : 0.f;
   }
+  for (int p = tid; p < B * inp; p += SB_THREADS) x_s[p] = sb_xt(n, p / inp, p % inp);
+  for (int p = tid; p < B * nJ; p += SB_THREADS) h2_s[(p / nJ) * Jc + p % nJ] = n.h2[(long long)(p / nJ) * H2 + j0 + p % nJ];
+  // ---- dz2[b][j] = (dout[b,:] . W3[j,:]) * relu'(h2[b,j])
   __syncthreads();
   if (c == 0 && n.loss_out && tid == 0) {
     float s = 0.f;
     for (int w = 0; w < SB_THREADS / 32; ++w) s += red_s[w];
     n.loss_out[0] = s;
   }
-  // ---- dz2[b][j] = (dout[b,:] . W3[j,:]) * relu'(h2[b,j])
+#pragma unroll 4
   for (int p = tid; p < B * H2; p += SB_THREADS) {
     const int b = p / H2, j = p % H2;
+    const float hv = n.h2[p];
     float s = 0.f;
-    for (int o = 0; o < O; ++o) s = fmaf(dout_s[b * O + o], n.w3_snapshot[j * O + o], s);
-    dz2_s[b * H2p + j] = n.h2[(long long)b * H2 + j] > 0.f ? s : 0.f;
+    for (int o = 0; o < O; ++o) s = fmaf(dout_s[b * O + o], __ldg(n.w3_snapshot + j * O + o), s);
+    dz2_s[b * H2p + j] = hv > 0.f ? s : 0.f;
   }
+  if (bulk) sb_mbar_wait(bar_a, 0);
   __syncthreads();
-  // ---- dh1[b][i] = dz2[b,:] . W2[i,:] ; dz1 = dh1 * relu'(h1)      (B x nI dot products of length H2)
-  for (int p = tid; p < B * SB_NI; p += SB_THREADS) {
-    const int b = p / SB_NI, i = p % SB_NI;
-    float s = 0.f;
-    if (i < nI) {
-      const float* dz = dz2_s + b * H2p;
-      const float* w = w2_s + i * H2p;
-      for (int j = 0; j < H2; ++j) s = fmaf(dz[j], w[j], s);
-      if (!(h1_s[p] > 0.f)) s = 0.f;
+  // ---- dh1[b][i] = dz2[b,:] . W2[i,:] ; dz1 = dh1 * relu'(h1): a warp takes unit i (broadcast W2 row), lanes take b
+  for (int i = warp; i < SB_NI; i += SB_THREADS / 32) {
+    for (int b = lane; b < B; b += 32) {
+      float s = 0.f;
+      if (i < nI) {
+        const float* dz = dz2_s + b * H2p;
+        const float* w = pw + i * H2;
+#pragma unroll 4
+        for (int j = 0; j < H2; ++j) s = fmaf(dz[j], w[j], s);
+        if (!(h1_s[b * SB_NI + i] > 0.f)) s = 0.f;
+      }
+      dz1_s[b * SB_NI + i] = s;
     }
-    dz1_s[p] = s;
   }
   // ---- dW2[i][j] = sum_b h1[b,i] dz2[b,j], straight into Adam (thread = column j, 16 accumulators)
   for (int j = tid; j < H2; j += SB_THREADS) {
@@ -261,42 +448,53 @@ __global__ void __launch_bounds__(SB_THREADS) k_sb_update(const __grid_constant_
       }
     }
 #pragma unroll
-    for (int i = 0; i < SB_NI; ++i)
-      if (i < nI)
-        sb_adam(n.theta, n.m, n.v, n.target, oW2 + (long long)(i0 + i) * H2 + j, acc[i], lr_eff, isb2, n.beta1,
-                n.beta2, n.eps, n.tau);
+    for (int i = 0; i < SB_NI; ++i) {
+      if (i < nI) {
+        const int q = i * H2 + j;
+        float pn, mn, vn, tn;
+        sb_adam_vals(pw[q], pw[SB_NI * H2 + q], pw[2 * SB_NI * H2 + q], n.target ? pw[3 * SB_NI * H2 + q] : 0.f, acc[i],
+                     lr_eff, isb2, n.beta1, n.beta2, n.eps, n.tau, pn, mn, vn, tn);
+        n.theta[w2off + q] = pn;
+        n.m[w2off + q] = mn;
+        n.v[w2off + q] = vn;
+        if (n.target) n.target[w2off + q] = tn;
+      }
+    }
   }
   __syncthreads();
-  // ---- dW1[k][i] = sum_b x[b,k] dz1[b,i] ; db1[i] = sum_b dz1[b,i]   ((inp + 1) x nI outputs)
-  for (int p = tid; p < (inp + 1) * SB_NI; p += SB_THREADS) {
-    const int k = p / SB_NI, i = p % SB_NI;
-    if (i >= nI) continue;
+  // ---- everything small, one flattened pass (one round trip to HBM for its Adam state):
+  //      dW1[k][i] = sum_b x[b,k] dz1[b,i], db1[i] = sum_b dz1[b,i]            ((inp + 1) x nI outputs)
+  //      dW3[j][o] = sum_b h2[b,j] dout[b,o], db2[j] = sum_b dz2[b,j]          (nJ x (O + 1) outputs, this CTA's share)
+  //      db3[o] = sum_b dout[b,o]                                             (last CTA)
+  const int n1 = (inp + 1) * SB_NI, n2 = nJ * (O + 1), n3 = (c == C - 1) ? O : 0;
+  for (int p = tid; p < n1 + n2 + n3; p += SB_THREADS) {
     float s = 0.f;
-    if (k < inp) {
-      for (int b = 0; b < B; ++b) s = fmaf(sb_xt(n, b, k), dz1_s[b * SB_NI + i], s);
-      sb_adam(n.theta, n.m, n.v, n.target, oW1 + (long long)k * H1 + i0 + i, s, lr_eff, isb2, n.beta1, n.beta2, n.eps, n.tau);
+    long long idx;
+    if (p < n1) {
+      const int k = p / SB_NI, i = p % SB_NI;
+      if (i >= nI) continue;
+      if (k < inp) {
+        for (int b = 0; b < B; ++b) s = fmaf(x_s[b * inp + k], dz1_s[b * SB_NI + i], s);
+        idx = oW1 + (long long)k * H1 + i0 + i;
+      } else {
+        for (int b = 0; b < B; ++b) s += dz1_s[b * SB_NI + i];
+        idx = ob1 + i0 + i;
+      }
+    } else if (p < n1 + n2) {
+      const int q = p - n1, jj = q / (O + 1), o = q % (O + 1);
+      if (o < O) {
+        for (int b = 0; b < B; ++b) s = fmaf(h2_s[b * Jc + jj], dout_s[b * O + o], s);
+        idx = oW3 + (long long)(j0 + jj) * O + o;
+      } else {
+        for (int b = 0; b < B; ++b) s += dz2_s[b * H2p + j0 + jj];
+        idx = ob2 + j0 + jj;
+      }
     } else {
-      for (int b = 0; b < B; ++b) s += dz1_s[b * SB_NI + i];
-      sb_adam(n.theta, n.m, n.v, n.target, ob1 + i0 + i, s, lr_eff, isb2, n.beta1, n.beta2, n.eps, n.tau);
+      const int o = p - n1 - n2;
+      for (int b = 0; b < B; ++b) s += dout_s[b * O + o];
+      idx = ob3 + o;
     }
-  }
-  // ---- this CTA's share of the output layer: dW3[j][o] = sum_b h2[b,j] dout[b,o] ; db2[j] = sum_b dz2[b,j]
-  const int Jc = (H2 + C - 1) / C, j0 = c * Jc, nJ = max(0, min(Jc, H2 - j0));
-  for (int p = tid; p < nJ * (O + 1); p += SB_THREADS) {
-    const int j = j0 + p / (O + 1), o = p % (O + 1);
-    float s = 0.f;
-    if (o < O) {
-      for (int b = 0; b < B; ++b) s = fmaf(n.h2[(long long)b * H2 + j], dout_s[b * O + o], s);
-      sb_adam(n.theta, n.m, n.v, n.target, oW3 + (long long)j * O + o, s, lr_eff, isb2, n.beta1, n.beta2, n.eps, n.tau);
-    } else {
-      for (int b = 0; b < B; ++b) s += dz2_s[b * H2p + j];
-      sb_adam(n.theta, n.m, n.v, n.target, ob2 + j, s, lr_eff, isb2, n.beta1, n.beta2, n.eps, n.tau);
-    }
-  }
-  if (c == C - 1 && tid < O) {                 // db3[o] = sum_b dout[b,o]
-    float s = 0.f;
-    for (int b = 0; b < B; ++b) s += dout_s[b * O + tid];
-    sb_adam(n.theta, n.m, n.v, n.target, ob3 + tid, s, lr_eff, isb2, n.beta1, n.beta2, n.eps, n.tau);
+    sb_adam(n.theta, n.m, n.v, n.target, idx, s, lr_eff, isb2, n.beta1, n.beta2, n.eps, n.tau);
   }
 }
 
@@ -307,26 +505,35 @@ static bool sb_dims_ok(int inp, int H1, int H2, int O, int n0, int n1) {
 
 extern "C" int rlc_sb_forward(rlc_handle* h, const rlc_sb_net* nets, int n_nets, int B, void* stream) {
   RLC_REQUIRE(h && nets && n_nets >= 1 && n_nets <= RLC_SB_MAX_NETS && B >= 1 && B <= RLC_SB_MAX_B);
+  static int smem_set = 0;
   SbFwdArgs args;
   size_t smem = 0;
+  int base = 0;
   for (int i = 0; i < n_nets; ++i) {
     const rlc_sb_net& n = nets[i];
     RLC_REQUIRE(n.theta && n.out && sb_dims_ok(n.inp, n.H1, n.H2, n.O, n.n0, n.n1));
     RLC_REQUIRE((n.n0 == 0 || n.x0) && (n.n1 == 0 || n.x1));
+    RLC_REQUIRE(n.rows >= 0 && n.rows <= 65536 && n.x0_div >= 0 && n.x1_mod >= 0);
     RLC_REQUIRE(!n.policy || (n.O % 2 == 0 && n.O / 2 <= 16 && n.log_std_min <= n.log_std_max));
     RLC_REQUIRE(!n.adam_state || n.adam_variant == RLC_ADAM_TORCH || n.adam_variant == RLC_ADAM_TF);
     args.net[i] = n;
-    const size_t s = sizeof(float) * ((size_t)(n.inp + n.H1 + n.H2) * SB_ROWS + (size_t)SB_ROWS * n.O);
+    args.cta_base[i] = base;
+    base += ((n.rows ? n.rows : B) + SB_ROWS - 1) / SB_ROWS;
+    const size_t s = sizeof(float) * ((size_t)SB_NST * SB_KC * SB_THREADS + (size_t)(n.inp + n.H1 + n.H2) * SB_ROWS +
+                                      (size_t)SB_ROWS * n.O);
     smem = s > smem ? s : smem;
   }
+  args.cta_base[n_nets] = base;
   args.n_nets = n_nets;
   args.B = B;
-  if (smem > 48 * 1024) {
+  const char* dbg_env = getenv("RLC_SB_DEBUG");   // hex device address of a >= 128-slot uint64 buffer (timing scripts)
+  args.dbg = dbg_env ? (unsigned long long*)strtoull(dbg_env, nullptr, 16) : nullptr;
+  if (smem > 48 * 1024 && (int)smem > smem_set) {
     RLC_REQUIRE(smem <= h->smem_optin);
     RLC_CUDA(cudaFuncSetAttribute(k_sb_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = (int)smem;
   }
-  const int row_ctas = (B + SB_ROWS - 1) / SB_ROWS;
-  k_sb_forward<<<n_nets * row_ctas, SB_THREADS, smem, (cudaStream_t)stream>>>(args);
+  k_sb_forward<<<base, SB_THREADS, smem, (cudaStream_t)stream>>>(args);
   RLC_LAUNCH_CHECK(h);
   return RLC_OK;
 }
@@ -355,8 +562,9 @@ extern "C" int rlc_sb_update(rlc_handle* h, const rlc_sb_train* nets, int n_nets
     args.net[i] = n;
     args.cta_base[i] = base;
     base += (n.H1 + SB_NI - 1) / SB_NI;
-    const size_t s = sizeof(float) * ((size_t)B * n.O + (size_t)(B + SB_NI) * (n.H2 + 1) + 2 * (size_t)B * SB_NI +
-                                      SB_THREADS / 32);
+    const int Cn = (n.H1 + SB_NI - 1) / SB_NI, Jc = (n.H2 + Cn - 1) / Cn;
+    const size_t s = sizeof(float) * ((size_t)4 * SB_NI * n.H2 + 2 * (size_t)B * SB_NI + 8 + (size_t)B * n.O +
+                                      (size_t)B * (n.H2 + 1) + (size_t)B * n.inp + (size_t)B * Jc);
     smem = s > smem ? s : smem;
     rlc_invalidate_pack(h, n.theta);
     if (n.target) rlc_invalidate_pack(h, n.target);

@@ -216,7 +216,7 @@ class _KLNetwork(object):
     def _small_ok(self, B):
         dims = (self.pi.H1, self.pi.H2, self.critic.H1, self.critic.H2)
         return (self.fused_small and self.world_size == 1 and B <= SB_MAX_B and self.optim_type in ("intg", "hard_intg")
-                and max(dims) <= 512 and self.state_dim + self.action_dim <= 256 and 2 * self.action_dim <= 32)
+                and max(dims) <= 400 and self.state_dim + self.action_dim <= 256 and 2 * self.action_dim <= 32)
 
     def _build_small(self, st, B):
         """Descriptors of the two fused launches (kept alive on ``st``; the C side copies them at launch)."""
@@ -228,7 +228,7 @@ class _KLNetwork(object):
         bf = st.sb_buf
         p = lambda t: None if t is None else t.data_ptr()
         sac = self.q_update_type == "sac"
-        fwd = (RlcSbNet * 4)()
+        fwd = (RlcSbNet * 5)()
 
         def net(n, theta, inp, H1, H2, O, x0, n0, x1, n1, h1, h2, out, w3, opt):
             n.theta, n.inp, n.H1, n.H2, n.O = p(theta), inp, H1, H2, O
@@ -247,6 +247,13 @@ class _KLNetwork(object):
         n.action, n.logp, n.mean, n.mu_raw, n.log_std, n.z = (p(ev[k]) for k in ("action", "logp", "mean", "mu_raw", "log_std", "z"))
         net(fwd[3], self.critic.theta, S + A, self.critic.H1, self.critic.H2, 1, d["s"], S, d["a"], A, bf["h1q"], bf["h2q"],
             st.q_reg, bf["w3q"], self.q_opt)
+        # the B x N grid evaluation with the PRE-update theta_Q rides in the same launch when it is small (cfg1: 1 984 rows);
+        # larger stacks go to rlc_critic_eval (tensor path) on the side stream
+        N = self.intgrl_actions_len
+        st.sb_grid_fused = B * N <= 4096
+        net(fwd[4], self.critic.theta, S + A, self.critic.H1, self.critic.H2, 1, d["s"], S, self.intgrl_actions, A, None, None,
+            st.q_grid, None, None)
+        fwd[4].rows, fwd[4].x0_div, fwd[4].x1_mod = B * N, N, N
         st.sb_fwd = fwd
         fwd2 = (RlcSbNet * 1)()                       # 'sac': Q(s, a_new) needs the policy's sample first (:143-146)
         net(fwd2[0], self.critic.theta, S + A, self.critic.H1, self.critic.H2, 1, d["s"], S, ev["action"], A, None, None,
@@ -273,21 +280,25 @@ class _KLNetwork(object):
         st.sb_upd = upd
 
     def _enqueue_small(self, st, B, device_inputs=False):
-        """The same update as :meth:`_enqueue` in five launches: grid evaluation (side stream) || all forward passes ->
-        FKL/RKL reduction with get_logprob fused (2) -> all backward passes + Adam."""
+        """The same update as :meth:`_enqueue` in four launches: all forward passes, the B x N grid evaluation among them
+        -> FKL/RKL reduction with get_logprob fused (2) -> all backward passes + Adam."""
         if getattr(st, "sb_fwd", None) is None:
             self._build_small(st, B)
         lib, alpha = self.eng.lib, self.entropy_scale
         main, s_grid = st.stream, st.s_grid
         if not device_inputs:
             st.in_dev.copy_(st.in_host, non_blocking=True)
-        s_grid.wait_stream(main)
-        with torch.cuda.stream(s_grid):
-            self.critic_grid.eval_into(st.d["s"], self.intgrl_actions, st.q_grid, self.precision)   # pre-update theta_Q
-        check(lib.rlc_sb_forward(self.eng.h, st.sb_fwd, 4, B, _stream()))
+        if st.sb_grid_fused:
+            check(lib.rlc_sb_forward(self.eng.h, st.sb_fwd, 5, B, _stream()))
+        else:
+            s_grid.wait_stream(main)
+            with torch.cuda.stream(s_grid):
+                self.critic_grid.eval_into(st.d["s"], self.intgrl_actions, st.q_grid, self.precision)   # pre-update theta_Q
+            check(lib.rlc_sb_forward(self.eng.h, st.sb_fwd, 4, B, _stream()))
         if self.q_update_type == "sac":
             check(lib.rlc_sb_forward(self.eng.h, st.sb_fwd2, 1, B, _stream()))
-        main.wait_stream(s_grid)
+        if not st.sb_grid_fused:
+            main.wait_stream(s_grid)
         if self.KIND == "fkl":
             self.eng.fkl_policy(st.q_grid, self.intgrl_weights, self.intgrl_actions, self.action_scale, st.ev["mu_raw"],
                                 st.ev["log_std"], alpha, b_total=B, out=(st.loss_b, st.dmean, st.dls))
