@@ -19,7 +19,7 @@
 
 #define SB_ROWS 16       // rows per forward CTA
 #define SB_THREADS 256
-#define SB_NI 16         // hidden-1 units per backward CTA
+#define SB_NI 8          // hidden-1 units per backward CTA (more, smaller CTAs: every phase that scales with it is latency)
 #define SB_KC 16         // weight rows per ring stage
 #define SB_NST 4         // ring stages (bulk copies in flight: SB_NST * SB_KC * J * 4 bytes, 51 KB at J = 200)
 #define SB_WAIT_LIMIT (1u << 26)
@@ -41,6 +41,7 @@ struct SbUpdArgs {
   int cta_base[RLC_SB_MAX_NETS + 1];
   int n_nets, B;
   float inv_btotal;
+  unsigned long long* dbg;
 };
 
 __device__ __forceinline__ uint32_t sb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -316,7 +317,11 @@ __global__ void __launch_bounds__(SB_THREADS) k_sb_update(const __grid_constant_
   const int c = blockIdx.x - args.cta_base[ni], C = args.cta_base[ni + 1] - args.cta_base[ni];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, B = args.B;
   const int inp = n.inp, H1 = n.H1, H2 = n.H2, O = n.O;
-  const int H2p = H2 + 1;                       // padded rows: lanes walking b hit distinct banks
+  unsigned long long* dbg = args.dbg;
+  SB_TRACE(64);
+  // row stride of dz2: a multiple of 4 floats (float4 reads along j) with an ODD number of quads, so that float4 reads
+  // by lanes walking b (dh1 phase) fall in distinct bank groups; pad columns stay 0
+  const int H2p = 4 * (((H2 + 3) >> 2) | 1);
   const int i0 = c * SB_NI, nI = min(SB_NI, H1 - i0);
   const int Jc = (H2 + C - 1) / C, j0 = c * Jc, nJ = max(0, min(Jc, H2 - j0));
   // shared-memory carve-up (float offsets; the first four blocks are multiples of 4 floats)
@@ -324,9 +329,9 @@ __global__ void __launch_bounds__(SB_THREADS) k_sb_update(const __grid_constant_
   float* h1_s = pw + 4 * SB_NI * H2;            // [B][SB_NI]
   float* dz1_s = h1_s + B * SB_NI;              // [B][SB_NI]
   float* red_s = dz1_s + B * SB_NI;             // [8]
-  float* dout_s = red_s + 8;                    // [B][O]
-  float* dz2_s = dout_s + B * O;                // [B][H2p]
-  float* x_s = dz2_s + B * H2p;                 // [B][inp]
+  float* dz2_s = red_s + 8;                     // [B][H2p]     (16-byte aligned rows)
+  float* dout_s = dz2_s + B * H2p;              // [B][O]
+  float* x_s = dout_s + B * O;                  // [B][inp]
   float* h2_s = x_s + B * inp;                  // [B][Jc]      this CTA's share of the output layer
   const long long oW1 = 0, ob1 = (long long)inp * H1, oW2 = ob1 + H1, ob2 = oW2 + (long long)H1 * H2, oW3 = ob2 + H2,
                   ob3 = oW3 + (long long)H2 * O;
@@ -388,6 +393,8 @@ __global__ void __launch_bounds__(SB_THREADS) k_sb_update(const __grid_constant_
     }
     dout_s[p] = d;
   }
+  if (H2p != H2)
+    for (int p = tid; p < B * (H2p - H2); p += SB_THREADS) dz2_s[(p / (H2p - H2)) * H2p + H2 + p % (H2p - H2)] = 0.f;
   if (c == 0 && n.loss_out) {                  // deterministic: warp sums, then a serial sum over the 8 warps
     loss_part = warp_sum(loss_part);
     if (lane == 0) red_s[warp] = loss_part;
@@ -401,67 +408,117 @@ __global__ void __launch_bounds__(SB_THREADS) k_sb_update(const __grid_constant_
   for (int p = tid; p < B * nJ; p += SB_THREADS) h2_s[(p / nJ) * Jc + p % nJ] = n.h2[(long long)(p / nJ) * H2 + j0 + p % nJ];
   // ---- dz2[b][j] = (dout[b,:] . W3[j,:]) * relu'(h2[b,j])
   __syncthreads();
+  SB_TRACE(65);
   if (c == 0 && n.loss_out && tid == 0) {
     float s = 0.f;
     for (int w = 0; w < SB_THREADS / 32; ++w) s += red_s[w];
     n.loss_out[0] = s;
   }
-#pragma unroll 4
-  for (int p = tid; p < B * H2; p += SB_THREADS) {
-    const int b = p / H2, j = p % H2;
-    const float hv = n.h2[p];
-    float s = 0.f;
-    for (int o = 0; o < O; ++o) s = fmaf(dout_s[b * O + o], __ldg(n.w3_snapshot + j * O + o), s);
-    dz2_s[b * H2p + j] = hv > 0.f ? s : 0.f;
+  // thread = column j: its W3 row in registers, coalesced h2 loads over b, no integer division
+  for (int j = tid; j < H2; j += SB_THREADS) {
+    float w3r[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) w3r[o] = o < O ? __ldg(n.w3_snapshot + j * O + o) : 0.f;
+#pragma unroll 8
+    for (int b = 0; b < B; ++b) {
+      const float hv = n.h2[(long long)b * H2 + j];
+      float s = 0.f;
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+        if (o < O) s = fmaf(dout_s[b * O + o], w3r[o], s);
+      for (int o = 4; o < O; ++o) s = fmaf(dout_s[b * O + o], __ldg(n.w3_snapshot + j * O + o), s);
+      dz2_s[b * H2p + j] = hv > 0.f ? s : 0.f;
+    }
   }
+  SB_TRACE(66);
   if (bulk) sb_mbar_wait(bar_a, 0);
   __syncthreads();
-  // ---- dh1[b][i] = dz2[b,:] . W2[i,:] ; dz1 = dh1 * relu'(h1): a warp takes unit i (broadcast W2 row), lanes take b
+  SB_TRACE(67);
+  // ---- dh1[b][i] = dz2[b,:] . W2[i,:] ; dz1 = dh1 * relu'(h1): a warp takes unit i (its W2 row is a broadcast read),
+  //      lanes take b, four partial sums break the FMA dependency chain.  (A variant with the W2 row in registers,
+  //      lanes over columns and shuffle reductions measured 3x slower.)
   for (int i = warp; i < SB_NI; i += SB_THREADS / 32) {
     for (int b = lane; b < B; b += 32) {
-      float s = 0.f;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
       if (i < nI) {
         const float* dz = dz2_s + b * H2p;
         const float* w = pw + i * H2;
+        for (int j = 0; j < H2; j += 4) {         // pad columns of dz2 are 0
+          const float4 d = *reinterpret_cast<const float4*>(dz + j);
+          float4 ww;
+          if (j + 3 < H2 && (H2 & 3) == 0) ww = *reinterpret_cast<const float4*>(w + j);
+          else ww = make_float4(w[j], j + 1 < H2 ? w[j + 1] : 0.f, j + 2 < H2 ? w[j + 2] : 0.f, j + 3 < H2 ? w[j + 3] : 0.f);
+          s0 = fmaf(d.x, ww.x, s0);
+          s1 = fmaf(d.y, ww.y, s1);
+          s2 = fmaf(d.z, ww.z, s2);
+          s3 = fmaf(d.w, ww.w, s3);
+        }
+        s0 = (s0 + s1) + (s2 + s3);
+        if (!(h1_s[b * SB_NI + i] > 0.f)) s0 = 0.f;
+      }
+      dz1_s[b * SB_NI + i] = s0;
+    }
+  }
+  SB_TRACE(68);
+  // ---- dW2[i][j] = sum_b h1[b,i] dz2[b,j], straight into Adam.  4 x 4 register tiles (4 units x 4 columns per thread):
+  //      per b one float4 of dz2 and one broadcast float4 of h1 feed 16 FMAs.
+  for (int jb = 0; jb < H2; jb += SB_THREADS) {
+    const int jq = tid & 63, ig = tid >> 6, j = jb + 4 * jq;
+    if (j >= H2 || 4 * ig >= SB_NI) continue;
+    float acc[4][4];   // [unit][column]
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[u][q] = 0.f;
 #pragma unroll 4
-        for (int j = 0; j < H2; ++j) s = fmaf(dz[j], w[j], s);
-        if (!(h1_s[b * SB_NI + i] > 0.f)) s = 0.f;
-      }
-      dz1_s[b * SB_NI + i] = s;
-    }
-  }
-  // ---- dW2[i][j] = sum_b h1[b,i] dz2[b,j], straight into Adam (thread = column j, 16 accumulators)
-  for (int j = tid; j < H2; j += SB_THREADS) {
-    float acc[SB_NI];
-#pragma unroll
-    for (int i = 0; i < SB_NI; ++i) acc[i] = 0.f;
     for (int b = 0; b < B; ++b) {
-      const float d = dz2_s[b * H2p + j];
-      const float4* h4 = reinterpret_cast<const float4*>(h1_s + b * SB_NI);
-#pragma unroll
-      for (int q = 0; q < SB_NI / 4; ++q) {
-        const float4 h = h4[q];
-        acc[4 * q + 0] = fmaf(h.x, d, acc[4 * q + 0]);
-        acc[4 * q + 1] = fmaf(h.y, d, acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(h.z, d, acc[4 * q + 2]);
-        acc[4 * q + 3] = fmaf(h.w, d, acc[4 * q + 3]);
-      }
+      const float4 d = *reinterpret_cast<const float4*>(dz2_s + b * H2p + j);     // H2p % 4 == 0; pad columns are 0
+      const float4 h = *reinterpret_cast<const float4*>(h1_s + b * SB_NI + 4 * ig);
+      acc[0][0] = fmaf(h.x, d.x, acc[0][0]); acc[0][1] = fmaf(h.x, d.y, acc[0][1]);
+      acc[0][2] = fmaf(h.x, d.z, acc[0][2]); acc[0][3] = fmaf(h.x, d.w, acc[0][3]);
+      acc[1][0] = fmaf(h.y, d.x, acc[1][0]); acc[1][1] = fmaf(h.y, d.y, acc[1][1]);
+      acc[1][2] = fmaf(h.y, d.z, acc[1][2]); acc[1][3] = fmaf(h.y, d.w, acc[1][3]);
+      acc[2][0] = fmaf(h.z, d.x, acc[2][0]); acc[2][1] = fmaf(h.z, d.y, acc[2][1]);
+      acc[2][2] = fmaf(h.z, d.z, acc[2][2]); acc[2][3] = fmaf(h.z, d.w, acc[2][3]);
+      acc[3][0] = fmaf(h.w, d.x, acc[3][0]); acc[3][1] = fmaf(h.w, d.y, acc[3][1]);
+      acc[3][2] = fmaf(h.w, d.z, acc[3][2]); acc[3][3] = fmaf(h.w, d.w, acc[3][3]);
     }
 #pragma unroll
-    for (int i = 0; i < SB_NI; ++i) {
-      if (i < nI) {
-        const int q = i * H2 + j;
+    for (int u = 0; u < 4; ++u) {
+      const int i = 4 * ig + u;
+      if (i >= nI) continue;
+      const int e = i * H2 + j;
+      if (bulk && (H2 & 3) == 0) {   // aligned rows: 128-bit shared loads and coalesced 128-bit stores
+        const float4 p4 = *reinterpret_cast<const float4*>(pw + e), m4 = *reinterpret_cast<const float4*>(pw + SB_NI * H2 + e),
+                     v4 = *reinterpret_cast<const float4*>(pw + 2 * SB_NI * H2 + e);
+        const float4 t4 = n.target ? *reinterpret_cast<const float4*>(pw + 3 * SB_NI * H2 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 pn, mn, vn, tn;
+        sb_adam_vals(p4.x, m4.x, v4.x, t4.x, acc[u][0], lr_eff, isb2, n.beta1, n.beta2, n.eps, n.tau, pn.x, mn.x, vn.x, tn.x);
+        sb_adam_vals(p4.y, m4.y, v4.y, t4.y, acc[u][1], lr_eff, isb2, n.beta1, n.beta2, n.eps, n.tau, pn.y, mn.y, vn.y, tn.y);
+        sb_adam_vals(p4.z, m4.z, v4.z, t4.z, acc[u][2], lr_eff, isb2, n.beta1, n.beta2, n.eps, n.tau, pn.z, mn.z, vn.z, tn.z);
+        sb_adam_vals(p4.w, m4.w, v4.w, t4.w, acc[u][3], lr_eff, isb2, n.beta1, n.beta2, n.eps, n.tau, pn.w, mn.w, vn.w, tn.w);
+        *reinterpret_cast<float4*>(n.theta + w2off + e) = pn;
+        *reinterpret_cast<float4*>(n.m + w2off + e) = mn;
+        *reinterpret_cast<float4*>(n.v + w2off + e) = vn;
+        if (n.target) *reinterpret_cast<float4*>(n.target + w2off + e) = tn;
+        continue;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (j + q >= H2) continue;
         float pn, mn, vn, tn;
-        sb_adam_vals(pw[q], pw[SB_NI * H2 + q], pw[2 * SB_NI * H2 + q], n.target ? pw[3 * SB_NI * H2 + q] : 0.f, acc[i],
-                     lr_eff, isb2, n.beta1, n.beta2, n.eps, n.tau, pn, mn, vn, tn);
-        n.theta[w2off + q] = pn;
-        n.m[w2off + q] = mn;
-        n.v[w2off + q] = vn;
-        if (n.target) n.target[w2off + q] = tn;
+        sb_adam_vals(pw[e + q], pw[SB_NI * H2 + e + q], pw[2 * SB_NI * H2 + e + q], n.target ? pw[3 * SB_NI * H2 + e + q] : 0.f,
+                     acc[u][q], lr_eff, isb2, n.beta1, n.beta2, n.eps, n.tau, pn, mn, vn, tn);
+        n.theta[w2off + e + q] = pn;
+        n.m[w2off + e + q] = mn;
+        n.v[w2off + e + q] = vn;
+        if (n.target) n.target[w2off + e + q] = tn;
       }
     }
   }
+  SB_TRACE(69);
   __syncthreads();
+  SB_TRACE(70);
   // ---- everything small, one flattened pass (one round trip to HBM for its Adam state):
   //      dW1[k][i] = sum_b x[b,k] dz1[b,i], db1[i] = sum_b dz1[b,i]            ((inp + 1) x nI outputs)
   //      dW3[j][o] = sum_b h2[b,j] dout[b,o], db2[j] = sum_b dz2[b,j]          (nJ x (O + 1) outputs, this CTA's share)
@@ -496,6 +553,7 @@ __global__ void __launch_bounds__(SB_THREADS) k_sb_update(const __grid_constant_
     }
     sb_adam(n.theta, n.m, n.v, n.target, idx, s, lr_eff, isb2, n.beta1, n.beta2, n.eps, n.tau);
   }
+  SB_TRACE(71);
 }
 
 static bool sb_dims_ok(int inp, int H1, int H2, int O, int n0, int n1) {
@@ -564,7 +622,7 @@ extern "C" int rlc_sb_update(rlc_handle* h, const rlc_sb_train* nets, int n_nets
     base += (n.H1 + SB_NI - 1) / SB_NI;
     const int Cn = (n.H1 + SB_NI - 1) / SB_NI, Jc = (n.H2 + Cn - 1) / Cn;
     const size_t s = sizeof(float) * ((size_t)4 * SB_NI * n.H2 + 2 * (size_t)B * SB_NI + 8 + (size_t)B * n.O +
-                                      (size_t)B * (n.H2 + 1) + (size_t)B * n.inp + (size_t)B * Jc);
+                                      (size_t)B * (n.H2 + 8) + (size_t)B * n.inp + (size_t)B * Jc);
     smem = s > smem ? s : smem;
     rlc_invalidate_pack(h, n.theta);
     if (n.target) rlc_invalidate_pack(h, n.target);
@@ -573,6 +631,8 @@ extern "C" int rlc_sb_update(rlc_handle* h, const rlc_sb_train* nets, int n_nets
   args.n_nets = n_nets;
   args.B = B;
   args.inv_btotal = 1.f / (float)B_total;
+  const char* dbg_env = getenv("RLC_SB_DEBUG");
+  args.dbg = dbg_env ? (unsigned long long*)strtoull(dbg_env, nullptr, 16) : nullptr;
   if (smem > 48 * 1024 && (int)smem > smem_set) {
     RLC_REQUIRE(smem <= h->smem_optin);
     RLC_CUDA(cudaFuncSetAttribute(k_sb_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

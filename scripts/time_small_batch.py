@@ -54,3 +54,15 @@ timeit("rlc_reduce_rkl_policy (k_grid_logterms + k_policy_reduce)", lambda: net.
 timeit("k_env_step_train", exp._env_step)
 timeit("k_loop_stage", lambda: exp._stage(True))
 timeit("whole training step (graph of 1)", lambda: exp._train_step(True), reps=20)
+
+# %globaltimer trace of one rlc_sb_update launch (CTA 0, thread 0)
+dbg = torch.zeros(128, dtype=torch.int64, device=net.device)
+os.environ["RLC_SB_DEBUG"] = hex(dbg.data_ptr())
+for _ in range(3):
+    check(lib.rlc_sb_forward(h, st.sb_fwd, 5, B, _stream()))
+    check(lib.rlc_sb_update(h, st.sb_upd, 3, B, B, _stream()))
+torch.cuda.synchronize()
+t = dbg.cpu().numpy()
+names = {65: "prologue loads staged", 66: "dz2 done", 67: "bulk W2 rows + moments arrived", 68: "dh1/dz1 done", 69: "dW2 + Adam done",
+         70: "barrier", 71: "small parameters + Adam done"}
+print("rlc_sb_update trace (ns from kernel start):", {names[k]: int(t[k] - t[64]) for k in sorted(names)})
