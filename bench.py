@@ -407,6 +407,33 @@ def run_b200(args, rank, local_rank, world):
     torch.cuda.synchronize()
     sweep_ms = (time.perf_counter() - t0) * 1e3 / n_sw
 
+    # cfg1 / cfg5 as whole RUNS (environment + replay + agent on the device, rlcontrol_b200/device_loop.py): the README
+    # command's loop -- env.step, replay add, minibatch sample, full update_network, Polyak, sample_action per step,
+    # evaluation sessions (10 greedy episodes every 500 steps) included -- for 1 run and 8 interleaved runs per GPU
+    from rlcontrol_b200 import device_loop as dl
+    run_steps = 3000
+    env_json = {"environment": "Pendulum-v0", "TotalMilSteps": run_steps / 1e6, "EpisodeSteps": -1,
+                "EvalIntervalMilSteps": 0.0005, "EvalEpisodes": 10}
+    spec_dl = dl.EnvSpec(env_json)
+
+    def make_run(seed):
+        c = kl_config(rb.Engine(local_rank), 3, 1, 2.0, B1, 64, 200, 200, random_seed=seed, gamma=0.99, warmup_steps=0,
+                      buffer_size=1e6, sample_for_eval="False", **{k: v for k, v in spec_dl.env_params().items()
+                                                                    if k in ("state_min", "state_max")})
+        torch.manual_seed(seed)
+        return dl.DeviceExperiment(kl_networks.ReverseKLNetwork(None, None, c), env_json, c)
+
+    def timed_runs(exps):
+        for e in exps:
+            e._build()
+        torch.cuda.synchronize()
+        t0_ = time.perf_counter()
+        dl.run_interleaved(exps)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0_
+    run1_s = timed_runs([make_run(0)])
+    run8_s = timed_runs([make_run(i) for i in range(8)])
+
     # cfg4, the full ForwardKL update_network on this rank's B=4096 minibatch with the synthetic [N,A] grid
     # (q/v/pi networks 400-300, three backward passes and Adam steps; tensor-core grid evaluation inside)
     torch.manual_seed(1)
@@ -501,6 +528,13 @@ def run_b200(args, rank, local_rank, world):
                       "cfg5_sweep8_updates_per_sec": world * 8 * 1e3 / sweep_ms, "cfg5_sweep8_ms_per_round": sweep_ms,
                       "cfg5_definition": "8 independent cfg1 agents per GPU (own handles, streams and graph each), one full update "
                                          "each per round, launched back to back then awaited; replicas only",
+                      "cfg1_run_env_steps_per_sec": run_steps / run1_s,
+                      "cfg5_runs8_env_steps_per_sec": world * 8 * run_steps / run8_s,
+                      "device_run_definition": "whole runs of the README command on the device (Pendulum-v0 + ReverseKL, %d steps "
+                                               "each): per step env.step + replay add + minibatch of 32 from the reference's index "
+                                               "stream + full update_network + Polyak + sample_action, evaluation sessions (10 x "
+                                               "200 greedy steps every 500 steps) inside the timed region; 1 run / 8 interleaved "
+                                               "runs per GPU (rlcontrol_b200.device_loop)" % run_steps,
                       "critic_update_rows_per_rank": B,
                       "critic_update_allreduce": "nccl sum of theta_Q grads" if world > 1 else "none (1 rank)"},
         }

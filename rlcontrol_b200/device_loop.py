@@ -140,7 +140,8 @@ class DeviceExperiment:
     ``run()`` returns the tuple ``Experiment.run()`` returns; ``run_data()`` the dict main.py stores per run.
     ``begin() / launch_chunk() / finish()`` let a sweep interleave several runs on one GPU."""
 
-    def __init__(self, network, env_json: dict, config, chunk_steps: int = 250, buffer_capacity: int | None = None):
+    def __init__(self, network, env_json: dict, config, chunk_steps: int = 250, buffer_capacity: int | None = None,
+                 steps_per_graph: int = 25):
         self.net, self.spec, self.cfg = network, EnvSpec(env_json), config
         sp = self.spec
         if (sp.state_dim, sp.action_dim) != (network.state_dim, network.action_dim):
@@ -153,6 +154,7 @@ class DeviceExperiment:
         self.warmup = int(getattr(config, "warmup_steps", 0))
         self.seed = int(config.random_seed)
         self.K = int(chunk_steps)
+        self.U = max(1, int(steps_per_graph))                          # learning steps captured per graph launch
         self.ring = 2 * self.K                                         # two halves: one in flight, one being filled
         # every stored transition needs a slot only until evicted: the run adds at most total_steps of them
         cap = int(getattr(config, "buffer_size", 1e6))
@@ -297,6 +299,9 @@ class DeviceExperiment:
             self._eval_session()
         self.stream.synchronize()
         self.g_learn = self._capture(lambda: self._train_step(True))
+        # U consecutive learning steps as ONE graph: the host's launch cost per step drops by U (with 8 runs sharing a
+        # GPU the single host thread, not the device, was the limit)
+        self.g_learn_u = self._capture(lambda: [self._train_step(True) for _ in range(self.U)]) if self.U > 1 else None
         self.g_nolearn = self._capture(lambda: self._train_step(False))
         self.g_eval = self._capture(self._eval_session)
         for t, s_ in zip(ts, saved):
@@ -378,10 +383,19 @@ class DeviceExperiment:
         with torch.cuda.stream(self.stream):
             for dst, src in ((self.f_eps_act, self.h_eps_act), (self.f_eps_upd, self.h_eps_upd), (self.f_idx, self.h_idx)):
                 dst[lo:lo + n].copy_(src[lo:lo + n], non_blocking=True)
-            for i in range(n):
-                (self.g_learn if learn[i] else self.g_nolearn).replay()
-                self.t += 1
-                if sp.eval_interval > 0 and self.t % sp.eval_interval == 0:
+            i, U, ei = 0, self.U, sp.eval_interval
+            while i < n:
+                # a U-step graph when the next U steps all learn and no evaluation session falls inside them
+                if self.g_learn_u is not None and i + U <= n and learn[i:i + U].all() and \
+                        (ei <= 0 or (self.t % ei) + U <= ei):
+                    self.g_learn_u.replay()
+                    self.t += U
+                    i += U
+                else:
+                    (self.g_learn if learn[i] else self.g_nolearn).replay()
+                    self.t += 1
+                    i += 1
+                if ei > 0 and self.t % ei == 0:
                     self.g_eval.replay()
                     self.sessions += 1
                     self.timesteps_at_eval.append(self.t)

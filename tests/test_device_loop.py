@@ -138,7 +138,7 @@ def test_device_experiment_matches_oracle_loop(eng, env_name, ep, kind):
     net = (kl_networks.ReverseKLNetwork if kind == "rkl" else kl_networks.ForwardKLNetwork)(None, None, cfg)
     twin = _oracle_twin(net, kind)
     want = oenv.run_experiment(twin, env_json, seed, B, 0.99, _draws_like_device(torch, seed, 1, B, K, 70))
-    exp = dl.DeviceExperiment(net, env_json, cfg, chunk_steps=K)
+    exp = dl.DeviceExperiment(net, env_json, cfg, chunk_steps=K, steps_per_graph=1 if kind == "fkl" else 4)
     before = net.export_parameters()
     got = exp.run()
     (ep_r, ev_r, ep_s, ev_s, t_ev, _, _, n_ep, cum) = got
@@ -170,7 +170,7 @@ def test_interleaved_runs_equal_solo_runs(eng):
     def make(seed):
         cfg = _config(spec, seed, engine=None)
         torch.manual_seed(seed)
-        return dl.DeviceExperiment(kl_networks.ReverseKLNetwork(None, None, cfg), env_json, cfg, chunk_steps=20)
+        return dl.DeviceExperiment(kl_networks.ReverseKLNetwork(None, None, cfg), env_json, cfg, chunk_steps=20, steps_per_graph=5)
     solo = [make(s).run() for s in (0, 1, 2)]
     exps = [make(s) for s in (0, 1, 2)]
     together = dl.run_interleaved(exps)
