@@ -178,3 +178,40 @@ def test_interleaved_runs_equal_solo_runs(eng):
         for x, y in zip(a[:5], b[:5]):
             assert x == y                                      # bit-identical: runs share nothing
     assert solo[0][0] != solo[1][0]
+
+
+def test_main_device_writes_the_reference_pickle(eng, tmp_path):
+    """`python -m rlcontrol_b200.main_device` with main.py's arguments: INDEX decoding, grouping of runs on the GPU and
+    the pickled dictionary of main.py:80-95,188-203."""
+    import json
+    import pickle
+    from rlcontrol_b200 import main_device
+    env_json = {"environment": "Pendulum-v0", "TotalMilSteps": 60e-6, "EpisodeSteps": 12, "EvalIntervalMilSteps": 20e-6,
+                "EvalEpisodes": 2}
+    agent_json = {"agent": "ReverseKL", "sweeps": {
+        "norm_type": ["input_norm"], "exploration_policy": ["none"], "actor_l1_dim": [24], "actor_l2_dim": [24],
+        "critic_l1_dim": [32], "critic_l2_dim": [24], "pi_lr": [1e-3], "qf_vf_lr": [1e-2, 1e-3], "sample_for_eval": ["False"],
+        "use_true_q": ["False"], "entropy_scale": [0.1], "l_param": [6], "N_param": [16], "optim_type": ["intg"],
+        "q_update_type": ["non_sac"]}}
+    (tmp_path / "Pendulum-v0.json").write_text(json.dumps(env_json))
+    (tmp_path / "reverse_kl.json").write_text(json.dumps(agent_json))
+    main_device.main(["--env_json", str(tmp_path / "Pendulum-v0.json"), "--agent_json", str(tmp_path / "reverse_kl.json"),
+                      "--indices", "0", "1", "4", "--save_dir", str(tmp_path / "results"), "--runs_per_gpu", "3"])
+    path = tmp_path / "results" / "Pendulum-v0_reverse_klresults" / "data_0_1_4.pkl"
+    data = pickle.loads(path.read_bytes())
+    assert data["experiment"]["agent"]["agent_name"] == "ReverseKL"
+    assert data["experiment"]["environment"] == {"env_name": "Pendulum-v0", "total_timesteps": 60.0, "steps_per_episode": 12,
+                                                 "eval_interval_timesteps": 20.0, "eval_episodes": 2}
+    assert sorted(data["experiment_data"]) == [0, 1]                       # two settings (qf_vf_lr), two runs each
+    for setting, lr in ((0, 1e-2), (1, 1e-3)):
+        d = data["experiment_data"][setting]
+        assert d["agent_params"]["qf_vf_lr"] == lr and len(d["runs"]) == 2
+        assert [r["random_seed"] for r in d["runs"]] == [0, 1]             # RANDOM_SEED = RUN_NUM (main.py:131-141)
+        for r in d["runs"]:
+            assert r["eval_episode_rewards"].shape == (4, 2) and r["timesteps_at_eval"].tolist() == [0, 20, 40, 60]
+            assert r["train_episode_steps"].tolist() == [12] * 5 and r["total_train_episodes"] == 5
+            assert np.all(r["train_episode_rewards"] < 0) and r["episodes_per_eval"] == 2
+    # same seed, different learning rate: the first episodes coincide until learning starts to matter
+    a, b = data["experiment_data"][0]["runs"][0], data["experiment_data"][1]["runs"][0]
+    np.testing.assert_allclose(a["eval_episode_rewards"][0], b["eval_episode_rewards"][0], rtol=1e-12)
+    assert not np.allclose(a["eval_episode_rewards"][-1], b["eval_episode_rewards"][-1], rtol=1e-9)
