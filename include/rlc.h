@@ -385,6 +385,16 @@ int rlc_env_step_train(rlc_handle* h, const rlc_env* env, int64_t* cur, double* 
 int rlc_loop_stage(rlc_handle* h, const int64_t* cur, int B, int A, int64_t feed_rows, const float* eps_act_feed,
                    const float* eps_upd_feed, const int* idx_feed, int64_t cap, float* eps_act, float* eps_upd,
                    int64_t* slots, void* stream);
+/* rlc_env_step_train + rlc_loop_stage + rlc_replay_gather as ONE launch (the head of a captured training step):
+ * env.step and the replay append, then this step's feeds are staged (eps_act[A], eps_upd[B,A]) and the minibatch
+ * idx_feed[k,:] is gathered from the ring into s_out[B,S], a_out[B,A], r_out[B], s2_out[B,S], g_out[B].
+ * idx_feed == NULL (steps before learning starts): only eps_act is staged. */
+int rlc_loop_step(rlc_handle* h, const rlc_env* env, int64_t* cur, double* env_state, int* ep_step, float* obs,
+                  const float* action, const double* reset_feed, int64_t reset_rows, float* rb_state, float* rb_action,
+                  float* rb_reward, float* rb_next_state, float* rb_gamma, int64_t cap, float gamma, int64_t ring_rows,
+                  double* reward_log, int* flag_log, int B, const float* eps_act_feed, const float* eps_upd_feed,
+                  const int* idx_feed, float* eps_act, float* eps_upd, float* s_out, float* a_out, float* r_out,
+                  float* s2_out, float* g_out, void* stream);
 
 /* ---- small-minibatch fast path of the ForwardKL / ReverseKL update (cfg1 / cfg5) -------------------
  * forwardkl_network.py:123-209 / reversekl_network.py:130-217 at B <= 64 rows: every B-row forward pass in ONE

@@ -127,14 +127,13 @@ __global__ void k_eval_store(int E, const double* __restrict__ ep_ret, const int
 // episode limit -> next observation (or the next episode's reset observation) into obs.
 // cur: [0] step row k in this chunk's feeds/logs  [1] replay count  [2] replay head  [3] reset-feed row
 //      [4] total steps taken
-__global__ void k_env_step_train(rlc_env env, long long* __restrict__ cur, double* __restrict__ state,
+__device__ __forceinline__ void env_step_train_body(const rlc_env& env, long long* __restrict__ cur, double* __restrict__ state,
                                  int* __restrict__ ep_step, float* __restrict__ obs,
                                  const float* __restrict__ action, const double* __restrict__ reset_feed,
                                  long long reset_rows, float* __restrict__ rb_state, float* __restrict__ rb_action,
                                  float* __restrict__ rb_reward, float* __restrict__ rb_next,
                                  float* __restrict__ rb_gamma, long long cap, float gamma, long long log_rows,
                                  double* __restrict__ reward_log, int* __restrict__ flag_log) {
-  if (threadIdx.x != 0) return;
   const long long k = cur[0] % log_rows;
   const EnvOut o = env_dynamics(env, state[0], state[1], action);
   const int n = ep_step[0] + 1;
@@ -179,6 +178,73 @@ __global__ void k_env_step_train(rlc_env env, long long* __restrict__ cur, doubl
   }
   cur[0] = (k + 1) % log_rows;   // feeds and logs are a ring: the host fills one half while the other is in flight
   cur[4] += 1;
+}
+
+__global__ void k_env_step_train(rlc_env env, long long* __restrict__ cur, double* __restrict__ state,
+                                 int* __restrict__ ep_step, float* __restrict__ obs,
+                                 const float* __restrict__ action, const double* __restrict__ reset_feed,
+                                 long long reset_rows, float* __restrict__ rb_state, float* __restrict__ rb_action,
+                                 float* __restrict__ rb_reward, float* __restrict__ rb_next,
+                                 float* __restrict__ rb_gamma, long long cap, float gamma, long long log_rows,
+                                 double* __restrict__ reward_log, int* __restrict__ flag_log) {
+  if (threadIdx.x != 0) return;
+  env_step_train_body(env, cur, state, ep_step, obs, action, reset_feed, reset_rows, rb_state, rb_action, rb_reward, rb_next,
+                      rb_gamma, cap, gamma, log_rows, reward_log, flag_log);
+}
+
+// The head of a training step as ONE launch (one CTA): env.step + replay append by thread 0, then -- behind a block
+// barrier, which also orders thread 0's global writes for the rest of the CTA -- the feeds of this step are staged and
+// the minibatch is gathered from the ring (the row just appended may be among the sampled ones).  Three launches of a
+// few microseconds each became one; inside a captured step every launch boundary is ~2 us of dependent latency.
+struct LoopStepArgs {
+  rlc_env env;
+  long long* cur;
+  double* state;
+  int* ep_step;
+  float* obs;
+  const float* action;
+  const double* reset_feed;
+  long long reset_rows;
+  float *rb_state, *rb_action, *rb_reward, *rb_next, *rb_gamma;
+  long long cap;
+  float gamma;
+  long long ring_rows;
+  double* reward_log;
+  int* flag_log;
+  int B;
+  const float *eps_act_feed, *eps_upd_feed;
+  const int* idx_feed;
+  float *eps_act, *eps_upd;
+  float *s_out, *a_out, *r_out, *s2_out, *g_out;
+};
+
+__global__ void __launch_bounds__(256) k_loop_step(const __grid_constant__ LoopStepArgs p) {
+  const int tid = threadIdx.x;
+  if (tid == 0)
+    env_step_train_body(p.env, p.cur, p.state, p.ep_step, p.obs, p.action, p.reset_feed, p.reset_rows, p.rb_state,
+                        p.rb_action, p.rb_reward, p.rb_next, p.rb_gamma, p.cap, p.gamma, p.ring_rows, p.reward_log,
+                        p.flag_log);
+  __threadfence_block();
+  __syncthreads();
+  const int S = p.env.S, A = p.env.A, B = p.B;
+  const long long k = (p.cur[0] % p.ring_rows + p.ring_rows - 1) % p.ring_rows;   // the row thread 0 just logged
+  const long long head = p.cur[2], count = p.cur[1];
+  if (tid < A) p.eps_act[tid] = p.eps_act_feed[k * A + tid];
+  if (!p.idx_feed) return;                   // steps before learning starts: nothing to sample
+  for (int t = tid; t < B * A; t += blockDim.x) p.eps_upd[t] = p.eps_upd_feed[k * B * A + t];
+  const int W = 2 * S + A + 2;               // floats per gathered transition
+  for (int t = tid; t < B * W; t += blockDim.x) {
+    const int b = t / W, f = t % W;
+    long long i = p.idx_feed[k * B + b];
+    if (i < 0) i = 0;
+    if (count > 0 && i >= count) i = count - 1;
+    const long long slot = (head + i) % p.cap;
+    if (f < S) p.s_out[b * S + f] = p.rb_state[slot * S + f];
+    else if (f < 2 * S) p.s2_out[b * S + (f - S)] = p.rb_next[slot * S + (f - S)];
+    else if (f < 2 * S + A) p.a_out[b * A + (f - 2 * S)] = p.rb_action[slot * A + (f - 2 * S)];
+    else if (f == 2 * S + A) p.r_out[b] = p.rb_reward[slot];
+    else p.g_out[b] = p.rb_gamma[slot];
+  }
 }
 
 // Stage step k = cur[0]-1 of the host-drawn feeds into the fixed buffers the captured update reads: the N(0,1)
@@ -261,6 +327,29 @@ extern "C" int rlc_loop_stage(rlc_handle* h, const int64_t* cur, int B, int A, i
   k_loop_stage<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const long long*)cur, B, A, feed_rows, eps_act_feed,
                                                                   eps_upd_feed, idx_feed, cap, eps_act, eps_upd,
                                                                   (long long*)slots);
+  RLC_LAUNCH_CHECK(h);
+  return RLC_OK;
+}
+
+extern "C" int rlc_loop_step(rlc_handle* h, const rlc_env* env, int64_t* cur, double* env_state, int* ep_step, float* obs,
+                             const float* action, const double* reset_feed, int64_t reset_rows, float* rb_state,
+                             float* rb_action, float* rb_reward, float* rb_next_state, float* rb_gamma, int64_t cap,
+                             float gamma, int64_t ring_rows, double* reward_log, int* flag_log, int B,
+                             const float* eps_act_feed, const float* eps_upd_feed, const int* idx_feed, float* eps_act,
+                             float* eps_upd, float* s_out, float* a_out, float* r_out, float* s2_out, float* g_out,
+                             void* stream) {
+  RLC_REQUIRE(h && env_ok(env) && cur && env_state && ep_step && obs && action && reset_feed && reset_rows >= 1);
+  RLC_REQUIRE(rb_state && rb_action && rb_reward && rb_next_state && rb_gamma && cap >= 1 && ring_rows >= 1 && reward_log &&
+              flag_log && eps_act_feed && eps_act && B >= 0);
+  RLC_REQUIRE(!idx_feed || (eps_upd_feed && eps_upd && s_out && a_out && r_out && s2_out && g_out && B >= 1));
+  LoopStepArgs p;
+  p.env = *env; p.cur = (long long*)cur; p.state = env_state; p.ep_step = ep_step; p.obs = obs; p.action = action;
+  p.reset_feed = reset_feed; p.reset_rows = reset_rows; p.rb_state = rb_state; p.rb_action = rb_action;
+  p.rb_reward = rb_reward; p.rb_next = rb_next_state; p.rb_gamma = rb_gamma; p.cap = cap; p.gamma = gamma;
+  p.ring_rows = ring_rows; p.reward_log = reward_log; p.flag_log = flag_log; p.B = B; p.eps_act_feed = eps_act_feed;
+  p.eps_upd_feed = eps_upd_feed; p.idx_feed = idx_feed; p.eps_act = eps_act; p.eps_upd = eps_upd; p.s_out = s_out;
+  p.a_out = a_out; p.r_out = r_out; p.s2_out = s2_out; p.g_out = g_out;
+  k_loop_step<<<1, 256, 0, (cudaStream_t)stream>>>(p);
   RLC_LAUNCH_CHECK(h);
   return RLC_OK;
 }

@@ -674,8 +674,13 @@ extern "C" int rlc_sb_forward(rlc_handle* h, const rlc_sb_net* nets, int n_nets,
     const size_t act = (size_t)(n.inp + n.H1 + n.H2) * SB_ROWS + (size_t)SB_ROWS * n.O;
     const size_t s_ring = sizeof(float) * ((size_t)SB_NST * SB_KC * SB_THREADS + act);
     const size_t s_res = sizeof(float) * ((size_t)n.inp * n.H1 + (size_t)n.H1 * n.H2 + 4 * SB_THREADS * 4 + act);
-    const bool res = (((uintptr_t)n.theta) & 15) == 0 && ((n.inp * n.H1) & 3) == 0 && (n.H1 & 3) == 0 && (n.H2 & 3) == 0 &&
-                     s_res + 1024 <= h->smem_optin && getenv("RLC_SB_NO_RESIDENT") == nullptr;
+    // resident weights pay off for the tiny latency-critical launches (sample_action, an evaluation step: one or two
+    // CTAs); at ~205 KB they leave room for one CTA per SM, so the big launch of a training step keeps the ring (two
+    // CTAs per SM: with 8 runs sharing the GPU its 132 CTAs per run are throughput, not latency)
+    int total_ctas = 0;
+    for (int q = 0; q < n_nets; ++q) total_ctas += ((nets[q].rows ? nets[q].rows : B) + SB_ROWS - 1) / SB_ROWS;
+    const bool res = total_ctas <= 8 && (((uintptr_t)n.theta) & 15) == 0 && ((n.inp * n.H1) & 3) == 0 && (n.H1 & 3) == 0 &&
+                     (n.H2 & 3) == 0 && s_res + 1024 <= h->smem_optin && getenv("RLC_SB_NO_RESIDENT") == nullptr;
     args.resident[i] = res ? 1 : 0;
     const size_t s = res ? s_res : s_ring;
     smem = s > smem ? s : smem;

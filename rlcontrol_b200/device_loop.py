@@ -242,13 +242,16 @@ class DeviceExperiment:
     def _train_step(self, learn: bool):
         """experiment.py:118-142 for one step; ``learn`` = BaseAgent.learn's size test (base_agent.py:64-66)."""
         sp, rb, d = self.spec, self.rb, self.st.d
-        self._env_step()
-        self._stage(learn)
+        # env.step + replay append + this step's feeds + minibatch gather: one launch (rlc_loop_step)
+        check(self.lib.rlc_loop_step(
+            self.eng.h, C.byref(sp.desc), _ptr(self.cur), _ptr(self.env_state), _ptr(self.ep_step), _ptr(self.obs),
+            _ptr(self.act["action"]), _ptr(self.train_resets), self.train_resets.shape[0], _ptr(rb["s"]), _ptr(rb["a"]),
+            _ptr(rb["r"]), _ptr(rb["s2"]), _ptr(rb["g"]), self.cap, self.gamma, self.ring, _ptr(self.reward_log),
+            _ptr(self.flag_log), self.B, _ptr(self.f_eps_act), _ptr(self.f_eps_upd) if learn else None,
+            _ptr(self.f_idx) if learn else None, _ptr(self.eps_act), _ptr(d["eps"]) if learn else None,
+            _ptr(d["s"]) if learn else None, _ptr(d["a"]) if learn else None, _ptr(d["r"]) if learn else None,
+            _ptr(d["s2"]) if learn else None, _ptr(d["g"]) if learn else None, _stream()))
         if learn:
-            check(self.lib.rlc_replay_gather(self.eng.h, _ptr(rb["s"]), _ptr(rb["a"]), _ptr(rb["r"]), _ptr(rb["s2"]),
-                                             _ptr(rb["g"]), self.cap, sp.state_dim, sp.action_dim, _ptr(self.slots),
-                                             self.B, _ptr(d["s"]), _ptr(d["a"]), _ptr(d["r"]), _ptr(d["s2"]), _ptr(d["g"]),
-                                             _stream()))
             self.net._enqueue(self.st, self.B, device_inputs=True)
             if not self.small:
                 self.net.eng_v.soft_update(self.net.target_v.theta, self.net.v.theta, self.net.tau)
