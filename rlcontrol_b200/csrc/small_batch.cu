@@ -18,6 +18,8 @@
 #include "policy_math.cuh"
 
 #define SB_ROWS 16       // rows per forward CTA
+#define SB_LD 20         // floats per k in the activation tiles ([K][SB_LD], rows 0..15 used): 5 quads per row, so float4
+                         // stores of consecutive columns by consecutive lanes fall in distinct bank groups
 #define SB_THREADS 256
 #define SB_NI 8          // hidden-1 units per backward CTA (more, smaller CTAs: every phase that scales with it is latency)
 #define SB_KC 16         // weight rows per ring stage
@@ -99,15 +101,22 @@ __device__ __forceinline__ void sb_fma16(float (&acc)[4][4], const float4 a, con
   acc[3][2] = fmaf(a.z, w.w, acc[3][2]); acc[3][3] = fmaf(a.w, w.w, acc[3][3]);
 }
 
-// out(r, j) = bias[j] + sum_k in_s[k][r] * W[k][j] for the CTA's 16 rows; `in_s` is k-major ([K][16]).  A thread owns a
-// 4-column x 4-row register tile: per k it reads its 4 weights and its 4 row operands as ONE float4 each (the row
-// operands are a warp-wide broadcast) for 16 FMAs.  The first version gave a thread one column and all 16 rows: four
-// broadcast float4 per k per thread, and the load/store unit's return bandwidth (4 cycles per 128-bit warp load), not
-// the FMA pipe, set the pace (%globaltimer trace: 500 ns per 8-row chunk).  Row groups beyond `nrows` (padding rows
-// of a short pass, e.g. the single row of sample_action) do not compute.  f(j, r, v) consumes one finished value.
+
+// (A 3xTF32 mma.sync.m16n8k8 version of this tile was built and measured: legacy mma.sync issues at ~40 cycles per
+// instruction here, 512 ns per 16-row chunk against 290-500 ns for the CUDA-core tile -- no gain, removed.)
+
+// out(r, j) = bias[j] + sum_k in_s[k][r] * W[k][j] for the CTA's 16 rows; `in_s` is k-major ([K][SB_LD]).  A thread owns
+// a 4-column x 4-row register tile: columns cq, cq+64, cq+128, cq+192 of the 256-column block (consecutive lanes =
+// consecutive columns: conflict-free weight reads and coalesced stores) and rows 4rg..4rg+3 (one broadcast float4 per
+// k).  History, all measured: one column x 16 rows per thread was bound by the load/store unit's return path (four
+// broadcast LDS.128 per k per thread); `if (kk < nk)` predicates kept the compiler from hoisting loads (the full-chunk
+// path is branch-free); owning 4 ADJACENT columns made the epilogue's shared-memory stores a 32-way bank conflict
+// (2 us per layer) -- with this mapping and SB_LD = 20 a finished column goes out as one conflict-free float4.
+// Row groups beyond `nrows` (padding rows of a short pass) do not compute.  f4(j, r0, v) consumes rows r0..r0+3 of
+// column j.
 template <class F>
 __device__ __forceinline__ void sb_layer(const float* __restrict__ W, const float* __restrict__ bias, int K, int J,
-                                         const float* __restrict__ in_s, int nrows, SbRing& ring, F f,
+                                         const float* __restrict__ in_s, int nrows, SbRing& ring, F f4,
                                          unsigned long long* dbg = nullptr, int dbg0 = 0) {
   const int tid = threadIdx.x, cq = tid & 63, rg = tid >> 6;
   const bool row_active = 4 * rg < nrows;
@@ -132,11 +141,12 @@ __device__ __forceinline__ void sb_layer(const float* __restrict__ W, const floa
     //  the __syncthreads orders those reads before the copy is issued)
     if (bulk && tid == 0)
       for (int c = 0; c < min(SB_NST, nch); ++c) issue(c);
-    const bool col_active = 4 * cq < jc;
-    float acc[4][4];   // [column][row]
+    int col[4];          // this thread's columns inside the block, clamped so that every load is in range
+    float acc[4][4];     // [column][row]
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float bj = (col_active && 4 * cq + q < jc) ? bias[jb + 4 * cq + q] : 0.f;
+      col[q] = min(cq + 64 * q, jc - 1);
+      const float bj = bias[jb + col[q]];
 #pragma unroll
       for (int r = 0; r < 4; ++r) acc[q][r] = bj;
     }
@@ -155,25 +165,27 @@ __device__ __forceinline__ void sb_layer(const float* __restrict__ W, const floa
         }
         __syncthreads();
       }
-      if (col_active && row_active) {
-        const float* wp = wst + 4 * cq;
-        const float* ap = in_s + k0 * SB_ROWS + 4 * rg;
+      if (row_active) {
+        const float* ap = in_s + k0 * SB_LD + 4 * rg;
         if (nk == SB_KC) {       // full chunk: branch-free, operands of 4 k steps loaded ahead of their 64 FMAs
 #pragma unroll
           for (int kk0 = 0; kk0 < SB_KC; kk0 += 4) {
             float4 w[4], a[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              w[u] = *reinterpret_cast<const float4*>(wp + (kk0 + u) * js);
-              a[u] = *reinterpret_cast<const float4*>(ap + (kk0 + u) * SB_ROWS);
+              const float* wr = wst + (kk0 + u) * js;
+              w[u] = make_float4(wr[col[0]], wr[col[1]], wr[col[2]], wr[col[3]]);
+              a[u] = *reinterpret_cast<const float4*>(ap + (kk0 + u) * SB_LD);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) sb_fma16(acc, a[u], w[u]);
           }
         } else {
-          for (int kk = 0; kk < nk; ++kk)
-            sb_fma16(acc, *reinterpret_cast<const float4*>(ap + kk * SB_ROWS),
-                     *reinterpret_cast<const float4*>(wp + kk * js));
+          for (int kk = 0; kk < nk; ++kk) {
+            const float* wr = wst + kk * js;
+            sb_fma16(acc, *reinterpret_cast<const float4*>(ap + kk * SB_LD),
+                     make_float4(wr[col[0]], wr[col[1]], wr[col[2]], wr[col[3]]));
+          }
         }
       }
       SB_TRACE(dbg0 + 2 * c + 1);
@@ -182,14 +194,11 @@ __device__ __forceinline__ void sb_layer(const float* __restrict__ W, const floa
       if (bulk && tid == 0 && c + SB_NST < nch) issue(c + SB_NST);
     }
     ring.uses = bulk ? base_use + nch : base_use;   // the fallback never touches the mbarriers
-    if (col_active) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (4 * cq + q < jc) {
-#pragma unroll
-          for (int r = 0; r < 4; ++r) f(jb + 4 * cq + q, 4 * rg + r, row_active ? acc[q][r] : 0.f);
-        }
-    }
+    for (int q = 0; q < 4; ++q)
+      if (cq + 64 * q < jc)
+        f4(jb + cq + 64 * q, 4 * rg,
+           row_active ? make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]) : make_float4(0.f, 0.f, 0.f, 0.f));
   }
 }
 
@@ -199,21 +208,22 @@ __device__ __forceinline__ void sb_layer(const float* __restrict__ W, const floa
 // them idle, and add the partial sums through `red` ([4][256][4] floats).
 template <class F>
 __device__ __forceinline__ void sb_layer_res(const float* __restrict__ Ws, const float* __restrict__ bias, int K, int J,
-                                             const float* __restrict__ in_s, int nrows, float* __restrict__ red, F f) {
+                                             const float* __restrict__ in_s, int nrows, float* __restrict__ red, F f4) {
   const int tid = threadIdx.x, cq = tid & 63, rg = tid >> 6;
   const bool ksplit = nrows <= 4;
   for (int jb = 0; jb < J; jb += SB_THREADS) {
     const int jc = min(SB_THREADS, J - jb);
-    const bool col_active = 4 * cq < jc;
+    int col[4];
     float acc[4][4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float bj = (col_active && 4 * cq + q < jc && (!ksplit || rg == 0)) ? bias[jb + 4 * cq + q] : 0.f;
+      col[q] = min(cq + 64 * q, jc - 1);
+      const float bj = (!ksplit || rg == 0) ? bias[jb + col[q]] : 0.f;
 #pragma unroll
       for (int r = 0; r < 4; ++r) acc[q][r] = bj;
     }
-    if (col_active && (ksplit || 4 * rg < nrows)) {
-      const float* wp = Ws + jb + 4 * cq;
+    if (ksplit || 4 * rg < nrows) {
+      const float* wp = Ws + jb;
       const float* ap = in_s + (ksplit ? 0 : 4 * rg);
       const int kstep = ksplit ? 4 : 1;
       int k = ksplit ? rg : 0;
@@ -221,23 +231,25 @@ __device__ __forceinline__ void sb_layer_res(const float* __restrict__ Ws, const
         float4 w[4], a[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          w[u] = *reinterpret_cast<const float4*>(wp + (long long)(k + u * kstep) * J);
-          a[u] = *reinterpret_cast<const float4*>(ap + (k + u * kstep) * SB_ROWS);
+          const float* wr = wp + (long long)(k + u * kstep) * J;
+          w[u] = make_float4(wr[col[0]], wr[col[1]], wr[col[2]], wr[col[3]]);
+          a[u] = *reinterpret_cast<const float4*>(ap + (k + u * kstep) * SB_LD);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) sb_fma16(acc, a[u], w[u]);
       }
-      for (; k < K; k += kstep)
-        sb_fma16(acc, *reinterpret_cast<const float4*>(ap + k * SB_ROWS), *reinterpret_cast<const float4*>(wp + (long long)k * J));
+      for (; k < K; k += kstep) {
+        const float* wr = wp + (long long)k * J;
+        sb_fma16(acc, *reinterpret_cast<const float4*>(ap + k * SB_LD), make_float4(wr[col[0]], wr[col[1]], wr[col[2]], wr[col[3]]));
+      }
     }
     if (ksplit) {
       __syncthreads();
-      if (col_active) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<float4*>(red + ((rg * SB_THREADS + 4 * cq + q) << 2)) =
+      for (int q = 0; q < 4; ++q)
+        if (cq + 64 * q < jc)
+          *reinterpret_cast<float4*>(red + ((rg * SB_THREADS + cq + 64 * q) << 2)) =
               make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
-      }
       __syncthreads();
       // thread (column tid): sum the four partials of its column, rows 0..3
       if (tid < jc) {
@@ -247,18 +259,17 @@ __device__ __forceinline__ void sb_layer_res(const float* __restrict__ Ws, const
           const float4 t = *reinterpret_cast<const float4*>(red + ((g * SB_THREADS + tid) << 2));
           s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
         }
-        f(jb + tid, 0, s.x); f(jb + tid, 1, s.y); f(jb + tid, 2, s.z); f(jb + tid, 3, s.w);
+        f4(jb + tid, 0, s);
 #pragma unroll
-        for (int r = 4; r < SB_ROWS; ++r) f(jb + tid, r, 0.f);
+        for (int r0 = 4; r0 < SB_ROWS; r0 += 4) f4(jb + tid, r0, make_float4(0.f, 0.f, 0.f, 0.f));
       }
-    } else if (col_active) {
+    } else {
       const bool row_active = 4 * rg < nrows;
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        if (4 * cq + q < jc) {
-#pragma unroll
-          for (int r = 0; r < 4; ++r) f(jb + 4 * cq + q, 4 * rg + r, row_active ? acc[q][r] : 0.f);
-        }
+        if (cq + 64 * q < jc)
+          f4(jb + cq + 64 * q, 4 * rg,
+             row_active ? make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]) : make_float4(0.f, 0.f, 0.f, 0.f));
     }
   }
 }
@@ -279,9 +290,12 @@ __global__ void __launch_bounds__(SB_THREADS) k_sb_forward(const __grid_constant
   SbRing ring;
   ring.buf = sm;                                                  // ring: [SB_NST][SB_KC][SB_THREADS] | resident: W1, W2, red
   float* x_s = sm + (resident ? inp * H1 + H1 * H2 + 4 * SB_THREADS * 4 : SB_NST * SB_KC * SB_THREADS);   // [inp][16]
-  float* h1_s = x_s + inp * SB_ROWS;                              // [H1][16]
-  float* h2_s = h1_s + H1 * SB_ROWS;                              // [H2][16]
-  float* o_s = h2_s + H2 * SB_ROWS;                               // [16][O]
+  float* h1_s = x_s + inp * SB_LD;                              // [H1][16]
+  float* h2_s = h1_s + H1 * SB_LD;                              // [H2][16]
+  float* o_s = h2_s + H2 * SB_LD;                               // [16][O]
+  float* w3_s = o_s + SB_ROWS * O;                               // [H2][O] + b3[O]: staged early, with both bias vectors --
+  float* b2_s = w3_s + H2 * O + O;                               // [H2]      nothing on the critical path waits on HBM
+  float* b1_s = b2_s + H2;                                       // [H1]
   ring.bar0 = sb_smem_u32(bars);
   ring.uses = 0;
   if (tid == 0) {
@@ -304,9 +318,15 @@ __global__ void __launch_bounds__(SB_THREADS) k_sb_forward(const __grid_constant
   const float* b2 = W2 + (long long)H1 * H2;
   const float* W3 = b2 + H2;
   const float* b3 = W3 + (long long)H2 * O;
+  for (int i = tid; i < H2 * O; i += SB_THREADS) {
+    const float w = W3[i];
+    w3_s[i] = w;
+    if (rc == 0 && n.w3_snapshot) n.w3_snapshot[i] = w;
+  }
+  for (int i = tid; i < O; i += SB_THREADS) w3_s[H2 * O + i] = b3[i];
+  for (int i = tid; i < H2; i += SB_THREADS) b2_s[i] = b2[i];
+  for (int i = tid; i < H1; i += SB_THREADS) b1_s[i] = b1[i];
   if (rc == 0) {
-    if (n.w3_snapshot)
-      for (int i = tid; i < H2 * O; i += SB_THREADS) n.w3_snapshot[i] = W3[i];
     if (n.adam_state && tid == 0) {         // as k_adam_prep (critic_fp32.cu): the update launch reads the factors
       const int t = ++n.adam_state[0];
       const double bc1 = 1.0 - pow((double)n.beta1, (double)t), bc2 = 1.0 - pow((double)n.beta2, (double)t);
@@ -324,34 +344,36 @@ __global__ void __launch_bounds__(SB_THREADS) k_sb_forward(const __grid_constant
   }
   for (int i = tid; i < inp * SB_ROWS; i += SB_THREADS) {
     const int k = i / SB_ROWS, r = i % SB_ROWS;
-    x_s[i] = (b0 + r < rows) ? sb_x(n, b0 + r, k) : 0.f;
+    x_s[k * SB_LD + r] = (b0 + r < rows) ? sb_x(n, b0 + r, k) : 0.f;
   }
   __syncthreads();
   SB_TRACE(1);
   const int nrows = min(SB_ROWS, rows - b0);
-  auto put_h1 = [&](int j, int r, float v) {
-    const float a = fmaxf(v, 0.f);
-    h1_s[j * SB_ROWS + r] = a;
-    if (n.h1 && r < nrows) n.h1[(long long)(b0 + r) * H1 + j] = a;
+  auto put = [&](float* hs, float* hg, int Hn, int j, int r0, float4 v) {
+    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    *reinterpret_cast<float4*>(hs + j * SB_LD + r0) = v;
+    if (hg) {
+      if (r0 < nrows) hg[(long long)(b0 + r0) * Hn + j] = v.x;
+      if (r0 + 1 < nrows) hg[(long long)(b0 + r0 + 1) * Hn + j] = v.y;
+      if (r0 + 2 < nrows) hg[(long long)(b0 + r0 + 2) * Hn + j] = v.z;
+      if (r0 + 3 < nrows) hg[(long long)(b0 + r0 + 3) * Hn + j] = v.w;
+    }
   };
-  auto put_h2 = [&](int j, int r, float v) {
-    const float a = fmaxf(v, 0.f);
-    h2_s[j * SB_ROWS + r] = a;
-    if (n.h2 && r < nrows) n.h2[(long long)(b0 + r) * H2 + j] = a;
-  };
+  auto put_h1 = [&](int j, int r0, float4 v) { put(h1_s, n.h1, H1, j, r0, v); };
+  auto put_h2 = [&](int j, int r0, float4 v) { put(h2_s, n.h2, H2, j, r0, v); };
   if (resident) {
     float* red = sm + inp * H1 + H1 * H2;
     sb_mbar_wait(ring.bar0, 0);
-    sb_layer_res(sm, b1, inp, H1, x_s, nrows, red, put_h1);
+    sb_layer_res(sm, b1_s, inp, H1, x_s, nrows, red, put_h1);
     __syncthreads();
     SB_TRACE(2);
     sb_mbar_wait(ring.bar0 + 8, 0);
-    sb_layer_res(sm + inp * H1, b2, H1, H2, h1_s, nrows, red, put_h2);
+    sb_layer_res(sm + inp * H1, b2_s, H1, H2, h1_s, nrows, red, put_h2);
   } else {
-    sb_layer(W1, b1, inp, H1, x_s, nrows, ring, put_h1);
+    sb_layer(W1, b1_s, inp, H1, x_s, nrows, ring, put_h1);
     __syncthreads();
     SB_TRACE(2);
-    sb_layer(W2, b2, H1, H2, h1_s, nrows, ring, put_h2, dbg, 8);
+    sb_layer(W2, b2_s, H1, H2, h1_s, nrows, ring, put_h2, dbg, 8);
   }
   __syncthreads();
   SB_TRACE(3);
@@ -360,10 +382,10 @@ __global__ void __launch_bounds__(SB_THREADS) k_sb_forward(const __grid_constant
   for (int p = warp; p < nrows * O; p += SB_THREADS / 32) {
     const int r = p / O, o = p % O;
     float s = 0.f;
-    for (int j = lane; j < H2; j += 32) s = fmaf(h2_s[j * SB_ROWS + r], __ldg(W3 + (long long)j * O + o), s);
+    for (int j = lane; j < H2; j += 32) s = fmaf(h2_s[j * SB_LD + r], w3_s[j * O + o], s);
     s = warp_sum(s);
     if (lane == 0) {
-      s += b3[o];
+      s += w3_s[H2 * O + o];
       o_s[r * O + o] = s;
       if (b0 + r < rows) n.out[(long long)(b0 + r) * O + o] = s;
     }
@@ -671,7 +693,7 @@ extern "C" int rlc_sb_forward(rlc_handle* h, const rlc_sb_net* nets, int n_nets,
     args.net[i] = n;
     args.cta_base[i] = base;
     base += ((n.rows ? n.rows : B) + SB_ROWS - 1) / SB_ROWS;
-    const size_t act = (size_t)(n.inp + n.H1 + n.H2) * SB_ROWS + (size_t)SB_ROWS * n.O;
+    const size_t act = (size_t)(n.inp + n.H1 + n.H2) * SB_LD + (size_t)SB_ROWS * n.O + (size_t)n.H2 * n.O + n.O + n.H1 + n.H2;
     const size_t s_ring = sizeof(float) * ((size_t)SB_NST * SB_KC * SB_THREADS + act);
     const size_t s_res = sizeof(float) * ((size_t)n.inp * n.H1 + (size_t)n.H1 * n.H2 + 4 * SB_THREADS * 4 + act);
     // resident weights pay off for the tiny latency-critical launches (sample_action, an evaluation step: one or two

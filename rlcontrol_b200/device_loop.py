@@ -115,7 +115,9 @@ def sample_n_k(rng: np.random.RandomState, n: int, k: int) -> np.ndarray:
         return np.empty((0,), dtype=np.int64)
     if 3 * k >= n:
         return rng.choice(n, k, replace=False)
-    result = rng.choice(n, 2 * k)
+    # RandomState.choice(int n, size) without p is randint(0, n, size) on the same stream (same draws, same state
+    # afterwards: tests/test_oracle_env.py) at half the call overhead
+    result = rng.randint(0, n, size=2 * k)
     if len(set(result[:k].tolist())) == k:
         return result[:k]
     selected = set()
@@ -126,7 +128,7 @@ def sample_n_k(rng: np.random.RandomState, n: int, k: int) -> np.ndarray:
             x = result[i] = result[j]
             j += 1
             if j == 2 * k:
-                result[k:] = rng.choice(n, k)
+                result[k:] = rng.randint(0, n, size=k)
                 j = k
         selected.add(x)
     return result[:k]

@@ -43,7 +43,7 @@ for (inp, H1, H2, O, B, mis) in [(3, 200, 200, 2, 1, 0), (3, 200, 200, 2, 1, 1),
 # 8+2c / 9+2c / 10+2c = layer-2 chunk c: data arrived / computed / CTA past the barrier, 3 layer 2 done, 4 output layer done
 dbg = torch.zeros(128, dtype=torch.int64, device=dev)
 os.environ["RLC_SB_DEBUG"] = hex(dbg.data_ptr())
-inp, H1, H2, O, B = 3, 200, 200, 2, 1
+inp, H1, H2, O, B = 3, 200, 200, 2, int(os.environ.get('TRACE_B', 1))
 numel = inp * H1 + H1 + H1 * H2 + H2 + H2 * O + O
 theta = torch.randn(numel, device=dev) * 0.1
 x, out = torch.randn(B, inp, device=dev), torch.zeros(B, O, device=dev)
@@ -56,4 +56,4 @@ torch.cuda.synchronize()
 t = dbg.cpu().numpy()
 t0 = t[0]
 print("trace ns:", {k: int(t[k] - t0) for k in (1, 2, 3, 4)})
-print("layer-2 chunks (arrived, computed, past barrier):", [(int(t[8 + 2 * c] - t0), int(t[9 + 2 * c] - t0), int(t[10 + 2 * c] - t0)) for c in range(25)])
+print("layer-2 chunks (arrived, computed, past barrier):", [(int(t[8 + 2 * c] - t0), int(t[9 + 2 * c] - t0), int(t[10 + 2 * c] - t0)) for c in range(13)])
