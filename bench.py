@@ -333,8 +333,38 @@ def run_b200(args, rank, local_rank, world):
         torch.cuda.synchronize()
         trials.append((time.perf_counter() - t0) * 1e3)
     gc.enable()
+    e2e_blk_ms = float(np.median(trials))     # blocking call per step: copy in, launch, wait, copy out, strictly in sequence
+    blk_trials = trials
+    # the same steps through the pipelined API (steps.ForwardKLGridPipeline, two slots): every step still pays its own
+    # H2D and D2H copies, but step i+1 is staged and uploaded while step i computes; this is the headline e2e number
+    from rlcontrol_b200.steps import ForwardKLGridPipeline
+    pipe = ForwardKLGridPipeline(critic, a_d, w_d, ACTION_SCALE, alpha, B, precision=prec, depth=2)
+
+    def pipe_run(k_steps):
+        acc = 0.0
+        pipe.submit(*host_in[0])
+        for i in range(1, k_steps):
+            pipe.submit(*host_in[i & 3])
+            r = pipe.result()
+            acc += float(r[0][0]) + float(r[1][0, 0])
+        r = pipe.result()
+        return acc + float(r[0][0]) + float(r[1][0, 0])
+
+    pipe.submit(*host_in[0])
+    if abs(float(pipe.result()[0][0]) - loss_dev0) > 1e-5 * max(1.0, abs(loss_dev0)):
+        raise SystemExit("bench.py: pipelined e2e step disagrees with the device-resident step")
+    pipe_run(max(args.warmup, 3))
+    gc.disable()
+    trials = []
+    for _ in range(5):
+        barrier()
+        t0 = time.perf_counter()
+        pipe_run(args.steps)
+        torch.cuda.synchronize()
+        trials.append((time.perf_counter() - t0) * 1e3)
+    gc.enable()
     e2e_wall_ms = float(np.median(trials))
-    e2e_ms = e2e_wall_ms          # host-synchronous every step: wall clock IS the end-to-end time
+    e2e_ms = e2e_wall_ms          # every result is read on the host inside the window: wall clock IS the end-to-end time
     barrier()
     h2d = (fstep.s_host.numel() + fstep.mean_host.numel() + fstep.log_std_host.numel()) * 4
     d2h = (fstep.loss_host.numel() + fstep.dmean_host.numel() + fstep.dlog_std_host.numel()) * 4
@@ -464,10 +494,10 @@ def run_b200(args, rank, local_rank, world):
         cfg4_full_ms = float(tt.cpu())
 
     # ---- max over ranks ----
-    tm = torch.tensor([ms_total, e2e_ms, k1_ms, upd_ms, e2e_wall_ms], dtype=torch.float64, device=dev)
+    tm = torch.tensor([ms_total, e2e_ms, k1_ms, upd_ms, e2e_wall_ms, e2e_blk_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, k1_ms, upd_ms, e2e_wall_ms = [float(x) for x in tm.cpu()]
+    ms_total, e2e_ms, k1_ms, upd_ms, e2e_wall_ms, e2e_blk_ms = [float(x) for x in tm.cpu()]
 
     if rank == 0:
         peaks, peak_src = {}, "fallback"
@@ -505,7 +535,13 @@ def run_b200(args, rank, local_rank, world):
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
                     "wall_ms_per_step": e2e_wall_ms / args.steps, "trials": 5,
                     "trial_ms_per_step_min_max": [min(trials) / args.steps, max(trials) / args.steps],
-                    "api": "rlcontrol_b200.steps.ForwardKLGridStep(states, mean, log_std) -> (loss_b, dmean, dlog_std): host arrays in, host arrays out, one CUDA-graph launch + sync per step; timed with the host clock"},
+                    "blocking_value": evals_total / (e2e_blk_ms * 1e-3), "blocking_ms_per_step": e2e_blk_ms / args.steps,
+                    "blocking_trial_ms_per_step_min_max": [min(blk_trials) / args.steps, max(blk_trials) / args.steps],
+                    "api": "rlcontrol_b200.steps.ForwardKLGridPipeline: submit(states, mean, log_std) / result() -> (loss_b, dmean, "
+                           "dlog_std), host arrays in, host arrays out, two slots in flight (step i+1 is staged and uploaded while "
+                           "step i computes; every step pays its own H2D and D2H copy and its result is read on the host inside "
+                           "the timed window); blocking_* = the same steps through ForwardKLGridStep.__call__ (copy, launch, wait, "
+                           "copy in strict sequence); timed with the host clock"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "K1 fused T-in critic eval: k_critic_umma_grid (+ k_grid_parts pre-pass) [%s arithmetic]" % critic.tensor_arithmetic(True), "bound": "tensor",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,

@@ -112,6 +112,103 @@ class ForwardKLGridStep:
         return self.loss_host, self.dmean_host, self.dlog_std_host
 
 
+class ForwardKLGridPipeline:
+    """The same step as :class:`ForwardKLGridStep` for callers that keep the device busy: ``depth`` slots, each with its
+    own pinned staging and device buffers, the H2D copy of step i+1 and the D2H copy of step i-1 running on their own
+    streams under the kernels of step i.
+
+        p.submit(states, mean, log_std)     # stage + enqueue, returns at once
+        loss_b, dmean, dlog_std = p.result()    # oldest outstanding step; blocks until its result is on the host
+
+    Every step still pays its own host->device and device->host copies; what disappears is the serialisation of copy,
+    compute and host-side staging (a blocking ``__call__`` costs ~0.15 ms of it per step at cfg4)."""
+
+    def __init__(self, critic: Critic, grid, weights, action_scale: float, entropy_scale: float, B: int,
+                 precision="auto", b_total: Optional[int] = None, depth: int = 2):
+        eng = critic.eng
+        dev = eng.device
+        self.critic, self.eng = critic, eng
+        self.grid, self.w = _f32(grid, dev), _f32(weights, dev).reshape(-1)
+        self.N, self.A = self.grid.shape
+        if self.A != critic.A or self.w.numel() != self.N:
+            raise ValueError("grid / weights do not match the critic")
+        self.B, self.scale, self.alpha, self.prec = int(B), float(action_scale), float(entropy_scale), precision
+        self.b_total = int(b_total or B)
+        S, A = critic.S, self.A
+        n_in, n_out = B * (S + 2 * A), B * (1 + 2 * A)
+        self.s_in, self.s_compute, self.s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
+
+        def views(flat, shapes):
+            out, off = [], 0
+            for sh in shapes:
+                n = int(torch.Size(sh).numel())
+                out.append(flat[off:off + n].view(sh))
+                off += n
+            return out
+        self.slots = []
+        for _ in range(max(1, int(depth))):
+            sl = type("Slot", (), {})()
+            sl.in_host = torch.empty((n_in,), dtype=torch.float32).pin_memory()
+            sl.out_host = torch.empty((n_out,), dtype=torch.float32).pin_memory()
+            sl.in_dev = torch.empty((n_in,), dtype=torch.float32, device=dev)
+            sl.out_dev = torch.empty((n_out,), dtype=torch.float32, device=dev)
+            sl.h_in = views(sl.in_host, [(B, S), (B, A), (B, A)])
+            sl.d_in = views(sl.in_dev, [(B, S), (B, A), (B, A)])
+            sl.h_out = tuple(views(sl.out_host, [(B,), (B, A), (B, A)]))
+            sl.d_out = tuple(views(sl.out_dev, [(B,), (B, A), (B, A)]))
+            sl.q = torch.empty((B, self.N), dtype=torch.float32, device=dev)
+            sl.ev_in, sl.ev_done, sl.ev_out = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+            sl.graph = None
+            self.slots.append(sl)
+        # warm up (workspace growth, operand pack) and capture the kernels of every slot
+        for sl in self.slots:
+            with torch.cuda.stream(self.s_compute):
+                for _ in range(2):
+                    self._kernels(sl)
+            self.s_compute.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.s_compute):
+                self._kernels(sl)
+            sl.graph = g
+        self._next, self._oldest, self._outstanding = 0, 0, 0
+
+    def _kernels(self, sl):
+        self.critic.eval_into(sl.d_in[0], self.grid, sl.q, self.prec)
+        self.eng.fkl_policy(sl.q, self.w, self.grid, self.scale, sl.d_in[1], sl.d_in[2], self.alpha,
+                            b_total=self.b_total, out=sl.d_out)
+
+    def submit(self, states, mean, log_std):
+        if self._outstanding == len(self.slots):
+            raise RuntimeError("every slot is in flight: call result() first")
+        sl = self.slots[self._next]
+        for dst, src in zip(sl.h_in, (states, mean, log_std)):
+            dst.copy_(torch.as_tensor(src, dtype=torch.float32).reshape(dst.shape))
+        with torch.cuda.stream(self.s_in):
+            sl.in_dev.copy_(sl.in_host, non_blocking=True)
+            sl.ev_in.record(self.s_in)
+        with torch.cuda.stream(self.s_compute):
+            self.s_compute.wait_event(sl.ev_in)
+            sl.graph.replay()
+            sl.ev_done.record(self.s_compute)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(sl.ev_done)
+            sl.out_host.copy_(sl.out_dev, non_blocking=True)
+            sl.ev_out.record(self.s_out)
+        self._next = (self._next + 1) % len(self.slots)
+        self._outstanding += 1
+
+    def result(self):
+        """(loss_b [B], dmean [B,A], dlog_std [B,A]) of the oldest outstanding step: pinned host tensors, valid until
+        that slot is submitted again."""
+        if self._outstanding == 0:
+            raise RuntimeError("nothing was submitted")
+        sl = self.slots[self._oldest]
+        sl.ev_out.synchronize()
+        self._oldest = (self._oldest + 1) % len(self.slots)
+        self._outstanding -= 1
+        return sl.h_out
+
+
 class GridAgentUpdateStep:
     """The hot-path part of one ForwardKL / ReverseKL ``update_network`` (forwardkl_network.py:123-209,
     reversekl_network.py:130-217) as ONE CUDA graph:
