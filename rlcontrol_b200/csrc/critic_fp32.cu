@@ -273,11 +273,106 @@ k_tmid_rows(const float* __restrict__ p, const float* __restrict__ a, int act_pe
   }
 }
 
+// Forward-only variant with a 4-row register tile per thread (rows base + tid + 256 u): every broadcast read of
+// W2a / w3 from shared memory feeds four rows, and the action dimension is an exact template parameter.  With one row per
+// thread (k_tmid_rows) the kernel was bound by the load/store unit -- 9 broadcast LDS.128 per 4 columns per row, and
+// A = 6 padded to 8 -- at 18 TFLOP/s fp32 on 2(A+1)H2 flop/row.
+#define TMID_RPT 4
+template <int AT>
+__global__ void __launch_bounds__(256)
+k_tmid_rows4(const float* __restrict__ p, const float* __restrict__ a, int act_per_state, long long R, int N,
+             int H2, const float* __restrict__ W2a, const float* __restrict__ w3, const float* __restrict__ b3,
+             float* __restrict__ q_out) {
+  extern __shared__ float sm[];
+  const int H2P = (H2 + 3) & ~3;
+  float* w3s = sm;         // [H2P]
+  float* was = sm + H2P;   // [AT][H2P]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < H2P; i += 256) w3s[i] = (i < H2) ? w3[i] : 0.f;
+  for (int i = tid; i < AT * H2P; i += 256) {
+    const int ai = i / H2P, j = i - ai * H2P;
+    was[i] = (j < H2) ? W2a[(long long)ai * H2 + j] : 0.f;
+  }
+  __syncthreads();
+  const long long row0 = (long long)blockIdx.x * (256 * TMID_RPT) + tid;
+  float ar[TMID_RPT][AT], q[TMID_RPT];
+  const float* pb[TMID_RPT];
+#pragma unroll
+  for (int u = 0; u < TMID_RPT; ++u) {
+    const long long row = min(row0 + 256 * u, R - 1);       // clamped: tail threads recompute the last row, never store it
+    const long long b = row / N;
+    const long long arow = act_per_state ? row : (row - b * N);
+#pragma unroll
+    for (int i = 0; i < AT; ++i) ar[u][i] = a[arow * AT + i];
+    pb[u] = p + b * H2;
+    q[u] = 0.f;
+  }
+  for (int j = 0; j < H2P; j += 4) {
+    float z[TMID_RPT][4];
+#pragma unroll
+    for (int u = 0; u < TMID_RPT; ++u)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) z[u][c] = (j + c < H2) ? __ldg(pb[u] + j + c) : 0.f;
+#pragma unroll
+    for (int i = 0; i < AT; ++i) {
+      const float4 w = *reinterpret_cast<const float4*>(was + i * H2P + j);
+#pragma unroll
+      for (int u = 0; u < TMID_RPT; ++u) {
+        z[u][0] = fmaf(ar[u][i], w.x, z[u][0]);
+        z[u][1] = fmaf(ar[u][i], w.y, z[u][1]);
+        z[u][2] = fmaf(ar[u][i], w.z, z[u][2]);
+        z[u][3] = fmaf(ar[u][i], w.w, z[u][3]);
+      }
+    }
+    const float4 w3v = *reinterpret_cast<const float4*>(w3s + j);
+#pragma unroll
+    for (int u = 0; u < TMID_RPT; ++u) {
+      q[u] = fmaf(w3v.x, fmaxf(z[u][0], 0.f), q[u]);
+      q[u] = fmaf(w3v.y, fmaxf(z[u][1], 0.f), q[u]);
+      q[u] = fmaf(w3v.z, fmaxf(z[u][2], 0.f), q[u]);
+      q[u] = fmaf(w3v.w, fmaxf(z[u][3], 0.f), q[u]);
+    }
+  }
+  const float bias3 = __ldg(b3);
+#pragma unroll
+  for (int u = 0; u < TMID_RPT; ++u)
+    if (row0 + 256 * u < R) q_out[row0 + 256 * u] = q[u] + bias3;
+}
+
+template <int AT>
+static int launch_tmid_rows4(rlc_handle* h, const rlc_critic* c, const float* p, const float* a, int act_per_state,
+                             long long R, int N, float* q_out, cudaStream_t st) {
+  const ThetaView t = theta_view(RLC_TMID, c->S, c->A, c->H1, c->H2);
+  const int H2P = (c->H2 + 3) & ~3;
+  const size_t smem = (size_t)(H2P * (1 + AT)) * sizeof(float);
+  if (smem > h->smem_optin) return RLC_ERR_UNSUPPORTED;
+  const long long blocks = (R + 256 * TMID_RPT - 1) / (256 * TMID_RPT);
+  if (blocks > 0x7fffffffLL) return RLC_ERR_INVALID;
+  auto kern = k_tmid_rows4<AT>;
+  RLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)blocks, 256, smem, st>>>(p, a, act_per_state, R, N, c->H2, c->theta + t.oW2 + (int64_t)c->H1 * c->H2,
+                                            c->theta + t.ow3, c->theta + t.ob3, q_out);
+  RLC_LAUNCH_CHECK(h);
+  return RLC_OK;
+}
+
 template <bool GRAD>
 static int launch_tmid_rows(rlc_handle* h, const rlc_critic* c, const float* p, const float* a,
                             int act_per_state, long long R, int N, float* q_out, float* dqda_out,
                             cudaStream_t st) {
   if (R == 0) return RLC_OK;
+  if (!GRAD && q_out && R >= (long long)h->num_sms * 256 * TMID_RPT && c->A <= 8) {   // enough rows to fill the machine
+    switch (c->A) {
+      case 1: return launch_tmid_rows4<1>(h, c, p, a, act_per_state, R, N, q_out, st);
+      case 2: return launch_tmid_rows4<2>(h, c, p, a, act_per_state, R, N, q_out, st);
+      case 3: return launch_tmid_rows4<3>(h, c, p, a, act_per_state, R, N, q_out, st);
+      case 4: return launch_tmid_rows4<4>(h, c, p, a, act_per_state, R, N, q_out, st);
+      case 5: return launch_tmid_rows4<5>(h, c, p, a, act_per_state, R, N, q_out, st);
+      case 6: return launch_tmid_rows4<6>(h, c, p, a, act_per_state, R, N, q_out, st);
+      case 7: return launch_tmid_rows4<7>(h, c, p, a, act_per_state, R, N, q_out, st);
+      default: return launch_tmid_rows4<8>(h, c, p, a, act_per_state, R, N, q_out, st);
+    }
+  }
   const ThetaView t = theta_view(RLC_TMID, c->S, c->A, c->H1, c->H2);
   const float* W2a = c->theta + t.oW2 + (int64_t)c->H1 * c->H2;
   const float* w3 = c->theta + t.ow3;

@@ -189,6 +189,50 @@ k_fkl(const float* __restrict__ q, const float* __restrict__ w, const float* __r
   if (lane == 0) loss_b[b] = -acc;
 }
 
+// ForwardKL with the scaled row cached in shared memory (one warp = one state, N floats per warp): one global read of
+// q and one IEEE division per element for the whole kernel; same arithmetic and the same per-lane summation order as
+// k_fkl.  The streaming variant re-read the row from L2 and re-divided it in each of its three passes (47 us at
+// B=4096, N=1024); the register-cached one (93 registers) lost more to occupancy than it saved (69 us).
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
+k_fkl_smem(const float* __restrict__ q, const float* __restrict__ w, const float* __restrict__ logp,
+           int B, int N, float alpha, float inv_btotal, float* __restrict__ loss_b,
+           float* __restrict__ boltz, float* __restrict__ dlogp) {
+  extern __shared__ float fkl_rows[];
+  const int b = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  float* t = fkl_rows + (size_t)(threadIdx.x >> 5) * N;
+  const float* row = q + (long long)b * N;
+  const float* lp = logp + (long long)b * N;
+  float m = -CUDART_INF_F;
+#pragma unroll 8
+  for (int n = lane; n < N; n += 32) {
+    const float v = __fdiv_rn(row[n], alpha);
+    t[n] = v;
+    m = fmaxf(m, v);
+  }
+  m = warp_max(m);
+  float z = 0.f;
+#pragma unroll 8
+  for (int n = lane; n < N; n += 32) {        // a lane re-reads only what it wrote: no barrier needed
+    const float e = expf(t[n] - m);
+    t[n] = e;
+    z = fmaf(e, w[n], z);
+  }
+  z = warp_sum(z);
+  float acc = 0.f;
+#pragma unroll 8
+  for (int n = lane; n < N; n += 32) {
+    const float p = __fdiv_rn(t[n], z);
+    const float pw = p * w[n];
+    acc = fmaf(pw, lp[n], acc);
+    if (boltz) boltz[(long long)b * N + n] = p;
+    if (dlogp) dlogp[(long long)b * N + n] = -pw * inv_btotal;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) loss_b[b] = -acc;
+}
+
 // ReverseKL (reversekl_network.py:181-190 ; hard 197-203: alpha = 0)
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
 k_rkl(const float* __restrict__ q, const float* __restrict__ v, const float* __restrict__ w,
@@ -460,9 +504,13 @@ extern "C" int rlc_reduce_fkl(rlc_handle* h, const float* q, const float* w, con
 #define RLC_FKL(NPL_)                                                          \
   k_fkl<NPL_><<<nblocks(B), 32 * WARPS_PER_BLOCK, 0, (cudaStream_t)stream>>>( \
       q, w, logp, B, N, entropy_scale, 1.f / (float)B_total, loss_b_out, boltz_out, dlogp_out)
-  // measured on B200 at B=4096, N=1024: the register-cached variant (NPL=32, 93 registers) runs 69 us, the
-  // streaming one 47 us -- occupancy matters more than the re-reads here; small rows still take the cached path
+  // measured on B200 at B=4096, N=1024: register-cached (NPL=32, 93 registers) 69 us, streaming 47 us, shared-memory
+  // row cache (rows up to 3072 floats at 4 warps per CTA) the fastest; small rows keep the register path
+  const size_t row_smem = (size_t)WARPS_PER_BLOCK * N * sizeof(float);
   if (N <= 128) RLC_FKL(4);
+  else if (row_smem <= 48 * 1024)
+    k_fkl_smem<<<nblocks(B), 32 * WARPS_PER_BLOCK, row_smem, (cudaStream_t)stream>>>(
+        q, w, logp, B, N, entropy_scale, 1.f / (float)B_total, loss_b_out, boltz_out, dlogp_out);
   else RLC_FKL(0);
 #undef RLC_FKL
   RLC_LAUNCH_CHECK(h);
