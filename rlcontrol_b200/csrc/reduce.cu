@@ -189,45 +189,58 @@ k_fkl(const float* __restrict__ q, const float* __restrict__ w, const float* __r
   if (lane == 0) loss_b[b] = -acc;
 }
 
-// ForwardKL with the scaled row cached in shared memory (one warp = one state, N floats per warp): one global read of
-// q and one IEEE division per element for the whole kernel; same arithmetic and the same per-lane summation order as
-// k_fkl.  The streaming variant re-read the row from L2 and re-divided it in each of its three passes (47 us at
-// B=4096, N=1024); the register-cached one (93 registers) lost more to occupancy than it saved (69 us).
+// ForwardKL with the row in shared memory (one warp = one state).  ncu on the streaming variant: 15 % issue-active,
+// 32 warps stalled on the long scoreboard per issue -- one dependent HBM round trip after another (three passes, eight
+// scalar loads in flight per lane).  Here a lane issues ALL its loads of q and logp up front as 128-bit loads (16 in
+// flight at N = 1024), divides once, and every later pass reads shared memory; outputs leave as 128-bit stores.
+// Same arithmetic per element; the per-lane summation order follows the float4 layout (n = 4 (lane + 32 i) + c).
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
 k_fkl_smem(const float* __restrict__ q, const float* __restrict__ w, const float* __restrict__ logp,
            int B, int N, float alpha, float inv_btotal, float* __restrict__ loss_b,
            float* __restrict__ boltz, float* __restrict__ dlogp) {
-  extern __shared__ float fkl_rows[];
+  extern __shared__ __align__(16) float fkl_rows[];
   const int b = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
-  float* t = fkl_rows + (size_t)(threadIdx.x >> 5) * N;
-  const float* row = q + (long long)b * N;
-  const float* lp = logp + (long long)b * N;
+  const int N4 = N >> 2;                                       // N % 4 == 0 (host-checked)
+  float4* t4 = reinterpret_cast<float4*>(fkl_rows + (size_t)(threadIdx.x >> 5) * 2 * N);
+  float4* l4 = t4 + N4;
+  const float4* row4 = reinterpret_cast<const float4*>(q + (long long)b * N);
+  const float4* lp4 = reinterpret_cast<const float4*>(logp + (long long)b * N);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
   float m = -CUDART_INF_F;
 #pragma unroll 8
-  for (int n = lane; n < N; n += 32) {
-    const float v = __fdiv_rn(row[n], alpha);
-    t[n] = v;
-    m = fmaxf(m, v);
+  for (int i = lane; i < N4; i += 32) {
+    float4 v = __ldg(row4 + i);
+    const float4 l = __ldg(lp4 + i);
+    v.x = __fdiv_rn(v.x, alpha); v.y = __fdiv_rn(v.y, alpha); v.z = __fdiv_rn(v.z, alpha); v.w = __fdiv_rn(v.w, alpha);
+    t4[i] = v;
+    l4[i] = l;
+    m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
   }
   m = warp_max(m);
   float z = 0.f;
-#pragma unroll 8
-  for (int n = lane; n < N; n += 32) {        // a lane re-reads only what it wrote: no barrier needed
-    const float e = expf(t[n] - m);
-    t[n] = e;
-    z = fmaf(e, w[n], z);
+#pragma unroll 4
+  for (int i = lane; i < N4; i += 32) {        // a lane re-reads only what it wrote: no barrier needed
+    float4 e = t4[i];
+    const float4 ww = __ldg(w4 + i);
+    e.x = expf(e.x - m); e.y = expf(e.y - m); e.z = expf(e.z - m); e.w = expf(e.w - m);
+    t4[i] = e;
+    z = fmaf(e.x, ww.x, z); z = fmaf(e.y, ww.y, z); z = fmaf(e.z, ww.z, z); z = fmaf(e.w, ww.w, z);
   }
   z = warp_sum(z);
   float acc = 0.f;
-#pragma unroll 8
-  for (int n = lane; n < N; n += 32) {
-    const float p = __fdiv_rn(t[n], z);
-    const float pw = p * w[n];
-    acc = fmaf(pw, lp[n], acc);
-    if (boltz) boltz[(long long)b * N + n] = p;
-    if (dlogp) dlogp[(long long)b * N + n] = -pw * inv_btotal;
+  float4* bz4 = boltz ? reinterpret_cast<float4*>(boltz + (long long)b * N) : nullptr;
+  float4* dl4 = dlogp ? reinterpret_cast<float4*>(dlogp + (long long)b * N) : nullptr;
+#pragma unroll 4
+  for (int i = lane; i < N4; i += 32) {
+    const float4 e = t4[i], l = l4[i], ww = __ldg(w4 + i);
+    float4 p, pw;
+    p.x = __fdiv_rn(e.x, z); p.y = __fdiv_rn(e.y, z); p.z = __fdiv_rn(e.z, z); p.w = __fdiv_rn(e.w, z);
+    pw.x = p.x * ww.x; pw.y = p.y * ww.y; pw.z = p.z * ww.z; pw.w = p.w * ww.w;
+    acc = fmaf(pw.x, l.x, acc); acc = fmaf(pw.y, l.y, acc); acc = fmaf(pw.z, l.z, acc); acc = fmaf(pw.w, l.w, acc);
+    if (bz4) bz4[i] = p;
+    if (dl4) dl4[i] = make_float4(-pw.x * inv_btotal, -pw.y * inv_btotal, -pw.z * inv_btotal, -pw.w * inv_btotal);
   }
   acc = warp_sum(acc);
   if (lane == 0) loss_b[b] = -acc;
@@ -505,10 +518,12 @@ extern "C" int rlc_reduce_fkl(rlc_handle* h, const float* q, const float* w, con
   k_fkl<NPL_><<<nblocks(B), 32 * WARPS_PER_BLOCK, 0, (cudaStream_t)stream>>>( \
       q, w, logp, B, N, entropy_scale, 1.f / (float)B_total, loss_b_out, boltz_out, dlogp_out)
   // measured on B200 at B=4096, N=1024: register-cached (NPL=32, 93 registers) 69 us, streaming 47 us, shared-memory
-  // row cache (rows up to 3072 floats at 4 warps per CTA) the fastest; small rows keep the register path
-  const size_t row_smem = (size_t)WARPS_PER_BLOCK * N * sizeof(float);
+  // row cache (rows up to 1536 floats at 4 warps per CTA, 16-byte aligned) the fastest; small rows keep the register path
+  const size_t row_smem = (size_t)WARPS_PER_BLOCK * 2 * N * sizeof(float);
+  const bool vec_ok = (N & 3) == 0 && ((((uintptr_t)q) | ((uintptr_t)logp) | ((uintptr_t)w) | ((uintptr_t)boltz_out) |
+                                        ((uintptr_t)dlogp_out)) & 15) == 0;
   if (N <= 128) RLC_FKL(4);
-  else if (row_smem <= 48 * 1024)
+  else if (vec_ok && row_smem <= 48 * 1024)
     k_fkl_smem<<<nblocks(B), 32 * WARPS_PER_BLOCK, row_smem, (cudaStream_t)stream>>>(
         q, w, logp, B, N, entropy_scale, 1.f / (float)B_total, loss_b_out, boltz_out, dlogp_out);
   else RLC_FKL(0);
