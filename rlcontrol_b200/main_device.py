@@ -72,6 +72,12 @@ def run_indices(env_json: dict, agent_json: dict, indices, save_dir: str, env_na
     return path, data
 
 
+def rank_indices(indices, rank: int, world: int):
+    """(start, step, stop) of the INDEX values rank ``rank`` of ``world`` runs: every world-th one, no overlap."""
+    start, step, stop = (int(x) for x in indices)
+    return start + rank * step, step * world, stop
+
+
 def main(argv=None):
     p = argparse.ArgumentParser()
     p.add_argument("--env_json", type=str, required=True)
@@ -89,8 +95,7 @@ def main(argv=None):
         agent_json = json.load(f, object_pairs_hook=OrderedDict)
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
-    start, step, stop = args.indices
-    mine = (start + rank * step, step * world, stop)           # every WORLD_SIZE-th INDEX; no communication
+    mine = rank_indices(args.indices, rank, world)             # every WORLD_SIZE-th INDEX; no communication
     import torch
     torch.cuda.set_device(local)
     path, _ = run_indices(env_json, agent_json, mine, args.save_dir, env_name, agent_name, args.runs_per_gpu, device=local)

@@ -75,3 +75,16 @@ def test_sweep_runner_agents_are_independent_and_overlapped(eng):
                 np.testing.assert_array_equal(x, y)
     with pytest.raises(NotImplementedError):
         sweep.SweepRunner("DDPG", sweeps, PENDULUM, [0])
+
+
+def test_main_device_rank_partition_covers_every_index_once():
+    """torchrun ranks of rlcontrol_b200.main_device split range(START, STOP, STEP) without overlap (replicas only)."""
+    from rlcontrol_b200.main_device import rank_indices
+    for indices in [(0, 1, 64), (3, 2, 50), (0, 1, 5), (10, 7, 11)]:
+        rng_of = lambda t: list(range(t[0], t[2], t[1]))            # main.py:113: range(indices[0], indices[2], indices[1])
+        want = rng_of(indices)
+        for world in (1, 2, 4, 8):
+            got = [rng_of(rank_indices(indices, r, world)) for r in range(world)]
+            flat = sorted(i for g in got for i in g)
+            assert flat == want
+            assert all(g == want[r::world] for r, g in enumerate(got))
