@@ -426,7 +426,7 @@ __device__ __forceinline__ void sb_adam(float* __restrict__ theta, float* __rest
 
 __global__ void __launch_bounds__(SB_THREADS) k_sb_update(const __grid_constant__ SbUpdArgs args) {
   extern __shared__ __align__(128) float sm[];
-  __shared__ __align__(8) unsigned long long bar;
+  __shared__ __align__(8) unsigned long long bar, bar_h2;
   int ni = 0;
   while (ni + 1 < args.n_nets && (int)blockIdx.x >= args.cta_base[ni + 1]) ++ni;
   const rlc_sb_train& n = args.net[ni];
@@ -442,7 +442,8 @@ __global__ void __launch_bounds__(SB_THREADS) k_sb_update(const __grid_constant_
   const int Jc = (H2 + C - 1) / C, j0 = c * Jc, nJ = max(0, min(Jc, H2 - j0));
   // shared-memory carve-up (float offsets; the first four blocks are multiples of 4 floats)
   float* pw = sm;                               // [4][SB_NI][H2]  theta | m | v | target rows of W2 owned here
-  float* h1_s = pw + 4 * SB_NI * H2;            // [B][SB_NI]
+  float* h2f_s = pw + 4 * SB_NI * H2;           // [B][H2]        the whole second hidden layer (bulk copy)
+  float* h1_s = h2f_s + ((B * H2 + 3) & ~3);    // [B][SB_NI]
   float* dz1_s = h1_s + B * SB_NI;              // [B][SB_NI]
   float* red_s = dz1_s + B * SB_NI;             // [8]
   float* dz2_s = red_s + 8;                     // [B][H2p]     (16-byte aligned rows)
@@ -460,10 +461,18 @@ __global__ void __launch_bounds__(SB_THREADS) k_sb_update(const __grid_constant_
   const bool bulk = ((((uintptr_t)(n.theta + w2off)) | ((uintptr_t)(n.m + w2off)) | ((uintptr_t)(n.v + w2off)) |
                       (n.target ? (uintptr_t)(n.target + w2off) : 0)) & 15) == 0 && (slice_bytes & 15) == 0 &&
                     ((SB_NI * H2) & 3) == 0;
-  const uint32_t bar_a = sb_smem_u32(&bar);
+  const uint32_t bar_a = sb_smem_u32(&bar), bar_b = sb_smem_u32(&bar_h2);
+  const uint32_t h2_bytes = (uint32_t)(B * H2 * 4);
+  const bool bulk_h2 = (((uintptr_t)n.h2) & 15) == 0 && (h2_bytes & 15) == 0;
   if (tid == 0) {
     sb_mbar_init(bar_a, 1);
+    sb_mbar_init(bar_b, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (bulk_h2) {   // needed first (dz2), so it is issued first
+      sb_mbar_expect_tx(bar_b, h2_bytes);
+      for (uint32_t off = 0; off < h2_bytes; off += 32768u)
+        sb_bulk_g2s(sb_smem_u32(h2f_s) + off, reinterpret_cast<const char*>(n.h2) + off, min(32768u, h2_bytes - off), bar_b);
+    }
     if (bulk) {
       sb_mbar_expect_tx(bar_a, slice_bytes * (n.target ? 4 : 3));
       sb_bulk_g2s(sb_smem_u32(pw), n.theta + w2off, slice_bytes, bar_a);
@@ -531,13 +540,15 @@ __global__ void __launch_bounds__(SB_THREADS) k_sb_update(const __grid_constant_
     n.loss_out[0] = s;
   }
   // thread = column j: its W3 row in registers, coalesced h2 loads over b, no integer division
+  if (bulk_h2) sb_mbar_wait(bar_b, 0);
+  const float* h2src = bulk_h2 ? h2f_s : n.h2;   // (generic pointer: shared or global)
   for (int j = tid; j < H2; j += SB_THREADS) {
     float w3r[4];
 #pragma unroll
     for (int o = 0; o < 4; ++o) w3r[o] = o < O ? __ldg(n.w3_snapshot + j * O + o) : 0.f;
 #pragma unroll 8
     for (int b = 0; b < B; ++b) {
-      const float hv = n.h2[(long long)b * H2 + j];
+      const float hv = h2src[(long long)b * H2 + j];
       float s = 0.f;
 #pragma unroll
       for (int o = 0; o < 4; ++o)
@@ -747,7 +758,7 @@ extern "C" int rlc_sb_update(rlc_handle* h, const rlc_sb_train* nets, int n_nets
     args.cta_base[i] = base;
     base += (n.H1 + SB_NI - 1) / SB_NI;
     const int Cn = (n.H1 + SB_NI - 1) / SB_NI, Jc = (n.H2 + Cn - 1) / Cn;
-    const size_t s = sizeof(float) * ((size_t)4 * SB_NI * n.H2 + 2 * (size_t)B * SB_NI + 8 + (size_t)B * n.O +
+    const size_t s = sizeof(float) * ((size_t)4 * SB_NI * n.H2 + (size_t)B * n.H2 + 4 + 2 * (size_t)B * SB_NI + 8 + (size_t)B * n.O +
                                       (size_t)B * (n.H2 + 8) + (size_t)B * n.inp + (size_t)B * Jc);
     smem = s > smem ? s : smem;
     rlc_invalidate_pack(h, n.theta);
