@@ -587,32 +587,34 @@ __global__ void __launch_bounds__(SB_THREADS) k_sb_update(const __grid_constant_
     }
   }
   SB_TRACE(68);
-  // ---- dW2[i][j] = sum_b h1[b,i] dz2[b,j], straight into Adam.  4 x 4 register tiles (4 units x 4 columns per thread):
-  //      per b one float4 of dz2 and one broadcast float4 of h1 feed 16 FMAs.
+  // ---- dW2[i][j] = sum_b h1[b,i] dz2[b,j], straight into Adam.  Register tiles of SB_NI/4 units x 4 columns, so that
+  //      all four thread groups work: the Adam arithmetic (an IEEE sqrt and division per parameter) is a long
+  //      dependent chain per thread -- with 4-unit tiles only two groups were busy and it took 4.7 us of the kernel.
+  constexpr int UPT = SB_NI / 4;                // units per thread
   for (int jb = 0; jb < H2; jb += SB_THREADS) {
     const int jq = tid & 63, ig = tid >> 6, j = jb + 4 * jq;
-    if (j >= H2 || 4 * ig >= SB_NI) continue;
-    float acc[4][4];   // [unit][column]
+    if (j >= H2) continue;
+    float acc[UPT][4];   // [unit][column]
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < UPT; ++u)
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[u][q] = 0.f;
 #pragma unroll 4
     for (int b = 0; b < B; ++b) {
       const float4 d = *reinterpret_cast<const float4*>(dz2_s + b * H2p + j);     // H2p % 4 == 0; pad columns are 0
-      const float4 h = *reinterpret_cast<const float4*>(h1_s + b * SB_NI + 4 * ig);
-      acc[0][0] = fmaf(h.x, d.x, acc[0][0]); acc[0][1] = fmaf(h.x, d.y, acc[0][1]);
-      acc[0][2] = fmaf(h.x, d.z, acc[0][2]); acc[0][3] = fmaf(h.x, d.w, acc[0][3]);
-      acc[1][0] = fmaf(h.y, d.x, acc[1][0]); acc[1][1] = fmaf(h.y, d.y, acc[1][1]);
-      acc[1][2] = fmaf(h.y, d.z, acc[1][2]); acc[1][3] = fmaf(h.y, d.w, acc[1][3]);
-      acc[2][0] = fmaf(h.z, d.x, acc[2][0]); acc[2][1] = fmaf(h.z, d.y, acc[2][1]);
-      acc[2][2] = fmaf(h.z, d.z, acc[2][2]); acc[2][3] = fmaf(h.z, d.w, acc[2][3]);
-      acc[3][0] = fmaf(h.w, d.x, acc[3][0]); acc[3][1] = fmaf(h.w, d.y, acc[3][1]);
-      acc[3][2] = fmaf(h.w, d.z, acc[3][2]); acc[3][3] = fmaf(h.w, d.w, acc[3][3]);
-    }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = 4 * ig + u;
+      for (int u = 0; u < UPT; ++u) {
+        const float hv = h1_s[b * SB_NI + UPT * ig + u];                          // warp-wide broadcast
+        acc[u][0] = fmaf(hv, d.x, acc[u][0]);
+        acc[u][1] = fmaf(hv, d.y, acc[u][1]);
+        acc[u][2] = fmaf(hv, d.z, acc[u][2]);
+        acc[u][3] = fmaf(hv, d.w, acc[u][3]);
+      }
+    }
+    SB_TRACE(72);
+#pragma unroll
+    for (int u = 0; u < UPT; ++u) {
+      const int i = UPT * ig + u;
       if (i >= nI) continue;
       const int e = i * H2 + j;
       if (bulk && (H2 & 3) == 0) {   // aligned rows: 128-bit shared loads and coalesced 128-bit stores

@@ -63,6 +63,6 @@ for _ in range(3):
     check(lib.rlc_sb_update(h, st.sb_upd, 3, B, B, _stream()))
 torch.cuda.synchronize()
 t = dbg.cpu().numpy()
-names = {65: "prologue loads staged", 66: "dz2 done", 67: "bulk W2 rows + moments arrived", 68: "dh1/dz1 done", 69: "dW2 + Adam done",
+names = {65: "prologue loads staged", 66: "dz2 done", 67: "bulk W2 rows + moments arrived", 68: "dh1/dz1 done", 72: "dW2 sums done (before Adam)", 69: "dW2 + Adam done",
          70: "barrier", 71: "small parameters + Adam done"}
 print("rlc_sb_update trace (ns from kernel start):", {names[k]: int(t[k] - t[64]) for k in sorted(names)})
