@@ -123,9 +123,9 @@ def _draws_like_device(torch, seed, A, B, K, total):
     return lambda kind, t: (start if t == 0 else act[t - 1:t]) if kind == "act" else upd[t]
 
 
-@pytest.mark.parametrize("env_name,ep,kind", [("Pendulum-v0", 12, "rkl"), ("Bimodal1DEnv_uneq_var1", -1, "rkl"),
-                                             ("Pendulum-v0", 9, "fkl")])
-def test_device_experiment_matches_oracle_loop(eng, env_name, ep, kind):
+@pytest.mark.parametrize("env_name,ep,kind,fused", [("Pendulum-v0", 12, "rkl", True), ("Bimodal1DEnv_uneq_var1", -1, "rkl", True),
+                                                   ("Pendulum-v0", 9, "fkl", True), ("Pendulum-v0", 12, "rkl", False)])
+def test_device_experiment_matches_oracle_loop(eng, env_name, ep, kind, fused):
     import torch
     from rlcontrol_b200 import device_loop as dl
     from rlcontrol_b200 import kl_networks
@@ -134,8 +134,10 @@ def test_device_experiment_matches_oracle_loop(eng, env_name, ep, kind):
     spec = dl.EnvSpec(env_json)
     seed, B, K = 3, 8, 16                                     # 70 steps = 4 full chunks of 16 + 6: the feed ring wraps
     cfg = _config(spec, seed, kind, B, engine=eng)
+    cfg.fused_small_batch = fused                             # False: the generic multi-kernel update and acting path
     torch.manual_seed(seed)
     net = (kl_networks.ReverseKLNetwork if kind == "rkl" else kl_networks.ForwardKLNetwork)(None, None, cfg)
+    assert net._small_ok(B) == fused
     twin = _oracle_twin(net, kind)
     want = oenv.run_experiment(twin, env_json, seed, B, 0.99, _draws_like_device(torch, seed, 1, B, K, 70))
     exp = dl.DeviceExperiment(net, env_json, cfg, chunk_steps=K, steps_per_graph=1 if kind == "fkl" else 4)
