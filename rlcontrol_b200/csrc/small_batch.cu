@@ -685,6 +685,13 @@ __global__ void __launch_bounds__(SB_THREADS) k_sb_update(const __grid_constant_
   SB_TRACE(71);
 }
 
+// RLC_SB_DEBUG = hex device address of a >= 128-slot uint64 buffer (timing scripts set it before the launch they trace;
+// re-read on every call because they set it after the library is loaded -- one getenv, no allocation)
+static unsigned long long* sb_debug_buffer() {
+  const char* e = getenv("RLC_SB_DEBUG");
+  return e ? (unsigned long long*)strtoull(e, nullptr, 16) : nullptr;
+}
+
 static bool sb_dims_ok(int inp, int H1, int H2, int O, int n0, int n1) {
   return inp >= 1 && inp <= 256 && H1 >= 1 && H1 <= 512 && H2 >= 1 && H2 <= 512 && O >= 1 && O <= 32 &&
          n0 >= 0 && n1 >= 0 && n0 + n1 == inp;
@@ -692,7 +699,6 @@ static bool sb_dims_ok(int inp, int H1, int H2, int O, int n0, int n1) {
 
 extern "C" int rlc_sb_forward(rlc_handle* h, const rlc_sb_net* nets, int n_nets, int B, void* stream) {
   RLC_REQUIRE(h && nets && n_nets >= 1 && n_nets <= RLC_SB_MAX_NETS && B >= 1 && B <= RLC_SB_MAX_B);
-  static int smem_set = 0;
   SbFwdArgs args;
   size_t smem = 0;
   int base = 0;
@@ -723,12 +729,10 @@ extern "C" int rlc_sb_forward(rlc_handle* h, const rlc_sb_net* nets, int n_nets,
   args.cta_base[n_nets] = base;
   args.n_nets = n_nets;
   args.B = B;
-  const char* dbg_env = getenv("RLC_SB_DEBUG");   // hex device address of a >= 128-slot uint64 buffer (timing scripts)
-  args.dbg = dbg_env ? (unsigned long long*)strtoull(dbg_env, nullptr, 16) : nullptr;
-  if (smem > 48 * 1024 && (int)smem > smem_set) {
+  args.dbg = sb_debug_buffer();
+  if (smem > 48 * 1024) {   // a per-device function attribute: set on every launch that needs it (host-side, ~1 us)
     RLC_REQUIRE(smem <= h->smem_optin);
     RLC_CUDA(cudaFuncSetAttribute(k_sb_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = (int)smem;
   }
   k_sb_forward<<<base, SB_THREADS, smem, (cudaStream_t)stream>>>(args);
   RLC_LAUNCH_CHECK(h);
@@ -737,7 +741,6 @@ extern "C" int rlc_sb_forward(rlc_handle* h, const rlc_sb_net* nets, int n_nets,
 
 extern "C" int rlc_sb_update(rlc_handle* h, const rlc_sb_train* nets, int n_nets, int B, int B_total, void* stream) {
   RLC_REQUIRE(h && nets && n_nets >= 1 && n_nets <= RLC_SB_MAX_NETS && B >= 1 && B <= RLC_SB_MAX_B && B_total >= B);
-  static int smem_set = 0;
   SbUpdArgs args;
   size_t smem = 0;
   int base = 0;
@@ -770,12 +773,10 @@ extern "C" int rlc_sb_update(rlc_handle* h, const rlc_sb_train* nets, int n_nets
   args.n_nets = n_nets;
   args.B = B;
   args.inv_btotal = 1.f / (float)B_total;
-  const char* dbg_env = getenv("RLC_SB_DEBUG");
-  args.dbg = dbg_env ? (unsigned long long*)strtoull(dbg_env, nullptr, 16) : nullptr;
-  if (smem > 48 * 1024 && (int)smem > smem_set) {
+  args.dbg = sb_debug_buffer();
+  if (smem > 48 * 1024) {
     RLC_REQUIRE(smem <= h->smem_optin);
     RLC_CUDA(cudaFuncSetAttribute(k_sb_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = (int)smem;
   }
   k_sb_update<<<base, SB_THREADS, smem, (cudaStream_t)stream>>>(args);
   RLC_LAUNCH_CHECK(h);
