@@ -134,6 +134,57 @@ def sample_n_k(rng: np.random.RandomState, n: int, k: int) -> np.ndarray:
     return result[:k]
 
 
+_HOST_LIB = None
+
+
+def _host_lib():
+    """librlc_host.so (csrc/hostrng.c): the same index stream for a whole chunk of steps in C; None when not built."""
+    global _HOST_LIB
+    if _HOST_LIB is None:
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "librlc_host.so")
+        try:
+            lib = C.CDLL(path)
+            lib.rlc_host_sample_chunk.restype = C.c_int
+            lib.rlc_host_sample_chunk.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+            _HOST_LIB = lib
+        except OSError:
+            _HOST_LIB = False
+    return _HOST_LIB or None
+
+
+def sample_chunk(rng: np.random.RandomState, sizes: np.ndarray, k: int, out: np.ndarray, use_c: bool = True):
+    """``out[i] = sample_n_k(rng, sizes[i], k)`` for every step i with ``sizes[i] > 0``, in step order, on the caller's
+    RandomState (same draws and same final state as calling :func:`sample_n_k` step by step).  Steps in the rejection
+    branch (3k < n) go through the C helper in one call; the few early permutation-branch steps stay in Python."""
+    sizes = np.ascontiguousarray(sizes, dtype=np.int64)
+    n_steps = len(sizes)
+    lib = _host_lib() if use_c else None
+    i = 0
+    while i < n_steps:
+        if sizes[i] == 0:
+            i += 1
+            continue
+        if lib is None or 3 * k >= sizes[i] or sizes[i] > 2 ** 32:
+            out[i] = sample_n_k(rng, int(sizes[i]), k)
+            i += 1
+            continue
+        # the longest run of steps the C helper covers (sizes never shrink below 3k again in a run, but be general)
+        j = i
+        while j < n_steps and (sizes[j] == 0 or (3 * k < sizes[j] <= 2 ** 32)):
+            j += 1
+        st = rng.get_state()
+        key, pos = np.ascontiguousarray(st[1], dtype=np.uint32).copy(), C.c_int(int(st[2]))
+        block = np.empty((j - i, k), np.int32)
+        rc = lib.rlc_host_sample_chunk(key.ctypes.data, C.byref(pos), sizes[i:j].ctypes.data, j - i, int(k), block.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("rlc_host_sample_chunk failed")
+        rng.set_state((st[0], key, pos.value, st[3], st[4]))
+        sel = sizes[i:j] > 0
+        out[i:j][sel] = block[sel]
+        i = j
+
+
 class DeviceExperiment:
     """One run (one sweep INDEX) of ``Experiment`` on the device.
 
@@ -356,20 +407,17 @@ class DeviceExperiment:
         self.h_eps_act[lo:lo + n] = torch.randn(n, A, generator=self.gen)
         self.h_eps_upd[lo:lo + n] = torch.randn(n, B, A, generator=self.gen)
         idx = self.h_idx.numpy()
-        learn = np.zeros(n, bool)
         bandit = sp.desc.kind == ENV_BIMODAL1D
         thresh = max(self.warmup, B)
-        for i in range(n):
-            self.ep_t += 1
-            done = bandit or self.ep_t >= sp.episode_limit
-            truncated = (not bandit) and done and self.ep_t == sp.episode_limit
-            if not truncated:
-                self.replay_n = min(self.replay_n + 1, self.cap)
-            if done:
-                self.ep_t = 0
-            if self.replay_n > thresh:
-                learn[i] = True
-                idx[lo + i] = sample_n_k(self.rng_replay, self.replay_n, B)
+        # per-step bookkeeping of the reference loop, vectorised over the chunk: position inside the episode, whether the
+        # step is cut by the episode limit (not stored, experiment.py:127-134), replay size after the step
+        L = 1 if bandit else sp.episode_limit
+        pos = (self.ep_t + np.arange(n)) % L + 1
+        truncated = np.zeros(n, bool) if bandit else pos == L
+        sizes = np.minimum(self.replay_n + np.cumsum(~truncated), self.cap)
+        learn = sizes > thresh                                  # BaseAgent.learn (base_agent.py:64-66)
+        self.ep_t, self.replay_n = int(pos[-1] % L), int(sizes[-1])
+        sample_chunk(self.rng_replay, np.where(learn, sizes, 0), B, idx[lo:lo + n])
         return learn
 
     def launch_chunk(self):

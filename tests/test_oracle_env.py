@@ -126,3 +126,28 @@ def test_oracle_experiment_loop_bookkeeping(env_name, ep):
     first = next(t for t in range(30) if (t + 1) // limit * stored_per_ep + min((t + 1) % limit, stored_per_ep) > 4)
     assert upd == list(range(first, 30))
     assert [t for k, t in calls if k == "act"] == list(range(30)) + ([30] if 30 % limit else [])
+
+
+@pytest.mark.parametrize("k,n0,steps,seed", [(32, 20, 400, 0), (8, 25, 300, 1), (32, 97, 50, 2), (4, 13, 200, 3), (32, 100000, 64, 4)])
+def test_chunked_c_sampler_is_numpy_stream_bit_for_bit(k, n0, steps, seed):
+    """csrc/hostrng.c (MT19937 + masked rejection + the duplicate-replacement loop) against numpy's RandomState driven
+    step by step by the oracle's sample_n_k: same indices, same generator state afterwards -- through the small-n
+    permutation branch (left to numpy), populations just above 3k (many collisions, second-half refills) and steps
+    without a minibatch."""
+    assert dl._host_lib() is not None, "librlc_host.so is not built (make -C rlcontrol_b200/csrc)"
+    sizes = np.array([0 if (i % 7 == 3 or n0 + i <= k) else n0 + i for i in range(steps)], np.int64)
+    sizes[steps // 2:] = np.minimum(sizes[steps // 2:], n0 + steps // 2 + 5)        # the ring is full: the size stops growing
+    r_ref, r_c, r_py = (np.random.RandomState(seed) for _ in range(3))
+    want = np.zeros((steps, k), np.int64)
+    for i, n in enumerate(sizes):
+        if n:
+            want[i] = onp.sample_n_k(r_ref, int(n), k)
+    got_c, got_py = np.zeros((steps, k), np.int32), np.zeros((steps, k), np.int32)
+    dl.sample_chunk(r_c, sizes, k, got_c)
+    dl.sample_chunk(r_py, sizes, k, got_py, use_c=False)
+    np.testing.assert_array_equal(got_c, want)
+    np.testing.assert_array_equal(got_py, want)
+    a, b, c = r_ref.get_state(), r_c.get_state(), r_py.get_state()
+    np.testing.assert_array_equal(a[1], b[1])
+    assert a[2] == b[2] and a[2] == c[2]
+    assert r_ref.randint(1 << 30) == r_c.randint(1 << 30) == r_py.randint(1 << 30)
