@@ -1,7 +1,7 @@
 // K6: replay minibatch gather / scatter over a device-resident struct-of-arrays ring
 // (utils/replaybuffer.py:25-37).  HBM-bound: algorithmic bytes = B*(2S+A+2)*4 read + the same
-// written (+8 B per index).  One warp per sampled transition; every field row is copied with
-// coalesced (16-byte when aligned) loads.
+// written (+8 B per index).  Gather: one thread per output float (k_replay_gather_flat); scatter and the
+// fallback gather: one warp per transition, every field row copied with coalesced (16-byte when aligned) loads.
 #include "common.cuh"
 
 __device__ __forceinline__ void copy_row(const float* __restrict__ src, float* __restrict__ dst,
@@ -36,6 +36,62 @@ k_replay_gather(const float* __restrict__ state, const float* __restrict__ actio
   }
 }
 
+// Element-per-thread gather (default): a CTA owns `gr` consecutive sampled rows and walks their gr*(2S+A+2) output
+// floats with one thread per float, so every lane of a load instruction is live (the warp-per-row kernel below keeps
+// 17 + 17 + 6 + 2 of 4 x 32 lanes busy at S=17, A=6), the loads of a batch of UNROLL elements are all issued before the
+// first store, and both the ring reads (within a field row) and the output writes are contiguous across lanes.
+// Element -> (row, field offset) by a multiply-high with a host-computed reciprocal (exact for every i < 32 E when E <= 8192; checked exhaustively in tests/test_abi.py).
+#define GATHER_THREADS 128
+#define GATHER_MAX_ROWS 32
+#define GATHER_UNROLL 4
+
+__global__ void __launch_bounds__(GATHER_THREADS)
+k_replay_gather_flat(const float* __restrict__ state, const float* __restrict__ action,
+                     const float* __restrict__ reward, const float* __restrict__ next_state,
+                     const float* __restrict__ gamma, long long cap, int S, int A,
+                     const long long* __restrict__ idx, int B, int gr, unsigned magic,
+                     float* __restrict__ s_out, float* __restrict__ a_out, float* __restrict__ r_out,
+                     float* __restrict__ s2_out, float* __restrict__ g_out) {
+  __shared__ long long sidx[GATHER_MAX_ROWS];
+  const int tid = threadIdx.x;
+  const long long row0 = (long long)blockIdx.x * gr;
+  const int nrow = (int)min((long long)gr, (long long)B - row0);
+  if (tid < nrow) {
+    const long long j = idx[row0 + tid];
+    sidx[tid] = (j < 0 || j >= cap) ? -1ll : j;   // host wrapper validates indices; never read out of bounds
+  }
+  __syncthreads();
+  const unsigned E = (unsigned)(2 * S + A + 2);
+  const unsigned total = (unsigned)nrow * E;
+  for (unsigned base = tid; base < total; base += GATHER_THREADS * GATHER_UNROLL) {
+    float v[GATHER_UNROLL];
+    float* dst[GATHER_UNROLL];
+#pragma unroll
+    for (int u = 0; u < GATHER_UNROLL; ++u) {
+      const unsigned i = base + u * GATHER_THREADS;
+      dst[u] = nullptr;
+      if (i < total) {
+        const unsigned r = __umulhi(i, magic);
+        int e = (int)(i - r * E);
+        const long long j = sidx[r];
+        const long long row = row0 + r;
+        if (j >= 0) {
+          const float* src;
+          if (e < S) { src = state + j * S + e; dst[u] = s_out + row * S + e; }
+          else if ((e -= S) < S) { src = next_state + j * S + e; dst[u] = s2_out + row * S + e; }
+          else if ((e -= S) < A) { src = action + j * A + e; dst[u] = a_out + row * A + e; }
+          else if (e == A) { src = reward + j; dst[u] = r_out + row; }
+          else { src = gamma + j; dst[u] = g_out + row; }
+          v[u] = __ldg(src);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < GATHER_UNROLL; ++u)
+      if (dst[u]) *dst[u] = v[u];
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_replay_scatter(float* __restrict__ state, float* __restrict__ action, float* __restrict__ reward,
                  float* __restrict__ next_state, float* __restrict__ gamma, long long cap, int S,
@@ -65,9 +121,20 @@ extern "C" int rlc_replay_gather(rlc_handle* h, const float* state, const float*
   RLC_REQUIRE(s_out && a_out && r_out && s2_out && g_out && cap >= 1 && S >= 1 && A >= 1 && B >= 0);
   if (B == 0) return RLC_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  k_replay_gather<<<(unsigned)(((long long)B * 32 + 255) / 256), 256, 0, st>>>(
-      state, action, reward, next_state, gamma, cap, S, A, (const long long*)idx, B, s_out, a_out,
-      r_out, s2_out, g_out);
+  const long long E = 2LL * S + A + 2;
+  static const bool warp_rows = getenv("RLC_GATHER_WARP") != nullptr;   // A/B switch for the older kernel
+  if (warp_rows || E > 8192) {   // reciprocal checked exhaustively for E <= 8192 (tests/test_abi.py)
+    k_replay_gather<<<(unsigned)(((long long)B * 32 + 255) / 256), 256, 0, st>>>(
+        state, action, reward, next_state, gamma, cap, S, A, (const long long*)idx, B, s_out, a_out,
+        r_out, s2_out, g_out);
+  } else {
+    // small minibatches: few rows per CTA so the launch still spreads over the SMs
+    const int gr = B >= h->num_sms * 16 * GATHER_MAX_ROWS ? GATHER_MAX_ROWS : 8;
+    const unsigned magic = (unsigned)((1ULL << 32) / (unsigned long long)E) + 1u;
+    k_replay_gather_flat<<<(unsigned)((B + gr - 1) / gr), GATHER_THREADS, 0, st>>>(
+        state, action, reward, next_state, gamma, cap, S, A, (const long long*)idx, B, gr, magic, s_out,
+        a_out, r_out, s2_out, g_out);
+  }
   RLC_LAUNCH_CHECK(h);
   return RLC_OK;
 }

@@ -10,11 +10,20 @@ PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 RING = 10
 
 
+ONLY = os.environ.get("HBM_ONLY", "")          # substring filter on the kernel names, e.g. HBM_ONLY=K6
+NCU = os.environ.get("HBM_NCU", "") == "1"      # under ncu: two eager calls per kernel, no graph, no timing
+
+
 def timeit(fn, reps=20):
     """Device time per call: the calls are captured into one CUDA graph (RING calls over the rotating buffers) and the
     graph is replayed, so the number is kernel time, not the Python/ctypes issue rate (a few us per call, which is
     longer than several of these kernels)."""
     st = torch.cuda.Stream()
+    if NCU:
+        with torch.cuda.stream(st):
+            fn(0); fn(1)
+        st.synchronize()
+        return 1.0
     with torch.cuda.stream(st):
         for i in range(RING):
             fn(i)
@@ -36,6 +45,10 @@ def timeit(fn, reps=20):
 
 
 def report(name, nbytes, sec, note=""):
+    if ONLY and ONLY not in name:
+        return
+    sec = sec() if callable(sec) else sec
+    note = note(sec) if callable(note) else note
     gbs = nbytes / sec / 1e9
     print(json.dumps({"kernel": name, "algorithmic_bytes": int(nbytes), "us": round(sec * 1e6, 2), "GB_per_s": round(gbs, 1),
                       "hbm_peak_GB_per_s": PEAK, "frac": round(gbs / PEAK, 3), "note": note}), flush=True)
@@ -51,23 +64,23 @@ def main():
     w = torch.rand(N, device=dev, generator=g)
     v = torch.randn(B, device=dev, generator=g)
     report("K3 rlc_reduce_topk k=6 (idx + q_sel, no gather) q[4096,1024]", B * N * 4 + B * k * 12,
-           timeit(lambda i: eng.topk(qs[i], k)), "k selection rounds over a register-resident row")
-    report("K3 rlc_reduce_stats (argmax, max, mean)", B * N * 4 + B * 16, timeit(lambda i: eng.stats(qs[i])))
-    report("K3 rlc_reduce_lse (SQL soft value)", B * N * 4 + B * 4, timeit(lambda i: eng.soft_value(qs[i], A)))
+           lambda: timeit(lambda i: eng.topk(qs[i], k)), "k selection rounds over a register-resident row")
+    report("K3 rlc_reduce_stats (argmax, max, mean)", B * N * 4 + B * 16, lambda: timeit(lambda i: eng.stats(qs[i])))
+    report("K3 rlc_reduce_lse (SQL soft value)", B * N * 4 + B * 4, lambda: timeit(lambda i: eng.soft_value(qs[i], A)))
     report("K3 rlc_reduce_fkl (q, logp in; loss_b out)", 2 * B * N * 4 + B * 4,
-           timeit(lambda i: eng.fkl(qs[i], w, lps[i], 0.1, want_boltz=False, want_grad=False)))
+           lambda: timeit(lambda i: eng.fkl(qs[i], w, lps[i], 0.1, want_boltz=False, want_grad=False)))
     report("K3 rlc_reduce_fkl (q, logp in; loss_b, boltz, dlogp out)", 4 * B * N * 4 + B * 4,
-           timeit(lambda i: eng.fkl(qs[i], w, lps[i], 0.1)))
+           lambda: timeit(lambda i: eng.fkl(qs[i], w, lps[i], 0.1)))
     report("K3 rlc_reduce_rkl (q, logp in; loss_b, dlogp out)", 3 * B * N * 4 + B * 8,
-           timeit(lambda i: eng.rkl(qs[i], v, w, lps[i], 0.1)))
+           lambda: timeit(lambda i: eng.rkl(qs[i], v, w, lps[i], 0.1)))
     grid = torch.rand(N, A, device=dev, generator=g) * 1.9 - 0.95
     mean = torch.randn(B, A, device=dev, generator=g) * 0.5
     lstd = torch.randn(B, A, device=dev, generator=g) * 0.3 - 0.5
     outp = (torch.empty(B, device=dev), torch.empty(B, A, device=dev), torch.empty(B, A, device=dev))
     report("K3 rlc_reduce_fkl_policy (q in; loss_b, dmean, dlog_std out; log-density in place, A=6)", B * N * 4 + B * (1 + 2 * A) * 4,
-           timeit(lambda i: eng.fkl_policy(qs[i], w, grid, 1.0, mean, lstd, 0.1, out=outp)), "k_grid_logterms + k_policy_reduce")
+           lambda: timeit(lambda i: eng.fkl_policy(qs[i], w, grid, 1.0, mean, lstd, 0.1, out=outp)), "k_grid_logterms + k_policy_reduce")
     report("K3 rlc_reduce_rkl_policy (same, ReverseKL)", B * N * 4 + B * (2 + 2 * A) * 4,
-           timeit(lambda i: eng.rkl_policy(qs[i], v, w, grid, 1.0, mean, lstd, 0.1, out=outp)), "k_grid_logterms + k_policy_reduce")
+           lambda: timeit(lambda i: eng.rkl_policy(qs[i], v, w, grid, 1.0, mean, lstd, 0.1, out=outp)), "k_grid_logterms + k_policy_reduce")
     # K2: hoisted T-mid evaluation with per-state actions (cfg3 critic at cfg4 size): actions in, q out
     S, H1, H2 = 17, 400, 300
     rng = np.random.RandomState(0)
@@ -76,9 +89,9 @@ def main():
                                                      rb.LAYOUT_IN_OUT)
     s = torch.randn(B, S, device=dev, generator=g)
     acts = [torch.rand(B, N, A, device=dev, generator=g) * 2 - 1 for _ in range(RING)]
-    sec = timeit(lambda i: cr.eval_into(s, acts[i], qs[i], "fp32"), 5)
-    report("K2 T-mid hoisted evaluation, per-state actions [4096,1024,6] (state term + rows)", B * N * (A + 1) * 4, sec,
-           "also %.1f TFLOP/s fp32 on 2(A+1)H2 flop/row: issue-bound, not HBM-bound" % (B * N * 2 * (A + 1) * H2 / sec / 1e12))
+    report("K2 T-mid hoisted evaluation, per-state actions [4096,1024,6] (state term + rows)", B * N * (A + 1) * 4,
+           lambda: timeit(lambda i: cr.eval_into(s, acts[i], qs[i], "fp32"), 5),
+           lambda sec: "also %.1f TFLOP/s fp32 on 2(A+1)H2 flop/row: issue-bound, not HBM-bound" % (B * N * 2 * (A + 1) * H2 / sec / 1e12))
     # K6: replay gather on a 4M-slot ring (S=17, A=6): 168 B per sampled transition in, the same out
     from rlcontrol_b200.replaybuffer import ReplayBuffer
     cap, nb = 1 << 22, 1 << 20
@@ -95,7 +108,7 @@ def main():
         check(eng.lib.rlc_replay_gather(eng.h, _ptr(st_), _ptr(ac_), _ptr(rw_), _ptr(s2_), _ptr(gm_), cap, S, A, _ptr(idxs[i % 4]), nb,
                                         *[_ptr(o) for o in outs], _stream()))
     row = (2 * S + A + 2) * 4
-    report("K6 rlc_replay_gather, 1M random transitions from a 4M-slot ring (S=17, A=6)", nb * (2 * row + 8), timeit(gather, 5),
+    report("K6 rlc_replay_gather, 1M random transitions from a 4M-slot ring (S=17, A=6)", nb * (2 * row + 8), lambda: timeit(gather, 5),
            "random 68/24/4-byte segments: sector-granular reads, so the DRAM traffic exceeds the algorithmic bytes")
 
 

@@ -1,10 +1,12 @@
 """gpurun_out/sb_TAG.ncu-rep (scripts/ncu_small_batch.sh) -> profiles/TAG_small_batch_ncu.md: one column per captured launch
-of the small-minibatch / device-loop kernels.  Usage: python scripts/summarise_sb_ncu.py TAG"""
+of the small-minibatch / device-loop kernels.  Usage: python scripts/summarise_sb_ncu.py TAG
+With a second argument "hbm": gpurun_out/hbm_TAG.ncu-rep (scripts/ncu_hbm_kernels.sh) -> profiles/TAG_hbm_kernels_ncu.md."""
 import csv, io, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
-rep = os.path.join(ROOT, "gpurun_out", f"sb_{tag}.ncu-rep")
+HBM = len(sys.argv) > 2 and sys.argv[2] == "hbm"
+rep = os.path.join(ROOT, "gpurun_out", f"{'hbm' if HBM else 'sb'}_{tag}.ncu-rep")
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, data = rows[0], rows[1], rows[2:]
@@ -28,6 +30,10 @@ for r in data:
     if key not in seen:
         seen.add(key)
         keep.append(r)
+if HBM:
+    KEYS.insert(12, "dram__throughput.avg.pct_of_peak_sustained_elapsed")
+    KEYS.insert(13, "lts__t_sector_hit_rate.pct")
+    KEYS.insert(14, "smsp__average_warp_latency_issue_stalled_lg_throttle.ratio")
 out = [f"# ncu --set full: small-minibatch fast path and device-loop glue kernels ({tag})\n",
        "Captured by `scripts/ncu_small_batch.sh` from `scripts/time_small_batch.py` (cfg1 shape: B=32, N=62, 200-200); "
        "one column per distinct (kernel, grid size). Durations under ncu are cold-cache and serialised: the warm device "
@@ -38,6 +44,13 @@ for k in KEYS:
     for i, h in enumerate(hdr):
         if h == k:
             out.append(f"| {h} | {units[i]} | " + " | ".join(r[i] for r in keep) + " |")
-dst = os.path.join(ROOT, "profiles", f"{tag}_small_batch_ncu.md")
+if HBM:
+    out[0] = f"# ncu --set full: memory-bound kernels K2 / K3 / K6 ({tag})\n"
+    out[1] = ("Captured by `scripts/ncu_hbm_kernels.sh` from `HBM_NCU=1 scripts/bench_hbm_kernels.py` (q[4096,1024], cfg4-size "
+              "T-mid stack, 1M-transition gather from a 4M-slot ring); one column per distinct (kernel, grid size). Durations "
+              "under ncu are cold-cache and serialised: the warm device times are in `" + tag + "_secondary.jsonl` / "
+              "`hbm_kernels_" + tag + ".jsonl` (CUDA events over graph replays). dram bytes = measured traffic per launch, "
+              "to set beside the algorithmic bytes of the bench lines.\n")
+dst = os.path.join(ROOT, "profiles", f"{tag}_{'hbm_kernels' if HBM else 'small_batch'}_ncu.md")
 open(dst, "w").write("\n".join(out) + "\n")
 print("wrote", dst, "kernels:", [r[kn].split("(")[0] for r in keep])
