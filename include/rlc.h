@@ -327,6 +327,20 @@ int rlc_replay_scatter(rlc_handle* h, float* state, float* action, float* reward
                        const int64_t* slot, int n, const float* s_in, const float* a_in,
                        const float* r_in, const float* s2_in, const float* g_in, void* stream);
 
+/* Record layout of the same ring (the HBM-first variant of row a17; ReplayBuffer(layout="record")): ONE array
+ * rec[cap, stride] of fixed-stride records [state S | action A | reward | next_state S | gamma | pad], with
+ * stride = rlc_replay_rec_stride(S, A) = 2S+A+2 rounded up to 16 floats, so every record starts on a 64-byte
+ * boundary and a random transition is a single contiguous read (utils/replaybuffer.py:25-37 stores one
+ * Transition tuple per entry: same grouping).  Arguments otherwise as rlc_replay_gather / rlc_replay_scatter;
+ * out-of-range slots are skipped.  rlc_replay_rec_stride is host-only and returns RLC_ERR_INVALID (< 0) on bad dims. */
+int rlc_replay_rec_stride(int S, int A);
+int rlc_replay_gather_rec(rlc_handle* h, const float* rec, int64_t cap, int stride, int S, int A,
+                          const int64_t* idx, int B, float* s_out, float* a_out, float* r_out,
+                          float* s2_out, float* g_out, void* stream);
+int rlc_replay_scatter_rec(rlc_handle* h, float* rec, int64_t cap, int stride, int S, int A,
+                           const int64_t* slot, int n, const float* s_in, const float* a_in,
+                           const float* r_in, const float* s2_in, const float* g_in, void* stream);
+
 /* Device-side minibatch index sampling: k distinct uniform indices in [0, n) from a
  * counter-based Philox stream keyed by (seed, counter) -- a pure function of its arguments, so a run is
  * reproducible, but NOT the numpy stream of RandomAccessQueue.sample_n_k (custom_collections.py:107-131; the

@@ -119,6 +119,9 @@ SIGNATURES = {
     "rlc_mixture_nll": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "rlc_svgd_action_grads": (_i, [_p, _cr, _p, _i, _p, _i, _p, _i, _f, _f, _p, _p, _p, _p, _p, _p]),
     "rlc_replay_gather": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p]),
+    "rlc_replay_rec_stride": (_i, [_i, _i]),
+    "rlc_replay_gather_rec": (_i, [_p, _p, _i64, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p]),
+    "rlc_replay_scatter_rec": (_i, [_p, _p, _i64, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p]),
     "rlc_replay_sample": (_i, [_p, _i64, _i, C.c_uint64, C.c_uint64, _i64, _i64, _p, _p, _p]),
     "rlc_replay_scatter": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p]),
     "rlc_env_reset": (_i, [_p, _en, _i, _p, _i64, _p, _p, _p, _p, _p, _p, _p]),

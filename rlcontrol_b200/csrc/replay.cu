@@ -155,6 +155,105 @@ extern "C" int rlc_replay_scatter(rlc_handle* h, float* state, float* action, fl
 }
 
 // ---------------------------------------------------------------------------------------------
+// Record layout (the HBM-first layout; ReplayBuffer(layout="record")): one ring of fixed-stride records
+// rec[cap, stride] = [state S | action A | reward | next_state S | gamma | pad], stride a multiple of 16 floats so a
+// record starts on a 64-byte boundary -- the DRAM access granularity.  A random transition then costs
+// ceil(4(2S+A+2)/64) 64-byte reads of ONE DRAM page instead of five partially used reads in five arrays (ncu on the
+// struct-of-arrays gather at S=17, A=6: 646 MB read per 1M transitions against 176 MB algorithmic; a 192-byte record
+// reads 192 MB).  Same CTA structure as k_replay_gather_flat, but field by field: the dense side of a field is
+// contiguous over the CTA's rows, so only the record address needs the (row, column) split.
+// ---------------------------------------------------------------------------------------------
+template <bool GATHER>
+__device__ __forceinline__ void rec_field(float* __restrict__ rec, int stride, const long long* sidx,
+                                          float* __restrict__ dense, int off, int W, unsigned magic, int nrow,
+                                          int tid) {
+  const unsigned total = (unsigned)(nrow * W);
+  for (unsigned base = tid; base < total; base += GATHER_THREADS * GATHER_UNROLL) {
+    float v[GATHER_UNROLL];
+    long long ra[GATHER_UNROLL];
+#pragma unroll
+    for (int u = 0; u < GATHER_UNROLL; ++u) {
+      const unsigned i = base + u * GATHER_THREADS;
+      ra[u] = -1;
+      if (i < total) {
+        const unsigned r = W == 1 ? i : __umulhi(i, magic);
+        const long long j = sidx[r];
+        if (j >= 0) {
+          ra[u] = j * stride + off + (int)(i - r * (unsigned)W);
+          v[u] = GATHER ? __ldg(rec + ra[u]) : __ldg(dense + i);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < GATHER_UNROLL; ++u) {
+      if (ra[u] >= 0) {
+        if (GATHER) dense[base + u * GATHER_THREADS] = v[u];
+        else rec[ra[u]] = v[u];
+      }
+    }
+  }
+}
+
+template <bool GATHER>
+__global__ void __launch_bounds__(GATHER_THREADS)
+k_replay_rec(float* __restrict__ rec, long long cap, int stride, int S, int A, const long long* __restrict__ idx,
+             int B, int gr, unsigned magicS, unsigned magicA, float* __restrict__ s, float* __restrict__ a,
+             float* __restrict__ r, float* __restrict__ s2, float* __restrict__ g) {
+  __shared__ long long sidx[GATHER_MAX_ROWS];
+  const int tid = threadIdx.x;
+  const long long row0 = (long long)blockIdx.x * gr;
+  const int nrow = (int)min((long long)gr, (long long)B - row0);
+  if (tid < nrow) {
+    const long long j = idx[row0 + tid];
+    sidx[tid] = (j < 0 || j >= cap) ? -1ll : j;   // out-of-range slots are skipped, never dereferenced
+  }
+  __syncthreads();
+  rec_field<GATHER>(rec, stride, sidx, s + row0 * S, 0, S, magicS, nrow, tid);
+  rec_field<GATHER>(rec, stride, sidx, a + row0 * A, S, A, magicA, nrow, tid);
+  rec_field<GATHER>(rec, stride, sidx, s2 + row0 * S, S + A + 1, S, magicS, nrow, tid);
+  if (tid < nrow && sidx[tid] >= 0) {             // the two scalars of a row: one thread per row
+    float* p = rec + sidx[tid] * stride;
+    if (GATHER) { r[row0 + tid] = __ldg(p + S + A); g[row0 + tid] = __ldg(p + 2 * S + A + 1); }
+    else { p[S + A] = r[row0 + tid]; p[2 * S + A + 1] = g[row0 + tid]; }
+  }
+}
+
+extern "C" int rlc_replay_rec_stride(int S, int A) {
+  if (S < 1 || A < 1 || S > 4000 || A > 4000) return RLC_ERR_INVALID;
+  return (2 * S + A + 2 + 15) / 16 * 16;
+}
+
+template <bool GATHER>
+static int replay_rec_launch(rlc_handle* h, float* rec, int64_t cap, int stride, int S, int A, const int64_t* idx,
+                             int B, float* s, float* a, float* r, float* s2, float* g, void* stream) {
+  RLC_REQUIRE(h && rec && idx && s && a && r && s2 && g && cap >= 1 && B >= 0);
+  RLC_REQUIRE(S >= 1 && A >= 1 && S <= 4000 && A <= 4000 && stride >= 2 * S + A + 2);
+  if (B == 0) return RLC_OK;
+  const int gr = B >= h->num_sms * 16 * GATHER_MAX_ROWS ? GATHER_MAX_ROWS : 8;
+  const unsigned magicS = S == 1 ? 0u : (unsigned)((1ULL << 32) / (unsigned)S) + 1u;
+  const unsigned magicA = A == 1 ? 0u : (unsigned)((1ULL << 32) / (unsigned)A) + 1u;
+  k_replay_rec<GATHER><<<(unsigned)((B + gr - 1) / gr), GATHER_THREADS, 0, (cudaStream_t)stream>>>(
+      rec, cap, stride, S, A, (const long long*)idx, B, gr, magicS, magicA, s, a, r, s2, g);
+  RLC_LAUNCH_CHECK(h);
+  return RLC_OK;
+}
+
+extern "C" int rlc_replay_gather_rec(rlc_handle* h, const float* rec, int64_t cap, int stride, int S, int A,
+                                     const int64_t* idx, int B, float* s_out, float* a_out, float* r_out,
+                                     float* s2_out, float* g_out, void* stream) {
+  return replay_rec_launch<true>(h, const_cast<float*>(rec), cap, stride, S, A, idx, B, s_out, a_out, r_out, s2_out,
+                                 g_out, stream);
+}
+
+extern "C" int rlc_replay_scatter_rec(rlc_handle* h, float* rec, int64_t cap, int stride, int S, int A,
+                                      const int64_t* slot, int n, const float* s_in, const float* a_in,
+                                      const float* r_in, const float* s2_in, const float* g_in, void* stream) {
+  return replay_rec_launch<false>(h, rec, cap, stride, S, A, slot, n, const_cast<float*>(s_in),
+                                  const_cast<float*>(a_in), const_cast<float*>(r_in), const_cast<float*>(s2_in),
+                                  const_cast<float*>(g_in), stream);
+}
+
+// ---------------------------------------------------------------------------------------------
 // N4: device-side minibatch index sampling -- k DISTINCT uniform indices in [0, n), written as ring
 // slots (head + i) % cap, with no host round trip (the host sampler RandomAccessQueue.sample_n_k,
 // custom_collections.py:107-131, stays the default because it reproduces the reference's stream).

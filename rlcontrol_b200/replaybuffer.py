@@ -3,8 +3,11 @@
 Mirrors ``utils/replaybuffer.py:14-42`` (``ReplayBuffer.add / get_size / sample_batch``) and the
 index sampler of ``utils/custom_collections.py:103-131`` (``RandomAccessQueue.sample_n_k`` on a
 ``np.random.RandomState(seed)``), so a run with the same seed draws the same minibatches.  The
-list-of-namedtuples storage is replaced by a struct-of-arrays ring in HBM; ``sample_batch`` is one
-gather kernel (``rlc_replay_gather``).  Logical FIFO index i <-> ring slot (head + i) % capacity."""
+list-of-namedtuples storage is replaced by a ring in HBM; ``sample_batch`` is one gather kernel.
+Logical FIFO index i <-> ring slot (head + i) % capacity.  Two layouts: ``"soa"`` (default; five arrays
+``state[cap,S] action[cap,A] reward[cap] next_state[cap,S] gamma[cap]``, ``rlc_replay_gather``) and
+``"record"`` (one array of 64-byte-aligned fixed-stride records, ``rlc_replay_gather_rec``: a random
+transition is one contiguous DRAM read instead of five; the one to use for large minibatches)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -18,7 +21,10 @@ from .engine import Engine, _ptr, _stream
 
 class ReplayBuffer(object):
     def __init__(self, buffer_size, random_seed, state_dim=None, action_dim=None, engine: Engine = None,
-                 flush_every: int = 256, sample_on_device: bool = False):
+                 flush_every: int = 256, sample_on_device: bool = False, layout: str = "soa"):
+        if layout not in ("soa", "record"):
+            raise ValueError("layout must be 'soa' or 'record'")
+        self.layout = layout
         # sample_on_device: draw the minibatch indices with rlc_replay_sample (Philox, no host round trip) instead of
         # the reference's numpy stream; falls back to the host sampler when 3k >= n or k > 4096
         self.sample_on_device = bool(sample_on_device)
@@ -39,9 +45,19 @@ class ReplayBuffer(object):
     def _alloc(self):
         dev, cap = self.eng.device, self.buffer_size
         z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
-        self.state, self.next_state = z(cap, self.S), z(cap, self.S)
-        self.action = z(cap, self.A)
-        self.reward, self.gamma = z(cap), z(cap)
+        if self.layout == "record":
+            S, A = self.S, self.A
+            self.stride = int(self.eng.lib.rlc_replay_rec_stride(S, A))
+            if self.stride < 0:
+                check(self.stride)
+            self.rec = z(cap, self.stride)
+            # field views of the records (inspection / checkpointing; the kernels take `rec`)
+            self.state, self.action, self.reward = self.rec[:, :S], self.rec[:, S:S + A], self.rec[:, S + A]
+            self.next_state, self.gamma = self.rec[:, S + A + 1:2 * S + A + 1], self.rec[:, 2 * S + A + 1]
+        else:
+            self.state, self.next_state = z(cap, self.S), z(cap, self.S)
+            self.action = z(cap, self.A)
+            self.reward, self.gamma = z(cap), z(cap)
         self._alloc_done = True
 
     # utils/replaybuffer.py:25-27
@@ -79,6 +95,11 @@ class ReplayBuffer(object):
         s2_in = h2d(np.stack([p[3] for p in pend]))
         g_in = h2d(np.array([p[4] for p in pend], np.float32))
         slot_t = h2d(slots)
+        if self.layout == "record":
+            check(self.eng.lib.rlc_replay_scatter_rec(self.eng.h, _ptr(self.rec), cap, self.stride, self.S, self.A,
+                                                      _ptr(slot_t), len(pend), _ptr(s_in), _ptr(a_in), _ptr(r_in),
+                                                      _ptr(s2_in), _ptr(g_in), _stream()))
+            return
         check(self.eng.lib.rlc_replay_scatter(self.eng.h, _ptr(self.state), _ptr(self.action), _ptr(self.reward),
                                               _ptr(self.next_state), _ptr(self.gamma), cap, self.S, self.A,
                                               _ptr(slot_t), len(pend), _ptr(s_in), _ptr(a_in), _ptr(r_in),
@@ -145,10 +166,15 @@ class ReplayBuffer(object):
             torch.from_numpy(np.ascontiguousarray(slots, dtype=np.int64)).to(dev)
         e = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
         s, a, r, s2, g = e(B, self.S), e(B, self.A), e(B), e(B, self.S), e(B)
-        check(self.eng.lib.rlc_replay_gather(self.eng.h, _ptr(self.state), _ptr(self.action), _ptr(self.reward),
-                                             _ptr(self.next_state), _ptr(self.gamma), self.buffer_size, self.S,
-                                             self.A, _ptr(slot_t), B, _ptr(s), _ptr(a), _ptr(r), _ptr(s2), _ptr(g),
-                                             _stream()))
+        if self.layout == "record":
+            check(self.eng.lib.rlc_replay_gather_rec(self.eng.h, _ptr(self.rec), self.buffer_size, self.stride, self.S,
+                                                     self.A, _ptr(slot_t), B, _ptr(s), _ptr(a), _ptr(r), _ptr(s2),
+                                                     _ptr(g), _stream()))
+        else:
+            check(self.eng.lib.rlc_replay_gather(self.eng.h, _ptr(self.state), _ptr(self.action), _ptr(self.reward),
+                                                 _ptr(self.next_state), _ptr(self.gamma), self.buffer_size, self.S,
+                                                 self.A, _ptr(slot_t), B, _ptr(s), _ptr(a), _ptr(r), _ptr(s2), _ptr(g),
+                                                 _stream()))
         out = (s, a, r, s2, g)
         if as_numpy:
             return tuple(t.cpu().numpy() for t in out)

@@ -110,6 +110,15 @@ def main():
     row = (2 * S + A + 2) * 4
     report("K6 rlc_replay_gather, 1M random transitions from a 4M-slot ring (S=17, A=6)", nb * (2 * row + 8), lambda: timeit(gather, 5),
            "random 68/24/4-byte segments: sector-granular reads, so the DRAM traffic exceeds the algorithmic bytes")
+    # the same gather from the record layout (one 64-byte-aligned 192-byte record per transition)
+    lib = eng.lib
+    stride = lib.rlc_replay_rec_stride(S, A)
+    rec = torch.randn(cap, stride, device=dev, generator=g)
+
+    def gather_rec(i):
+        check(lib.rlc_replay_gather_rec(eng.h, _ptr(rec), cap, stride, S, A, _ptr(idxs[i % 4]), nb, *[_ptr(o) for o in outs], _stream()))
+    report("K6 rlc_replay_gather_rec, same gather from 64-byte-aligned records (stride %d floats)" % stride, nb * (2 * row + 8),
+           lambda: timeit(gather_rec, 5), "one contiguous %d-byte DRAM read per transition" % (stride * 4))
 
 
 if __name__ == "__main__":

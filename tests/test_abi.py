@@ -90,8 +90,9 @@ def test_invalid_arguments_return_status_not_crash():
 
 def test_gather_reciprocal_is_exact():
     """csrc/replay.cu k_replay_gather_flat maps output float i -> sampled row i // E with __umulhi(i, 2^32 // E + 1);
-    the launcher takes that kernel only for E = 2S+A+2 <= 8192 and at most 32 rows per CTA.  Every (E, i) it can see:"""
-    for E in range(5, 8193):
+    the launcher takes that kernel only for E = 2S+A+2 <= 8192 and at most 32 rows per CTA (the record-layout kernels
+    use the same split per field, widths S, A <= 4000).  Every (E, i) it can see:"""
+    for E in range(2, 8193):
         magic = np.uint64((1 << 32) // E + 1)
         i = np.arange(0, 32 * E, dtype=np.uint64)
         assert np.array_equal((i * magic) >> np.uint64(32), i // np.uint64(E)), E
