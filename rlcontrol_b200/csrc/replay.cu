@@ -122,8 +122,7 @@ extern "C" int rlc_replay_gather(rlc_handle* h, const float* state, const float*
   if (B == 0) return RLC_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const long long E = 2LL * S + A + 2;
-  static const bool warp_rows = getenv("RLC_GATHER_WARP") != nullptr;   // A/B switch for the older kernel
-  if (warp_rows || E > 8192) {   // reciprocal checked exhaustively for E <= 8192 (tests/test_abi.py)
+  if (E > 8192) {   // reciprocal checked exhaustively for E <= 8192 (tests/test_abi.py)
     k_replay_gather<<<(unsigned)(((long long)B * 32 + 255) / 256), 256, 0, st>>>(
         state, action, reward, next_state, gamma, cap, S, A, (const long long*)idx, B, s_out, a_out,
         r_out, s2_out, g_out);
