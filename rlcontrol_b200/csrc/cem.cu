@@ -394,7 +394,9 @@ extern "C" int rlc_cem(rlc_handle* h, const rlc_critic* c, const float* s, int B
   }
   if (c->A <= 1) RLC_CEM_CASE(1)
   else if (c->A <= 2) RLC_CEM_CASE(2)
+  else if (c->A <= 3) RLC_CEM_CASE(3)
   else if (c->A <= 4) RLC_CEM_CASE(4)
+  else if (c->A <= 6) RLC_CEM_CASE(6)
   else RLC_CEM_CASE(8)
 #undef RLC_CEM_CASE
   RLC_LAUNCH_CHECK(h);

@@ -6,18 +6,17 @@
 #include "rows_gemm.cuh"
 
 // =============================================================================================
-// Fused two-layer kernel: 32 rows per CTA (small batches still spread over many SMs), layer-1
+// Fused two-layer kernel: TM = 32 (or 8, for few rows) rows per CTA, layer-1
 // activations kept in shared memory, W2 streamed through a double-buffered shared-memory ring in
 // 16-row chunks (register-staged: the loads of chunk c+1 are in flight while chunk c is consumed),
-// layer 2 register-tiled: a warp owns 4 rows (activation reads are warp-wide broadcasts, float4
+// layer 2 register-tiled: a warp owns TM/8 rows (activation reads are warp-wide broadcasts, float4
 // along k) and a lane owns the columns lane, lane+32, ... (conflict-free W2 reads).
 // Epilogue = w3 dot (T-in q) or store p (T-mid state term).
 // =============================================================================================
 enum { MODE_TIN_Q = 0, MODE_TMID_P = 1 };
-#define MLP2_TM 32
 #define MLP2_KC 16
 
-template <int NJ, int MODE>
+template <int NJ, int MODE, int TM>
 __global__ void __launch_bounds__(256)
 k_mlp2_rows(const float* __restrict__ s, const float* __restrict__ a, int act_per_state,
             long long R, int N, int S, int A, int H1, int H2, const float* __restrict__ W1,
@@ -32,10 +31,11 @@ k_mlp2_rows(const float* __restrict__ s, const float* __restrict__ a, int act_pe
   const int nchunks = (H1 + MLP2_KC - 1) / MLP2_KC;
   const int H1P = nchunks * MLP2_KC;
   float* xs = sm;                        // [TM][K1P]
-  float* h1s = xs + MLP2_TM * K1P;       // [TM][H1P]   (columns >= H1 are zero)
-  float* w2s = h1s + MLP2_TM * H1P;      // [2][KC][H2S]
-  const long long r0 = (long long)blockIdx.x * MLP2_TM;
+  float* h1s = xs + TM * K1P;       // [TM][H1P]   (columns >= H1 are zero)
+  float* w2s = h1s + TM * H1P;      // [2][KC][H2S]
+  const long long r0 = (long long)blockIdx.x * TM;
   const int tid = threadIdx.x, lane = tid & 31, rg = tid >> 5;
+  constexpr int RW = TM / 8;             // rows per warp
 
   // first W2 chunk: issue the loads before the layer-1 work so their latency is hidden behind it
   constexpr int NST = NJ * MLP2_KC / 8;  // chunk elements per thread
@@ -46,7 +46,7 @@ k_mlp2_rows(const float* __restrict__ s, const float* __restrict__ a, int act_pe
     stg[t] = (kr < H1 && col < H2) ? __ldg(W2 + (long long)kr * H2 + col) : 0.f;
   }
 
-  for (int i = tid; i < MLP2_TM * K1; i += 256) {
+  for (int i = tid; i < TM * K1; i += 256) {
     const int r = i / K1, k = i - r * K1;
     const long long row = r0 + r;
     float v = 0.f;
@@ -69,7 +69,7 @@ k_mlp2_rows(const float* __restrict__ s, const float* __restrict__ a, int act_pe
   }
   __syncthreads();
 
-  for (int i = tid; i < MLP2_TM * H1P; i += 256) {
+  for (int i = tid; i < TM * H1P; i += 256) {
     const int r = i / H1P, j = i - r * H1P;
     float v = 0.f;
     if (j < H1) {
@@ -84,12 +84,12 @@ k_mlp2_rows(const float* __restrict__ s, const float* __restrict__ a, int act_pe
   for (int t = 0; t < NST; ++t) w2s[tid + 256 * t] = stg[t];
   __syncthreads();
 
-  float acc[4][NJ];
+  float acc[RW][NJ];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < RW; ++i)
 #pragma unroll
     for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
-  const float* hrow = h1s + (rg * 4) * H1P;
+  const float* hrow = h1s + (rg * RW) * H1P;
   for (int c = 0; c < nchunks; ++c) {
     const bool more = c + 1 < nchunks;
     if (more) {
@@ -103,9 +103,9 @@ k_mlp2_rows(const float* __restrict__ s, const float* __restrict__ a, int act_pe
     const float* wb = w2s + (c & 1) * (MLP2_KC * H2S) + lane;
 #pragma unroll
     for (int kk = 0; kk < MLP2_KC; kk += 4) {
-      float4 hv[4];
+      float4 hv[RW];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RW; ++i)
         hv[i] = *reinterpret_cast<const float4*>(hrow + i * H1P + c * MLP2_KC + kk);
 #pragma unroll
       for (int k4 = 0; k4 < 4; ++k4) {
@@ -113,7 +113,7 @@ k_mlp2_rows(const float* __restrict__ s, const float* __restrict__ a, int act_pe
         for (int j = 0; j < NJ; ++j) {
           const float w = wb[(kk + k4) * H2S + 32 * j];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < RW; ++i) {
             const float hval = k4 == 0 ? hv[i].x : k4 == 1 ? hv[i].y : k4 == 2 ? hv[i].z : hv[i].w;
             acc[i][j] = fmaf(hval, w, acc[i][j]);
           }
@@ -129,23 +129,25 @@ k_mlp2_rows(const float* __restrict__ s, const float* __restrict__ a, int act_pe
   }
 
   if (MODE == MODE_TIN_Q) {
-    float qs[4] = {0.f, 0.f, 0.f, 0.f};
+    float qs[RW];
+#pragma unroll
+    for (int i = 0; i < RW; ++i) qs[i] = 0.f;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int col = lane + 32 * j;
       if (col < H2) {
         const float bb = __ldg(b2 + col), ww = __ldg(w3 + col);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) qs[i] = fmaf(ww, fmaxf(acc[i][j] + bb, 0.f), qs[i]);
+        for (int i = 0; i < RW; ++i) qs[i] = fmaf(ww, fmaxf(acc[i][j] + bb, 0.f), qs[i]);
       }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) qs[i] = warp_sum(qs[i]);
+    for (int i = 0; i < RW; ++i) qs[i] = warp_sum(qs[i]);
     if (lane == 0) {
       const float bb3 = __ldg(b3);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const long long row = r0 + rg * 4 + i;
+      for (int i = 0; i < RW; ++i) {
+        const long long row = r0 + rg * RW + i;
         if (row < R) out[row] = qs[i] + bb3;
       }
     }
@@ -156,8 +158,8 @@ k_mlp2_rows(const float* __restrict__ s, const float* __restrict__ a, int act_pe
       if (col < H2) {
         const float bb = __ldg(b2 + col);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const long long row = r0 + rg * 4 + i;
+        for (int i = 0; i < RW; ++i) {
+          const long long row = r0 + rg * RW + i;
           if (row < R) out[row * H2 + col] = acc[i][j] + bb;
         }
       }
@@ -177,17 +179,25 @@ static int launch_mlp2(rlc_handle* h, const float* s, const float* a, int act_pe
   const int H1P = (H1 + MLP2_KC - 1) / MLP2_KC * MLP2_KC;
   const int NJ = H2 <= 64 ? 2 : H2 <= 128 ? 4 : H2 <= 224 ? 7 : H2 <= 320 ? 10 : 16;
   if (H2 > 512) return RLC_ERR_UNSUPPORTED;
+  // few rows (a CEM call's B = 256 state terms, a small grid evaluation): 8 rows per CTA (one per warp) instead of 32, so
+  // the launch covers 4x as many SMs and a CTA's serial layer-1 + W2-streaming chain is 4x shorter; same k order, so the
+  // results are bit-identical
+  const int TMv = R <= 16LL * h->num_sms ? 8 : 32;
   const size_t smem =
-      (size_t)(MLP2_TM * K1P + MLP2_TM * H1P + 2 * MLP2_KC * NJ * 32) * sizeof(float);
+      (size_t)(TMv * K1P + TMv * H1P + 2 * MLP2_KC * NJ * 32) * sizeof(float);
   if (smem > h->smem_optin) return RLC_ERR_UNSUPPORTED;
-  const long long blocks = (R + MLP2_TM - 1) / MLP2_TM;
+  const long long blocks = (R + TMv - 1) / TMv;
   if (blocks > 0x7fffffffLL) return RLC_ERR_INVALID;
-#define RLC_MLP2_CASE(NJV)                                                                       \
+#define RLC_MLP2_LAUNCH(NJV, TMV)                                                                \
   {                                                                                              \
-    auto kern = k_mlp2_rows<NJV, MODE>;                                                          \
+    auto kern = k_mlp2_rows<NJV, MODE, TMV>;                                                     \
     RLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<(unsigned)blocks, 256, smem, st>>>(s, a, act_per_state, R, N, S, A, H1, H2, W1, b1,   \
                                               W2, b2, w3, b3, smin, smax, out);                  \
+  }
+#define RLC_MLP2_CASE(NJV)                                                                       \
+  {                                                                                              \
+    if (TMv == 8) RLC_MLP2_LAUNCH(NJV, 8) else RLC_MLP2_LAUNCH(NJV, 32)                          \
   }
   if (NJ == 2) RLC_MLP2_CASE(2)
   else if (NJ == 4) RLC_MLP2_CASE(4)
@@ -195,6 +205,7 @@ static int launch_mlp2(rlc_handle* h, const float* s, const float* a, int act_pe
   else if (NJ == 10) RLC_MLP2_CASE(10)
   else RLC_MLP2_CASE(16)
 #undef RLC_MLP2_CASE
+#undef RLC_MLP2_LAUNCH
   RLC_LAUNCH_CHECK(h);
   return RLC_OK;
 }
