@@ -210,10 +210,87 @@ static int launch_mlp2(rlc_handle* h, const float* s, const float* a, int act_pe
   return RLC_OK;
 }
 
+// T-mid state term for FEW rows (a CEM call's B = 256, an Actor-Expert minibatch): the launch is a latency chain, not
+// a throughput problem -- k_mlp2_rows walks W2 in 25 dependent 16-row chunks per CTA.  Here a CTA owns 8 rows x 32
+// output columns, so its whole W2 slice (H1 x 32 floats) fits in shared memory and is fetched by ONE wave of cp.async
+// that flies under the layer-1 work; a warp is a row, a lane a column.  grid = ceil(R/8) x ceil(H2/32) CTAs (320 at
+// B=256, H2=300 instead of 32).  Same operation order as k_mlp2_rows (k ascending, bias last): bit-identical results.
+#define STC_ROWS 8
+__global__ void __launch_bounds__(256)
+k_state_term_cols(const float* __restrict__ s, int R, int S, int H1, int H2, const float* __restrict__ W1,
+                  const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ b2,
+                  const float* __restrict__ smin, const float* __restrict__ smax, float* __restrict__ out) {
+  extern __shared__ __align__(16) float sm[];
+  const int K1P = (S + 3) & ~3, H1P = (H1 + 3) & ~3;
+  float* xs = sm;                          // [8][K1P]
+  float* h1s = xs + STC_ROWS * K1P;        // [8][H1P]  (columns >= H1 are zero)
+  float* w2s = h1s + STC_ROWS * H1P;       // [H1][32]
+  const int tid = threadIdx.x, lane = tid & 31, wr = tid >> 5;
+  const int r0 = blockIdx.x * STC_ROWS, col0 = blockIdx.y * 32;
+  // the CTA's W2 slice, straight into shared memory (4-byte cp.async: the slice rows are not 16-byte aligned in general)
+  for (int e = tid; e < H1 * 32; e += 256) {
+    const int k = e >> 5, col = col0 + (e & 31);
+    if (col < H2) {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(w2s + e);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(W2 + (long long)k * H2 + col) : "memory");
+    } else {
+      w2s[e] = 0.f;
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = tid; i < STC_ROWS * S; i += 256) {
+    const int r = i / S, k = i - r * S;
+    float v = 0.f;
+    if (r0 + r < R) {
+      v = s[(long long)(r0 + r) * S + k];
+      if (smin) v = fminf(fmaxf(v, smin[k]), smax[k]);
+    }
+    xs[r * K1P + k] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < STC_ROWS * H1P; i += 256) {
+    const int r = i / H1P, j = i - r * H1P;
+    float v = 0.f;
+    if (j < H1) {
+      float acc = b1[j];
+      const float* xr = xs + r * K1P;
+      for (int k = 0; k < S; ++k) acc = fmaf(xr[k], __ldg(W1 + (long long)k * H1 + j), acc);
+      v = fmaxf(acc, 0.f);
+    }
+    h1s[i] = v;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const float* hrow = h1s + wr * H1P;
+  const float* wb = w2s + lane;
+  float acc = 0.f;
+  for (int k = 0; k < H1P; k += 4) {
+    const float4 hv = *reinterpret_cast<const float4*>(hrow + k);
+    acc = fmaf(hv.x, wb[(k + 0) * 32], acc);
+    if (k + 1 < H1) acc = fmaf(hv.y, wb[(k + 1) * 32], acc);
+    if (k + 2 < H1) acc = fmaf(hv.z, wb[(k + 2) * 32], acc);
+    if (k + 3 < H1) acc = fmaf(hv.w, wb[(k + 3) * 32], acc);
+  }
+  const int row = r0 + wr, col = col0 + lane;
+  if (row < R && col < H2) out[(long long)row * H2 + col] = acc + __ldg(b2 + col);
+}
+
 int rlc_tmid_state_term(rlc_handle* h, const rlc_critic* c, const float* s, int B, float* p_out,
                         cudaStream_t st) {
   const ThetaView t = theta_view(RLC_TMID, c->S, c->A, c->H1, c->H2);
   const float* th = c->theta;
+  {
+    const int K1P = (c->S + 3) & ~3, H1P = (c->H1 + 3) & ~3;
+    const size_t smem = (size_t)(STC_ROWS * K1P + STC_ROWS * H1P + c->H1 * 32) * sizeof(float);
+    if (B > 0 && B <= 16 * h->num_sms && smem <= h->smem_optin) {
+      RLC_CUDA(cudaFuncSetAttribute(k_state_term_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const dim3 grid((unsigned)((B + STC_ROWS - 1) / STC_ROWS), (unsigned)((c->H2 + 31) / 32));
+      k_state_term_cols<<<grid, 256, smem, st>>>(s, B, c->S, c->H1, c->H2, th + t.oW1, th + t.ob1, th + t.oW2,
+                                                 th + t.ob2, c->smin, c->smax, p_out);
+      RLC_LAUNCH_CHECK(h);
+      return RLC_OK;
+    }
+  }
   return launch_mlp2<MODE_TMID_P>(h, s, nullptr, 0, B, 1, c->S, c->A, c->H1, c->H2, th + t.oW1,
                                   th + t.ob1, th + t.oW2, th + t.ob2, th + t.ow3, th + t.ob3,
                                   c->smin, c->smax, p_out, st);

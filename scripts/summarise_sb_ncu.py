@@ -5,8 +5,9 @@ import csv, io, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
-HBM = len(sys.argv) > 2 and sys.argv[2] == "hbm"
-rep = os.path.join(ROOT, "gpurun_out", f"{'hbm' if HBM else 'sb'}_{tag}.ncu-rep")
+KIND = sys.argv[2] if len(sys.argv) > 2 else "sb"          # sb | hbm | cem
+HBM = KIND in ("hbm", "cem")
+rep = os.path.join(ROOT, "gpurun_out", f"{KIND}_{tag}.ncu-rep")
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, data = rows[0], rows[1], rows[2:]
@@ -51,6 +52,11 @@ if HBM:
               "under ncu are cold-cache and serialised: the warm device times are in `" + tag + "_secondary.jsonl` / "
               "`hbm_kernels_" + tag + ".jsonl` (CUDA events over graph replays). dram bytes = measured traffic per launch, "
               "to set beside the algorithmic bytes of the bench lines.\n")
-dst = os.path.join(ROOT, "profiles", f"{tag}_{'hbm_kernels' if HBM else 'small_batch'}_ncu.md")
+if KIND == "cem":
+    out[0] = f"# ncu --set full: cfg3 QT-Opt CEM predict_action ({tag})\n"
+    out[1] = ("Captured by `scripts/ncu_cem.sh` (B=256, N=1024, 3 iterations, 2 mixture components, 400-300 T-mid critic): the "
+              "state-term kernel (`k_mlp2_rows`, T-mid mode, 8 rows per CTA) and the one-CTA-per-state CEM kernel. Both are "
+              "latency-bound (256 / 32 CTAs on 148 SMs); warm device times are in `scripts/time_cem_parts.py`'s output, DESIGN K4.\n")
+dst = os.path.join(ROOT, "profiles", f"{tag}_{ {'hbm': 'hbm_kernels', 'cem': 'cem', 'sb': 'small_batch'}[KIND] }_ncu.md")
 open(dst, "w").write("\n".join(out) + "\n")
 print("wrote", dst, "kernels:", [r[kn].split("(")[0] for r in keep])

@@ -29,6 +29,12 @@ def dev_time(fn, reps=20):
     st.synchronize()
     return e0.elapsed_time(e1) / (reps * 5) * 1e3
 amin, amax = t(-np.ones(A, np.float32)), t(np.ones(A, np.float32))
+if os.environ.get("CEM_ONCE") == "1":          # under ncu (scripts/ncu_cem.sh): two eager cfg3 calls, nothing else
+    noise = t(rng.randn(2, B, N, A).astype(np.float32)); cu = t(rng.uniform(size=(2, B, N)).astype(np.float32))
+    for _ in range(2):
+        cr.cem(sd, u0, noise, cu, top_m, 2, -np.ones(A), np.ones(A))
+    torch.cuda.synchronize()
+    sys.exit(0)
 for iters in (1, 2, 3):
     noise = t(rng.randn(iters - 1, B, N, A).astype(np.float32)) if iters > 1 else None
     cu = t(rng.uniform(size=(iters - 1, B, N)).astype(np.float32)) if iters > 1 else None
