@@ -192,7 +192,7 @@ def run_reference(args, rank, world):
                              "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -581,10 +581,19 @@ def run_b200(args, rank, local_rank, world):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_arm(params, s_np, a_np, w_np, (mean_np, lstd_np), alpha)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+_LINE_OUT = [None]     # the process's original stdout (set in main)
+
+
+def emit(line: dict):
+    out = _LINE_OUT[0] or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -600,6 +609,11 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    # stdout carries exactly ONE line (the JSON): libraries that write to file descriptor 1 themselves (NCCL prints its
+    # version banner there when NCCL_DEBUG is set) are sent to stderr; the JSON line goes to the saved descriptor
+    sys.stdout.flush()
+    _LINE_OUT[0] = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
