@@ -54,7 +54,10 @@ extern "C" {
 #define RLC_PREC_FP32 0 /* CUDA-core fp32 FMA, fp32 accumulate (bit-comparable to the CPU path ~1e-6) */
 #define RLC_PREC_FP16 1 /* tcgen05.mma kind::f16, fp16 operands, fp32 accumulate in TMEM (default for large B*N) */
 #define RLC_PREC_BF16 2 /* tcgen05.mma kind::f16, bf16 operands, fp32 accumulate in TMEM */
-#define RLC_PREC_AUTO 3 /* FP16 tensor path when B*N >= 16384 rows and the shape is supported, else FP32 */
+#define RLC_PREC_AUTO 3 /* parity-preserving choice: FP16X3 for shared-grid T-in evaluations of >= 16384 rows, else FP32 */
+#define RLC_PREC_FP16X3 4 /* strict tensor mode (shared grids): both operands split into fp16 hi+lo, three tcgen05.mma per
+                             K step into one fp32 TMEM accumulator (h_hi.W_hi + h_lo.W_hi + h_hi.W_lo): 22-bit operands,
+                             ~1e-5 of the exact Q (fp32-class parity with forwardkl_network.py:263-268) at 3x the MMA work */
 
 /* Adam flavour of rlc_adam_step */
 #define RLC_ADAM_TORCH 0 /* torch.optim.Adam: p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps) */
@@ -128,6 +131,11 @@ int rlc_umma_last_error(rlc_handle* h, void* stream);
  * r() = rounding to the operand type (fp16/bf16); accumulation is fp32.  Env knobs (debug):
  * RLC_UMMA_MODE=ss selects 0; RLC_UMMA_GRID=0 disables 3. */
 int rlc_umma_mode(const rlc_critic* c, int act_mode);
+/* Same for an explicit precision; adds
+ *   4  "grid3"  RLC_PREC_FP16X3, shared grids: h = fl32(PS[b] + PA[n]) from fp32 tables, relu, h = h_hi + h_lo (fp16 each);
+ *               W' = fl32(2^k |w3_j| W2[:,j]) = W_hi + W_lo (fp16 each, 2^k also normalises max|W2| to [2^8,2^9));
+ *               z = h_hi.W_hi + h_lo.W_hi + h_hi.W_lo, then the folded head. */
+int rlc_umma_mode_prec(const rlc_critic* c, int act_mode, int precision);
 
 /* ---- per-state reductions (rows a3, a4, a8, a9, a10) ------------------------------------ */
 /* row.argsort()[::-1][:k] (ActorExpert.py:177, qt_opt_network.py:166): descending, ties -> larger

@@ -101,6 +101,12 @@ def tin_eval_rounded(s, a, params, kind="fp16", head="ss"):
                       are formed in fp32 and rounded to ``kind``, their sum is rounded once more
                       (one packed fma) -- followed by the folded head.
 
+    ``head="grid3"``  the strict split mode (RLC_PREC_FP16X3, shared grids, ``kind`` is ignored: fp16):
+                      h = relu(fl32(PS_b + PA_n)) with fp32 tables (same fp32 FMA chains), h = h_hi + h_lo with
+                      h_hi = r(h), h_lo = r(h - h_hi); W' = fl32(2^k |w3_j| W2[j,:]) = W_hi + W_lo likewise, 2^k the
+                      head-folding scale times 2^e2 with 2^e2 max(|W2|,|b2|) in [2^8, 2^9);
+                      z = h_hi.W_hi + h_lo.W_hi + h_hi.W_lo (the bias rides on an always-one feature), folded head.
+
     The CUDA kernel must match THIS to ~1e-5 rms (it does exactly this arithmetic with fp32
     accumulators); the distance from ``tin_eval(..., float64)`` is the cost of the operand type."""
     W1, b1, W2, b2, W3, b3 = [np.asarray(p, np.float64) for p in params]
@@ -110,6 +116,8 @@ def tin_eval_rounded(s, a, params, kind="fp16", head="ss"):
     N = a.shape[0] if a.ndim == 2 else a.shape[1]
     x = np.concatenate([stack_state_major(s, N), stack_actions(a, B)], axis=1)
     r = lambda z: round_operand(z, kind)
+    if head == "grid3":
+        return _tin_eval_grid3(s, a, params)
     if head == "grid":
         if a.ndim != 2:
             raise ValueError("head='grid' is the shared-grid arithmetic")
@@ -148,6 +156,47 @@ def tin_eval_rounded(s, a, params, kind="fp16", head="ss"):
         q = (z @ sign) / np.float64(scale) + b3.reshape(())
     else:
         raise ValueError(head)
+    return q.reshape(B, N)
+
+
+def _tin_eval_grid3(s, a, params):
+    """Stated arithmetic of the split tensor mode (csrc/critic_umma_grid3.cuh), fp64 accumulate."""
+    if np.asarray(a).ndim != 2:
+        raise ValueError("head='grid3' is a shared-grid arithmetic")
+    f32, f64 = np.float32, np.float64
+    W1, b1, W2, b2, W3, b3 = [np.asarray(p, f32) for p in params]
+    s = np.asarray(s, f32)
+    a = np.asarray(a, f32)
+    B, N, S = s.shape[0], a.shape[0], s.shape[1]
+    r16 = lambda z: round_operand(z, "fp16")
+
+    def fma_chain(xs, Wt, init):
+        acc = np.broadcast_to(np.asarray(init, f32), (xs.shape[0], Wt.shape[1])).astype(f32)
+        for k in range(xs.shape[1]):
+            acc = (acc.astype(f64) + xs[:, k:k + 1].astype(f64) * Wt[k].astype(f64)).astype(f32)
+        return acc
+
+    ps = fma_chain(s, W1[:, :S].T.copy(), b1)                        # [B,H1] fp32
+    pa = fma_chain(a, W1[:, S:].T.copy(), f32(0))                    # [N,H1] fp32
+    h = np.maximum((ps[:, None, :] + pa[None, :, :]).astype(f32), f32(0)).reshape(B * N, -1)   # one fp32 add
+    h_hi = r16(h)
+    h_lo = r16((h.astype(f64) - h_hi).astype(f32))                   # exact difference
+    w3 = W3.reshape(-1)
+    mx = f32(np.abs(w3).max())
+    scale = f32(1.0)
+    if mx > 0 and np.isfinite(mx):
+        scale = f32(np.ldexp(1.0, 1 - int(np.frexp(mx)[1])))
+    mx2 = f32(max(np.abs(W2).max(), np.abs(b2).max()))
+    if mx2 > 0 and np.isfinite(mx2):
+        scale = f32(scale * f32(np.ldexp(1.0, 9 - int(np.frexp(mx2)[1]))))
+    sw = (scale * np.abs(w3)).astype(f32)                            # exact (power of two)
+    Wp = np.clip((sw[:, None] * W2).astype(f32), -65504, 65504)      # [H2,H1], one fp32 rounding
+    bp = np.clip((sw * b2.reshape(-1)).astype(f32), -65504, 65504)
+    W_hi, b_hi = r16(Wp), r16(bp)
+    W_lo, b_lo = r16((Wp.astype(f64) - W_hi).astype(f32)), r16((bp.astype(f64) - b_hi).astype(f32))
+    z = h_hi @ W_hi.T + h_lo @ W_hi.T + h_hi @ W_lo.T + (b_hi + b_lo)
+    sign = np.where(w3 < 0, -1.0, 1.0)
+    q = (np.maximum(z, 0) @ sign) / f64(scale) + f64(b3.reshape(()))
     return q.reshape(B, N)
 
 

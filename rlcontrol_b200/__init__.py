@@ -7,7 +7,7 @@ ReverseKLNetwork), ``replaybuffer`` and ``quadrature``.
 There is no CPU fallback: importing works anywhere, using it needs the built library and a GPU."""
 from . import _lib  # noqa: F401
 from ._lib import (ACT_PER_STATE, ACT_SHARED, ADAM_TF, ADAM_TORCH, LAYOUT_IN_OUT, LAYOUT_OUT_IN,  # noqa: F401
-                   PREC_AUTO, PREC_BF16, PREC_FP16, PREC_FP32, TIN, TMID, RlcError)
+                   PREC_AUTO, PREC_BF16, PREC_FP16, PREC_FP16X3, PREC_FP32, TIN, TMID, RlcError)
 
 __all__ = ["Engine", "Critic", "CriticOptimizer", "Mlp"]
 

@@ -11,10 +11,10 @@ LIB_PATH = os.environ.get("RLC_LIB_PATH") or os.path.join(_HERE, "librlc.so")   
 TIN, TMID = 0, 1
 LAYOUT_OUT_IN, LAYOUT_IN_OUT = 0, 1
 ACT_SHARED, ACT_PER_STATE = 0, 1
-PREC_FP32, PREC_FP16, PREC_BF16, PREC_AUTO = 0, 1, 2, 3
+PREC_FP32, PREC_FP16, PREC_BF16, PREC_AUTO, PREC_FP16X3 = 0, 1, 2, 3, 4
 ADAM_TORCH, ADAM_TF = 0, 1
 
-PREC_BY_NAME = {"fp32": PREC_FP32, "fp16": PREC_FP16, "bf16": PREC_BF16, "auto": PREC_AUTO}
+PREC_BY_NAME = {"fp32": PREC_FP32, "fp16": PREC_FP16, "bf16": PREC_BF16, "auto": PREC_AUTO, "fp16x3": PREC_FP16X3}
 
 
 class RlcCritic(C.Structure):
@@ -91,6 +91,7 @@ SIGNATURES = {
     "rlc_tmid_eval_grad": (_i, [_p, _cr, _p, _i, _p, _i, _i, _p, _p, _p]),
     "rlc_umma_last_error": (_i, [_p, _p]),
     "rlc_umma_mode": (_i, [_cr, _i]),
+    "rlc_umma_mode_prec": (_i, [_cr, _i, _i]),
     "rlc_reduce_topk": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p]),
     "rlc_reduce_stats": (_i, [_p, _p, _i, _i, _p, _p, _p, _p]),
     "rlc_reduce_lse": (_i, [_p, _p, _i, _i, _i, _p, _p]),

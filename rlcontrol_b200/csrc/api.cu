@@ -54,19 +54,35 @@ extern "C" int rlc_destroy(rlc_handle* h) {
   if (h->err_flag) cudaFree(h->err_flag);
   for (int i = 0; i < RLC_MAX_PACKS; ++i)
     if (h->packs[i].dev) cudaFree(h->packs[i].dev);
+  for (int i = 0; i < h->n_retired; ++i) cudaFree(h->retired[i]);
   delete h;
   return RLC_OK;
 }
 
 extern "C" int64_t rlc_launch_count(const rlc_handle* h) { return h ? h->launches : 0; }
 
+int rlc_retire_block(rlc_handle* h, void* old_block) {
+  if (!old_block) return RLC_OK;
+  if (h->n_retired < RLC_MAX_RETIRED) {
+    h->retired[h->n_retired++] = old_block;
+    return RLC_OK;
+  }
+  RLC_CUDA(cudaDeviceSynchronize());     // list full: nothing older than 64 growths is expected to be replayed
+  cudaFree(old_block);
+  return RLC_OK;
+}
+
+// Scratch of at least `bytes`.  Grow-only and geometric (>= 1.5x), so a handle retires a handful of blocks at most.
+// The outgrown block stays allocated: captured graphs (kl_networks, steps, device_loop) that ran on this handle before
+// the growth keep their baked-in pointer valid; eager calls move on to the new block.
 int rlc_workspace(rlc_handle* h, size_t bytes, void** out) {
   if (bytes > h->ws_bytes) {
-    RLC_CUDA(cudaDeviceSynchronize());
-    if (h->ws) cudaFree(h->ws);
+    const int rc = rlc_retire_block(h, h->ws);
+    if (rc) return rc;
     h->ws = nullptr;
-    h->ws_bytes = 0;
     size_t want = bytes + (bytes >> 2) + 4096;
+    if (want < h->ws_bytes + (h->ws_bytes >> 1)) want = h->ws_bytes + (h->ws_bytes >> 1);
+    h->ws_bytes = 0;
     cudaError_t e = cudaMalloc(&h->ws, want);
     if (e != cudaSuccess) {
       (void)cudaGetLastError();
@@ -102,18 +118,23 @@ extern "C" int rlc_critic_eval(rlc_handle* h, const rlc_critic* c, const float* 
                                void* stream) {
   RLC_REQUIRE(h && critic_ok(c) && s && a && q_out && B >= 0 && N >= 0);
   RLC_REQUIRE(act_mode == RLC_ACT_SHARED || act_mode == RLC_ACT_PER_STATE);
-  RLC_REQUIRE(precision >= RLC_PREC_FP32 && precision <= RLC_PREC_AUTO);
+  RLC_REQUIRE(precision >= RLC_PREC_FP32 && precision <= RLC_PREC_FP16X3);
   if ((long long)B * N == 0) return RLC_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == RLC_PREC_AUTO) {
-    precision = (c->topology == RLC_TIN && (long long)B * N >= 16384 && rlc_umma_supported(h, c, B, N))
-                    ? RLC_PREC_FP16
+    // AUTO never trades parity for speed: the split tensor mode (fp32-class, 1e-5 of the exact Q) where it applies
+    // (large shared-grid T-in evaluations), the fp32 CUDA-core path everywhere else.  The single-rounding fp16/bf16
+    // modes (5e-3 max error) are only used when asked for by name.
+    precision = (c->topology == RLC_TIN && act_mode == RLC_ACT_SHARED && (long long)B * N >= 16384 &&
+                 rlc_umma3_supported(h, c))
+                    ? RLC_PREC_FP16X3
                     : RLC_PREC_FP32;
   }
   if (precision == RLC_PREC_FP32) return rlc_eval_fp32(h, c, s, B, a, N, act_mode, q_out, st);
   // tensor-core path: T-in only (T-mid is not a dense contraction once hoisted)
   if (c->topology != RLC_TIN) return RLC_ERR_UNSUPPORTED;
   if (h->sm_major != 10) return RLC_ERR_ARCH;
-  if (!rlc_umma_supported(h, c, B, N)) return RLC_ERR_UNSUPPORTED;
+  if (precision == RLC_PREC_FP16X3 ? !rlc_umma3_supported(h, c) : !rlc_umma_supported(h, c, B, N))
+    return RLC_ERR_UNSUPPORTED;
   return rlc_eval_umma(h, c, s, B, a, N, act_mode, precision, q_out, st);
 }

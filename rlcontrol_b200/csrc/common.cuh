@@ -8,6 +8,7 @@
 #include "../../include/rlc.h"
 
 #define RLC_MAX_PACKS 8
+#define RLC_MAX_RETIRED 64
 
 // Pre-packed fp16/bf16 tensor-core operands of one theta (see critic_umma.cu).
 struct rlc_pack {
@@ -30,7 +31,15 @@ struct rlc_handle {
   rlc_pack packs[RLC_MAX_PACKS];
   int pack_rr;
   int* err_flag;  // device int raised by bounded waits in the tcgen05 kernel
+  // Blocks replaced by a larger one (workspace, operand packs) are RETIRED, not freed: a CUDA graph captured earlier
+  // has their addresses baked in and keeps replaying into them.  Freed in rlc_destroy.
+  void* retired[RLC_MAX_RETIRED];
+  int n_retired;
 };
+
+// Replace a device block: the old one is kept alive for captured graphs (falls back to synchronise + free when the
+// retirement list is full).
+int rlc_retire_block(rlc_handle* h, void* old_block);
 
 extern thread_local char g_rlc_cuda_err[512];
 
@@ -93,6 +102,7 @@ int rlc_eval_fp32(rlc_handle* h, const rlc_critic* c, const float* s, int B, con
 int rlc_eval_umma(rlc_handle* h, const rlc_critic* c, const float* s, int B, const float* a, int N,
                   int act_mode, int prec, float* q_out, cudaStream_t st);
 bool rlc_umma_supported(const rlc_handle* h, const rlc_critic* c, int B, int N);
+bool rlc_umma3_supported(const rlc_handle* h, const rlc_critic* c);   // split mode (RLC_PREC_FP16X3), shared grids
 // p[B,H2] = relu(clip(s) W1 + b1) W2[:H1] + b2 for a T-mid critic (state-only hoisted term)
 int rlc_tmid_state_term(rlc_handle* h, const rlc_critic* c, const float* s, int B, float* p_out,
                         cudaStream_t st);

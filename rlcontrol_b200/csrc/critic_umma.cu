@@ -1347,6 +1347,11 @@ bool rlc_umma_supported(const rlc_handle* h, const rlc_critic* c, int B, int N) 
   return true;
 }
 
+struct Grid3Parts;
+static int launch_pack_x3(rlc_handle* h, const float* theta, const PackGeom& G, unsigned char* b0, unsigned char* b1,
+                          cudaStream_t st);
+__global__ void k_pack_scale3(const float* __restrict__ theta, PackGeom G, unsigned char* blob0, unsigned char* blob1);
+
 static int get_pack(rlc_handle* h, const rlc_critic* c, int prec, const PackGeom& G,
                     cudaStream_t st, rlc_pack** out) {
   rlc_pack* slot = nullptr;
@@ -1359,8 +1364,8 @@ static int get_pack(rlc_handle* h, const rlc_critic* c, int prec, const PackGeom
     slot = &h->packs[h->pack_rr];
     h->pack_rr = (h->pack_rr + 1) % RLC_MAX_PACKS;
     if (slot->dev && slot->bytes < (size_t)2 * G.blob_bytes) {
-      RLC_CUDA(cudaDeviceSynchronize());
-      cudaFree(slot->dev);
+      const int rcr = rlc_retire_block(h, slot->dev);     // kept alive for graphs captured with the old pack
+      if (rcr) return rcr;
       slot->dev = nullptr;
     }
     if (!slot->dev) {
@@ -1383,7 +1388,12 @@ static int get_pack(rlc_handle* h, const rlc_critic* c, int prec, const PackGeom
       k_pack_head<<<1, 32, 0, st>>>(c->theta, G, b0, b1);
       RLC_LAUNCH_CHECK(h);
     }
-    if (prec == RLC_PREC_BF16) k_pack_umma<RLC_PREC_BF16><<<blocks, 256, 0, st>>>(c->theta, G, b0, b1);
+    if (prec == RLC_PREC_FP16X3) {          // split mode: hi | lo weight blobs, extra power-of-two column scale
+      k_pack_scale3<<<1, 1024, 0, st>>>(c->theta, G, b0, b1);
+      RLC_LAUNCH_CHECK(h);
+      const int rc3 = launch_pack_x3(h, c->theta, G, b0, b1, st);
+      if (rc3) return rc3;
+    } else if (prec == RLC_PREC_BF16) k_pack_umma<RLC_PREC_BF16><<<blocks, 256, 0, st>>>(c->theta, G, b0, b1);
     else k_pack_umma<RLC_PREC_FP16><<<blocks, 256, 0, st>>>(c->theta, G, b0, b1);
     RLC_LAUNCH_CHECK(h);
     slot->valid = true;
@@ -1393,9 +1403,14 @@ static int get_pack(rlc_handle* h, const rlc_critic* c, int prec, const PackGeom
 }
 
 #include "critic_umma_grid.cuh"
+#include "critic_umma_grid3.cuh"
 
 int rlc_eval_umma(rlc_handle* h, const rlc_critic* c, const float* s, int B, const float* a, int N,
                   int act_mode, int prec, float* q_out, cudaStream_t st) {
+  if (prec == RLC_PREC_FP16X3) {             // strict split mode: shared grids only, never a silent downgrade
+    if (act_mode != RLC_ACT_SHARED) return RLC_ERR_UNSUPPORTED;
+    return rlc_eval_umma_grid3(h, c, s, B, a, N, q_out, st);
+  }
   PackGeom G;
   const int ts = umma_mode();
   if (!make_geom(c, G, ts)) return RLC_ERR_UNSUPPORTED;
@@ -1501,6 +1516,14 @@ extern "C" int rlc_umma_mode(const rlc_critic* c, int act_mode) {
   GridPlan gp;
   if (act_mode == RLC_ACT_SHARED && grid_mode() && plan_grid(G, gp)) return 3;
   return 1;
+}
+
+extern "C" int rlc_umma_mode_prec(const rlc_critic* c, int act_mode, int precision) {
+  if (precision != RLC_PREC_FP16X3) return rlc_umma_mode(c, act_mode);
+  if (!critic_ok(c) || c->topology != RLC_TIN || act_mode != RLC_ACT_SHARED) return -1;
+  PackGeom G;
+  Grid3Plan gp;
+  return (make_geom3(c, G) && plan_grid3(G, 232448, gp)) ? 4 : -1;
 }
 
 // Debug/diagnostic: last error flag raised by a bounded wait inside the kernel (0 = none).

@@ -456,6 +456,10 @@ class DeviceExperiment:
             self.h_flag[lo:lo + n].copy_(self.flag_log[lo:lo + n], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.stream)
+        # the replays moved theta_Q on the device: drop the host-side validity of the cached tensor-core operand packs, so
+        # an eager evaluation between chunks (q_net.eval_grid, getQFunction) repacks from the current parameters
+        self.net.critic.invalidate()
+        self.net.critic_grid.invalidate()
         self.events[self.chunk] = ev
         self.pending.append((self.chunk, n))
         self.chunk += 1

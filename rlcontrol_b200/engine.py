@@ -411,11 +411,13 @@ class Critic:
                                                mode, prec, _ptr(q_out), _stream()))
         return q_out
 
-    def tensor_arithmetic(self, shared_actions: bool) -> str:
-        """Which stated arithmetic the tensor path uses for this critic ("ss" | "folded" | "grid" |
-        "unsupported"; include/rlc.h rlc_umma_mode) -- the oracle restatement to compare against."""
-        m = int(self.eng.lib.rlc_umma_mode(C.byref(self._desc), ACT_SHARED if shared_actions else ACT_PER_STATE))
-        return {0: "ss", 1: "folded", 3: "grid"}.get(m, "unsupported")
+    def tensor_arithmetic(self, shared_actions: bool, precision="fp16") -> str:
+        """Which stated arithmetic the tensor path uses for this critic ("ss" | "folded" | "grid" | "grid3" |
+        "unsupported"; include/rlc.h rlc_umma_mode_prec) -- the oracle restatement to compare against."""
+        prec = PREC_BY_NAME[precision] if isinstance(precision, str) else int(precision)
+        m = int(self.eng.lib.rlc_umma_mode_prec(C.byref(self._desc), ACT_SHARED if shared_actions else ACT_PER_STATE,
+                                                prec))
+        return {0: "ss", 1: "folded", 3: "grid", 4: "grid3"}.get(m, "unsupported")
 
     def eval_grad(self, s, a):
         """T-mid only: (q [B,N], dq/da [B,N,A]) without materialising the stack."""

@@ -108,6 +108,16 @@ class _KLNetwork(object):
         c1, c2 = int(config.critic_l1_dim), int(config.critic_l2_dim)
         eng = getattr(config, "engine", None)
         self.eng = eng if eng is not None else Engine()
+        # one handle = one scratch arena and one operand-pack cache: an agent that captures CUDA graphs on it must own it
+        # (a second agent's kernels would write the same scratch from another stream while the first one's graph replays)
+        if getattr(self.eng, "_graph_owner", None) is not None:
+            raise ValueError("config.engine is already owned by another graph-capturing agent: give every "
+                             "ForwardKLNetwork / ReverseKLNetwork its own rlcontrol_b200.Engine")
+        self.eng._graph_owner = self
+        # 'auto' = parity-preserving: the split tensor mode (fp16 hi+lo operands, ~1e-5 of the fp32 reference) for large
+        # shared-grid evaluations, the fp32 CUDA-core path otherwise; the single-rounding 'fp16'/'bf16' modes carry up to
+        # 5e-3 of Q, which exp(q / entropy_scale) amplifies at the small entropy scales the reference sweeps (0.01, 0.001),
+        # so they are opt-in only
         self.precision = getattr(config, "precision", "auto")
         dev = self.eng.device
         # The update's branches (Q regression | grid evaluation + policy | V) overlap on separate streams inside the
@@ -146,6 +156,9 @@ class _KLNetwork(object):
         # reference's batch means and every rank then applies identical Adam steps.
         self.process_group = getattr(config, "process_group", None)
         self.world_size = int(getattr(config, "world_size", 1))
+        # global minibatch size of a data-parallel update (default: equal shards, world_size x local batch); with
+        # parallel.shard_bounds' uneven shards (B % world != 0) the caller passes the true total
+        self.global_batch = getattr(config, "global_batch_size", None)
         # ---- integration grid (:58-102)
         grid = getattr(config, "integration_grid", None)      # optional (actions [N,A], weights [N]) override
         acts, w = grid if grid is not None else integration_grid(A, self.action_scale, getattr(config, "N_param", 64),
@@ -328,7 +341,7 @@ class _KLNetwork(object):
         alpha, sac = self.entropy_scale, self.q_update_type == "sac"
         intg = self.optim_type in ("intg", "hard_intg")
         dp = self.world_size > 1
-        bt = B * self.world_size
+        bt = int(self.global_batch) if (dp and self.global_batch) else B * self.world_size
         need_q_new = sac or not intg
         main, s_grid, s_v, s_pi = st.stream, st.s_grid, st.s_v, st.s_pi
         if not device_inputs:                  # device_loop.py fills st.d[...] on the device (replay gather, staged draws)
@@ -376,7 +389,7 @@ class _KLNetwork(object):
                 self.eng_grid.policy_head_grad(st.head, 0, dmean=st.dmean, dlog_std=st.dls, out=st.dhead)
                 self.eng_grid.mean_into(st.loss_b, o[2:3])
                 if dp:
-                    o[2:3].mul_(1.0 / self.world_size)     # this rank's share of the global mean over states
+                    o[2:3].mul_(float(B) / float(bt))      # this rank's share of the global mean over states
             else:
                 self.eng_grid.policy_head_grad(st.head, 1 if self.optim_type == "ll" else 2, z=st.ev["z"],
                                                logp=st.ev["logp"], q_new=st.q_new, v=st.v_out, entropy_scale=alpha,
@@ -441,6 +454,9 @@ class _KLNetwork(object):
     def update_network_async(self, state_batch, action_batch, next_state_batch, reward_batch, gamma_batch, eps=None):
         """Stage the minibatch and launch the update without waiting for it (independent agents of a sweep
         overlap on one GPU this way: launch them all, then :meth:`wait` each)."""
+        as_np = lambda x: x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+        state_batch, action_batch, next_state_batch, reward_batch, gamma_batch = (
+            as_np(x) for x in (state_batch, action_batch, next_state_batch, reward_batch, gamma_batch))
         s = np.asarray(state_batch, np.float32)
         B = s.shape[0]
         st = self._step_for(B)
@@ -457,6 +473,11 @@ class _KLNetwork(object):
         with torch.cuda.stream(st.stream):
             if st.graph is not None:
                 st.graph.replay()
+                # the replay moves theta_Q on the device; the host-side validity of the cached tensor-core operand packs
+                # was only cleared at capture time, so clear it after every replay (an eager q_net.eval_grid(...) between
+                # updates would otherwise reuse operands packed from the previous theta)
+                self.critic.invalidate()
+                self.critic_grid.invalidate()
             else:
                 self._enqueue(st, B)
         self._pending = st

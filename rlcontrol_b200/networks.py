@@ -37,6 +37,10 @@ def _engine(config) -> Engine:
 
 
 def _np(x):
+    """numpy fp32 view of what a manager passes in -- numpy (the reference contract) or a tensor on any device
+    (ReplayBuffer.sample_batch(as_numpy=False) keeps minibatches on the GPU)."""
+    if isinstance(x, torch.Tensor):
+        x = x.detach().cpu().numpy()
     return np.asarray(x, np.float32)
 
 
@@ -68,8 +72,10 @@ class _TMidBase(object):
         self.action_min, self.action_max = np.asarray(config.action_min, np.float64), np.asarray(config.action_max, np.float64)
         self.learning_rate, self.tau = float(lr), float(config.tau)
         self.norm_type = getattr(config, "norm_type", "none")
-        if self.norm_type not in ("none", "input_norm", "layer"):
-            # base_network.py:53-65: 'batch' needs batch-norm statistics; the AE networks raise too (ae_network.py:93-94)
+        if self.norm_type not in ("none", "input_norm"):
+            # base_network.py:53-65: 'batch' needs batch-norm statistics (the AE networks raise too, ae_network.py:93-94) and
+            # 'layer' inserts tf.contrib.layers.layer_norm(center, scale) after both FC layers -- this critic has neither the
+            # parameters nor the op, so accepting it would silently train a different network
             raise NotImplementedError("norm_type %r is not supported on the B200 path" % (self.norm_type,))
         self.l1, self.l2 = int(l1), int(l2)
         self.eng = _engine(config)

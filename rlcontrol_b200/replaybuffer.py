@@ -147,7 +147,10 @@ class ReplayBuffer(object):
         return result[:k]
 
     # utils/replaybuffer.py:32-37
-    def sample_batch(self, batch_size, as_numpy=False):
+    def sample_batch(self, batch_size, as_numpy=True):
+        """Five numpy arrays like the reference (``map(np.array, zip(*batch))``, utils/replaybuffer.py:36-37), which is
+        what ``BaseAgent.learn`` hands to ``update_network``; ``as_numpy=False`` keeps the gathered minibatch on the
+        device (the drop-in networks accept both)."""
         assert self.get_size() >= batch_size
         self._flush()
         if self.sample_on_device and 0 < batch_size <= 4096 and 3 * batch_size < self.get_size():
@@ -160,7 +163,7 @@ class ReplayBuffer(object):
         slots = (self._head + idx) % self.buffer_size
         return self.gather_slots(slots, as_numpy=as_numpy)
 
-    def gather_slots(self, slots, as_numpy=False):
+    def gather_slots(self, slots, as_numpy=True):
         dev, B = self.eng.device, len(slots)
         slot_t = slots if isinstance(slots, torch.Tensor) else \
             torch.from_numpy(np.ascontiguousarray(slots, dtype=np.int64)).to(dev)
@@ -181,5 +184,11 @@ class ReplayBuffer(object):
         return out
 
     def clear(self):
+        """utils/replaybuffer.py:40-42: the reference re-creates the queue WITHOUT a seed
+        (``RandomAccessQueue(maxlen=self.buffer_size)`` -> ``RandomState(None)``), so the index stream after a clear
+        is freshly (OS-)seeded there too; the ring is emptied in place."""
         self._count = self._head = 0
         self._pending = []
+        self.rng = np.random.RandomState(None)
+        self._seed = int(self.rng.randint(0, 2 ** 31 - 1))
+        self._draws = 0
