@@ -4,20 +4,25 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N ...            # the reference-equivalent CPU path
 
-Workload (config.workload = "cfg4"): ForwardKL large batch, per GPU B=4096 states x N=1024 grid
-actions, S=17, A=6, 400-300 T-in critic (BASELINE.json configs[3], the shape the target is quoted
-on).  One *step* = one pass of the hot path over one replay minibatch:
-    K1  rlc_critic_eval   q[B,N] = Q(s_b, a_n)   (tcgen05 kernel, fp16 operands / fp32 accumulate)
+Workload (config.workload = "cfg4"): ForwardKL large batch, ONE minibatch of B=4096 states x N=1024 grid actions,
+S=17, A=6, 400-300 T-in critic (BASELINE.json configs[3], the shape the target is quoted on), sharded over the ranks
+(--scaling strong, default; --scaling weak gives every rank its own B=4096).  One *step* = one pass of the hot path over
+the minibatch:
+    K1  rlc_critic_eval   q[B,N] = Q(s_b, a_n)   (tcgen05 kernel; default precision fp16x3 = both operands split into
+                          fp16 hi+lo, three MMAs per K step, fp32 accumulate: fp32-class results, 2e-5 of the reference)
     K3  rlc_reduce_fkl_policy  per-state Boltzmann weights + policy loss over the grid, with the
                           tanh-Gaussian log-density evaluated in place from mean/log_std [B,A]
-metric = (s,a) Q-evaluations per second, whole job (all ranks).  States shard over ranks with no
-data-path collective (weak scaling: every rank gets its own B=4096 minibatch).
+metric = (s,a) Q-evaluations per second, whole job (all ranks).  States shard over ranks with no data-path collective.
 
-value : inputs already resident in HBM, CUDA events on the launching stream around exactly K steps.
+value : inputs already resident in HBM, CUDA events on the launching stream around exactly K steps, max over ranks.
 e2e   : the same step through the public API with HOST (pinned) inputs: H2D copy of the states and
         the policy head outputs (mean, log_std), D2H read of the per-state loss, in the timed region.
 roofline : dominant kernel = K1; achieved = algorithmic flops / its mean launch time
-        measured with CUDA events in this process; peak from MEASURED_PEAKS.json.
+        measured with CUDA events in this process; peak from MEASURED_PEAKS.json.  sustained = the same for a >= 3 s loop.
+parity : every rank checks a sample of its rows against the exact fp64 oracle (gate: 1e-3, north_star); at N > 1 the
+        data-parallel critic update is checked on hardware against the concatenated batch (dp_update_max_abs_diff).
+update_step : the cfg4 update as BASELINE.json states it -- critic regression on the shard, NCCL all-reduce of the
+        theta_Q gradients (hidden under K1), Adam, repack, K1, K3 -- one update of the global batch per step.
 cpu_baseline / --impl reference : oracle/oracle_torch.py (the reference's torch-CPU arithmetic,
         materialised stacks) on all host cores, on a bounded sample of the same workload.
 """
@@ -37,7 +42,7 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-WORKLOAD = dict(workload="cfg4", B_per_gpu=4096, N=1024, S=17, A=6, H1=400, H2=300, topology="T-in",
+WORKLOAD = dict(workload="cfg4", B_global=4096, B_per_gpu=4096, N=1024, S=17, A=6, H1=400, H2=300, topology="T-in",
                 reduction="forward_kl (Boltzmann weights + tanh-Gaussian log-density + policy loss and its gradient wrt the policy head)", action_layout="shared_grid[N,A]", entropy_scale=0.1)
 RING = 10                     # rotating input/output sets: 10 x q[B,N] (16.8 MB each) = 168 MB > 126 MB L2
 METRIC = "sampled_q_evals_per_sec"
@@ -186,7 +191,7 @@ def run_reference(args, rank, world):
               f"minibatch through oracle/oracle_torch.py (the reference's torch-CPU arithmetic, materialised stacks)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": dict(W, sample_states_per_step=b_sample),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                              "sample": sample},
@@ -198,9 +203,68 @@ def run_reference(args, rank, world):
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+PARITY_TOL = 1e-3            # north_star: Q within 1e-3 relative of the reference (metric of tests/conftest.rel_err)
+
+
+def _allreduce_max(vals, dev, world):
+    import torch.distributed as dist
+    t = torch.tensor(vals, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.cpu()]
+
+
+def _q_parity(critic, prec, s_rows, a_np, params, q_rows_gpu):
+    """This rank's Q against the exact fp64 oracle on a sample of its rows (the only place this arm touches oracle/)."""
+    from oracle import oracle_np as onp
+    q_ref = onp.tin_eval(s_rows, a_np, params, dtype=np.float64)
+    den = np.maximum(np.abs(q_ref), np.sqrt((q_ref ** 2).mean(1, keepdims=True)))
+    err = np.abs(q_rows_gpu - q_ref) / den
+    out = {"rows_checked": int(q_ref.size), "rel_err_rms": float(np.sqrt((err ** 2).mean())),
+           "rel_err_max": float(err.max())}
+    head = critic.tensor_arithmetic(True, prec) if prec != "fp32" else None
+    if head is not None:
+        q_rnd = onp.tin_eval_rounded(s_rows, a_np, params, "bf16" if prec == "bf16" else "fp16", head=head)
+        d = np.abs(q_rows_gpu - q_rnd) / den
+        out["vs_stated_arithmetic_rms"] = float(np.sqrt((d ** 2).mean()))
+        out["vs_stated_arithmetic_max"] = float(d.max())
+        out["stated_arithmetic"] = head
+    return out
+
+
+def _dp_update_gate(rb, eng, rank, world, dev):
+    """Hardware parity of the data-parallel critic update (forwardkl_network.py:133-140,199-201 is a mean over the WHOLE
+    batch): every rank regresses on its shard (gradients pre-scaled by 1/B_total), one NCCL sum all-reduce, identical Adam
+    steps -- against the same two steps on the concatenated batch computed locally.  fp32, small network."""
+    S, A, H1, H2, Bl = 17, 6, 64, 48, 32
+    rng = np.random.RandomState(7)
+    params = make_params(rng, S, A, H1, H2)
+    Bt = Bl * world
+    batches = [(rng.randn(Bt, S).astype(np.float32), rng.uniform(-1, 1, (Bt, A)).astype(np.float32),
+                rng.randn(Bt).astype(np.float32)) for _ in range(2)]
+    t = lambda x: torch.as_tensor(x, device=dev)
+    c_dp = rb.Critic(eng, rb.TIN, S, A, H1, H2).load(*params, rb.LAYOUT_OUT_IN)
+    c_1 = rb.Critic(eng, rb.TIN, S, A, H1, H2).load(*params, rb.LAYOUT_OUT_IN)
+    o_dp, o_1 = rb.CriticOptimizer(c_dp, lr=1e-2), rb.CriticOptimizer(c_1, lr=1e-2)
+    sl = slice(rank * Bl, (rank + 1) * Bl)
+    for s_, a_, y_ in batches:
+        o_dp.step(t(s_[sl]), t(a_[sl]), t(y_[sl]), world_size=world)
+        o_1.step(t(s_), t(a_), t(y_), world_size=1)
+    diff = float((c_dp.theta - c_1.theta).abs().max())
+    moved = float((c_1.theta - t(np.zeros(1, np.float32))).abs().max())
+    import torch.distributed as dist
+    mx = c_dp.theta.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    spread = float((mx - c_dp.theta).abs().max())          # 0 when every rank holds identical parameters
+    diff, spread = _allreduce_max([diff, spread], dev, world)
+    return {"dp_update_max_abs_diff": diff, "dp_param_spread_across_ranks": spread, "dp_gate_rows_per_rank": Bl,
+            "dp_gate_steps": len(batches), "dp_gate_theta_scale": moved}
+
+
 def run_b200(args, rank, local_rank, world):
     import torch.distributed as dist
     import rlcontrol_b200 as rb
+    from rlcontrol_b200.parallel import shard_bounds
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback "
@@ -210,66 +274,74 @@ def run_b200(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     W = WORKLOAD
-    B, N, S, A, H1, H2 = W["B_per_gpu"], W["N"], W["S"], W["A"], W["H1"], W["H2"]
+    Bg, N, S, A, H1, H2 = W["B_global"], W["N"], W["S"], W["A"], W["H1"], W["H2"]
     alpha = W["entropy_scale"]
+    strong = args.scaling == "strong"
     rng = np.random.RandomState(0)
     params = make_params(rng, S, A, H1, H2)                       # identical weights on every rank
-    rng_in = np.random.RandomState(1000 + rank)                   # each rank: its own minibatch shard
-    s_np, a_np, w_np, (mean_np, lstd_np) = make_inputs(rng_in, B, N, S, A)
+    if strong:
+        # cfg4 as BASELINE.json states it: ONE minibatch of B=4096 states, sharded over the ranks (contiguous, balanced)
+        s_all, _, _, (mean_all, lstd_all) = make_inputs(np.random.RandomState(1000), Bg, N, S, A)
+        lo, hi = shard_bounds(Bg, rank, world)
+        s_np, mean_np, lstd_np = s_all[lo:hi], mean_all[lo:hi], lstd_all[lo:hi]
+        B_total = Bg
+    else:
+        # weak scaling: every rank its own B=4096 minibatch
+        s_np, _, _, (mean_np, lstd_np) = make_inputs(np.random.RandomState(1000 + rank), Bg, N, S, A)
+        B_total = Bg * world
+    B = s_np.shape[0]
     a_np, w_np = make_inputs(np.random.RandomState(1), 1, N, S, A)[1:3]   # the grid is shared by all ranks
+    ring = max(10, int(np.ceil(1.4e8 / (B * N * 4))))             # rotating q sets: > 126 MB of L2 in total
 
     eng = rb.Engine(local_rank)
     critic = rb.Critic(eng, rb.TIN, S, A, H1, H2).load(*params, rb.LAYOUT_OUT_IN)
     prec = args.precision
     t = lambda x: torch.as_tensor(x, device=dev)
     a_d, w_d = t(a_np), t(w_np)
-    # rotating sets so that consecutive steps never find their inputs/outputs in L2
-    s_ring = [t(np.roll(s_np, i, axis=0).copy()) for i in range(RING)]
-    mean_ring = [t(np.roll(mean_np, i, axis=0).copy()) for i in range(RING)]
-    lstd_ring = [t(np.roll(lstd_np, i, axis=0).copy()) for i in range(RING)]
+    s_ring = [t(np.roll(s_np, i, axis=0).copy()) for i in range(ring)]
+    mean_ring = [t(np.roll(mean_np, i, axis=0).copy()) for i in range(ring)]
+    lstd_ring = [t(np.roll(lstd_np, i, axis=0).copy()) for i in range(ring)]
     ACTION_SCALE = 1.0
-    q_ring = [torch.empty((B, N), dtype=torch.float32, device=dev) for _ in range(RING)]
+    q_ring = [torch.empty((B, N), dtype=torch.float32, device=dev) for _ in range(ring)]
 
-    def step(i):
-        j = i % RING
-        q = critic.eval_into(s_ring[j], a_d, q_ring[j], prec)
-        loss_b, dmean, dlstd, _ = eng.fkl_policy(q, w_d, a_d, ACTION_SCALE, mean_ring[j], lstd_ring[j], alpha)
+    def step(i, p=prec):
+        j = i % ring
+        q = critic.eval_into(s_ring[j], a_d, q_ring[j], p)
+        loss_b, dmean, dlstd, _ = eng.fkl_policy(q, w_d, a_d, ACTION_SCALE, mean_ring[j], lstd_ring[j], alpha,
+                                                 b_total=B_total)
         return loss_b
-
-    # ---- parity gate, part of the cpu_baseline leg (rank 0 at N=1; the only place this arm touches oracle/, as the
-    # checker): the oracle evaluates a sample of this rank's rows and the device results must match it ----
-    loss0 = step(0)
-    torch.cuda.synchronize()
-    if eng.umma_error() != 0:
-        raise SystemExit("bench.py: tcgen05 kernel raised its error flag")
-    parity = None
-    if world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle_np as onp
-        rows = np.arange(0, B, B // 8)[:8]
-        q_ref = onp.tin_eval(s_np[rows], a_np, params, dtype=np.float64)
-        q_gpu = q_ring[0][torch.as_tensor(rows, device=dev)].cpu().numpy()
-        den = np.maximum(np.abs(q_ref), np.sqrt((q_ref ** 2).mean(1, keepdims=True)))
-        err = np.abs(q_gpu - q_ref) / den
-        parity = {"rows_checked": int(q_ref.size), "rel_err_rms": float(np.sqrt((err ** 2).mean())),
-                  "rel_err_max": float(err.max())}
-        if prec in ("fp16", "bf16"):
-            q_rnd = onp.tin_eval_rounded(s_np[rows], a_np, params, prec,
-                                           head=critic.tensor_arithmetic(True))
-            d = np.abs(q_gpu - q_rnd) / den
-            parity["vs_stated_arithmetic_rms"] = float(np.sqrt((d ** 2).mean()))
-            parity["vs_stated_arithmetic_max"] = float(d.max())
-            ok = parity["vs_stated_arithmetic_rms"] < 3e-5 and parity["vs_stated_arithmetic_max"] < 2e-3
-        else:
-            ok = parity["rel_err_max"] < 2e-5
-        per_state = onp.fkl_policy_reduce(q_gpu, w_np, a_np, mean_np[rows], lstd_np[rows], ACTION_SCALE, alpha)[0]
-        ok = ok and np.allclose(loss0.cpu().numpy()[rows], per_state, rtol=1e-3, atol=1e-5)
-        if not ok:
-            raise SystemExit(f"bench.py: parity gate failed: {parity}")
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # ---- parity gate on EVERY rank (the oracle is the checker): a sample of this rank's rows against the exact oracle ----
+    loss0 = step(0)
+    torch.cuda.synchronize()
+    if eng.umma_error() != 0:
+        raise SystemExit("bench.py: tcgen05 kernel raised its error flag")
+    parity = None
+    if not args.no_parity:
+        from oracle import oracle_np as onp
+        rows = np.unique(np.linspace(0, B - 1, 8).astype(int))
+        q_gpu = q_ring[0][torch.as_tensor(rows, device=dev)].cpu().numpy()
+        parity = _q_parity(critic, prec, s_np[rows], a_np, params, q_gpu)
+        per_state = onp.fkl_policy_reduce(q_gpu, w_np, a_np, mean_np[rows], lstd_np[rows], ACTION_SCALE, alpha)[0]
+        red_ok = bool(np.allclose(loss0.cpu().numpy()[rows], per_state, rtol=1e-3, atol=1e-5))
+        strict = prec in ("fp16x3", "fp32")
+        ok_local = red_ok and (parity["rel_err_max"] < PARITY_TOL if strict else
+                               (parity["vs_stated_arithmetic_rms"] < 3e-5 and parity["vs_stated_arithmetic_max"] < 2e-3))
+        worst = _allreduce_max([parity["rel_err_rms"], parity["rel_err_max"], 0.0 if ok_local else 1.0], dev, world)
+        parity.update(rel_err_rms=worst[0], rel_err_max=worst[1], ranks_checked=world, tolerance=PARITY_TOL,
+                      meets_north_star_1e3=bool(worst[1] < PARITY_TOL), reduction_matches_oracle=red_ok,
+                      oracle="oracle_np.tin_eval fp64 (exact), metric |dq| / max(|q|, rms_state q), worst rank")
+        if worst[2] != 0.0:
+            raise SystemExit(f"bench.py: parity gate failed on some rank: {parity}")
+        if world > 1:
+            parity.update(_dp_update_gate(rb, rb.Engine(local_rank), rank, world, dev))
+            if parity["dp_update_max_abs_diff"] > 2e-5 or parity["dp_param_spread_across_ranks"] != 0.0:
+                raise SystemExit(f"bench.py: data-parallel update parity gate failed: {parity}")
 
     # ---- device-resident timing: exactly K steps between two events ----
     clocks = ClockSampler(local_rank)          # helper process starts sampling now; the window is marked below
@@ -288,22 +360,21 @@ def run_b200(args, rank, local_rank, world):
     ms_total = ev0.elapsed_time(ev1)
 
     # ---- dominant kernel alone (roofline): K1 launches only, CUDA events on the same stream ----
-    k1_reps = max(args.steps, 10)
-    for i in range(3):
-        critic.eval_into(s_ring[i % RING], a_d, q_ring[i % RING], prec)
-    torch.cuda.synchronize()
-    ev0.record()
-    for i in range(k1_reps):
-        critic.eval_into(s_ring[i % RING], a_d, q_ring[i % RING], prec)
-    ev1.record()
-    torch.cuda.synchronize()
-    k1_ms = ev0.elapsed_time(ev1) / k1_reps
+    def k1_time(p, reps):
+        for i in range(3):
+            critic.eval_into(s_ring[i % ring], a_d, q_ring[i % ring], p)
+        torch.cuda.synchronize()
+        ev0.record()
+        for i in range(reps):
+            critic.eval_into(s_ring[i % ring], a_d, q_ring[i % ring], p)
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / reps
+    k1_ms = k1_time(prec, max(args.steps, 10))
 
     # ---- end to end through the public API: host inputs in, host result out, every step ----
-    # rlcontrol_b200.steps.ForwardKLGridStep: one CUDA-graph launch = H2D of the minibatch (states,
-    # policy head outputs) from pinned memory, K1, K3, D2H of loss and policy-head gradients.
-    from rlcontrol_b200.steps import ForwardKLGridStep
-    fstep = ForwardKLGridStep(critic, a_d, w_d, ACTION_SCALE, alpha, B, precision=prec)
+    from rlcontrol_b200.steps import ForwardKLGridStep, ForwardKLGridPipeline
+    fstep = ForwardKLGridStep(critic, a_d, w_d, ACTION_SCALE, alpha, B, precision=prec, b_total=B_total)
     host_in = [(torch.as_tensor(np.roll(s_np, i, axis=0).copy()), torch.as_tensor(np.roll(mean_np, i, axis=0).copy()),
                 torch.as_tensor(np.roll(lstd_np, i, axis=0).copy())) for i in range(4)]
 
@@ -313,32 +384,24 @@ def run_b200(args, rank, local_rank, world):
         return float(loss_host[0]) + float(dmean_host[0, 0])
 
     chk = e2e_step(0)
-    # the end-to-end call must reproduce the device-resident step on the same inputs (ring slot 0 = host set 0); the
-    # device-resident step itself is what the parity gate above checked against the oracle
     loss_dev0 = float(loss0[0])
     if not np.isfinite(chk) or abs(float(fstep.loss_host[0]) - loss_dev0) > 1e-5 * max(1.0, abs(loss_dev0)):
         raise SystemExit("bench.py: e2e step disagrees with the device-resident step")
     for i in range(args.warmup):
         e2e_step(i)
-    # host-timed: exactly K steps per trial; 5 trials, the median is reported (host jitter on a shared box
-    # occasionally doubles a single 20-step window), min/max kept in the line
     import gc
     gc.disable()
-    trials = []
+    blk_trials = []
     for _ in range(5):
         barrier()
         t0 = time.perf_counter()
         for i in range(args.steps):
             e2e_step(i)
         torch.cuda.synchronize()
-        trials.append((time.perf_counter() - t0) * 1e3)
+        blk_trials.append((time.perf_counter() - t0) * 1e3)
     gc.enable()
-    e2e_blk_ms = float(np.median(trials))     # blocking call per step: copy in, launch, wait, copy out, strictly in sequence
-    blk_trials = trials
-    # the same steps through the pipelined API (steps.ForwardKLGridPipeline, two slots): every step still pays its own
-    # H2D and D2H copies, but step i+1 is staged and uploaded while step i computes; this is the headline e2e number
-    from rlcontrol_b200.steps import ForwardKLGridPipeline
-    pipe = ForwardKLGridPipeline(critic, a_d, w_d, ACTION_SCALE, alpha, B, precision=prec, depth=2)
+    e2e_blk_ms = float(np.median(blk_trials))
+    pipe = ForwardKLGridPipeline(critic, a_d, w_d, ACTION_SCALE, alpha, B, precision=prec, b_total=B_total, depth=2)
 
     def pipe_run(k_steps):
         acc = 0.0
@@ -363,31 +426,86 @@ def run_b200(args, rank, local_rank, world):
         torch.cuda.synchronize()
         trials.append((time.perf_counter() - t0) * 1e3)
     gc.enable()
-    e2e_wall_ms = float(np.median(trials))
-    e2e_ms = e2e_wall_ms          # every result is read on the host inside the window: wall clock IS the end-to-end time
+    e2e_ms = float(np.median(trials))          # every result is read on the host inside the window: wall clock IS end to end
     barrier()
     h2d = (fstep.s_host.numel() + fstep.mean_host.numel() + fstep.log_std_host.numel()) * 4
     d2h = (fstep.loss_host.numel() + fstep.dmean_host.numel() + fstep.dlog_std_host.numel()) * 4
 
-    # ---- secondary: critic regression update (a15/a16) incl. the NCCL grad all-reduce when N>1 ----
-    a_reg = t(rng_in.uniform(-1, 1, (B, A)).astype(np.float32))
-    y_reg = t(rng_in.randn(B).astype(np.float32))
+    # ---- sustained: the same step looped for >= --sustain-s seconds (power-capped clocks), then K1 alone ----
+    def sustained(fn, seconds):
+        sampler = ClockSampler(local_rank)
+        n_done, ms_acc = 0, 0.0
+        barrier()
+        t_end = time.perf_counter() + seconds
+        with sampler:
+            while time.perf_counter() < t_end:
+                ev0.record()
+                for i in range(50):
+                    fn(n_done + i)
+                ev1.record()
+                torch.cuda.synchronize()
+                ms_acc += ev0.elapsed_time(ev1)
+                n_done += 50
+        return ms_acc / n_done, n_done, sampler.summary()
+    sus = None
+    if args.sustain_s > 0:
+        sus_step_ms, sus_n, sus_clk = sustained(step, args.sustain_s)
+        sus_k1_ms, sus_k1_n, sus_k1_clk = sustained(
+            lambda i: critic.eval_into(s_ring[i % ring], a_d, q_ring[i % ring], prec), max(1.0, args.sustain_s / 2))
+        sus = (sus_step_ms, sus_n, sus_clk, sus_k1_ms, sus_k1_n, sus_k1_clk)
+
+    # ---- the UPDATE step of cfg4: critic regression on this rank's shard, its gradient all-reduce (NCCL, on a side
+    # stream, hidden under the grid evaluation, which reads the PRE-update theta_Q like the reference), Adam, operand
+    # repack, grid evaluation, ForwardKL reduction (forwardkl_network.py:133-140,160-201) ----
+    a_reg = t(np.random.RandomState(2000 + rank).uniform(-1, 1, (B, A)).astype(np.float32))
+    y_reg = t(np.random.RandomState(3000 + rank).randn(B).astype(np.float32))
+    g_q = torch.zeros_like(critic.theta)
+    m_q, v_q = torch.zeros_like(critic.theta), torch.zeros_like(critic.theta)
+    loss_q, q_reg = torch.zeros((1,), dtype=torch.float32, device=dev), torch.zeros((B,), dtype=torch.float32, device=dev)
+    comm = torch.cuda.Stream(device=dev)
+    ev_g, ev_c = torch.cuda.Event(), torch.cuda.Event()
+    adam_t = [0]
+
+    def update_step(i):
+        j = i % ring
+        main = torch.cuda.current_stream()
+        critic.grads_into(s_ring[j], a_reg, y_reg, g_q, loss_q, q_reg, b_total=B_total)
+        if world > 1:
+            ev_g.record(main)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev_g)
+                dist.all_reduce(g_q, op=dist.ReduceOp.SUM)
+                ev_c.record(comm)
+        q = critic.eval_into(s_ring[j], a_d, q_ring[j], prec)            # theta_Q(t): before this step's Adam
+        eng.fkl_policy(q, w_d, a_d, ACTION_SCALE, mean_ring[j], lstd_ring[j], alpha, b_total=B_total)
+        if world > 1:
+            main.wait_event(ev_c)
+        adam_t[0] += 1
+        eng.adam_step(critic.theta, g_q, m_q, v_q, adam_t[0], 1e-5, rb.ADAM_TORCH)
+        critic.invalidate()                                                # next step repacks the split operands
+
+    for i in range(max(args.warmup, 3)):
+        update_step(i)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        update_step(args.warmup + i)
+    ev1.record()
+    barrier()
+    upd_step_ms = ev0.elapsed_time(ev1) / args.steps
+    # the regression part alone (grads + all-reduce + Adam, nothing to hide under)
     opt = rb.CriticOptimizer(rb.Critic(eng, rb.TIN, S, A, H1, H2).load(*params, rb.LAYOUT_OUT_IN), lr=1e-3)
     for _ in range(3):
         opt.step(s_ring[0], a_reg, y_reg, world_size=world)
     barrier()
-    upd_reps = 20
     ev0.record()
-    for _ in range(upd_reps):
+    for _ in range(20):
         opt.step(s_ring[0], a_reg, y_reg, world_size=world)
     ev1.record()
     barrier()
-    upd_ms = ev0.elapsed_time(ev1) / upd_reps
+    upd_ms = ev0.elapsed_time(ev1) / 20
 
-    # ---- secondary: cfg1 (the README command: Pendulum ReverseKL, B=32, N_param=64 -> N=62, S=3, A=1, 200-200).
-    # One FULL agent update through the drop-in class: ReverseKLNetwork.update_network + update_target_network
-    # (q, v and pi networks, three Adam steps, Polyak), numpy minibatch in, losses out, host-synchronous like
-    # the reference's loop (agents/ReverseKL.py:81-90) -- one CUDA-graph launch per update.
+    # ---- the full drop-in ForwardKL update_network on this rank's shard (q, v, pi networks, three backward passes) ----
     from types import SimpleNamespace
     from rlcontrol_b200 import kl_networks
 
@@ -400,6 +518,156 @@ def run_b200(args, rank, local_rank, world):
         d.update(kw)
         return SimpleNamespace(**d)
 
+    torch.manual_seed(1)
+    ag4 = kl_networks.ForwardKLNetwork(None, None, kl_config(rb.Engine(local_rank), S, A, 1.0, B, 64, H1, H2,
+                                                               integration_grid=(a_np, w_np), precision=prec,
+                                                               world_size=world, global_batch_size=B_total))
+    rr = np.random.RandomState(4000 + rank)
+    b4 = (s_np, rr.uniform(-1, 1, (B, A)).astype(np.float32), np.roll(s_np, 1, axis=0),
+          rr.randn(B).astype(np.float32), np.full(B, 0.99, np.float32))
+    for _ in range(3):
+        ag4.update_network(*b4)
+        ag4.update_target_network()
+    barrier()
+    n4 = 20
+    t0 = time.perf_counter()
+    for _ in range(n4):
+        ag4.update_network(*b4)
+        ag4.update_target_network()
+    torch.cuda.synchronize()
+    cfg4_full_ms = (time.perf_counter() - t0) * 1e3 / n4
+
+    extras = {}
+    if world == 1 and not args.no_extras:
+        extras = _single_gpu_extras(args, rb, eng, critic, local_rank, dev, kl_config, step, k1_time, s_np, a_np, params,
+                                    q_ring, alpha, B, N)
+
+    # ---- max over ranks ----
+    ms_total, e2e_ms, k1_ms, upd_ms, e2e_blk_ms, upd_step_ms, cfg4_full_ms = _allreduce_max(
+        [ms_total, e2e_ms, k1_ms, upd_ms, e2e_blk_ms, upd_step_ms, cfg4_full_ms], dev, world)
+
+    if rank == 0:
+        peaks, peak_src = {}, "fallback"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+            peak_src = "measured"
+        except Exception:
+            pass
+        peak_tf = float(peaks.get("bf16_tflops", 1590.0))
+        peak_sus = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        flops = algorithmic_flops(B, N, S, A, H1, H2)             # per launch = this rank's shard
+        achieved = flops / (k1_ms * 1e-3) / 1e12
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch_" + prec)
+        except Exception:
+            pass
+        evals_per_step = (Bg if strong else Bg * world) * N
+        evals_total = evals_per_step * args.steps
+        kern = {"fp16x3": "k_critic_umma_grid3 (+ k_grid3_parts pre-pass)", "fp16": "k_critic_umma_grid (+ k_grid_parts8)",
+                "bf16": "k_critic_umma_grid (+ k_grid_parts8)", "fp32": "k_mlp2_rows"}[prec]
+        line = {
+            "metric": METRIC, "value": evals_total / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": {"fp16x3": "f16x3", "fp16": "f16", "bf16": "bf16", "fp32": "f32"}[prec],
+            "dtype_detail": {"fp16x3": "both operands split into f16 hi+lo, three tcgen05 kind::f16 MMAs per K step, f32 accumulate "
+                                       "in TMEM: 22-bit operands, f32-class results (the reference computes in f32)",
+                             "fp16": "f16 operands, f32 accumulate in TMEM (tcgen05 kind::f16): 5e-3 max error, opt-in fast mode",
+                             "bf16": "bf16 operands, f32 accumulate in TMEM (tcgen05 kind::f16)",
+                             "fp32": "f32 CUDA cores"}[prec],
+            "data": "synthetic",
+            "config": dict(workload=W["workload"], B_global=(Bg if strong else Bg * world), B_per_gpu=B, N=N, S=S, A=A, H1=H1, H2=H2,
+                           topology=W["topology"], reduction=W["reduction"], action_layout=W["action_layout"],
+                           entropy_scale=alpha, precision=prec,
+                           l2="rotating %d input/output sets per rank (%.0f MB > 126 MB L2), no flush kernels in the timed region"
+                              % (ring, ring * B * N * 4 / 1e6),
+                           parallelism=(f"ONE minibatch of {Bg} states sharded over {world} rank(s) (strong scaling), " if strong else
+                                        f"{Bg} states per rank, {world} rank(s) (weak scaling), ") +
+                                       "no data-path collective in the evaluation; the update step's critic-gradient "
+                                       "all-reduce is reported in update_step"),
+            "clocks": clocks.summary(),
+            "e2e": {"value": evals_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps, "trials": 5,
+                    "trial_ms_per_step_min_max": [min(trials) / args.steps, max(trials) / args.steps],
+                    "blocking_value": evals_total / (e2e_blk_ms * 1e-3), "blocking_ms_per_step": e2e_blk_ms / args.steps,
+                    "api": "rlcontrol_b200.steps.ForwardKLGridPipeline: submit(states, mean, log_std) / result() -> (loss_b, dmean, "
+                           "dlog_std), host arrays in, host arrays out, two slots in flight (step i+1 is staged and uploaded while "
+                           "step i computes; every step pays its own H2D and D2H copy and its result is read on the host inside "
+                           "the timed window); blocking_* = the same steps through ForwardKLGridStep.__call__ (copy, launch, wait, "
+                           "copy in strict sequence); timed with the host clock, max over ranks"},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "K1 fused T-in critic eval: %s [%s arithmetic]" % (
+                             kern, critic.tensor_arithmetic(True, prec) if prec != "fp32" else "fp32"),
+                         "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                         "peak_source": f"{peak_src} bf16_tflops (burst; sustained {peak_sus})",
+                         "flops_per_launch": flops, "ms_per_launch": k1_ms, "traffic": traffic,
+                         "note": "algorithmic flops (SURVEY 8d: one product per weight); the split mode executes 3 tensor-core "
+                                 "products per algorithmic one, so the tensor pipe itself runs at ~3x this fraction"
+                                 if prec == "fp16x3" else None},
+            "parity": parity,
+            "update_step": {"ms": upd_step_ms, "updates_per_sec": 1e3 / upd_step_ms,
+                            "q_evals_per_sec": evals_per_step / (upd_step_ms * 1e-3),
+                            "definition": "one data-parallel cfg4 update per step (ONE update of the global batch, whatever the rank "
+                                          "count): critic regression grads on the shard -> NCCL sum all-reduce of theta_Q grads on "
+                                          "a side stream, hidden under the grid evaluation (which reads the pre-update theta_Q, "
+                                          "forwardkl_network.py:133-164) -> ForwardKL reduction -> Adam -> operand repack; CUDA "
+                                          "events, max over ranks",
+                            "allreduce": ("nccl sum, %d floats, overlapped with K1" % critic.theta.numel()) if world > 1
+                                         else "none (1 rank)",
+                            "critic_regression_alone_ms": upd_ms},
+            "extra": dict({"cfg4_full_update_ms": cfg4_full_ms, "cfg4_full_updates_per_sec": 1e3 / cfg4_full_ms,
+                           "cfg4_full_update_definition":
+                               "kl_networks.ForwardKLNetwork.update_network + update_target_network on this rank's shard (%d "
+                               "states per rank; q, v, pi networks 400-300, grid N=1024, three backward passes + Adam steps), "
+                               "numpy minibatch in, losses out, host-synchronous, max over ranks; ONE update of the global batch; "
+                               % B + ("one CUDA graph" if world == 1 else
+                                      "ONE NCCL sum all-reduce of the [g_Q|g_V|g_pi] buffer per update, eager launches")}, **extras),
+        }
+        if sus is not None:
+            sus_step_ms, sus_n, sus_clk, sus_k1_ms, sus_k1_n, sus_k1_clk = sus
+            ach_s = flops / (sus_k1_ms * 1e-3) / 1e12
+            line["sustained"] = {
+                "seconds": args.sustain_s, "step_ms": sus_step_ms, "steps": sus_n,
+                "value": evals_per_step / (sus_step_ms * 1e-3),
+                "clocks": sus_clk, "k1_ms": sus_k1_ms, "k1_launches": sus_k1_n, "k1_clocks": sus_k1_clk,
+                "k1_tflops": ach_s, "k1_frac_of_sustained_peak": ach_s / peak_sus, "k1_frac_of_burst_peak": ach_s / peak_tf,
+                "note": "rank 0's loop (every rank runs it); the K-step window above is a burst measurement"}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_arm(params, s_np, a_np, w_np, (mean_np, lstd_np), alpha)
+        emit(line)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _single_gpu_extras(args, rb, eng, critic, local_rank, dev, kl_config, step, k1_time, s_np, a_np, params, q_ring, alpha, B, N):
+    """Secondary numbers at N=1: the opt-in single-rounding fp16 mode with its error stated, cfg1 / cfg5 updates and runs."""
+    from rlcontrol_b200 import kl_networks
+    out = {}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    critic.load(*params, rb.LAYOUT_OUT_IN)        # the update-step timing moved theta_Q: back to the benchmark's parameters
+    if args.precision != "fp16":
+        for i in range(3):
+            step(i, "fp16")
+        torch.cuda.synchronize()
+        ev0.record()
+        for i in range(20):
+            step(i, "fp16")
+        ev1.record()
+        torch.cuda.synchronize()
+        fast_ms = ev0.elapsed_time(ev1) / 20
+        fast_k1 = k1_time("fp16", 20)
+        rows = np.unique(np.linspace(0, B - 1, 8).astype(int))
+        critic.eval_into(torch.as_tensor(s_np, device=dev), torch.as_tensor(a_np, device=dev), q_ring[0], "fp16")
+        fp = _q_parity(critic, "fp16", s_np[rows], a_np, params, q_ring[0][torch.as_tensor(rows, device=dev)].cpu().numpy())
+        out["fast_mode_fp16"] = {"step_ms": fast_ms, "q_evals_per_sec": B * N / (fast_ms * 1e-3), "k1_ms": fast_k1,
+                                 "k1_tflops": algorithmic_flops(B, N, critic.S, critic.A, critic.H1, critic.H2) / (fast_k1 * 1e-3) / 1e12,
+                                 "parity": fp, "meets_north_star_1e3": bool(fp["rel_err_max"] < PARITY_TOL),
+                                 "note": "precision='fp16': ONE rounding of each operand to 11 bits, 1/3 of the MMA work; opt-in, not "
+                                         "the headline, because its max error exceeds north_star's 1e-3"}
     rng1 = np.random.RandomState(5)
     B1 = 32
     batches1 = [(rng1.randn(B1, 3), rng1.uniform(-2, 2, (B1, 1)), rng1.randn(B1, 3), rng1.randn(B1), np.full(B1, 0.99))
@@ -420,9 +688,6 @@ def run_b200(args, rank, local_rank, world):
         update_cfg1(i)
     torch.cuda.synchronize()
     cfg1_ms = (time.perf_counter() - t0) * 1e3 / n_upd
-
-    # cfg5 share of one GPU: 8 independent agents (sweep INDEX runs, main_concurrent.py:64-81), each with its own
-    # handles / streams / graph, overlapping on the device; replicas only, no communication
     agents = [kl_networks.ReverseKLNetwork(None, None, kl_config(rb.Engine(local_rank), 3, 1, 2.0, B1, 64, 200, 200))
               for _ in range(8)]
 
@@ -441,10 +706,6 @@ def run_b200(args, rank, local_rank, world):
         sweep_step(i)
     torch.cuda.synchronize()
     sweep_ms = (time.perf_counter() - t0) * 1e3 / n_sw
-
-    # cfg1 / cfg5 as whole RUNS (environment + replay + agent on the device, rlcontrol_b200/device_loop.py): the README
-    # command's loop -- env.step, replay add, minibatch sample, full update_network, Polyak, sample_action per step,
-    # evaluation sessions (10 greedy episodes every 500 steps) included -- for 1 run and 8 interleaved runs per GPU
     from rlcontrol_b200 import device_loop as dl
     run_steps = 3000
     env_json = {"environment": "Pendulum-v0", "TotalMilSteps": run_steps / 1e6, "EpisodeSteps": -1,
@@ -468,123 +729,23 @@ def run_b200(args, rank, local_rank, world):
         return time.perf_counter() - t0_
     run1_s = timed_runs([make_run(0)])
     run8_s = timed_runs([make_run(i) for i in range(8)])
-
-    # cfg4, the full ForwardKL update_network on this rank's B=4096 minibatch with the synthetic [N,A] grid
-    # (q/v/pi networks 400-300, three backward passes and Adam steps; tensor-core grid evaluation inside)
-    torch.manual_seed(1)
-    ag4 = kl_networks.ForwardKLNetwork(None, None, kl_config(rb.Engine(local_rank), S, A, 1.0, B, 64, H1, H2,
-                                                               integration_grid=(a_np, w_np), precision=prec,
-                                                               world_size=world))
-    b4 = (s_np, rng_in.uniform(-1, 1, (B, A)).astype(np.float32), np.roll(s_np, 1, axis=0),
-          rng_in.randn(B).astype(np.float32), np.full(B, 0.99, np.float32))
-    for _ in range(3):
-        ag4.update_network(*b4)
-        ag4.update_target_network()
-    torch.cuda.synchronize()
-    n4 = 20
-    t0 = time.perf_counter()
-    for _ in range(n4):
-        ag4.update_network(*b4)
-        ag4.update_target_network()
-    torch.cuda.synchronize()
-    cfg4_full_ms = (time.perf_counter() - t0) * 1e3 / n4
-    if world > 1:
-        tt = torch.tensor([cfg4_full_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        cfg4_full_ms = float(tt.cpu())
-
-    # ---- max over ranks ----
-    tm = torch.tensor([ms_total, e2e_ms, k1_ms, upd_ms, e2e_wall_ms, e2e_blk_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, k1_ms, upd_ms, e2e_wall_ms, e2e_blk_ms = [float(x) for x in tm.cpu()]
-
-    if rank == 0:
-        peaks, peak_src = {}, "fallback"
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                peaks = json.load(f)
-            peak_src = "measured"
-        except Exception:
-            pass
-        peak_tf = float(peaks.get("bf16_tflops", 1590.0))
-        flops = algorithmic_flops(B, N, S, A, H1, H2)
-        achieved = flops / (k1_ms * 1e-3) / 1e12
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
-        except Exception:
-            pass
-        evals_total = world * B * N * args.steps
-        line = {
-            "metric": METRIC, "value": evals_total / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[prec],
-            "dtype_detail": {"fp16": "f16 operands, f32 accumulate in TMEM (tcgen05 kind::f16)",
-                             "bf16": "bf16 operands, f32 accumulate in TMEM (tcgen05 kind::f16)",
-                             "fp32": "f32 CUDA cores"}[prec],
-            "data": "synthetic",
-            "config": dict(W, global_states=B * world, precision=prec,
-                           l2="rotating %d input/output sets (%.0f MB > 126 MB L2), no flush kernels in the timed region"
-                              % (RING, RING * 2 * B * N * 4 / 1e6),
-                           parallelism=f"states sharded over {world} rank(s), no data-path collective"),
-            "clocks": clocks.summary(),
-            "e2e": {"value": evals_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
-                    "wall_ms_per_step": e2e_wall_ms / args.steps, "trials": 5,
-                    "trial_ms_per_step_min_max": [min(trials) / args.steps, max(trials) / args.steps],
-                    "blocking_value": evals_total / (e2e_blk_ms * 1e-3), "blocking_ms_per_step": e2e_blk_ms / args.steps,
-                    "blocking_trial_ms_per_step_min_max": [min(blk_trials) / args.steps, max(blk_trials) / args.steps],
-                    "api": "rlcontrol_b200.steps.ForwardKLGridPipeline: submit(states, mean, log_std) / result() -> (loss_b, dmean, "
-                           "dlog_std), host arrays in, host arrays out, two slots in flight (step i+1 is staged and uploaded while "
-                           "step i computes; every step pays its own H2D and D2H copy and its result is read on the host inside "
-                           "the timed window); blocking_* = the same steps through ForwardKLGridStep.__call__ (copy, launch, wait, "
-                           "copy in strict sequence); timed with the host clock"},
-            "gpu_launches": int(launches),
-            "roofline": {"kernel": "K1 fused T-in critic eval: k_critic_umma_grid (+ k_grid_parts pre-pass) [%s arithmetic]" % critic.tensor_arithmetic(True), "bound": "tensor",
-                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "peak_source": f"{peak_src} bf16_tflops (burst; sustained "
-                                        f"{peaks.get('bf16_tflops_sustained', 1400.0)})",
-                         "flops_per_launch": flops, "ms_per_launch": k1_ms, "traffic": traffic},
-            "parity": parity,
-            "extra": {"critic_update_ms": upd_ms, "critic_updates_per_sec": 1e3 / upd_ms,
-                      "agent_update_hot_path_ms": ms_total / args.steps + upd_ms,
-                      "agent_updates_per_sec": world * 1e3 / (ms_total / args.steps + upd_ms),
-                      "agent_update_definition": "cfg4 per rank: critic regression step (grads + all-reduce + Adam) "
-                                                 "+ sampled-action evaluation + ForwardKL policy reduction",
-                      "cfg4_full_update_ms": cfg4_full_ms, "cfg4_full_updates_per_sec": 1e3 / cfg4_full_ms,
-                      "cfg4_full_update_definition": "kl_networks.ForwardKLNetwork.update_network + update_target_network, B=4096 "
-                                                     "states per rank (q, v, pi networks 400-300, grid N=1024, three backward "
-                                                     "passes + Adam steps), numpy minibatch in, losses out; " +
-                                                     ("one CUDA graph" if world == 1 else
-                                                      "global batch %d sharded over %d ranks, ONE NCCL sum all-reduce of the "
-                                                      "[g_Q|g_V|g_pi] buffer per update, eager launches" % (B * world, world)),
-                      "cfg1_update_ms": cfg1_ms, "cfg1_updates_per_sec": 1e3 / cfg1_ms,
-                      "cfg1_definition": "README command shape (Pendulum ReverseKL: B=32 N=62 S=3 A=1 200-200): one FULL agent update "
-                                         "through kl_networks.ReverseKLNetwork.update_network + update_target_network (q, v, pi "
-                                         "networks, three Adam steps, Polyak), numpy minibatch in, losses out, host-synchronous, "
-                                         "one CUDA-graph launch per update",
-                      "cfg5_sweep8_updates_per_sec": world * 8 * 1e3 / sweep_ms, "cfg5_sweep8_ms_per_round": sweep_ms,
-                      "cfg5_definition": "8 independent cfg1 agents per GPU (own handles, streams and graph each), one full update "
-                                         "each per round, launched back to back then awaited; replicas only",
-                      "cfg1_run_env_steps_per_sec": run_steps / run1_s,
-                      "cfg5_runs8_env_steps_per_sec": world * 8 * run_steps / run8_s,
-                      "device_run_definition": "whole runs of the README command on the device (Pendulum-v0 + ReverseKL, %d steps "
-                                               "each): per step env.step + replay add + minibatch of 32 from the reference's index "
-                                               "stream + full update_network + Polyak + sample_action, evaluation sessions (10 x "
-                                               "200 greedy steps every 500 steps) inside the timed region; 1 run / 8 interleaved "
-                                               "runs per GPU (rlcontrol_b200.device_loop)" % run_steps,
-                      "critic_update_rows_per_rank": B,
-                      "critic_update_allreduce": "nccl sum of theta_Q grads" if world > 1 else "none (1 rank)"},
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_arm(params, s_np, a_np, w_np, (mean_np, lstd_np), alpha)
-        emit(line)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    out.update({
+        "cfg1_update_ms": cfg1_ms, "cfg1_updates_per_sec": 1e3 / cfg1_ms,
+        "cfg1_definition": "README command shape (Pendulum ReverseKL: B=32 N=62 S=3 A=1 200-200): one FULL agent update "
+                           "through kl_networks.ReverseKLNetwork.update_network + update_target_network (q, v, pi "
+                           "networks, three Adam steps, Polyak), numpy minibatch in, losses out, host-synchronous, "
+                           "one CUDA-graph launch per update",
+        "cfg5_sweep8_updates_per_sec": 8 * 1e3 / sweep_ms, "cfg5_sweep8_ms_per_round": sweep_ms,
+        "cfg5_definition": "8 independent cfg1 agents per GPU (own handles, streams and graph each), one full update "
+                           "each per round, launched back to back then awaited; replicas only",
+        "cfg1_run_env_steps_per_sec": run_steps / run1_s,
+        "cfg5_runs8_env_steps_per_sec": 8 * run_steps / run8_s,
+        "device_run_definition": "whole runs of the README command on the device (Pendulum-v0 + ReverseKL, %d steps "
+                                 "each): per step env.step + replay add + minibatch of 32 from the reference's index "
+                                 "stream + full update_network + Polyak + sample_action, evaluation sessions (10 x "
+                                 "200 greedy steps every 500 steps) inside the timed region; 1 run / 8 interleaved "
+                                 "runs per GPU (rlcontrol_b200.device_loop)" % run_steps})
+    return out
 
 
 _LINE_OUT = [None]     # the process's original stdout (set in main)
@@ -602,8 +763,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp16", "bf16", "fp32"],
+                    help="arithmetic of the grid evaluation; fp16x3 (default, headline) is the split tensor mode that meets "
+                         "north_star's 1e-3; fp16/bf16 are the single-rounding fast modes")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): cfg4 as BASELINE.json states it, ONE B=4096 minibatch sharded over the ranks; "
+                         "weak: B=4096 per rank")
+    ap.add_argument("--sustain-s", type=float, default=3.0, help="seconds of the sustained-clock loop (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity gates (profiling runs)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary N=1 measurements (cfg1, cfg5, fast mode)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", 0))

@@ -592,6 +592,41 @@ def cem_iterate(q_fn, s, u0, noise, comp_u, top_m, num_modal, a_min, a_max, tol=
     return Wt, Mu, Cv, all_idx
 
 
+def cem_iterate_forced(q_fn, s, u0, noise, comp_u, top_m, num_modal, a_min, a_max, forced_idx, tol=1e-2):
+    """Teacher-forced replay of :func:`cem_iterate` for parity checks: every iteration's candidates are sampled from the
+    mixture refit on ``forced_idx[it-1]`` (the elites the implementation under test picked), so each iteration is a pure
+    function of identical inputs and a near-tie in one iteration cannot hide what later iterations do.
+    Returns (q per iteration [iters,B,N] as q_fn returns it, this oracle's own top-m per iteration [iters,B,top_m],
+    weights, means, covs after the last forced refit)."""
+    s = np.asarray(s)
+    B, N, A = u0.shape
+    iters = 1 + (0 if noise is None else noise.shape[0])
+    a_min = np.asarray(a_min, np.float64)
+    a_max = np.asarray(a_max, np.float64)
+    actions = a_min + u0.astype(np.float64) * (a_max - a_min)
+    Wt = np.zeros((B, num_modal))
+    Mu = np.zeros((B, num_modal, A))
+    Cv = np.zeros((B, num_modal, A))
+    qs, own = [], np.zeros((iters, B, top_m), np.int64)
+    for it in range(iters):
+        if it > 0:
+            actions = np.stack([
+                gmm_sample_with_noise(Wt[b], Mu[b], Cv[b], comp_u[it - 1, b], noise[it - 1, b])
+                for b in range(B)])
+        q = np.asarray(q_fn(s, actions.astype(F32)))
+        qs.append(q)
+        own[it] = topk_desc(q, top_m)
+        el = gather_elites(actions.astype(F32), np.asarray(forced_idx[it])).astype(np.float64)
+        for b in range(B):
+            if num_modal == 1:
+                w, mu, cv = gmm_fit_1comp(el[b])
+            else:
+                resp0 = labels_to_resp(farthest_point_labels(el[b]), num_modal)
+                w, mu, cv, _ = gmm_fit_bounded(el[b], resp0, tol=tol)
+            Wt[b], Mu[b], Cv[b] = w, mu, cv
+    return np.stack(qs), own, Wt, Mu, Cv
+
+
 def cem_final_action(weights, means):
     """``gmm.means_[np.argmax(gmm.weights_)]`` (qt_opt_network.py:180)."""
     k = np.argmax(weights, axis=1)

@@ -110,10 +110,15 @@ class _KLNetwork(object):
         self.eng = eng if eng is not None else Engine()
         # one handle = one scratch arena and one operand-pack cache: an agent that captures CUDA graphs on it must own it
         # (a second agent's kernels would write the same scratch from another stream while the first one's graph replays)
-        if getattr(self.eng, "_graph_owner", None) is not None:
-            raise ValueError("config.engine is already owned by another graph-capturing agent: give every "
-                             "ForwardKLNetwork / ReverseKLNetwork its own rlcontrol_b200.Engine")
-        self.eng._graph_owner = self
+        # Sequential reuse is safe (outgrown scratch blocks are retired, not freed: csrc/api.cu), concurrent use is not.
+        import weakref
+        prev = getattr(self.eng, "_graph_owner", None)
+        if prev is not None and prev() is not None:
+            import warnings
+            warnings.warn("config.engine is shared with another live ForwardKLNetwork / ReverseKLNetwork: their updates "
+                          "must not overlap in time (one scratch arena per handle); give concurrently running agents "
+                          "their own rlcontrol_b200.Engine", RuntimeWarning, stacklevel=3)
+        self.eng._graph_owner = weakref.ref(self)
         # 'auto' = parity-preserving: the split tensor mode (fp16 hi+lo operands, ~1e-5 of the fp32 reference) for large
         # shared-grid evaluations, the fp32 CUDA-core path otherwise; the single-rounding 'fp16'/'bf16' modes carry up to
         # 5e-3 of Q, which exp(q / entropy_scale) amplifies at the small entropy scales the reference sweeps (0.01, 0.001),

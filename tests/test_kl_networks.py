@@ -334,3 +334,102 @@ def test_small_batch_path_equals_generic_path(eng, name):
         for i, (a, b) in enumerate(zip(pa[k], pb[k])):
             move = np.abs(np.asarray(b) - pre[k][i].reshape(np.asarray(b).shape)).max() + 1e-12
             assert np.abs(a - b).max() <= 2e-3 * move + 2e-7, (k, i)
+
+
+# ---------------------------------------------------------------------------------------------
+# round-2 regressions (advisor findings)
+# ---------------------------------------------------------------------------------------------
+def _big_grid_agent(eng_factory, use_graph, alpha=0.2, B=64, seed=11):
+    """An FKL agent whose grid evaluation takes the tensor path under precision='auto' (B * N >= 16384 rows, shared grid)."""
+    import torch
+    from rlcontrol_b200 import kl_networks
+    g, _, _ = load_full("full_fkl_intg_nonsac")
+    S, A, N = 5, 2, 512
+    rng = np.random.RandomState(seed)
+    grid = (rng.uniform(-1.5, 1.5, (N, A)).astype(np.float32), np.full(N, 2.0 / N, np.float32))
+    cfg = _config(eng_factory(), g, state_dim=S, state_min=[-3.0] * S, state_max=[3.0] * S, action_dim=A,
+                  action_min=[-1.5] * A, action_max=[1.5] * A, actor_l1_dim=64, actor_l2_dim=48, critic_l1_dim=128,
+                  critic_l2_dim=96, optim_type="intg", q_update_type="non_sac", entropy_scale=alpha, batch_size=B,
+                  integration_grid=grid, use_cuda_graph=use_graph, fused_small_batch=False)
+    torch.manual_seed(seed)
+    net = kl_networks.ForwardKLNetwork(None, None, cfg)
+    p = net.export_parameters()
+    p["q"][4] = p["q"][4] * 100          # a head that makes Q O(1) instead of O(1e-3)
+    net.load_reference_parameters(p["q"], p["v"], p["tv"], p["pi"])
+    batch = lambda: (rng.randn(B, S), rng.uniform(-1.5, 1.5, (B, A)), rng.randn(B, S), rng.randn(B), np.full(B, 0.99))
+    return net, grid, batch
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_eval_grid_after_graph_replay_uses_current_theta(eng, use_graph):
+    """update -> eval_grid('auto') -> update -> eval_grid('auto'): the eager tensor-path evaluation between graph replays
+    must see the parameters the replay just wrote (the cached operand pack is invalidated after every replay)."""
+    import rlcontrol_b200 as rb
+    net, grid, batch = _big_grid_agent(lambda: rb.Engine(0), use_graph)
+    s_eval = np.random.RandomState(1).randn(64, 5).astype(np.float32)
+    seen = []
+    for _ in range(3):
+        net.update_network(*batch())
+        net.update_target_network()
+        q_auto = net.q_net.eval_grid(s_eval, grid[0], "auto").cpu().numpy()       # 64 x 512 rows: split tensor mode
+        q_32 = net.q_net.eval_grid(s_eval, grid[0], "fp32").cpu().numpy()
+        assert net.eng.umma_error() == 0
+        den = np.maximum(np.abs(q_32), np.sqrt((q_32 ** 2).mean(1, keepdims=True)))
+        assert (np.abs(q_auto - q_32) / den).max() < 4e-5
+        seen.append(q_32)
+    assert np.abs(seen[2] - seen[0]).max() > 1e-4       # theta_Q really moved between the evaluations
+
+
+def test_policy_gradient_at_small_entropy_scale_on_the_default_path(eng):
+    """entropy_scale = 0.01 (the reference sweeps down to 0.001): exp(q / alpha) turns a 5e-3 error of Q into an O(1)
+    error of the Boltzmann weights.  The default precision ('auto' = split tensor mode here) must reproduce the fp64
+    oracle's per-state loss and policy-head gradients; the opt-in single-rounding fp16 mode is shown not to."""
+    import bench
+    import torch
+    from oracle import oracle_np as onp
+    from test_gpu_parity import _tin
+    W = bench.WORKLOAD
+    params = bench.make_params(np.random.RandomState(0), W["S"], W["A"], W["H1"], W["H2"])
+    s, a, w, (mean, lstd) = bench.make_inputs(np.random.RandomState(1000), 32, W["N"], W["S"], W["A"])
+    alpha = 0.01
+    cr = _tin(eng, params, W["S"], W["A"], W["H1"], W["H2"])
+    t = lambda x: torch.as_tensor(x, device=eng.device)
+    q_ref = onp.tin_eval(s, a, params, dtype=np.float64)
+    ref = onp.fkl_policy_reduce(q_ref, w, a, mean, lstd, 1.0, alpha)
+
+    def run(prec):
+        q = cr.eval(s, a, prec)
+        loss_b, dm, ds, _ = eng.fkl_policy(q, t(w), t(a), 1.0, t(mean), t(lstd), alpha)
+        return [x.cpu().numpy() for x in (loss_b, dm, ds)]
+
+    def worst(out):
+        return max(np.abs(o - r).max() / max(np.abs(r).max(), 1e-30) for o, r in zip(out, ref[:3]))
+    assert cr.tensor_arithmetic(True, "fp16x3") == "grid3"
+    assert torch.equal(cr.eval(s, a, "auto"), cr.eval(s, a, "fp16x3"))
+    e_auto, e_fast = worst(run("auto")), worst(run("fp16"))
+    assert e_auto < 2e-3, e_auto                    # q error 1e-5 * |q| / alpha ~ 1e-3 in the exponent
+    assert e_fast > 10 * e_auto, (e_fast, e_auto)   # why 'fp16' is opt-in
+
+
+def test_replay_sample_feeds_update_network_directly(eng):
+    """The two drop-ins compose like the reference's BaseAgent.learn (base_agent.py:64-70): sample_batch's output goes
+    straight into update_network -- numpy by default, device tensors with as_numpy=False."""
+    import rlcontrol_b200 as rb
+    from rlcontrol_b200 import kl_networks
+    from rlcontrol_b200.replaybuffer import ReplayBuffer
+    g, pre, _ = load_full("full_rkl_intg_nonsac")
+    net = kl_networks.ReverseKLNetwork(None, None, _config(rb.Engine(0), g))
+    net.load_reference_parameters(pre["q"], pre["v"], pre["tv"], pre["pi"])
+    buf = ReplayBuffer(1000, 0, 3, 1, engine=eng)
+    rng = np.random.RandomState(0)
+    for _ in range(200):
+        buf.add(rng.randn(3), rng.uniform(-2, 2, 1), rng.randn(), rng.randn(3), 0.99)
+    out = buf.sample_batch(32)
+    assert all(isinstance(x, np.ndarray) for x in out)
+    state, action, reward, next_state, gamma = out               # base_agent.py:66-67, the same unpacking and call
+    net.update_network(state, action, next_state, reward, gamma)
+    assert np.isfinite(net.last_losses).all()
+    state, action, reward, next_state, gamma = buf.sample_batch(32, as_numpy=False)
+    assert all(x.is_cuda for x in (state, action, reward, next_state, gamma))
+    net.update_network(state, action, next_state, reward, gamma)
+    assert np.isfinite(net.last_losses).all()

@@ -396,3 +396,25 @@ def test_svgd_kernel_restatement_properties():
     assert np.all(same[0] == 1.0) and np.all(same[2] == 0.5)                      # zero distances -> h_min floor
     g, _, _ = onp.svgd_action_gradients(np.zeros((3, 5, 2)), xs * 0.5, ys * 0.5)
     assert g.shape == (3, 4, 2) and np.all(np.isfinite(g))
+
+
+def test_cem_forced_replay_equals_free_run_on_its_own_elites():
+    """cem_iterate_forced fed with cem_iterate's own elite indices reproduces it (mixture and per-iteration top-m)."""
+    rng = np.random.RandomState(3)
+    S, A, H1, H2, B, N, iters, M = 3, 2, 24, 16, 6, 64, 3, 2
+    k1, k2 = np.sqrt(3 / S), np.sqrt(3 / (H1 + A))
+    p = [rng.uniform(-k1, k1, (S, H1)).astype(np.float32), rng.uniform(-k1, k1, H1).astype(np.float32),
+         rng.uniform(-k2, k2, (H1 + A, H2)).astype(np.float32), rng.uniform(-k2, k2, H2).astype(np.float32),
+         rng.uniform(-1, 1, (H2, 1)).astype(np.float32), rng.uniform(-1, 1, 1).astype(np.float32)]
+    s = rng.randn(B, S).astype(np.float32)
+    u0 = rng.uniform(size=(B, N, A)).astype(np.float32)
+    noise = rng.randn(iters - 1, B, N, A).astype(np.float32)
+    cu = rng.uniform(size=(iters - 1, B, N)).astype(np.float32)
+    qf = lambda st, ac: onp.tmid_eval_hoisted(st, ac, p, dtype=np.float64)
+    W, Mu, Cv, idx = onp.cem_iterate(qf, s, u0, noise, cu, 6, M, -np.ones(A), np.ones(A))
+    Q, own, W2, Mu2, Cv2 = onp.cem_iterate_forced(qf, s, u0, noise, cu, 6, M, -np.ones(A), np.ones(A), idx)
+    assert Q.shape == (iters, B, N)
+    np.testing.assert_array_equal(own, idx)
+    np.testing.assert_array_equal(W2, W)
+    np.testing.assert_array_equal(Mu2, Mu)
+    np.testing.assert_array_equal(Cv2, Cv)
