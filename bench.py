@@ -146,7 +146,7 @@ def cpu_arm(params, s, a, w, pol, entropy_scale, budget_s=12.0, b_sample=256, ma
     from oracle import oracle_torch as ot
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    net = ot.SoftQNetworkPort(*params)
+    net, kind, what = _cpu_critic(params)
     ts, ta, tw = (torch.as_tensor(x) for x in (s[:b_sample], a, w))
     tl = (torch.as_tensor(pol[0][:b_sample]), torch.as_tensor(pol[1][:b_sample]))
     for _ in range(warmup):
@@ -158,10 +158,27 @@ def cpu_arm(params, s, a, w, pol, entropy_scale, budget_s=12.0, b_sample=256, ma
         times.append(time.perf_counter() - t0)
     med = float(np.median(times))
     evals = b_sample * a.shape[0]
-    return {"value": evals / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+    return {"value": evals / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
             "sample": f"first {b_sample} of {s.shape[0]} states x N={a.shape[0]} ({evals} rows), "
-                      f"median of {len(times)} reps, oracle/oracle_torch.py (reference torch-CPU arithmetic)",
+                      f"median of {len(times)} reps, {what}",
             "ms_per_sample": med * 1e3}
+
+
+def _cpu_critic(params):
+    """The critic the CPU arm times: the reference's own SoftQNetwork class when build() could copy the unmodified file
+    into oracle/_ref/ (kind "reference"), else the line-by-line port (kind "port").  Both run through
+    oracle_torch.fkl_sampled_step, the restatement of the stacking + per-state reduction lines :160-194."""
+    from oracle import oracle_torch as ot
+    try:
+        from oracle import ref_loader
+        net = ref_loader.reference_softq(params)
+    except Exception:
+        net = None
+    if net is not None:
+        return net, "reference", ("critic forward on the materialised B*N stack = the reference's own SoftQNetwork class "
+                                  "(agents/network/forwardkl_network.py:250-268, unmodified copy under oracle/_ref/); stacking, "
+                                  "Boltzmann reduction and get_logprob lines :160-194,:324-351 as restated in oracle/oracle_torch.py")
+    return ot.SoftQNetworkPort(*params), "port", "oracle/oracle_torch.py (reference torch-CPU arithmetic)"
 
 
 def run_reference(args, rank, world):
@@ -175,7 +192,7 @@ def run_reference(args, rank, world):
     from oracle import oracle_torch as ot
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    net = ot.SoftQNetworkPort(*params)
+    net, kind, what = _cpu_critic(params)
     b_sample = 256
     ts, ta, tw = (torch.as_tensor(x) for x in (s[:b_sample], a, w))
     tl = (torch.as_tensor(pol[0][:b_sample]), torch.as_tensor(pol[1][:b_sample]))
@@ -188,12 +205,12 @@ def run_reference(args, rank, world):
     evals = b_sample * W["N"]
     value = evals * args.steps / dt
     sample = (f"each step = first {b_sample} of {W['B_per_gpu']} states x N={W['N']} ({evals} rows) of the cfg4 "
-              f"minibatch through oracle/oracle_torch.py (the reference's torch-CPU arithmetic, materialised stacks)")
+              f"minibatch, materialised stacks; {what}")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": dict(W, sample_states_per_step=b_sample),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
                              "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

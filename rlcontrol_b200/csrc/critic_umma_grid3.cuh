@@ -360,14 +360,6 @@ __global__ void __launch_bounds__(G3_THREADS, 1) k_critic_umma_grid3(const Grid3
       const uint32_t lo_off = (uint32_t)P.w_half_bytes >> 4;   // lo chunk inside a weight stage (streaming both)
       const uint32_t whi_lo = um::desc_lo(base + (uint32_t)P.sm_whi, lbo);   // resident W_hi
       const int np = P.parts.np;
-      uint32_t idp[G3_MAX_NP], dp[G3_MAX_NP], bo[G3_MAX_NP];   // per accumulator part: idesc, TMEM column, B row offset (>>4 of bytes)
-#pragma unroll
-      for (int p = 0; p < G3_MAX_NP; ++p) {
-        const int b0 = P.parts.base[p < np ? p : 0], w = P.parts.base[p < np ? p + 1 : 1] - b0;
-        idp[p] = um::make_idesc(0u, 256, w);
-        dp[p] = tmem_base + (uint32_t)b0;
-        bo[p] = (uint32_t)(b0 / 2);
-      }
       const uint32_t alo = (uint32_t)(KC >> 1);
       bool ok = true;
       uint32_t slot = 0, spar = 0, ws = 0, wpar = 0;
@@ -391,31 +383,36 @@ __global__ void __launch_bounds__(G3_THREADS, 1) k_critic_umma_grid3(const Grid3
           const uint32_t b_hi = P.resident_hi ? whi_lo + (uint32_t)(P.ch.start[c] >> 3) * (lbo >> 4) : b_st;
           const uint32_t b_lo = P.resident_hi ? b_st : b_st + lo_off;
           const uint32_t acc0 = c > 0 ? 1u : 0u;
-#pragma unroll
-          for (int p = 0; p < G3_MAX_NP; ++p) {
-            if (p < np && ok) {
-              if (c == 0 && P.micro != 1) {
-                long long t3 = G3T();
-                ok = ok && um::mbar_wait(bar(B3_L2_EMPTY + p), tpar ^ 1u, P.err, 60 + p);
-                um::tc_fence_after();
-                if (p) pd_ += G3T() - t3; else pc_ += G3T() - t3;
-                if (issuer) G3TR(0, tl, 100 + p);         // accumulator part p handed back
-              }
-              if (ok && issuer) {
-                const uint32_t d = dp[p], idesc = idp[p];
-                const uint32_t bh = b_hi + bo[p], bl = b_lo + bo[p];
-                switch (ksteps) {
-                  case 6: um::issue_half3<6>(d, a_hi, a_lo, bh, bl, kstep, idesc, acc0); break;
-                  case 5: um::issue_half3<5>(d, a_hi, a_lo, bh, bl, kstep, idesc, acc0); break;
-                  case 4: um::issue_half3<4>(d, a_hi, a_lo, bh, bl, kstep, idesc, acc0); break;
-                  case 3: um::issue_half3<3>(d, a_hi, a_lo, bh, bl, kstep, idesc, acc0); break;
-                  case 2: um::issue_half3<2>(d, a_hi, a_lo, bh, bl, kstep, idesc, acc0); break;
-                  default: um::issue_half3<1>(d, a_hi, a_lo, bh, bl, kstep, idesc, acc0); break;
-                }
-                if (c == nch - 1) um::commit2(bar(B3_L2_FULL + p));   // part p is handed over before part p+1 is issued
-              }
-              __syncwarp();
+#pragma unroll 1
+          for (int p = 0; p < np && ok; ++p) {
+            if (c == 0 && P.micro != 1) {
+              long long t3 = G3T();
+              ok = ok && um::mbar_wait(bar(B3_L2_EMPTY + p), tpar ^ 1u, P.err, 60 + p);
+              um::tc_fence_after();
+              if (p) pd_ += G3T() - t3; else pc_ += G3T() - t3;
+              if (issuer) G3TR(0, tl, 100 + p);         // accumulator part p handed back
             }
+            if (ok && issuer) {
+              // per accumulator part: TMEM column, instruction descriptor (N = part width), B row offset (>>4 of bytes)
+              const int pb0 = P.parts.base[p], pw = P.parts.base[p + 1] - pb0;
+              const uint32_t d = tmem_base + (uint32_t)pb0, idesc = um::make_idesc(0u, 256, pw);
+              const uint32_t bh = b_hi + (uint32_t)(pb0 >> 1), bl = b_lo + (uint32_t)(pb0 >> 1);
+              switch (ksteps) {
+                case 6: um::issue_half3<6>(d, a_hi, a_lo, bh, bl, kstep, idesc, acc0); break;
+                case 5: um::issue_half3<5>(d, a_hi, a_lo, bh, bl, kstep, idesc, acc0); break;
+                case 4: um::issue_half3<4>(d, a_hi, a_lo, bh, bl, kstep, idesc, acc0); break;
+                default:
+#pragma unroll 1
+                  for (int k = 0; k < ksteps; ++k) {
+                    um::mma2_ts(d, a_hi + 8u * (uint32_t)k, um::desc64(bh + (uint32_t)k * kstep), idesc, acc0 | (uint32_t)(k > 0));
+                    um::mma2_ts_acc(d, a_lo + 8u * (uint32_t)k, um::desc64(bh + (uint32_t)k * kstep), idesc);
+                    um::mma2_ts_acc(d, a_hi + 8u * (uint32_t)k, um::desc64(bl + (uint32_t)k * kstep), idesc);
+                  }
+                  break;
+              }
+              if (c == nch - 1) um::commit2(bar(B3_L2_FULL + p));   // part p is handed over before part p+1 is issued
+            }
+            __syncwarp();
           }
           if (ok && issuer) {
             um::commit2(bar(B3_H1_EMPTY + (int)slot));

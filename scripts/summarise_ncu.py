@@ -39,8 +39,13 @@ if os.path.exists(rep):
             v = float(v.replace(",", ""))
             return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
         traffic = sum(tob(r[ir], units[ir]) + tob(r[iw], units[iw]) for r in rows[2:]) / (len(rows) - 2)
-        json.dump({"dram_bytes_per_launch": traffic, "source": f"profiles/{tag}_k1_ncu.md (ncu --set full)"},
-                  open(os.path.join(P, "k1_traffic.json"), "w"))
+        kname = rows[2][kn]
+        prec = "fp16x3" if "grid3" in kname else "fp16"
+        tj = os.path.join(P, "k1_traffic.json")
+        cur = json.load(open(tj)) if os.path.exists(tj) else {}
+        cur["dram_bytes_per_launch_" + prec] = traffic
+        cur["source_" + prec] = f"profiles/{tag}_k1_ncu.md (ncu --set full, {kname[:40]})"
+        json.dump(cur, open(tj, "w"), indent=1)
     except Exception as e:
         print("traffic:", e)
 launch_csv = os.path.join(G, f"launches_{tag}.csv")
@@ -58,19 +63,23 @@ if os.path.exists(launch_csv):
         agg[name][0] += 1
         agg[name][1] += v
     tot = sum(v[1] for v in agg.values())
-    out.append(f"\n## launch list (ncu --metrics gpu__time_duration.sum --clock-control none) of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline`\n")
-    out.append("Cold-cache, serialised times: compare SHARES. The command runs the parity gate, warm-up + 2 timed steps, "
-               "the K1-only loop, the e2e loop and the critic-update loop (k_gemm/k_head_grads/k_colsum/k_adam).\n")
+    out.append(f"\n## launch list (ncu --metrics gpu__time_duration.sum --clock-control none) of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras --no-parity --sustain-s 0`\n")
+    out.append("Cold-cache, serialised times: compare SHARES. The command runs warm-up + 2 timed steps, the K1-only loop, the e2e "
+               "loops, the update-step loop (k_gemm/k_head_grads/k_colsum/k_adam + repack) and the full drop-in update.\n")
     out.append("| kernel | launches | total us | mean us | share |")
     out.append("|---|---|---|---|---|")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append(f"| {k} | {v[0]} | {v[1]:.1f} | {v[1] / v[0]:.1f} | {v[1] / tot:.3f} |")
     step = {k: v[1] / v[0] for k, v in agg.items()}
     k1 = [v for k, v in step.items() if "k_critic_umma" in k]
-    fk = [v for k, v in step.items() if k.startswith("k_fkl")]
+    fk = [v for k, v in step.items() if k.startswith("k_fkl") or k.startswith("k_policy_reduce")]
     if k1 and fk:
-        out.append(f"\nOne bench *step* = 1 x k_critic_umma ({k1[0]:.1f} us) + 1 x k_fkl ({fk[0]:.1f} us): "
-                   f"K1's share of the step = {k1[0] / (k1[0] + fk[0]):.3f}.")
+        pre = [v for k, v in step.items() if "k_grid3_parts" in k or "k_grid_parts" in k]
+        lt = [v for k, v in step.items() if "k_grid_logterms" in k]
+        rest = (pre[0] if pre else 0.0) + (lt[0] if lt else 0.0)
+        out.append(f"\nOne bench *step* = pre-pass ({pre[0] if pre else 0:.1f} us) + K1 ({k1[0]:.1f} us) + grid log-terms "
+                   f"({lt[0] if lt else 0:.1f} us) + policy-fused reduction ({fk[0]:.1f} us): K1's share of the step = "
+                   f"{k1[0] / (k1[0] + fk[0] + rest):.3f}.")
 bj = os.path.join(G, f"bench_{tag}.json")
 if os.path.exists(bj) and os.path.getsize(bj):
     out.append(f"\n## bench line of the same build (gpurun_out/bench_{tag}.json)\n\n```json\n" + open(bj).read().strip() + "\n```")

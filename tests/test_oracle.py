@@ -418,3 +418,20 @@ def test_cem_forced_replay_equals_free_run_on_its_own_elites():
     np.testing.assert_array_equal(W2, W)
     np.testing.assert_array_equal(Mu2, Mu)
     np.testing.assert_array_equal(Cv2, Cv)
+
+
+def test_reference_class_cpu_arm_equals_port():
+    """bench.py's CPU arm: the reference's own SoftQNetwork (unmodified copy under oracle/_ref/, made by build()) and the
+    line-by-line port produce the same Q; skipped where the copy does not exist."""
+    import torch
+    from oracle import oracle_torch as ot, ref_loader
+    rng = np.random.RandomState(0)
+    S, A, H1, H2 = 5, 2, 32, 24
+    p = [rng.randn(H1, S + A).astype(np.float32), rng.randn(H1).astype(np.float32), rng.randn(H2, H1).astype(np.float32),
+         rng.randn(H2).astype(np.float32), rng.randn(1, H2).astype(np.float32), rng.randn(1).astype(np.float32)]
+    net = ref_loader.reference_softq(p)
+    if net is None:
+        pytest.skip("oracle/_ref/ not built (no /root/reference at build time)")
+    s, a = torch.randn(40, S), torch.randn(40, A)
+    with torch.no_grad():
+        np.testing.assert_array_equal(net(s, a).numpy(), ot.SoftQNetworkPort(*p)(s, a).numpy())
