@@ -59,6 +59,10 @@ extern "C" {
                              K step into one fp32 TMEM accumulator (h_hi.W_hi + h_lo.W_hi + h_hi.W_lo): 22-bit operands,
                              ~1e-5 of the exact Q (fp32-class parity with forwardkl_network.py:263-268) at 3x the MMA work */
 
+#define RLC_PREC_FP16C8 5 /* fast split mode (shared grids): the fp16 product plus its two corrections on the FP8 pipe (kind::f8f6f4,
+                             twice the MMA rate): h_hi.W_hi + e4m3(2^9 h_lo).e4m3(2^-9 W_hi) + e5m2(h_hi).e4m3(W_lo): ~2e-4 max of
+                             the exact Q (inside north_star's 1e-3 with margin) at 2/3 of FP16X3's tensor-pipe time */
+
 /* Adam flavour of rlc_adam_step */
 #define RLC_ADAM_TORCH 0 /* torch.optim.Adam: p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps) */
 #define RLC_ADAM_TF 1    /* tf.train.AdamOptimizer: p -= lr*sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v)+eps) */
@@ -134,7 +138,8 @@ int rlc_umma_mode(const rlc_critic* c, int act_mode);
 /* Same for an explicit precision; adds
  *   4  "grid3"  RLC_PREC_FP16X3, shared grids: h = fl32(PS[b] + PA[n]) from fp32 tables, relu, h = h_hi + h_lo (fp16 each);
  *               W' = fl32(2^k |w3_j| W2[:,j]) = W_hi + W_lo (fp16 each, 2^k also normalises max|W2| to [2^8,2^9));
- *               z = h_hi.W_hi + h_lo.W_hi + h_hi.W_lo, then the folded head. */
+ *               z = h_hi.W_hi + h_lo.W_hi + h_hi.W_lo, then the folded head.
+ *   5  "grid3c8" RLC_PREC_FP16C8: same h, W' and hi parts; the corrections use 8-bit operands (see RLC_PREC_FP16C8). */
 int rlc_umma_mode_prec(const rlc_critic* c, int act_mode, int precision);
 
 /* ---- per-state reductions (rows a3, a4, a8, a9, a10) ------------------------------------ */

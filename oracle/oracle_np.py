@@ -84,6 +84,18 @@ def round_operand(x, kind):
     raise ValueError(kind)
 
 
+def round_fp8(x, kind):
+    """Round-to-nearest-even to an 8-bit float (``cvt.rn.satfinite``), returned as float64: 'e4m3' (3 mantissa bits,
+    min normal 2^-6, max 448) or 'e5m2' (2 mantissa bits, min normal 2^-14, max 57344); subnormals kept, overflow
+    saturates.  Operand types of the FP8 correction terms of RLC_PREC_FP16C8."""
+    mb, emin, mx = {"e4m3": (3, -6, 448.0), "e5m2": (2, -14, 57344.0)}[kind]
+    x = np.asarray(x, np.float64)
+    ax = np.abs(x)
+    e = np.maximum(np.floor(np.log2(np.where(ax > 0, ax, 1.0))), emin)
+    step = np.exp2(e - mb)
+    return np.sign(x) * np.minimum(np.round(ax / step) * step, mx)
+
+
 def tin_eval_rounded(s, a, params, kind="fp16", head="ss"):
     """T-in evaluation with the operand rounding of the tensor-core path made explicit (fp64
     accumulate): x=[s;a], W1, b1 (folded as a ones column) and the ReLU'd layer-1 activations are
@@ -106,6 +118,9 @@ def tin_eval_rounded(s, a, params, kind="fp16", head="ss"):
                       h_hi = r(h), h_lo = r(h - h_hi); W' = fl32(2^k |w3_j| W2[j,:]) = W_hi + W_lo likewise, 2^k the
                       head-folding scale times 2^e2 with 2^e2 max(|W2|,|b2|) in [2^8, 2^9);
                       z = h_hi.W_hi + h_lo.W_hi + h_hi.W_lo (the bias rides on an always-one feature), folded head.
+    ``head="grid3c8"`` RLC_PREC_FP16C8: same h, W' and hi parts, the two corrections with 8-bit operands:
+                      z = h_hi.W_hi + e4m3(2^9 (h - h_hi)).e4m3(2^-9 W_hi) + e5m2(h_hi).e4m3(W' - W_hi),
+                      e5m2(h_hi) = upper byte of the fp16 bits of h_hi + 0x80 (round half up).
 
     The CUDA kernel must match THIS to ~1e-5 rms (it does exactly this arithmetic with fp32
     accumulators); the distance from ``tin_eval(..., float64)`` is the cost of the operand type."""
@@ -118,6 +133,8 @@ def tin_eval_rounded(s, a, params, kind="fp16", head="ss"):
     r = lambda z: round_operand(z, kind)
     if head == "grid3":
         return _tin_eval_grid3(s, a, params)
+    if head == "grid3c8":
+        return _tin_eval_grid3(s, a, params, c8=True)
     if head == "grid":
         if a.ndim != 2:
             raise ValueError("head='grid' is the shared-grid arithmetic")
@@ -159,8 +176,8 @@ def tin_eval_rounded(s, a, params, kind="fp16", head="ss"):
     return q.reshape(B, N)
 
 
-def _tin_eval_grid3(s, a, params):
-    """Stated arithmetic of the split tensor mode (csrc/critic_umma_grid3.cuh), fp64 accumulate."""
+def _tin_eval_grid3(s, a, params, c8=False, sa=9, sb=0):
+    """Stated arithmetic of the split tensor modes (csrc/critic_umma_grid3.cuh), fp64 accumulate."""
     if np.asarray(a).ndim != 2:
         raise ValueError("head='grid3' is a shared-grid arithmetic")
     f32, f64 = np.float32, np.float64
@@ -193,8 +210,19 @@ def _tin_eval_grid3(s, a, params):
     Wp = np.clip((sw[:, None] * W2).astype(f32), -65504, 65504)      # [H2,H1], one fp32 rounding
     bp = np.clip((sw * b2.reshape(-1)).astype(f32), -65504, 65504)
     W_hi, b_hi = r16(Wp), r16(bp)
-    W_lo, b_lo = r16((Wp.astype(f64) - W_hi).astype(f32)), r16((bp.astype(f64) - b_hi).astype(f32))
-    z = h_hi @ W_hi.T + h_lo @ W_hi.T + h_hi @ W_lo.T + (b_hi + b_lo)
+    if c8:
+        h_lo8 = round_fp8((h.astype(f64) - h_hi).astype(f32).astype(f64) * 2.0 ** sa, "e4m3")
+        # e5m2 copy of h_hi: the upper byte of the fp16 value after adding half an e5m2 ulp (round half UP in magnitude)
+        u = np.asarray(h_hi, np.float32).astype(np.float16).view(np.uint16).astype(np.uint32)
+        h_hi8 = (((u + 0x80) & 0xFF00).astype(np.uint16).view(np.float16).astype(f64)) * 2.0 ** -sb
+        W_hi8 = round_fp8(W_hi * 2.0 ** -sa, "e4m3")
+        W_lo8 = round_fp8((Wp.astype(f64) - W_hi).astype(f32).astype(f64) * 2.0 ** sb, "e4m3")
+        b_lo8 = round_fp8((bp.astype(f64) - b_hi).astype(f32).astype(f64) * 2.0 ** sb, "e4m3")
+        # the bias feature is h = 1: hi part 1, lo part 0, e5m2(2^-sb) exact
+        z = h_hi @ W_hi.T + h_lo8 @ W_hi8.T + h_hi8 @ W_lo8.T + b_hi + (2.0 ** -sb) * b_lo8
+    else:
+        W_lo, b_lo = r16((Wp.astype(f64) - W_hi).astype(f32)), r16((bp.astype(f64) - b_hi).astype(f32))
+        z = h_hi @ W_hi.T + h_lo @ W_hi.T + h_hi @ W_lo.T + (b_hi + b_lo)
     sign = np.where(w3 < 0, -1.0, 1.0)
     q = (np.maximum(z, 0) @ sign) / f64(scale) + f64(b3.reshape(()))
     return q.reshape(B, N)

@@ -11,10 +11,11 @@ LIB_PATH = os.environ.get("RLC_LIB_PATH") or os.path.join(_HERE, "librlc.so")   
 TIN, TMID = 0, 1
 LAYOUT_OUT_IN, LAYOUT_IN_OUT = 0, 1
 ACT_SHARED, ACT_PER_STATE = 0, 1
-PREC_FP32, PREC_FP16, PREC_BF16, PREC_AUTO, PREC_FP16X3 = 0, 1, 2, 3, 4
+PREC_FP32, PREC_FP16, PREC_BF16, PREC_AUTO, PREC_FP16X3, PREC_FP16C8 = 0, 1, 2, 3, 4, 5
 ADAM_TORCH, ADAM_TF = 0, 1
 
-PREC_BY_NAME = {"fp32": PREC_FP32, "fp16": PREC_FP16, "bf16": PREC_BF16, "auto": PREC_AUTO, "fp16x3": PREC_FP16X3}
+PREC_BY_NAME = {"fp32": PREC_FP32, "fp16": PREC_FP16, "bf16": PREC_BF16, "auto": PREC_AUTO, "fp16x3": PREC_FP16X3,
+                "fp16c8": PREC_FP16C8}
 
 
 class RlcCritic(C.Structure):

@@ -118,7 +118,7 @@ extern "C" int rlc_critic_eval(rlc_handle* h, const rlc_critic* c, const float* 
                                void* stream) {
   RLC_REQUIRE(h && critic_ok(c) && s && a && q_out && B >= 0 && N >= 0);
   RLC_REQUIRE(act_mode == RLC_ACT_SHARED || act_mode == RLC_ACT_PER_STATE);
-  RLC_REQUIRE(precision >= RLC_PREC_FP32 && precision <= RLC_PREC_FP16X3);
+  RLC_REQUIRE(precision >= RLC_PREC_FP32 && precision <= RLC_PREC_FP16C8);
   if ((long long)B * N == 0) return RLC_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == RLC_PREC_AUTO) {
@@ -126,7 +126,7 @@ extern "C" int rlc_critic_eval(rlc_handle* h, const rlc_critic* c, const float* 
     // (large shared-grid T-in evaluations), the fp32 CUDA-core path everywhere else.  The single-rounding fp16/bf16
     // modes (5e-3 max error) are only used when asked for by name.
     precision = (c->topology == RLC_TIN && act_mode == RLC_ACT_SHARED && (long long)B * N >= 16384 &&
-                 rlc_umma3_supported(h, c))
+                 rlc_umma3_supported(h, c, RLC_PREC_FP16X3))
                     ? RLC_PREC_FP16X3
                     : RLC_PREC_FP32;
   }
@@ -134,7 +134,8 @@ extern "C" int rlc_critic_eval(rlc_handle* h, const rlc_critic* c, const float* 
   // tensor-core path: T-in only (T-mid is not a dense contraction once hoisted)
   if (c->topology != RLC_TIN) return RLC_ERR_UNSUPPORTED;
   if (h->sm_major != 10) return RLC_ERR_ARCH;
-  if (precision == RLC_PREC_FP16X3 ? !rlc_umma3_supported(h, c) : !rlc_umma_supported(h, c, B, N))
+  if ((precision == RLC_PREC_FP16X3 || precision == RLC_PREC_FP16C8) ? !rlc_umma3_supported(h, c, precision)
+                                                                     : !rlc_umma_supported(h, c, B, N))
     return RLC_ERR_UNSUPPORTED;
   return rlc_eval_umma(h, c, s, B, a, N, act_mode, precision, q_out, st);
 }

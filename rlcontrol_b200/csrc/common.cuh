@@ -102,7 +102,7 @@ int rlc_eval_fp32(rlc_handle* h, const rlc_critic* c, const float* s, int B, con
 int rlc_eval_umma(rlc_handle* h, const rlc_critic* c, const float* s, int B, const float* a, int N,
                   int act_mode, int prec, float* q_out, cudaStream_t st);
 bool rlc_umma_supported(const rlc_handle* h, const rlc_critic* c, int B, int N);
-bool rlc_umma3_supported(const rlc_handle* h, const rlc_critic* c);   // split mode (RLC_PREC_FP16X3), shared grids
+bool rlc_umma3_supported(const rlc_handle* h, const rlc_critic* c, int prec);   // split modes (FP16X3 / FP16C8), shared grids
 // p[B,H2] = relu(clip(s) W1 + b1) W2[:H1] + b2 for a T-mid critic (state-only hoisted term)
 int rlc_tmid_state_term(rlc_handle* h, const rlc_critic* c, const float* s, int B, float* p_out,
                         cudaStream_t st);

@@ -19,6 +19,7 @@
 // are sent to the leader CTA's barriers through shared::cluster addresses).
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
+#include <cuda_fp8.h>
 
 #include "common.cuh"
 
@@ -1348,8 +1349,8 @@ bool rlc_umma_supported(const rlc_handle* h, const rlc_critic* c, int B, int N) 
 }
 
 struct Grid3Parts;
-static int launch_pack_x3(rlc_handle* h, const float* theta, const PackGeom& G, unsigned char* b0, unsigned char* b1,
-                          cudaStream_t st);
+static int launch_pack_x3(rlc_handle* h, const float* theta, const PackGeom& G, int mode, unsigned char* b0,
+                          unsigned char* b1, cudaStream_t st);
 __global__ void k_pack_scale3(const float* __restrict__ theta, PackGeom G, unsigned char* blob0, unsigned char* blob1);
 
 static int get_pack(rlc_handle* h, const rlc_critic* c, int prec, const PackGeom& G,
@@ -1388,10 +1389,10 @@ static int get_pack(rlc_handle* h, const rlc_critic* c, int prec, const PackGeom
       k_pack_head<<<1, 32, 0, st>>>(c->theta, G, b0, b1);
       RLC_LAUNCH_CHECK(h);
     }
-    if (prec == RLC_PREC_FP16X3) {          // split mode: hi | lo weight blobs, extra power-of-two column scale
+    if (prec == RLC_PREC_FP16X3 || prec == RLC_PREC_FP16C8) {   // split modes: hi | lo weight blobs, extra power-of-two column scale
       k_pack_scale3<<<1, 1024, 0, st>>>(c->theta, G, b0, b1);
       RLC_LAUNCH_CHECK(h);
-      const int rc3 = launch_pack_x3(h, c->theta, G, b0, b1, st);
+      const int rc3 = launch_pack_x3(h, c->theta, G, prec == RLC_PREC_FP16C8 ? 1 : 0, b0, b1, st);
       if (rc3) return rc3;
     } else if (prec == RLC_PREC_BF16) k_pack_umma<RLC_PREC_BF16><<<blocks, 256, 0, st>>>(c->theta, G, b0, b1);
     else k_pack_umma<RLC_PREC_FP16><<<blocks, 256, 0, st>>>(c->theta, G, b0, b1);
@@ -1407,9 +1408,9 @@ static int get_pack(rlc_handle* h, const rlc_critic* c, int prec, const PackGeom
 
 int rlc_eval_umma(rlc_handle* h, const rlc_critic* c, const float* s, int B, const float* a, int N,
                   int act_mode, int prec, float* q_out, cudaStream_t st) {
-  if (prec == RLC_PREC_FP16X3) {             // strict split mode: shared grids only, never a silent downgrade
+  if (prec == RLC_PREC_FP16X3 || prec == RLC_PREC_FP16C8) {   // split modes: shared grids only, never a silent downgrade
     if (act_mode != RLC_ACT_SHARED) return RLC_ERR_UNSUPPORTED;
-    return rlc_eval_umma_grid3(h, c, s, B, a, N, q_out, st);
+    return rlc_eval_umma_grid3(h, c, s, B, a, N, prec, q_out, st);
   }
   PackGeom G;
   const int ts = umma_mode();
@@ -1519,11 +1520,12 @@ extern "C" int rlc_umma_mode(const rlc_critic* c, int act_mode) {
 }
 
 extern "C" int rlc_umma_mode_prec(const rlc_critic* c, int act_mode, int precision) {
-  if (precision != RLC_PREC_FP16X3) return rlc_umma_mode(c, act_mode);
+  if (precision != RLC_PREC_FP16X3 && precision != RLC_PREC_FP16C8) return rlc_umma_mode(c, act_mode);
   if (!critic_ok(c) || c->topology != RLC_TIN || act_mode != RLC_ACT_SHARED) return -1;
   PackGeom G;
   Grid3Plan gp;
-  return (make_geom3(c, G) && plan_grid3(G, 232448, gp)) ? 4 : -1;
+  const int mode = g3_mode_of(precision);
+  return (make_geom3(c, G, mode) && plan_grid3(G, 232448, gp, mode)) ? (mode == G3_C8 ? 5 : 4) : -1;
 }
 
 // Debug/diagnostic: last error flag raised by a bounded wait inside the kernel (0 = none).

@@ -28,14 +28,23 @@
 // TMEM lane quarter, each building half of a chunk's columns) | 12-19 epilogue 2.
 #pragma once
 
-#ifndef G3_E1W
-#define G3_E1W 4             // epilogue-1 warps: 4 (one per TMEM lane quarter) or 8 (two, each half of a chunk's units)
-#endif
-#ifndef G3_E2G
-#define G3_E2G 4             // epilogue-2 column groups (x 4 lane quarters = warps): 2 or 4
-#endif
+// Two arithmetic modes share the kernel (template parameter MODE):
+//   G3_X3 (RLC_PREC_FP16X3): z = h_hi.W_hi + h_lo.W_hi + h_hi.W_lo, all fp16 (kind::f16, K = 16 per MMA) -- fp32-class, 1e-5.
+//   G3_C8 (RLC_PREC_FP16C8): the two correction terms on the FP8 pipe (kind::f8f6f4, K = 32 per MMA, twice the rate):
+//          z = h_hi.W_hi [fp16] + e4m3(2^9 h_lo).e4m3(2^-9 W_hi) + e5m2(h_hi).e4m3(W_lo)
+//          a correction only needs ~4 bits of its own (it is 2^-12 of the product): 2e-4 max of the exact Q on cfg4
+//          (oracle_np.tin_eval_rounded(head="grid3c8")), 2/3 of the tensor-pipe time of G3_X3.
+#define G3_X3 0
+#define G3_C8 1
+#define G3_E2G 4             // epilogue-2 column groups (x 4 lane quarters = 16 warps)
+__host__ __device__ constexpr int g3_e1w(int mode) { return mode == G3_C8 ? 8 : 4; }   // epilogue-1 warps (C8 builds 3 operands)
+__host__ __device__ constexpr int g3_threads(int mode) { return 32 * (4 + g3_e1w(mode) + 4 * G3_E2G); }
+#define G3_E1W g3_e1w(MODE)
 #define G3_W2_0 (4 + G3_E1W) // first epilogue-2 warp
-#define G3_THREADS (32 * (4 + G3_E1W + 4 * G3_E2G))
+#define G3_THREADS g3_threads(MODE)
+#define G3_C8_SA 9           // C8: h_lo is scaled by 2^SA into e4m3's normal range, W_hi by 2^-SA (W' < 2^10 by construction)
+#define G3_C8_SB 0           // C8: W_lo and the e5m2 copy of h are used unscaled (e5m2 has fp16's range; W_lo < 2^-2 by construction)
+#define G3_RANGE_LIMIT_C8 500.f   // C8: |h_lo| 2^9 must stay below e4m3's 448: |PS|, |PA| <= 500 -> h < 1024, h_lo <= 0.25
 #define G3_MAX_NP 5          // accumulator column parts
 #define G3_VR (G3_E2G >= 4 ? 48 : 64)   // accumulator columns an epilogue-2 thread holds per part
 #define G3_MAX_NCH 8
@@ -67,7 +76,8 @@ struct Grid3Params {
   const float* ps;            // [B][H1P] fp32, PS[b][H1] = 1 (bias carrier of layer 2)
   const float* pa;            // [nch][NT*32][KC+PAD] fp32, zero rows past N
   const unsigned char* blob[2];
-  int off_hi, off_lo, off_c0;
+  int off_hi, off_lo, off_c0;   // X3: fp16 hi | fp16 lo;  C8: fp16 hi | [e4m3 hi8 | e4m3 lo8] starting at off_lo
+  int w8_bytes;                 // C8: bytes of one e4m3 weight chunk of KC features = (KC/16) * lbo
   int lbo;                    // bytes between consecutive K groups of 8 in a weight blob = (H2P/2)*16
   int w_stages, pa_stages;
   int resident_hi;            // 1: W_hi stays in shared memory for the whole kernel (sm_whi), only W_lo streams
@@ -81,10 +91,9 @@ struct Grid3Params {
 };
 
 enum {
-  B3_PA_FULL = 0,     // [4]  count 1 + tx  (local)   table loader -> ep1
+  B3_PA_FULL = 0,     // [4]  count 1 + tx  (local)   table loader -> ep1 (PA tile + PS slices of one chunk)
   B3_PA_EMPTY = 4,    // [4]  count E1W     (local)   ep1 warps -> table loader
-  B3_PS_FULL = 8,     // [2]  count 1 + tx  (local)
-  B3_PS_EMPTY = 10,   // [2]  count E1W     (local)
+                      // slots 8..11 unused (the PS rows travel with the PA tile of each chunk)
   B3_W_FULL = 12,     // [4]  count 1 + tx  (local)   weight loader -> relay
   B3_W_EMPTY = 16,    // [4]  count 1       (both)    MMA commit -> weight loaders
   B3_W_READY = 20,    // [4]  count 2       (leader)  relay of each CTA -> MMA
@@ -101,7 +110,7 @@ __global__ void __launch_bounds__(128)
 k_grid3_parts(const float* __restrict__ theta, const float* __restrict__ s, const float* __restrict__ a,
               const float* __restrict__ smin, const float* __restrict__ smax, int B, int N, int S, int A, int H1, int H2,
               int H1P, int KC, Grid3Chunks ch, int NT, int state_groups, float* __restrict__ PS,
-              float* __restrict__ PA, int* __restrict__ err) {
+              float* __restrict__ PA, int* __restrict__ err, float limit) {
   extern __shared__ float xs[];                               // [GR_PRE_ROWS][K]
   const ThetaView t = theta_view(RLC_TIN, S, A, H1, H2);
   const float* W1 = theta + t.oW1;   // [S+A][H1]
@@ -140,7 +149,7 @@ k_grid3_parts(const float* __restrict__ theta, const float* __restrict__ s, cons
     for (int r = 0; r < GR_PRE_ROWS; ++r)
       if (r0 + r < B) {
         const float v = (j == H1) ? 1.f : acc[r];
-        bad = bad || !(fabsf(v) <= G3_RANGE_LIMIT);
+        bad = bad || !(fabsf(v) <= limit);
         PS[(size_t)(r0 + r) * H1P + j] = v;
       }
   } else {
@@ -153,7 +162,7 @@ k_grid3_parts(const float* __restrict__ theta, const float* __restrict__ s, cons
       const int n = r0 + r;                                   // 0 .. NT*32-1 (rows past N are zero)
       if (n < NT * 32) {
         const float v = (j < H1 && n < N) ? acc[r] : 0.f;
-        bad = bad || !(fabsf(v) <= G3_RANGE_LIMIT);
+        bad = bad || !(fabsf(v) <= limit);
         PA[((size_t)c * NT * 32 + n) * pitch + jj] = v;
       }
     }
@@ -164,7 +173,7 @@ k_grid3_parts(const float* __restrict__ theta, const float* __restrict__ s, cons
 // Weight pack for the split mode: W' = fl32(sw_j * W2[k][j]) (bias row k = H1: sw_j * b2_j), sw_j = scale |w3_j| with the
 // column permutation and `scale` written by k_pack_head + k_pack_scale3;  hi = r16(W'), lo = r16(W' - hi).  Same
 // no-swizzle K-major core-matrix layout and pair split as k_pack_umma's W2 region.
-__global__ void k_pack_x3(const float* __restrict__ theta, PackGeom G, Grid3Parts parts, unsigned char* blob0,
+__global__ void k_pack_x3(const float* __restrict__ theta, PackGeom G, Grid3Parts parts, int mode, unsigned char* blob0,
                           unsigned char* blob1) {
   const ThetaView t = theta_view(RLC_TIN, G.S, G.A, G.H1, G.H2);
   const float* W2 = theta + t.oW2;   // [H1][H2]
@@ -186,11 +195,20 @@ __global__ void k_pack_x3(const float* __restrict__ theta, PackGeom G, Grid3Part
   }
   v = fminf(fmaxf(v, -65504.f), 65504.f);
   const __half hi = __float2half_rn(v);
-  const __half lo = __float2half_rn(v - __half2float(hi));
   unsigned char* blob = rank ? blob1 : blob0;
-  const long long off = (long long)(k / 8) * ((G.H2P / 2) * 16) + (long long)(l / 8) * 128 + (l % 8) * 16 + (k % 8) * 2;
+  const long long lbo = (G.H2P / 2) * 16;
+  const long long off = (long long)(k / 8) * lbo + (long long)(l / 8) * 128 + (l % 8) * 16 + (k % 8) * 2;
   *reinterpret_cast<__half*>(blob + G.off_w2 + off) = hi;
-  *reinterpret_cast<__half*>(blob + G.off_w1 + off) = lo;     // off_w1 = start of the lo region in this geometry
+  if (mode == G3_X3) {
+    *reinterpret_cast<__half*>(blob + G.off_w1 + off) = __float2half_rn(v - __half2float(hi));   // off_w1 = lo region
+  } else {
+    // 8-bit operands: same core-matrix layout with 16 K-elements per 16-byte row; [hi8 | lo8] after the fp16 region
+    const long long off8 = (long long)(k / 16) * lbo + (long long)(l / 8) * 128 + (l % 8) * 16 + (k % 16);
+    const long long sz8 = (long long)(G.H1P / 16) * lbo;
+    blob[G.off_w1 + off8] = (unsigned char)__nv_cvt_float_to_fp8(ldexpf(__half2float(hi), -G3_C8_SA), __NV_SATFINITE, __NV_E4M3);
+    blob[G.off_w1 + sz8 + off8] =
+        (unsigned char)__nv_cvt_float_to_fp8(ldexpf(v - __half2float(hi), G3_C8_SB), __NV_SATFINITE, __NV_E4M3);
+  }
 }
 
 // Extra power-of-two column scale of the split mode: 2^e2 with 2^e2 * max(|W2|, |b2|) in [2^8, 2^9), so that W' < 2^10
@@ -238,6 +256,37 @@ __device__ __forceinline__ void issue_half3(uint32_t d, uint32_t a_hi, uint32_t 
     mma2_ts_acc(d, a_hi + 8u * (uint32_t)k, desc64(bl + (uint32_t)k * kstep), idesc);
   }
 }
+// D[tmem] += A[tmem] * B[smem]^T on the FP8 pipe (kind::f8f6f4, K = 32 per instruction; operand formats in idesc)
+__device__ __forceinline__ void mma2_ts_f8(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.eq.b32 p, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t make_idesc_ab(uint32_t afmt, uint32_t bfmt, int M, int N) {
+  return (1u << 4) | (afmt << 7) | (bfmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// One accumulator part of one K chunk in C8 mode: KS K=16 steps of the fp16 product, then KS/2 K=32 steps of each FP8
+// correction (a_lo8 x b_hi8: e4m3 x e4m3;  a_hi8 x b_lo8: e5m2 x e4m3).
+template <int KS>
+__device__ __forceinline__ void issue_part_c8(uint32_t d, uint32_t a_hi, uint32_t a_lo8, uint32_t a_hi8, uint32_t b16,
+                                              uint32_t b_hi8, uint32_t b_lo8, uint32_t kstep, uint32_t id16, uint32_t id_t2,
+                                              uint32_t id_t3, uint32_t acc0) {
+  mma2_ts(d, a_hi, desc64(b16), id16, acc0);
+#pragma unroll
+  for (int k = 1; k < KS; ++k) mma2_ts_acc(d, a_hi + 8u * (uint32_t)k, desc64(b16 + (uint32_t)k * kstep), id16);
+#pragma unroll
+  for (int k = 0; k < KS / 2; ++k) mma2_ts_f8(d, a_lo8 + 8u * (uint32_t)k, desc64(b_hi8 + (uint32_t)k * kstep), id_t2);
+#pragma unroll
+  for (int k = 0; k < KS / 2; ++k) mma2_ts_f8(d, a_hi8 + 8u * (uint32_t)k, desc64(b_lo8 + (uint32_t)k * kstep), id_t3);
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
+               : "memory");
+}
 }  // namespace um
 
 // relu_signed_round for at most G3_VR = 64 columns held in registers (all indices static).
@@ -269,7 +318,40 @@ __device__ __forceinline__ void relu_signed_round8(const uint32_t* v, int w, int
   }
 }
 
-template <bool PROF>
+// Epilogue 1, one unit of 16 activations of one row: h = relu(PS + PA) in fp32 (one add), hi = fp16(h) packed in 8 cells;
+// X3: lo[0..7] = fp16(h - hi) cells;  C8: lo[0..3] = e4m3(2^SA (h - hi)) cells, lo[4..7] = e5m2(hi) cells.
+template <int MODE>
+__device__ __forceinline__ void ep1_unit(const float4* __restrict__ pa4, const float4* __restrict__ ps4, int u, uint32_t* hi,
+                                         uint32_t* lo) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float4 x = pa4[u * 4 + g];
+    const float4 y = ps4[u * 4 + g];
+    const float v0 = fmaxf(x.x + y.x, 0.f), v1 = fmaxf(x.y + y.y, 0.f);
+    const float v2 = fmaxf(x.z + y.z, 0.f), v3 = fmaxf(x.w + y.w, 0.f);
+    const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    hi[g * 2 + 0] = *reinterpret_cast<const uint32_t*>(&h01);
+    hi[g * 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+    if (MODE == G3_C8) {
+      constexpr float SA = (float)(1 << G3_C8_SA);
+      const uint32_t l01 = __nv_cvt_float2_to_fp8x2(make_float2((v0 - f01.x) * SA, (v1 - f01.y) * SA), __NV_SATFINITE, __NV_E4M3);
+      const uint32_t l23 = __nv_cvt_float2_to_fp8x2(make_float2((v2 - f23.x) * SA, (v3 - f23.y) * SA), __NV_SATFINITE, __NV_E4M3);
+      lo[g] = l01 | (l23 << 16);                      // four consecutive K elements per 32-bit cell, lowest first
+      // e5m2 IS the upper byte of fp16 (same sign and exponent fields, 2 of the 10 mantissa bits): round h_hi to it with
+      // one packed integer add (+half an e5m2 ulp; h >= 0 and finite, so no carry crosses a half) and pick the four upper
+      // bytes -- no FP8 conversion instruction (they are the slow ones) and no scaling of h
+      lo[4 + g] = __byte_perm(hi[g * 2 + 0] + 0x00800080u, hi[g * 2 + 1] + 0x00800080u, 0x7531);
+    } else {
+      const __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y);
+      const __half2 l23 = __floats2half2_rn(v2 - f23.x, v3 - f23.y);
+      lo[g * 2 + 0] = *reinterpret_cast<const uint32_t*>(&l01);
+      lo[g * 2 + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+    }
+  }
+}
+
+template <bool PROF, int MODE>
 __global__ void __launch_bounds__(G3_THREADS, 1) k_critic_umma_grid3(const Grid3Params P) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_addr = um::smem_u32(smem_raw);
@@ -281,7 +363,7 @@ __global__ void __launch_bounds__(G3_THREADS, 1) k_critic_umma_grid3(const Grid3
   const uint32_t pair = um::cluster_id_x();
   const uint32_t npairs = um::num_clusters_x();
 
-  const uint32_t sW = base + P.sm_w, sPA = base + P.sm_pa, sPS = base + P.sm_ps, sBar = base + P.sm_bar;
+  const uint32_t sW = base + P.sm_w, sPA = base + P.sm_pa, sBar = base + P.sm_bar;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + P.sm_bar + B3_COUNT * 8);
   float* qpart = reinterpret_cast<float*>(base_ptr + P.sm_qp);   // [2][E2G-1][128] partial sums
   auto bar = [&](int i) -> uint32_t { return sBar + 8u * (uint32_t)i; };
@@ -298,10 +380,6 @@ __global__ void __launch_bounds__(G3_THREADS, 1) k_critic_umma_grid3(const Grid3
       um::mbar_init(bar(B3_W_FULL + i), 1);
       um::mbar_init(bar(B3_W_EMPTY + i), 1);
       um::mbar_init(bar(B3_W_READY + i), 2);
-    }
-    for (int i = 0; i < 2; ++i) {
-      um::mbar_init(bar(B3_PS_FULL + i), 1);
-      um::mbar_init(bar(B3_PS_EMPTY + i), G3_E1W);
     }
     for (int i = 0; i < G3_MAX_NP; ++i) {
       um::mbar_init(bar(B3_L2_FULL + i), 1);
@@ -381,7 +459,9 @@ __global__ void __launch_bounds__(G3_THREADS, 1) k_critic_umma_grid3(const Grid3
           const uint32_t a_lo = a_hi + alo;
           const uint32_t b_st = um::desc_lo(sW + ws * (uint32_t)P.w_stage_bytes, lbo);
           const uint32_t b_hi = P.resident_hi ? whi_lo + (uint32_t)(P.ch.start[c] >> 3) * (lbo >> 4) : b_st;
-          const uint32_t b_lo = P.resident_hi ? b_st : b_st + lo_off;
+          const uint32_t b_lo = P.resident_hi ? b_st : b_st + lo_off;     // X3: fp16 lo chunk; C8: e4m3 hi8 chunk, lo8 after it
+          const uint32_t b_lo8 = b_lo + ((uint32_t)P.w8_bytes >> 4);
+          const uint32_t a_hi8 = a_lo + (uint32_t)(KC >> 2);              // C8 slot: [hi16 KC/2 | lo8 KC/4 | hi8 KC/4] columns
           const uint32_t acc0 = c > 0 ? 1u : 0u;
 #pragma unroll 1
           for (int p = 0; p < np && ok; ++p) {
@@ -397,6 +477,15 @@ __global__ void __launch_bounds__(G3_THREADS, 1) k_critic_umma_grid3(const Grid3
               const int pb0 = P.parts.base[p], pw = P.parts.base[p + 1] - pb0;
               const uint32_t d = tmem_base + (uint32_t)pb0, idesc = um::make_idesc(0u, 256, pw);
               const uint32_t bh = b_hi + (uint32_t)(pb0 >> 1), bl = b_lo + (uint32_t)(pb0 >> 1);
+              if (MODE == G3_C8) {
+                const uint32_t id_t2 = um::make_idesc_ab(0u, 0u, 256, pw), id_t3 = um::make_idesc_ab(1u, 0u, 256, pw);
+                const uint32_t bl8 = b_lo8 + (uint32_t)(pb0 >> 1);
+                switch (ksteps) {
+                  case 6: um::issue_part_c8<6>(d, a_hi, a_lo, a_hi8, bh, bl, bl8, kstep, idesc, id_t2, id_t3, acc0); break;
+                  case 4: um::issue_part_c8<4>(d, a_hi, a_lo, a_hi8, bh, bl, bl8, kstep, idesc, id_t2, id_t3, acc0); break;
+                  default: um::issue_part_c8<2>(d, a_hi, a_lo, a_hi8, bh, bl, bl8, kstep, idesc, id_t2, id_t3, acc0); break;
+                }
+              } else
               switch (ksteps) {
                 case 6: um::issue_half3<6>(d, a_hi, a_lo, bh, bl, kstep, idesc, acc0); break;
                 case 5: um::issue_half3<5>(d, a_hi, a_lo, bh, bl, kstep, idesc, acc0); break;
@@ -437,32 +526,30 @@ __global__ void __launch_bounds__(G3_THREADS, 1) k_critic_umma_grid3(const Grid3
       bool ok = true;
       const int pitch_b = (KC + G3_PA_PAD) * 4;
       const uint32_t pa_tile_bytes = 32u * (uint32_t)pitch_b;
-      const uint32_t ps_row_bytes = (uint32_t)P.H1P * 4u;
       const size_t pa_chunk_stride = (size_t)P.NT * 32 * pitch_b;   // bytes between chunks in PA
       uint32_t st = 0, spar = 0;
       for (int tl = 0; tl < ntiles && ok; ++tl) {
         int b0, n0;
         tile_coords(tl, b0, n0);
-        const int pb = tl & 1;
-        ok = um::mbar_wait(bar(B3_PS_EMPTY + pb), (uint32_t)(((tl >> 1) & 1) ^ 1), P.err, 51);
-        if (!ok) break;
-        if (P.micro & 2) { um::mbar_arrive_local(bar(B3_PS_FULL + pb)); }
-        else um::mbar_expect_tx(bar(B3_PS_FULL + pb), 4u * ps_row_bytes);
-        for (int i = 0; i < 4 && !(P.micro & 2); ++i) {
-          const int b = (b0 + i < P.B) ? b0 + i : P.B - 1;
-          um::bulk_g2s(sPS + (uint32_t)(pb * P.ps_stage_bytes) + (uint32_t)i * ps_row_bytes,
-                       reinterpret_cast<const unsigned char*>(P.ps) + (size_t)b * ps_row_bytes, ps_row_bytes,
-                       bar(B3_PS_FULL + pb));
-        }
         for (int c = 0; c < nch && ok; ++c) {
           ok = um::mbar_wait(bar(B3_PA_EMPTY + (int)st), spar ^ 1u, P.err, 52);
           if (!ok) break;
-          if (P.micro & 2) um::mbar_arrive_local(bar(B3_PA_FULL + (int)st));
-          else um::mbar_expect_tx(bar(B3_PA_FULL + (int)st), pa_tile_bytes);
-          if (!(P.micro & 2)) um::bulk_g2s(sPA + st * (uint32_t)P.pa_stage_bytes,
-                       reinterpret_cast<const unsigned char*>(P.pa) + (size_t)c * pa_chunk_stride +
-                           (size_t)n0 * pitch_b,
-                       pa_tile_bytes, bar(B3_PA_FULL + (int)st));
+          // one stage = the chunk's PA tile (32 actions) + the chunk's slice of the 4 PS rows (4 x width floats)
+          const uint32_t ps_slice = (uint32_t)P.ch.width[c] * 4u;
+          const uint32_t dst = sPA + st * (uint32_t)P.pa_stage_bytes;
+          if (P.micro & 2) {
+            um::mbar_arrive_local(bar(B3_PA_FULL + (int)st));
+          } else {
+            um::mbar_expect_tx(bar(B3_PA_FULL + (int)st), pa_tile_bytes + 4u * ps_slice);
+            um::bulk_g2s(dst, reinterpret_cast<const unsigned char*>(P.pa) + (size_t)c * pa_chunk_stride + (size_t)n0 * pitch_b,
+                         pa_tile_bytes, bar(B3_PA_FULL + (int)st));
+            for (int i = 0; i < 4; ++i) {
+              const int b = (b0 + i < P.B) ? b0 + i : P.B - 1;
+              um::bulk_g2s(dst + pa_tile_bytes + (uint32_t)i * (uint32_t)(KC * 4),
+                           reinterpret_cast<const unsigned char*>(P.ps) + ((size_t)b * P.H1P + (size_t)P.ch.start[c]) * 4,
+                           ps_slice, bar(B3_PA_FULL + (int)st));
+            }
+          }
           if (++st == past_n) { st = 0; spar ^= 1u; }
         }
       }
@@ -483,6 +570,15 @@ __global__ void __launch_bounds__(G3_THREADS, 1) k_critic_umma_grid3(const Grid3
           const uint32_t dst = sW + ws * (uint32_t)P.w_stage_bytes;
           if (P.micro & 2) {
             um::mbar_arrive_local(bar(B3_W_FULL + (int)ws));
+          } else if (MODE == G3_C8) {
+            // [fp16 hi chunk unless resident] [e4m3 hi8 chunk] [e4m3 lo8 chunk]; the 8-bit regions follow each other in the blob
+            const uint32_t b8 = bytes >> 1;
+            const size_t src8 = src >> 1, sz8 = (size_t)(P.H1P >> 4) * (size_t)P.lbo;
+            const uint32_t d8 = dst + (P.resident_hi ? 0u : (uint32_t)P.w_half_bytes);
+            um::mbar_expect_tx(bar(B3_W_FULL + (int)ws), (P.resident_hi ? 0u : bytes) + 2u * b8);
+            if (!P.resident_hi) um::bulk_g2s(dst, whi + src, bytes, bar(B3_W_FULL + (int)ws));
+            um::bulk_g2s(d8, wlo + src8, b8, bar(B3_W_FULL + (int)ws));
+            um::bulk_g2s(d8 + (uint32_t)P.w8_bytes, wlo + sz8 + src8, b8, bar(B3_W_FULL + (int)ws));
           } else if (P.resident_hi) {
             um::mbar_expect_tx(bar(B3_W_FULL + (int)ws), bytes);
             um::bulk_g2s(dst, wlo + src, bytes, bar(B3_W_FULL + (int)ws));
@@ -538,46 +634,37 @@ __global__ void __launch_bounds__(G3_THREADS, 1) k_critic_umma_grid3(const Grid3
     bool ok = true;
     uint32_t st = 0, ppar = 0, slot = 0, spar = 0;
     for (int tl = 0; tl < ntiles && ok; ++tl) {
-      const int pb = tl & 1;
-      ok = um::mbar_wait(bar(B3_PS_FULL + pb), (uint32_t)((tl >> 1) & 1), P.err, 33);
-      if (!ok) break;
-      const unsigned char* ps_row = base_ptr + P.sm_ps + pb * P.ps_stage_bytes + q4 * (P.H1P * 4);
       for (int c = 0; c < nch; ++c) {
         long long t0 = G3T();
         ok = um::mbar_wait(bar(B3_PA_FULL + (int)st), ppar, P.err, 31);
+        if (!ok) break;
         long long t1 = G3T();
-        ok = ok && um::mbar_wait(bar(B3_H1_EMPTY + (int)slot), spar ^ 1u, P.err, 32);
+        const int nunit = P.ch.width[c] >> 4;
+        const int ub = nunit * cg / (G3_E1W / 4), ue = nunit * (cg + 1) / (G3_E1W / 4);
+        const float4* pa4 = reinterpret_cast<const float4*>(base_ptr + P.sm_pa + st * P.pa_stage_bytes + lane * pitch_b);
+        const float4* ps4 = reinterpret_cast<const float4*>(base_ptr + P.sm_pa + st * P.pa_stage_bytes + 32 * pitch_b +
+                                                            q4 * (KC * 4));
+        const uint32_t tcol = lane_addr + SLOT0 + slot * (uint32_t)KC;
+        ok = um::mbar_wait(bar(B3_H1_EMPTY + (int)slot), spar ^ 1u, P.err, 32);
         if (!ok) break;
         um::tc_fence_after();
         long long t2 = G3T();
         pa_ += t1 - t0;
         pb_ += t2 - t1;
         if (tid == 128) G3TR(1, tl, c * 10 + 1);        // slot free + PA here: start building
-        const int nunit = P.ch.width[c] >> 4;
-        const int ub = nunit * cg / (G3_E1W / 4), ue = nunit * (cg + 1) / (G3_E1W / 4);
-        const float4* pa4 = reinterpret_cast<const float4*>(base_ptr + P.sm_pa + st * P.pa_stage_bytes + lane * pitch_b);
-        const float4* ps4 = reinterpret_cast<const float4*>(ps_row + P.ch.start[c] * 4);
-        const uint32_t tcol = lane_addr + SLOT0 + slot * (uint32_t)KC;
+        // (Measured alternative for C8: computing the warp's share into registers BEFORE the slot is free and only storing
+        // afterwards -- 48 live registers per thread at the 72-register budget of 896 threads: spills, 1.58 vs 1.48 ms.)
 #pragma unroll 1
-        for (int u = ub; u < ue && !(P.micro & 4); ++u) {   // 16 activations -> 8 packed hi cells + 8 packed lo cells
+        for (int u = ub; u < ue && !(P.micro & 4); ++u) {   // 16 activations -> 8 packed hi cells + the lo operand cells
           uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const float4 x = pa4[u * 4 + g];
-            const float4 y = ps4[u * 4 + g];
-            const float v0 = fmaxf(x.x + y.x, 0.f), v1 = fmaxf(x.y + y.y, 0.f);
-            const float v2 = fmaxf(x.z + y.z, 0.f), v3 = fmaxf(x.w + y.w, 0.f);
-            const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
-            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-            const __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y);
-            const __half2 l23 = __floats2half2_rn(v2 - f23.x, v3 - f23.y);
-            hi[g * 2 + 0] = *reinterpret_cast<const uint32_t*>(&h01);
-            hi[g * 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
-            lo[g * 2 + 0] = *reinterpret_cast<const uint32_t*>(&l01);
-            lo[g * 2 + 1] = *reinterpret_cast<const uint32_t*>(&l23);
-          }
+          ep1_unit<MODE>(pa4, ps4, u, hi, lo);
           um::tmem_st8(tcol + (uint32_t)(u * 8), hi);
-          um::tmem_st8(tcol + alo + (uint32_t)(u * 8), lo);
+          if (MODE == G3_C8) {
+            um::tmem_st4(tcol + alo + (uint32_t)(u * 4), lo);
+            um::tmem_st4(tcol + alo + (uint32_t)(KC >> 2) + (uint32_t)(u * 4), lo + 4);
+          } else {
+            um::tmem_st8(tcol + alo + (uint32_t)(u * 8), lo);
+          }
         }
         __syncwarp();
         if (lane == 0) um::mbar_arrive_local(bar(B3_PA_EMPTY + (int)st));   // PA stage consumed
@@ -592,8 +679,6 @@ __global__ void __launch_bounds__(G3_THREADS, 1) k_critic_umma_grid3(const Grid3
         if (++st == past_n) { st = 0; ppar ^= 1u; }
         if (++slot == nslot) { slot = 0; spar ^= 1u; }
       }
-      __syncwarp();
-      if (lane == 0) um::mbar_arrive_local(bar(B3_PS_EMPTY + pb));
     }
     if (prof && rank == 0 && tid == 128) {
       long long* o = P.prof + (size_t)pair * 32 + 8; o[0] = pa_; o[1] = pb_; o[2] = pc_; o[3] = pd_;
@@ -686,8 +771,13 @@ struct Grid3Plan {
   int sm_w, sm_pa, sm_ps, sm_qp, sm_bar, w_stage, w_half, pa_stage, ps_stage, total;
 };
 
-static bool make_geom3(const rlc_critic* c, PackGeom& G) {
+static bool make_geom3(const rlc_critic* c, PackGeom& G, int mode = G3_X3) {
   if (!make_geom(c, G, 1)) return false;
+  if (mode == G3_C8) {          // kind::f8f6f4: K = 32 per MMA, N a multiple of 32 at M = 256
+    G.H1P = (c->H1 + 1 + 31) & ~31;
+    G.H2P = (c->H2 + 31) & ~31;
+    if (G.H2P > 480) return false;
+  }
   const int sz = (G.H1P / 8) * (G.H2P / 2) * 16;
   G.CH = 0; G.nch = 0;                 // the split pack does not depend on the chunking (no W1 region)
   G.off_w2 = 0;                        // hi
@@ -700,9 +790,11 @@ static bool make_geom3(const rlc_critic* c, PackGeom& G) {
 }
 
 // Accumulator column parts: as few as possible, widths multiples of 16 as even as possible (304 -> 160 + 144).
-static bool make_parts3(int H2P, Grid3Parts& pt) {
+static bool make_parts3(int H2P, Grid3Parts& pt, int mode = G3_X3) {
   memset(&pt, 0, sizeof(pt));
-  const int units = H2P / 16;
+  const int U = mode == G3_C8 ? 32 : 16;            // part widths: multiples of 16 (kind::f16) or 32 (kind::f8f6f4)
+  if (H2P % U) return false;
+  const int units = H2P / U;
   int np = (H2P + 191) / 192;                     // fewest parts an epilogue-2 thread can hold (wider MMAs are more efficient)
   {
     const char* e = getenv("RLC_G3_NP");          // tuning knob: number of accumulator parts
@@ -712,7 +804,7 @@ static bool make_parts3(int H2P, Grid3Parts& pt) {
   if (np < 1 || np > G3_MAX_NP) return false;
   int b = 0;
   for (int p = 0; p < np; ++p) {
-    const int w = 16 * (units / np + (p < units % np ? 1 : 0));
+    const int w = U * (units / np + (p < units % np ? 1 : 0));
     if (w > G3_E2G * G3_VR || w > 256) return false;
     pt.base[p] = b;
     b += w;
@@ -722,35 +814,36 @@ static bool make_parts3(int H2P, Grid3Parts& pt) {
   return b == H2P;
 }
 
-static bool plan_grid3(const PackGeom& G, size_t smem_limit, Grid3Plan& p) {
+static bool plan_grid3(const PackGeom& G, size_t smem_limit, Grid3Plan& p, int mode = G3_X3) {
   memset(&p, 0, sizeof(p));
-  if (!make_parts3(G.H2P, p.parts)) return false;
-  int kc = ((512 - G.H2P) / 2) & ~15;
+  if (!make_parts3(G.H2P, p.parts, mode)) return false;
+  const int CU = mode == G3_C8 ? 32 : 16;           // chunk widths: multiples of one MMA's K
+  int kc = ((512 - G.H2P) / 2) & ~(CU - 1);
   if (kc > 96) kc = 96;
   {
     const char* e = getenv("RLC_G3_KC");          // tuning knob: chunk width
-    if (e) { const int v = atoi(e); if (v >= 16 && v <= kc && (v & 15) == 0) kc = v; }
+    if (e) { const int v = atoi(e); if (v >= CU && v <= kc && (v % CU) == 0) kc = v; }
   }
   if (kc > G.H1P) kc = G.H1P;
-  if (kc < 16) return false;
+  if (kc < CU) return false;
   p.KC = kc;
   p.nslot = (512 - G.H2P) / kc;
   if (p.nslot > G3_MAX_SLOT) p.nslot = G3_MAX_SLOT;
   if (p.nslot < 2) return false;
   // chunks: ceil(H1P / KC) of them, the 16-feature units spread evenly (416 -> 96 + 4 x 80): no chunk's MMAs are
   // much shorter than the time epilogue 1 needs to build the next one
-  const int units = G.H1P / 16, n = (G.H1P + kc - 1) / kc;
+  const int units = G.H1P / CU, n = (G.H1P + kc - 1) / kc;
   if (n > G3_MAX_NCH) return false;
   for (int i = 0, f = 0; i < n; ++i) {
-    const int w = 16 * (units / n + (i < units % n ? 1 : 0));
+    const int w = CU * (units / n + (i < units % n ? 1 : 0));
     p.ch.start[i] = f; p.ch.width[i] = w; f += w;
   }
   p.ch.nch = n;
   const int lbo = (G.H2P / 2) * 16;
   p.w_half = (kc / 8) * lbo;
-  p.pa_stage = 32 * (kc + G3_PA_PAD) * 4;
-  p.ps_stage = 4 * G.H1P * 4;
-  const int tail = 128 * 4 * 2 * (G3_E2G - 1) + B3_COUNT * 8 + 16 + 1024 + 256;
+  p.pa_stage = 32 * (kc + G3_PA_PAD) * 4 + 4 * kc * 4;     // PA tile + the chunk's slice of the tile's 4 PS rows
+  p.ps_stage = 0;
+  const int tail = 128 * 4 * 2 * (G3_E2G - 1) + B3_COUNT * 8 + 16 + 1024;
   p.whi_bytes = (G.H1P / 8) * lbo;
   // Preferred: W_hi resident, only W_lo streams (half the bulk-copy writes into shared memory, whose bandwidth the
   // tensor core's operand reads need); otherwise both stream.  Stage counts: as deep as fits, weights first.
@@ -762,10 +855,12 @@ static bool plan_grid3(const PackGeom& G, size_t smem_limit, Grid3Plan& p) {
   }
   bool found = false;
   for (int res = mode_res; res >= 0 && !found; --res) {
+    // per stage: X3 = [fp16 hi unless resident | fp16 lo];  C8 = [fp16 hi unless resident | e4m3 hi8 | e4m3 lo8] (2 x w_half / 2)
     const int wst = res ? p.w_half : 2 * p.w_half;
     for (int i = 0; i < 4 && !found; ++i) {
-      const long long need = (long long)(res ? p.whi_bytes : 0) + (long long)combos[i][0] * wst +
-                             (long long)combos[i][1] * p.pa_stage + 2 * p.ps_stage + tail;
+      long long need = (long long)(res ? p.whi_bytes : 0) + (long long)combos[i][0] * wst +
+                       (long long)combos[i][1] * p.pa_stage;
+      need = ((need + 127) & ~127ll) + tail;           // exactly the carve below
       if (need <= (long long)smem_limit) {
         p.resident_hi = res; p.w_stage = wst; p.w_stages = combos[i][0]; p.pa_stages = combos[i][1];
         found = true;
@@ -776,38 +871,42 @@ static bool plan_grid3(const PackGeom& G, size_t smem_limit, Grid3Plan& p) {
   p.sm_whi = 0;
   p.sm_w = p.resident_hi ? p.whi_bytes : 0;
   p.sm_pa = p.sm_w + p.w_stages * p.w_stage;
-  p.sm_ps = p.sm_pa + p.pa_stages * p.pa_stage;
-  p.sm_qp = (p.sm_ps + 2 * p.ps_stage + 127) & ~127;
+  p.sm_ps = 0;
+  p.sm_qp = (p.sm_pa + p.pa_stages * p.pa_stage + 127) & ~127;
   p.sm_bar = p.sm_qp + 2 * 128 * 4 * (G3_E2G - 1);
   p.total = p.sm_bar + B3_COUNT * 8 + 16 + 1024;
   return (size_t)p.total <= smem_limit;
 }
 
-static int launch_pack_x3(rlc_handle* h, const float* theta, const PackGeom& G, unsigned char* b0, unsigned char* b1,
-                          cudaStream_t st) {
+static int launch_pack_x3(rlc_handle* h, const float* theta, const PackGeom& G, int mode, unsigned char* b0,
+                          unsigned char* b1, cudaStream_t st) {
   Grid3Parts pt;
-  if (!make_parts3(G.H2P, pt)) return RLC_ERR_UNSUPPORTED;
+  if (!make_parts3(G.H2P, pt, mode)) return RLC_ERR_UNSUPPORTED;
   const long long n3 = (long long)G.H1P * G.H2P;
-  k_pack_x3<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(theta, G, pt, b0, b1);
+  k_pack_x3<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(theta, G, pt, mode, b0, b1);
   (void)h;
   return RLC_OK;
 }
 
-bool rlc_umma3_supported(const rlc_handle* h, const rlc_critic* c) {
+static inline int g3_mode_of(int prec) { return prec == RLC_PREC_FP16C8 ? G3_C8 : G3_X3; }
+
+bool rlc_umma3_supported(const rlc_handle* h, const rlc_critic* c, int prec) {
   if (h->sm_major != 10 || c->topology != RLC_TIN) return false;
   PackGeom G;
   Grid3Plan gp;
-  return make_geom3(c, G) && plan_grid3(G, h->smem_optin, gp);
+  const int mode = g3_mode_of(prec);
+  return make_geom3(c, G, mode) && plan_grid3(G, h->smem_optin, gp, mode);
 }
 
 static int rlc_eval_umma_grid3(rlc_handle* h, const rlc_critic* c, const float* s, int B, const float* a, int N,
-                               float* q_out, cudaStream_t st) {
+                               int prec, float* q_out, cudaStream_t st) {
   PackGeom G;
   Grid3Plan gp;
-  if (!make_geom3(c, G) || !plan_grid3(G, h->smem_optin, gp)) return RLC_ERR_UNSUPPORTED;
+  const int mode = g3_mode_of(prec);
+  if (!make_geom3(c, G, mode) || !plan_grid3(G, h->smem_optin, gp, mode)) return RLC_ERR_UNSUPPORTED;
   if ((long long)B * N >= (1ll << 31)) return RLC_ERR_UNSUPPORTED;
   rlc_pack* pk = nullptr;
-  int rc = get_pack(h, c, RLC_PREC_FP16X3, G, st, &pk);
+  int rc = get_pack(h, c, prec, G, st, &pk);
   if (rc) return rc;
   const int NT = (N + 31) / 32;
   const int pitch = gp.KC + G3_PA_PAD;
@@ -822,7 +921,8 @@ static int rlc_eval_umma_grid3(rlc_handle* h, const rlc_critic* c, const float* 
     const dim3 blocks((unsigned)(sg + ag), (unsigned)((G.H1P + 127) / 128));
     const size_t pre_smem = (size_t)GR_PRE_ROWS * (c->S > c->A ? c->S : c->A) * sizeof(float);
     k_grid3_parts<<<blocks, 128, pre_smem, st>>>(c->theta, s, a, c->smin, c->smax, B, N, c->S, c->A, c->H1, c->H2,
-                                                  G.H1P, gp.KC, gp.ch, NT, sg, PS, PA, h->err_flag);
+                                                  G.H1P, gp.KC, gp.ch, NT, sg, PS, PA, h->err_flag,
+                                                  mode == G3_C8 ? G3_RANGE_LIMIT_C8 : G3_RANGE_LIMIT);
     RLC_LAUNCH_CHECK(h);
   }
   Grid3Params P;
@@ -837,6 +937,7 @@ static int rlc_eval_umma_grid3(rlc_handle* h, const rlc_critic* c, const float* 
   P.blob[1] = P.blob[0] + G.blob_bytes;
   P.off_hi = G.off_w2; P.off_lo = G.off_w1; P.off_c0 = G.off_c0;
   P.lbo = (G.H2P / 2) * 16;
+  P.w8_bytes = gp.w_half / 2;
   P.w_stages = gp.w_stages; P.pa_stages = gp.pa_stages;
   P.resident_hi = gp.resident_hi; P.sm_whi = gp.sm_whi; P.whi_bytes = gp.whi_bytes;
   P.sm_w = gp.sm_w; P.sm_pa = gp.sm_pa; P.sm_ps = gp.sm_ps; P.sm_qp = gp.sm_qp; P.sm_bar = gp.sm_bar;
@@ -849,7 +950,7 @@ static int rlc_eval_umma_grid3(rlc_handle* h, const rlc_critic* c, const float* 
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(pairs * 2));
-  cfg.blockDim = dim3(G3_THREADS);
+  cfg.blockDim = dim3(g3_threads(mode));
   cfg.dynamicSmemBytes = (size_t)gp.total;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -869,7 +970,9 @@ static int rlc_eval_umma_grid3(rlc_handle* h, const rlc_critic* c, const float* 
     RLC_CUDA(cudaMemsetAsync(prof_dev, 0, (4096 + 4 * 2048) * sizeof(long long), st));
     P.prof = prof_dev;
   }
-  void (*kern)(const Grid3Params) = P.prof ? k_critic_umma_grid3<true> : k_critic_umma_grid3<false>;
+  void (*kern)(const Grid3Params) =
+      mode == G3_C8 ? (P.prof ? k_critic_umma_grid3<true, G3_C8> : k_critic_umma_grid3<false, G3_C8>)
+                    : (P.prof ? k_critic_umma_grid3<true, G3_X3> : k_critic_umma_grid3<false, G3_X3>);
   RLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gp.total));
   RLC_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
   RLC_LAUNCH_CHECK(h);

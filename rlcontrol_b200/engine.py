@@ -417,7 +417,7 @@ class Critic:
         prec = PREC_BY_NAME[precision] if isinstance(precision, str) else int(precision)
         m = int(self.eng.lib.rlc_umma_mode_prec(C.byref(self._desc), ACT_SHARED if shared_actions else ACT_PER_STATE,
                                                 prec))
-        return {0: "ss", 1: "folded", 3: "grid", 4: "grid3"}.get(m, "unsupported")
+        return {0: "ss", 1: "folded", 3: "grid", 4: "grid3", 5: "grid3c8"}.get(m, "unsupported")
 
     def eval_grad(self, s, a):
         """T-mid only: (q [B,N], dq/da [B,N,A]) without materialising the stack."""

@@ -19,7 +19,7 @@ def main():
     a = torch.rand(N, A, device="cuda") * 2 - 1
     a_ps = torch.rand(B, N, A, device="cuda") * 2 - 1
     flops = B * 2 * S * H1 + B * N * 2 * (A * H1 + H1 * H2 + H2)
-    cases = (("fp16x3 shared", a, "fp16x3"), ("fp16 shared", a, "fp16"), ("fp16 per-state", a_ps, "fp16"), ("bf16 shared", a, "bf16"),
+    cases = (("fp16c8 shared", a, "fp16c8"), ("fp16x3 shared", a, "fp16x3"), ("fp16 shared", a, "fp16"), ("fp16 per-state", a_ps, "fp16"), ("bf16 shared", a, "bf16"),
              ("fp32 shared (B/8)", a, "fp32"))
     if os.environ.get("ONLY"):
         cases = [c for c in cases if c[0].startswith(os.environ["ONLY"] + " shared")]

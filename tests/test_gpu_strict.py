@@ -13,49 +13,66 @@ pytestmark = pytest.mark.gpu
 
 TOL_STRICT = 2e-5          # max of |dq| / max(|q|, rms_state q) against the exact oracle / the reference's q
 TOL_STATED = 2e-5          # max against the fp64 restatement of the kernel's own arithmetic (head="grid3")
+# "fp16c8" (RLC_PREC_FP16C8): the same split with the two correction terms on the FP8 pipe.  Held to 6e-4 max against the
+# exact oracle (north_star: 1e-3; the fp64 emulation of its arithmetic gives 1.7e-4 .. 3.5e-4 on these inputs) and to the
+# same 2e-5 against ITS stated arithmetic (head="grid3c8") -- the kernel computes exactly what it says.
+TOL_C8 = 6e-4
+MODES = {"fp16x3": ("grid3", TOL_STRICT), "fp16c8": ("grid3c8", TOL_C8)}
 
 
-def _check(cr, eng, s, a, p, exact=None):
-    q = cr.eval(s, a, "fp16x3").cpu().numpy()
+def _check(cr, eng, s, a, p, exact=None, prec="fp16x3"):
+    head, tol = MODES[prec]
+    q = cr.eval(s, a, prec).cpu().numpy()
     assert eng.umma_error() == 0
-    assert cr.tensor_arithmetic(True, "fp16x3") == "grid3"
+    assert cr.tensor_arithmetic(True, prec) == head
     exact = onp.tin_eval(s, a, p, dtype=np.float64) if exact is None else exact
     e = rel_err(q, exact).max()
-    assert e < TOL_STRICT, f"fp16x3 vs exact: {e:.3e}"
-    d = rel_err(q, onp.tin_eval_rounded(s, a, p, head="grid3")).max()
-    assert d < TOL_STATED, f"fp16x3 vs stated arithmetic: {d:.3e}"
+    assert e < tol, f"{prec} vs exact: {e:.3e}"
+    d = rel_err(q, onp.tin_eval_rounded(s, a, p, head=head)).max()
+    assert d < TOL_STATED, f"{prec} vs stated arithmetic: {d:.3e}"
     return q
 
 
 @pytest.mark.parametrize("name,dims", [("tin_cfg1.npz", (3, 1, 200, 200)),
                                        ("tin_400_300.npz", (17, 6, 400, 300)),
                                        ("tin_cfg4_exact.npz", (3, 1, 400, 300))])
-def test_strict_golden(eng, name, dims):
-    """q of the reference's own SoftQNetwork (oracle/make_golden.py) within 2e-5 on the tensor path."""
+@pytest.mark.parametrize("prec", ["fp16x3", "fp16c8"])
+def test_strict_golden(eng, name, dims, prec):
+    """q of the reference's own SoftQNetwork (oracle/make_golden.py) within 2e-5 (fp16x3) / 6e-4 (fp16c8) on the tensor path."""
     g = golden(name)
     p = _p(g)
-    _check(_tin(eng, p, *dims), eng, g["s"], g["a"], p, exact=g["q"].astype(np.float64))
+    _check(_tin(eng, p, *dims), eng, g["s"], g["a"], p, exact=g["q"].astype(np.float64), prec=prec)
 
 
 @pytest.mark.parametrize("B,N", [(1, 1), (5, 257), (64, 62), (1, 513), (3, 31), (4, 32), (9, 1024), (130, 33)])
-def test_strict_ragged_shapes(eng, B, N):
+@pytest.mark.parametrize("prec", ["fp16x3", "fp16c8"])
+def test_strict_ragged_shapes(eng, B, N, prec):
     rng = np.random.RandomState(B * 1000 + N)
     S, A, H1, H2 = 5, 2, 72, 40
     p = _rand_tin(rng, S, A, H1, H2, last=3.0)
     s = rng.randn(B, S).astype(np.float32)
     a = rng.uniform(-1, 1, (N, A)).astype(np.float32)
-    _check(_tin(eng, p, S, A, H1, H2), eng, s, a, p)
+    _check(_tin(eng, p, S, A, H1, H2), eng, s, a, p, prec=prec)
 
 
 @pytest.mark.parametrize("S,A,H1,H2", [(3, 1, 200, 200), (17, 6, 400, 300), (1, 1, 32, 32), (30, 8, 256, 256),
                                        (11, 3, 100, 480), (2, 2, 16, 304), (4, 2, 95, 33), (6, 3, 191, 300)])
-def test_strict_network_shapes(eng, S, A, H1, H2):
-    """Chunking (narrow chunk second / single chunk), slot count, N split and weight-ring geometry across widths."""
+@pytest.mark.parametrize("prec", ["fp16x3", "fp16c8"])
+def test_strict_network_shapes(eng, S, A, H1, H2, prec):
+    """Chunking, slot count, accumulator parts and weight-ring geometry (resident / streamed) across widths."""
     rng = np.random.RandomState(S * 7 + H1)
     p = _rand_tin(rng, S, A, H1, H2, last=5.0)
     s = rng.randn(9, S).astype(np.float32)
     a = rng.uniform(-1, 1, (190, A)).astype(np.float32)
-    _check(_tin(eng, p, S, A, H1, H2), eng, s, a, p)
+    cr = _tin(eng, p, S, A, H1, H2)
+    if prec == "fp16c8" and H2 > 448:
+        # 480 accumulator columns leave 32 TMEM columns: no room for two activation slots of one K=32 step each
+        import rlcontrol_b200 as rb
+        assert cr.tensor_arithmetic(True, prec) == "unsupported"
+        with pytest.raises(rb.RlcError):
+            cr.eval(s, a, prec)
+        return
+    _check(cr, eng, s, a, p, prec=prec)
 
 
 def test_strict_state_clip_and_scales(eng):
@@ -89,6 +106,7 @@ def test_strict_bench_workload_and_index_parity(eng):
     s, a, _, _ = bench.make_inputs(np.random.RandomState(1000), 64, W["N"], W["S"], W["A"])
     cr = _tin(eng, params, W["S"], W["A"], W["H1"], W["H2"])
     ref = onp.tin_eval(s, a, params, dtype=np.float64)
+    _check(cr, eng, s, a, params, exact=ref, prec="fp16c8")
     q = _check(cr, eng, s, a, params, exact=ref)
     import torch
     idx = eng.topk(torch.as_tensor(q, device=eng.device), 6)[0].cpu().numpy()
