@@ -404,7 +404,11 @@ int rlc_eval_store(rlc_handle* h, int E, const double* ep_ret, const int* ep_ste
 int rlc_env_step_train(rlc_handle* h, const rlc_env* env, int64_t* cur, double* env_state, int* ep_step,
                        float* obs, const float* action, const double* reset_feed, int64_t reset_rows,
                        float* rb_state, float* rb_action, float* rb_reward, float* rb_next_state, float* rb_gamma,
-                       int64_t cap, float gamma, int64_t log_rows, double* reward_log, int* flag_log, void* stream);
+                       int64_t cap, float gamma, int64_t log_rows, double* reward_log, int* flag_log, int64_t rb_pitch,
+                       void* stream);
+/* rb_pitch (rlc_env_step_train, rlc_loop_step): 0 = the five rb_* pointers are struct-of-arrays rings; > 0 = they are the field
+ * views of ONE record ring (rlc_replay_rec_stride floats per 64-byte-aligned record, rlc_replay_*_rec) and share this row
+ * pitch in floats -- the default layout of ReplayBuffer and of the device-resident loop. */
 /* Stage row k = (cur[0]-1) mod feed_rows (the row rlc_env_step_train just logged) of the host-drawn feeds into the fixed buffers a captured update reads: eps_act[A] <-
  * eps_act_feed[k] (sample_action's N(0,1) draws), eps_upd[B,A] <- eps_upd_feed[k] (pi.evaluate's draws inside
  * update_network), slots[B] <- (cur[2] + idx_feed[k,b]) % cap (RandomAccessQueue.sample_n_k's logical indices as
@@ -421,7 +425,7 @@ int rlc_loop_step(rlc_handle* h, const rlc_env* env, int64_t* cur, double* env_s
                   float* rb_reward, float* rb_next_state, float* rb_gamma, int64_t cap, float gamma, int64_t ring_rows,
                   double* reward_log, int* flag_log, int B, const float* eps_act_feed, const float* eps_upd_feed,
                   const int* idx_feed, float* eps_act, float* eps_upd, float* s_out, float* a_out, float* r_out,
-                  float* s2_out, float* g_out, void* stream);
+                  float* s2_out, float* g_out, int64_t rb_pitch, void* stream);
 
 /* ---- small-minibatch fast path of the ForwardKL / ReverseKL update (cfg1 / cfg5) -------------------
  * forwardkl_network.py:123-209 / reversekl_network.py:130-217 at B <= 64 rows: every B-row forward pass in ONE

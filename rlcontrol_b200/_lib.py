@@ -130,9 +130,9 @@ SIGNATURES = {
     "rlc_env_step_eval": (_i, [_p, _en, _i, _p, _p, _p, _p, _p, _p, _p]),
     "rlc_eval_store": (_i, [_p, _i, _p, _p, _p, _i64, _p, _p, _p]),
     "rlc_env_step_train": (_i, [_p, _en, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _i64, _f, _i64, _p, _p,
-                                _p]),
+                                _i64, _p]),
     "rlc_loop_step": (_i, [_p, _en, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _i64, _f, _i64, _p, _p, _i, _p, _p, _p,
-                           _p, _p, _p, _p, _p, _p, _p, _p]),
+                           _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "rlc_sb_forward": (_i, [_p, C.POINTER(RlcSbNet), _i, _i, _p]),
     "rlc_sb_update": (_i, [_p, C.POINTER(RlcSbTrain), _i, _i, _i, _p]),
     "rlc_loop_stage": (_i, [_p, _p, _i, _i, _i64, _p, _p, _p, _i64, _p, _p, _p, _p]),

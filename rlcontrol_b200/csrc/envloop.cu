@@ -133,7 +133,10 @@ __device__ __forceinline__ void env_step_train_body(const rlc_env& env, long lon
                                  long long reset_rows, float* __restrict__ rb_state, float* __restrict__ rb_action,
                                  float* __restrict__ rb_reward, float* __restrict__ rb_next,
                                  float* __restrict__ rb_gamma, long long cap, float gamma, long long log_rows,
-                                 double* __restrict__ reward_log, int* __restrict__ flag_log) {
+                                 double* __restrict__ reward_log, int* __restrict__ flag_log, long long rb_pitch) {
+  // rb_pitch: 0 = five struct-of-arrays rings (row pitch S, A, 1, S, 1); > 0 = the RECORD ring (replay.cu): one array of
+  // fixed-stride 64-byte-aligned records, the five pointers are its field views and share this row pitch
+  const long long ps = rb_pitch ? rb_pitch : env.S, pa = rb_pitch ? rb_pitch : env.A, p1 = rb_pitch ? rb_pitch : 1;
   const long long k = cur[0] % log_rows;
   const EnvOut o = env_dynamics(env, state[0], state[1], action);
   const int n = ep_step[0] + 1;
@@ -152,12 +155,12 @@ __device__ __forceinline__ void env_step_train_body(const rlc_env& env, long lon
       cur[2] = (head + 1) % cap;
     }
     for (int i = 0; i < env.S; ++i) {
-      rb_state[slot * env.S + i] = obs[i];
-      rb_next[slot * env.S + i] = obs_n[i];
+      rb_state[slot * ps + i] = obs[i];
+      rb_next[slot * ps + i] = obs_n[i];
     }
-    for (int i = 0; i < env.A; ++i) rb_action[slot * env.A + i] = action[i];
-    rb_reward[slot] = (float)o.reward;
-    rb_gamma[slot] = done ? 0.f : gamma;   // is_terminal -> transition gamma 0.0 (base_agent.py:54-57)
+    for (int i = 0; i < env.A; ++i) rb_action[slot * pa + i] = action[i];
+    rb_reward[slot * p1] = (float)o.reward;
+    rb_gamma[slot * p1] = done ? 0.f : gamma;   // is_terminal -> transition gamma 0.0 (base_agent.py:54-57)
   }
   reward_log[k] = o.reward;
   flag_log[k] = done | (truncated << 1);
@@ -186,10 +189,10 @@ __global__ void k_env_step_train(rlc_env env, long long* __restrict__ cur, doubl
                                  long long reset_rows, float* __restrict__ rb_state, float* __restrict__ rb_action,
                                  float* __restrict__ rb_reward, float* __restrict__ rb_next,
                                  float* __restrict__ rb_gamma, long long cap, float gamma, long long log_rows,
-                                 double* __restrict__ reward_log, int* __restrict__ flag_log) {
+                                 double* __restrict__ reward_log, int* __restrict__ flag_log, long long rb_pitch) {
   if (threadIdx.x != 0) return;
   env_step_train_body(env, cur, state, ep_step, obs, action, reset_feed, reset_rows, rb_state, rb_action, rb_reward, rb_next,
-                      rb_gamma, cap, gamma, log_rows, reward_log, flag_log);
+                      rb_gamma, cap, gamma, log_rows, reward_log, flag_log, rb_pitch);
 }
 
 // The head of a training step as ONE launch (one CTA): env.step + replay append by thread 0, then -- behind a block
@@ -206,6 +209,7 @@ struct LoopStepArgs {
   const double* reset_feed;
   long long reset_rows;
   float *rb_state, *rb_action, *rb_reward, *rb_next, *rb_gamma;
+  long long rb_pitch;        // 0 = struct-of-arrays rings, > 0 = record ring row pitch (floats)
   long long cap;
   float gamma;
   long long ring_rows;
@@ -223,7 +227,7 @@ __global__ void __launch_bounds__(256) k_loop_step(const __grid_constant__ LoopS
   if (tid == 0)
     env_step_train_body(p.env, p.cur, p.state, p.ep_step, p.obs, p.action, p.reset_feed, p.reset_rows, p.rb_state,
                         p.rb_action, p.rb_reward, p.rb_next, p.rb_gamma, p.cap, p.gamma, p.ring_rows, p.reward_log,
-                        p.flag_log);
+                        p.flag_log, p.rb_pitch);
   __threadfence_block();
   __syncthreads();
   const int S = p.env.S, A = p.env.A, B = p.B;
@@ -233,17 +237,18 @@ __global__ void __launch_bounds__(256) k_loop_step(const __grid_constant__ LoopS
   if (!p.idx_feed) return;                   // steps before learning starts: nothing to sample
   for (int t = tid; t < B * A; t += blockDim.x) p.eps_upd[t] = p.eps_upd_feed[k * B * A + t];
   const int W = 2 * S + A + 2;               // floats per gathered transition
+  const long long ps = p.rb_pitch ? p.rb_pitch : S, pa = p.rb_pitch ? p.rb_pitch : A, p1 = p.rb_pitch ? p.rb_pitch : 1;
   for (int t = tid; t < B * W; t += blockDim.x) {
     const int b = t / W, f = t % W;
     long long i = p.idx_feed[k * B + b];
     if (i < 0) i = 0;
     if (count > 0 && i >= count) i = count - 1;
     const long long slot = (head + i) % p.cap;
-    if (f < S) p.s_out[b * S + f] = p.rb_state[slot * S + f];
-    else if (f < 2 * S) p.s2_out[b * S + (f - S)] = p.rb_next[slot * S + (f - S)];
-    else if (f < 2 * S + A) p.a_out[b * A + (f - 2 * S)] = p.rb_action[slot * A + (f - 2 * S)];
-    else if (f == 2 * S + A) p.r_out[b] = p.rb_reward[slot];
-    else p.g_out[b] = p.rb_gamma[slot];
+    if (f < S) p.s_out[b * S + f] = p.rb_state[slot * ps + f];
+    else if (f < 2 * S) p.s2_out[b * S + (f - S)] = p.rb_next[slot * ps + (f - S)];
+    else if (f < 2 * S + A) p.a_out[b * A + (f - 2 * S)] = p.rb_action[slot * pa + (f - 2 * S)];
+    else if (f == 2 * S + A) p.r_out[b] = p.rb_reward[slot * p1];
+    else p.g_out[b] = p.rb_gamma[slot * p1];
   }
 }
 
@@ -306,14 +311,14 @@ extern "C" int rlc_env_step_train(rlc_handle* h, const rlc_env* env, int64_t* cu
                                   int* ep_step, float* obs, const float* action, const double* reset_feed,
                                   int64_t reset_rows, float* rb_state, float* rb_action, float* rb_reward,
                                   float* rb_next_state, float* rb_gamma, int64_t cap, float gamma,
-                                  int64_t log_rows, double* reward_log, int* flag_log, void* stream) {
+                                  int64_t log_rows, double* reward_log, int* flag_log, int64_t rb_pitch, void* stream) {
   RLC_REQUIRE(h && env_ok(env) && cur && env_state && ep_step && obs && action && reset_feed && reset_rows >= 1);
   RLC_REQUIRE(rb_state && rb_action && rb_reward && rb_next_state && rb_gamma && cap >= 1 && log_rows >= 1 &&
-              reward_log && flag_log);
+              reward_log && flag_log && rb_pitch >= 0);
   k_env_step_train<<<1, 32, 0, (cudaStream_t)stream>>>(*env, (long long*)cur, env_state, ep_step, obs, action,
                                                        reset_feed, reset_rows, rb_state, rb_action, rb_reward,
                                                        rb_next_state, rb_gamma, cap, gamma, log_rows, reward_log,
-                                                       flag_log);
+                                                       flag_log, (long long)rb_pitch);
   RLC_LAUNCH_CHECK(h);
   return RLC_OK;
 }
@@ -337,15 +342,16 @@ extern "C" int rlc_loop_step(rlc_handle* h, const rlc_env* env, int64_t* cur, do
                              float gamma, int64_t ring_rows, double* reward_log, int* flag_log, int B,
                              const float* eps_act_feed, const float* eps_upd_feed, const int* idx_feed, float* eps_act,
                              float* eps_upd, float* s_out, float* a_out, float* r_out, float* s2_out, float* g_out,
-                             void* stream) {
+                             int64_t rb_pitch, void* stream) {
   RLC_REQUIRE(h && env_ok(env) && cur && env_state && ep_step && obs && action && reset_feed && reset_rows >= 1);
   RLC_REQUIRE(rb_state && rb_action && rb_reward && rb_next_state && rb_gamma && cap >= 1 && ring_rows >= 1 && reward_log &&
-              flag_log && eps_act_feed && eps_act && B >= 0);
+              flag_log && eps_act_feed && eps_act && B >= 0 && rb_pitch >= 0);
   RLC_REQUIRE(!idx_feed || (eps_upd_feed && eps_upd && s_out && a_out && r_out && s2_out && g_out && B >= 1));
   LoopStepArgs p;
   p.env = *env; p.cur = (long long*)cur; p.state = env_state; p.ep_step = ep_step; p.obs = obs; p.action = action;
   p.reset_feed = reset_feed; p.reset_rows = reset_rows; p.rb_state = rb_state; p.rb_action = rb_action;
   p.rb_reward = rb_reward; p.rb_next = rb_next_state; p.rb_gamma = rb_gamma; p.cap = cap; p.gamma = gamma;
+  p.rb_pitch = rb_pitch;
   p.ring_rows = ring_rows; p.reward_log = reward_log; p.flag_log = flag_log; p.B = B; p.eps_act_feed = eps_act_feed;
   p.eps_upd_feed = eps_upd_feed; p.idx_feed = idx_feed; p.eps_act = eps_act; p.eps_upd = eps_upd; p.s_out = s_out;
   p.a_out = a_out; p.r_out = r_out; p.s2_out = s2_out; p.g_out = g_out;

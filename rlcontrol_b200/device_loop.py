@@ -225,7 +225,13 @@ class DeviceExperiment:
         self.ev_ret_log, self.ev_steps_log = z(n_sessions, E, dt=torch.float64), z(n_sessions, E, dt=torch.int32)
         self.n_sessions = n_sessions
         # replay ring (struct of arrays, as replaybuffer.py)
-        self.rb = dict(s=z(self.cap, S), a=z(self.cap, A), r=z(self.cap), s2=z(self.cap, S), g=z(self.cap))
+        # replay ring in the RECORD layout (one 64-byte-aligned record [s | a | r | s' | gamma | pad] per transition, the
+        # default of replaybuffer.ReplayBuffer): the five arrays the loop kernels take are field views sharing one row pitch
+        self.rb_stride = int(self.lib.rlc_replay_rec_stride(S, A))
+        self.rb_rec = z(self.cap, self.rb_stride)
+        rec = self.rb_rec
+        self.rb = dict(s=rec[:, :S], a=rec[:, S:S + A], r=rec[:, S + A], s2=rec[:, S + A + 1:2 * S + A + 1],
+                       g=rec[:, 2 * S + A + 1])
         # per-step feeds and logs: ring of 2K rows, indexed by cur[0] on the device
         R = self.ring
         self.f_eps_act, self.f_eps_upd, self.f_idx = z(R, A), z(R, B, A), z(R, B, dt=torch.int32)
@@ -283,7 +289,8 @@ class DeviceExperiment:
                                           _ptr(self.ep_step), _ptr(self.obs), _ptr(self.act["action"]),
                                           _ptr(self.train_resets), self.train_resets.shape[0], _ptr(rb["s"]),
                                           _ptr(rb["a"]), _ptr(rb["r"]), _ptr(rb["s2"]), _ptr(rb["g"]), self.cap,
-                                          self.gamma, self.ring, _ptr(self.reward_log), _ptr(self.flag_log), _stream()))
+                                          self.gamma, self.ring, _ptr(self.reward_log), _ptr(self.flag_log), self.rb_stride,
+                                          _stream()))
 
     def _stage(self, learn: bool):
         sp = self.spec
@@ -303,7 +310,7 @@ class DeviceExperiment:
             _ptr(self.flag_log), self.B, _ptr(self.f_eps_act), _ptr(self.f_eps_upd) if learn else None,
             _ptr(self.f_idx) if learn else None, _ptr(self.eps_act), _ptr(d["eps"]) if learn else None,
             _ptr(d["s"]) if learn else None, _ptr(d["a"]) if learn else None, _ptr(d["r"]) if learn else None,
-            _ptr(d["s2"]) if learn else None, _ptr(d["g"]) if learn else None, _stream()))
+            _ptr(d["s2"]) if learn else None, _ptr(d["g"]) if learn else None, self.rb_stride, _stream()))
         if learn:
             self.net._enqueue(self.st, self.B, device_inputs=True)
             if not self.small:

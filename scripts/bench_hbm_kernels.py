@@ -92,6 +92,36 @@ def main():
     report("K2 T-mid hoisted evaluation, per-state actions [4096,1024,6] (state term + rows)", B * N * (A + 1) * 4,
            lambda: timeit(lambda i: cr.eval_into(s, acts[i], qs[i], "fp32"), 5),
            lambda sec: "also %.1f TFLOP/s fp32 on 2(A+1)H2 flop/row: issue-bound, not HBM-bound" % (B * N * 2 * (A + 1) * H2 / sec / 1e12))
+    # K5 input gradient dQ/da on the whole B x N stack (AE+ ascent ae_plus_network.py:310-343, SQL sql_network.py:101-107):
+    # T-mid fused evaluation + gradient (hoisted, per-state actions), and the T-in row kernel on a stacked slice
+    gs = [torch.empty(B, N, A, device=dev) for _ in range(2)]
+
+    def tmid_grad(i):
+        from rlcontrol_b200._lib import check as _chk
+        from rlcontrol_b200.engine import _ptr as _pp, _stream as _ss
+        import ctypes as _C
+        _chk(eng.lib.rlc_tmid_eval_grad(eng.h, _C.byref(cr._desc), _pp(s), B, _pp(acts[i]), N, rb.ACT_PER_STATE, _pp(qs[i]),
+                                        _pp(gs[i % 2]), _ss()))
+    report("K5 dQ/da T-mid on the B x N stack [4096,1024,6] (rlc_tmid_eval_grad: q and dq/da out)", B * N * (2 * A + 1) * 4,
+           lambda: timeit(tmid_grad, 3),
+           lambda sec: "%.2f G rows/s; %.1f TFLOP/s fp32 on 4(A+1)H2 flop/row" % (B * N / sec / 1e9, B * N * 4 * (A + 1) * H2 / sec / 1e12))
+    crin = rb.Critic(eng, rb.TIN, S, A, H1, H2).load(u(.2, H1, S + A), u(.2, H1), u(.05, H2, H1), u(.05, H2), u(.3, 1, H2), u(.3, 1),
+                                                      rb.LAYOUT_OUT_IN)
+    R = B * N // 8                                        # 524 288 stacked rows (an eighth of the cfg4 stack; fp32 CUDA cores)
+    s_rows = torch.randn(R, S, device=dev, generator=g)
+    a_rows = torch.rand(R, A, device=dev, generator=g) * 2 - 1
+    g_rows, q_rows = torch.empty(R, A, device=dev), torch.empty(R, device=dev)
+
+    def tin_grad(i):
+        from rlcontrol_b200._lib import check as _chk
+        from rlcontrol_b200.engine import _ptr as _pp, _stream as _ss
+        import ctypes as _C
+        _chk(eng.lib.rlc_critic_grad_action(eng.h, _C.byref(crin._desc), _pp(s_rows), _pp(a_rows), R, _pp(g_rows), _pp(q_rows), _ss()))
+    fl_row = 2 * ((S + A) * H1 + H1 * H2 + H2) + 2 * (H2 + H1 * H2 + A * H1)
+    report("K5 dQ/da T-in on %d stacked rows (rlc_critic_grad_action, fp32 CUDA cores)" % R, R * (S + 2 * A + 1) * 4,
+           lambda: timeit(tin_grad, 2),
+           lambda sec: "%.3f G rows/s = %.1f TFLOP/s fp32 (forward + input-gradient, %d flop/row); the full 4.19M-row stack takes %.1f ms"
+                       % (R / sec / 1e9, R * fl_row / sec / 1e12, fl_row, sec * 8 * 1e3))
     # K6: replay gather on a 4M-slot ring (S=17, A=6): 168 B per sampled transition in, the same out
     from rlcontrol_b200.replaybuffer import ReplayBuffer
     cap, nb = 1 << 22, 1 << 20
