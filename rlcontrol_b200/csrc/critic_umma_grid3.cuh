@@ -105,7 +105,8 @@ enum {
 };
 
 // Pre-pass, fp32 tables (8 rows per CTA as k_grid_parts8):  PS[b][j] = b1[j] + sum_k clip(s[b][k]) W1[k][j]  (j < H1),
-// PS[b][H1] = 1;  PA[c][n][jj] = sum_k a[n][k] W1[S+k][start_c + jj].  Same fp32 FMA order as the fp16 pre-pass.
+// PS[b][H1] = 1;  PA[c][n][jj] = sum_k a[n][k] W1[S+k][start_c + jj].  Same fp32 FMA order as the fp16 pre-pass.  Both tables
+// are stored multiplied by 1/2 (exact), see ep1_unit.
 __global__ void __launch_bounds__(128)
 k_grid3_parts(const float* __restrict__ theta, const float* __restrict__ s, const float* __restrict__ a,
               const float* __restrict__ smin, const float* __restrict__ smax, int B, int N, int S, int A, int H1, int H2,
@@ -150,7 +151,7 @@ k_grid3_parts(const float* __restrict__ theta, const float* __restrict__ s, cons
       if (r0 + r < B) {
         const float v = (j == H1) ? 1.f : acc[r];
         bad = bad || !(fabsf(v) <= limit);
-        PS[(size_t)(r0 + r) * H1P + j] = v;
+        PS[(size_t)(r0 + r) * H1P + j] = 0.5f * v;        // tables are stored HALVED (exact): relu(x) = x/2 + |x/2|
       }
   } else {
     int c = 0;
@@ -163,7 +164,7 @@ k_grid3_parts(const float* __restrict__ theta, const float* __restrict__ s, cons
       if (n < NT * 32) {
         const float v = (j < H1 && n < N) ? acc[r] : 0.f;
         bad = bad || !(fabsf(v) <= limit);
-        PA[((size_t)c * NT * 32 + n) * pitch + jj] = v;
+        PA[((size_t)c * NT * 32 + n) * pitch + jj] = 0.5f * v;
       }
     }
   }
@@ -289,22 +290,42 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* v) {
 }
 }  // namespace um
 
-// relu_signed_round for at most G3_VR = 64 columns held in registers (all indices static).
+// 2 * sign * relu(z) summed over NU units of 8 columns: relu(z) = (z + |z|) / 2 exactly, so the ReLU is an FADD with a free
+// |.| source modifier on the FMA pipe instead of an FMNMX on the (half-rate, shared with epilogue 1's min/max, permutes and
+// conversions) ALU pipe; the factor 2 is folded into the power-of-two output scale.
+template <int NU>
+__device__ __forceinline__ void relu2_signed_sum(const uint32_t* v, int kpos, float& a0, float& a1, float& a2, float& a3) {
+#pragma unroll
+  for (int p = 0; p < NU; ++p) {
+    const float sg = (p < kpos) ? 1.f : -1.f;
+#pragma unroll
+    for (int e = 0; e < 8; e += 4) {
+      const float z0 = __uint_as_float(v[p * 8 + e + 0]), z1 = __uint_as_float(v[p * 8 + e + 1]);
+      const float z2 = __uint_as_float(v[p * 8 + e + 2]), z3 = __uint_as_float(v[p * 8 + e + 3]);
+      a0 = fmaf(z0 + fabsf(z0), sg, a0);
+      a1 = fmaf(z1 + fabsf(z1), sg, a1);
+      a2 = fmaf(z2 + fabsf(z2), sg, a2);
+      a3 = fmaf(z3 + fabsf(z3), sg, a3);
+    }
+  }
+}
+
+// relu_signed_round for at most G3_VR = 64 columns held in registers (all indices static); accumulates 2x the signed sum.
 __device__ __forceinline__ void relu_signed_round8(const uint32_t* v, int w, int rel, float& a0, float& a1, float& a2,
                                                    float& a3) {
   if (rel <= 0 || rel >= w || (rel & 7) == 0) {
     const int kpos = rel <= 0 ? 0 : (rel >= w ? 8 : (rel >> 3));
     switch (w >> 3) {
 #if G3_VR >= 64
-      case 8: relu_signed_sum<8>(v, kpos, a0, a1, a2, a3); break;
-      case 7: relu_signed_sum<7>(v, kpos, a0, a1, a2, a3); break;
+      case 8: relu2_signed_sum<8>(v, kpos, a0, a1, a2, a3); break;
+      case 7: relu2_signed_sum<7>(v, kpos, a0, a1, a2, a3); break;
 #endif
-      case 6: relu_signed_sum<6>(v, kpos, a0, a1, a2, a3); break;
-      case 5: relu_signed_sum<5>(v, kpos, a0, a1, a2, a3); break;
-      case 4: relu_signed_sum<4>(v, kpos, a0, a1, a2, a3); break;
-      case 3: relu_signed_sum<3>(v, kpos, a0, a1, a2, a3); break;
-      case 2: relu_signed_sum<2>(v, kpos, a0, a1, a2, a3); break;
-      default: relu_signed_sum<1>(v, kpos, a0, a1, a2, a3); break;
+      case 6: relu2_signed_sum<6>(v, kpos, a0, a1, a2, a3); break;
+      case 5: relu2_signed_sum<5>(v, kpos, a0, a1, a2, a3); break;
+      case 4: relu2_signed_sum<4>(v, kpos, a0, a1, a2, a3); break;
+      case 3: relu2_signed_sum<3>(v, kpos, a0, a1, a2, a3); break;
+      case 2: relu2_signed_sum<2>(v, kpos, a0, a1, a2, a3); break;
+      default: relu2_signed_sum<1>(v, kpos, a0, a1, a2, a3); break;
     }
   } else {
 #pragma unroll
@@ -312,7 +333,7 @@ __device__ __forceinline__ void relu_signed_round8(const uint32_t* v, int w, int
       if (p * 8 < w) {
 #pragma unroll
         for (int e = 0; e < 8; ++e)
-          a0 = fmaf(fmaxf(__uint_as_float(v[p * 8 + e]), 0.f), (p * 8 + e >= rel) ? -1.f : 1.f, a0);
+          a0 = fmaf(__uint_as_float(v[p * 8 + e]) + fabsf(__uint_as_float(v[p * 8 + e])), (p * 8 + e >= rel) ? -1.f : 1.f, a0);
       }
     }
   }
@@ -330,7 +351,10 @@ __device__ __forceinline__ void ep1_unit(const float4* __restrict__ pa4, const f
     // packed fp32 adds / multiplies (FADD2 / FMUL2): half the instructions of the scalar forms, same roundings
     const float2 s01 = __fadd2_rn(make_float2(x.x, x.y), make_float2(y.x, y.y));
     const float2 s23 = __fadd2_rn(make_float2(x.z, x.w), make_float2(y.z, y.w));
-    const float2 v01 = make_float2(fmaxf(s01.x, 0.f), fmaxf(s01.y, 0.f)), v23 = make_float2(fmaxf(s23.x, 0.f), fmaxf(s23.y, 0.f));
+    // the tables hold PS/2 and PA/2 (exact), so s = (PS + PA)/2 and relu(PS + PA) = s + |s| EXACTLY: an FADD with a free |.|
+    // source modifier on the FMA pipe instead of an FMNMX on the half-rate ALU pipe (which the conversions and permutes need)
+    const float2 v01 = make_float2(s01.x + fabsf(s01.x), s01.y + fabsf(s01.y));
+    const float2 v23 = make_float2(s23.x + fabsf(s23.x), s23.y + fabsf(s23.y));
     const __half2 h01 = __float22half2_rn(v01), h23 = __float22half2_rn(v23);
     const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
     hi[g * 2 + 0] = *reinterpret_cast<const uint32_t*>(&h01);
@@ -747,7 +771,7 @@ __global__ void __launch_bounds__(G3_THREADS, 1) k_critic_umma_grid3(const Grid3
           float tot = acc;
 #pragma unroll
           for (int g = 0; g < G3_E2G - 1; ++g) tot += qp[g * 128 + rloc];
-          if (b < P.B && n < P.N) P.q[(size_t)b * P.N + n] = fmaf(inv_scale, tot, b3v);
+          if (b < P.B && n < P.N) P.q[(size_t)b * P.N + n] = fmaf(0.5f * inv_scale, tot, b3v);   // tot = 2 x the signed sum
         }
       }
     }
