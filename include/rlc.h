@@ -116,6 +116,20 @@ int rlc_invalidate_pack(rlc_handle* h, const float* theta);
 int rlc_critic_eval(rlc_handle* h, const rlc_critic* c, const float* s, int B, const float* a,
                     int N, int act_mode, int precision, float* q_out, void* stream);
 
+/* The whole sampled-action step of ForwardKL (mode 0, forwardkl_network.py:160-194 + get_logprob :324-351) or ReverseKL
+ * (mode 1, reversekl_network.py:176-203; `hard` = the hard_intg variant, v[B] = V(s)) in ONE call: Q(s_b, a_n) on the shared grid
+ * [N,A] and its per-state policy reduction, loss_b[B], dL/dmean[B,A], dL/dlog_std[B,A] (gradients scaled by 1/B_total).
+ * fuse != 0 with precision RLC_PREC_FP16X3 / FP16C8 (or AUTO) and B >= 8 x the SM count: the reduction runs inside the
+ * evaluation kernel's epilogue (state-major tiles, online softmax over the state's action blocks) and q[B,N] never reaches
+ * memory unless q_out is given.  Otherwise (and always with fuse == 0, which is ~30 us faster at cfg4: the fused variant pays
+ * the 7-vs-6.9 state-group imbalance of 148 persistent CTAs) it composes rlc_critic_eval + rlc_reduce_{fkl,rkl}_policy with
+ * the same results.  q_out may be NULL. */
+int rlc_critic_eval_reduce_policy(rlc_handle* h, const rlc_critic* c, const float* s, int B, const float* grid, int N,
+                                  const float* w, float action_scale, const float* mean, const float* log_std,
+                                  const float* v, float entropy_scale, int mode, int hard, int B_total, int precision,
+                                  int fuse, float* q_out, float* loss_b_out, float* dmean_out, float* dlog_std_out,
+                                  void* stream);
+
 /* B x N evaluation *and* dQ/da of a T-mid critic without materialising the stack: the AE+
  * ascent (ae_plus_network.py:310-343, ActorExpert_Plus.py:130) evaluates action_grads on B*N rows
  * whose states repeat N times.  dqda_out[B,N,A]; q_out[B,N] or NULL. */

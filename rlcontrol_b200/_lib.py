@@ -89,6 +89,8 @@ SIGNATURES = {
     "rlc_unpack_theta": (_i, [_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "rlc_invalidate_pack": (_i, [_p, _p]),
     "rlc_critic_eval": (_i, [_p, _cr, _p, _i, _p, _i, _i, _i, _p, _p]),
+    "rlc_critic_eval_reduce_policy": (_i, [_p, _cr, _p, _i, _p, _i, _p, _f, _p, _p, _p, _f, _i, _i, _i, _i, _i, _p, _p, _p, _p,
+                                           _p]),
     "rlc_tmid_eval_grad": (_i, [_p, _cr, _p, _i, _p, _i, _i, _p, _p, _p]),
     "rlc_umma_last_error": (_i, [_p, _p]),
     "rlc_umma_mode": (_i, [_cr, _i]),

@@ -139,3 +139,52 @@ extern "C" int rlc_critic_eval(rlc_handle* h, const rlc_critic* c, const float* 
     return RLC_ERR_UNSUPPORTED;
   return rlc_eval_umma(h, c, s, B, a, N, act_mode, precision, q_out, st);
 }
+
+// Sampled-action step in one call: Q on the B x N grid and its per-state policy reduction.  fuse != 0: on the split tensor
+// kernels the reduction runs inside K1's epilogue (state-major tiles, online softmax) and q[B,N] is only written when q_out
+// is given; fuse == 0 (the faster choice at cfg4): evaluation kernel + policy-fused reduction kernel.
+extern "C" int rlc_critic_eval_reduce_policy(rlc_handle* h, const rlc_critic* c, const float* s, int B, const float* grid,
+                                             int N, const float* w, float action_scale, const float* mean,
+                                             const float* log_std, const float* v, float entropy_scale, int mode,
+                                             int hard, int B_total, int precision, int fuse, float* q_out,
+                                             float* loss_b_out, float* dmean_out, float* dlog_std_out, void* stream) {
+  RLC_REQUIRE(h && critic_ok(c) && s && grid && w && mean && log_std && loss_b_out && B >= 0 && N >= 1);
+  RLC_REQUIRE((mode == 0 || mode == 1) && (mode == 0 || v) && B_total >= B && B_total >= 1 && action_scale > 0.f);
+  RLC_REQUIRE(precision >= RLC_PREC_FP32 && precision <= RLC_PREC_FP16C8 && (mode == 1 || entropy_scale > 0.f));
+  if (B == 0) return RLC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float alpha = (mode == 1 && hard) ? 0.f : entropy_scale;
+  int prec = precision;
+  if (prec == RLC_PREC_AUTO)
+    prec = (c->topology == RLC_TIN && (long long)B * N >= 16384 && rlc_umma3_supported(h, c, RLC_PREC_FP16X3)) ? RLC_PREC_FP16X3
+                                                                                                                : RLC_PREC_FP32;
+  if (fuse && (prec == RLC_PREC_FP16X3 || prec == RLC_PREC_FP16C8)) {
+    rlc_fuse_args f;
+    f.mode = mode + 1; f.A = c->A; f.w = w; f.grid = grid; f.mean = mean; f.log_std = log_std; f.v = v;
+    f.action_scale = action_scale; f.alpha = alpha; f.B_total = B_total;
+    f.loss_b = loss_b_out; f.dmean = dmean_out; f.dlog_std = dlog_std_out;
+    const int rc = rlc_eval_umma_grid3_fused(h, c, s, B, grid, N, prec, q_out, &f, st);
+    if (rc != RLC_ERR_UNSUPPORTED) return rc;
+  }
+  // composition: evaluation into q (scratch when the caller does not want it), then the policy-fused reduction kernel
+  float* q = q_out;
+  if (!q) {
+    // the evaluation kernels use the front of the handle's workspace themselves: a separate block, retired with the handle
+    static thread_local float* q_scratch = nullptr;
+    static thread_local size_t q_scratch_n = 0;
+    const size_t need = (size_t)B * N;
+    if (need > q_scratch_n) {
+      if (q_scratch) { const int rcr = rlc_retire_block(h, q_scratch); if (rcr) return rcr; }
+      RLC_CUDA(cudaMalloc(&q_scratch, need * sizeof(float)));
+      q_scratch_n = need;
+    }
+    q = q_scratch;
+  }
+  int rc = rlc_critic_eval(h, c, s, B, grid, N, RLC_ACT_SHARED, prec, q, stream);
+  if (rc) return rc;
+  if (mode == 0)
+    return rlc_reduce_fkl_policy(h, q, w, grid, c->A, action_scale, mean, log_std, B, N, entropy_scale, B_total, loss_b_out,
+                                 dmean_out, dlog_std_out, nullptr, stream);
+  return rlc_reduce_rkl_policy(h, q, v, w, grid, c->A, action_scale, mean, log_std, B, N, entropy_scale, hard, B_total,
+                               loss_b_out, dmean_out, dlog_std_out, nullptr, stream);
+}

@@ -107,6 +107,22 @@ bool rlc_umma3_supported(const rlc_handle* h, const rlc_critic* c, int prec);   
 int rlc_tmid_state_term(rlc_handle* h, const rlc_critic* c, const float* s, int B, float* p_out,
                         cudaStream_t st);
 
+// U[k][n] = atanh(a_nk / scale), J[n] = sum_k log(1 - (a_nk/scale)^2 + 1e-6): grid-only terms of the policy log-density (reduce.cu)
+int rlc_launch_grid_logterms(rlc_handle* h, const float* grid, int N, int A, float action_scale, float* U, float* J,
+                             cudaStream_t st);
+// fused evaluation + per-state policy reduction on the split tensor kernels (critic_umma_grid3.cuh); RLC_ERR_UNSUPPORTED when
+// the shape does not qualify (the caller then composes rlc_critic_eval + rlc_reduce_*_policy)
+struct rlc_fuse_args {
+  int mode;                   // 1 = ForwardKL, 2 = ReverseKL
+  int A;
+  const float *w, *grid, *mean, *log_std, *v;
+  float action_scale, alpha;
+  int B_total;
+  float *loss_b, *dmean, *dlog_std;
+};
+int rlc_eval_umma_grid3_fused(rlc_handle* h, const rlc_critic* c, const float* s, int B, const float* a, int N, int prec,
+                              float* q_out, const rlc_fuse_args* f, cudaStream_t st);
+
 // dQ/da on R stacked rows, state row r/rep (critic_fp32.cu)
 int rlc_critic_grad_action_rep(rlc_handle* h, const rlc_critic* c, const float* s, int rep,
                                const float* a, long long R, float* dqda_out, float* q_out,

@@ -20,6 +20,7 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <cuda_fp8.h>
+#include <math_constants.h>
 
 #include "common.cuh"
 

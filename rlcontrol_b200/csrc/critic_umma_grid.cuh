@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(128)
 k_grid_parts8(const float* __restrict__ theta, const float* __restrict__ s, const float* __restrict__ a,
               const float* __restrict__ smin, const float* __restrict__ smax, int B, int N, int S, int A,
               int H1, int H2, int H1P, int CH, int nch, int NT, int state_groups, unsigned short* __restrict__ PS,
-              unsigned short* __restrict__ PA) {
+              unsigned short* __restrict__ PA, int* __restrict__ err) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   extern __shared__ float xs[];                               // [GR_PRE_ROWS][K]  (K = S for states, A for actions)
   const ThetaView t = theta_view(RLC_TIN, S, A, H1, H2);
@@ -178,6 +178,14 @@ k_grid_parts8(const float* __restrict__ theta, const float* __restrict__ s, cons
 #pragma unroll
       for (int r = 0; r < GR_PRE_ROWS; ++r) acc[r] = fmaf(xs[r * K + k], w, acc[r]);
     }
+  }
+  // fp16 operands: a layer-1 pre-activation beyond half of fp16's range would saturate silently (the sum PS + PA is formed
+  // in fp16) -- raise the handle's error flag (code 91) so that the caller switches to precision "bf16" / "fp32"
+  if (PREC == RLC_PREC_FP16 && j < H1) {
+    bool bad = false;
+#pragma unroll
+    for (int r = 0; r < GR_PRE_ROWS; ++r) bad = bad || ((r0 + r < (is_state ? B : N)) && !(fabsf(acc[r]) <= 32000.f));
+    if (bad) atomicCAS(err, 0, 91);
   }
   if (is_state) {
 #pragma unroll
@@ -639,10 +647,10 @@ static int rlc_eval_umma_grid(rlc_handle* h, const rlc_critic* c, const PackGeom
     const size_t pre_smem = (size_t)GR_PRE_ROWS * (c->S > c->A ? c->S : c->A) * sizeof(float);
     if (prec == RLC_PREC_BF16)
       k_grid_parts8<RLC_PREC_BF16><<<blocks, 128, pre_smem, st>>>(c->theta, s, a, c->smin, c->smax, B, N, c->S, c->A, c->H1,
-                                                                   c->H2, G.H1P, gp.CH, gp.nch, NT, sg, PS, PA);
+                                                                   c->H2, G.H1P, gp.CH, gp.nch, NT, sg, PS, PA, h->err_flag);
     else
       k_grid_parts8<RLC_PREC_FP16><<<blocks, 128, pre_smem, st>>>(c->theta, s, a, c->smin, c->smax, B, N, c->S, c->A, c->H1,
-                                                                   c->H2, G.H1P, gp.CH, gp.nch, NT, sg, PS, PA);
+                                                                   c->H2, G.H1P, gp.CH, gp.nch, NT, sg, PS, PA, h->err_flag);
     RLC_LAUNCH_CHECK(h);
   } else {
     const dim3 blocks((unsigned)(B + NT * 32), (unsigned)((G.H1P + 127) / 128));

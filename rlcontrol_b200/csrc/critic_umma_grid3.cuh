@@ -51,6 +51,9 @@ __host__ __device__ constexpr int g3_threads(int mode) { return 32 * (4 + g3_e1w
 #define G3_PA_PAD 4          // floats of padding per PA row: pitch (KC+4)*4 B keeps the 16-byte LDS conflict-free
 #define G3_MAX_WST 4
 #define G3_MAX_SLOT 3
+#ifndef POL_MAX_A
+#define POL_MAX_A 8          // same bound as reduce.cu's policy-fused reductions
+#endif
 #define G3_RANGE_LIMIT 32000.f   // |PS|, |PA| above this cannot be added and split in fp16 (max 65504): error flag 91
 
 struct Grid3Chunks {
@@ -84,6 +87,13 @@ struct Grid3Params {
   int sm_whi, whi_bytes;
   int sm_w, sm_pa, sm_ps, sm_qp, sm_bar, w_stage_bytes, w_half_bytes, pa_stage_bytes, ps_stage_bytes;
   int* err;
+  // fused per-state reduction (rlc_critic_eval_reduce_policy): 0 = none (q only), 1 = ForwardKL, 2 = ReverseKL.  Needs the
+  // state-major tile order (a CTA owns whole state groups across all NT action blocks), see tile_coords.
+  int fuse, state_major, A_pol;
+  int NSG;                    // number of 4-state groups = ceil(B / 4)
+  const float *fw, *fU, *fJ, *fmean, *flstd, *fv;     // w[N], U[A][N], J[N] (k_grid_logterms), mean/log_std [B][A], v[B] (RKL)
+  float alpha, inv_btotal;
+  float *loss_b, *dmean, *dlstd;
   long long* prof;            // RLC_UMMA_PROF=1: 32 x int64 per pair (cycle accounting per role)
   int micro;                  // RLC_UMMA_MICRO (diagnostic, output garbage): 1 = MMA issuer free-runs, everyone else idle;
                               // bit flags keeping the full barrier protocol: 2 = loaders copy nothing, 4 = epilogue 1 builds
@@ -377,7 +387,9 @@ __device__ __forceinline__ void ep1_unit(const float4* __restrict__ pa4, const f
   }
 }
 
-template <bool PROF, int MODE>
+// FA: 0 = evaluation only; > 0 = the per-state policy reduction fused into epilogue 2, compiled for action dimensions <= FA
+// (the reduction's running sums live in registers, so the plain kernel must not carry them)
+template <bool PROF, int MODE, int FA>
 __global__ void __launch_bounds__(G3_THREADS, 1) k_critic_umma_grid3(const Grid3Params P) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_addr = um::smem_u32(smem_raw);
@@ -442,17 +454,31 @@ __global__ void __launch_bounds__(G3_THREADS, 1) k_critic_umma_grid3(const Grid3
     }                                                                             \
   } while (0)
 
-  const int ntiles = (P.num_pair_tiles > (int)pair)
-                         ? (P.num_pair_tiles - (int)pair + (int)npairs - 1) / (int)npairs
-                         : 0;
+  // tiles of this pair.  Round-robin order: pair-tile t = pair + tl * npairs covers CTA tiles 2t, 2t+1 (any B).  State-major
+  // order (fused reduction): CTA g = 2*pair + rank owns state groups g, g + 2*npairs, ... and walks each group's NT action
+  // blocks consecutively, so that a state's N evaluations all pass through the same epilogue-2 threads.
+  const int Gc = 2 * (int)npairs;
+  const int ntiles = P.state_major
+                         ? ((P.NSG > 2 * (int)pair) ? ((P.NSG - 2 * (int)pair + Gc - 1) / Gc) * P.NT : 0)
+                         : ((P.num_pair_tiles > (int)pair) ? (P.num_pair_tiles - (int)pair + (int)npairs - 1) / (int)npairs : 0);
   const int nch = P.ch.nch, KC = P.KC;
   const uint32_t SLOT0 = (uint32_t)P.H2P;             // TMEM column of activation slot 0: [hi KC/2 | lo KC/2]
   const uint32_t nslot = (uint32_t)P.nslot, wst_n = (uint32_t)P.w_stages, past_n = (uint32_t)P.pa_stages;
-  auto tile_coords = [&](int tl, int& b0, int& n0) {
+  auto tile_coords = [&](int tl, int& b0, int& n0) -> bool {       // returns false for a padding tile (computed, never stored)
+    if (P.state_major) {
+      int sg = 2 * (int)pair + (int)rank + (tl / P.NT) * Gc;
+      const bool valid = sg < P.NSG;
+      if (!valid) sg = P.NSG - 1;
+      b0 = sg * 4;
+      n0 = (tl % P.NT) * 32;
+      return valid;
+    }
     long long ct = 2ll * ((long long)pair + (long long)tl * npairs) + rank;
-    if (ct >= P.num_cta_tiles) ct = P.num_cta_tiles - 1;   // odd tail: recompute the last tile, never stored twice
+    const bool valid = ct < P.num_cta_tiles;
+    if (!valid) ct = P.num_cta_tiles - 1;                  // odd tail: recompute the last tile, never stored twice
     b0 = (int)(ct / P.NT) * 4;
     n0 = (int)(ct % P.NT) * 32;
+    return valid;
   };
 
   if (warp == 0) {
@@ -720,6 +746,12 @@ __global__ void __launch_bounds__(G3_THREADS, 1) k_critic_umma_grid3(const Grid3
     const int rloc = q4 * 32 + lane;
     const int np = P.parts.np;
     bool ok = true;
+    // fused reduction state of this thread's (state, lane) across the state group's action blocks
+    constexpr int FAN = FA > 0 ? FA : 1;
+    float fm = -CUDART_INF_F, fz = 0.f, facc = 0.f, fgm[FAN], fgl[FAN];
+    float cmu = 0.f, ch = 0.f, cgs = 0.f, cc0 = 0.f, cvb = 0.f;
+#pragma unroll
+    for (int k = 0; k < FAN; ++k) { fgm[k] = 0.f; fgl[k] = 0.f; }
     for (int tl = 0; tl < ntiles && ok; ++tl) {
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       for (int p = 0; p < np; ++p) {
@@ -765,13 +797,96 @@ __global__ void __launch_bounds__(G3_THREADS, 1) k_critic_umma_grid3(const Grid3
       if (cg) qp[(cg - 1) * 128 + rloc] = acc;
       um::named_bar_sync(1, 128 * G3_E2G);
       if (!cg) {
-        const long long ct = 2ll * ((long long)pair + (long long)tl * npairs) + rank;
-        if (ct < P.num_cta_tiles) {
-          const int b = (int)(ct / P.NT) * 4 + q4, n = (int)(ct % P.NT) * 32 + lane;
-          float tot = acc;
+        int b0, n0;
+        const bool valid = tile_coords(tl, b0, n0);
+        const int b = b0 + q4, n = n0 + lane;
+        float tot = acc;
 #pragma unroll
-          for (int g = 0; g < G3_E2G - 1; ++g) tot += qp[g * 128 + rloc];
-          if (b < P.B && n < P.N) P.q[(size_t)b * P.N + n] = fmaf(0.5f * inv_scale, tot, b3v);   // tot = 2 x the signed sum
+        for (int g = 0; g < G3_E2G - 1; ++g) tot += qp[g * 128 + rloc];
+        const float qv = fmaf(0.5f * inv_scale, tot, b3v);       // tot = 2 x the signed sum
+        const bool live = valid && b < P.B && n < P.N;
+        if (live && P.q) P.q[(size_t)b * P.N + n] = qv;
+        if (FA > 0 && P.fuse) {
+          // ---- fused per-state reduction (the arithmetic of k_policy_reduce, reduce.cu; forwardkl_network.py:165-194 with
+          // get_logprob :324-351 in place; ReverseKL reversekl_network.py:181-203).  This thread sees q(s_b, a_n) for its
+          // state and n = lane, lane + 32, ...: ForwardKL keeps an ONLINE softmax (running max, rescaled sums).
+          const int A = P.A_pol, nb = P.state_major ? (tl % P.NT) : 0;
+          if (nb == 0) {                                   // new state group: per-state constants (lane k holds dimension k)
+            fz = 0.f; facc = 0.f; fm = -CUDART_INF_F;
+#pragma unroll
+            for (int k = 0; k < FAN; ++k) { fgm[k] = 0.f; fgl[k] = 0.f; }
+            const int bb = b < P.B ? b : P.B - 1;
+            float ls = 0.f;
+            if (lane < A) {
+              ls = __ldg(P.flstd + (size_t)bb * A + lane);
+              const float sd = expf(ls);
+              cmu = __ldg(P.fmean + (size_t)bb * A + lane);
+              ch = (A == 1) ? 0.5f / (sd * sd) : 0.5f / sd;
+              cgs = (A == 1) ? 1.f / (sd * sd) : 0.5f / sd;
+            }
+            float c = (A == 1) ? -ls : -0.5f * ls;                 // A == 1: Normal(mean, std); A > 1: std as covariance (:350)
+            c = (lane < A) ? c : 0.f;
+            c = warp_sum(c);
+            cc0 = c - 0.9189385332046727f * (float)A;
+            cvb = (P.fuse == 2) ? __ldg(P.fv + bb) : 0.f;
+          }
+          float lp = cc0, wn = 0.f, d[FAN];
+          if (n < P.N) { lp -= __ldg(P.fJ + n); wn = __ldg(P.fw + n); }
+#pragma unroll
+          for (int k = 0; k < FAN; ++k) {
+            const float mu_k = __shfl_sync(0xffffffffu, cmu, k), h_k = __shfl_sync(0xffffffffu, ch, k);
+            d[k] = 0.f;
+            if (k < A && n < P.N) {
+              d[k] = __ldg(P.fU + (size_t)k * P.N + n) - mu_k;
+              lp = fmaf(-h_k * d[k], d[k], lp);
+            }
+          }
+          float g = 0.f;                                  // weight of this (state, action) pair in the gradient sums
+          if (P.fuse == 1) {
+            const float x = qv * (1.f / P.alpha);
+            const float mn = live ? fmaxf(fm, x) : fm;
+            const float sc = (mn == fm) ? 1.f : expf(fm - mn);     // rescale of the running sums (exp(-inf) = 0 the first time)
+            const float e = live ? expf(x - mn) * wn : 0.f;
+            fm = mn;
+            fz = fmaf(fz, sc, e);
+            facc = fmaf(facc, sc, e * lp);
+#pragma unroll
+            for (int k = 0; k < FAN; ++k) { fgm[k] *= sc; fgl[k] *= sc; }
+            g = e;
+          } else if (live) {
+            const float pe = expf(lp), inner = (qv - cvb) - P.alpha * lp;
+            facc = fmaf(-pe * inner, wn, facc);
+            g = (-pe * (inner - P.alpha)) * wn;
+          }
+#pragma unroll
+          for (int k = 0; k < FAN; ++k) {
+            const float h_k = __shfl_sync(0xffffffffu, ch, k), gs_k = __shfl_sync(0xffffffffu, cgs, k);
+            if (k < A) {
+              fgm[k] = fmaf(g, 2.f * h_k * d[k], fgm[k]);
+              fgl[k] = fmaf(g, (A == 1) ? (gs_k * d[k] * d[k] - 1.f) : (gs_k * d[k] * d[k] - 0.5f), fgl[k]);
+            }
+          }
+          if (nb == P.NT - 1 || !P.state_major) {                  // the state's last action block: combine the 32 lanes
+            float sc = 1.f, zt = 1.f;
+            if (P.fuse == 1) {
+              const float M = warp_max(fm);
+              sc = (fm == -CUDART_INF_F) ? 0.f : expf(fm - M);
+              zt = warp_sum(fz * sc);
+            }
+            const float at = warp_sum(facc * sc);
+            const float post = (P.fuse == 1) ? -1.f / zt : 1.f;    // FKL: loss = -sum p lp, g = -p / B_total
+            if (lane == 0 && valid && b < P.B) P.loss_b[b] = (P.fuse == 1) ? -at / zt : at;
+#pragma unroll
+            for (int k = 0; k < FAN; ++k) {
+              if (k < A) {
+                const float gm_t = warp_sum(fgm[k] * sc) * post * P.inv_btotal, gl_t = warp_sum(fgl[k] * sc) * post * P.inv_btotal;
+                if (lane == 0 && valid && b < P.B) {
+                  if (P.dmean) P.dmean[(size_t)b * A + k] = gm_t;
+                  if (P.dlstd) P.dlstd[(size_t)b * A + k] = gl_t;
+                }
+              }
+            }
+          }
         }
       }
     }
@@ -916,6 +1031,15 @@ static int launch_pack_x3(rlc_handle* h, const float* theta, const PackGeom& G, 
 
 static inline int g3_mode_of(int prec) { return prec == RLC_PREC_FP16C8 ? G3_C8 : G3_X3; }
 
+static int rlc_eval_umma_grid3(rlc_handle* h, const rlc_critic* c, const float* s, int B, const float* a, int N,
+                               int prec, float* q_out, cudaStream_t st, const rlc_fuse_args* fuse);
+
+int rlc_eval_umma_grid3_fused(rlc_handle* h, const rlc_critic* c, const float* s, int B, const float* a, int N, int prec,
+                              float* q_out, const rlc_fuse_args* f, cudaStream_t st) {
+  if (h->sm_major != 10 || c->topology != RLC_TIN || (prec != RLC_PREC_FP16X3 && prec != RLC_PREC_FP16C8)) return RLC_ERR_UNSUPPORTED;
+  return rlc_eval_umma_grid3(h, c, s, B, a, N, prec, q_out, st, f);
+}
+
 bool rlc_umma3_supported(const rlc_handle* h, const rlc_critic* c, int prec) {
   if (h->sm_major != 10 || c->topology != RLC_TIN) return false;
   PackGeom G;
@@ -925,23 +1049,32 @@ bool rlc_umma3_supported(const rlc_handle* h, const rlc_critic* c, int prec) {
 }
 
 static int rlc_eval_umma_grid3(rlc_handle* h, const rlc_critic* c, const float* s, int B, const float* a, int N,
-                               int prec, float* q_out, cudaStream_t st) {
+                               int prec, float* q_out, cudaStream_t st, const rlc_fuse_args* fuse = nullptr) {
   PackGeom G;
   Grid3Plan gp;
   const int mode = g3_mode_of(prec);
   if (!make_geom3(c, G, mode) || !plan_grid3(G, h->smem_optin, gp, mode)) return RLC_ERR_UNSUPPORTED;
   if ((long long)B * N >= (1ll << 31)) return RLC_ERR_UNSUPPORTED;
+  // the fused reduction needs the state-major tile order: every CTA must own at least two whole state groups, or the
+  // persistent grid would idle (small minibatches keep the round-robin order and the separate reduction kernel)
+  if (fuse && ((B + 3) / 4 < 2 * h->num_sms || fuse->A < 1 || fuse->A > POL_MAX_A || fuse->A != c->A)) return RLC_ERR_UNSUPPORTED;
   rlc_pack* pk = nullptr;
   int rc = get_pack(h, c, prec, G, st, &pk);
   if (rc) return rc;
   const int NT = (N + 31) / 32;
   const int pitch = gp.KC + G3_PA_PAD;
-  const size_t nps = ((size_t)B * G.H1P + 63) & ~(size_t)63, npa = (size_t)gp.ch.nch * NT * 32 * pitch;
+  const size_t nps = ((size_t)B * G.H1P + 63) & ~(size_t)63, npa = ((size_t)gp.ch.nch * NT * 32 * pitch + 63) & ~(size_t)63;
+  const size_t nuj = fuse ? (size_t)N * (fuse->A + 1) : 0;
   void* ws = nullptr;
-  rc = rlc_workspace(h, (nps + npa) * sizeof(float) + 256, &ws);
+  rc = rlc_workspace(h, (nps + npa + nuj) * sizeof(float) + 256, &ws);
   if (rc) return rc;
   float* PS = (float*)ws;
   float* PA = PS + nps;                                        // 256-byte aligned
+  float* UJ = PA + npa;
+  if (fuse) {
+    rc = rlc_launch_grid_logterms(h, fuse->grid, N, fuse->A, fuse->action_scale, UJ, UJ + (size_t)N * fuse->A, st);
+    if (rc) return rc;
+  }
   {
     const int sg = (B + GR_PRE_ROWS - 1) / GR_PRE_ROWS, ag = (NT * 32 + GR_PRE_ROWS - 1) / GR_PRE_ROWS;
     const dim3 blocks((unsigned)(sg + ag), (unsigned)((G.H1P + 127) / 128));
@@ -969,6 +1102,13 @@ static int rlc_eval_umma_grid3(rlc_handle* h, const rlc_critic* c, const float* 
   P.sm_w = gp.sm_w; P.sm_pa = gp.sm_pa; P.sm_ps = gp.sm_ps; P.sm_qp = gp.sm_qp; P.sm_bar = gp.sm_bar;
   P.w_stage_bytes = gp.w_stage; P.w_half_bytes = gp.w_half; P.pa_stage_bytes = gp.pa_stage; P.ps_stage_bytes = gp.ps_stage;
   P.err = h->err_flag;
+  P.NSG = (B + 3) / 4;
+  if (fuse) {
+    P.fuse = fuse->mode; P.state_major = 1; P.A_pol = fuse->A;
+    P.fw = fuse->w; P.fU = UJ; P.fJ = UJ + (size_t)N * fuse->A; P.fmean = fuse->mean; P.flstd = fuse->log_std; P.fv = fuse->v;
+    P.alpha = fuse->alpha; P.inv_btotal = 1.f / (float)fuse->B_total;
+    P.loss_b = fuse->loss_b; P.dmean = fuse->dmean; P.dlstd = fuse->dlog_std;
+  }
 
   int pairs = h->num_sms / 2;
   if (pairs > P.num_pair_tiles) pairs = P.num_pair_tiles;
@@ -996,9 +1136,20 @@ static int rlc_eval_umma_grid3(rlc_handle* h, const rlc_critic* c, const float* 
     RLC_CUDA(cudaMemsetAsync(prof_dev, 0, (4096 + 4 * 2048) * sizeof(long long), st));
     P.prof = prof_dev;
   }
-  void (*kern)(const Grid3Params) =
-      mode == G3_C8 ? (P.prof ? k_critic_umma_grid3<true, G3_C8> : k_critic_umma_grid3<false, G3_C8>)
-                    : (P.prof ? k_critic_umma_grid3<true, G3_X3> : k_critic_umma_grid3<false, G3_X3>);
+  void (*kern)(const Grid3Params) = nullptr;
+  if (fuse) {
+    const int fa = fuse->A <= 1 ? 1 : fuse->A <= 2 ? 2 : fuse->A <= 4 ? 4 : fuse->A <= 6 ? 6 : 8;
+    P.prof = nullptr;
+#define G3_FUSED(M_)                                                                                            \
+    (fa == 1 ? k_critic_umma_grid3<false, M_, 1> : fa == 2 ? k_critic_umma_grid3<false, M_, 2>                   \
+     : fa == 4 ? k_critic_umma_grid3<false, M_, 4> : fa == 6 ? k_critic_umma_grid3<false, M_, 6>                 \
+                                                             : k_critic_umma_grid3<false, M_, 8>)
+    kern = mode == G3_C8 ? G3_FUSED(G3_C8) : G3_FUSED(G3_X3);
+#undef G3_FUSED
+  } else {
+    kern = mode == G3_C8 ? (P.prof ? k_critic_umma_grid3<true, G3_C8, 0> : k_critic_umma_grid3<false, G3_C8, 0>)
+                         : (P.prof ? k_critic_umma_grid3<true, G3_X3, 0> : k_critic_umma_grid3<false, G3_X3, 0>);
+  }
   RLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gp.total));
   RLC_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
   RLC_LAUNCH_CHECK(h);

@@ -544,6 +544,14 @@ extern "C" int rlc_reduce_rkl(rlc_handle* h, const float* q, const float* v, con
   return RLC_OK;
 }
 
+// U[k][n], J[n] tables of the grid (used by the fused evaluation + reduction of critic_umma_grid3.cuh as well)
+int rlc_launch_grid_logterms(rlc_handle* h, const float* grid, int N, int A, float action_scale, float* U, float* J,
+                             cudaStream_t st) {
+  k_grid_logterms<<<(N + 127) / 128, 128, 0, st>>>(grid, N, A, 1.f / action_scale, 1e-6f, U, J);
+  RLC_LAUNCH_CHECK(h);
+  return RLC_OK;
+}
+
 static int policy_reduce(rlc_handle* h, int mode, const float* q, const float* v, const float* w,
                          const float* grid, int A, float action_scale, const float* mean,
                          const float* log_std, int B, int N, float alpha, int B_total, float* loss_b_out,

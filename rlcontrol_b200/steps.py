@@ -25,8 +25,11 @@ class ForwardKLGridStep:
 
     def __init__(self, critic: Critic, grid, weights, action_scale: float, entropy_scale: float, B: int,
                  precision="auto", b_total: Optional[int] = None, use_graph: bool = True,
-                 repack_each_step: bool = False):
+                 repack_each_step: bool = False, keep_q: bool = False):
         eng = critic.eng
+        # one call per step (rlc_critic_eval_reduce_policy): evaluation kernel + policy-fused reduction kernel; q[B,N] is
+        # library scratch unless keep_q (then ``self.q`` holds it)
+        self.keep_q = bool(keep_q)
         dev = eng.device
         self.critic, self.eng = critic, eng
         self.grid, self.w = _f32(grid, dev), _f32(weights, dev).reshape(-1)
@@ -41,7 +44,7 @@ class ForwardKLGridStep:
         # mirrored on the device: ONE H2D and ONE D2H copy per step (each small copy costs a few us of latency)
         S, A = critic.S, self.A
         n_in, n_out = B * (S + 2 * A), B * (1 + 2 * A)
-        self._in_host = torch.empty((n_in,), dtype=torch.float32).pin_memory()
+        self._in_host = torch.zeros((n_in,), dtype=torch.float32).pin_memory()   # warm-up launches read it: no garbage
         self._out_host = torch.empty((n_out,), dtype=torch.float32).pin_memory()
         self._in_dev = torch.empty((n_in,), dtype=torch.float32, device=dev)
         self._out_dev = torch.empty((n_out,), dtype=torch.float32, device=dev)
@@ -67,9 +70,9 @@ class ForwardKLGridStep:
         self._in_dev.copy_(self._in_host, non_blocking=True)
         if self.repack:
             self.critic.invalidate()
-        self.critic.eval_into(self.s, self.grid, self.q, self.prec)
-        self.eng.fkl_policy(self.q, self.w, self.grid, self.scale, self.mean, self.log_std, self.alpha,
-                            b_total=self.b_total, out=self._out_views)
+        self.critic.eval_reduce_policy(self.s, self.grid, self.w, self.scale, self.mean, self.log_std, self.alpha,
+                                       b_total=self.b_total, precision=self.prec, want_q=self.q if self.keep_q else False,
+                                       out=self._out_views)
         self._out_host.copy_(self._out_dev, non_blocking=True)
 
     def _capture(self):
@@ -124,8 +127,9 @@ class ForwardKLGridPipeline:
     compute and host-side staging (a blocking ``__call__`` costs ~0.15 ms of it per step at cfg4)."""
 
     def __init__(self, critic: Critic, grid, weights, action_scale: float, entropy_scale: float, B: int,
-                 precision="auto", b_total: Optional[int] = None, depth: int = 2):
+                 precision="auto", b_total: Optional[int] = None, depth: int = 2, keep_q: bool = False):
         eng = critic.eng
+        self.keep_q = bool(keep_q)
         dev = eng.device
         self.critic, self.eng = critic, eng
         self.grid, self.w = _f32(grid, dev), _f32(weights, dev).reshape(-1)
@@ -148,7 +152,7 @@ class ForwardKLGridPipeline:
         self.slots = []
         for _ in range(max(1, int(depth))):
             sl = type("Slot", (), {})()
-            sl.in_host = torch.empty((n_in,), dtype=torch.float32).pin_memory()
+            sl.in_host = torch.zeros((n_in,), dtype=torch.float32).pin_memory()
             sl.out_host = torch.empty((n_out,), dtype=torch.float32).pin_memory()
             sl.in_dev = torch.empty((n_in,), dtype=torch.float32, device=dev)
             sl.out_dev = torch.empty((n_out,), dtype=torch.float32, device=dev)
@@ -173,9 +177,9 @@ class ForwardKLGridPipeline:
         self._next, self._oldest, self._outstanding = 0, 0, 0
 
     def _kernels(self, sl):
-        self.critic.eval_into(sl.d_in[0], self.grid, sl.q, self.prec)
-        self.eng.fkl_policy(sl.q, self.w, self.grid, self.scale, sl.d_in[1], sl.d_in[2], self.alpha,
-                            b_total=self.b_total, out=sl.d_out)
+        self.critic.eval_reduce_policy(sl.d_in[0], self.grid, self.w, self.scale, sl.d_in[1], sl.d_in[2], self.alpha,
+                                       b_total=self.b_total, precision=self.prec, want_q=sl.q if self.keep_q else False,
+                                       out=sl.d_out)
 
     def submit(self, states, mean, log_std):
         if self._outstanding == len(self.slots):
@@ -232,8 +236,8 @@ class GridAgentUpdateStep:
         self.grid, self.w = _f32(grid, dev), _f32(weights, dev).reshape(-1)
         self.N, self.A = self.grid.shape
         self.B, self.scale, self.alpha, self.prec = int(B), float(action_scale), float(entropy_scale), precision
-        pin = lambda *sh: torch.empty(sh, dtype=torch.float32).pin_memory()
-        devt = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)
+        pin = lambda *sh: torch.zeros(sh, dtype=torch.float32).pin_memory()     # the warm-up launches read these: no garbage
+        devt = lambda *sh: torch.zeros(sh, dtype=torch.float32, device=dev)
         S, A = critic.S, self.A
         self.host_in = dict(s=pin(B, S), a=pin(B, A), y=pin(B), mean=pin(B, A), log_std=pin(B, A), v=pin(B))
         self.dev_in = dict(s=devt(B, S), a=devt(B, A), y=devt(B), mean=devt(B, A), log_std=devt(B, A), v=devt(B))

@@ -27,6 +27,18 @@ def eng():
     return rb.Engine(0)
 
 
+@pytest.fixture(autouse=True)
+def _no_stale_kernel_error_flag(request):
+    """After every GPU test: the session handle's device error flag (bounded mbarrier waits, operand-range checks) must be
+    clear -- a test that provokes it reads (= clears) it itself, so a flag left behind is a failure of THAT test and never
+    leaks into the next one."""
+    yield
+    if "eng" in request.fixturenames:
+        e = request.getfixturevalue("eng")
+        code = e.umma_error()
+        assert code == 0, f"kernel error flag {code} left set by {request.node.name}"
+
+
 def rel_err(x, ref):
     """|x-ref| / max(|ref|, rms(ref) per state) -- the error metric of SURVEY 7 (element-wise
     relative error is undefined where Q crosses 0)."""

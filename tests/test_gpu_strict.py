@@ -170,6 +170,81 @@ def test_strict_range_flag(eng):
     cr = _tin(eng, p, S, A, H1, H2)
     s = (rng.randn(8, S) * 1e6).astype(np.float32)
     a = rng.uniform(-1, 1, (64, A)).astype(np.float32)
-    cr.eval(s, a, "fp16x3")
-    assert eng.umma_error() == 91
-    assert eng.umma_error() == 0            # cleared on read
+    for prec in ("fp16x3", "fp16c8", "fp16"):
+        cr.eval(s, a, prec)
+        assert eng.umma_error() == 91, prec
+        assert eng.umma_error() == 0            # cleared on read
+    q = cr.eval(s, a, "bf16")                   # bf16 has fp32's range: no flag, finite results
+    assert eng.umma_error() == 0 and np.isfinite(q.cpu().numpy()).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# fused evaluation + per-state policy reduction (rlc_critic_eval_reduce_policy): the reduction inside K1's epilogue
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["fkl", "rkl"])
+@pytest.mark.parametrize("prec", ["fp16x3", "fp16c8"])
+@pytest.mark.parametrize("S,A,H1,H2,B,N", [(17, 6, 400, 300, 1280, 1024), (3, 1, 200, 200, 1200, 62), (5, 2, 72, 40, 1333, 257)])
+def test_fused_eval_reduce_matches_composition_and_oracle(eng, kind, prec, S, A, H1, H2, B, N):
+    """B >= 8 x SMs: the reduction runs in the evaluation kernel (online softmax across a state's action blocks, state-major
+    tiles).  It must agree with the two-kernel composition on the same q (1e-5) and with the fp64 oracle evaluated on the
+    EXACT q (loss / gradients to the precision the mode's q carries), with and without the q output."""
+    import torch
+    rng = np.random.RandomState(B + N + A)
+    p = _rand_tin(rng, S, A, H1, H2, last=3.0)
+    cr = _tin(eng, p, S, A, H1, H2)
+    s = rng.randn(B, S).astype(np.float32)
+    a = rng.uniform(-0.95, 0.95, (N, A)).astype(np.float32)
+    w = rng.uniform(0.5, 1.5, N).astype(np.float32) / N
+    mean = (rng.randn(B, A) * 0.5).astype(np.float32)
+    lstd = (rng.randn(B, A) * 0.3 - 0.5).astype(np.float32)
+    v = rng.randn(B).astype(np.float32)
+    alpha = 0.2
+    lb, dm, ds, q = cr.eval_reduce_policy(s, a, w, 1.0, mean, lstd, alpha, kind=kind, v=v, precision=prec, want_q=True,
+                                          b_total=2 * B, fuse=True)
+    assert eng.umma_error() == 0
+    lb2, dm2, ds2, q_none = cr.eval_reduce_policy(s, a, w, 1.0, mean, lstd, alpha, kind=kind, v=v, precision=prec, b_total=2 * B,
+                                                  fuse=True)
+    assert q_none is None
+    for x, y in ((lb, lb2), (dm, dm2), (ds, ds2)):
+        assert torch.equal(x, y)                                   # the q output does not change the reduction
+    assert torch.equal(q, cr.eval(s, a, prec))                     # same q as the plain evaluation, bit for bit
+    t = lambda z: torch.as_tensor(z, device=eng.device)
+    if kind == "fkl":
+        ref = eng.fkl_policy(q, t(w), t(a), 1.0, t(mean), t(lstd), alpha, b_total=2 * B)
+    else:
+        ref = eng.rkl_policy(q, t(v), t(w), t(a), 1.0, t(mean), t(lstd), alpha, b_total=2 * B)
+    for mine, r in zip((lb, dm, ds), ref[:3]):
+        r = r.cpu().numpy()
+        np.testing.assert_allclose(mine.cpu().numpy(), r, rtol=2e-4, atol=2e-5 * max(1e-6, np.abs(r).max()))
+    rows = np.r_[0:8, B - 8:B]
+    q64 = onp.tin_eval(s[rows], a, p, dtype=np.float64)
+    if kind == "fkl":
+        o = onp.fkl_policy_reduce(q64, w, a, mean[rows], lstd[rows], 1.0, alpha)
+    else:
+        o = onp.rkl_policy_reduce(q64, v[rows], w, a, mean[rows], lstd[rows], 1.0, alpha)
+    scale = len(rows) / (2 * B)          # the oracle's gradients are for the mean over `rows`, the kernel's for 1 / b_total
+    tol = 5e-3 if prec == "fp16c8" else 5e-4
+    np.testing.assert_allclose(lb.cpu().numpy()[rows], o[0], rtol=tol, atol=tol * np.abs(o[0]).max())
+    np.testing.assert_allclose(dm.cpu().numpy()[rows], o[1] * scale, rtol=tol, atol=tol * np.abs(o[1] * scale).max())
+    np.testing.assert_allclose(ds.cpu().numpy()[rows], o[2] * scale, rtol=tol, atol=tol * np.abs(o[2] * scale).max())
+
+
+def test_fused_eval_reduce_small_batch_composes(eng):
+    """Below 8 x SMs states the call composes the evaluation and the reduction kernel (same API, same results); fp32 too."""
+    import torch
+    rng = np.random.RandomState(2)
+    S, A, H1, H2, B, N = 5, 2, 72, 40, 96, 200
+    p = _rand_tin(rng, S, A, H1, H2, last=3.0)
+    cr = _tin(eng, p, S, A, H1, H2)
+    s = rng.randn(B, S).astype(np.float32)
+    a = rng.uniform(-0.95, 0.95, (N, A)).astype(np.float32)
+    w = np.full(N, 2.0 / N, np.float32)
+    mean, lstd = (rng.randn(B, A) * 0.5).astype(np.float32), (rng.randn(B, A) * 0.3 - 0.5).astype(np.float32)
+    t = lambda z: torch.as_tensor(z, device=eng.device)
+    for prec in ("fp32", "fp16x3", "auto"):
+        for fuse in (True, False):
+            lb, dm, ds, q = cr.eval_reduce_policy(s, a, w, 1.0, mean, lstd, 0.3, precision=prec, want_q=True, fuse=fuse)
+            ref = eng.fkl_policy(cr.eval(s, a, prec), t(w), t(a), 1.0, t(mean), t(lstd), 0.3)
+            assert torch.equal(lb, ref[0]) and torch.equal(dm, ref[1]) and torch.equal(ds, ref[2])
+            lb2 = cr.eval_reduce_policy(s, a, w, 1.0, mean, lstd, 0.3, precision=prec, fuse=fuse)[0]
+            assert torch.equal(lb, lb2)
