@@ -40,7 +40,8 @@ if os.path.exists(rep):
             return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
         traffic = sum(tob(r[ir], units[ir]) + tob(r[iw], units[iw]) for r in rows[2:]) / (len(rows) - 2)
         kname = rows[2][kn]
-        prec = "fp16x3" if "grid3" in kname else "fp16"
+        m3 = re.search(r"grid3<[^,]*,\s*(?:\(int\))?(\d)", kname)
+        prec = ("fp16c8" if m3 and m3.group(1) == "1" else "fp16x3") if "grid3" in kname else "fp16"
         tj = os.path.join(P, "k1_traffic.json")
         cur = json.load(open(tj)) if os.path.exists(tj) else {}
         cur["dram_bytes_per_launch_" + prec] = traffic
