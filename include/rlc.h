@@ -266,6 +266,21 @@ int rlc_mlp_forward(rlc_handle* h, const rlc_mlp* m, const float* x, int B, floa
 int rlc_mlp_grads(rlc_handle* h, const rlc_mlp* m, const float* x, const float* act,
                   const float* dout, int B, float* grad_out, float* dx_out, void* stream);
 
+/* The GEMM the B-row layers above (torch.nn.Linear forward/backward on the minibatch, forwardkl_network.py:263-268,
+ * 283-290,296-301 and their autograd) and rlc_critic_grads / rlc_critic_grad_action are built from, for parity tests and
+ * callers with their own layer structure:  C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] (+ bias[N]), A := relu(A) at load when
+ * relu_a, C *= (maskZ > 0) when maskZ (same shape as C, leading dimension ldz); row-major with leading dimensions;
+ * trans_a: A is stored [K,M]; trans_b: B is stored [N,K].  split_k != 0 (weight gradients X^T G: trans_a, !trans_b, no
+ * bias/mask, ldc == N) splits the long K = batch dimension over the grid and sums the slabs in a fixed order.
+ * path: 0 = dispatcher (tcgen05 3xTF32 kernel for dense launches, fp32 CUDA-core tile kernel for small ones), 1 = CUDA
+ * cores, 2 = tensor cores whatever the shape.  Both paths are fp32-class (<= ~1e-6 relative). */
+int rlc_rows_gemm(rlc_handle* h, int trans_a, int trans_b, int M, int N, int K, const float* A, int lda, const float* B,
+                  int ldb, float* C, int ldc, const float* bias, const float* maskZ, int ldz, int relu_a, float alpha,
+                  int split_k, int path, void* stream);
+/* Diagnostic: pin the dispatcher of every B-row GEMM issued by THIS host thread (rlc_critic_grads, rlc_mlp_*, ...):
+ * -1 = default, 0 = CUDA cores only, 2 = tensor cores whatever the shape.  Returns the previous setting. */
+int rlc_rows_gemm_force(int mode);
+
 /* PolicyNetwork.evaluate (forwardkl_network.py:303-322, reversekl_network.py:325-344) on the policy
  * head head[B,2A] = [mean_raw | log_std_raw]; eps[B,A] = the N(0,1) draws behind normal.sample()
  * (NULL = zeros, i.e. the mean action).  A == 1: Normal(mean, std); A > 1: MultivariateNormal with

@@ -576,7 +576,7 @@ static size_t train_ws_bytes(const rlc_critic* c, long long R) {
   size_t n = (size_t)R * (t.in1 + 2 * (size_t)c->H1 + 2 * (size_t)c->H2 + 1);
   if (c->topology == RLC_TMID) n += (size_t)R * (c->H1 + c->A);
   const size_t maxw = (size_t)(c->H1 > c->H2 ? c->H1 : c->H2) + 1;
-  n += (size_t)SPLITK_MAX * (size_t)(t.in2 > t.in1 ? t.in2 : t.in1) * maxw;   // split-K slabs of the largest weight
+  n += (size_t)SPLITK_MAX * ((size_t)(t.in2 > t.in1 ? t.in2 : t.in1) + 1) * maxw;   // split-K slabs of the largest weight
   n += (size_t)COLRED_MAX_CHUNKS * maxw;                                        // column-reduction partials
   return n * sizeof(float) + 64 * 16;
 }
@@ -597,7 +597,7 @@ static TrainWs carve(const rlc_critic* c, long long R, float* base) {
   w.G1 = take((size_t)R * c->H1);
   w.dq = take((size_t)R);
   const size_t maxw = (size_t)(c->H1 > c->H2 ? c->H1 : c->H2) + 1;
-  w.slabs = take((size_t)SPLITK_MAX * (size_t)(t.in2 > t.in1 ? t.in2 : t.in1) * maxw);
+  w.slabs = take((size_t)SPLITK_MAX * ((size_t)(t.in2 > t.in1 ? t.in2 : t.in1) + 1) * maxw);
   w.part = take((size_t)COLRED_MAX_CHUNKS * maxw);
   return w;
 }
@@ -701,27 +701,23 @@ extern "C" int rlc_critic_grads(rlc_handle* h, const rlc_critic* c, const float*
   // gw3[j] = sum_r relu(Z2[r,j]) dq[r], gb3 = sum_r dq[r]: theta stores [w3 (H2) | b3 (1)] contiguously
   rc = colred<1>(h, w.Z2, w.dq, B, c->H2, c->H2, w.part, grad_out + t.ow3, st);
   if (rc) return rc;
-  // gb2 = colsum(G2)
-  rc = colred<0>(h, w.G2, nullptr, B, c->H2, c->H2, w.part, grad_out + t.ob2, st);
-  if (rc) return rc;
+  // [gW2 ; gb2] = [relu(Z1) | 1]^T G2 (theta stores W2 and b2 contiguously)
   GemmEpi e{nullptr, nullptr, 0, 0, 1.f};
   if (c->topology == RLC_TIN) {
     GemmEpi er = e;
-    er.reluA = 1;  // gW2 = relu(Z1)^T G2
-    rc = gemm_splitk(h, c->H1, c->H2, B, w.Z1, c->H1, w.G2, c->H2, grad_out + t.oW2, er, w.slabs, st);
+    er.reluA = 1;
+    rc = gemm_splitk_bias(h, c->H1, c->H2, B, w.Z1, c->H1, w.G2, c->H2, grad_out + t.oW2, er, w.slabs, w.part, st);
   } else {
-    rc = gemm_splitk(h, c->H1 + c->A, c->H2, B, w.ZC, c->H1 + c->A, w.G2, c->H2, grad_out + t.oW2, e,
-                     w.slabs, st);
+    rc = gemm_splitk_bias(h, c->H1 + c->A, c->H2, B, w.ZC, c->H1 + c->A, w.G2, c->H2, grad_out + t.oW2, e, w.slabs,
+                          w.part, st);
   }
   if (rc) return rc;
   // G1 = (G2 W2[:H1]^T) * [Z1>0]
   GemmEpi em{nullptr, w.Z1, c->H1, 0, 1.f};
   rc = gemm(h, false, true, B, c->H1, c->H2, w.G2, c->H2, th + t.oW2, c->H2, w.G1, c->H1, em, st);
   if (rc) return rc;
-  rc = colred<0>(h, w.G1, nullptr, B, c->H1, c->H1, w.part, grad_out + t.ob1, st);
-  if (rc) return rc;
-  // gW1 = X^T G1
-  return gemm_splitk(h, t.in1, c->H1, B, w.X, t.in1, w.G1, c->H1, grad_out + t.oW1, e, w.slabs, st);
+  // [gW1 ; gb1] = [X | 1]^T G1
+  return gemm_splitk_bias(h, t.in1, c->H1, B, w.X, t.in1, w.G1, c->H1, grad_out + t.oW1, e, w.slabs, w.part, st);
 }
 
 // T-mid dQ/da over a B x N block without materialising the stack (AE+ ascent, ae_plus_network.py:

@@ -37,6 +37,29 @@ extern "C" int rlc_mlp_offsets(int in, int H1, int H2, int O, int64_t off[6]) {
   return RLC_OK;
 }
 
+// The GEMM every B-row layer above is made of, exposed for parity tests and callers with their own layer structure.
+extern "C" int rlc_rows_gemm(rlc_handle* h, int trans_a, int trans_b, int M, int N, int K, const float* A, int lda,
+                             const float* Bm, int ldb, float* C, int ldc, const float* bias, const float* maskZ, int ldz,
+                             int relu_a, float alpha, int split_k, int path, void* stream) {
+  RLC_REQUIRE(h && A && Bm && C && M >= 0 && N >= 0 && K >= 0 && lda >= 1 && ldb >= 1 && ldc >= N);
+  RLC_REQUIRE(path == 0 || path == 1 || path == 2);
+  RLC_REQUIRE(!split_k || (trans_a && !trans_b && !bias && !maskZ && ldc == N));
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmEpi e{bias, maskZ, ldz, relu_a, alpha};
+  const int prev = rlc_gemm_tc_forced();
+  if (path != 0) rlc_gemm_tc_force(path == 1 ? 0 : 2);
+  int rc;
+  if (split_k) {
+    void* ws = nullptr;
+    rc = rlc_workspace(h, (size_t)SPLITK_MAX * M * N * sizeof(float) + 256, &ws);
+    if (!rc) rc = gemm_splitk(h, M, N, K, A, lda, Bm, ldb, C, e, (float*)ws, st);
+  } else {
+    rc = gemm(h, trans_a != 0, trans_b != 0, M, N, K, A, lda, Bm, ldb, C, ldc, e, st);
+  }
+  rlc_gemm_tc_force(prev);
+  return rc;
+}
+
 // Z1 = X W1 + b1 ; Z2 = relu(Z1) W2 + b2 ; out = relu(Z2) W3 + b3   (pre-activations kept)
 static int mlp_forward_rows(rlc_handle* h, const rlc_mlp* m, const float* x, int B, float* Z1,
                             float* Z2, float* out, cudaStream_t st) {
@@ -59,7 +82,7 @@ static size_t mlp_ws_floats(const rlc_mlp* m, long long B, bool need_act, bool n
     const size_t maxw = (size_t)(m->H1 > m->H2 ? m->H1 : m->H2) + 1;
     const size_t maxin = (size_t)(m->in > m->H1 ? m->in : m->H1);
     n += (size_t)B * ((size_t)m->H1 + m->H2 + m->O) + 16;
-    n += (size_t)SPLITK_MAX * (maxin > (size_t)m->H2 ? maxin : (size_t)m->H2) * maxw;
+    n += (size_t)SPLITK_MAX * ((maxin > (size_t)m->H2 ? maxin : (size_t)m->H2) + 1) * maxw;
     n += (size_t)COLRED_MAX_CHUNKS * maxw;
   }
   return n;
@@ -119,30 +142,25 @@ extern "C" int rlc_mlp_grads(rlc_handle* h, const rlc_mlp* m, const float* x, co
   float* G1 = take((size_t)B * m->H1);
   const size_t maxw = (size_t)(m->H1 > m->H2 ? m->H1 : m->H2) + 1;
   const size_t maxin = (size_t)(m->in > m->H1 ? m->in : m->H1);
-  float* slabs = take((size_t)SPLITK_MAX * (maxin > (size_t)m->H2 ? maxin : (size_t)m->H2) * maxw);
+  float* slabs = take((size_t)SPLITK_MAX * ((maxin > (size_t)m->H2 ? maxin : (size_t)m->H2) + 1) * maxw);
   float* part = take((size_t)COLRED_MAX_CHUNKS * maxw);
   GemmEpi e{nullptr, nullptr, 0, 0, 1.f};
   GemmEpi er{nullptr, nullptr, 0, 1, 1.f};
+  // every layer: [gW ; gb] = [input | 1]^T G, contiguous in theta
   // output layer: gW3 = relu(Z2)^T dout ; gb3 = colsum(dout)
-  rc = gemm_splitk(h, m->H2, m->O, B, Z2, m->H2, dout, m->O, grad_out + t.oW3, er, slabs, st);
-  if (rc) return rc;
-  rc = colred<0>(h, dout, nullptr, B, m->O, m->O, part, grad_out + t.ob3, st);
+  rc = gemm_splitk_bias(h, m->H2, m->O, B, Z2, m->H2, dout, m->O, grad_out + t.oW3, er, slabs, part, st);
   if (rc) return rc;
   // G2 = (dout W3^T) * [Z2 > 0]
   GemmEpi em2{nullptr, Z2, m->H2, 0, 1.f};
   rc = gemm(h, false, true, B, m->H2, m->O, dout, m->O, th + t.oW3, m->O, G2, m->H2, em2, st);
   if (rc) return rc;
-  rc = colred<0>(h, G2, nullptr, B, m->H2, m->H2, part, grad_out + t.ob2, st);
-  if (rc) return rc;
-  rc = gemm_splitk(h, m->H1, m->H2, B, Z1, m->H1, G2, m->H2, grad_out + t.oW2, er, slabs, st);
+  rc = gemm_splitk_bias(h, m->H1, m->H2, B, Z1, m->H1, G2, m->H2, grad_out + t.oW2, er, slabs, part, st);
   if (rc) return rc;
   // G1 = (G2 W2^T) * [Z1 > 0]
   GemmEpi em1{nullptr, Z1, m->H1, 0, 1.f};
   rc = gemm(h, false, true, B, m->H1, m->H2, G2, m->H2, th + t.oW2, m->H2, G1, m->H1, em1, st);
   if (rc) return rc;
-  rc = colred<0>(h, G1, nullptr, B, m->H1, m->H1, part, grad_out + t.ob1, st);
-  if (rc) return rc;
-  rc = gemm_splitk(h, m->in, m->H1, B, x, m->in, G1, m->H1, grad_out + t.oW1, e, slabs, st);
+  rc = gemm_splitk_bias(h, m->in, m->H1, B, x, m->in, G1, m->H1, grad_out + t.oW1, e, slabs, part, st);
   if (rc) return rc;
   if (dx_out)  // dX = G1 W1^T
     rc = gemm(h, false, true, B, m->in, m->H1, G1, m->H1, th + t.oW1, m->H1, dx_out, m->in, e, st);

@@ -2,20 +2,15 @@
 // B-row training paths (critic_fp32.cu: critic regression / dQ/da; mlp_rows.cu: value and policy nets).
 #pragma once
 #include "common.cuh"
+#include "rows_gemm_tc.cuh"
 
 // =============================================================================================
 // Tiled SGEMM used by the B-row training path and the T-in dQ/da:
 //   C[M,N] = opA(A)[M,K] * opB(B)[K,N]  (+ bias[N]) ; optional relu on A at load (A := relu(A)),
-//   optional mask multiply C *= (Z > 0).  Row-major with leading dimensions.
+//   optional mask multiply C *= (Z > 0).  Row-major with leading dimensions (GemmEpi: rows_gemm_tc.cuh).
+// Launches that are dense contractions (minibatches of >= ~1k rows) go to the tcgen05 kernel of rows_gemm_tc.cu
+// (3 x TF32 split, fp32-class results); this CUDA-core kernel keeps the latency-bound small ones.
 // =============================================================================================
-struct GemmEpi {
-  const float* bias;   // per output column or nullptr
-  const float* maskZ;  // same shape/ld as C or nullptr: C *= (Z>0)
-  int ldz;
-  int reluA;
-  float alpha;
-};
-
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256)
 k_gemm(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ Bm,
@@ -114,6 +109,8 @@ static int gemm_z(rlc_handle* h, bool ta, bool tb, int M, int N, int K, const fl
                   const float* Bm, int ldb, float* C, int ldc, GemmEpi epi, int nz, int klen,
                   long long cz_stride, cudaStream_t st) {
   if (M == 0 || N == 0) return RLC_OK;
+  if ((nz == 1 || klen % 32 == 0) && rlc_gemm_tc_ok(h, M, N, K))
+    return rlc_gemm_tc(h, ta, tb, M, N, K, A, lda, Bm, ldb, C, ldc, epi, nz, klen, cz_stride, st);
   dim3 grid((N + 63) / 64, (M + 63) / 64, nz);
   if (!ta && !tb) k_gemm<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, Bm, ldb, C, ldc, epi, klen, cz_stride);
   else if (ta && !tb) k_gemm<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, Bm, ldb, C, ldc, epi, klen, cz_stride);
@@ -142,18 +139,52 @@ static __global__ void k_sum_slabs(const float* __restrict__ part, long long n, 
 #define SPLITK_MAX 32
 static int gemm_splitk(rlc_handle* h, int M, int N, int K, const float* A, int lda, const float* Bm, int ldb,
                        float* C, GemmEpi epi, float* slabs, cudaStream_t st) {
-  int nz = (K + 127) / 128;
-  if (nz > SPLITK_MAX) nz = SPLITK_MAX;
+  int nz, klen = K > 0 ? K : 1;
+  if (slabs && rlc_gemm_tc_ok(h, M, N, K)) {
+    rlc_gemm_tc_splitk_plan(h, M, N, K, SPLITK_MAX, &nz, &klen);   // slices sized to fill the SMs with 128 x 128 tiles
+  } else {
+    nz = (K + 127) / 128;
+    if (nz > SPLITK_MAX) nz = SPLITK_MAX;
+    if (nz > 1) {
+      klen = (K + nz - 1) / nz;
+      klen = (klen + 15) & ~15;
+      nz = (K + klen - 1) / klen;
+    }
+  }
   if (nz <= 1 || !slabs) return gemm(h, true, false, M, N, K, A, lda, Bm, ldb, C, N, epi, st);
-  int klen = (K + nz - 1) / nz;
-  klen = (klen + 15) & ~15;
-  nz = (K + klen - 1) / klen;
   int rc = gemm_z(h, true, false, M, N, K, A, lda, Bm, ldb, slabs, N, epi, nz, klen, (long long)M * N, st);
   if (rc) return rc;
   const long long n = (long long)M * N;
   k_sum_slabs<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(slabs, n, nz, C);
   RLC_LAUNCH_CHECK(h);
   return RLC_OK;
+}
+
+// forward declaration (defined below)
+template <int MODE>
+static int colred(rlc_handle* h, const float* Mx, const float* dq, long long R, int N, int ld, float* part,
+                  float* out, cudaStream_t st);
+
+// Weight AND bias gradient of one layer, contiguous in theta's layout: C[(M+1),N] = [op(A) | 1]^T G, i.e. rows 0..M-1 =
+// A^T G (dW, [in,out]-major) and row M = column sums of G (db).  Dense launches: ONE split-K tensor-core GEMM whose
+// producer supplies the ones row; small ones: the CUDA-core split-K GEMM + the two-stage column reduction.
+static int gemm_splitk_bias(rlc_handle* h, int M, int N, int K, const float* A, int lda, const float* G, int ldg,
+                            float* C, GemmEpi epi, float* slabs, float* part, cudaStream_t st) {
+  if (slabs && rlc_gemm_tc_ok(h, M + 1, N, K)) {
+    int nz, klen;
+    rlc_gemm_tc_splitk_plan(h, M + 1, N, K, SPLITK_MAX, &nz, &klen);
+    epi.onesA = 1;
+    const long long n = (long long)(M + 1) * N;
+    if (nz <= 1) return rlc_gemm_tc(h, true, false, M + 1, N, K, A, lda, G, ldg, C, N, epi, 1, K, 0, st);
+    int rc = rlc_gemm_tc(h, true, false, M + 1, N, K, A, lda, G, ldg, slabs, N, epi, nz, klen, n, st);
+    if (rc) return rc;
+    k_sum_slabs<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(slabs, n, nz, C);
+    RLC_LAUNCH_CHECK(h);
+    return RLC_OK;
+  }
+  int rc = gemm_splitk(h, M, N, K, A, lda, G, ldg, C, epi, slabs, st);
+  if (rc) return rc;
+  return colred<0>(h, G, nullptr, K, N, ldg, part, C + (long long)M * N, st);
 }
 
 // Column reductions over the batch rows, two deterministic stages: stage 1 = one block per
