@@ -280,6 +280,9 @@ int rlc_rows_gemm(rlc_handle* h, int trans_a, int trans_b, int M, int N, int K, 
 /* Diagnostic: pin the dispatcher of every B-row GEMM issued by THIS host thread (rlc_critic_grads, rlc_mlp_*, ...):
  * -1 = default, 0 = CUDA cores only, 2 = tensor cores whatever the shape.  Returns the previous setting. */
 int rlc_rows_gemm_force(int mode);
+/* Same for the T-mid evaluation of large B x N stacks (rlc_critic_eval, RLC_TMID): -1 = default (tcgen05 tiles when the
+ * stack fills the machine), 0 = fp32 CUDA cores only, 2 = tensor cores whenever the shape is supported. */
+int rlc_tmid_tc_force(int mode);
 
 /* PolicyNetwork.evaluate (forwardkl_network.py:303-322, reversekl_network.py:325-344) on the policy
  * head head[B,2A] = [mean_raw | log_std_raw]; eps[B,A] = the N(0,1) draws behind normal.sample()

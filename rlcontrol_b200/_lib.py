@@ -116,6 +116,7 @@ SIGNATURES = {
     "rlc_mlp_grads": (_i, [_p, _ml, _p, _p, _p, _i, _p, _p, _p]),
     "rlc_rows_gemm": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _i, _p, _p, _i, _i, _f, _i, _i, _p]),
     "rlc_rows_gemm_force": (_i, [_i]),
+    "rlc_tmid_tc_force": (_i, [_i]),
     "rlc_policy_evaluate": (_i, [_p, _p, _p, _i, _i, _f, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
     "rlc_kl_targets": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _i, _p, _p, _p, _p]),
     "rlc_policy_head_grad": (_i, [_p, _p, _i, _i, _f, _f, _i, _p, _p, _p, _p, _p, _p, _f, _i, _p, _p, _p]),

@@ -104,8 +104,15 @@ int rlc_eval_umma(rlc_handle* h, const rlc_critic* c, const float* s, int B, con
 bool rlc_umma_supported(const rlc_handle* h, const rlc_critic* c, int B, int N);
 bool rlc_umma3_supported(const rlc_handle* h, const rlc_critic* c, int prec);   // split modes (FP16X3 / FP16C8), shared grids
 // p[B,H2] = relu(clip(s) W1 + b1) W2[:H1] + b2 for a T-mid critic (state-only hoisted term)
+// scratch (optional, rlc_tmid_state_scratch_floats(c, B) floats): lets dense state batches run as tensor-core GEMMs
 int rlc_tmid_state_term(rlc_handle* h, const rlc_critic* c, const float* s, int B, float* p_out,
-                        cudaStream_t st);
+                        cudaStream_t st, float* scratch = nullptr);
+size_t rlc_tmid_state_scratch_floats(const rlc_critic* c, int B);
+
+// T-mid rows of a B x N stack on the tensor cores (tmid_rows_tc.cu); p = state terms [B,H2]
+bool rlc_tmid_tc_ok(const rlc_handle* h, const rlc_critic* c, long long R, int N);
+int rlc_tmid_rows_tc(rlc_handle* h, const rlc_critic* c, const float* p, const float* a, int act_per_state, int B, int N,
+                     float* q_out, cudaStream_t st);
 
 // U[k][n] = atanh(a_nk / scale), J[n] = sum_k log(1 - (a_nk/scale)^2 + 1e-6): grid-only terms of the policy log-density (reduce.cu)
 int rlc_launch_grid_logterms(rlc_handle* h, const float* grid, int N, int A, float action_scale, float* U, float* J,

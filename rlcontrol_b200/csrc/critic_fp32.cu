@@ -275,10 +275,30 @@ k_state_term_cols(const float* __restrict__ s, int R, int S, int H1, int H2, con
   if (row < R && col < H2) out[(long long)row * H2 + col] = acc + __ldg(b2 + col);
 }
 
+__global__ void k_build_x(const float* __restrict__ s, const float* __restrict__ a, long long R, int S, int A, int tin,
+                          const float* __restrict__ smin, const float* __restrict__ smax, float* __restrict__ X, int rep);
+
+size_t rlc_tmid_state_scratch_floats(const rlc_critic* c, int B) {
+  return (((size_t)B * c->S + 3) & ~(size_t)3) + (size_t)B * c->H1 + 64;
+}
+
 int rlc_tmid_state_term(rlc_handle* h, const rlc_critic* c, const float* s, int B, float* p_out,
-                        cudaStream_t st) {
+                        cudaStream_t st, float* scratch) {
   const ThetaView t = theta_view(RLC_TMID, c->S, c->A, c->H1, c->H2);
   const float* th = c->theta;
+  if (scratch && B > 0 && rlc_gemm_tc_ok(h, B, c->H2, c->H1)) {
+    // dense batch of states: two GEMMs on the tensor cores (3xTF32, fp32-class) instead of the fused fp32 row kernel
+    float* X = scratch;
+    float* Z1 = scratch + (((size_t)B * c->S + 3) & ~(size_t)3);
+    const long long n = (long long)B * c->S;
+    k_build_x<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s, nullptr, B, c->S, c->A, 0, c->smin, c->smax, X, 1);
+    RLC_LAUNCH_CHECK(h);
+    GemmEpi e1{th + t.ob1, nullptr, 0, 0, 1.f};
+    int rc = gemm(h, false, false, B, c->H1, c->S, X, c->S, th + t.oW1, c->H1, Z1, c->H1, e1, st);
+    if (rc) return rc;
+    GemmEpi e2{th + t.ob2, nullptr, 0, 1, 1.f};   // A := relu(Z1); W2[:H1] are the first H1 rows of W2
+    return gemm(h, false, false, B, c->H2, c->H1, Z1, c->H1, th + t.oW2, c->H2, p_out, c->H2, e2, st);
+  }
   {
     const int K1P = (c->S + 3) & ~3, H1P = (c->H1 + 3) & ~3;
     const size_t smem = (size_t)(STC_ROWS * K1P + STC_ROWS * H1P + c->H1 * 32) * sizeof(float);
@@ -449,6 +469,8 @@ static int launch_tmid_rows(rlc_handle* h, const rlc_critic* c, const float* p, 
                             int act_per_state, long long R, int N, float* q_out, float* dqda_out,
                             cudaStream_t st) {
   if (R == 0) return RLC_OK;
+  if (!GRAD && q_out && N > 0 && R % N == 0 && rlc_tmid_tc_ok(h, c, R, N))   // large stacks: 128-row tiles on tcgen05
+    return rlc_tmid_rows_tc(h, c, p, a, act_per_state, (int)(R / N), N, q_out, st);
   if (!GRAD && q_out && R >= (long long)h->num_sms * 256 * TMID_RPT && c->A <= 8) {   // enough rows to fill the machine
     switch (c->A) {
       case 1: return launch_tmid_rows4<1>(h, c, p, a, act_per_state, R, N, q_out, st);
@@ -500,10 +522,11 @@ int rlc_eval_fp32(rlc_handle* h, const rlc_critic* c, const float* s, int B, con
                                    th + t.ow3, th + t.ob3, c->smin, c->smax, q_out, st);
   }
   void* ws = nullptr;
-  int rc = rlc_workspace(h, (size_t)B * c->H2 * sizeof(float), &ws);
+  const size_t np = ((size_t)B * c->H2 + 3) & ~(size_t)3;
+  int rc = rlc_workspace(h, (np + rlc_tmid_state_scratch_floats(c, B)) * sizeof(float), &ws);
   if (rc) return rc;
   float* p = (float*)ws;
-  rc = rlc_tmid_state_term(h, c, s, B, p, st);
+  rc = rlc_tmid_state_term(h, c, s, B, p, st, p + np);
   if (rc) return rc;
   return launch_tmid_rows<false>(h, c, p, a, act_mode == RLC_ACT_PER_STATE, R, N, q_out, nullptr,
                                  st);

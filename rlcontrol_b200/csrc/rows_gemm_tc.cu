@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const GemmTcParams P)
     gt::mbar_init(acc_bar, 1);
     gt::fence_mbar_init();
   }
-  if (warp == 0) gt::tmem_alloc(gt::smem_u32(tmem_slot), GT_BN);
+  if (warp == 0) gt::tmem_alloc(gt::smem_u32(tmem_slot), 2 * GT_BN);   // main accumulator + correction accumulator
   gt::tc_fence_before();
   __syncthreads();
   gt::tc_fence_after();
@@ -319,9 +319,13 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const GemmTcParams P)
           const uint32_t off = (uint32_t)k * 2u * GT_LBO;  // 8 tf32 = two 16-byte K chunks per MMA
           const uint64_t dah = gt::desc(a_hi + off), dal = gt::desc(a_lo + off), dbh = gt::desc(b_hi + off),
                          dbl = gt::desc(b_lo + off);
+          // The two correction products go to their OWN accumulator (columns GT_BN..): the tensor core's fp32 accumulate
+          // step truncates, which biases a long K sum by ~0.5 ulp of the running sum per MMA (measured: 5x the rms error
+          // of an fp32 FMA chain at K = 400 with all three products in one accumulator); the corrections are 2^-11 of
+          // the main sum, so their own truncation is invisible and the main accumulator sees a third of the steps.
           gt::mma_tf32(tmem_base, dah, dbh, idesc, (uint32_t)((it | k) != 0));
-          gt::mma_tf32(tmem_base, dal, dbh, idesc, 1u);
-          gt::mma_tf32(tmem_base, dah, dbl, idesc, 1u);
+          gt::mma_tf32(tmem_base + GT_BN, dal, dbh, idesc, (uint32_t)((it | k) != 0));
+          gt::mma_tf32(tmem_base + GT_BN, dah, dbl, idesc, 1u);
         }
         gt::commit(empty_bar(s));
         if (++s == GT_STAGES) { s = 0; ph ^= 1u; }
@@ -375,7 +379,12 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const GemmTcParams P)
             const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cbase;
 #pragma unroll
             for (int g = 0; g < GT_EPI_COLS / 16; ++g) gt::tmem_ld16(ta + 16u * g, v + 16 * g);
+            uint32_t c[GT_EPI_COLS];
+#pragma unroll
+            for (int g = 0; g < GT_EPI_COLS / 16; ++g) gt::tmem_ld16(ta + GT_BN + 16u * g, c + 16 * g);
             gt::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < GT_EPI_COLS; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(c[j]));
           } else {
 #pragma unroll
             for (int j = 0; j < GT_EPI_COLS; ++j) v[j] = 0u;
@@ -443,7 +452,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const GemmTcParams P)
   }
   gt::tc_fence_before();
   __syncthreads();
-  if (warp == 0) gt::tmem_dealloc(tmem_base, GT_BN);
+  if (warp == 0) gt::tmem_dealloc(tmem_base, 2 * GT_BN);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,538 @@
+// K2 on the tensor cores: the hoisted T-mid critic on a B x N stack of sampled actions (sm_100a, tcgen05).
+//
+//   q[b,n] = b3 + sum_j w3_j relu(p_b[j] + sum_i a[b,n,i] W2a[i][j])          critic_network.py:77-99 (hoisted: the state
+//   term p_b = relu(clip(s_b) W1 + b1) W2[:H1] + b2 is one row per STATE, rlc_tmid_state_term), evaluated on the np.repeat-ed
+//   stacks of ActorExpert.py:162-182 / qt_opt_network.py:132-175 without materialising them.
+//
+// The fp32 kernel (k_tmid_rows4, critic_fp32.cu) spends 12 issue slots per (row, hidden unit) and runs at 27 TFLOP/s fp32:
+// 583 us for 4.2 M rows (ncu: issue-bound, 0.03 of the HBM roofline its 28 bytes per row would allow).  Here a tile of 128
+// rows of ONE state is a single small GEMM whose K dimension carries the state term as three extra "ones" columns:
+//
+//   Z'[128 x H2P] = Aop[128 x K] * Bop[K x H2P]      K = 4 nc, tf32 operands, fp32 accumulation in tensor memory
+//   Aop row  = [ 1, 1, 1, a_hi(A) | a_lo(A) | a_hi(A) ]                    a = a_hi + a_lo   (3 x TF32 split: fp32-class)
+//   Bop col j= [ p_hi, p_mid, p_lo, W_hi[:,j] | W_hi[:,j] | W_lo[:,j] ]    W = |w3_j| W2a[:,j], p = |w3_j| p_b[j] (exact)
+//
+// with the output head folded in as for K1: columns are scaled by |w3_j| and grouped into 16-wide blocks of one sign of w3_j
+// (positive and negative blocks interleaved), so the epilogue is  q = b3 + sum_blocks (+/-) sum_{16} relu(z')  -- two
+// instructions per (row, hidden unit), no per-column constants, and a running sum that stays at the magnitude of q.
+//
+// Roles (544 threads, persistent CTAs over contiguous tile ranges): warp 0 issues the MMAs (N parts of <= 160 columns into
+// a 3-deep ring of accumulators, 3 K steps each at A = 6); warps 1-8 are two producer groups building the A operand of
+// alternate tiles and the per-state first K chunk of B (the only part of B that changes with the state) in a 4-slot ring;
+// warps 9-16 are two epilogue groups draining alternate tiles (tcgen05.ld -> relu -> signed sums -> one coalesced store
+// of q per row).
+// What bounds it: the accumulator drain, 128 x H2P x 4 bytes per tile through tcgen05.ld.
+#include "common.cuh"
+
+#include <stdlib.h>
+
+#define TT_THREADS 544
+#define TT_SLOTS 4
+#define TT_PF 3            // producer prefetch depth (tiles of its group)
+#define TT_WAIT_LIMIT (1u << 24)
+#define TT_MAX_H2P 512
+
+struct TmidTcParams {
+  const float* p;      // [B, H2] state terms
+  const float* a;      // [N, A] or [B, N, A]
+  const float* W2a;    // [A, H2]
+  const float* w3;     // [H2]
+  const float* b3;
+  float* q;            // [B, N]
+  int B, N, H2, act_per_state;
+  int tps;             // tiles per state
+  long long tiles;     // B * tps
+  int* err;
+  int micro;           // RLC_TMID_MICRO (timing decomposition, q invalid): 1 = producers only signal, 2 = no MMAs,
+                       // 4 = epilogue without the relu/sum arithmetic, 8 = epilogue without tcgen05.ld
+};
+
+namespace tt {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > TT_WAIT_LIMIT) {
+      atomicCAS(err, 0, code);
+      return false;
+    }
+    if ((spins & 0xffff) == 0 && *(volatile int*)err != 0) return false;
+  }
+  return true;
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// c_format F32 @4 ; a_format, b_format TF32 (2) @7, @10 ; both K-major ; N>>3 @17 ; M>>4 @24
+__device__ __forceinline__ uint32_t idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// no-swizzle K-major descriptor: LBO = bytes between the two 16-byte K chunks of an MMA, SBO = 128 B between 8-row groups
+__device__ __forceinline__ uint64_t desc(uint32_t saddr, uint32_t lbo_bytes) {
+  const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+  constexpr uint32_t hi = (128u >> 4) | (1u << 14);
+  return ((uint64_t)hi << 32) | (uint64_t)lo;
+}
+__device__ __forceinline__ void split(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+  lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xffffe000u);
+}
+
+}  // namespace tt
+
+// shared-memory plan (host and device agree through this struct)
+struct TmidTcPlan {
+  int nc;        // 16-byte K chunks of the operands (even)
+  int c1, c2;    // chunks of the [1,1,1,a_hi] group and of each of the two A-wide groups
+  int H2P;       // padded hidden width (both sign blocks multiples of 16); upper bound used for the carve: H2 + 30 rounded
+  int off_c0, off_b, off_a, off_perm, off_scale, off_bar, total;
+};
+static inline __host__ __device__ TmidTcPlan tmid_tc_plan(int A, int H2) {
+  TmidTcPlan t;
+  t.c1 = (A + 3 + 3) / 4;
+  t.c2 = (A + 3) / 4;
+  t.nc = t.c1 + 2 * t.c2;
+  if (t.nc & 1) t.nc += 1;
+  t.H2P = ((H2 + 15) / 16 + 1) * 16;   // worst case of the two-block padding
+  int o = 0;
+  t.off_c0 = o;    o += TT_SLOTS * t.H2P * 16;
+  t.off_b = o;     o += t.nc * t.H2P * 16;
+  t.off_a = o;     o += TT_SLOTS * t.nc * 2048;
+  t.off_perm = o;  o += t.H2P * 4;
+  t.off_scale = o; o += t.H2P * 4;
+  t.off_bar = o;   o += 256;
+  t.total = o + 1024;
+  return t;
+}
+
+// barrier slots
+enum { TB_A_FULL = 0, TB_A_EMPTY = 4, TB_ACC_FULL = 8, TB_ACC_EMPTY = 12, TB_COUNT = 16 };
+
+template <int AT>
+__global__ void __launch_bounds__(TT_THREADS, 1) k_tmid_rows_tc(const TmidTcParams P) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw_addr = tt::smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  unsigned char* bp = smem_raw + (base - raw_addr);
+  const TmidTcPlan L = tmid_tc_plan(AT, P.H2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int* perm = reinterpret_cast<int*>(bp + L.off_perm);
+  float* scale = reinterpret_cast<float*>(bp + L.off_scale);
+  const uint32_t sBar = base + L.off_bar;
+  auto bar = [&](int i) -> uint32_t { return sBar + 8u * (uint32_t)i; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bp + L.off_bar + TB_COUNT * 8);
+  int* shp = reinterpret_cast<int*>(bp + L.off_bar + TB_COUNT * 8 + 8);   // [0] = sign mask of the column blocks, [1] = H2P
+
+  // ---- prologue: sign partition of the head, folded and split B operand, barriers, TMEM -------------------------
+  if (warp == 0) {
+    // Columns grouped in 16-wide blocks of ONE sign of w3, positive and negative blocks interleaved (stable inside a
+    // sign, zero padding at the end of a sign's last block).  A block's relu sum enters q with the block's sign, so the
+    // running q stays at the magnitude of q -- summing all positive columns and all negative columns separately would
+    // round at the magnitude of the two (cancelling) halves, ~50x the fp32 rounding of the reference's own sum.
+    int* tmp = reinterpret_cast<int*>(scale);          // sign lists; the scale table is filled after the barrier
+    int np = 0, nn = 0;
+    for (int j0 = 0; j0 < P.H2; j0 += 32) {
+      const int j = j0 + lane;
+      const bool pos = j < P.H2 && P.w3[j] > 0.f;
+      const unsigned m = __ballot_sync(0xffffffffu, pos);
+      if (pos) tmp[np + __popc(m & ((1u << lane) - 1u))] = j;
+      np += __popc(m);
+    }
+    for (int j0 = 0; j0 < P.H2; j0 += 32) {
+      const int j = j0 + lane;
+      const bool neg = j < P.H2 && !(P.w3[j] > 0.f);
+      const unsigned m = __ballot_sync(0xffffffffu, neg);
+      if (neg) tmp[np + nn + __popc(m & ((1u << lane) - 1u))] = j;
+      nn += __popc(m);
+    }
+    __syncwarp();
+    const int nbp = (np + 15) >> 4, nbn = (nn + 15) >> 4, nblk = nbp + nbn;
+    unsigned negmask = 0;
+    // block k: the min(nbp, nbn) leading pairs alternate (+, -), the surplus of the longer list follows
+    const int npair = nbp < nbn ? nbp : nbn;
+    for (int k = lane; k < nblk; k += 32) {
+      bool neg;
+      int src;
+      if (k < 2 * npair) { neg = (k & 1) != 0; src = k >> 1; }
+      else { neg = nbn > nbp; src = npair + (k - 2 * npair); }
+      for (int e = 0; e < 16; ++e) {
+        const int idx = src * 16 + e;
+        perm[k * 16 + e] = neg ? (idx < nn ? tmp[np + idx] : -1) : (idx < np ? tmp[idx] : -1);
+      }
+      if (neg) negmask |= 1u << k;
+    }
+    for (int o = 16; o > 0; o >>= 1) negmask |= __shfl_xor_sync(0xffffffffu, negmask, o);
+    if (lane == 0) { shp[0] = (int)negmask; shp[1] = nblk * 16; }
+  }
+  if (tid == 32) {
+    for (int i = 0; i < TT_SLOTS; ++i) {
+      tt::mbar_init(bar(TB_A_FULL + i), 4);
+      tt::mbar_init(bar(TB_A_EMPTY + i), 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      tt::mbar_init(bar(TB_ACC_FULL + i), 1);
+      tt::mbar_init(bar(TB_ACC_EMPTY + i), 4);
+    }
+    tt::fence_mbar_init();
+  }
+  __syncthreads();
+  const unsigned negmask = (unsigned)shp[0];   // bit k: 16-column block k carries negative output weights
+  const int H2P = shp[1];
+  const int CHS = H2P * 16;                       // byte stride between K chunks of B
+  // part width: the accumulator is drained in N parts of PW columns (<= 256 per MMA, 512 TMEM columns for the ring)
+  const int nparts = (H2P + 255) / 256 > 1 ? (H2P + 255) / 256 : (H2P > 160 ? 2 : 1);
+  const int PW = ((H2P + nparts - 1) / nparts + 15) & ~15;
+  const int NB = (512 / PW) < 4 ? (512 / PW) : 4;  // accumulator ring depth
+  for (int c = tid; c < H2P; c += TT_THREADS) scale[c] = perm[c] >= 0 ? fabsf(P.w3[perm[c]]) : 0.f;
+  __syncthreads();
+  {
+    // constant part of B: chunk kc, column c: 4 consecutive k
+    float* Bop = reinterpret_cast<float*>(bp + L.off_b);
+    for (int e = tid; e < L.nc * H2P; e += TT_THREADS) {
+      const int kc = e / H2P, c = e - kc * H2P;
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = 4 * kc + u;
+        int i = -1, lo = 0;                          // action row feeding this k, low part?
+        if (k < 4 * L.c1) { if (k >= 3) i = k - 3; }
+        else if (k < 4 * (L.c1 + L.c2)) i = k - 4 * L.c1;
+        else { i = k - 4 * (L.c1 + L.c2); lo = 1; }
+        float x = 0.f;
+        if (i >= 0 && i < AT && perm[c] >= 0) {
+          float h, l;
+          tt::split(scale[c] * P.W2a[(long long)i * P.H2 + perm[c]], h, l);
+          x = lo ? l : h;
+        }
+        v[u] = x;
+      }
+      *reinterpret_cast<float4*>(Bop + (size_t)e * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+  if (warp == 0) tt::tmem_alloc(tt::smem_u32(tmem_slot), 512);
+  tt::tc_fence_before();
+  __syncthreads();
+  tt::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // contiguous tile range of this CTA
+  const long long t_begin = P.tiles * blockIdx.x / gridDim.x, t_end = P.tiles * (blockIdx.x + 1) / gridDim.x;
+  const int ntl = (int)(t_end - t_begin);
+
+  if (warp == 0) {
+    // =========================================== MMA issuer ===========================================
+    if (tt::elect_one()) {
+      const int nks = L.nc / 2;
+      bool ok = true;
+      for (int tl = 0; tl < ntl && ok; ++tl) {
+        const uint32_t slot = (uint32_t)(tl % TT_SLOTS);
+        if (!tt::mbar_wait(bar(TB_A_FULL + slot), (uint32_t)(tl / TT_SLOTS) & 1u, P.err, 211)) break;
+        tt::fence_proxy_async();      // producers' generic-proxy stores -> tensor core reads (fence on the causality path)
+        tt::tc_fence_after();
+        const uint32_t a_s = base + L.off_a + slot * (uint32_t)(L.nc * 2048);
+        const uint32_t c0_s = base + L.off_c0 + slot * (uint32_t)CHS;
+        const uint32_t b_s = base + L.off_b;
+        for (int part = 0; part < nparts; ++part) {
+          const int u = tl * nparts + part;
+          const uint32_t buf = (uint32_t)(u % NB);
+          const int use = u / NB;
+          if (use > 0) {
+            if (!tt::mbar_wait(bar(TB_ACC_EMPTY + buf), (uint32_t)(use - 1) & 1u, P.err, 212)) { ok = false; break; }
+            tt::tc_fence_after();
+          }
+          const int col0 = part * PW;
+          const int pw = (H2P - col0 < PW) ? (H2P - col0) : PW;
+          const uint32_t idesc = tt::idesc_tf32(128, pw);
+          const uint32_t d = tmem_base + buf * (uint32_t)PW;
+          for (int ks = 0; ks < ((P.micro & 2) ? 0 : nks); ++ks) {
+            const uint64_t ad = tt::desc(a_s + (uint32_t)ks * 4096u, 2048u);
+            uint64_t bd;
+            if (ks == 0)   // K chunk 0 is the per-state one (this slot's copy), chunk 1 the constant one
+              bd = tt::desc(c0_s + (uint32_t)col0 * 16u, (b_s + (uint32_t)CHS) - c0_s);
+            else
+              bd = tt::desc(b_s + (uint32_t)(2 * ks) * (uint32_t)CHS + (uint32_t)col0 * 16u, (uint32_t)CHS);
+            tt::mma_tf32(d, ad, bd, idesc, (uint32_t)(ks != 0));
+          }
+          tt::commit(bar(TB_ACC_FULL + buf));
+        }
+        tt::commit(bar(TB_A_EMPTY + slot));
+      }
+    }
+    __syncwarp();
+  } else if (warp <= 8) {
+    // =========================================== producers ===========================================
+    // Two groups of 4 warps build alternate tiles, and each thread requests the actions of its NEXT tile before it works
+    // on the current one: a tile's 3 KB of actions come from HBM (~1 us), a tile period is ~0.7 us.
+    const int row = (tid - 32) & 127, pg = (tid - 32) >> 7;   // tile row 0..127, producer group
+    auto fetch = [&](int tl, float (&ar)[AT], int& b_out, bool& valid_out) {
+      const long long tile = t_begin + tl;
+      const int b = (int)(tile / P.tps);
+      const int n = (int)(tile - (long long)b * P.tps) * 128 + row;
+      const bool valid = n < P.N;
+      const float* ap = P.a + ((P.act_per_state ? (long long)b * P.N : 0LL) + (valid ? n : 0)) * AT;
+#pragma unroll
+      for (int i = 0; i < AT; ++i) {
+        float v;
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(ap + i));   // volatile: stays ahead of the waits below
+        ar[i] = valid ? v : 0.f;
+      }
+      b_out = b;
+      valid_out = valid;
+    };
+    // register ring: the actions of this group's next TT_PF tiles are in flight
+    float arn[TT_PF][AT];
+    int bn[TT_PF];
+    bool validn[TT_PF];
+#pragma unroll
+    for (int d = 0; d < TT_PF; ++d) {
+      bn[d] = 0;
+      validn[d] = false;
+      if (pg + 2 * d < ntl) fetch(pg + 2 * d, arn[d], bn[d], validn[d]);
+    }
+    bool pok = true;
+    for (int t0 = pg; t0 < ntl && pok; t0 += 2 * TT_PF) {
+#pragma unroll
+    for (int d = 0; d < TT_PF; ++d) {          // ring slot d is used in place (no register shuffling across in-flight loads)
+      const int tl = t0 + 2 * d;
+      if (tl >= ntl) break;
+      const uint32_t slot = (uint32_t)(tl % TT_SLOTS);
+      float ar[AT];
+#pragma unroll
+      for (int i = 0; i < AT; ++i) ar[i] = arn[d][i];
+      const int b = bn[d];
+      const bool valid = validn[d];
+      if (tl + 2 * TT_PF < ntl) fetch(tl + 2 * TT_PF, arn[d], bn[d], validn[d]);
+      if (tl >= TT_SLOTS) {
+        if (!tt::mbar_wait(bar(TB_A_EMPTY + slot), (uint32_t)(tl / TT_SLOTS - 1) & 1u, P.err, 213)) { pok = false; break; }
+      }
+      if (!(P.micro & 1)) {
+      // A operand: k -> value, written chunk by chunk
+      float* As = reinterpret_cast<float*>(bp + L.off_a + slot * (L.nc * 2048));
+      float hi[AT], lo[AT];
+#pragma unroll
+      for (int i = 0; i < AT; ++i) tt::split(ar[i], hi[i], lo[i]);
+      const float one = valid ? 1.f : 0.f;
+#pragma unroll
+      for (int kc = 0; kc < 8; ++kc) {       // nc <= 8 for A <= 8
+        if (kc >= L.nc) break;
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = 4 * kc + u;
+          float x = 0.f;
+          if (k < 3) x = one;
+          else if (k < 4 * L.c1) { if (k - 3 < AT) x = hi[(k - 3 < AT) ? k - 3 : 0]; }
+          else if (k < 4 * (L.c1 + L.c2)) { const int i = k - 4 * L.c1; if (i < AT) x = lo[(i < AT) ? i : 0]; }
+          else { const int i = k - 4 * (L.c1 + L.c2); if (i >= 0 && i < AT) x = hi[(i >= 0 && i < AT) ? i : 0]; }
+          v[u] = x;
+        }
+        *reinterpret_cast<float4*>(As + kc * 512 + row * 4) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+      // per-state K chunk 0 of B: [p_hi, p_mid, p_lo, W_hi[0]] per column (folded: p' = |w3| p).  The state term is ~100x
+      // the action term, so it is carried EXACTLY (three tf32 parts = 24 bits against the three ones of the A operand);
+      // with two parts its 2^-22 representation error was the largest term of the whole evaluation (4e-5 of q).
+      {
+        float* C0 = reinterpret_cast<float*>(bp + L.off_c0 + slot * CHS);
+        const float* B0 = reinterpret_cast<const float*>(bp + L.off_b);   // constant chunk 0: [0, 0, 0, W_hi[0]]
+        const float* pb = P.p + (long long)b * P.H2;
+        for (int c = row; c < H2P; c += 128) {
+          const int j = perm[c];
+          float h = 0.f, m = 0.f, l = 0.f;
+          if (j >= 0) {
+            const float x = scale[c] * __ldg(pb + j);
+            float r;
+            tt::split(x, h, r);              // r = rna(x - h): not used, the exact remainder is split again
+            tt::split(x - h, m, l);
+          }
+          *reinterpret_cast<float4*>(C0 + c * 4) = make_float4(h, m, l, B0[c * 4 + 3]);
+        }
+      }
+      }
+      __syncwarp();
+      if (lane == 0) tt::mbar_arrive(bar(TB_A_FULL + slot));
+    }
+    }
+  } else {
+    // =========================================== epilogue ===========================================
+    const int ew = warp - 9, grp = ew >> 2;
+    const int qd = warp & 3;                       // TMEM lane quarter this warp may read
+    const float bias3 = __ldg(P.b3);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
+    bool ok = true;
+    for (int tl = grp; tl < ntl && ok; tl += 2) {
+      const long long tile = t_begin + tl;
+      const int b = (int)(tile / P.tps);
+      const int n = (int)(tile - (long long)b * P.tps) * 128 + qd * 32 + lane;
+      float acc = 0.f;
+      for (int part = 0; part < nparts; ++part) {
+        const int u = tl * nparts + part;
+        const uint32_t buf = (uint32_t)(u % NB);
+        if (!tt::mbar_wait(bar(TB_ACC_FULL + buf), (uint32_t)(u / NB) & 1u, P.err, 214)) { ok = false; break; }
+        tt::tc_fence_after();
+        const int col0 = part * PW;
+        const int pw = (H2P - col0 < PW) ? (H2P - col0) : PW;
+        const uint32_t ta = lane_addr + buf * (uint32_t)PW;
+        for (int g0 = 0; g0 < pw; g0 += 64) {       // batches of up to 4 x 16 columns
+          uint32_t v[64];
+          const int ng = (pw - g0 >= 64) ? 4 : (pw - g0) / 16;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            if (g < ng && !(P.micro & 8)) tt::tmem_ld16(ta + (uint32_t)(g0 + 16 * g), v + 16 * g);
+          tt::tmem_ld_wait();
+          if (g0 + 64 >= pw) {                      // last batch of the part is in registers: hand the buffer back
+            tt::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tt::mbar_arrive(bar(TB_ACC_EMPTY + buf));
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g < ng && !(P.micro & 12)) {
+              float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+              for (int e = 0; e < 16; e += 2) {
+                s0 += fmaxf(__uint_as_float(v[16 * g + e]), 0.f);
+                s1 += fmaxf(__uint_as_float(v[16 * g + e + 1]), 0.f);
+              }
+              const float sb = s0 + s1;
+              acc += ((negmask >> ((col0 + g0 + 16 * g) >> 4)) & 1u) ? -sb : sb;
+            }
+          }
+        }
+      }
+      if (ok && n < P.N) P.q[(long long)b * P.N + n] = bias3 + acc;
+    }
+  }
+  tt::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tt::tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+static int tmid_tc_mode() {
+  static int mode = -1;   // RLC_TMID_TC: 0 = off, 1 = dispatcher (default), 2 = whenever the shape is supported (tests)
+  if (mode < 0) {
+    const char* e = getenv("RLC_TMID_TC");
+    mode = e ? atoi(e) : 1;
+    if (mode < 0 || mode > 2) mode = 1;
+  }
+  return mode;
+}
+
+static thread_local int g_tmid_force = -1;
+extern "C" int rlc_tmid_tc_force(int mode) {
+  const int prev = g_tmid_force;
+  g_tmid_force = (mode == 0 || mode == 2) ? mode : -1;
+  return prev;
+}
+
+bool rlc_tmid_tc_ok(const rlc_handle* h, const rlc_critic* c, long long R, int N) {
+  const int mode = g_tmid_force >= 0 ? g_tmid_force : tmid_tc_mode();
+  if (mode == 0 || h->sm_major != 10) return false;
+  if (c->A > 8 || N < 1 || R < 1) return false;
+  const TmidTcPlan L = tmid_tc_plan(c->A, c->H2);
+  if (L.H2P > TT_MAX_H2P || (size_t)L.total > h->smem_optin) return false;
+  if (mode == 2) return true;
+  // tiles are 128 rows of one state: worth it when states have (nearly) full tiles and the stack fills the machine
+  return N >= 96 && R >= (long long)h->num_sms * 1024;
+}
+
+template <int AT>
+static int launch_tc(rlc_handle* h, const TmidTcParams& P, int smem, int grid, cudaStream_t st) {
+  RLC_CUDA(cudaFuncSetAttribute(k_tmid_rows_tc<AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_tmid_rows_tc<AT><<<grid, TT_THREADS, smem, st>>>(P);
+  RLC_LAUNCH_CHECK(h);
+  return RLC_OK;
+}
+
+int rlc_tmid_rows_tc(rlc_handle* h, const rlc_critic* c, const float* p, const float* a, int act_per_state, int B, int N,
+                     float* q_out, cudaStream_t st) {
+  const ThetaView t = theta_view(RLC_TMID, c->S, c->A, c->H1, c->H2);
+  TmidTcParams P;
+  P.p = p; P.a = a; P.q = q_out;
+  P.W2a = c->theta + t.oW2 + (int64_t)c->H1 * c->H2;
+  P.w3 = c->theta + t.ow3;
+  P.b3 = c->theta + t.ob3;
+  P.B = B; P.N = N; P.H2 = c->H2; P.act_per_state = act_per_state;
+  P.tps = (N + 127) / 128;
+  P.tiles = (long long)B * P.tps;
+  P.err = h->err_flag;
+  {
+    static int micro = -1;
+    if (micro < 0) {
+      const char* e = getenv("RLC_TMID_MICRO");
+      micro = e ? atoi(e) : 0;
+    }
+    P.micro = micro;
+  }
+  const TmidTcPlan L = tmid_tc_plan(c->A, c->H2);
+  int grid = h->num_sms > 0 ? h->num_sms : 148;
+  if ((long long)grid > P.tiles) grid = (int)P.tiles;
+  switch (c->A) {
+    case 1: return launch_tc<1>(h, P, L.total, grid, st);
+    case 2: return launch_tc<2>(h, P, L.total, grid, st);
+    case 3: return launch_tc<3>(h, P, L.total, grid, st);
+    case 4: return launch_tc<4>(h, P, L.total, grid, st);
+    case 5: return launch_tc<5>(h, P, L.total, grid, st);
+    case 6: return launch_tc<6>(h, P, L.total, grid, st);
+    case 7: return launch_tc<7>(h, P, L.total, grid, st);
+    case 8: return launch_tc<8>(h, P, L.total, grid, st);
+    default: return RLC_ERR_UNSUPPORTED;
+  }
+}
