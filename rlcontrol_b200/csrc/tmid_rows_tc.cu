@@ -21,7 +21,11 @@
 // alternate tiles and the per-state first K chunk of B (the only part of B that changes with the state) in a 4-slot ring;
 // warps 9-16 are two epilogue groups draining alternate tiles (tcgen05.ld -> relu -> signed sums -> one coalesced store
 // of q per row).
-// What bounds it: the accumulator drain, 128 x H2P x 4 bytes per tile through tcgen05.ld.
+// What bounds it: the accumulator drain.  tcgen05.ld moves ~64 bytes per clock per SM, so the 128 x 320 fp32 accumulator of
+// a tile takes >= 2 560 cycles to read: 4.19 M rows cannot go below ~300 us on 148 SMs, and the 512 TMEM columns hold only
+// 1.6 tiles, so the commit -> drain -> release -> MMA round trip (~2 400 cycles per 3 accumulator parts with ALL work
+// removed: clock64 trace, profiles/r02i_rows_gemm.md) is not hidden either.  Measured ~320 us for the rows (+ 64 us state
+// term) against 520 us on CUDA cores.
 #include "common.cuh"
 
 #include <stdlib.h>
