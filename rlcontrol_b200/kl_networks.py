@@ -174,7 +174,8 @@ class _KLNetwork(object):
         self.device = dev
         self._steps = {}                      # batch size -> captured update
         self._act = {}                        # batch size -> action-selection buffers
-        # NCCL inside a multi-stream capture is not worth the risk: the data-parallel update runs eagerly
+        # The data-parallel update runs eagerly: capturing it (four stream branches + torch's NCCL all-reduce in one
+        # graph) was tried on 2 GPUs in round 2 and hung in the warm-up/capture sequence (tests/gpu_dp_update.py timed out)
         self.use_graph = bool(getattr(config, "use_cuda_graph", True)) and self.world_size == 1
         # small minibatches (cfg1 / cfg5): all B-row forward passes in one launch, all backward passes + Adam in one
         # launch (csrc/small_batch.cu) instead of ~60 dependent small kernels
