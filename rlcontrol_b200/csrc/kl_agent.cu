@@ -43,6 +43,7 @@ extern "C" int rlc_rows_gemm(rlc_handle* h, int trans_a, int trans_b, int M, int
                              int relu_a, float alpha, int split_k, int path, void* stream) {
   RLC_REQUIRE(h && A && Bm && C && M >= 0 && N >= 0 && K >= 0 && lda >= 1 && ldb >= 1 && ldc >= N);
   RLC_REQUIRE(path == 0 || path == 1 || path == 2);
+  RLC_REQUIRE(lda >= (trans_a ? M : K) && ldb >= (trans_b ? K : N) && (!maskZ || ldz >= N));
   RLC_REQUIRE(!split_k || (trans_a && !trans_b && !bias && !maskZ && ldc == N));
   cudaStream_t st = (cudaStream_t)stream;
   GemmEpi e{bias, maskZ, ldz, relu_a, alpha};

@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const GemmTcParams P)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bp + GT_STAGES * GT_STAGE_BYTES + 8 * (2 * GT_STAGES + 1));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.y * GT_BM, n0 = blockIdx.x * GT_BN;
+  const int m0 = blockIdx.x * GT_BM, n0 = blockIdx.y * GT_BN;   // row tiles on x: no 65 535 limit on the batch dimension
   const int kbeg = blockIdx.z * P.klen;
   const int kend = (kbeg + P.klen < P.K) ? kbeg + P.klen : P.K;
   const int nk = (kend > kbeg) ? (kend - kbeg + GT_BK - 1) / GT_BK : 0;
@@ -522,7 +522,8 @@ int rlc_gemm_tc(rlc_handle* h, bool ta, bool tb, int M, int N, int K, const floa
   P.b_vec = (tb && ldb % 4 == 0 && al16(Bm)) ? 1 : 0;
   P.c_vec = (ldc % 4 == 0 && al16(C) && cz_stride % 4 == 0) ? 1 : 0;
   P.z_vec = (epi.maskZ && epi.ldz % 4 == 0 && al16(epi.maskZ)) ? 1 : 0;
-  dim3 grid((N + GT_BN - 1) / GT_BN, (M + GT_BM - 1) / GT_BM, nz);
+  dim3 grid((M + GT_BM - 1) / GT_BM, (N + GT_BN - 1) / GT_BN, nz);
+  RLC_REQUIRE(grid.y <= 65535u && grid.z <= 65535u);
   // operand orientation in global memory: A is row-contiguous (element (m,k) at A[k*lda+m]) when ta;
   // B (rows = n) is row-contiguous (element (n,k) at B[k*ldb+n]) when NOT tb
   const bool a_rc = ta, b_rc = !tb;

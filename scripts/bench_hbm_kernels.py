@@ -118,7 +118,7 @@ def main():
         import ctypes as _C
         _chk(eng.lib.rlc_critic_grad_action(eng.h, _C.byref(crin._desc), _pp(s_rows), _pp(a_rows), R, _pp(g_rows), _pp(q_rows), _ss()))
     fl_row = 2 * ((S + A) * H1 + H1 * H2 + H2) + 2 * (H2 + H1 * H2 + A * H1)
-    report("K5 dQ/da T-in on %d stacked rows (rlc_critic_grad_action, fp32 CUDA cores)" % R, R * (S + 2 * A + 1) * 4,
+    report("K5 dQ/da T-in on %d stacked rows (rlc_critic_grad_action, row GEMMs on tcgen05 3xTF32)" % R, R * (S + 2 * A + 1) * 4,
            lambda: timeit(tin_grad, 2),
            lambda sec: "%.3f G rows/s = %.1f TFLOP/s fp32 (forward + input-gradient, %d flop/row); the full 4.19M-row stack takes %.1f ms"
                        % (R / sec / 1e9, R * fl_row / sec / 1e12, fl_row, sec * 8 * 1e3))

@@ -210,3 +210,23 @@ def test_grad_action_dense_rows(eng):
     gn = g.cpu().numpy()[idx]
     assert np.abs(gn - gref).max() < 5e-6 * np.abs(gref).max() + 1e-7
     np.testing.assert_allclose(q.cpu().numpy()[idx], qref.reshape(-1), rtol=1e-5, atol=2e-6)
+
+
+def test_rows_gemm_rejects_bad_arguments(eng):
+    """Leading dimensions smaller than the row length, a split-K request that is not a weight-gradient form: RLC_ERR_INVALID
+    before anything is launched."""
+    import torch
+    from rlcontrol_b200._lib import RlcError, check
+    from rlcontrol_b200.engine import _ptr, _stream
+    x = torch.zeros(64 * 64, device=eng.device)
+    n0 = eng.launches
+    for args in ((0, 0, 8, 8, 8, 4, 8, 8, 0, 0),        # lda < K
+                 (0, 1, 8, 8, 8, 8, 4, 8, 0, 0),        # ldb < K for a transposed B
+                 (0, 0, 8, 8, 8, 8, 8, 4, 0, 0),        # ldc < N
+                 (0, 0, 8, 8, 8, 8, 8, 8, 1, 0),        # split-K needs trans_a
+                 (0, 0, 8, 8, 8, 8, 8, 8, 0, 3)):       # unknown path
+        ta, tb, M, N, K, lda, ldb, ldc, split, path = args
+        with pytest.raises(RlcError):
+            check(eng.lib.rlc_rows_gemm(eng.h, ta, tb, M, N, K, _ptr(x), lda, _ptr(x), ldb, _ptr(x), ldc, None, None, 0, 0, 1.0,
+                                        split, path, _stream()))
+    assert eng.launches == n0
