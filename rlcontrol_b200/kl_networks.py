@@ -174,9 +174,12 @@ class _KLNetwork(object):
         self.device = dev
         self._steps = {}                      # batch size -> captured update
         self._act = {}                        # batch size -> action-selection buffers
-        # The data-parallel update runs eagerly: capturing it (four stream branches + torch's NCCL all-reduce in one
-        # graph) was tried on 2 GPUs in round 2 and hung in the warm-up/capture sequence (tests/gpu_dp_update.py timed out)
-        self.use_graph = bool(getattr(config, "use_cuda_graph", True)) and self.world_size == 1
+        # The data-parallel update (world_size > 1) is TWO graphs around an eager all-reduce: everything up to the joined
+        # gradients, then torch's NCCL all-reduce of [g_Q | g_V | g_pi] and of the loss shares on the update's stream,
+        # then the three Adam steps and the download.  (One graph with the collective inside -- four stream branches +
+        # NCCL in one capture -- hung on 2 GPUs in the warm-up/capture sequence; config.dp_cuda_graph=False: all eager.)
+        self.use_graph = bool(getattr(config, "use_cuda_graph", True)) and (
+            self.world_size == 1 or bool(getattr(config, "dp_cuda_graph", True)))
         # small minibatches (cfg1 / cfg5): all B-row forward passes in one launch, all backward passes + Adam in one
         # launch (csrc/small_batch.cu) instead of ~60 dependent small kernels
         self.fused_small = bool(getattr(config, "fused_small_batch", True))
@@ -331,7 +334,22 @@ class _KLNetwork(object):
         if not device_inputs:
             st.out_host.copy_(st.out_dev, non_blocking=True)
 
-    def _enqueue(self, st, B, device_inputs=False):
+    def _enqueue_dp_post(self, st, device_inputs=False):
+        """Data-parallel update, after the all-reduce: identical Adam steps on every rank, then the download."""
+        self.q_opt.step()
+        self.v_opt.step()
+        self.pi_opt.step()
+        self.critic.invalidate()
+        self.critic_grid.invalidate()
+        if not device_inputs:
+            st.out_host.copy_(st.out_dev, non_blocking=True)
+
+    def _allreduce_dp(self, st):
+        from .parallel import allreduce_grad_
+        allreduce_grad_(self.grad_flat, self.process_group)
+        allreduce_grad_(st.out_dev, self.process_group)     # every loss slot holds this rank's share of the global mean
+
+    def _enqueue(self, st, B, device_inputs=False, stop_before_allreduce=False):
         """One update on four streams (fork after the upload, join before the download); the dependency edges
         are exactly the data dependencies of update_network, so the captured graph runs the independent
         branches side by side: small batches are latency-bound, and this is what shortens the critical path.
@@ -407,14 +425,13 @@ class _KLNetwork(object):
         self.critic.grads_into(d["s"], d["a"], st.y, self.q_opt.grad, o[0:1], st.q_reg, b_total=bt)
         if dp:
             # join, ONE all-reduce over [g_Q | g_V | g_pi] (and the three loss shares), identical Adam steps everywhere
-            from .parallel import allreduce_grad_
             for br in (s_grid, s_v, s_pi):
                 main.wait_stream(br)
-            allreduce_grad_(self.grad_flat, self.process_group)
-            allreduce_grad_(o, self.process_group)     # every loss slot holds this rank's share of the global mean
-            self.q_opt.step()
-            self.v_opt.step()
-            self.pi_opt.step()
+            if stop_before_allreduce:          # first of the two captured graphs
+                return
+            self._allreduce_dp(st)
+            self._enqueue_dp_post(st, device_inputs)
+            return
         else:
             if intg:
                 main.wait_event(ev_grid)
@@ -447,8 +464,14 @@ class _KLNetwork(object):
                 st.stream.synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=st.stream):
-                    self._enqueue(st, B)
+                    self._enqueue(st, B, stop_before_allreduce=self.world_size > 1)
                 st.graph = g
+                st.graph_post = None
+                if self.world_size > 1:
+                    g2 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g2, stream=st.stream):
+                        self._enqueue_dp_post(st)
+                    st.graph_post = g2
                 for t, s_ in zip(ts, saved):
                     t.copy_(s_)
                 self.critic.invalidate()
@@ -479,6 +502,9 @@ class _KLNetwork(object):
         with torch.cuda.stream(st.stream):
             if st.graph is not None:
                 st.graph.replay()
+                if getattr(st, "graph_post", None) is not None:      # data-parallel: eager collective between the graphs
+                    self._allreduce_dp(st)
+                    st.graph_post.replay()
                 # the replay moves theta_Q on the device; the host-side validity of the cached tensor-core operand packs
                 # was only cleared at capture time, so clear it after every replay (an eager q_net.eval_grid(...) between
                 # updates would otherwise reuse operands packed from the previous theta)
