@@ -36,6 +36,9 @@
 //          (oracle_np.tin_eval_rounded(head="grid3c8")), 2/3 of the tensor-pipe time of G3_X3.
 #define G3_X3 0
 #define G3_C8 1
+#ifndef RLC_G3_PDL_DEFAULT
+#define RLC_G3_PDL_DEFAULT 0   // programmatic dependent launch of K1 behind its pre-pass (RLC_G3_PDL=0|1 overrides)
+#endif
 #define G3_E2G 4             // epilogue-2 column groups (x 4 lane quarters = 16 warps)
 __host__ __device__ constexpr int g3_e1w(int mode) { return mode == G3_C8 ? 8 : 4; }   // epilogue-1 warps (C8 builds 3 operands)
 __host__ __device__ constexpr int g3_threads(int mode) { return 32 * (4 + g3_e1w(mode) + 4 * G3_E2G); }
@@ -123,6 +126,10 @@ k_grid3_parts(const float* __restrict__ theta, const float* __restrict__ s, cons
               int H1P, int KC, Grid3Chunks ch, int NT, int state_groups, float* __restrict__ PS,
               float* __restrict__ PA, int* __restrict__ err, float limit) {
   extern __shared__ float xs[];                               // [GR_PRE_ROWS][K]
+  // programmatic dependent launch: the evaluation kernel behind this pre-pass may become resident and run its prologue
+  // (resident W_hi copy, barrier set-up, TMEM allocation: ~12 us) now; its table loader waits (griddepcontrol.wait) for
+  // this grid to complete before it touches PS/PA.  A no-op when the next launch does not ask for it.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const ThetaView t = theta_view(RLC_TIN, S, A, H1, H2);
   const float* W1 = theta + t.oW1;   // [S+A][H1]
   const float* b1 = theta + t.ob1;
@@ -575,6 +582,7 @@ __global__ void __launch_bounds__(G3_THREADS, 1) k_critic_umma_grid3(const Grid3
   } else if (warp == 1) {
     // =================================== table loader (one lane) ===================================
     if (lane == 0) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");   // the PS/PA tables of the pre-pass are complete and visible
       bool ok = true;
       const int pitch_b = (KC + G3_PA_PAD) * 4;
       const uint32_t pa_tile_bytes = 32u * (uint32_t)pitch_b;
@@ -1119,13 +1127,17 @@ static int rlc_eval_umma_grid3(rlc_handle* h, const rlc_critic* c, const float* 
   cfg.blockDim = dim3(g3_threads(mode));
   cfg.dynamicSmemBytes = (size_t)gp.total;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // overlap our prologue with k_grid3_parts
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  static int pdl = -1;
+  if (pdl < 0) { const char* e = getenv("RLC_G3_PDL"); pdl = e ? (e[0] == '1' ? 1 : 0) : RLC_G3_PDL_DEFAULT; }
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   static int prof_on = -1, micro = -1;
   static long long* prof_dev = nullptr;
   if (prof_on < 0) { const char* e = getenv("RLC_UMMA_PROF"); prof_on = (e && e[0] == '1') ? 1 : 0; }
