@@ -235,12 +235,14 @@ def _net_params(net):
 
 
 def gen_full_update(torch, mod, cls_name, name, alpha, optim_type="intg", q_update_type="non_sac", seed=0,
-                    n_updates=2, l1=64, l2=48):
+                    n_updates=2, l1=64, l2=48, B=32):
     """n_updates consecutive reference ``update_network`` + ``update_target_network`` calls
     (forwardkl_network.py:123-215 / reversekl_network.py:130-224) on Pendulum-shaped batches, ALL three
     networks recorded before and after every update, and the N(0,1) draws behind ``normal.sample()``
-    recorded as ``eps`` (torch.randn under the same seed; asserted to reproduce the reference's z)."""
-    S, A, B = 3, 1, 32
+    recorded as ``eps`` (torch.randn under the same seed; asserted to reproduce the reference's z).
+    B = 32 is the reference's minibatch; the ``*_dense`` fixtures (B = 2048, 128-128) put the same update on the
+    tensor-core training GEMMs of the B200 path (csrc/rows_gemm_tc.cu)."""
+    S, A = 3, 1
     cfg = make_config(S, A, 2.0, B, 64, l1, l2, alpha, state_max=[1.0, 1.0, 8.0])
     cfg.optim_type, cfg.q_update_type = optim_type, q_update_type
     cfg.pi_lr, cfg.qf_vf_lr = 1e-3, 2e-3
@@ -470,6 +472,9 @@ def gen_full_updates(torch, forwardkl_network, reversekl_network):
     gen_full_update(torch, *R, "full_rkl_hardintg_sac.npz", alpha=0.2, optim_type="hard_intg", q_update_type="sac", seed=5)
     gen_full_update(torch, *R, "full_rkl_ll_nonsac.npz", alpha=0.1, optim_type="ll", seed=6)
     gen_full_update(torch, *R, "full_rkl_hardll_sac.npz", alpha=0.1, optim_type="hard_ll", q_update_type="sac", seed=7)
+    gen_full_update(torch, *F, "full_fkl_intg_nonsac_dense.npz", alpha=0.1, seed=8, n_updates=1, l1=128, l2=128, B=2048)
+    gen_full_update(torch, *R, "full_rkl_intg_sac_dense.npz", alpha=0.2, q_update_type="sac", seed=9, n_updates=1, l1=128,
+                    l2=128, B=2048)
 
 
 def gen_bimodal_env():
@@ -532,6 +537,17 @@ if __name__ == "__main__":
         torch.set_num_threads(1)
         from agents.network import forwardkl_network, reversekl_network
         gen_full_updates(torch, forwardkl_network, reversekl_network)
+    elif len(sys.argv) > 1 and sys.argv[1] == "dense_updates":   # only the dense-minibatch full-update fixtures
+        os.makedirs(OUT, exist_ok=True)
+        install_stubs()
+        sys.path.insert(0, REF)
+        import torch
+        torch.set_num_threads(1)
+        from agents.network import forwardkl_network, reversekl_network
+        gen_full_update(torch, forwardkl_network, "ForwardKLNetwork", "full_fkl_intg_nonsac_dense.npz", alpha=0.1, seed=8,
+                        n_updates=1, l1=128, l2=128, B=2048)
+        gen_full_update(torch, reversekl_network, "ReverseKLNetwork", "full_rkl_intg_sac_dense.npz", alpha=0.2,
+                        q_update_type="sac", seed=9, n_updates=1, l1=128, l2=128, B=2048)
     elif len(sys.argv) > 1 and sys.argv[1] == "bimodal_env":     # only the bandit-environment fixture
         install_stubs()
         sys.path.insert(0, REF)

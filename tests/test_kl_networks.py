@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle_kl as okl
-from test_oracle_kl import FULL, load_full, make_agent
+from test_oracle_kl import FULL, FULL_DENSE, load_full, make_agent
 
 pytestmark = pytest.mark.gpu
 
@@ -140,7 +140,7 @@ def _config(eng, g, **kw):
 
 
 @pytest.mark.parametrize("use_graph", [True, False])
-@pytest.mark.parametrize("name", FULL)
+@pytest.mark.parametrize("name", FULL + FULL_DENSE)
 def test_dropin_update_network_matches_reference(eng, name, use_graph):
     """The recorded reference run, replayed through the drop-in class: same batches, same normal draws ->
     every parameter of q_net / v_net / target_v_net / pi_net after update 1 and update 2, the three
@@ -160,7 +160,15 @@ def test_dropin_update_network_matches_reference(eng, name, use_graph):
             for i, (m, ref) in enumerate(zip(mine[k], post[u][k])):
                 move = np.abs(ref - pre[k][i]).max() + 1e-12
                 err = np.abs(m.reshape(ref.shape) - ref).max()
-                assert err <= 5e-3 * move + 5e-7, (name, u, k, i, err, move)
+                if name in FULL_DENSE:
+                    # Adam's first step is lr * g / (|g| + 1e-8): where the 2048-row mean gradient of an element is within
+                    # ~100x of eps, an fp32-class difference in g (3e-7 of the largest gradient) moves the STEP by percents
+                    # of lr.  So: all but 0.1 % of the elements within 1e-2 of the move, none beyond 1e-1 of it.
+                    e = np.abs(m.reshape(ref.shape) - ref).ravel()
+                    assert np.quantile(e, 0.999) <= 1e-2 * move + 5e-7, (name, u, k, i, np.quantile(e, 0.999), move)
+                    assert err <= 1e-1 * move + 5e-7, (name, u, k, i, err, move)
+                else:
+                    assert err <= 5e-3 * move + 5e-7, (name, u, k, i, err, move)
     st = g["act_states"]
     np.testing.assert_allclose(net.sample_action(st, eps=g["act_eps"]), g["act_sample"], rtol=1e-4, atol=2e-5)
     np.testing.assert_allclose(net.predict_action(st), g["act_predict"], rtol=1e-4, atol=2e-5)

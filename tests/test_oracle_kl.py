@@ -10,6 +10,9 @@ from rlcontrol_b200 import quadrature
 
 FULL = ["full_fkl_intg_nonsac", "full_fkl_intg_sac", "full_rkl_intg_nonsac", "full_rkl_hardintg_sac",
         "full_rkl_ll_nonsac", "full_rkl_hardll_sac"]
+# the same reference update at a DENSE minibatch (B = 2048, 128-128 networks): one update each; on the GPU these run the B-row
+# training path on the tcgen05 3xTF32 GEMMs (csrc/rows_gemm_tc.cu) instead of the small-minibatch kernels
+FULL_DENSE = ["full_fkl_intg_nonsac_dense", "full_rkl_intg_sac_dense"]
 NP = dict(q=6, v=6, tv=6, pi=8)
 
 
@@ -28,7 +31,7 @@ def make_agent(name, g, pre):
                        float(g["tau"]), optim_type=str(g["optim_type"]), q_update_type=str(g["q_update_type"]))
 
 
-@pytest.mark.parametrize("name", FULL)
+@pytest.mark.parametrize("name", FULL + FULL_DENSE)
 def test_oracle_full_update_matches_reference(name):
     """Two consecutive update_network + update_target_network calls: every parameter of q_net, v_net,
     target_v_net and pi_net lands where the reference's torch autograd + Adam put it (fp32 there, fp64 here)."""
@@ -42,7 +45,10 @@ def test_oracle_full_update_matches_reference(name):
                 # one Adam step moves a weight by ~lr; the comparison is on the MOVE (parameters barely change)
                 move = np.abs(ref - pre[k][i]).max() + 1e-12
                 err = np.abs(m - ref).max()
-                assert err <= 2e-3 * move + 2e-7, (name, u, k, i, err, move)
+                # dense fixtures: the first Adam step is lr * g / (|g| + 1e-8), and with a 2048-row mean more elements of g sit
+                # near 1e-8, where the reference's fp32 gradient noise moves the step itself
+                tol = 6e-3 if name in FULL_DENSE else 2e-3
+                assert err <= tol * move + 2e-7, (name, u, k, i, err, move)
     st = g["act_states"]
     np.testing.assert_allclose(ag.sample_action(st, g["act_eps"]), g["act_sample"], rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(ag.predict_action(st), g["act_predict"], rtol=1e-4, atol=1e-5)
