@@ -24,7 +24,8 @@
 //     epilogue (alpha, bias, ReLU-derivative mask) on the way to global memory;
 //   * split-K over gridDim.z for the weight gradients (K = batch rows): every slice writes its own slab, the slabs are
 //     summed in a fixed order by the caller (deterministic).
-// Bounded mbarrier waits raise the handle's error flag instead of hanging.
+// Bounded mbarrier waits raise the handle's error flag instead of hanging.  Non-finite operands: inf splits into
+// (inf, inf - inf = NaN), so an infinite input yields NaN where the fp32 FMA kernel would yield inf.
 #include "rows_gemm_tc.cuh"
 
 #include <stdlib.h>

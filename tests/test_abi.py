@@ -46,6 +46,11 @@ def test_host_only_entry_points():
     assert list(off) == [0, 200, 400, 400 + 201 * 200, 400 + 201 * 200 + 200, 400 + 201 * 200 + 400]
     assert lib.rlc_theta_numel(7, 1, 1, 1, 1) == -1
     assert lib.rlc_theta_offsets(_lib.TIN, 0, 1, 1, 1, off) == -1
+    # dispatcher pins of the round-2 tensor-core paths: per-thread state, previous setting returned, junk = default
+    for fn in (lib.rlc_rows_gemm_force, lib.rlc_tmid_tc_force):
+        assert fn(0) == -1 and fn(2) == 0 and fn(7) == 2 and fn(-1) == -1
+    # null / malformed arguments are rejected before any CUDA call
+    assert lib.rlc_rows_gemm(None, 0, 0, 1, 1, 1, None, 1, None, 1, None, 1, None, None, 0, 0, 1.0, 0, 0, None) == -1
 
 
 def test_no_cpu_fallback_without_gpu():
