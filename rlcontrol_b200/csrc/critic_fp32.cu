@@ -386,11 +386,11 @@ k_tmid_rows(const float* __restrict__ p, const float* __restrict__ a, int act_pe
 // thread (k_tmid_rows) the kernel was bound by the load/store unit -- 9 broadcast LDS.128 per 4 columns per row, and
 // A = 6 padded to 8 -- at 18 TFLOP/s fp32 on 2(A+1)H2 flop/row.
 #define TMID_RPT 4
-template <int AT>
+template <int AT, bool GRAD>
 __global__ void __launch_bounds__(256)
 k_tmid_rows4(const float* __restrict__ p, const float* __restrict__ a, int act_per_state, long long R, int N,
              int H2, const float* __restrict__ W2a, const float* __restrict__ w3, const float* __restrict__ b3,
-             float* __restrict__ q_out) {
+             float* __restrict__ q_out, float* __restrict__ dqda_out) {
   extern __shared__ float sm[];
   const int H2P = (H2 + 3) & ~3;
   float* w3s = sm;         // [H2P]
@@ -404,6 +404,7 @@ k_tmid_rows4(const float* __restrict__ p, const float* __restrict__ a, int act_p
   __syncthreads();
   const long long row0 = (long long)blockIdx.x * (256 * TMID_RPT) + tid;
   float ar[TMID_RPT][AT], q[TMID_RPT];
+  float g[GRAD ? TMID_RPT : 1][AT];
   const float* pb[TMID_RPT];
 #pragma unroll
   for (int u = 0; u < TMID_RPT; ++u) {
@@ -414,6 +415,10 @@ k_tmid_rows4(const float* __restrict__ p, const float* __restrict__ a, int act_p
     for (int i = 0; i < AT; ++i) ar[u][i] = a[arow * AT + i];
     pb[u] = p + b * H2;
     q[u] = 0.f;
+    if (GRAD) {
+#pragma unroll
+      for (int i = 0; i < AT; ++i) g[u][i] = 0.f;
+    }
   }
   for (int j = 0; j < H2P; j += 4) {
     float z[TMID_RPT][4];
@@ -421,15 +426,16 @@ k_tmid_rows4(const float* __restrict__ p, const float* __restrict__ a, int act_p
     for (int u = 0; u < TMID_RPT; ++u)
 #pragma unroll
       for (int c = 0; c < 4; ++c) z[u][c] = (j + c < H2) ? __ldg(pb[u] + j + c) : 0.f;
+    float4 w[AT];
 #pragma unroll
     for (int i = 0; i < AT; ++i) {
-      const float4 w = *reinterpret_cast<const float4*>(was + i * H2P + j);
+      w[i] = *reinterpret_cast<const float4*>(was + i * H2P + j);
 #pragma unroll
       for (int u = 0; u < TMID_RPT; ++u) {
-        z[u][0] = fmaf(ar[u][i], w.x, z[u][0]);
-        z[u][1] = fmaf(ar[u][i], w.y, z[u][1]);
-        z[u][2] = fmaf(ar[u][i], w.z, z[u][2]);
-        z[u][3] = fmaf(ar[u][i], w.w, z[u][3]);
+        z[u][0] = fmaf(ar[u][i], w[i].x, z[u][0]);
+        z[u][1] = fmaf(ar[u][i], w[i].y, z[u][1]);
+        z[u][2] = fmaf(ar[u][i], w[i].z, z[u][2]);
+        z[u][3] = fmaf(ar[u][i], w[i].w, z[u][3]);
       }
     }
     const float4 w3v = *reinterpret_cast<const float4*>(w3s + j);
@@ -439,27 +445,45 @@ k_tmid_rows4(const float* __restrict__ p, const float* __restrict__ a, int act_p
       q[u] = fmaf(w3v.y, fmaxf(z[u][1], 0.f), q[u]);
       q[u] = fmaf(w3v.z, fmaxf(z[u][2], 0.f), q[u]);
       q[u] = fmaf(w3v.w, fmaxf(z[u][3], 0.f), q[u]);
+      if (GRAD) {   // dq/da_i += [z_j > 0] w3_j W2a[i][j]: same order over j as the one-row kernel (bit-identical)
+        const float g0 = (z[u][0] > 0.f) ? w3v.x : 0.f, g1 = (z[u][1] > 0.f) ? w3v.y : 0.f;
+        const float g2 = (z[u][2] > 0.f) ? w3v.z : 0.f, g3 = (z[u][3] > 0.f) ? w3v.w : 0.f;
+#pragma unroll
+        for (int i = 0; i < AT; ++i) {
+          g[u][i] = fmaf(g0, w[i].x, g[u][i]);
+          g[u][i] = fmaf(g1, w[i].y, g[u][i]);
+          g[u][i] = fmaf(g2, w[i].z, g[u][i]);
+          g[u][i] = fmaf(g3, w[i].w, g[u][i]);
+        }
+      }
     }
   }
   const float bias3 = __ldg(b3);
 #pragma unroll
-  for (int u = 0; u < TMID_RPT; ++u)
-    if (row0 + 256 * u < R) q_out[row0 + 256 * u] = q[u] + bias3;
+  for (int u = 0; u < TMID_RPT; ++u) {
+    if (row0 + 256 * u < R) {
+      if (q_out) q_out[row0 + 256 * u] = q[u] + bias3;
+      if (GRAD) {
+#pragma unroll
+        for (int i = 0; i < AT; ++i) dqda_out[(row0 + 256 * u) * AT + i] = g[u][i];
+      }
+    }
+  }
 }
 
-template <int AT>
+template <int AT, bool GRAD>
 static int launch_tmid_rows4(rlc_handle* h, const rlc_critic* c, const float* p, const float* a, int act_per_state,
-                             long long R, int N, float* q_out, cudaStream_t st) {
+                             long long R, int N, float* q_out, float* dqda_out, cudaStream_t st) {
   const ThetaView t = theta_view(RLC_TMID, c->S, c->A, c->H1, c->H2);
   const int H2P = (c->H2 + 3) & ~3;
   const size_t smem = (size_t)(H2P * (1 + AT)) * sizeof(float);
   if (smem > h->smem_optin) return RLC_ERR_UNSUPPORTED;
   const long long blocks = (R + 256 * TMID_RPT - 1) / (256 * TMID_RPT);
   if (blocks > 0x7fffffffLL) return RLC_ERR_INVALID;
-  auto kern = k_tmid_rows4<AT>;
+  auto kern = k_tmid_rows4<AT, GRAD>;
   RLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)blocks, 256, smem, st>>>(p, a, act_per_state, R, N, c->H2, c->theta + t.oW2 + (int64_t)c->H1 * c->H2,
-                                            c->theta + t.ow3, c->theta + t.ob3, q_out);
+                                            c->theta + t.ow3, c->theta + t.ob3, q_out, dqda_out);
   RLC_LAUNCH_CHECK(h);
   return RLC_OK;
 }
@@ -471,16 +495,16 @@ static int launch_tmid_rows(rlc_handle* h, const rlc_critic* c, const float* p, 
   if (R == 0) return RLC_OK;
   if (!GRAD && q_out && N > 0 && R % N == 0 && rlc_tmid_tc_ok(h, c, R, N))   // large stacks: 128-row tiles on tcgen05
     return rlc_tmid_rows_tc(h, c, p, a, act_per_state, (int)(R / N), N, q_out, st);
-  if (!GRAD && q_out && R >= (long long)h->num_sms * 256 * TMID_RPT && c->A <= 8) {   // enough rows to fill the machine
+  if ((GRAD || q_out) && R >= (long long)h->num_sms * 256 * TMID_RPT && c->A <= 8) {   // enough rows to fill the machine
     switch (c->A) {
-      case 1: return launch_tmid_rows4<1>(h, c, p, a, act_per_state, R, N, q_out, st);
-      case 2: return launch_tmid_rows4<2>(h, c, p, a, act_per_state, R, N, q_out, st);
-      case 3: return launch_tmid_rows4<3>(h, c, p, a, act_per_state, R, N, q_out, st);
-      case 4: return launch_tmid_rows4<4>(h, c, p, a, act_per_state, R, N, q_out, st);
-      case 5: return launch_tmid_rows4<5>(h, c, p, a, act_per_state, R, N, q_out, st);
-      case 6: return launch_tmid_rows4<6>(h, c, p, a, act_per_state, R, N, q_out, st);
-      case 7: return launch_tmid_rows4<7>(h, c, p, a, act_per_state, R, N, q_out, st);
-      default: return launch_tmid_rows4<8>(h, c, p, a, act_per_state, R, N, q_out, st);
+      case 1: return launch_tmid_rows4<1, GRAD>(h, c, p, a, act_per_state, R, N, q_out, dqda_out, st);
+      case 2: return launch_tmid_rows4<2, GRAD>(h, c, p, a, act_per_state, R, N, q_out, dqda_out, st);
+      case 3: return launch_tmid_rows4<3, GRAD>(h, c, p, a, act_per_state, R, N, q_out, dqda_out, st);
+      case 4: return launch_tmid_rows4<4, GRAD>(h, c, p, a, act_per_state, R, N, q_out, dqda_out, st);
+      case 5: return launch_tmid_rows4<5, GRAD>(h, c, p, a, act_per_state, R, N, q_out, dqda_out, st);
+      case 6: return launch_tmid_rows4<6, GRAD>(h, c, p, a, act_per_state, R, N, q_out, dqda_out, st);
+      case 7: return launch_tmid_rows4<7, GRAD>(h, c, p, a, act_per_state, R, N, q_out, dqda_out, st);
+      default: return launch_tmid_rows4<8, GRAD>(h, c, p, a, act_per_state, R, N, q_out, dqda_out, st);
     }
   }
   const ThetaView t = theta_view(RLC_TMID, c->S, c->A, c->H1, c->H2);
@@ -752,9 +776,10 @@ extern "C" int rlc_tmid_eval_grad(rlc_handle* h, const rlc_critic* c, const floa
   cudaStream_t st = (cudaStream_t)stream;
   if ((long long)B * N == 0) return RLC_OK;
   void* ws = nullptr;
-  int rc = rlc_workspace(h, (size_t)B * c->H2 * sizeof(float), &ws);
+  const size_t np = ((size_t)B * c->H2 + 3) & ~(size_t)3;
+  int rc = rlc_workspace(h, (np + rlc_tmid_state_scratch_floats(c, B)) * sizeof(float), &ws);
   if (rc) return rc;
-  rc = rlc_tmid_state_term(h, c, s, B, (float*)ws, st);
+  rc = rlc_tmid_state_term(h, c, s, B, (float*)ws, st, (float*)ws + np);   // dense state batches: tensor-core GEMMs
   if (rc) return rc;
   return launch_tmid_rows<true>(h, c, (const float*)ws, a, act_mode == RLC_ACT_PER_STATE,
                                 (long long)B * N, N, q_out, dqda_out, st);

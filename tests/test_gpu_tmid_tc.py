@@ -101,3 +101,29 @@ def test_tmid_tc_large_stack_default_dispatch_and_topk(eng):
         gaps = srt[:6] - srt[1:7]
         if (gaps > 1e-4 * rms[r]).all():
             assert np.array_equal(idx[r], order[r, :6])
+
+
+def test_tmid_eval_grad_large_stack_rows4(eng):
+    """rlc_tmid_eval_grad on a stack that fills the machine takes the 4-rows-per-thread gradient kernel: q bit-identical to
+    the forward rows4 kernel (same FMA sequence), dq/da against the oracle on sampled states, ragged tail included."""
+    rng = np.random.RandomState(31)
+    S, A, H1, H2, B, N = 17, 6, 400, 300, 161, 997
+    cr, p, smin, smax = _critic(eng, rng, S, A, H1, H2)
+    s = (rng.randn(B, S) * 2).astype(np.float32)
+    a = rng.uniform(-1, 1, (B, N, A)).astype(np.float32)
+    assert B * N >= 148 * 1024
+    prev_g = eng.lib.rlc_rows_gemm_force(0)          # state term on the CUDA cores for both calls
+    try:
+        qg, g = cr.eval_grad(s, a)
+    finally:
+        eng.lib.rlc_rows_gemm_force(prev_g)
+    q0 = _eval_forced(eng, cr, s, a, 0)
+    np.testing.assert_array_equal(qg.cpu().numpy(), q0)
+    qd, gd = cr.eval_grad(s, a)                      # default dispatch: the state term of 161 states runs as tensor-core GEMMs
+    assert eng.umma_error() == 0
+    assert rel_err(qd.cpu().numpy(), q0).max() < 2 * TOL_FP32        # two fp32-class results against each other
+    rows = np.array([0, 3, 77, B - 1])
+    assert rel_err(qd.cpu().numpy()[rows], onp.tmid_eval(s[rows], a[rows], p, smin, smax, dtype=np.float64)).max() < TOL_FP32
+    gref = onp.tmid_dq_da(onp.stack_state_major(s[rows], N), a[rows].reshape(-1, A), p, smin, smax)
+    gn = g.cpu().numpy()[rows].reshape(-1, A)
+    assert np.abs(gn - gref).max() < 2e-5 * np.abs(gref).max() + 1e-6
