@@ -8,7 +8,7 @@
 // Tiled SGEMM used by the B-row training path and the T-in dQ/da:
 //   C[M,N] = opA(A)[M,K] * opB(B)[K,N]  (+ bias[N]) ; optional relu on A at load (A := relu(A)),
 //   optional mask multiply C *= (Z > 0).  Row-major with leading dimensions (GemmEpi: rows_gemm_tc.cuh).
-// Launches that are dense contractions (minibatches of >= ~1k rows) go to the tcgen05 kernel of rows_gemm_tc.cu
+// Launches that are dense contractions (from ~128 rows of a 400-300 layer) go to the tcgen05 kernel of rows_gemm_tc.cu
 // (3 x TF32 split, fp32-class results); this CUDA-core kernel keeps the latency-bound small ones.
 // =============================================================================================
 template <bool TA, bool TB>

@@ -481,8 +481,10 @@ bool rlc_gemm_tc_ok(const rlc_handle* h, int M, int N, int K) {
   if (mode == 0 || !h || h->sm_major != 10) return false;
   if (M < 1 || N < 1 || K < 1) return false;
   if (mode == 2) return true;
-  // a 128 x 128 tile needs columns to fill and enough multiply-adds to amortise the pipeline fill
-  return N >= 32 && K >= 8 && (double)M * N * K >= (double)(1 << 24);
+  // Both kernels are latency-bound per CTA at these sizes (a launch of this one costs ~6 us + 0.83 us per 32-deep K step
+  // whatever M is; the CUDA-core tile kernel 23 us at 128..1024 x 300 x 400): the tensor path wins from ~128 rows of a
+  // 400-300 layer on (scripts/time_rows_gemm.py B); below that the small launches stay on the CUDA cores
+  return N >= 32 && K >= 8 && (double)M * N * K >= (double)(1 << 23);
 }
 
 void rlc_gemm_tc_splitk_plan(const rlc_handle* h, int M, int N, int K, int max_slabs, int* nz_out, int* klen_out) {
