@@ -167,7 +167,11 @@ static inline __host__ __device__ TmidTcPlan tmid_tc_plan(int A, int H2) {
 }
 
 // barrier slots
-enum { TB_A_FULL = 0, TB_A_EMPTY = 4, TB_ACC_FULL = 8, TB_ACC_EMPTY = 12, TB_COUNT = 16 };
+// TB_ACC_FULL: one ring of 4 per EPILOGUE GROUP (a unit's barrier belongs to the group that drains it, indexed by the unit's
+// position in that group's own sequence): every waiter sees every phase of the barriers it waits on, in order.  With one
+// barrier per accumulator buffer shared by both groups a group skips the other group's phases, and a parity wait that is a
+// phase ahead returns at once (2 buffers x 2 parts: error flag 214 in the random-shape sweep; tests/test_ring_protocol_model.py).
+enum { TB_A_FULL = 0, TB_A_EMPTY = 4, TB_ACC_FULL = 8, TB_ACC_EMPTY = 16, TB_COUNT = 20 };
 
 template <int AT>
 __global__ void __launch_bounds__(TT_THREADS, 1) k_tmid_rows_tc(const TmidTcParams P) {
@@ -230,10 +234,8 @@ __global__ void __launch_bounds__(TT_THREADS, 1) k_tmid_rows_tc(const TmidTcPara
       tt::mbar_init(bar(TB_A_FULL + i), 4);
       tt::mbar_init(bar(TB_A_EMPTY + i), 1);
     }
-    for (int i = 0; i < 4; ++i) {
-      tt::mbar_init(bar(TB_ACC_FULL + i), 1);
-      tt::mbar_init(bar(TB_ACC_EMPTY + i), 4);
-    }
+    for (int i = 0; i < 8; ++i) tt::mbar_init(bar(TB_ACC_FULL + i), 1);
+    for (int i = 0; i < 4; ++i) tt::mbar_init(bar(TB_ACC_EMPTY + i), 4);
     tt::fence_mbar_init();
   }
   __syncthreads();
@@ -285,8 +287,15 @@ __global__ void __launch_bounds__(TT_THREADS, 1) k_tmid_rows_tc(const TmidTcPara
     if (tt::elect_one()) {
       const int nks = L.nc / 2;
       bool ok = true;
+      // Everything this thread does between two waits sits on the commit -> drain -> release -> issue round trip that bounds
+      // the kernel: ring positions are running counters (integer divisions by the runtime ring sizes here and in the epilogue
+      // cost 80 us of 430: r02k).  Precomputing the descriptor words as well was slower (388 vs 352 us: the extra live
+      // registers of this one thread are paid by all 544).
+      uint32_t buf = 0, use_par = 1u;              // accumulator buffer of the next unit; parity of its PREVIOUS use's release
+      bool first_round = true;                     // no release to wait for during the first pass over the ring
+      uint32_t vi[2] = {0u, 0u};                   // per epilogue group: position in its ring of full barriers
       for (int tl = 0; tl < ntl && ok; ++tl) {
-        const uint32_t slot = (uint32_t)(tl % TT_SLOTS);
+        const uint32_t slot = (uint32_t)(tl & (TT_SLOTS - 1));
         if (!tt::mbar_wait(bar(TB_A_FULL + slot), (uint32_t)(tl / TT_SLOTS) & 1u, P.err, 211)) break;
         tt::fence_proxy_async();      // producers' generic-proxy stores -> tensor core reads (fence on the causality path)
         tt::tc_fence_after();
@@ -294,11 +303,8 @@ __global__ void __launch_bounds__(TT_THREADS, 1) k_tmid_rows_tc(const TmidTcPara
         const uint32_t c0_s = base + L.off_c0 + slot * (uint32_t)CHS;
         const uint32_t b_s = base + L.off_b;
         for (int part = 0; part < nparts; ++part) {
-          const int u = tl * nparts + part;
-          const uint32_t buf = (uint32_t)(u % NB);
-          const int use = u / NB;
-          if (use > 0) {
-            if (!tt::mbar_wait(bar(TB_ACC_EMPTY + buf), (uint32_t)(use - 1) & 1u, P.err, 212)) { ok = false; break; }
+          if (!first_round) {
+            if (!tt::mbar_wait(bar(TB_ACC_EMPTY + buf), use_par, P.err, 212)) { ok = false; break; }
             tt::tc_fence_after();
           }
           const int col0 = part * PW;
@@ -314,7 +320,12 @@ __global__ void __launch_bounds__(TT_THREADS, 1) k_tmid_rows_tc(const TmidTcPara
               bd = tt::desc(b_s + (uint32_t)(2 * ks) * (uint32_t)CHS + (uint32_t)col0 * 16u, (uint32_t)CHS);
             tt::mma_tf32(d, ad, bd, idesc, (uint32_t)(ks != 0));
           }
-          tt::commit(bar(TB_ACC_FULL + buf));
+          {
+            const int g = tl & 1;                          // the group that drains this unit; its own ring of barriers
+            tt::commit(bar(TB_ACC_FULL + 4 * g + (int)vi[g]));
+            if (++vi[g] == (uint32_t)NB) vi[g] = 0u;
+          }
+          if (++buf == (uint32_t)NB) { buf = 0u; first_round = false; use_par ^= 1u; }
         }
         tt::commit(bar(TB_A_EMPTY + slot));
       }
@@ -420,15 +431,16 @@ __global__ void __launch_bounds__(TT_THREADS, 1) k_tmid_rows_tc(const TmidTcPara
     const float bias3 = __ldg(P.b3);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
     bool ok = true;
+    // running positions: accumulator buffer of this group's next unit (the shared ring advances by the OTHER group's
+    // nparts units between two of this group's tiles) and this group's own ring of full barriers with its phase
+    uint32_t buf = (uint32_t)((grp * nparts) % NB), vi = 0u, vpar = 0u;
+    int b = (int)((t_begin + grp) / P.tps);
+    int tin = (int)((t_begin + grp) - (long long)b * P.tps);          // tile index inside the state
     for (int tl = grp; tl < ntl && ok; tl += 2) {
-      const long long tile = t_begin + tl;
-      const int b = (int)(tile / P.tps);
-      const int n = (int)(tile - (long long)b * P.tps) * 128 + qd * 32 + lane;
+      const int n = tin * 128 + qd * 32 + lane;
       float acc = 0.f;
       for (int part = 0; part < nparts; ++part) {
-        const int u = tl * nparts + part;
-        const uint32_t buf = (uint32_t)(u % NB);
-        if (!tt::mbar_wait(bar(TB_ACC_FULL + buf), (uint32_t)(u / NB) & 1u, P.err, 214)) { ok = false; break; }
+        if (!tt::mbar_wait(bar(TB_ACC_FULL + 4 * grp + (int)vi), vpar, P.err, 214)) { ok = false; break; }
         tt::tc_fence_after();
         const int col0 = part * PW;
         const int pw = (H2P - col0 < PW) ? (H2P - col0) : PW;
@@ -459,8 +471,14 @@ __global__ void __launch_bounds__(TT_THREADS, 1) k_tmid_rows_tc(const TmidTcPara
             }
           }
         }
+        if (++buf == (uint32_t)NB) buf = 0u;
+        if (++vi == (uint32_t)NB) { vi = 0u; vpar ^= 1u; }
       }
       if (ok && n < P.N) P.q[(long long)b * P.N + n] = bias3 + acc;
+      buf += (uint32_t)nparts;                       // skip the other group's tile
+      while (buf >= (uint32_t)NB) buf -= (uint32_t)NB;
+      tin += 2;
+      while (tin >= P.tps) { tin -= P.tps; ++b; }
     }
   }
   tt::tc_fence_before();

@@ -230,3 +230,28 @@ def test_rows_gemm_rejects_bad_arguments(eng):
             check(eng.lib.rlc_rows_gemm(eng.h, ta, tb, M, N, K, _ptr(x), lda, _ptr(x), ldb, _ptr(x), ldc, None, None, 0, 0, 1.0,
                                         split, path, _stream()))
     assert eng.launches == n0
+
+
+def test_tc_gemm_random_shapes(eng):
+    """Seeded sweep over ragged shapes, operand orientations, leading-dimension pads / misaligned bases and epilogue
+    options (tile edges in M, N and K, K tails of 1..31, vector and scalar load/store paths)."""
+    rng = np.random.RandomState(77)
+    for it in range(48):
+        M, N, K = int(rng.randint(1, 400)), int(rng.randint(1, 400)), int(rng.randint(1, 300))
+        ta, tb = int(rng.randint(2)), int(rng.randint(2))
+        pad = int(rng.choice([0, 0, 1, 2, 4]))
+        A = rng.randn(*((K, M) if ta else (M, K))).astype(np.float32)
+        Bm = rng.randn(*((N, K) if tb else (K, N))).astype(np.float32)
+        bias = rng.randn(N).astype(np.float32) if rng.randint(2) else None
+        Z = rng.randn(M, N).astype(np.float32) if rng.randint(2) else None
+        relu_a, alpha = bool(rng.randint(2)), float(rng.choice([1.0, -0.5, 3.25]))
+        c = _gemm(eng, A, Bm, ta, tb, bias=bias, Z=Z, relu_a=relu_a, alpha=alpha, pad=pad)
+        ref, scale = _ref(A, Bm, ta, tb, bias=bias, Z=Z, relu_a=relu_a, alpha=alpha)
+        err = (np.abs(c - ref) / scale).max()
+        assert err < TOL_TC, (it, M, N, K, ta, tb, pad, err)
+    for it in range(12):                                 # split-K weight-gradient form, incl. K shorter than one slice
+        K, M, N = int(rng.randint(1, 5000)), int(rng.randint(1, 420)), int(rng.randint(1, 420))
+        X, G = rng.randn(K, M).astype(np.float32), rng.randn(K, N).astype(np.float32)
+        c = _gemm(eng, X, G, 1, 0, split_k=True)
+        ref, scale = _ref(X, G, 1, 0)
+        assert (np.abs(c - ref) / scale).max() < TOL_TC, (it, K, M, N)

@@ -127,3 +127,26 @@ def test_tmid_eval_grad_large_stack_rows4(eng):
     gref = onp.tmid_dq_da(onp.stack_state_major(s[rows], N), a[rows].reshape(-1, A), p, smin, smax)
     gn = g.cpu().numpy()[rows].reshape(-1, A)
     assert np.abs(gn - gref).max() < 2e-5 * np.abs(gref).max() + 1e-6
+
+
+def test_tmid_tc_random_shapes(eng):
+    """Seeded sweep over (S, A <= 8, H1, H2 <= 480, B, N) with shared and per-state actions, tensor path forced: ragged tiles
+    (N not a multiple of 128), single states, hidden widths that are not multiples of 16, every action width."""
+    rng = np.random.RandomState(123)
+    for it in range(30):
+        S, A = int(rng.randint(1, 20)), int(rng.randint(1, 9))
+        H1, H2 = int(rng.randint(8, 200)), int(rng.randint(1, 481))
+        if it < 6:
+            H2 = [345, 400, 480, 161, 256, 257][it]          # accumulator ring of 2 / 3 / 4 buffers, one and two parts
+        B, N = int(rng.randint(1, 40)), int(rng.randint(1, 700))
+        per_state = bool(rng.randint(2))
+        cr, p, smin, smax = _critic(eng, rng, S, A, H1, H2)
+        s = (rng.randn(B, S) * 2).astype(np.float32)
+        a = rng.uniform(-1, 1, (B, N, A) if per_state else (N, A)).astype(np.float32)
+        ref = onp.tmid_eval(s, a, p, smin, smax, dtype=np.float64)
+        try:
+            q = _eval_forced(eng, cr, s, a, 2)
+        except AssertionError as ex:
+            raise AssertionError(f"kernel error flag for {(it, S, A, H1, H2, B, N, per_state)}: {ex}")
+        e = rel_err(q, ref).max()
+        assert e < TOL_FP32, (it, S, A, H1, H2, B, N, per_state, e)
