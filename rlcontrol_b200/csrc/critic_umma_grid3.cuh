@@ -39,9 +39,23 @@
 #ifndef RLC_G3_PDL_DEFAULT
 #define RLC_G3_PDL_DEFAULT 0   // programmatic dependent launch of K1 behind its pre-pass (RLC_G3_PDL=0|1 overrides)
 #endif
-#define G3_E2G 4             // epilogue-2 column groups (x 4 lane quarters = 16 warps)
-__host__ __device__ constexpr int g3_e1w(int mode) { return mode == G3_C8 ? 8 : 4; }   // epilogue-1 warps (C8 builds 3 operands)
-__host__ __device__ constexpr int g3_threads(int mode) { return 32 * (4 + g3_e1w(mode) + 4 * G3_E2G); }
+#ifndef G3_C8_E1W
+#define G3_C8_E1W 8          // epilogue-1 warps of the C8 kernel (8 or 12); its epilogue 2 gets the rest of 24 warps
+#endif
+__host__ __device__ constexpr int g3_e1w(int mode) { return mode == G3_C8 ? G3_C8_E1W : 4; }   // epilogue-1 warps (C8 builds 3 operands)
+// epilogue-2 column groups (x 4 lane quarters = warps)
+#ifndef G3_C8_E2G
+#define G3_C8_E2G ((24 - G3_C8_E1W) / 4)
+#endif
+__host__ __device__ constexpr int g3_e2g(int mode) { return mode == G3_C8 ? G3_C8_E2G : 4; }
+__host__ __device__ constexpr int g3_threads(int mode) { return 32 * (4 + g3_e1w(mode) + 4 * g3_e2g(mode)); }
+// accumulator columns an epilogue-2 thread holds per part
+#ifndef G3_C8_VR
+#define G3_C8_VR (g3_e2g(G3_C8) >= 4 ? 48 : 64)
+#endif
+__host__ __device__ constexpr int g3_vr(int mode) { return mode == G3_C8 ? G3_C8_VR : 48; }
+#define G3_E2G g3_e2g(MODE)
+#define G3_VR g3_vr(MODE)
 #define G3_E1W g3_e1w(MODE)
 #define G3_W2_0 (4 + G3_E1W) // first epilogue-2 warp
 #define G3_THREADS g3_threads(MODE)
@@ -49,7 +63,6 @@ __host__ __device__ constexpr int g3_threads(int mode) { return 32 * (4 + g3_e1w
 #define G3_C8_SB 0           // C8: W_lo and the e5m2 copy of h are used unscaled (e5m2 has fp16's range; W_lo < 2^-2 by construction)
 #define G3_RANGE_LIMIT_C8 500.f   // C8: |h_lo| 2^9 must stay below e4m3's 448: |PS|, |PA| <= 500 -> h < 1024, h_lo <= 0.25
 #define G3_MAX_NP 5          // accumulator column parts
-#define G3_VR (G3_E2G >= 4 ? 48 : 64)   // accumulator columns an epilogue-2 thread holds per part
 #define G3_MAX_NCH 8
 #define G3_PA_PAD 4          // floats of padding per PA row: pitch (KC+4)*4 B keeps the 16-byte LDS conflict-free
 #define G3_MAX_WST 4
@@ -100,7 +113,7 @@ struct Grid3Params {
   long long* prof;            // RLC_UMMA_PROF=1: 32 x int64 per pair (cycle accounting per role)
   int micro;                  // RLC_UMMA_MICRO (diagnostic, output garbage): 1 = MMA issuer free-runs, everyone else idle;
                               // bit flags keeping the full barrier protocol: 2 = loaders copy nothing, 4 = epilogue 1 builds
-                              // nothing, 8 = epilogue 2 loads/sums nothing
+                              // nothing, 8 = epilogue 2 loads/sums nothing, 32 = epilogue 1 loads and stores without the arithmetic
 };
 
 enum {
@@ -328,15 +341,16 @@ __device__ __forceinline__ void relu2_signed_sum(const uint32_t* v, int kpos, fl
 }
 
 // relu_signed_round for at most G3_VR = 64 columns held in registers (all indices static); accumulates 2x the signed sum.
+template <int VR>
 __device__ __forceinline__ void relu_signed_round8(const uint32_t* v, int w, int rel, float& a0, float& a1, float& a2,
                                                    float& a3) {
   if (rel <= 0 || rel >= w || (rel & 7) == 0) {
     const int kpos = rel <= 0 ? 0 : (rel >= w ? 8 : (rel >> 3));
+    if constexpr (VR >= 64) {
+      if ((w >> 3) == 8) { relu2_signed_sum<8>(v, kpos, a0, a1, a2, a3); return; }
+      if ((w >> 3) == 7) { relu2_signed_sum<7>(v, kpos, a0, a1, a2, a3); return; }
+    }
     switch (w >> 3) {
-#if G3_VR >= 64
-      case 8: relu2_signed_sum<8>(v, kpos, a0, a1, a2, a3); break;
-      case 7: relu2_signed_sum<7>(v, kpos, a0, a1, a2, a3); break;
-#endif
       case 6: relu2_signed_sum<6>(v, kpos, a0, a1, a2, a3); break;
       case 5: relu2_signed_sum<5>(v, kpos, a0, a1, a2, a3); break;
       case 4: relu2_signed_sum<4>(v, kpos, a0, a1, a2, a3); break;
@@ -346,7 +360,7 @@ __device__ __forceinline__ void relu_signed_round8(const uint32_t* v, int w, int
     }
   } else {
 #pragma unroll
-    for (int p = 0; p < G3_VR / 8; ++p) {
+    for (int p = 0; p < VR / 8; ++p) {
       if (p * 8 < w) {
 #pragma unroll
         for (int e = 0; e < 8; ++e)
@@ -486,6 +500,75 @@ __global__ void __launch_bounds__(G3_THREADS, 1) k_critic_umma_grid3(const Grid3
     b0 = (int)(ct / P.NT) * 4;
     n0 = (int)(ct % P.NT) * 32;
     return valid;
+  };
+
+  // One warp's share of one activation chunk: h = relu(PS[b] + PA[n]) in fp32 -> the chunk's A operands in its TMEM slot.
+  // TMEM lane quarter == state b0 + q4 of the tile, lane == grid action n0 + lane: a 16-byte PA load covers 32 distinct
+  // rows (4 full wavefronts), a PS load is one broadcast wavefront.  (Measured alternative: lane <-> (state lane/8,
+  // action 8*q4 + lane%8) reads 8 PA rows per warp but a 128-bit load still costs one wavefront per quarter-warp, and the
+  // PS load stops being a single broadcast: 8 wavefronts per pair instead of 5 -- slower, 1.83 vs 1.76 ms.)
+  // k of nk: the chunk's 16-feature units go round-robin over the nk epilogue-1 warps of a lane quarter.
+  // (Measured alternative, round 2: the epilogue-2 warps -- idle ~60 % of a tile, waiting for the accumulator -- building
+  // shares too, either of every chunk or only of the mid-tile chunks with pre-arrivals for the others: every chunk's
+  // hand-shake then waits for the slowest of 24 warps, some of them busy draining: 1.93 - 2.76 ms against 1.45.)
+  const uint32_t b_lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t b_h1f0 = um::mapa(bar(B3_H1_FULL), 0);
+  auto build_chunk = [&](int tl, int c, int k, int nk, uint32_t& st, uint32_t& ppar, uint32_t& slot, uint32_t& spar) -> bool {
+    const int q4 = warp & 3;
+    const int pitch_b = (KC + G3_PA_PAD) * 4;
+    const uint32_t alo = (uint32_t)(KC >> 1);
+    long long t0 = G3T();
+    if (!um::mbar_wait(bar(B3_PA_FULL + (int)st), ppar, P.err, 31)) return false;
+    long long t1 = G3T();
+    const int nunit = P.ch.width[c] >> 4;
+    const float4* pa4 = reinterpret_cast<const float4*>(base_ptr + P.sm_pa + st * P.pa_stage_bytes + lane * pitch_b);
+    const float4* ps4 = reinterpret_cast<const float4*>(base_ptr + P.sm_pa + st * P.pa_stage_bytes + 32 * pitch_b +
+                                                        q4 * (KC * 4));
+    const uint32_t tcol = b_lane_addr + SLOT0 + slot * (uint32_t)KC;
+    if (!um::mbar_wait(bar(B3_H1_EMPTY + (int)slot), spar ^ 1u, P.err, 32)) return false;
+    um::tc_fence_after();
+    long long t2 = G3T();
+    pa_ += t1 - t0; pb_ += t2 - t1;
+    if (tid == 128) G3TR(1, tl, c * 10 + 1);        // slot free + PA here: start building
+    // (Measured alternative for C8: computing the warp's share into registers BEFORE the slot is free and only storing
+    // afterwards -- 48 live registers per thread at the 72-register budget of 896 threads: spills, 1.58 vs 1.48 ms.)
+#pragma unroll 1
+    for (int u = k; u < nunit && !(P.micro & 4); u += nk) {   // 16 activations -> 8 packed hi cells + the lo operand cells
+      uint32_t hi[8], lo[8];
+      if (P.micro & 32) {     // timing decomposition only: the loads and the TMEM stores without the arithmetic
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);   // (& 64: without the PA loads, & 128: without the PS loads, & 256: no stores)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float4 x = make_float4(1.f, 2.f, 3.f, 4.f), y = x;
+          if (!(P.micro & 64)) x = pa4[u * 4 + g];
+          if (!(P.micro & 128)) y = ps4[u * 4 + g];
+          t.x += x.x + y.x; t.y += x.y + y.y; t.z += x.z + y.z; t.w += x.w + y.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { hi[i] = __float_as_uint((i & 1) ? t.x + t.y : t.z + t.w); lo[i] = hi[i]; }
+        if ((P.micro & 256) && hi[0] != 0x12345u) continue;
+      } else
+      ep1_unit<MODE>(pa4, ps4, u, hi, lo);
+      um::tmem_st8(tcol + (uint32_t)(u * 8), hi);
+      if (MODE == G3_C8) {
+        um::tmem_st4(tcol + alo + (uint32_t)(u * 4), lo);
+        um::tmem_st4(tcol + alo + (uint32_t)(KC >> 2) + (uint32_t)(u * 4), lo + 4);
+      } else {
+        um::tmem_st8(tcol + alo + (uint32_t)(u * 8), lo);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) um::mbar_arrive_local(bar(B3_PA_EMPTY + (int)st));   // PA stage consumed
+    long long t3 = G3T();
+    um::tmem_st_wait();
+    um::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) um::mbar_arrive_cluster(b_h1f0 + 8u * slot);
+    if (tid == 128) G3TR(1, tl, c * 10 + 2);        // chunk published
+    pc_ += t3 - t2; pd_ += G3T() - t3;
+    if (++st == past_n) { st = 0; ppar ^= 1u; }
+    if (++slot == nslot) { slot = 0; spar ^= 1u; }
+    return true;
   };
 
   if (warp == 0) {
@@ -681,65 +764,11 @@ __global__ void __launch_bounds__(G3_THREADS, 1) k_critic_umma_grid3(const Grid3
     }
   } else if (warp < G3_W2_0) {
     // ===== epilogue 1: h = relu(PS[b] + PA[n]) in fp32 -> fp16 hi | lo -> TMEM slot (layer 2's A operands) =====
-    // TMEM lane quarter == state b0 + q4 of the tile, lane == grid action n0 + lane: a 16-byte PA load covers 32 distinct
-    // rows (4 full wavefronts), a PS load is one broadcast wavefront.  (Measured alternative: lane <-> (state lane/8,
-    // action 8*q4 + lane%8) reads 8 PA rows per warp but a 128-bit load still costs one wavefront per quarter-warp, and the
-    // PS load stops being a single broadcast: 8 wavefronts per pair instead of 5 -- slower, 1.83 vs 1.76 ms.)
-    const int q4 = warp & 3;
-    const int cg = (warp - 4) >> 2;                // which share of each chunk's 16-feature units this warp builds
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
-    const uint32_t h1f0 = um::mapa(bar(B3_H1_FULL), 0);
-    const int pitch_b = (KC + G3_PA_PAD) * 4;
-    const uint32_t alo = (uint32_t)(KC >> 1);
+    const int cg = (warp - 4) >> 2;                // this warp's index among the builders of its lane quarter
     bool ok = true;
     uint32_t st = 0, ppar = 0, slot = 0, spar = 0;
-    for (int tl = 0; tl < ntiles && ok; ++tl) {
-      for (int c = 0; c < nch; ++c) {
-        long long t0 = G3T();
-        ok = um::mbar_wait(bar(B3_PA_FULL + (int)st), ppar, P.err, 31);
-        if (!ok) break;
-        long long t1 = G3T();
-        const int nunit = P.ch.width[c] >> 4;
-        const int ub = nunit * cg / (G3_E1W / 4), ue = nunit * (cg + 1) / (G3_E1W / 4);
-        const float4* pa4 = reinterpret_cast<const float4*>(base_ptr + P.sm_pa + st * P.pa_stage_bytes + lane * pitch_b);
-        const float4* ps4 = reinterpret_cast<const float4*>(base_ptr + P.sm_pa + st * P.pa_stage_bytes + 32 * pitch_b +
-                                                            q4 * (KC * 4));
-        const uint32_t tcol = lane_addr + SLOT0 + slot * (uint32_t)KC;
-        ok = um::mbar_wait(bar(B3_H1_EMPTY + (int)slot), spar ^ 1u, P.err, 32);
-        if (!ok) break;
-        um::tc_fence_after();
-        long long t2 = G3T();
-        pa_ += t1 - t0;
-        pb_ += t2 - t1;
-        if (tid == 128) G3TR(1, tl, c * 10 + 1);        // slot free + PA here: start building
-        // (Measured alternative for C8: computing the warp's share into registers BEFORE the slot is free and only storing
-        // afterwards -- 48 live registers per thread at the 72-register budget of 896 threads: spills, 1.58 vs 1.48 ms.)
-#pragma unroll 1
-        for (int u = ub; u < ue && !(P.micro & 4); ++u) {   // 16 activations -> 8 packed hi cells + the lo operand cells
-          uint32_t hi[8], lo[8];
-          ep1_unit<MODE>(pa4, ps4, u, hi, lo);
-          um::tmem_st8(tcol + (uint32_t)(u * 8), hi);
-          if (MODE == G3_C8) {
-            um::tmem_st4(tcol + alo + (uint32_t)(u * 4), lo);
-            um::tmem_st4(tcol + alo + (uint32_t)(KC >> 2) + (uint32_t)(u * 4), lo + 4);
-          } else {
-            um::tmem_st8(tcol + alo + (uint32_t)(u * 8), lo);
-          }
-        }
-        __syncwarp();
-        if (lane == 0) um::mbar_arrive_local(bar(B3_PA_EMPTY + (int)st));   // PA stage consumed
-        long long t3 = G3T();
-        um::tmem_st_wait();
-        um::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) um::mbar_arrive_cluster(h1f0 + 8u * slot);
-        if (tid == 128) G3TR(1, tl, c * 10 + 2);        // chunk published
-        pc_ += t3 - t2;
-        pd_ += G3T() - t3;
-        if (++st == past_n) { st = 0; ppar ^= 1u; }
-        if (++slot == nslot) { slot = 0; spar ^= 1u; }
-      }
-    }
+    for (int tl = 0; tl < ntiles && ok; ++tl)
+      for (int c = 0; c < nch && ok; ++c) ok = build_chunk(tl, c, cg, G3_E1W / 4, st, ppar, slot, spar);
     if (prof && rank == 0 && tid == 128) {
       long long* o = P.prof + (size_t)pair * 32 + 8; o[0] = pa_; o[1] = pb_; o[2] = pc_; o[3] = pd_;
     }
@@ -776,11 +805,12 @@ __global__ void __launch_bounds__(G3_THREADS, 1) k_critic_umma_grid3(const Grid3
         const int jb = hb + u0 * 8, w = (u1 - u0) * 8;
         uint32_t v[G3_VR];
         const uint32_t t0c = lane_addr + (uint32_t)jb;
-        switch ((P.micro & 8) ? 0 : (w >> 3)) {                              // static register indices for every width
-#if G3_VR >= 64
-          case 8: um::tmem_ld32p(t0c, v); um::tmem_ld32p(t0c + 32, v + 32); break;
-          case 7: um::tmem_ld32p(t0c, v); um::tmem_ld16p(t0c + 32, v + 32); um::tmem_ld8p(t0c + 48, v + 48); break;
-#endif
+        int nu = (P.micro & 8) ? 0 : (w >> 3);
+        if constexpr (G3_VR >= 64) {
+          if (nu == 8) { um::tmem_ld32p(t0c, v); um::tmem_ld32p(t0c + 32, v + 32); nu = 0; }
+          else if (nu == 7) { um::tmem_ld32p(t0c, v); um::tmem_ld16p(t0c + 32, v + 32); um::tmem_ld8p(t0c + 48, v + 48); nu = 0; }
+        }
+        switch (nu) {                                                        // static register indices for every width
           case 6: um::tmem_ld32p(t0c, v); um::tmem_ld16p(t0c + 32, v + 32); break;
           case 5: um::tmem_ld32p(t0c, v); um::tmem_ld8p(t0c + 32, v + 32); break;
           case 4: um::tmem_ld32p(t0c, v); break;
@@ -795,7 +825,7 @@ __global__ void __launch_bounds__(G3_THREADS, 1) k_critic_umma_grid3(const Grid3
         if (lane == 0) um::mbar_arrive_cluster(l2e0 + 8u * (uint32_t)p);     // part p handed back
         { long long tt = G3T(); pb_ += tt - t1; t1 = tt; }
         if (tid == 32 * G3_W2_0) G3TR(2, tl, p * 10 + 1);    // loaded + released
-        if (w > 0 && !(P.micro & 8)) relu_signed_round8(v, w, npos - jb, a0, a1, a2, a3);
+        if (w > 0 && !(P.micro & 8)) relu_signed_round8<G3_VR>(v, w, npos - jb, a0, a1, a2, a3);
         { long long tt = G3T(); pc_ += tt - t1; }
         if (tid == 32 * G3_W2_0) G3TR(2, tl, p * 10 + 2);    // math done
       }
@@ -920,11 +950,23 @@ struct Grid3Plan {
   int sm_w, sm_pa, sm_ps, sm_qp, sm_bar, w_stage, w_half, pa_stage, ps_stage, total;
 };
 
+// Column granularity of the C8 accumulator parts.  The PTX shape table allows N in steps of 16 at cta_group::2 for
+// kind::f8f6f4 as for kind::f16 (the multiple-of-32 rule is a CuTe static_assert, not the hardware's): 300 -> 304 instead
+// of 320 columns, 5 % less tensor-pipe, accumulator-drain and epilogue-2 work.  RLC_G3_C8_N16=0 restores steps of 32.
+#ifndef RLC_G3_C8_N16_DEFAULT
+#define RLC_G3_C8_N16_DEFAULT 1
+#endif
+static int g3_c8_unit() {
+  static int u = 0;
+  if (!u) { const char* e = getenv("RLC_G3_C8_N16"); u = (e ? e[0] == '1' : RLC_G3_C8_N16_DEFAULT) ? 16 : 32; }
+  return u;
+}
+
 static bool make_geom3(const rlc_critic* c, PackGeom& G, int mode = G3_X3) {
   if (!make_geom(c, G, 1)) return false;
-  if (mode == G3_C8) {          // kind::f8f6f4: K = 32 per MMA, N a multiple of 32 at M = 256
+  if (mode == G3_C8) {          // kind::f8f6f4: K = 32 per MMA
     G.H1P = (c->H1 + 1 + 31) & ~31;
-    G.H2P = (c->H2 + 31) & ~31;
+    G.H2P = (c->H2 + g3_c8_unit() - 1) & ~(g3_c8_unit() - 1);
     if (G.H2P > 480) return false;
   }
   const int sz = (G.H1P / 8) * (G.H2P / 2) * 16;
@@ -941,7 +983,7 @@ static bool make_geom3(const rlc_critic* c, PackGeom& G, int mode = G3_X3) {
 // Accumulator column parts: as few as possible, widths multiples of 16 as even as possible (304 -> 160 + 144).
 static bool make_parts3(int H2P, Grid3Parts& pt, int mode = G3_X3) {
   memset(&pt, 0, sizeof(pt));
-  const int U = mode == G3_C8 ? 32 : 16;            // part widths: multiples of 16 (kind::f16) or 32 (kind::f8f6f4)
+  const int U = mode == G3_C8 ? g3_c8_unit() : 16;  // part widths: multiples of 16 (see g3_c8_unit)
   if (H2P % U) return false;
   const int units = H2P / U;
   int np = (H2P + 191) / 192;                     // fewest parts an epilogue-2 thread can hold (wider MMAs are more efficient)
@@ -950,11 +992,13 @@ static bool make_parts3(int H2P, Grid3Parts& pt, int mode = G3_X3) {
     if (e) { const int v = atoi(e); if (v >= 1 && v <= G3_MAX_NP) np = v; }
   }
   if (np > units) np = units;
+  // more parts when an epilogue-2 thread could not hold its share of the widest one
+  while (np < units && np < G3_MAX_NP && U * ((units + np - 1) / np) > g3_e2g(mode) * g3_vr(mode)) ++np;
   if (np < 1 || np > G3_MAX_NP) return false;
   int b = 0;
   for (int p = 0; p < np; ++p) {
     const int w = U * (units / np + (p < units % np ? 1 : 0));
-    if (w > G3_E2G * G3_VR || w > 256) return false;
+    if (w > g3_e2g(mode) * g3_vr(mode) || w > 256) return false;
     pt.base[p] = b;
     b += w;
   }
@@ -983,6 +1027,7 @@ static bool plan_grid3(const PackGeom& G, size_t smem_limit, Grid3Plan& p, int m
   // much shorter than the time epilogue 1 needs to build the next one
   const int units = G.H1P / CU, n = (G.H1P + kc - 1) / kc;
   if (n > G3_MAX_NCH) return false;
+  // (wide chunks first or last makes no measurable difference: 1.448 vs 1.449 ms)
   for (int i = 0, f = 0; i < n; ++i) {
     const int w = CU * (units / n + (i < units % n ? 1 : 0));
     p.ch.start[i] = f; p.ch.width[i] = w; f += w;
@@ -992,7 +1037,7 @@ static bool plan_grid3(const PackGeom& G, size_t smem_limit, Grid3Plan& p, int m
   p.w_half = (kc / 8) * lbo;
   p.pa_stage = 32 * (kc + G3_PA_PAD) * 4 + 4 * kc * 4;     // PA tile + the chunk's slice of the tile's 4 PS rows
   p.ps_stage = 0;
-  const int tail = 128 * 4 * 2 * (G3_E2G - 1) + B3_COUNT * 8 + 16 + 1024;
+  const int tail = 128 * 4 * 2 * (g3_e2g(mode) - 1) + B3_COUNT * 8 + 16 + 1024;
   p.whi_bytes = (G.H1P / 8) * lbo;
   // Preferred: W_hi resident, only W_lo streams (half the bulk-copy writes into shared memory, whose bandwidth the
   // tensor core's operand reads need); otherwise both stream.  Stage counts: as deep as fits, weights first.
@@ -1022,7 +1067,7 @@ static bool plan_grid3(const PackGeom& G, size_t smem_limit, Grid3Plan& p, int m
   p.sm_pa = p.sm_w + p.w_stages * p.w_stage;
   p.sm_ps = 0;
   p.sm_qp = (p.sm_pa + p.pa_stages * p.pa_stage + 127) & ~127;
-  p.sm_bar = p.sm_qp + 2 * 128 * 4 * (G3_E2G - 1);
+  p.sm_bar = p.sm_qp + 2 * 128 * 4 * (g3_e2g(mode) - 1);
   p.total = p.sm_bar + B3_COUNT * 8 + 16 + 1024;
   return (size_t)p.total <= smem_limit;
 }

@@ -38,7 +38,12 @@ def main():
         ts = [ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]
         ms = float(np.median(ts))
         fl = flops * ss.shape[0] / B
-        print(f"{name:22s} {ms:8.3f} ms  (min {min(ts):.3f})  {fl/ms/1e9:8.1f} TFLOP/s  {ss.shape[0]*N/ms/1e6:8.2f} G Q-evals/s  err={eng.umma_error()}",
+        chk = ""
+        if os.environ.get("CHECK"):        # parity of this build/knob setting against the fp32-class split mode (same inputs)
+            qr = cr.eval(ss, act if act.dim() == 2 else act[: ss.shape[0]], "fp16x3" if prec != "fp16x3" else "fp32")
+            d = (torch.as_tensor(q) - torch.as_tensor(qr)).abs().max().item()
+            chk = f"  max|dq|/max|q| vs {'fp16x3' if prec != 'fp16x3' else 'fp32'} = {d / torch.as_tensor(qr).abs().max().item():.2e}"
+        print(f"{name:22s} {ms:8.3f} ms  (min {min(ts):.3f})  {fl/ms/1e9:8.1f} TFLOP/s  {ss.shape[0]*N/ms/1e6:8.2f} G Q-evals/s  err={eng.umma_error()}{chk}",
               flush=True)
 
 if __name__ == "__main__":
