@@ -37,7 +37,7 @@
 #define G3_X3 0
 #define G3_C8 1
 #ifndef RLC_G3_PDL_DEFAULT
-#define RLC_G3_PDL_DEFAULT 1   // programmatic dependent launch of K1 behind its pre-pass (RLC_G3_PDL=0|1 overrides)
+#define RLC_G3_PDL_DEFAULT 0   // programmatic dependent launch of K1 behind its pre-pass (RLC_G3_PDL=0|1 overrides)
 #endif
 #ifndef G3_C8_E1W
 #define G3_C8_E1W 8          // epilogue-1 warps of the C8 kernel (8 or 12); its epilogue 2 gets the rest of 24 warps
